@@ -1,0 +1,10 @@
+"""dagsfm_b200 -- B200-native hot path of AIBluefisher/DAGSfM.
+
+Python here is a thin host-side mirror of the reference's matcher / verifier /
+bundle-adjuster interfaces over the C ABI (include/dagsfm_b200.h); all numeric
+work runs in the hand-written sm_100a CUDA library.
+"""
+from ._lib import B2Error, MatchOptions, lib  # noqa: F401
+from .matching import SiftMatchGPU, SiftMatchingOptions, match_sift_features_gpu  # noqa: F401
+
+__version__ = "0.1"
