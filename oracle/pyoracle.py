@@ -95,3 +95,176 @@ def match_pairs_mt(descs: list, pairs, max_ratio=0.8, max_distance=0.7, cross_ch
                                  np.float32(max_distance), int(cross_check), n_threads,
                                  counts.ctypes.data, C.byref(cs))
     return t, counts, cs.value
+
+
+# ======================================================================== two-view
+class OrcCamera(C.Structure):
+    _fields_ = [("model", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
+                ("has_prior_focal", C.c_int32), ("params", C.c_double * 12)]
+
+
+class OrcTvOptions(C.Structure):
+    """TwoViewGeometry::Options + RANSACOptions with the matcher's defaults
+    (src/feature/sift.h:142-158, src/estimators/two_view_geometry.h:80-117)."""
+    _fields_ = [("min_num_inliers", C.c_int32), ("detect_watermark", C.c_int32),
+                ("min_E_F_inlier_ratio", C.c_double), ("max_H_inlier_ratio", C.c_double),
+                ("watermark_min_inlier_ratio", C.c_double), ("watermark_border_size", C.c_double),
+                ("max_error", C.c_double), ("min_inlier_ratio", C.c_double), ("confidence", C.c_double),
+                ("min_num_trials", C.c_int64), ("max_num_trials", C.c_int64)]
+
+
+class OrcTvResult(C.Structure):
+    _fields_ = [("config", C.c_int32), ("n_inliers", C.c_int32),
+                ("E_inl", C.c_int32), ("F_inl", C.c_int32), ("H_inl", C.c_int32),
+                ("E_trials", C.c_int32), ("F_trials", C.c_int32), ("H_trials", C.c_int32),
+                ("E", C.c_double * 9), ("F", C.c_double * 9), ("H", C.c_double * 9)]
+
+
+def tv_default_options() -> OrcTvOptions:
+    return OrcTvOptions(15, 1, 0.95, 0.8, 0.7, 0.1, 4.0, 0.25, 0.999, 30, 10000)
+
+
+def make_camera(model=2, width=1000, height=1000, params=(1200.0, 500.0, 500.0, 0.0), prior=True) -> OrcCamera:
+    c = OrcCamera()
+    c.model, c.width, c.height, c.has_prior_focal = model, width, height, int(prior)
+    for i, v in enumerate(params):
+        c.params[i] = v
+    return c
+
+
+_tv_ready = False
+
+
+def _tv():
+    global _tv_ready
+    L = lib()
+    if not _tv_ready:
+        vp, d, i32, i64 = C.c_void_p, C.c_double, C.c_int, C.c_int64
+        L.orc_f7.argtypes = [vp, vp, vp]
+        L.orc_eight_point.argtypes = [i32, vp, vp, i32, vp]
+        L.orc_e5.argtypes = [i32, vp, vp, vp, vp, vp]
+        L.orc_h_dlt.argtypes = [i32, vp, vp, vp]
+        L.orc_e5_system.argtypes = [vp, vp]; L.orc_e5_system.restype = None
+        L.orc_e5_det_coeffs.argtypes = [vp, vp]; L.orc_e5_det_coeffs.restype = None
+        L.orc_residuals.argtypes = [i32, i32, vp, vp, vp, vp]; L.orc_residuals.restype = None
+        L.orc_compute_num_trials.argtypes = [C.c_uint64, C.c_uint64, d, i32]
+        L.orc_compute_num_trials.restype = C.c_uint64
+        L.orc_poly_roots.argtypes = [i32, vp, vp, vp]
+        L.orc_svd.argtypes = [vp, i32, i32, vp, vp]; L.orc_svd.restype = None
+        L.orc_sample_stream.argtypes = [C.c_uint, i32, i32, i32, vp]; L.orc_sample_stream.restype = None
+        L.orc_image_to_world.argtypes = [C.POINTER(OrcCamera), i32, vp, vp]; L.orc_image_to_world.restype = None
+        L.orc_ransac.argtypes = [i32, i32, i32, vp, vp, d, d, d, i64, i64, C.c_uint, vp, vp, vp, vp, vp]
+        L.orc_two_view.argtypes = [C.POINTER(OrcCamera), vp, C.POINTER(OrcCamera), vp, vp, i32,
+                                   C.POINTER(OrcTvOptions), C.c_uint, C.POINTER(OrcTvResult), vp]
+        L.orc_two_view.restype = None
+        L.orc_two_view_pairs_mt.argtypes = [vp, vp, vp, C.c_long, vp, vp, C.POINTER(OrcTvOptions), vp, i32, vp]
+        L.orc_two_view_pairs_mt.restype = d
+        _tv_ready = True
+    return L
+
+
+def _p(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+EST_E5, EST_F7, EST_H4, EST_T2 = 0, 1, 2, 3
+
+
+def f7(p1, p2):
+    p1, p2 = _p(p1), _p(p2)
+    out = np.zeros((3, 3, 3))
+    n = _tv().orc_f7(p1.ctypes.data, p2.ctypes.data, out.ctypes.data)
+    return out[:n]
+
+
+def eight_point(p1, p2, essential=False):
+    p1, p2 = _p(p1), _p(p2)
+    out = np.zeros((3, 3))
+    _tv().orc_eight_point(len(p1), p1.ctypes.data, p2.ctypes.data, int(essential), out.ctypes.data)
+    return out
+
+
+def e5(p1, p2, with_system=False):
+    p1, p2 = _p(p1), _p(p2)
+    out = np.zeros((10, 3, 3)); A = np.zeros((10, 20)); c = np.zeros(11)
+    n = _tv().orc_e5(len(p1), p1.ctypes.data, p2.ctypes.data, out.ctypes.data, A.ctypes.data, c.ctypes.data)
+    return (out[:n], A, c) if with_system else out[:n]
+
+
+def h_dlt(p1, p2):
+    p1, p2 = _p(p1), _p(p2)
+    out = np.zeros((3, 3))
+    _tv().orc_h_dlt(len(p1), p1.ctypes.data, p2.ctypes.data, out.ctypes.data)
+    return out
+
+
+def e5_system(basis_4x9):
+    b = _p(basis_4x9); A = np.zeros((10, 20))
+    _tv().orc_e5_system(b.ctypes.data, A.ctypes.data)
+    return A
+
+
+def e5_det_coeffs(B_colmajor39):
+    b = _p(B_colmajor39); c = np.zeros(11)
+    _tv().orc_e5_det_coeffs(b.ctypes.data, c.ctypes.data)
+    return c
+
+
+def residuals(est_type, p1, p2, M):
+    p1, p2, M = _p(p1), _p(p2), _p(M)
+    r = np.zeros(len(p1))
+    _tv().orc_residuals(est_type, len(p1), p1.ctypes.data, p2.ctypes.data, M.ctypes.data, r.ctypes.data)
+    return r
+
+
+def compute_num_trials(num_inliers, num_samples, confidence, kmin):
+    return int(_tv().orc_compute_num_trials(num_inliers, num_samples, confidence, kmin))
+
+
+def poly_roots(coeffs):
+    c = _p(coeffs); re = np.zeros(len(c)); im = np.zeros(len(c))
+    n = _tv().orc_poly_roots(len(c), c.ctypes.data, re.ctypes.data, im.ctypes.data)
+    return (re[:n], im[:n]) if n >= 0 else None
+
+
+def svd(A):
+    A = _p(A); m, n = A.shape
+    s = np.zeros(n); V = np.zeros((n, n))
+    _tv().orc_svd(A.ctypes.data, m, n, s.ctypes.data, V.ctypes.data)
+    return s, V
+
+
+def sample_stream(seed, total, k, n_trials):
+    out = np.zeros((n_trials, k), dtype=np.int32)
+    _tv().orc_sample_stream(seed, total, k, n_trials, out.ctypes.data)
+    return out
+
+
+def image_to_world(cam: OrcCamera, xy):
+    xy = _p(xy); out = np.zeros_like(xy)
+    _tv().orc_image_to_world(C.byref(cam), len(xy), xy.ctypes.data, out.ctypes.data)
+    return out
+
+
+def ransac(est_type, X, Y, max_error, min_inlier_ratio=0.1, confidence=0.99, min_num_trials=0,
+           max_num_trials=2**62, seed=0, use_lo=True):
+    X, Y = _p(X), _p(Y)
+    n = len(X)
+    model = np.zeros((3, 3)); ni = C.c_int32(0); rs = C.c_double(0); nt = C.c_int64(0)
+    mask = np.zeros(max(n, 1), dtype=np.uint8)
+    ok = _tv().orc_ransac(est_type, int(use_lo), n, X.ctypes.data, Y.ctypes.data, max_error, min_inlier_ratio,
+                          confidence, min_num_trials, max_num_trials, seed, model.ctypes.data,
+                          C.byref(ni), C.byref(rs), C.byref(nt), mask.ctypes.data)
+    return {"success": bool(ok), "model": model, "num_inliers": ni.value, "residual_sum": rs.value,
+            "num_trials": nt.value, "mask": mask[:n].astype(bool)}
+
+
+def two_view(cam1, pts1, cam2, pts2, matches, opt=None, seed=0):
+    opt = opt or tv_default_options()
+    pts1, pts2 = _p(pts1), _p(pts2)
+    m = np.ascontiguousarray(matches, dtype=np.uint32).reshape(-1, 2)
+    res = OrcTvResult()
+    inl = np.zeros((max(len(m), 1), 2), dtype=np.uint32)
+    _tv().orc_two_view(C.byref(cam1), pts1.ctypes.data, C.byref(cam2), pts2.ctypes.data, m.ctypes.data, len(m),
+                       C.byref(opt), seed, C.byref(res), inl.ctypes.data)
+    return res, inl[: res.n_inliers].copy()

@@ -1,0 +1,1233 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY.  Never imported, linked or executed by the
+// product path (dagsfm_b200/); only tests/, __graft_entry__.smoke() and bench.py's
+// cpu_baseline / --impl reference legs may use it.
+//
+// CPU restatement of the reference's two-view geometric verification:
+//   src/optim/ransac.h:135-167            RANSAC ctor clamp, ComputeNumTrials
+//   src/optim/loransac.h:92-233           LORANSAC::Estimate
+//   src/optim/random_sampler.cc:43-62     RandomSampler (persistent partial Fisher-Yates)
+//   src/util/random.h:89-129, random.cc   PRNG = std::mt19937, uniform_int_distribution
+//   src/optim/support_measurement.cc:36-60 InlierSupportMeasurer
+//   src/estimators/utils.cc:38-131        CenterAndNormalizeImagePoints, Sampson error
+//   src/estimators/fundamental_matrix.cc  7-point (:47-142), 8-point (:150-192)
+//   src/estimators/essential_matrix.cc    5-point (:46-150), 8-point (:158-205)
+//   src/estimators/homography_matrix.cc   DLT (:44-92), transfer residual (:94-131)
+//   src/estimators/translation_transform.h:53-116
+//   src/base/polynomial.cc:208-279        FindPolynomialRootsCompanionMatrix
+//   src/base/camera_models.h:547-590,714-757 ImageToWorld / IterativeUndistortion
+//   src/estimators/two_view_geometry.cc:113-126,292-555 Estimate / EstimateCalibrated /
+//                                         EstimateUncalibrated / DetectWatermark
+//
+// The reference's linear algebra is Eigen (JacobiSVD, PartialPivLU, EigenSolver), a
+// third-party dependency that is NOT vendored under /root/reference and not installed
+// here (README.md:40 asks for the distro libeigen3-dev; no version pin).  Restated:
+// one-sided Jacobi SVD, Gaussian elimination with partial pivoting, Francis double-shift
+// QR on the companion matrix.  The generated 5-point polynomial files
+// (essential_matrix_poly.h / essential_matrix_coeffs.h) are restated by expanding the
+// same constraints with polynomial arithmetic at run time.
+// Known deviations from Eigen: (i) basis of a >1-dimensional null space (changes only
+// the sign of 5-point E matrices); (ii) polynomial roots are emitted in ascending order.
+// Pins: tests/test_oracle_twoview.py replays fundamental_matrix_test.cc:39-105,
+// essential_matrix_test.cc:47-124, homography_matrix_test.cc:42-70,
+// ransac_test.cc:65-84 and checks the 5-point system against values computed from the
+// reference's generated headers (tests/golden/e5_poly_golden.npz).
+// Parity UNPINNED for TwoViewGeometry::Estimate* as a whole: the reference has no test
+// of it (two_view_geometry_test.cc covers only the ctor and Invert()).
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <numeric>
+#include <random>
+#include <thread>
+#include <vector>
+
+namespace tv {
+
+struct Vec2 { double x, y; };
+struct Mat3 { double m[9]; double& operator()(int r, int c) { return m[3 * r + c]; } double operator()(int r, int c) const { return m[3 * r + c]; } };
+
+static Mat3 mul(const Mat3& a, const Mat3& b) {
+  Mat3 r;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double s = 0;
+      for (int k = 0; k < 3; ++k) s += a(i, k) * b(k, j);
+      r(i, j) = s;
+    }
+  return r;
+}
+static Mat3 transpose(const Mat3& a) {
+  Mat3 r;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) r(i, j) = a(j, i);
+  return r;
+}
+static Mat3 inverse(const Mat3& a) {
+  Mat3 r;
+  const double c00 = a(1, 1) * a(2, 2) - a(1, 2) * a(2, 1);
+  const double c01 = a(1, 2) * a(2, 0) - a(1, 0) * a(2, 2);
+  const double c02 = a(1, 0) * a(2, 1) - a(1, 1) * a(2, 0);
+  const double det = a(0, 0) * c00 + a(0, 1) * c01 + a(0, 2) * c02;
+  const double id = 1.0 / det;
+  r(0, 0) = c00 * id;
+  r(0, 1) = (a(0, 2) * a(2, 1) - a(0, 1) * a(2, 2)) * id;
+  r(0, 2) = (a(0, 1) * a(1, 2) - a(0, 2) * a(1, 1)) * id;
+  r(1, 0) = c01 * id;
+  r(1, 1) = (a(0, 0) * a(2, 2) - a(0, 2) * a(2, 0)) * id;
+  r(1, 2) = (a(0, 2) * a(1, 0) - a(0, 0) * a(1, 2)) * id;
+  r(2, 0) = c02 * id;
+  r(2, 1) = (a(0, 1) * a(2, 0) - a(0, 0) * a(2, 1)) * id;
+  r(2, 2) = (a(0, 0) * a(1, 1) - a(0, 1) * a(1, 0)) * id;
+  return r;
+}
+
+// ------------------------------------------------------------------ SVD
+// One-sided (Hestenes) Jacobi SVD of the m x n row-major matrix A (n <= 9 here).
+// On return: sigma[n] descending, V (n x n, row-major, columns = right singular
+// vectors in the same order), and, if U != nullptr, the m x n matrix of left
+// singular vectors scaled by sigma (i.e. A*V, columns orthogonal).
+static void jacobi_svd(const double* A, int m, int n, double* sigma, double* V, double* AV) {
+  std::vector<double> G(A, A + (size_t)m * n);
+  std::vector<double> W((size_t)n * n, 0.0);
+  for (int i = 0; i < n; ++i) W[i * n + i] = 1.0;
+  const double eps = std::numeric_limits<double>::epsilon();
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    bool rotated = false;
+    for (int p = 0; p < n - 1; ++p) {
+      for (int q = p + 1; q < n; ++q) {
+        double alpha = 0, beta = 0, gamma = 0;
+        for (int i = 0; i < m; ++i) {
+          const double gp = G[(size_t)i * n + p], gq = G[(size_t)i * n + q];
+          alpha += gp * gp;
+          beta += gq * gq;
+          gamma += gp * gq;
+        }
+        if (gamma == 0.0 || std::abs(gamma) <= eps * std::sqrt(alpha * beta)) continue;
+        rotated = true;
+        const double zeta = (beta - alpha) / (2.0 * gamma);
+        const double t = (zeta >= 0 ? 1.0 : -1.0) / (std::abs(zeta) + std::sqrt(1.0 + zeta * zeta));
+        const double c = 1.0 / std::sqrt(1.0 + t * t);
+        const double s = c * t;
+        for (int i = 0; i < m; ++i) {
+          const double gp = G[(size_t)i * n + p], gq = G[(size_t)i * n + q];
+          G[(size_t)i * n + p] = c * gp - s * gq;
+          G[(size_t)i * n + q] = s * gp + c * gq;
+        }
+        for (int i = 0; i < n; ++i) {
+          const double wp = W[i * n + p], wq = W[i * n + q];
+          W[i * n + p] = c * wp - s * wq;
+          W[i * n + q] = s * wp + c * wq;
+        }
+      }
+    }
+    if (!rotated) break;
+  }
+  std::vector<double> nrm(n);
+  for (int j = 0; j < n; ++j) {
+    double s = 0;
+    for (int i = 0; i < m; ++i) s += G[(size_t)i * n + j] * G[(size_t)i * n + j];
+    nrm[j] = std::sqrt(s);
+  }
+  std::vector<int> order(n);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return nrm[a] > nrm[b]; });
+  for (int j = 0; j < n; ++j) {
+    const int o = order[j];
+    sigma[j] = nrm[o];
+    for (int i = 0; i < n; ++i) V[i * n + j] = W[i * n + o];
+    if (AV)
+      for (int i = 0; i < m; ++i) AV[(size_t)i * n + j] = G[(size_t)i * n + o];
+  }
+}
+
+// U * diag(s) * V^T of a 3x3 matrix with its singular values replaced by s_new(sigma).
+template <typename F>
+static Mat3 svd3_rebuild(const Mat3& A, F&& new_sigma) {
+  double sig[3], V[9], AV[9];
+  jacobi_svd(A.m, 3, 3, sig, V, AV);
+  double sn[3] = {sig[0], sig[1], sig[2]};
+  new_sigma(sn);
+  Mat3 R;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double s = 0;
+      for (int k = 0; k < 3; ++k) {
+        if (sn[k] == 0.0 || sig[k] == 0.0) continue;
+        s += (AV[i * 3 + k] / sig[k]) * sn[k] * V[j * 3 + k];  // U(i,k) s_k V(j,k)
+      }
+      R(i, j) = s;
+    }
+  return R;
+}
+
+// --------------------------------------------------- polynomial roots (companion)
+// Eigenvalues of a real upper-Hessenberg matrix by the Francis double-shift QR
+// iteration (the classic "hqr").  a is n x n row-major, destroyed.  Returns false if
+// an eigenvalue needs more than 30*... iterations (Eigen reports NoConvergence).
+static bool hqr(std::vector<double>& a, int n, double* wr, double* wi) {
+  auto A = [&](int i, int j) -> double& { return a[(size_t)i * n + j]; };
+  int nn = n - 1;
+  double t = 0.0, p = 0, q = 0, r = 0, s = 0, w, x, y, z;
+  double anorm = 0.0;
+  for (int i = 0; i < n; ++i)
+    for (int j = std::max(i - 1, 0); j < n; ++j) anorm += std::abs(A(i, j));
+  while (nn >= 0) {
+    int its = 0, l;
+    do {
+      for (l = nn; l >= 1; --l) {
+        s = std::abs(A(l - 1, l - 1)) + std::abs(A(l, l));
+        if (s == 0.0) s = anorm;
+        if (std::abs(A(l, l - 1)) + s == s) {
+          A(l, l - 1) = 0.0;
+          break;
+        }
+      }
+      x = A(nn, nn);
+      if (l == nn) {  // one root
+        wr[nn] = x + t;
+        wi[nn--] = 0.0;
+      } else {
+        y = A(nn - 1, nn - 1);
+        w = A(nn, nn - 1) * A(nn - 1, nn);
+        if (l == nn - 1) {  // two roots
+          p = 0.5 * (y - x);
+          q = p * p + w;
+          z = std::sqrt(std::abs(q));
+          x += t;
+          if (q >= 0.0) {
+            z = p + (p >= 0 ? std::abs(z) : -std::abs(z));
+            wr[nn - 1] = wr[nn] = x + z;
+            if (z != 0.0) wr[nn] = x - w / z;
+            wi[nn - 1] = wi[nn] = 0.0;
+          } else {
+            wr[nn - 1] = wr[nn] = x + p;
+            wi[nn - 1] = -(wi[nn] = z);
+          }
+          nn -= 2;
+        } else {  // no root yet: QR step
+          if (its == 60) return false;
+          if (its == 10 || its == 20) {  // exceptional shift
+            t += x;
+            for (int i = 0; i <= nn; ++i) A(i, i) -= x;
+            s = std::abs(A(nn, nn - 1)) + std::abs(A(nn - 1, nn - 2));
+            y = x = 0.75 * s;
+            w = -0.4375 * s * s;
+          }
+          ++its;
+          int m;
+          for (m = nn - 2; m >= l; --m) {
+            z = A(m, m);
+            r = x - z;
+            s = y - z;
+            p = (r * s - w) / A(m + 1, m) + A(m, m + 1);
+            q = A(m + 1, m + 1) - z - r - s;
+            r = A(m + 2, m + 1);
+            s = std::abs(p) + std::abs(q) + std::abs(r);
+            p /= s;
+            q /= s;
+            r /= s;
+            if (m == l) break;
+            const double u = std::abs(A(m, m - 1)) * (std::abs(q) + std::abs(r));
+            const double v = std::abs(p) * (std::abs(A(m - 1, m - 1)) + std::abs(z) + std::abs(A(m + 1, m + 1)));
+            if (u + v == v) break;
+          }
+          for (int i = m + 2; i <= nn; ++i) {
+            A(i, i - 2) = 0.0;
+            if (i != m + 2) A(i, i - 3) = 0.0;
+          }
+          for (int k = m; k <= nn - 1; ++k) {
+            if (k != m) {
+              p = A(k, k - 1);
+              q = A(k + 1, k - 1);
+              r = 0.0;
+              if (k != nn - 1) r = A(k + 2, k - 1);
+              if ((x = std::abs(p) + std::abs(q) + std::abs(r)) != 0.0) {
+                p /= x;
+                q /= x;
+                r /= x;
+              }
+            }
+            const double sg = std::sqrt(p * p + q * q + r * r);
+            s = (p >= 0 ? sg : -sg);
+            if (s != 0.0) {
+              if (k == m) {
+                if (l != m) A(k, k - 1) = -A(k, k - 1);
+              } else {
+                A(k, k - 1) = -s * x;
+              }
+              p += s;
+              x = p / s;
+              y = q / s;
+              z = r / s;
+              q /= p;
+              r /= p;
+              for (int j = k; j <= nn; ++j) {
+                p = A(k, j) + q * A(k + 1, j);
+                if (k != nn - 1) {
+                  p += r * A(k + 2, j);
+                  A(k + 2, j) -= p * z;
+                }
+                A(k + 1, j) -= p * y;
+                A(k, j) -= p * x;
+              }
+              const int mmin = nn < k + 3 ? nn : k + 3;
+              for (int i = l; i <= mmin; ++i) {
+                p = x * A(i, k) + y * A(i, k + 1);
+                if (k != nn - 1) {
+                  p += z * A(i, k + 2);
+                  A(i, k + 2) -= p * r;
+                }
+                A(i, k + 1) -= p * q;
+                A(i, k) -= p;
+              }
+            }
+          }
+        }
+      }
+    } while (l < nn - 1);
+  }
+  return true;
+}
+
+// polynomial.cc:208-279.  coeffs: highest power first.  Roots returned sorted by
+// (real, imag) ascending (deviation: Eigen returns its deflation order).
+static bool FindPolynomialRootsCompanionMatrix(const std::vector<double>& coeffs_all,
+                                               std::vector<double>* real, std::vector<double>* imag) {
+  size_t lead = 0;
+  while (lead < coeffs_all.size() && coeffs_all[lead] == 0) ++lead;
+  std::vector<double> coeffs(coeffs_all.begin() + lead, coeffs_all.end());
+  const int degree = (int)coeffs.size() - 1;
+  real->clear();
+  imag->clear();
+  if (degree <= 0) return false;
+  if (degree == 1) {  // FindLinearPolynomialRoots
+    real->push_back(-coeffs[1] / coeffs[0]);
+    imag->push_back(0);
+    return true;
+  }
+  if (degree == 2) {  // FindQuadraticPolynomialRoots (polynomial.cc:81-138)
+    const double a = coeffs[0], b = coeffs[1], c = coeffs[2];
+    if (b == 0 && c == 0) {
+      real->push_back(0);
+      imag->push_back(0);
+      return true;
+    }
+    const double d = b * b - 4 * a * c;
+    if (d >= 0) {
+      const double sqrt_d = std::sqrt(d);
+      if (b >= 0) {
+        real->push_back((-b - sqrt_d) / (2 * a));
+        real->push_back((2 * c) / (-b - sqrt_d));
+      } else {
+        real->push_back((2 * c) / (-b + sqrt_d));
+        real->push_back((-b + sqrt_d) / (2 * a));
+      }
+      imag->assign(2, 0.0);
+    } else {
+      real->assign(2, -b / (2 * a));
+      imag->push_back(std::sqrt(-d) / (2 * a));
+      imag->push_back(-(*imag)[0]);
+    }
+    return true;
+  }
+  size_t trail = 0;
+  while (trail < coeffs.size() && coeffs[coeffs.size() - 1 - trail] == 0) ++trail;
+  coeffs.resize(coeffs.size() - trail);
+  if (coeffs.size() == 1) {
+    real->push_back(0);
+    imag->push_back(0);
+    return true;
+  }
+  const int n = (int)coeffs.size() - 1;
+  std::vector<double> C((size_t)n * n, 0.0);
+  for (int i = 1; i < n; ++i) C[(size_t)i * n + i - 1] = 1;
+  for (int j = 0; j < n; ++j) C[j] = -coeffs[j + 1] / coeffs[0];
+  std::vector<double> wr(n), wi(n);
+  if (!hqr(C, n, wr.data(), wi.data())) return false;
+  std::vector<int> order(n);
+  std::iota(order.begin(), order.end(), 0);
+  std::sort(order.begin(), order.end(), [&](int a, int b) {
+    return wr[a] < wr[b] || (wr[a] == wr[b] && wi[a] < wi[b]);
+  });
+  for (int k : order) {
+    real->push_back(wr[k]);
+    imag->push_back(wi[k]);
+  }
+  if (trail > 0) {  // "if there are trailing zeros, we must add zero as a solution"
+    real->push_back(0);
+    imag->push_back(0);
+  }
+  return true;
+}
+
+// ---------------------------------------------------------------- estimators/utils
+static void CenterAndNormalizeImagePoints(const std::vector<Vec2>& points, std::vector<Vec2>* normed, Mat3* matrix) {
+  double cx = 0, cy = 0;
+  for (const auto& p : points) { cx += p.x; cy += p.y; }
+  cx /= points.size();
+  cy /= points.size();
+  double rms = 0;
+  for (const auto& p : points) rms += (p.x - cx) * (p.x - cx) + (p.y - cy) * (p.y - cy);
+  rms = std::sqrt(rms / points.size());
+  const double nf = std::sqrt(2.0) / rms;
+  Mat3& M = *matrix;
+  M(0, 0) = nf; M(0, 1) = 0; M(0, 2) = -nf * cx;
+  M(1, 0) = 0; M(1, 1) = nf; M(1, 2) = -nf * cy;
+  M(2, 0) = 0; M(2, 1) = 0; M(2, 2) = 1;
+  normed->resize(points.size());
+  for (size_t i = 0; i < points.size(); ++i) {
+    const double p0 = points[i].x, p1 = points[i].y;
+    const double n0 = M(0, 0) * p0 + M(0, 1) * p1 + M(0, 2);
+    const double n1 = M(1, 0) * p0 + M(1, 1) * p1 + M(1, 2);
+    const double n2 = M(2, 0) * p0 + M(2, 1) * p1 + M(2, 2);
+    const double inv = 1.0 / n2;
+    (*normed)[i].x = n0 * inv;
+    (*normed)[i].y = n1 * inv;
+  }
+}
+
+static void ComputeSquaredSampsonError(const std::vector<Vec2>& p1, const std::vector<Vec2>& p2, const Mat3& E, std::vector<double>* res) {
+  res->resize(p1.size());
+  const double E_00 = E(0, 0), E_01 = E(0, 1), E_02 = E(0, 2), E_10 = E(1, 0), E_11 = E(1, 1), E_12 = E(1, 2), E_20 = E(2, 0), E_21 = E(2, 1), E_22 = E(2, 2);
+  for (size_t i = 0; i < p1.size(); ++i) {
+    const double x1_0 = p1[i].x, x1_1 = p1[i].y, x2_0 = p2[i].x, x2_1 = p2[i].y;
+    const double Ex1_0 = E_00 * x1_0 + E_01 * x1_1 + E_02;
+    const double Ex1_1 = E_10 * x1_0 + E_11 * x1_1 + E_12;
+    const double Ex1_2 = E_20 * x1_0 + E_21 * x1_1 + E_22;
+    const double Etx2_0 = E_00 * x2_0 + E_10 * x2_1 + E_20;
+    const double Etx2_1 = E_01 * x2_0 + E_11 * x2_1 + E_21;
+    const double x2tEx1 = x2_0 * Ex1_0 + x2_1 * Ex1_1 + Ex1_2;
+    (*res)[i] = x2tEx1 * x2tEx1 / (Ex1_0 * Ex1_0 + Ex1_1 * Ex1_1 + Etx2_0 * Etx2_0 + Etx2_1 * Etx2_1);
+  }
+}
+
+static void HomographyResiduals(const std::vector<Vec2>& p1, const std::vector<Vec2>& p2, const Mat3& H, std::vector<double>* res) {
+  res->resize(p1.size());
+  for (size_t i = 0; i < p1.size(); ++i) {
+    const double s_0 = p1[i].x, s_1 = p1[i].y, d_0 = p2[i].x, d_1 = p2[i].y;
+    const double pd_0 = H(0, 0) * s_0 + H(0, 1) * s_1 + H(0, 2);
+    const double pd_1 = H(1, 0) * s_0 + H(1, 1) * s_1 + H(1, 2);
+    const double pd_2 = H(2, 0) * s_0 + H(2, 1) * s_1 + H(2, 2);
+    const double inv = 1.0 / pd_2;
+    const double dd_0 = d_0 - pd_0 * inv;
+    const double dd_1 = d_1 - pd_1 * inv;
+    (*res)[i] = dd_0 * dd_0 + dd_1 * dd_1;
+  }
+}
+
+// ------------------------------------------------------------------ F 7-point
+static std::vector<Mat3> F7(const std::vector<Vec2>& p1, const std::vector<Vec2>& p2) {
+  double A[7 * 9];
+  for (int i = 0; i < 7; ++i) {
+    const double x0 = p1[i].x, y0 = p1[i].y, x1 = p2[i].x, y1 = p2[i].y;
+    double* a = A + 9 * i;
+    a[0] = x1 * x0; a[1] = x1 * y0; a[2] = x1; a[3] = y1 * x0; a[4] = y1 * y0; a[5] = y1; a[6] = x0; a[7] = y0; a[8] = 1;
+  }
+  double sig[9], V[81];
+  jacobi_svd(A, 7, 9, sig, V, nullptr);
+  double f1[9], f2[9];
+  for (int i = 0; i < 9; ++i) { f1[i] = V[i * 9 + 7]; f2[i] = V[i * 9 + 8]; }
+  for (int i = 0; i < 9; ++i) f1[i] -= f2[i];
+  const double t0 = f1[4] * f1[8] - f1[5] * f1[7];
+  const double t1 = f1[3] * f1[8] - f1[5] * f1[6];
+  const double t2 = f1[3] * f1[7] - f1[4] * f1[6];
+  const double t3 = f2[4] * f2[8] - f2[5] * f2[7];
+  const double t4 = f2[3] * f2[8] - f2[5] * f2[6];
+  const double t5 = f2[3] * f2[7] - f2[4] * f2[6];
+  std::vector<double> c(4);
+  c[0] = f1[0] * t0 - f1[1] * t1 + f1[2] * t2;
+  c[1] = f2[0] * t0 - f2[1] * t1 + f2[2] * t2 - f2[3] * (f1[1] * f1[8] - f1[2] * f1[7]) +
+         f2[4] * (f1[0] * f1[8] - f1[2] * f1[6]) - f2[5] * (f1[0] * f1[7] - f1[1] * f1[6]) +
+         f2[6] * (f1[1] * f1[5] - f1[2] * f1[4]) - f2[7] * (f1[0] * f1[5] - f1[2] * f1[3]) +
+         f2[8] * (f1[0] * f1[4] - f1[1] * f1[3]);
+  c[2] = f1[0] * t3 - f1[1] * t4 + f1[2] * t5 - f1[3] * (f2[1] * f2[8] - f2[2] * f2[7]) +
+         f1[4] * (f2[0] * f2[8] - f2[2] * f2[6]) - f1[5] * (f2[0] * f2[7] - f2[1] * f2[6]) +
+         f1[6] * (f2[1] * f2[5] - f2[2] * f2[4]) - f1[7] * (f2[0] * f2[5] - f2[2] * f2[3]) +
+         f1[8] * (f2[0] * f2[4] - f2[1] * f2[3]);
+  c[3] = f2[0] * t3 - f2[1] * t4 + f2[2] * t5;
+  std::vector<double> rr, ri;
+  std::vector<Mat3> models;
+  if (!FindPolynomialRootsCompanionMatrix(c, &rr, &ri)) return models;
+  for (size_t i = 0; i < rr.size(); ++i) {
+    if (std::abs(ri[i]) > 1e-10) continue;
+    const double lambda = rr[i];
+    double F[9];
+    for (int k = 0; k < 9; ++k) F[k] = lambda * f1[k] + 1 * f2[k];
+    if (std::abs(F[8]) < 1e-10) continue;  // F(2,2) of the col-major reshape == element 8
+    Mat3 M;
+    for (int k = 0; k < 9; ++k) M.m[k] = F[k] / F[8];  // reshape + transpose == row-major
+    models.push_back(M);
+  }
+  return models;
+}
+
+static void build_epipolar_cmatrix(const std::vector<Vec2>& n1, const std::vector<Vec2>& n2, std::vector<double>* cm) {
+  cm->resize(n1.size() * 9);
+  for (size_t i = 0; i < n1.size(); ++i) {
+    double* r = cm->data() + 9 * i;
+    r[0] = n1[i].x * n2[i].x; r[1] = n1[i].y * n2[i].x; r[2] = 1.0 * n2[i].x;
+    r[3] = n1[i].x * n2[i].y; r[4] = n1[i].y * n2[i].y; r[5] = 1.0 * n2[i].y;
+    r[6] = n1[i].x; r[7] = n1[i].y; r[8] = 1.0;
+  }
+}
+
+// fundamental_matrix.cc:150-192 (essential == false) / essential_matrix.cc:158-205 (true)
+static std::vector<Mat3> EightPoint(const std::vector<Vec2>& p1, const std::vector<Vec2>& p2, bool essential) {
+  std::vector<Vec2> n1, n2;
+  Mat3 T1, T2;
+  CenterAndNormalizeImagePoints(p1, &n1, &T1);
+  CenterAndNormalizeImagePoints(p2, &n2, &T2);
+  std::vector<double> cm;
+  build_epipolar_cmatrix(n1, n2, &cm);
+  double sig[9], V[81];
+  jacobi_svd(cm.data(), (int)p1.size(), 9, sig, V, nullptr);
+  Mat3 Em;  // ematrix_t.transpose(): row-major reshape of the null vector
+  for (int k = 0; k < 9; ++k) Em.m[k] = V[k * 9 + 8];
+  Mat3 F = svd3_rebuild(Em, [&](double* s) {
+    if (essential) { s[0] = (s[0] + s[1]) / 2.0; s[1] = s[0]; }
+    s[2] = 0.0;
+  });
+  return {mul(mul(transpose(T2), F), T1)};
+}
+
+// ------------------------------------------------------------------ H DLT
+static std::vector<Mat3> HomographyDLT(const std::vector<Vec2>& p1, const std::vector<Vec2>& p2) {
+  const size_t N = p1.size();
+  std::vector<Vec2> n1, n2;
+  Mat3 T1, T2;
+  CenterAndNormalizeImagePoints(p1, &n1, &T1);
+  CenterAndNormalizeImagePoints(p2, &n2, &T2);
+  std::vector<double> A(2 * N * 9, 0.0);
+  for (size_t i = 0, j = N; i < N; ++i, ++j) {
+    const double s_0 = n1[i].x, s_1 = n1[i].y, d_0 = n2[i].x, d_1 = n2[i].y;
+    double* a = A.data() + 9 * i;
+    a[0] = -s_0; a[1] = -s_1; a[2] = -1; a[6] = s_0 * d_0; a[7] = s_1 * d_0; a[8] = d_0;
+    double* b = A.data() + 9 * j;
+    b[3] = -s_0; b[4] = -s_1; b[5] = -1; b[6] = s_0 * d_1; b[7] = s_1 * d_1; b[8] = d_1;
+  }
+  double sig[9], V[81];
+  jacobi_svd(A.data(), (int)(2 * N), 9, sig, V, nullptr);
+  Mat3 Ht;  // H_t.transpose() == row-major reshape
+  for (int k = 0; k < 9; ++k) Ht.m[k] = V[k * 9 + 8];
+  return {mul(mul(inverse(T2), Ht), T1)};
+}
+
+// ------------------------------------------------------------------ E 5-point
+// Polynomials in (x,y,z) of total degree <= 3, dense 4x4x4 coefficient cube.
+struct Poly {
+  double c[4][4][4];
+  Poly() { memset(c, 0, sizeof c); }
+};
+static Poly padd(const Poly& a, const Poly& b, double sb = 1.0) {
+  Poly r;
+  for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) for (int k = 0; k < 4; ++k) r.c[i][j][k] = a.c[i][j][k] + sb * b.c[i][j][k];
+  return r;
+}
+static Poly pmul(const Poly& a, const Poly& b) {
+  Poly r;
+  for (int i = 0; i < 4; ++i) for (int j = 0; j < 4 - i; ++j) for (int k = 0; k < 4 - i - j; ++k) {
+    const double av = a.c[i][j][k];
+    if (av == 0) continue;
+    for (int l = 0; l < 4 - i; ++l) for (int m = 0; m < 4 - j; ++m) for (int n = 0; n < 4 - k; ++n) {
+      if (i + l + j + m + k + n > 3) continue;
+      r.c[i + l][j + m][k + n] += av * b.c[l][m][n];
+    }
+  }
+  return r;
+}
+static Poly pscale(const Poly& a, double s) {
+  Poly r;
+  for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) for (int k = 0; k < 4; ++k) r.c[i][j][k] = s * a.c[i][j][k];
+  return r;
+}
+// Column order of the 10x20 system (Nister / Stewenius, as in essential_matrix_poly.h):
+// x^3 y^3 x^2y xy^2 x^2z x^2 y^2z y^2 xyz xy | xz^2 xz x yz^2 yz y z^3 z^2 z 1
+static const int kMono[20][3] = {{3,0,0},{0,3,0},{2,1,0},{1,2,0},{2,0,1},{2,0,0},{0,2,1},{0,2,0},{1,1,1},{1,1,0},
+                                 {1,0,2},{1,0,1},{1,0,0},{0,1,2},{0,1,1},{0,1,0},{0,0,3},{0,0,2},{0,0,1},{0,0,0}};
+
+// Eb: the 4 null-space basis vectors (X,Y,Z,W), each a row-major 3x3.  A: 10 x 20 row-major.
+static void E5BuildSystem(const double Eb[4][9], double* A) {
+  Poly E[3][3];
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) {
+    E[r][c].c[1][0][0] = Eb[0][3 * r + c];
+    E[r][c].c[0][1][0] = Eb[1][3 * r + c];
+    E[r][c].c[0][0][1] = Eb[2][3 * r + c];
+    E[r][c].c[0][0][0] = Eb[3][3 * r + c];
+  }
+  std::vector<Poly> eq;
+  // det(E) = 0
+  {
+    Poly d = pmul(E[0][0], padd(pmul(E[1][1], E[2][2]), pmul(E[1][2], E[2][1]), -1.0));
+    d = padd(d, pmul(E[0][1], padd(pmul(E[1][0], E[2][2]), pmul(E[1][2], E[2][0]), -1.0)), -1.0);
+    d = padd(d, pmul(E[0][2], padd(pmul(E[1][0], E[2][1]), pmul(E[1][1], E[2][0]), -1.0)));
+    eq.push_back(d);
+  }
+  // E E^T E - 0.5 trace(E E^T) E = 0
+  Poly EEt[3][3];
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) {
+    Poly s;
+    for (int k = 0; k < 3; ++k) s = padd(s, pmul(E[r][k], E[c][k]));
+    EEt[r][c] = s;
+  }
+  Poly tr = padd(padd(EEt[0][0], EEt[1][1]), EEt[2][2]);
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) {
+    Poly s;
+    for (int k = 0; k < 3; ++k) s = padd(s, pmul(EEt[r][k], E[k][c]));
+    s = padd(s, pmul(pscale(tr, 0.5), E[r][c]), -1.0);
+    eq.push_back(s);
+  }
+  for (int r = 0; r < 10; ++r)
+    for (int m = 0; m < 20; ++m) A[r * 20 + m] = eq[r].c[kMono[m][0]][kMono[m][1]][kMono[m][2]];
+}
+
+// A1^{-1} A2 with partial pivoting (Eigen partialPivLu().solve()).  A: 10x20 row-major in/out.
+static bool E5Eliminate(double* A, double AA[10][10]) {
+  double M[10][20];
+  memcpy(M, A, sizeof M);
+  for (int col = 0; col < 10; ++col) {
+    int piv = col;
+    for (int r = col + 1; r < 10; ++r)
+      if (std::abs(M[r][col]) > std::abs(M[piv][col])) piv = r;
+    if (M[piv][col] == 0.0) return false;
+    if (piv != col)
+      for (int c = 0; c < 20; ++c) std::swap(M[piv][c], M[col][c]);
+    for (int r = col + 1; r < 10; ++r) {
+      const double f = M[r][col] / M[col][col];
+      if (f == 0.0) continue;
+      for (int c = col; c < 20; ++c) M[r][c] -= f * M[col][c];
+    }
+  }
+  for (int c = 0; c < 10; ++c) {
+    for (int r = 9; r >= 0; --r) {
+      double s = M[r][10 + c];
+      for (int k = r + 1; k < 10; ++k) s -= M[r][k] * AA[k][c];
+      AA[r][c] = s / M[r][r];
+    }
+  }
+  return true;
+}
+
+// poly helpers, highest degree first
+static std::vector<double> pm(const std::vector<double>& a, const std::vector<double>& b) {
+  std::vector<double> r(a.size() + b.size() - 1, 0.0);
+  for (size_t i = 0; i < a.size(); ++i)
+    for (size_t j = 0; j < b.size(); ++j) r[i + j] += a[i] * b[j];
+  return r;
+}
+static std::vector<double> psub(const std::vector<double>& a, const std::vector<double>& b) {
+  const size_t n = std::max(a.size(), b.size());
+  std::vector<double> r(n, 0.0);
+  for (size_t i = 0; i < a.size(); ++i) r[n - a.size() + i] += a[i];
+  for (size_t i = 0; i < b.size(); ++i) r[n - b.size() + i] -= b[i];
+  return r;
+}
+
+// Expansion of det(Bz) into the degree-10 polynomial (essential_matrix_coeffs.h), where
+// Bz(j,0) = cubic B[0..3][j], Bz(j,1) = cubic B[4..7][j], Bz(j,2) = quartic B[8..12][j].
+static std::vector<double> E5DetPoly(const double B[13][3]) {
+  std::vector<double> b0[3], b1[3], b2[3];
+  for (int j = 0; j < 3; ++j) {
+    b0[j] = {B[0][j], B[1][j], B[2][j], B[3][j]};
+    b1[j] = {B[4][j], B[5][j], B[6][j], B[7][j]};
+    b2[j] = {B[8][j], B[9][j], B[10][j], B[11][j], B[12][j]};
+  }
+  auto minor01 = [&](int r, int s) { return psub(pm(b0[r], b1[s]), pm(b0[s], b1[r])); };
+  std::vector<double> det = pm(minor01(1, 2), b2[0]);
+  det = psub(det, pm(minor01(0, 2), b2[1]));
+  std::vector<double> t = pm(minor01(0, 1), b2[2]);
+  for (size_t i = 0; i < det.size(); ++i) det[i] += t[i];
+  return det;
+}
+
+// essential_matrix.cc:46-150.  n >= 5 points.  Also returns the intermediate system for tests.
+static std::vector<Mat3> E5(const std::vector<Vec2>& p1, const std::vector<Vec2>& p2, double* A_out = nullptr, double* coeffs_out = nullptr) {
+  const int n = (int)p1.size();
+  std::vector<double> Q((size_t)n * 9);
+  for (int i = 0; i < n; ++i) {
+    const double x1_0 = p1[i].x, x1_1 = p1[i].y, x2_0 = p2[i].x, x2_1 = p2[i].y;
+    double* q = Q.data() + 9 * i;
+    q[0] = x1_0 * x2_0; q[1] = x1_1 * x2_0; q[2] = x2_0; q[3] = x1_0 * x2_1; q[4] = x1_1 * x2_1; q[5] = x2_1; q[6] = x1_0; q[7] = x1_1; q[8] = 1;
+  }
+  double sig[9], V[81];
+  jacobi_svd(Q.data(), n, 9, sig, V, nullptr);
+  double Eb[4][9];
+  for (int k = 0; k < 4; ++k)
+    for (int i = 0; i < 9; ++i) Eb[k][i] = V[i * 9 + 5 + k];
+  double A[200];
+  E5BuildSystem(Eb, A);
+  if (A_out) memcpy(A_out, A, sizeof A);
+  double AA[10][10];
+  std::vector<Mat3> models;
+  if (!E5Eliminate(A, AA)) return models;
+  // B(0..3,i): cubic (coefficient of x), B(4..7,i): cubic (y), B(8..12,i): quartic (1)
+  double B[13][3];
+  for (int i = 0; i < 3; ++i) {
+    B[0][i] = 0; B[4][i] = 0; B[8][i] = 0;
+    for (int k = 0; k < 3; ++k) B[1 + k][i] = AA[i * 2 + 4][k];
+    for (int k = 0; k < 3; ++k) B[5 + k][i] = AA[i * 2 + 4][3 + k];
+    for (int k = 0; k < 4; ++k) B[9 + k][i] = AA[i * 2 + 4][6 + k];
+    for (int k = 0; k < 3; ++k) B[0 + k][i] -= AA[i * 2 + 5][k];
+    for (int k = 0; k < 3; ++k) B[4 + k][i] -= AA[i * 2 + 5][3 + k];
+    for (int k = 0; k < 4; ++k) B[8 + k][i] -= AA[i * 2 + 5][6 + k];
+  }
+  std::vector<double> det = E5DetPoly(B);
+  if (coeffs_out) memcpy(coeffs_out, det.data(), 11 * sizeof(double));
+  std::vector<double> rr, ri;
+  if (!FindPolynomialRootsCompanionMatrix(det, &rr, &ri)) return models;
+  for (size_t i = 0; i < ri.size(); ++i) {
+    if (std::abs(ri[i]) > 1e-10) continue;
+    const double z1 = rr[i], z2 = z1 * z1, z3 = z2 * z1, z4 = z3 * z1;
+    Mat3 Bz;
+    for (int j = 0; j < 3; ++j) {
+      Bz(j, 0) = B[0][j] * z3 + B[1][j] * z2 + B[2][j] * z1 + B[3][j];
+      Bz(j, 1) = B[4][j] * z3 + B[5][j] * z2 + B[6][j] * z1 + B[7][j];
+      Bz(j, 2) = B[8][j] * z4 + B[9][j] * z3 + B[10][j] * z2 + B[11][j] * z1 + B[12][j];
+    }
+    double s3[3], V3[9];
+    jacobi_svd(Bz.m, 3, 3, s3, V3, nullptr);
+    const double X0 = V3[0 * 3 + 2], X1 = V3[1 * 3 + 2], X2 = V3[2 * 3 + 2];
+    if (std::abs(X2) < 1e-10) continue;
+    double ev[9], nrm = 0;
+    for (int k = 0; k < 9; ++k) {
+      ev[k] = Eb[0][k] * (X0 / X2) + Eb[1][k] * (X1 / X2) + Eb[2][k] * z1 + Eb[3][k];
+      nrm += ev[k] * ev[k];
+    }
+    nrm = std::sqrt(nrm);
+    Mat3 M;
+    for (int k = 0; k < 9; ++k) M.m[k] = ev[k] / nrm;
+    models.push_back(M);
+  }
+  return models;
+}
+
+// translation_transform.h:53-116 (kDim = 2): model = (tx, ty) stored in a Mat3's first 2 entries
+static std::vector<Mat3> Translation2(const std::vector<Vec2>& p1, const std::vector<Vec2>& p2) {
+  double sx = 0, sy = 0, dx = 0, dy = 0;
+  for (size_t i = 0; i < p1.size(); ++i) { sx += p1[i].x; sy += p1[i].y; dx += p2[i].x; dy += p2[i].y; }
+  Mat3 M;
+  memset(M.m, 0, sizeof M.m);
+  M.m[0] = (dx - sx) / p1.size();
+  M.m[1] = (dy - sy) / p1.size();
+  return {M};
+}
+static void TranslationResiduals(const std::vector<Vec2>& p1, const std::vector<Vec2>& p2, const Mat3& M, std::vector<double>* res) {
+  res->resize(p1.size());
+  for (size_t i = 0; i < p1.size(); ++i) {
+    const double ex = p2[i].x - (p1[i].x + M.m[0]), ey = p2[i].y - (p1[i].y + M.m[1]);
+    (*res)[i] = ex * ex + ey * ey;
+  }
+}
+
+// ------------------------------------------------------------------ RANSAC
+enum EstType { EST_E5 = 0, EST_F7 = 1, EST_H4 = 2, EST_T2 = 3 };
+static int MinSamples(int t) { return t == EST_E5 ? 5 : t == EST_F7 ? 7 : t == EST_H4 ? 4 : 1; }
+static int LocalMinSamples(int t) { return t == EST_E5 ? 5 : t == EST_F7 ? 8 : t == EST_H4 ? 4 : 1; }
+static std::vector<Mat3> Estimate(int t, const std::vector<Vec2>& a, const std::vector<Vec2>& b) {
+  switch (t) {
+    case EST_E5: return E5(a, b);
+    case EST_F7: return F7(a, b);
+    case EST_H4: return HomographyDLT(a, b);
+    default: return Translation2(a, b);
+  }
+}
+static std::vector<Mat3> LocalEstimate(int t, const std::vector<Vec2>& a, const std::vector<Vec2>& b) {
+  switch (t) {
+    case EST_E5: return E5(a, b);
+    case EST_F7: return EightPoint(a, b, false);
+    case EST_H4: return HomographyDLT(a, b);
+    default: return Translation2(a, b);
+  }
+}
+static void Residuals(int t, const std::vector<Vec2>& a, const std::vector<Vec2>& b, const Mat3& M, std::vector<double>* r) {
+  if (t == EST_H4) HomographyResiduals(a, b, M, r);
+  else if (t == EST_T2) TranslationResiduals(a, b, M, r);
+  else ComputeSquaredSampsonError(a, b, M, r);
+}
+
+struct RansacOptions {
+  double max_error = 0, min_inlier_ratio = 0.1, confidence = 0.99;
+  size_t min_num_trials = 0, max_num_trials = std::numeric_limits<size_t>::max();
+};
+struct Support { size_t num_inliers = 0; double residual_sum = std::numeric_limits<double>::max(); };
+struct Report {
+  bool success = false;
+  size_t num_trials = 0;
+  Support support;
+  std::vector<char> inlier_mask;
+  Mat3 model;
+  Report() { memset(model.m, 0, sizeof model.m); }
+};
+
+static size_t ComputeNumTrials(size_t num_inliers, size_t num_samples, double confidence, int kmin) {
+  const double inlier_ratio = num_inliers / static_cast<double>(num_samples);
+  const double nom = 1 - confidence;
+  if (nom <= 0) return std::numeric_limits<size_t>::max();
+  const double denom = 1 - std::pow(inlier_ratio, kmin);
+  if (denom <= 0) return 1;
+  return static_cast<size_t>(std::ceil(std::log(nom) / std::log(denom)));
+}
+static Support Evaluate(const std::vector<double>& residuals, double max_residual) {
+  Support s;
+  s.num_inliers = 0;
+  s.residual_sum = 0;
+  for (const double r : residuals)
+    if (r <= max_residual) { s.num_inliers += 1; s.residual_sum += r; }
+  return s;
+}
+static bool Compare(const Support& a, const Support& b) {
+  if (a.num_inliers > b.num_inliers) return true;
+  return a.num_inliers == b.num_inliers && a.residual_sum < b.residual_sum;
+}
+
+// util/random.h Shuffle + random_sampler.cc on an explicit PRNG.
+struct Sampler {
+  std::vector<size_t> idx;
+  size_t k;
+  explicit Sampler(size_t k_) : k(k_) {}
+  void Initialize(size_t total) { idx.resize(total); std::iota(idx.begin(), idx.end(), 0); }
+  void Sample(std::mt19937& prng, std::vector<size_t>* out) {
+    const uint32_t last = static_cast<uint32_t>(idx.size() - 1);
+    for (uint32_t i = 0; i < (uint32_t)k; ++i) {
+      std::uniform_int_distribution<uint32_t> distribution(i, last);
+      const auto j = distribution(prng);
+      std::swap(idx[i], idx[j]);
+    }
+    out->assign(idx.begin(), idx.begin() + k);
+  }
+};
+
+// loransac.h:92-233 (use_lo == true) and ransac.h:169-268 (use_lo == false).
+static Report RunRansac(int type, bool use_lo, RansacOptions opt, const std::vector<Vec2>& X, const std::vector<Vec2>& Y, std::mt19937& prng) {
+  const int kmin = MinSamples(type);
+  {  // RANSAC ctor, ransac.h:135-147
+    const size_t kNumSamples = 100000;
+    const size_t dyn = ComputeNumTrials(static_cast<size_t>(opt.min_inlier_ratio * kNumSamples), kNumSamples, opt.confidence, kmin);
+    opt.max_num_trials = std::min<size_t>(opt.max_num_trials, dyn);
+  }
+  const size_t num_samples = X.size();
+  Report report;
+  if (num_samples < (size_t)kmin) return report;
+  Support best_support;
+  Mat3 best_model;
+  memset(best_model.m, 0, sizeof best_model.m);
+  bool abort = false;
+  const double max_residual = opt.max_error * opt.max_error;
+  std::vector<double> residuals(num_samples);
+  std::vector<Vec2> X_inlier, Y_inlier, X_rand(kmin), Y_rand(kmin);
+  Sampler sampler(kmin);
+  sampler.Initialize(num_samples);
+  std::vector<size_t> sidx;
+  const size_t max_num_trials = opt.max_num_trials;
+  size_t dyn_max_num_trials = max_num_trials;
+  for (report.num_trials = 0; report.num_trials < max_num_trials; ++report.num_trials) {
+    if (abort) { report.num_trials += 1; break; }
+    sampler.Sample(prng, &sidx);
+    for (int i = 0; i < kmin; ++i) { X_rand[i] = X[sidx[i]]; Y_rand[i] = Y[sidx[i]]; }
+    const std::vector<Mat3> sample_models = Estimate(type, X_rand, Y_rand);
+    for (const auto& sample_model : sample_models) {
+      Residuals(type, X, Y, sample_model, &residuals);
+      const Support support = Evaluate(residuals, max_residual);
+      if (Compare(support, best_support)) {
+        best_support = support;
+        best_model = sample_model;
+        if (use_lo && support.num_inliers > (size_t)kmin && support.num_inliers >= (size_t)LocalMinSamples(type)) {
+          X_inlier.clear();
+          Y_inlier.clear();
+          for (size_t i = 0; i < residuals.size(); ++i)
+            if (residuals[i] <= max_residual) { X_inlier.push_back(X[i]); Y_inlier.push_back(Y[i]); }
+          const std::vector<Mat3> local_models = LocalEstimate(type, X_inlier, Y_inlier);
+          for (const auto& local_model : local_models) {
+            Residuals(type, X, Y, local_model, &residuals);
+            const Support local_support = Evaluate(residuals, max_residual);
+            if (Compare(local_support, best_support)) {
+              best_support = local_support;
+              best_model = local_model;
+            }
+          }
+        }
+        dyn_max_num_trials = ComputeNumTrials(best_support.num_inliers, num_samples, opt.confidence, kmin);
+      }
+      if (report.num_trials >= dyn_max_num_trials && report.num_trials >= opt.min_num_trials) {
+        abort = true;
+        break;
+      }
+    }
+  }
+  report.support = best_support;
+  report.model = best_model;
+  if (report.support.num_inliers < (size_t)kmin) return report;
+  report.success = true;
+  Residuals(type, X, Y, report.model, &residuals);
+  report.inlier_mask.resize(num_samples);
+  for (size_t i = 0; i < residuals.size(); ++i) report.inlier_mask[i] = residuals[i] <= max_residual;
+  return report;
+}
+
+// ------------------------------------------------------------------ camera
+// model ids as in camera_models.h: 0 SIMPLE_PINHOLE (f,cx,cy), 1 PINHOLE (fx,fy,cx,cy),
+// 2 SIMPLE_RADIAL (f,cx,cy,k).
+struct Camera { int model; int width, height; double params[12]; int has_prior_focal; };
+
+static void SimpleRadialDistortion(double k, double u, double v, double* du, double* dv) {
+  const double u2 = u * u, v2 = v * v, r2 = u2 + v2, radial = k * r2;
+  *du = u * radial;
+  *dv = v * radial;
+}
+static void IterativeUndistortionSR(double k, double* u, double* v) {
+  const double x0_0 = *u, x0_1 = *v;
+  double x_0 = *u, x_1 = *v;
+  for (size_t i = 0; i < 100; ++i) {
+    const double step0 = std::max(std::numeric_limits<double>::epsilon(), std::abs(1e-6 * x_0));
+    const double step1 = std::max(std::numeric_limits<double>::epsilon(), std::abs(1e-6 * x_1));
+    double dx0, dx1, b00, b01, f00, f01, b10, b11, f10, f11;
+    SimpleRadialDistortion(k, x_0, x_1, &dx0, &dx1);
+    SimpleRadialDistortion(k, x_0 - step0, x_1, &b00, &b01);
+    SimpleRadialDistortion(k, x_0 + step0, x_1, &f00, &f01);
+    SimpleRadialDistortion(k, x_0, x_1 - step1, &b10, &b11);
+    SimpleRadialDistortion(k, x_0, x_1 + step1, &f10, &f11);
+    const double J00 = 1 + (f00 - b00) / (2 * step0);
+    const double J01 = (f10 - b10) / (2 * step1);
+    const double J10 = (f01 - b01) / (2 * step0);
+    const double J11 = 1 + (f11 - b11) / (2 * step1);
+    // Eigen 2x2 inverse: adjugate times 1/det
+    const double invdet = 1.0 / (J00 * J11 - J01 * J10);
+    const double r0 = x_0 + dx0 - x0_0, r1 = x_1 + dx1 - x0_1;
+    const double s0 = (J11 * invdet) * r0 + (-J01 * invdet) * r1;
+    const double s1 = (-J10 * invdet) * r0 + (J00 * invdet) * r1;
+    x_0 -= s0;
+    x_1 -= s1;
+    if (s0 * s0 + s1 * s1 < 1e-10) break;
+  }
+  *u = x_0;
+  *v = x_1;
+}
+static Vec2 ImageToWorld(const Camera& c, Vec2 p) {
+  Vec2 w;
+  if (c.model == 0) { w.x = (p.x - c.params[1]) / c.params[0]; w.y = (p.y - c.params[2]) / c.params[0]; }
+  else if (c.model == 1) { w.x = (p.x - c.params[2]) / c.params[0]; w.y = (p.y - c.params[3]) / c.params[1]; }
+  else {
+    w.x = (p.x - c.params[1]) / c.params[0];
+    w.y = (p.y - c.params[2]) / c.params[0];
+    IterativeUndistortionSR(c.params[3], &w.x, &w.y);
+  }
+  return w;
+}
+static double ImageToWorldThreshold(const Camera& c, double thr) {
+  const double mf = (c.model == 1) ? (c.params[0] + c.params[1]) / 2 : c.params[0];
+  return thr / mf;
+}
+
+// ------------------------------------------------------------------ two-view
+enum Config { UNDEFINED = 0, DEGENERATE = 1, CALIBRATED = 2, UNCALIBRATED = 3, PLANAR = 4, PANORAMIC = 5, PLANAR_OR_PANORAMIC = 6, WATERMARK = 7, MULTIPLE = 8 };
+struct TvOptions {
+  size_t min_num_inliers = 15;
+  double min_E_F_inlier_ratio = 0.95, max_H_inlier_ratio = 0.8, watermark_min_inlier_ratio = 0.7, watermark_border_size = 0.1;
+  bool detect_watermark = true;
+  RansacOptions ransac;
+};
+struct TwoView {
+  int config = UNDEFINED;
+  Mat3 E, F, H;
+  std::vector<uint32_t> inlier_matches;  // pairs
+  size_t E_inl = 0, F_inl = 0, H_inl = 0;
+  size_t E_trials = 0, F_trials = 0, H_trials = 0;
+  TwoView() { memset(E.m, 0, 72); memset(F.m, 0, 72); memset(H.m, 0, 72); }
+};
+
+static bool InBox(const Vec2& p, double minx, double maxx, double miny, double maxy) {
+  return p.x >= minx && p.x <= maxx && p.y >= miny && p.y <= maxy;
+}
+static bool DetectWatermark(const Camera& c1, const std::vector<Vec2>& p1, const Camera& c2, const std::vector<Vec2>& p2,
+                            size_t num_inliers, const std::vector<char>& mask, const TvOptions& o, std::mt19937& prng) {
+  const double d1 = std::sqrt((double)(c1.width * c1.width + c1.height * c1.height));
+  const double d2 = std::sqrt((double)(c2.width * c2.width + c2.height * c2.height));
+  const double minx1 = o.watermark_border_size * d1, miny1 = minx1, maxx1 = c1.width - minx1, maxy1 = c1.height - miny1;
+  const double minx2 = o.watermark_border_size * d2, miny2 = minx2, maxx2 = c2.width - minx2, maxy2 = c2.height - miny2;
+  std::vector<Vec2> ip1(num_inliers), ip2(num_inliers);
+  size_t nb = 0, j = 0;
+  for (size_t i = 0; i < mask.size(); ++i) {
+    if (mask[i]) {
+      ip1[j] = p1[i];
+      ip2[j] = p2[i];
+      j += 1;
+      if (!InBox(p1[i], minx1, maxx1, miny1, maxy1) && !InBox(p2[i], minx2, maxx2, miny2, maxy2)) nb += 1;
+    }
+  }
+  const double ratio = static_cast<double>(nb) / num_inliers;
+  if (ratio < o.watermark_min_inlier_ratio) return false;
+  RansacOptions ro = o.ransac;
+  ro.min_inlier_ratio = o.watermark_min_inlier_ratio;
+  const Report rep = RunRansac(EST_T2, true, ro, ip1, ip2, prng);
+  const double inlier_ratio = static_cast<double>(rep.support.num_inliers) / num_inliers;
+  return inlier_ratio >= o.watermark_min_inlier_ratio;
+}
+
+static void ExtractInliers(const uint32_t* matches, size_t m, const std::vector<char>& mask, std::vector<uint32_t>* out) {
+  out->clear();
+  for (size_t i = 0; i < m; ++i)
+    if (mask[i]) { out->push_back(matches[2 * i]); out->push_back(matches[2 * i + 1]); }
+}
+
+// two_view_geometry.cc:292-425 (calibrated == true) / :427-489 (false)
+static void EstimateTwoView(const Camera& c1, const Vec2* pts1, const Camera& c2, const Vec2* pts2, const uint32_t* matches,
+                            size_t m, const TvOptions& o, bool calibrated, std::mt19937& prng, TwoView* out) {
+  if (m < o.min_num_inliers) { out->config = DEGENERATE; return; }
+  std::vector<Vec2> mp1(m), mp2(m), mn1, mn2;
+  for (size_t i = 0; i < m; ++i) { mp1[i] = pts1[matches[2 * i]]; mp2[i] = pts2[matches[2 * i + 1]]; }
+  Report E_report, F_report, H_report;
+  if (calibrated) {
+    mn1.resize(m);
+    mn2.resize(m);
+    for (size_t i = 0; i < m; ++i) { mn1[i] = ImageToWorld(c1, mp1[i]); mn2[i] = ImageToWorld(c2, mp2[i]); }
+    RansacOptions eo = o.ransac;
+    eo.max_error = (ImageToWorldThreshold(c1, o.ransac.max_error) + ImageToWorldThreshold(c2, o.ransac.max_error)) / 2;
+    E_report = RunRansac(EST_E5, true, eo, mn1, mn2, prng);
+    out->E = E_report.model;
+    out->E_inl = E_report.support.num_inliers;
+    out->E_trials = E_report.num_trials;
+  }
+  F_report = RunRansac(EST_F7, true, o.ransac, mp1, mp2, prng);
+  out->F = F_report.model;
+  out->F_inl = F_report.support.num_inliers;
+  out->F_trials = F_report.num_trials;
+  H_report = RunRansac(EST_H4, true, o.ransac, mp1, mp2, prng);
+  out->H = H_report.model;
+  out->H_inl = H_report.support.num_inliers;
+  out->H_trials = H_report.num_trials;
+
+  if (!calibrated) {
+    if ((!F_report.success && !H_report.success) ||
+        (F_report.support.num_inliers < o.min_num_inliers && H_report.support.num_inliers < o.min_num_inliers)) {
+      out->config = DEGENERATE;
+      return;
+    }
+    const double H_F = static_cast<double>(H_report.support.num_inliers) / F_report.support.num_inliers;
+    out->config = (H_F > o.max_H_inlier_ratio) ? PLANAR_OR_PANORAMIC : UNCALIBRATED;
+    // ExtractInlierMatches(matches, F num_inliers, F mask): an unsuccessful F has an empty mask
+    std::vector<char> mask = F_report.inlier_mask;
+    mask.resize(m, 0);
+    ExtractInliers(matches, m, mask, &out->inlier_matches);
+    if (o.detect_watermark && DetectWatermark(c1, mp1, c2, mp2, F_report.support.num_inliers, mask, o, prng)) out->config = WATERMARK;
+    return;
+  }
+
+  if ((!E_report.success && !F_report.success && !H_report.success) ||
+      (E_report.support.num_inliers < o.min_num_inliers && F_report.support.num_inliers < o.min_num_inliers &&
+       H_report.support.num_inliers < o.min_num_inliers)) {
+    out->config = DEGENERATE;
+    return;
+  }
+  const double E_F = static_cast<double>(E_report.support.num_inliers) / F_report.support.num_inliers;
+  const double H_F = static_cast<double>(H_report.support.num_inliers) / F_report.support.num_inliers;
+  const double H_E = static_cast<double>(H_report.support.num_inliers) / E_report.support.num_inliers;
+  const std::vector<char>* best = nullptr;
+  size_t num_inliers = 0;
+  if (E_report.success && E_F > o.min_E_F_inlier_ratio && E_report.support.num_inliers >= o.min_num_inliers) {
+    if (E_report.support.num_inliers >= F_report.support.num_inliers) { num_inliers = E_report.support.num_inliers; best = &E_report.inlier_mask; }
+    else { num_inliers = F_report.support.num_inliers; best = &F_report.inlier_mask; }
+    if (H_E > o.max_H_inlier_ratio) {
+      out->config = PLANAR_OR_PANORAMIC;
+      if (H_report.support.num_inliers > num_inliers) { num_inliers = H_report.support.num_inliers; best = &H_report.inlier_mask; }
+    } else {
+      out->config = CALIBRATED;
+    }
+  } else if (F_report.success && F_report.support.num_inliers >= o.min_num_inliers) {
+    num_inliers = F_report.support.num_inliers;
+    best = &F_report.inlier_mask;
+    if (H_F > o.max_H_inlier_ratio) {
+      out->config = PLANAR_OR_PANORAMIC;
+      if (H_report.support.num_inliers > num_inliers) { num_inliers = H_report.support.num_inliers; best = &H_report.inlier_mask; }
+    } else {
+      out->config = UNCALIBRATED;
+    }
+  } else if (H_report.success && H_report.support.num_inliers >= o.min_num_inliers) {
+    num_inliers = H_report.support.num_inliers;
+    best = &H_report.inlier_mask;
+    out->config = PLANAR_OR_PANORAMIC;
+  } else {
+    out->config = DEGENERATE;
+    return;
+  }
+  if (best != nullptr) {
+    ExtractInliers(matches, m, *best, &out->inlier_matches);
+    if (o.detect_watermark && DetectWatermark(c1, mp1, c2, mp2, num_inliers, *best, o, prng)) out->config = WATERMARK;
+  }
+}
+
+}  // namespace tv
+
+// ===================================================================== C API
+extern "C" {
+
+struct orc_camera { int32_t model, width, height, has_prior_focal; double params[12]; };
+struct orc_tv_options {
+  int32_t min_num_inliers; int32_t detect_watermark;
+  double min_E_F_inlier_ratio, max_H_inlier_ratio, watermark_min_inlier_ratio, watermark_border_size;
+  double max_error, min_inlier_ratio, confidence;
+  int64_t min_num_trials, max_num_trials;
+};
+struct orc_tv_result {
+  int32_t config; int32_t n_inliers;
+  int32_t E_inl, F_inl, H_inl, E_trials, F_trials, H_trials;
+  double E[9], F[9], H[9];
+};
+
+static std::vector<tv::Vec2> to_vec(const double* p, int n) {
+  std::vector<tv::Vec2> v(n);
+  for (int i = 0; i < n; ++i) { v[i].x = p[2 * i]; v[i].y = p[2 * i + 1]; }
+  return v;
+}
+static int put_models(const std::vector<tv::Mat3>& ms, double* out, int cap) {
+  int n = 0;
+  for (const auto& m : ms) {
+    if (n >= cap) break;
+    memcpy(out + 9 * n, m.m, 72);
+    ++n;
+  }
+  return n;
+}
+
+int orc_f7(const double* p1, const double* p2, double* out) { return put_models(tv::F7(to_vec(p1, 7), to_vec(p2, 7)), out, 3); }
+int orc_eight_point(int n, const double* p1, const double* p2, int essential, double* out) {
+  return put_models(tv::EightPoint(to_vec(p1, n), to_vec(p2, n), essential != 0), out, 1);
+}
+int orc_e5(int n, const double* p1, const double* p2, double* out, double* A_out, double* coeffs_out) {
+  return put_models(tv::E5(to_vec(p1, n), to_vec(p2, n), A_out, coeffs_out), out, 10);
+}
+int orc_h_dlt(int n, const double* p1, const double* p2, double* out) { return put_models(tv::HomographyDLT(to_vec(p1, n), to_vec(p2, n)), out, 1); }
+void orc_e5_system(const double* basis /*4x9*/, double* A /*10x20*/) {
+  double Eb[4][9];
+  memcpy(Eb, basis, sizeof Eb);
+  tv::E5BuildSystem(Eb, A);
+}
+void orc_e5_det_coeffs(const double* B_colmajor /*13x3*/, double* coeffs /*11*/) {
+  double B[13][3];
+  for (int r = 0; r < 13; ++r) for (int c = 0; c < 3; ++c) B[r][c] = B_colmajor[r + 13 * c];
+  const std::vector<double> d = tv::E5DetPoly(B);
+  memcpy(coeffs, d.data(), 11 * sizeof(double));
+}
+void orc_residuals(int type, int n, const double* p1, const double* p2, const double* M, double* res) {
+  tv::Mat3 m;
+  memcpy(m.m, M, 72);
+  std::vector<double> r;
+  tv::Residuals(type, to_vec(p1, n), to_vec(p2, n), m, &r);
+  memcpy(res, r.data(), n * sizeof(double));
+}
+uint64_t orc_compute_num_trials(uint64_t num_inliers, uint64_t num_samples, double confidence, int kmin) {
+  return tv::ComputeNumTrials(num_inliers, num_samples, confidence, kmin);
+}
+int orc_poly_roots(int n_coeffs, const double* coeffs, double* re, double* im) {
+  std::vector<double> c(coeffs, coeffs + n_coeffs), r, i;
+  if (!tv::FindPolynomialRootsCompanionMatrix(c, &r, &i)) return -1;
+  memcpy(re, r.data(), r.size() * 8);
+  memcpy(im, i.data(), i.size() * 8);
+  return (int)r.size();
+}
+void orc_svd(const double* A, int m, int n, double* sigma, double* V) { tv::jacobi_svd(A, m, n, sigma, V, nullptr); }
+// The sampler's index stream: n_trials x k indices for a population of `total`.
+void orc_sample_stream(unsigned seed, int total, int k, int n_trials, int32_t* out) {
+  std::mt19937 prng(seed);
+  tv::Sampler s(k);
+  s.Initialize(total);
+  std::vector<size_t> idx;
+  for (int t = 0; t < n_trials; ++t) {
+    s.Sample(prng, &idx);
+    for (int i = 0; i < k; ++i) out[t * k + i] = (int32_t)idx[i];
+  }
+}
+void orc_image_to_world(const orc_camera* cam, int n, const double* xy, double* out) {
+  tv::Camera c;
+  c.model = cam->model; c.width = cam->width; c.height = cam->height; c.has_prior_focal = cam->has_prior_focal;
+  memcpy(c.params, cam->params, sizeof c.params);
+  for (int i = 0; i < n; ++i) {
+    const tv::Vec2 w = tv::ImageToWorld(c, tv::Vec2{xy[2 * i], xy[2 * i + 1]});
+    out[2 * i] = w.x;
+    out[2 * i + 1] = w.y;
+  }
+}
+// One (LO-)RANSAC run.  mask: n bytes.  Returns success.
+int orc_ransac(int type, int use_lo, int n, const double* X, const double* Y, double max_error, double min_inlier_ratio,
+               double confidence, int64_t min_num_trials, int64_t max_num_trials, unsigned seed, double* model,
+               int32_t* num_inliers, double* residual_sum, int64_t* num_trials, uint8_t* mask) {
+  tv::RansacOptions o;
+  o.max_error = max_error; o.min_inlier_ratio = min_inlier_ratio; o.confidence = confidence;
+  o.min_num_trials = (size_t)min_num_trials; o.max_num_trials = (size_t)max_num_trials;
+  std::mt19937 prng(seed);
+  const tv::Report r = tv::RunRansac(type, use_lo != 0, o, to_vec(X, n), to_vec(Y, n), prng);
+  memcpy(model, r.model.m, 72);
+  *num_inliers = (int32_t)r.support.num_inliers;
+  *residual_sum = r.support.residual_sum;
+  *num_trials = (int64_t)r.num_trials;
+  memset(mask, 0, n);
+  for (size_t i = 0; i < r.inlier_mask.size(); ++i) mask[i] = r.inlier_mask[i];
+  return r.success ? 1 : 0;
+}
+
+static tv::TvOptions to_opts(const orc_tv_options* o) {
+  tv::TvOptions t;
+  t.min_num_inliers = o->min_num_inliers; t.detect_watermark = o->detect_watermark != 0;
+  t.min_E_F_inlier_ratio = o->min_E_F_inlier_ratio; t.max_H_inlier_ratio = o->max_H_inlier_ratio;
+  t.watermark_min_inlier_ratio = o->watermark_min_inlier_ratio; t.watermark_border_size = o->watermark_border_size;
+  t.ransac.max_error = o->max_error; t.ransac.min_inlier_ratio = o->min_inlier_ratio; t.ransac.confidence = o->confidence;
+  t.ransac.min_num_trials = (size_t)o->min_num_trials; t.ransac.max_num_trials = (size_t)o->max_num_trials;
+  return t;
+}
+static tv::Camera to_cam(const orc_camera* cam) {
+  tv::Camera c;
+  c.model = cam->model; c.width = cam->width; c.height = cam->height; c.has_prior_focal = cam->has_prior_focal;
+  memcpy(c.params, cam->params, sizeof c.params);
+  return c;
+}
+
+// TwoViewGeometry::Estimate (two_view_geometry.cc:113-126) for one pair, PRNG seeded with `seed`
+// (the reference's verifier thread PRNG is a continuous stream E -> F -> H -> watermark).
+// inlier_matches: capacity m pairs.
+void orc_two_view(const orc_camera* cam1, const double* pts1, const orc_camera* cam2, const double* pts2,
+                  const uint32_t* matches, int m, const orc_tv_options* opt, unsigned seed, orc_tv_result* res,
+                  uint32_t* inlier_matches) {
+  const tv::Camera c1 = to_cam(cam1), c2 = to_cam(cam2);
+  std::mt19937 prng(seed);
+  tv::TwoView tvw;
+  const bool calibrated = c1.has_prior_focal && c2.has_prior_focal;
+  tv::EstimateTwoView(c1, reinterpret_cast<const tv::Vec2*>(pts1), c2, reinterpret_cast<const tv::Vec2*>(pts2), matches,
+                      (size_t)m, to_opts(opt), calibrated, prng, &tvw);
+  res->config = tvw.config;
+  res->n_inliers = (int32_t)(tvw.inlier_matches.size() / 2);
+  res->E_inl = (int32_t)tvw.E_inl; res->F_inl = (int32_t)tvw.F_inl; res->H_inl = (int32_t)tvw.H_inl;
+  res->E_trials = (int32_t)tvw.E_trials; res->F_trials = (int32_t)tvw.F_trials; res->H_trials = (int32_t)tvw.H_trials;
+  memcpy(res->E, tvw.E.m, 72); memcpy(res->F, tvw.F.m, 72); memcpy(res->H, tvw.H.m, 72);
+  if (!tvw.inlier_matches.empty()) memcpy(inlier_matches, tvw.inlier_matches.data(), tvw.inlier_matches.size() * 4);
+}
+
+// Multi-threaded CPU baseline: `n_threads` verifier workers, one pair at a time each
+// (TwoViewGeometryVerifier::Run, src/feature/matching.cc:571-608,647-673).
+// pts: per-image pointers; match_off[n_pairs+1] offsets into matches (pairs of uint32).
+double orc_two_view_pairs_mt(const orc_camera* cams, const double* const* pts, const uint32_t* pairs, long n_pairs,
+                             const int64_t* match_off, const uint32_t* matches, const orc_tv_options* opt,
+                             const uint32_t* seeds, int n_threads, orc_tv_result* results) {
+  std::atomic<long> next(0);
+  const auto t0 = std::chrono::steady_clock::now();
+  std::vector<std::thread> th;
+  for (int t = 0; t < n_threads; ++t) {
+    th.emplace_back([&]() {
+      std::vector<uint32_t> inl;
+      for (;;) {
+        const long p = next.fetch_add(1);
+        if (p >= n_pairs) break;
+        const uint32_t i1 = pairs[2 * p], i2 = pairs[2 * p + 1];
+        const int m = (int)(match_off[p + 1] - match_off[p]);
+        inl.resize(2 * (size_t)std::max(m, 1));
+        orc_two_view(&cams[i1], pts[i1], &cams[i2], pts[i2], matches + 2 * match_off[p], m, opt, seeds[p], &results[p], inl.data());
+      }
+    });
+  }
+  for (auto& x : th) x.join();
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+}  // extern "C"
