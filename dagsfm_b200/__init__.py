@@ -7,4 +7,7 @@ work runs in the hand-written sm_100a CUDA library.
 from ._lib import B2Error, MatchOptions, lib  # noqa: F401
 from .matching import SiftMatchGPU, SiftMatchingOptions, match_sift_features_gpu  # noqa: F401
 
+from .verification import (Camera, TwoViewGeometryVerifier, TwoViewOptions,  # noqa: F401
+                           TwoViewResult)
+
 __version__ = "0.1"

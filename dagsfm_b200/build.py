@@ -1,25 +1,29 @@
 """In-tree build of the sm_100a shared library (nvcc cross-compiles without a GPU).
 
     python -m dagsfm_b200.build          # build if stale
-    python -m dagsfm_b200.build --force
+    python -m dagsfm_b200.build --force [-v]
+
+Each .cu is compiled to an object (in parallel) and the objects are linked into
+dagsfm_b200/libdagsfm_b200.so.  The two-view verifier and bundle-adjustment
+translation units are built with --fmad=false: their FP64 arithmetic must be the
+same IEEE operations as the reference's scalar C++ (no FMA contraction).
 """
 from __future__ import annotations
 
 import os
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
+OBJ = PKG / "_obj"
 LIB = PKG / "libdagsfm_b200.so"
 
-NVCC_FLAGS = [
-    "-gencode", "arch=compute_100a,code=sm_100a",
-    "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
-    "-cudart", "static",
-]
+COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+          "-Xcompiler", "-fPIC"]
+NO_FMA_PREFIXES = ("verify_", "ba_")
 
 
 def sources() -> list[Path]:
@@ -34,20 +38,41 @@ def stale() -> bool:
     return any(p.stat().st_mtime > t for p in deps)
 
 
+def _compile(nvcc: str, src: Path, verbose: bool) -> tuple[Path, str]:
+    obj = OBJ / (src.stem + ".o")
+    hdr_t = max([p.stat().st_mtime for p in list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) +
+                 [PKG.parent / "include" / "dagsfm_b200.h"]])
+    if obj.exists() and obj.stat().st_mtime > max(src.stat().st_mtime, hdr_t) and not verbose:
+        return obj, ""
+    cmd = [nvcc, *COMMON, "-c", "-o", str(obj), str(src)]
+    if src.name.startswith(NO_FMA_PREFIXES):
+        cmd.insert(1, "--fmad=false")
+    if verbose:
+        cmd[1:1] = ["-Xptxas", "-v"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed on {src.name}:\n{r.stdout}{r.stderr}")
+    return obj, r.stderr
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and not stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", str(LIB), *map(str, sources())]
+    OBJ.mkdir(exist_ok=True)
+    if force:
+        for o in OBJ.glob("*.o"):
+            o.unlink()
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        res = list(ex.map(lambda s: _compile(nvcc, s, verbose), sources()))
     if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
+        for _, log in res:
+            sys.stderr.write(log)
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static",
+           "-o", str(LIB), *[str(o) for o, _ in res]]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
-        sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError("nvcc failed building libdagsfm_b200.so")
-    if verbose:
-        sys.stderr.write(r.stderr)
+        raise RuntimeError(f"link failed:\n{r.stdout}{r.stderr}")
     return LIB
 
 

@@ -1,0 +1,903 @@
+// Two-view geometric verification on the GPU: one warp owns one image pair and runs
+// the reference's whole decision procedure for it,
+//
+//   TwoViewGeometry::Estimate                    src/estimators/two_view_geometry.cc:113-126
+//   EstimateCalibrated / EstimateUncalibrated    :292-425 / :427-489
+//   DetectWatermark                              :491-555
+//   LORANSAC::Estimate                           src/optim/loransac.h:92-233
+//   RandomSampler + Shuffle over std::mt19937    src/optim/random_sampler.cc:43-62, util/random.h:89-129
+//   InlierSupportMeasurer                        src/optim/support_measurement.cc:36-60
+//   Sampson / transfer residuals                 src/estimators/utils.cc:87-131, homography_matrix.cc:94-131
+//
+// Batching inside the warp: 32 RANSAC trials at a time.  Lane j solves the minimal
+// problem of trial j (FP64, per-lane, see verify_solvers.cuh); then the warp replays the
+// trials IN ORDER and scores each hypothesis with all 32 lanes: coalesced 16-byte match
+// loads, one residual per lane, __ballot_sync + popc inlier counting.  The sequential
+// semantics (strict support comparison, local optimisation on every new best, dynamic
+// trial bound, the loop-counter quirk) are replayed exactly; the PRNG draws of trials that
+// were sampled but fall after the abort point are pushed back into the stream.
+//
+// Compiled with --fmad=false so that residuals are the same IEEE operations as the
+// reference's scalar C++ code.
+#include <cuda_runtime.h>
+
+#include <cfloat>
+#include <cstdint>
+
+#include "../../include/dagsfm_b200.h"
+#include "verify_common.cuh"
+#include "verify_solvers.cuh"
+
+namespace b2 {
+namespace vf {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+// -------------------------------------------------------------------- PRNG
+// std::mt19937 (result_type = uint_fast32_t, 32 significant bits).
+struct WarpShared {
+  uint32_t mt[624];
+  uint32_t ring[512];   // FIFO of raw mt outputs; rollback = moving r back
+  uint32_t samp[32][8]; // sample indices of the 32 trials of a batch
+  uint32_t pos_after[32];
+  double V[81];         // right singular vectors of the warp-level Jacobi SVD
+  int nm[32];
+  int lo_nm;
+  uint32_t mti, w, r;
+};
+
+__device__ inline void mt_seed(WarpShared& s, uint32_t seed) {
+  s.mt[0] = seed;
+  for (int i = 1; i < 624; ++i) s.mt[i] = 1812433253u * (s.mt[i - 1] ^ (s.mt[i - 1] >> 30)) + (uint32_t)i;
+  s.mti = 624;
+  s.w = 0;
+  s.r = 0;
+}
+__device__ inline uint32_t mt_next(WarpShared& s) {
+  if (s.mti >= 624) {
+    for (int k = 0; k < 624; ++k) {
+      const uint32_t y = (s.mt[k] & 0x80000000u) | (s.mt[(k + 1) % 624] & 0x7fffffffu);
+      s.mt[k] = s.mt[(k + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    }
+    s.mti = 0;
+  }
+  uint32_t y = s.mt[s.mti++];
+  y ^= (y >> 11);
+  y ^= (y << 7) & 0x9d2c5680u;
+  y ^= (y << 15) & 0xefc60000u;
+  y ^= (y >> 18);
+  return y;
+}
+// next raw output through the FIFO (lane 0 only)
+__device__ inline uint32_t raw_next(WarpShared& s) {
+  if (s.r == s.w) {
+    s.ring[s.w & 511u] = mt_next(s);
+    ++s.w;
+  }
+  return s.ring[(s.r++) & 511u];
+}
+// libstdc++ (GCC >= 11) std::uniform_int_distribution<uint32_t>(a, b) on a 32-bit URBG:
+// Lemire's nearly-divisionless method (bits/uniform_int_dist.h, _S_nd<uint64_t>).
+__device__ inline uint32_t uniform_u32(WarpShared& s, uint32_t a, uint32_t b) {
+  const uint32_t urange = b - a;
+  if (urange == 0xffffffffu) return raw_next(s) + a;
+  const uint32_t range = urange + 1;
+  uint64_t product = (uint64_t)raw_next(s) * (uint64_t)range;
+  uint32_t low = (uint32_t)product;
+  if (low < range) {
+    const uint32_t threshold = (0u - range) % range;
+    while (low < threshold) {
+      product = (uint64_t)raw_next(s) * (uint64_t)range;
+      low = (uint32_t)product;
+    }
+  }
+  return (uint32_t)(product >> 32) + a;
+}
+
+// ----------------------------------------------------------------- residuals
+__device__ __forceinline__ double sampson(const double* E, double x1_0, double x1_1, double x2_0, double x2_1) {
+  const double Ex1_0 = E[0] * x1_0 + E[1] * x1_1 + E[2];
+  const double Ex1_1 = E[3] * x1_0 + E[4] * x1_1 + E[5];
+  const double Ex1_2 = E[6] * x1_0 + E[7] * x1_1 + E[8];
+  const double Etx2_0 = E[0] * x2_0 + E[3] * x2_1 + E[6];
+  const double Etx2_1 = E[1] * x2_0 + E[4] * x2_1 + E[7];
+  const double x2tEx1 = x2_0 * Ex1_0 + x2_1 * Ex1_1 + Ex1_2;
+  return x2tEx1 * x2tEx1 / (Ex1_0 * Ex1_0 + Ex1_1 * Ex1_1 + Etx2_0 * Etx2_0 + Etx2_1 * Etx2_1);
+}
+__device__ __forceinline__ double transfer(const double* H, double s_0, double s_1, double d_0, double d_1) {
+  const double pd_0 = H[0] * s_0 + H[1] * s_1 + H[2];
+  const double pd_1 = H[3] * s_0 + H[4] * s_1 + H[5];
+  const double pd_2 = H[6] * s_0 + H[7] * s_1 + H[8];
+  const double inv_pd_2 = 1.0 / pd_2;
+  const double dd_0 = d_0 - pd_0 * inv_pd_2;
+  const double dd_1 = d_1 - pd_1 * inv_pd_2;
+  return dd_0 * dd_0 + dd_1 * dd_1;
+}
+__device__ __forceinline__ double translation_res(const double* T, double a0, double a1, double b0, double b1) {
+  const double e0 = (b0 - a0) - T[0], e1 = (b1 - a1) - T[1];
+  return e0 * e0 + e1 * e1;
+}
+__device__ __forceinline__ double residual(int type, const double* M, double2 a, double2 b) {
+  if (type == EST_H4) return transfer(M, a.x, a.y, b.x, b.y);
+  if (type == EST_T2) return translation_res(M, a.x, a.y, b.x, b.y);
+  return sampson(M, a.x, a.y, b.x, b.y);
+}
+
+// InlierSupportMeasurer::Evaluate, count only (all lanes return the same value).
+__device__ int score_count(int type, const double2* P1, const double2* P2, int M, const double* model, double max_res,
+                           int lane) {
+  int cnt = 0;
+  for (int i0 = 0; i0 < M; i0 += 32) {
+    const int i = i0 + lane;
+    bool in = false;
+    if (i < M) in = residual(type, model, P1[i], P2[i]) <= max_res;
+    cnt += __popc(__ballot_sync(kFull, in));
+  }
+  return cnt;
+}
+// ... and its residual_sum: a sequential FP64 sum in index order (support_measurement.cc:43-46);
+// optionally writes the inlier mask.  Needed only on ties and for a new best.
+__device__ double score_sum(int type, const double2* P1, const double2* P2, int M, const double* model, double max_res,
+                            int lane, uint8_t* mask_out) {
+  double sum = 0;
+  for (int i0 = 0; i0 < M; i0 += 32) {
+    const int i = i0 + lane;
+    bool in = false;
+    double r = 0;
+    if (i < M) {
+      r = residual(type, model, P1[i], P2[i]);
+      in = r <= max_res;
+      if (mask_out) mask_out[i] = in ? 1 : 0;
+    }
+    unsigned m = __ballot_sync(kFull, in);
+    while (m) {
+      const int b = __ffs(m) - 1;
+      const double v = __shfl_sync(kFull, r, b);
+      sum += v;
+      m &= m - 1;
+    }
+  }
+  return sum;
+}
+
+// x86-64 GCC semantics of static_cast<size_t>(double) (cvttsd2si based), which the
+// reference relies on in ComputeNumTrials when log(denom) == 0 (ransac.h:166).
+__device__ inline unsigned long long x86_f64_to_u64(double x) {
+  const double two63 = 9223372036854775808.0;
+  if (x != x) return 0x8000000000000000ull;
+  if (x >= two63) {
+    const double y = x - two63;
+    if (!(y < two63)) return 0ull;  // cvttsd2si indefinite (0x8000...) xor sign bit
+    return (unsigned long long)(long long)y ^ 0x8000000000000000ull;
+  }
+  if (x <= -two63) return 0x8000000000000000ull;
+  return (unsigned long long)(long long)x;
+}
+// RANSAC::ComputeNumTrials (ransac.h:149-167)
+__device__ inline unsigned long long compute_num_trials(unsigned long long num_inliers, unsigned long long num_samples,
+                                                        double confidence, int kmin) {
+  const double inlier_ratio = (double)num_inliers / (double)num_samples;
+  const double nom = 1 - confidence;
+  if (nom <= 0) return 0xffffffffffffffffull;
+  const double denom = 1 - pow(inlier_ratio, (double)kmin);
+  if (denom <= 0) return 1;
+  return x86_f64_to_u64(ceil(log(nom) / log(denom)));
+}
+
+// ------------------------------------------------------- warp-level Jacobi SVD
+// G: rows x 9, column-major (G[c * ld + r]) in global scratch; V (9x9 row-major) in shared.
+// One-sided Jacobi; lanes split the rows.  On return V's columns are sorted by descending
+// singular value (sig in shared too).
+__device__ void warp_jacobi9(double* G, int rows, int ld, double* V, double* sig, int lane) {
+  for (int i = lane; i < 81; i += 32) V[i] = (i / 9 == i % 9) ? 1.0 : 0.0;
+  __syncwarp();
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    bool rotated = false;
+    for (int p = 0; p < 8; ++p) {
+      for (int q = p + 1; q < 9; ++q) {
+        double alpha = 0, beta = 0, gamma = 0;
+        double* gp = G + (size_t)p * ld;
+        double* gq = G + (size_t)q * ld;
+        for (int i = lane; i < rows; i += 32) {
+          const double a = gp[i], b = gq[i];
+          alpha += a * a;
+          beta += b * b;
+          gamma += a * b;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          alpha += __shfl_xor_sync(kFull, alpha, o);
+          beta += __shfl_xor_sync(kFull, beta, o);
+          gamma += __shfl_xor_sync(kFull, gamma, o);
+        }
+        if (gamma == 0.0 || fabs(gamma) <= kEps * sqrt(alpha * beta)) continue;
+        rotated = true;
+        const double zeta = (beta - alpha) / (2.0 * gamma);
+        const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        const double c = 1.0 / sqrt(1.0 + t * t);
+        const double s = c * t;
+        for (int i = lane; i < rows; i += 32) {
+          const double a = gp[i], b = gq[i];
+          gp[i] = c * a - s * b;
+          gq[i] = s * a + c * b;
+        }
+        if (lane < 9) {
+          const double a = V[lane * 9 + p], b = V[lane * 9 + q];
+          V[lane * 9 + p] = c * a - s * b;
+          V[lane * 9 + q] = s * a + c * b;
+        }
+        __syncwarp();
+      }
+    }
+    if (!rotated) break;
+  }
+  // column norms -> order (every lane computes the same permutation)
+  double nrm[9];
+  for (int j = 0; j < 9; ++j) {
+    double s = 0;
+    const double* g = G + (size_t)j * ld;
+    for (int i = lane; i < rows; i += 32) s += g[i] * g[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
+    nrm[j] = sqrt(s);
+  }
+  int order[9];
+  for (int j = 0; j < 9; ++j) {
+    int rank = 0;
+    for (int i = 0; i < 9; ++i) rank += (nrm[i] > nrm[j] || (nrm[i] == nrm[j] && i < j)) ? 1 : 0;
+    order[rank] = j;
+  }
+  double row[9];
+  if (lane < 9)
+    for (int j = 0; j < 9; ++j) row[j] = V[lane * 9 + order[j]];
+  __syncwarp();
+  if (lane < 9) {
+    for (int j = 0; j < 9; ++j) V[lane * 9 + j] = row[j];
+    sig[lane] = nrm[order[lane]];
+  }
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------- local estimators
+// Hartley statistics of the inlier points (index list inl[0..N)) -- warp-parallel sums.
+__device__ void warp_hartley(const double2* P, const uint32_t* inl, int N, int lane, double* T) {
+  double cx = 0, cy = 0;
+  for (int k = lane; k < N; k += 32) {
+    const double2 p = P[inl[k]];
+    cx += p.x;
+    cy += p.y;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    cx += __shfl_xor_sync(kFull, cx, o);
+    cy += __shfl_xor_sync(kFull, cy, o);
+  }
+  cx /= N;
+  cy /= N;
+  double rms = 0;
+  for (int k = lane; k < N; k += 32) {
+    const double2 p = P[inl[k]];
+    const double dx = p.x - cx, dy = p.y - cy;
+    rms += dx * dx + dy * dy;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) rms += __shfl_xor_sync(kFull, rms, o);
+  rms = sqrt(rms / N);
+  const double nf = sqrt(2.0) / rms;
+  T[0] = nf; T[1] = 0; T[2] = -nf * cx; T[3] = 0; T[4] = nf; T[5] = -nf * cy; T[6] = 0; T[7] = 0; T[8] = 1;
+}
+__device__ __forceinline__ double2 apply_T(const double* T, double2 p) {
+  const double n0 = T[0] * p.x + T[1] * p.y + T[2];
+  const double n1 = T[3] * p.x + T[4] * p.y + T[5];
+  const double n2 = T[6] * p.x + T[7] * p.y + T[8];
+  const double inv = 1.0 / n2;
+  return make_double2(n0 * inv, n1 * inv);
+}
+
+// Local estimator on the N inliers listed in inl[]; writes models (<= 10 x 9) to `models`
+// (global scratch, visible to all lanes) and returns the count (uniform).
+__device__ int local_estimate(int type, const double2* P1, const double2* P2, const uint32_t* inl, int N, double* G,
+                              int ld, WarpShared& sh, double* sig_sh, double* models, int lane) {
+  if (type == EST_T2) {  // translation_transform.h:84-102: mean_dst - mean_src, sums in index order
+    if (lane == 0) {
+      double sx = 0, sy = 0, dx = 0, dy = 0;
+      for (int k = 0; k < N; ++k) {
+        const double2 a = P1[inl[k]], b = P2[inl[k]];
+        sx += a.x; sy += a.y; dx += b.x; dy += b.y;
+      }
+      sx /= N; sy /= N; dx /= N; dy /= N;
+      for (int k = 0; k < 9; ++k) models[k] = 0.0;
+      models[0] = dx - sx;
+      models[1] = dy - sy;
+    }
+    __syncwarp();
+    return 1;
+  }
+  int nm = 0;
+  if (type == EST_E5) {
+    for (int k = lane; k < N; k += 32) {
+      const double2 a = P1[inl[k]], b = P2[inl[k]];
+      G[0 * (size_t)ld + k] = a.x * b.x; G[1 * (size_t)ld + k] = a.y * b.x; G[2 * (size_t)ld + k] = b.x;
+      G[3 * (size_t)ld + k] = a.x * b.y; G[4 * (size_t)ld + k] = a.y * b.y; G[5 * (size_t)ld + k] = b.y;
+      G[6 * (size_t)ld + k] = a.x; G[7 * (size_t)ld + k] = a.y; G[8 * (size_t)ld + k] = 1;
+    }
+    __syncwarp();
+    warp_jacobi9(G, N, ld, sh.V, sig_sh, lane);
+    if (lane == 0) {
+      double Eb[36];
+      for (int k = 0; k < 4; ++k)
+        for (int i = 0; i < 9; ++i) Eb[9 * k + i] = sh.V[i * 9 + 5 + k];
+      sh.lo_nm = solve_e5_from_basis(Eb, models);
+    }
+    __syncwarp();
+    nm = sh.lo_nm;
+    __syncwarp();
+    return nm;
+  }
+  double T1[9], T2[9];
+  warp_hartley(P1, inl, N, lane, T1);
+  warp_hartley(P2, inl, N, lane, T2);
+  int rows;
+  if (type == EST_F7) {  // 8-point, fundamental_matrix.cc:150-192
+    rows = N;
+    for (int k = lane; k < N; k += 32) {
+      const double2 a = apply_T(T1, P1[inl[k]]), b = apply_T(T2, P2[inl[k]]);
+      G[0 * (size_t)ld + k] = a.x * b.x; G[1 * (size_t)ld + k] = a.y * b.x; G[2 * (size_t)ld + k] = 1.0 * b.x;
+      G[3 * (size_t)ld + k] = a.x * b.y; G[4 * (size_t)ld + k] = a.y * b.y; G[5 * (size_t)ld + k] = 1.0 * b.y;
+      G[6 * (size_t)ld + k] = a.x; G[7 * (size_t)ld + k] = a.y; G[8 * (size_t)ld + k] = 1.0;
+    }
+  } else {  // homography DLT, homography_matrix.cc:44-92: rows [0,N) and [N,2N)
+    rows = 2 * N;
+    for (int k = lane; k < N; k += 32) {
+      const double2 s = apply_T(T1, P1[inl[k]]), d = apply_T(T2, P2[inl[k]]);
+      const int j = N + k;
+      G[0 * (size_t)ld + k] = -s.x; G[1 * (size_t)ld + k] = -s.y; G[2 * (size_t)ld + k] = -1;
+      G[3 * (size_t)ld + k] = 0; G[4 * (size_t)ld + k] = 0; G[5 * (size_t)ld + k] = 0;
+      G[6 * (size_t)ld + k] = s.x * d.x; G[7 * (size_t)ld + k] = s.y * d.x; G[8 * (size_t)ld + k] = d.x;
+      G[0 * (size_t)ld + j] = 0; G[1 * (size_t)ld + j] = 0; G[2 * (size_t)ld + j] = 0;
+      G[3 * (size_t)ld + j] = -s.x; G[4 * (size_t)ld + j] = -s.y; G[5 * (size_t)ld + j] = -1;
+      G[6 * (size_t)ld + j] = s.x * d.y; G[7 * (size_t)ld + j] = s.y * d.y; G[8 * (size_t)ld + j] = d.y;
+    }
+  }
+  __syncwarp();
+  warp_jacobi9(G, rows, ld, sh.V, sig_sh, lane);
+  if (lane == 0) {
+    double nv[9];
+    for (int k = 0; k < 9; ++k) nv[k] = sh.V[k * 9 + 8];
+    if (type == EST_F7) finish_f8(nv, T1, T2, models);
+    else finish_h(nv, T1, T2, models);
+  }
+  __syncwarp();
+  return 1;
+}
+
+struct RansacResult {
+  bool success;
+  int num_inliers;
+  double residual_sum;
+  long long num_trials;
+  double model[9];
+};
+
+struct Scratch {
+  double2 *px1, *px2, *nx1, *nx2;  // matched points, pixel / normalised   [Mcap]
+  double2 *ip1, *ip2;              // inlier pixel points (watermark)       [Mcap]
+  uint32_t* idx;                   // sampler's persistent index vector     [Mcap]
+  uint32_t* inl;                   // inlier index list                     [Mcap]
+  double* G;                       // 9 columns x ld (ld = 2*Mcap)
+  int ld;
+  double* models;                  // [32][10][9] per-lane sample models
+  double* lomodels;                // [10][9] local models
+  uint8_t* mask[3];                // E, F, H inlier masks                  [Mcap]
+  uint8_t* tmask;                  // scratch mask
+};
+
+// LORANSAC::Estimate for one estimator over the matched points (P1,P2)[0..M).
+__device__ void ransac_warp(int type, const double2* P1, const double2* P2, int M, double max_error,
+                            double min_inlier_ratio, double confidence, long long min_num_trials,
+                            long long max_num_trials_opt, WarpShared& sh, double* sig_sh, const Scratch& sc,
+                            uint8_t* mask_out, RansacResult* out, int lane) {
+  const int kmin = min_samples(type), klo = local_min_samples(type);
+  out->success = false;
+  out->num_trials = 0;
+  out->num_inliers = 0;
+  out->residual_sum = DBL_MAX;
+  for (int k = 0; k < 9; ++k) out->model[k] = 0.0;
+  // RANSAC ctor (ransac.h:135-147)
+  unsigned long long max_trials = (unsigned long long)max_num_trials_opt;
+  {
+    const unsigned long long dyn = compute_num_trials((unsigned long long)(min_inlier_ratio * 100000.0), 100000ull, confidence, kmin);
+    if (dyn < max_trials) max_trials = dyn;
+  }
+  if (M < kmin) return;
+  const double max_residual = max_error * max_error;
+  int best_count = 0;
+  double best_sum = DBL_MAX;
+  double best_model[9];
+  for (int k = 0; k < 9; ++k) best_model[k] = 0.0;
+  bool abort = false;
+  for (int i = lane; i < M; i += 32) sc.idx[i] = (uint32_t)i;  // sampler.Initialize
+  __syncwarp();
+  unsigned long long dyn_max = max_trials;
+  unsigned long long t0 = 0;
+  unsigned long long num_trials = 0;
+  bool ended = false;
+  while (t0 < max_trials) {
+    if (abort) {  // abort was raised by the last trial of the previous batch (loransac.h:131-134)
+      num_trials = t0 + 1;
+      ended = true;
+      break;
+    }
+    const int nb = (int)((max_trials - t0) < 32ull ? (max_trials - t0) : 32ull);
+    // --- lane 0: sample indices for trials t0 .. t0+nb-1 (Shuffle of the persistent vector)
+    if (lane == 0) {
+      const uint32_t last = (uint32_t)(M - 1);
+      for (int j = 0; j < nb; ++j) {
+        for (uint32_t i = 0; i < (uint32_t)kmin; ++i) {
+          const uint32_t jj = uniform_u32(sh, i, last);
+          const uint32_t a = sc.idx[i], b = sc.idx[jj];
+          sc.idx[i] = b;
+          sc.idx[jj] = a;
+        }
+        for (int i = 0; i < kmin; ++i) sh.samp[j][i] = sc.idx[i];
+        sh.pos_after[j] = sh.r;
+      }
+    }
+    __syncwarp();
+    // --- lane j: minimal solver of trial t0 + j
+    {
+      int nm = 0;
+      double* mymodels = sc.models + (size_t)lane * 90;
+      if (lane < nb) {
+        double a[14], b[14];
+        for (int i = 0; i < kmin; ++i) {
+          const double2 pa = P1[sh.samp[lane][i]], pb = P2[sh.samp[lane][i]];
+          a[2 * i] = pa.x; a[2 * i + 1] = pa.y; b[2 * i] = pb.x; b[2 * i + 1] = pb.y;
+        }
+        double mm[90];
+        if (type == EST_E5) nm = solve_e5(a, b, mm);
+        else if (type == EST_F7) nm = solve_f7(a, b, mm);
+        else if (type == EST_H4) nm = solve_h4(a, b, mm);
+        else {  // translation from one sample: mean_dst - mean_src with n = 1
+          for (int k = 0; k < 9; ++k) mm[k] = 0.0;
+          mm[0] = b[0] / 1.0 - a[0] / 1.0;
+          mm[1] = b[1] / 1.0 - a[1] / 1.0;
+          nm = 1;
+        }
+        for (int k = 0; k < 9 * nm; ++k) mymodels[k] = mm[k];
+      }
+      sh.nm[lane] = nm;
+    }
+    __syncwarp();
+    // --- ordered replay
+    for (int j = 0; j < nb; ++j) {
+      const unsigned long long trial = t0 + j;
+      if (abort) {  // loransac.h:131-134: the for-increment already happened, then += 1
+        num_trials = trial + 1;
+        ended = true;
+        if (lane == 0) sh.r = sh.pos_after[j - 1];  // un-draw trials >= j (j >= 1 here)
+        break;
+      }
+      const int nm = sh.nm[j];
+      for (int mi = 0; mi < nm; ++mi) {
+        double model[9];
+        for (int k = 0; k < 9; ++k) model[k] = sc.models[(size_t)j * 90 + 9 * mi + k];
+        const int cnt = score_count(type, P1, P2, M, model, max_residual, lane);
+        bool better = cnt > best_count;
+        double sum = 0;
+        if (cnt >= best_count) {
+          sum = score_sum(type, P1, P2, M, model, max_residual, lane, sc.tmask);
+          sum = __shfl_sync(kFull, sum, 0);
+          if (cnt == best_count) better = sum < best_sum;
+        }
+        if (better) {
+          best_count = cnt;
+          best_sum = sum;
+          for (int k = 0; k < 9; ++k) best_model[k] = model[k];
+          if (cnt > kmin && cnt >= klo) {
+            // inlier list of the sample model (mask just written by score_sum)
+            __syncwarp();
+            int N = 0;
+            for (int i0 = 0; i0 < M; i0 += 32) {
+              const int i = i0 + lane;
+              const bool in = (i < M) && sc.tmask[i];
+              const unsigned bm = __ballot_sync(kFull, in);
+              if (in) sc.inl[N + __popc(bm & ((1u << lane) - 1))] = (uint32_t)i;
+              N += __popc(bm);
+            }
+            __syncwarp();
+            const int nlm = local_estimate(type, P1, P2, sc.inl, N, sc.G, sc.ld, sh, sig_sh, sc.lomodels, lane);
+            for (int li = 0; li < nlm; ++li) {
+              double lm[9];
+              for (int k = 0; k < 9; ++k) lm[k] = sc.lomodels[9 * li + k];
+              const int lc = score_count(type, P1, P2, M, lm, max_residual, lane);
+              bool lbetter = lc > best_count;
+              double lsum = 0;
+              if (lc >= best_count) {
+                lsum = score_sum(type, P1, P2, M, lm, max_residual, lane, nullptr);
+                lsum = __shfl_sync(kFull, lsum, 0);
+                if (lc == best_count) lbetter = lsum < best_sum;
+              }
+              if (lbetter) {
+                best_count = lc;
+                best_sum = lsum;
+                for (int k = 0; k < 9; ++k) best_model[k] = lm[k];
+              }
+            }
+          }
+          dyn_max = compute_num_trials((unsigned long long)best_count, (unsigned long long)M, confidence, kmin);
+        }
+        if (trial >= dyn_max && trial >= (unsigned long long)min_num_trials) {
+          abort = true;
+          break;
+        }
+      }
+    }
+    if (ended) break;
+    t0 += nb;
+    __syncwarp();
+  }
+  if (!ended) num_trials = max_trials;
+  out->num_trials = (long long)num_trials;
+  out->num_inliers = best_count;
+  out->residual_sum = best_sum;
+  for (int k = 0; k < 9; ++k) out->model[k] = best_model[k];
+  if (best_count < kmin) return;
+  out->success = true;
+  score_sum(type, P1, P2, M, best_model, max_residual, lane, mask_out);
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------ cameras
+__device__ inline void simple_radial_distortion(double k, double u, double v, double* du, double* dv) {
+  const double u2 = u * u, v2 = v * v, r2 = u2 + v2, radial = k * r2;
+  *du = u * radial;
+  *dv = v * radial;
+}
+// Camera::ImageToWorld (camera_models.h:734-746) incl. IterativeUndistortion (:547-590)
+__device__ inline double2 image_to_world(const b2_camera& c, double2 p) {
+  double u, v;
+  if (c.model == 0) {
+    u = (p.x - c.params[1]) / c.params[0];
+    v = (p.y - c.params[2]) / c.params[0];
+  } else if (c.model == 1) {
+    u = (p.x - c.params[2]) / c.params[0];
+    v = (p.y - c.params[3]) / c.params[1];
+  } else {
+    u = (p.x - c.params[1]) / c.params[0];
+    v = (p.y - c.params[2]) / c.params[0];
+    const double k = c.params[3];
+    const double x0_0 = u, x0_1 = v;
+    double x_0 = u, x_1 = v;
+    for (int i = 0; i < 100; ++i) {
+      const double step0 = fmax(DBL_EPSILON, fabs(1e-6 * x_0));
+      const double step1 = fmax(DBL_EPSILON, fabs(1e-6 * x_1));
+      double dx0, dx1, b00, b01, f00, f01, b10, b11, f10, f11;
+      simple_radial_distortion(k, x_0, x_1, &dx0, &dx1);
+      simple_radial_distortion(k, x_0 - step0, x_1, &b00, &b01);
+      simple_radial_distortion(k, x_0 + step0, x_1, &f00, &f01);
+      simple_radial_distortion(k, x_0, x_1 - step1, &b10, &b11);
+      simple_radial_distortion(k, x_0, x_1 + step1, &f10, &f11);
+      const double J00 = 1 + (f00 - b00) / (2 * step0);
+      const double J01 = (f10 - b10) / (2 * step1);
+      const double J10 = (f01 - b01) / (2 * step0);
+      const double J11 = 1 + (f11 - b11) / (2 * step1);
+      const double invdet = 1.0 / (J00 * J11 - J01 * J10);
+      const double r0 = x_0 + dx0 - x0_0, r1 = x_1 + dx1 - x0_1;
+      const double s0 = (J11 * invdet) * r0 + (-J01 * invdet) * r1;
+      const double s1 = (-J10 * invdet) * r0 + (J00 * invdet) * r1;
+      x_0 -= s0;
+      x_1 -= s1;
+      if (s0 * s0 + s1 * s1 < 1e-10) break;
+    }
+    u = x_0;
+    v = x_1;
+  }
+  return make_double2(u, v);
+}
+__device__ inline double image_to_world_threshold(const b2_camera& c, double thr) {
+  const double mf = (c.model == 1) ? (c.params[0] + c.params[1]) / 2 : c.params[0];
+  return thr / mf;
+}
+
+__global__ void normalize_points_kernel(const b2_camera* __restrict__ cams, const int64_t* __restrict__ img_off,
+                                        int n_images, const double2* __restrict__ xy, double2* __restrict__ nxy,
+                                        int64_t n_total) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n_total) return;
+  int lo = 0, hi = n_images - 1;  // image of keypoint i: last img with img_off <= i
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (img_off[mid] <= i) lo = mid; else hi = mid - 1;
+  }
+  nxy[i] = image_to_world(cams[lo], xy[i]);
+}
+
+__device__ __forceinline__ bool in_box(double2 p, double minx, double maxx, double miny, double maxy) {
+  return p.x >= minx && p.x <= maxx && p.y >= miny && p.y <= maxy;
+}
+
+// ------------------------------------------------------------------ main kernel
+constexpr int kWarpsPerBlock = 4;
+
+__global__ void __launch_bounds__(32 * kWarpsPerBlock)
+verify_pairs_kernel(VerifyArgs A) {
+  __shared__ WarpShared shs[kWarpsPerBlock];
+  __shared__ double sigs[kWarpsPerBlock][9];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  WarpShared& sh = shs[wib];
+  double* sig_sh = sigs[wib];
+  const int worker = blockIdx.x * kWarpsPerBlock + wib;
+  // carve this worker's scratch
+  Scratch sc;
+  {
+    uint8_t* base = A.scratch + (size_t)worker * A.scratch_stride;
+    const size_t mc = (size_t)A.m_cap;
+    sc.px1 = (double2*)base; base += mc * 16;
+    sc.px2 = (double2*)base; base += mc * 16;
+    sc.nx1 = (double2*)base; base += mc * 16;
+    sc.nx2 = (double2*)base; base += mc * 16;
+    sc.ip1 = (double2*)base; base += mc * 16;
+    sc.ip2 = (double2*)base; base += mc * 16;
+    sc.G = (double*)base; base += mc * 2 * 9 * 8;
+    sc.ld = (int)(2 * mc);
+    sc.models = (double*)base; base += 32 * 90 * 8;
+    sc.lomodels = (double*)base; base += 90 * 8;
+    sc.idx = (uint32_t*)base; base += mc * 4;
+    sc.inl = (uint32_t*)base; base += mc * 4;
+    sc.mask[0] = base; base += mc;
+    sc.mask[1] = base; base += mc;
+    sc.mask[2] = base; base += mc;
+    sc.tmask = base;
+  }
+  const b2_two_view_options& o = A.opt;
+  for (;;) {
+    long long p = 0;
+    if (lane == 0) p = (long long)atomicAdd(A.work_counter, 1ull);
+    p = __shfl_sync(kFull, p, 0);
+    if (p >= A.n_pairs) break;
+    const uint32_t i1 = A.pairs[2 * p], i2 = A.pairs[2 * p + 1];
+    const int64_t moff = A.match_off[p];
+    const int M = (int)(A.match_off[p + 1] - moff);
+    b2_two_view_result res;
+    res.config = 0;
+    res.n_inliers = 0;
+    res.E_num_inliers = res.F_num_inliers = res.H_num_inliers = 0;
+    res.E_num_trials = res.F_num_trials = res.H_num_trials = 0;
+    for (int k = 0; k < 9; ++k) res.E[k] = res.F[k] = res.H[k] = 0.0;
+    bool done = false;
+    if (i1 >= (uint32_t)A.n_images || i2 >= (uint32_t)A.n_images || M > A.m_cap) {
+      if (lane == 0) atomicExch(A.err, 1);
+      res.config = 1;
+      done = true;
+    }
+    if (!done && (unsigned long long)M < (unsigned long long)o.min_num_inliers) {
+      res.config = 1;  // DEGENERATE (two_view_geometry.cc:298-301)
+      done = true;
+    }
+    if (!done) {
+      const b2_camera c1 = A.cams[i1], c2 = A.cams[i2];
+      const bool calibrated = c1.has_prior_focal_length && c2.has_prior_focal_length;
+      const uint32_t* mt = A.matches + 2 * moff;
+      const int64_t o1 = A.img_off[i1], o2 = A.img_off[i2];
+      for (int i = lane; i < M; i += 32) {
+        const uint32_t a = mt[2 * i], b = mt[2 * i + 1];
+        sc.px1[i] = A.xy[o1 + a];
+        sc.px2[i] = A.xy[o2 + b];
+        sc.nx1[i] = A.nxy[o1 + a];
+        sc.nx2[i] = A.nxy[o2 + b];
+      }
+      if (lane == 0) mt_seed(sh, A.seeds[p]);
+      __syncwarp();
+      RansacResult E, F, H;
+      E.success = false; E.num_inliers = 0; E.num_trials = 0;
+      for (int k = 0; k < 9; ++k) E.model[k] = 0.0;
+      if (calibrated) {
+        const double e_err = (image_to_world_threshold(c1, o.max_error) + image_to_world_threshold(c2, o.max_error)) / 2;
+        ransac_warp(EST_E5, sc.nx1, sc.nx2, M, e_err, o.min_inlier_ratio, o.confidence, o.min_num_trials,
+                    o.max_num_trials, sh, sig_sh, sc, sc.mask[0], &E, lane);
+      }
+      ransac_warp(EST_F7, sc.px1, sc.px2, M, o.max_error, o.min_inlier_ratio, o.confidence, o.min_num_trials,
+                  o.max_num_trials, sh, sig_sh, sc, sc.mask[1], &F, lane);
+      ransac_warp(EST_H4, sc.px1, sc.px2, M, o.max_error, o.min_inlier_ratio, o.confidence, o.min_num_trials,
+                  o.max_num_trials, sh, sig_sh, sc, sc.mask[2], &H, lane);
+      for (int k = 0; k < 9; ++k) { res.E[k] = E.model[k]; res.F[k] = F.model[k]; res.H[k] = H.model[k]; }
+      res.E_num_inliers = E.num_inliers; res.F_num_inliers = F.num_inliers; res.H_num_inliers = H.num_inliers;
+      res.E_num_trials = (int)E.num_trials; res.F_num_trials = (int)F.num_trials; res.H_num_trials = (int)H.num_trials;
+      const unsigned long long mni = (unsigned long long)o.min_num_inliers;
+      const unsigned long long En = E.num_inliers, Fn = F.num_inliers, Hn = H.num_inliers;
+      int best = -1;  // which mask
+      unsigned long long num_inliers = 0;
+      bool best_valid = true;  // an unsuccessful report has an EMPTY mask
+      if (!calibrated) {
+        if ((!F.success && !H.success) || (Fn < mni && Hn < mni)) {
+          res.config = 1;
+        } else {
+          const double H_F = (double)Hn / (double)Fn;
+          res.config = (H_F > o.max_H_inlier_ratio) ? 6 : 3;
+          best = 1;
+          num_inliers = Fn;
+          best_valid = F.success;
+        }
+      } else {
+        if ((!E.success && !F.success && !H.success) || (En < mni && Fn < mni && Hn < mni)) {
+          res.config = 1;
+        } else {
+          const double E_F = (double)En / (double)Fn;
+          const double H_F = (double)Hn / (double)Fn;
+          const double H_E = (double)Hn / (double)En;
+          if (E.success && E_F > o.min_E_F_inlier_ratio && En >= mni) {
+            if (En >= Fn) { num_inliers = En; best = 0; best_valid = E.success; }
+            else { num_inliers = Fn; best = 1; best_valid = F.success; }
+            if (H_E > o.max_H_inlier_ratio) {
+              res.config = 6;
+              if (Hn > num_inliers) { num_inliers = Hn; best = 2; best_valid = H.success; }
+            } else {
+              res.config = 2;
+            }
+          } else if (F.success && Fn >= mni) {
+            num_inliers = Fn; best = 1; best_valid = true;
+            if (H_F > o.max_H_inlier_ratio) {
+              res.config = 6;
+              if (Hn > num_inliers) { num_inliers = Hn; best = 2; best_valid = H.success; }
+            } else {
+              res.config = 3;
+            }
+          } else if (H.success && Hn >= mni) {
+            num_inliers = Hn; best = 2; best_valid = true;
+            res.config = 6;
+          } else {
+            res.config = 1;
+          }
+        }
+      }
+      if (best >= 0 && res.config != 1) {
+        // ExtractInlierMatches (two_view_geometry.cc:54-66) in match order
+        const uint8_t* mk = sc.mask[best];
+        uint32_t* outm = A.inlier_out + 2 * moff;
+        int N = 0, nb_border = 0;
+        const double d1 = sqrt((double)(c1.width * c1.width + c1.height * c1.height));
+        const double d2 = sqrt((double)(c2.width * c2.width + c2.height * c2.height));
+        const double minx1 = o.watermark_border_size * d1, maxx1 = c1.width - minx1, maxy1 = c1.height - minx1;
+        const double minx2 = o.watermark_border_size * d2, maxx2 = c2.width - minx2, maxy2 = c2.height - minx2;
+        for (int i0 = 0; i0 < M; i0 += 32) {
+          const int i = i0 + lane;
+          const bool in = best_valid && (i < M) && mk[i];
+          const unsigned bm = __ballot_sync(kFull, in);
+          bool border = false;
+          if (in) {
+            const int pos = N + __popc(bm & ((1u << lane) - 1));
+            outm[2 * pos] = mt[2 * i];
+            outm[2 * pos + 1] = mt[2 * i + 1];
+            sc.ip1[pos] = sc.px1[i];
+            sc.ip2[pos] = sc.px2[i];
+            border = !in_box(sc.px1[i], minx1, maxx1, minx1, maxy1) && !in_box(sc.px2[i], minx2, maxx2, minx2, maxy2);
+          }
+          nb_border += __popc(__ballot_sync(kFull, border));
+          N += __popc(bm);
+        }
+        res.n_inliers = N;
+        __syncwarp();
+        if (o.detect_watermark) {
+          // DetectWatermark (:491-555); num_inliers is the report's count (== N when the mask is valid)
+          const double ratio = (double)nb_border / (double)num_inliers;
+          if (!(ratio < o.watermark_min_inlier_ratio)) {
+            RansacResult T;
+            ransac_warp(EST_T2, sc.ip1, sc.ip2, (int)num_inliers, o.max_error, o.watermark_min_inlier_ratio,
+                        o.confidence, o.min_num_trials, o.max_num_trials, sh, sig_sh, sc, sc.tmask, &T, lane);
+            const double inlier_ratio = (double)T.num_inliers / (double)num_inliers;
+            if (inlier_ratio >= o.watermark_min_inlier_ratio) res.config = 7;
+          }
+        }
+      }
+    }
+    if (lane == 0) A.results[p] = res;
+    __syncwarp();
+  }
+}
+
+// ----------------------------------------------------------------- test seams
+__global__ void score_models_kernel(int type, int n, const double2* P1, const double2* P2, int n_models,
+                                    const double* models, double max_res, int* counts, double* sums, uint8_t* masks) {
+  const int lane = threadIdx.x & 31;
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= n_models) return;
+  double model[9];
+  for (int k = 0; k < 9; ++k) model[k] = models[9 * w + k];
+  const int c = score_count(type, P1, P2, n, model, max_res, lane);
+  double s = score_sum(type, P1, P2, n, model, max_res, lane, masks + (size_t)w * n);
+  s = __shfl_sync(kFull, s, 0);
+  if (lane == 0) {
+    counts[w] = c;
+    sums[w] = s;
+  }
+}
+
+__global__ void debug_sample_stream_kernel(uint32_t seed, int total, int k, int n_trials, uint32_t* idx, int* out) {
+  __shared__ WarpShared sh;
+  if (threadIdx.x == 0) {
+    mt_seed(sh, seed);
+    for (int i = 0; i < total; ++i) idx[i] = i;
+    for (int t = 0; t < n_trials; ++t) {
+      for (uint32_t i = 0; i < (uint32_t)k; ++i) {
+        const uint32_t j = uniform_u32(sh, i, (uint32_t)(total - 1));
+        const uint32_t a = idx[i], b = idx[j];
+        idx[i] = b;
+        idx[j] = a;
+      }
+      for (int i = 0; i < k; ++i) out[t * k + i] = (int)idx[i];
+    }
+  }
+}
+
+__global__ void debug_solve_kernel(int type, int n, const double2* P1, const double2* P2, double* G, uint32_t* inl,
+                                   double* models, int* n_models) {
+  __shared__ WarpShared sh;
+  __shared__ double sig[9];
+  const int lane = threadIdx.x;
+  if (type == 3) {  // F 8-point local estimator on all n points
+    for (int i = lane; i < n; i += 32) inl[i] = i;
+    __syncwarp();
+    const int nm = local_estimate(EST_F7, P1, P2, inl, n, G, 2 * n, sh, sig, models, lane);
+    if (lane == 0) *n_models = nm;
+    return;
+  }
+  if (type <= 2 && n > min_samples(type)) {  // local estimators E5 / H on n points
+    for (int i = lane; i < n; i += 32) inl[i] = i;
+    __syncwarp();
+    const int nm = local_estimate(type, P1, P2, inl, n, G, 2 * n, sh, sig, models, lane);
+    if (lane == 0) *n_models = nm;
+    return;
+  }
+  if (lane == 0) {
+    double a[14], b[14], mm[90];
+    for (int i = 0; i < n; ++i) { a[2 * i] = P1[i].x; a[2 * i + 1] = P1[i].y; b[2 * i] = P2[i].x; b[2 * i + 1] = P2[i].y; }
+    int nm = 0;
+    if (type == EST_E5) nm = solve_e5(a, b, mm);
+    else if (type == EST_F7) nm = solve_f7(a, b, mm, models + 45);
+    else nm = solve_h4(a, b, mm);
+    for (int k = 0; k < 9 * nm; ++k) models[k] = mm[k];
+    *n_models = nm;
+  }
+}
+
+}  // namespace vf
+
+// ---------------------------------------------------------------- launchers
+size_t verify_scratch_stride(int m_cap) {
+  const size_t mc = (size_t)m_cap;
+  size_t b = mc * 16 * 6 + mc * 2 * 9 * 8 + 32 * 90 * 8 + 90 * 8 + mc * 4 * 2 + mc * 4;
+  return (b + 255) / 256 * 256;
+}
+int verify_warps_per_block() { return vf::kWarpsPerBlock; }
+
+cudaError_t launch_normalize_points(const b2_camera* cams, const int64_t* img_off, int n_images, const double* xy,
+                                    double* nxy, int64_t n_total, cudaStream_t s) {
+  if (n_total == 0) return cudaSuccess;
+  vf::normalize_points_kernel<<<(unsigned)((n_total + 127) / 128), 128, 0, s>>>(
+      cams, img_off, n_images, (const double2*)xy, (double2*)nxy, n_total);
+  return cudaGetLastError();
+}
+cudaError_t launch_verify_pairs(const VerifyArgs& a, int n_blocks, cudaStream_t s) {
+  vf::verify_pairs_kernel<<<n_blocks, 32 * vf::kWarpsPerBlock, 0, s>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_score_models(int type, int n, const double* p1, const double* p2, int n_models, const double* models,
+                                double max_res, int* counts, double* sums, uint8_t* masks, cudaStream_t s) {
+  if (n_models == 0) return cudaSuccess;
+  vf::score_models_kernel<<<(n_models + 3) / 4, 128, 0, s>>>(type, n, (const double2*)p1, (const double2*)p2, n_models,
+                                                              models, max_res, counts, sums, masks);
+  return cudaGetLastError();
+}
+cudaError_t launch_debug_sample_stream(uint32_t seed, int total, int k, int n_trials, uint32_t* idx, int* out,
+                                       cudaStream_t s) {
+  vf::debug_sample_stream_kernel<<<1, 32, 0, s>>>(seed, total, k, n_trials, idx, out);
+  return cudaGetLastError();
+}
+cudaError_t launch_debug_solve(int type, int n, const double* p1, const double* p2, double* G, uint32_t* inl,
+                               double* models, int* n_models, cudaStream_t s) {
+  vf::debug_solve_kernel<<<1, 32, 0, s>>>(type, n, (const double2*)p1, (const double2*)p2, G, inl, models, n_models);
+  return cudaGetLastError();
+}
+
+}  // namespace b2

@@ -119,6 +119,92 @@ int b2_match_run(b2_matcher* m, const b2_match_options* opt,
 int b2_match_last_timing(b2_matcher* m, double* tc_kernel_s, double* all_kernels_s,
                          int64_t* tc_launches, int64_t* fixup_candidates);
 
+
+/* ================================================================= VERIFY ==
+ * Replaces: TwoViewGeometry::Estimate (src/estimators/two_view_geometry.h:180-184,
+ * .cc:113-126) as called by TwoViewGeometryVerifier::Run for every matched pair
+ * (src/feature/matching.cc:571-608): LO-RANSAC (src/optim/loransac.h:92-233) over
+ * E 5-point, F 7-point (LO 8-point) and H 4-point DLT with Sampson / transfer
+ * residuals, the configuration decision of EstimateCalibrated / EstimateUncalibrated
+ * (two_view_geometry.cc:292-489) and DetectWatermark (:491-555).
+ * NOT included (stays with the caller): the relative pose / triangulation
+ * angle of EstimateWithRelativePose (:232-290).
+ *
+ * The reference's verifier threads never seed their PRNG (src/util/random.cc:46-49), so
+ * it is itself run-to-run random; here every pair carries an explicit seed that
+ * initialises a std::mt19937-identical stream consumed E -> F -> H -> watermark.
+ */
+typedef struct b2_verifier b2_verifier;
+
+typedef struct b2_camera {          /* Camera (src/base/camera.h) reduced to what the path reads */
+  int32_t model;                    /* 0 SIMPLE_PINHOLE f,cx,cy | 1 PINHOLE fx,fy,cx,cy | 2 SIMPLE_RADIAL f,cx,cy,k */
+  int32_t width, height;
+  int32_t has_prior_focal_length;   /* Camera::HasPriorFocalLength() */
+  double params[12];
+} b2_camera;
+
+typedef struct b2_two_view_options { /* TwoViewGeometry::Options + RANSACOptions */
+  int32_t min_num_inliers;           /* 15   (two_view_geometry.h:82, sift.h:158) */
+  int32_t detect_watermark;          /* 1    (two_view_geometry.h:98)             */
+  double min_E_F_inlier_ratio;       /* 0.95 */
+  double max_H_inlier_ratio;         /* 0.8  */
+  double watermark_min_inlier_ratio; /* 0.7  */
+  double watermark_border_size;      /* 0.1  */
+  double max_error;                  /* 4.0 px  (sift.h:143)  */
+  double min_inlier_ratio;           /* 0.25    (sift.h:153)  */
+  double confidence;                 /* 0.999   (sift.h:146)  */
+  int64_t min_num_trials;            /* 30      (sift.h:150)  */
+  int64_t max_num_trials;            /* 10000   (sift.h:151)  */
+} b2_two_view_options;
+
+typedef struct b2_two_view_result {  /* public fields of TwoViewGeometry (two_view_geometry.h:278-301) */
+  int32_t config;                    /* ConfigurationType: 1 DEGENERATE 2 CALIBRATED 3 UNCALIBRATED
+                                        6 PLANAR_OR_PANORAMIC 7 WATERMARK */
+  int32_t n_inliers;                 /* inlier_matches.size() */
+  int32_t E_num_inliers, F_num_inliers, H_num_inliers;
+  int32_t E_num_trials, F_num_trials, H_num_trials;
+  double E[9], F[9], H[9];           /* row-major */
+} b2_two_view_result;
+
+void b2_two_view_default_options(b2_two_view_options* opt);
+int b2_verify_create(int device, b2_verifier** out);
+int b2_verify_destroy(b2_verifier* v);
+/* Cameras + keypoint locations (x,y as double, i.e. FeatureKeypointsToPointsVector,
+ * src/feature/utils.cc:38-45) of all images, HOST pointers; copied to HBM, where the
+ * normalised coordinates Camera::ImageToWorld (incl. IterativeUndistortion,
+ * src/base/camera_models.h:547-590) are computed once per keypoint. */
+int b2_verify_set_images(b2_verifier* v, int32_t n_images, const b2_camera* cams,
+                         const double* const* xy, const int32_t* n_pts);
+/* Verifies n_pairs pairs.  HOST buffers: pairs [n][2]; match_offsets [n+1] and matches
+ * [total][2] exactly as b2_match_pairs produces them; seeds [n]; results [n];
+ * inlier_matches [total][2]: the inliers of pair p are written at match_offsets[p]
+ * (results[p].n_inliers of them, in match order). */
+int b2_verify_pairs(b2_verifier* v, int64_t n_pairs, const uint32_t* pairs,
+                    const int64_t* match_offsets, const uint32_t* matches,
+                    const b2_two_view_options* opt, const uint32_t* seeds,
+                    b2_two_view_result* results, uint32_t* inlier_matches);
+/* Same with every buffer in DEVICE memory (chains onto b2_match_pairs_device). */
+int b2_verify_pairs_device(b2_verifier* v, int64_t n_pairs, const uint32_t* pairs_dev,
+                           const int64_t* match_offsets_dev, const uint32_t* matches_dev,
+                           const b2_two_view_options* opt, const uint32_t* seeds_dev,
+                           b2_two_view_result* results_dev, uint32_t* inlier_matches_dev);
+/* Kernel-level seam == Estimator::Residuals + InlierSupportMeasurer::Evaluate
+ * (src/optim/support_measurement.cc:36-48) for n_models models over n points (HOST buffers).
+ * type: 0/1 Sampson (E/F), 2 homography transfer.  counts[n_models], sums[n_models]
+ * (residual sum in index order), masks[n_models][n] bytes. */
+int b2_score_models(b2_verifier* v, int32_t type, int32_t n, const double* xy1, const double* xy2,
+                    int32_t n_models, const double* models, double max_residual,
+                    int32_t* counts, double* sums, uint8_t* masks);
+/* Test hook: the sampler's index stream (RandomSampler over std::mt19937(seed)), n_trials x k. */
+int b2_verify_debug_sample_stream(b2_verifier* v, uint32_t seed, int32_t total, int32_t k,
+                                  int32_t n_trials, int32_t* out);
+/* Test hook: the minimal / local solvers on one point set. type 0 E5, 1 F7, 2 H4, 3 F8(LO).
+ * models_out [10][9]; returns the model count in *n_models. */
+int b2_verify_debug_solve(b2_verifier* v, int32_t type, int32_t n, const double* xy1,
+                          const double* xy2, double* models_out, int32_t* n_models);
+/* Device seconds (CUDA events) of the last b2_verify_pairs* call. */
+int b2_verify_last_timing(b2_verifier* v, double* kernel_s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -711,14 +711,15 @@ static std::vector<Mat3> Translation2(const std::vector<Vec2>& p1, const std::ve
   for (size_t i = 0; i < p1.size(); ++i) { sx += p1[i].x; sy += p1[i].y; dx += p2[i].x; dy += p2[i].y; }
   Mat3 M;
   memset(M.m, 0, sizeof M.m);
-  M.m[0] = (dx - sx) / p1.size();
-  M.m[1] = (dy - sy) / p1.size();
+  sx /= p1.size(); sy /= p1.size(); dx /= p2.size(); dy /= p2.size();  // mean_src, mean_dst
+  M.m[0] = dx - sx;
+  M.m[1] = dy - sy;
   return {M};
 }
 static void TranslationResiduals(const std::vector<Vec2>& p1, const std::vector<Vec2>& p2, const Mat3& M, std::vector<double>* res) {
   res->resize(p1.size());
   for (size_t i = 0; i < p1.size(); ++i) {
-    const double ex = p2[i].x - (p1[i].x + M.m[0]), ey = p2[i].y - (p1[i].y + M.m[1]);
+    const double ex = (p2[i].x - p1[i].x) - M.m[0], ey = (p2[i].y - p1[i].y) - M.m[1];
     (*res)[i] = ex * ex + ey * ey;
   }
 }
