@@ -1,0 +1,583 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY.  Never imported, linked or executed by the
+// product path (dagsfm_b200/); only tests/, __graft_entry__.smoke() and bench.py's
+// cpu_baseline / --impl reference legs may use it.
+//
+// CPU restatement (FP64) of the reference's bundle adjustment as it is configured for
+// the final global BA:
+//   src/base/cost_functions.h:44-88     BundleAdjustmentCostFunction (variable pose)
+//   src/base/cost_functions.h:90-158    BundleAdjustmentConstantPoseCostFunction
+//   src/base/camera_models.h:714-757    SIMPLE_RADIAL WorldToImage (+ SIMPLE_PINHOLE, PINHOLE)
+//   src/optim/bundle_adjustment.cc:338-526 AddImageToProblem / ParameterizeCameras / Points
+//     (QuaternionParameterization on qvec, SubsetParameterization on tvec and intrinsics,
+//      constant cameras / poses / points)
+//   src/optim/bundle_adjustment.cc:258-310 Solve -> ceres::Solve
+//   src/controllers/distributed_mapper_controller.cpp:522-542 GlobalBundleAdjustment options
+// The arithmetic of the solve lives in Ceres Solver -- a third-party dependency that is NOT
+// under /root/reference (find_package(Ceres), CMakeLists.txt:87; docker/Dockerfile:35 pins
+// 1.14.0) and is not installed here.  Restated from its published algorithm and defaults
+// (trust_region_minimizer.cc, levenberg_marquardt_strategy.cc, schur_complement_solver.cc,
+// rotation.h, local_parameterization.cc of Ceres 1.14): Levenberg-Marquardt trust region,
+// Jacobi column scaling 1/(1+|col|), diagonal clamp [1e-6, 1e32], radius 1e4 / update rule,
+// min_relative_decrease 1e-3, exact Schur-complement step (DENSE/SPARSE_SCHUR).
+// The Jacobian is analytic (Ceres uses autodiff of the same formulas); tests check it
+// against central differences.
+// PARITY UNPINNED: the reference's tests pin only structure (num_residuals_reduced,
+// num_effective_parameters_reduced, which blocks move: bundle_adjustment_test.cc:186-645)
+// and four residual values (cost_functions_test.cc:41-98) -- replayed in
+// tests/test_oracle_ba.py -- not the numeric result of a solve.  The vendored PBA built
+// into oracle/_ref is the reference-owned convergence check / CPU timing baseline.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+namespace ba {
+
+// ----------------------------------------------------------------- camera models
+static int NumParams(int model) { return model == 0 ? 3 : 4; }
+// focal / principal / extra parameter index sets (camera_models.h Initialize*Idxs)
+static void ParamKinds(int model, int kind[4]) {  // 0 focal, 1 principal point, 2 extra
+  if (model == 0) { kind[0] = 0; kind[1] = 1; kind[2] = 1; kind[3] = -1; }
+  else if (model == 1) { kind[0] = 0; kind[1] = 0; kind[2] = 1; kind[3] = 1; }
+  else { kind[0] = 0; kind[1] = 1; kind[2] = 1; kind[3] = 2; }
+}
+
+// residual + Jacobians of one observation.
+// q (w,x,y,z), t, X, params -> r[2]; Jq 2x3 (local, after the 4x3 parameterization Jacobian),
+// Jt 2x3, JX 2x3, Jk 2x4.
+static void Evaluate(int model, const double* q, const double* t, const double* X, const double* k, const double* obs,
+                     double* r, double* Jq, double* Jt, double* JX, double* Jk) {
+  const double w = q[0], x = q[1], y = q[2], z = q[3];
+  // ceres::UnitQuaternionRotatePoint
+  const double t2 = w * x, t3 = w * y, t4 = w * z, t5 = -x * x, t6 = x * y, t7 = x * z, t8 = -y * y, t9 = y * z,
+               t1 = -z * z;
+  double p[3];
+  p[0] = 2 * ((t8 + t1) * X[0] + (t6 - t4) * X[1] + (t3 + t7) * X[2]) + X[0];
+  p[1] = 2 * ((t4 + t6) * X[0] + (t5 + t1) * X[1] + (t9 - t2) * X[2]) + X[1];
+  p[2] = 2 * ((t7 - t3) * X[0] + (t2 + t9) * X[1] + (t5 + t8) * X[2]) + X[2];
+  p[0] += t[0];
+  p[1] += t[1];
+  p[2] += t[2];
+  const double u = p[0] / p[2], v = p[1] / p[2];
+  double xi, yi;          // image point
+  double dxdu, dxdv, dydu, dydv;
+  double dk[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+  if (model == 0) {
+    xi = k[0] * u + k[1]; yi = k[0] * v + k[2];
+    dxdu = k[0]; dxdv = 0; dydu = 0; dydv = k[0];
+    dk[0][0] = u; dk[0][1] = 1; dk[1][0] = v; dk[1][2] = 1;
+  } else if (model == 1) {
+    xi = k[0] * u + k[2]; yi = k[1] * v + k[3];
+    dxdu = k[0]; dxdv = 0; dydu = 0; dydv = k[1];
+    dk[0][0] = u; dk[0][2] = 1; dk[1][1] = v; dk[1][3] = 1;
+  } else {
+    const double u2 = u * u, v2 = v * v, r2 = u2 + v2, radial = k[3] * r2;
+    const double du = u * radial, dv = v * radial;
+    const double xd = u + du, yd = v + dv;
+    xi = k[0] * xd + k[1]; yi = k[0] * yd + k[2];
+    dxdu = k[0] * (1 + radial + 2 * k[3] * u2); dxdv = k[0] * (2 * k[3] * u * v);
+    dydu = k[0] * (2 * k[3] * u * v); dydv = k[0] * (1 + radial + 2 * k[3] * v2);
+    dk[0][0] = xd; dk[0][1] = 1; dk[0][3] = k[0] * u * r2;
+    dk[1][0] = yd; dk[1][2] = 1; dk[1][3] = k[0] * v * r2;
+  }
+  r[0] = xi - obs[0];
+  r[1] = yi - obs[1];
+  if (!Jq) return;
+  // d(u,v)/dp
+  const double ip2 = 1.0 / p[2];
+  const double dudp[3] = {ip2, 0, -p[0] * ip2 * ip2}, dvdp[3] = {0, ip2, -p[1] * ip2 * ip2};
+  double drdp[2][3];
+  for (int c = 0; c < 3; ++c) {
+    drdp[0][c] = dxdu * dudp[c] + dxdv * dvdp[c];
+    drdp[1][c] = dydu * dudp[c] + dydv * dvdp[c];
+  }
+  // dp/dX = 2M + I (the rotation matrix of the formula)
+  const double R[3][3] = {{2 * (t8 + t1) + 1, 2 * (t6 - t4), 2 * (t3 + t7)},
+                          {2 * (t4 + t6), 2 * (t5 + t1) + 1, 2 * (t9 - t2)},
+                          {2 * (t7 - t3), 2 * (t2 + t9), 2 * (t5 + t8) + 1}};
+  for (int i = 0; i < 2; ++i)
+    for (int c = 0; c < 3; ++c) {
+      JX[3 * i + c] = drdp[i][0] * R[0][c] + drdp[i][1] * R[1][c] + drdp[i][2] * R[2][c];
+      Jt[3 * i + c] = drdp[i][c];
+    }
+  // dp/dq (3x4): 2 * dM/dq_k * X
+  const double X0 = X[0], X1 = X[1], X2 = X[2];
+  const double dpdq[3][4] = {
+      {2 * (-z * X1 + y * X2), 2 * (y * X1 + z * X2), 2 * (-2 * y * X0 + x * X1 + w * X2), 2 * (-2 * z * X0 - w * X1 + x * X2)},
+      {2 * (z * X0 - x * X2), 2 * (y * X0 - 2 * x * X1 - w * X2), 2 * (x * X0 + z * X2), 2 * (w * X0 - 2 * z * X1 + y * X2)},
+      {2 * (-y * X0 + x * X1), 2 * (z * X0 + w * X1 - 2 * x * X2), 2 * (-w * X0 + z * X1 - 2 * y * X2), 2 * (x * X0 + y * X1)}};
+  // QuaternionParameterization::ComputeJacobian (4x3)
+  const double JL[4][3] = {{-x, -y, -z}, {w, z, -y}, {-z, w, x}, {y, -x, w}};
+  for (int i = 0; i < 2; ++i) {
+    double drdq[4];
+    for (int a = 0; a < 4; ++a) drdq[a] = drdp[i][0] * dpdq[0][a] + drdp[i][1] * dpdq[1][a] + drdp[i][2] * dpdq[2][a];
+    for (int c = 0; c < 3; ++c)
+      Jq[3 * i + c] = drdq[0] * JL[0][c] + drdq[1] * JL[1][c] + drdq[2] * JL[2][c] + drdq[3] * JL[3][c];
+    for (int a = 0; a < 4; ++a) Jk[4 * i + a] = dk[i][a];
+  }
+}
+
+// QuaternionParameterization::Plus
+static void QuatPlus(const double* x, const double* delta, double* out) {
+  const double nd = std::sqrt(delta[0] * delta[0] + delta[1] * delta[1] + delta[2] * delta[2]);
+  if (nd > 0.0) {
+    const double s = std::sin(nd) / nd;
+    const double qd[4] = {std::cos(nd), s * delta[0], s * delta[1], s * delta[2]};
+    // QuaternionProduct(q_delta, x)
+    out[0] = qd[0] * x[0] - qd[1] * x[1] - qd[2] * x[2] - qd[3] * x[3];
+    out[1] = qd[0] * x[1] + qd[1] * x[0] + qd[2] * x[3] - qd[3] * x[2];
+    out[2] = qd[0] * x[2] - qd[1] * x[3] + qd[2] * x[0] + qd[3] * x[1];
+    out[3] = qd[0] * x[3] + qd[1] * x[2] - qd[2] * x[1] + qd[3] * x[0];
+  } else {
+    for (int i = 0; i < 4; ++i) out[i] = x[i];
+  }
+}
+
+struct Problem {
+  int n_img, n_cam, n_pts;
+  long n_obs;
+  double *qvec, *tvec;        // [n_img*4], [n_img*3]
+  const int* img_cam;         // camera of each image
+  const uint8_t* pose_const;  // 1 = constant pose
+  const uint8_t* tvec_const;  // bitmask of constant tvec components
+  const int* cam_model;
+  double* cam_params;         // [n_cam*4]
+  const uint8_t* cam_const;   // 1 = whole camera constant
+  int refine_focal, refine_principal, refine_extra;
+  double* xyz;
+  const uint8_t* pt_const;
+  const int *obs_img, *obs_pt;  // sorted by point
+  const double* obs_xy;
+};
+struct Options {
+  int max_num_iterations;
+  double function_tolerance, gradient_tolerance, parameter_tolerance;
+  int n_threads;
+};
+struct Summary {
+  double initial_cost, final_cost;
+  int num_successful_steps, num_unsuccessful_steps, termination;  // 0 convergence, 1 no convergence, 2 failure
+  int num_residuals, num_effective_parameters;
+  double seconds;
+};
+
+struct Layout {
+  std::vector<int> pose_col;  // [n_img*6], -1 = constant
+  std::vector<int> intr_col;  // [n_cam*4]
+  std::vector<int> pt_col;    // [n_pts] first of 3, -1 = constant (relative to the point block)
+  int n_cam_cols = 0, n_pt_var = 0;
+};
+
+static Layout MakeLayout(const Problem& P) {
+  Layout L;
+  L.pose_col.assign((size_t)P.n_img * 6, -1);
+  L.intr_col.assign((size_t)P.n_cam * 4, -1);
+  L.pt_col.assign(P.n_pts, -1);
+  int c = 0;
+  // which cameras / images / points actually appear
+  std::vector<char> img_used(P.n_img, 0), cam_used(P.n_cam, 0), pt_used(P.n_pts, 0);
+  for (long o = 0; o < P.n_obs; ++o) { img_used[P.obs_img[o]] = 1; cam_used[P.img_cam[P.obs_img[o]]] = 1; pt_used[P.obs_pt[o]] = 1; }
+  for (int i = 0; i < P.n_img; ++i) {
+    if (!img_used[i] || P.pose_const[i]) continue;
+    for (int k = 0; k < 3; ++k) L.pose_col[6 * i + k] = c++;
+    for (int k = 0; k < 3; ++k)
+      if (!(P.tvec_const[i] & (1 << k))) L.pose_col[6 * i + 3 + k] = c++;
+  }
+  for (int cm = 0; cm < P.n_cam; ++cm) {
+    if (!cam_used[cm] || P.cam_const[cm]) continue;
+    int kind[4];
+    ParamKinds(P.cam_model[cm], kind);
+    for (int k = 0; k < NumParams(P.cam_model[cm]); ++k) {
+      const bool var = (kind[k] == 0 && P.refine_focal) || (kind[k] == 1 && P.refine_principal) || (kind[k] == 2 && P.refine_extra);
+      if (var) L.intr_col[4 * cm + k] = c++;
+    }
+  }
+  L.n_cam_cols = c;
+  int pv = 0;
+  for (int p = 0; p < P.n_pts; ++p)
+    if (pt_used[p] && !P.pt_const[p]) L.pt_col[p] = pv++;
+  L.n_pt_var = pv;
+  return L;
+}
+
+// In-place Cholesky (lower) of the dense SPD matrix A (n x n row-major); returns false if not PD.
+static bool CholeskySolve(std::vector<double>& A, int n, std::vector<double>& b) {
+  const int NB = 64;
+  for (int k0 = 0; k0 < n; k0 += NB) {
+    const int kb = std::min(NB, n - k0);
+    for (int j = k0; j < k0 + kb; ++j) {  // factor the diagonal block and the panel below it column by column
+      double d = A[(size_t)j * n + j];
+      for (int k = k0; k < j; ++k) d -= A[(size_t)j * n + k] * A[(size_t)j * n + k];
+      if (!(d > 0)) return false;
+      d = std::sqrt(d);
+      A[(size_t)j * n + j] = d;
+#pragma omp parallel for schedule(static)
+      for (int i = j + 1; i < n; ++i) {
+        double s = A[(size_t)i * n + j];
+        for (int k = k0; k < j; ++k) s -= A[(size_t)i * n + k] * A[(size_t)j * n + k];
+        A[(size_t)i * n + j] = s / d;
+      }
+    }
+    const int r0 = k0 + kb;  // trailing update A22 -= L21 L21^T (lower part)
+#pragma omp parallel for schedule(dynamic, 8)
+    for (int i = r0; i < n; ++i) {
+      const double* li = &A[(size_t)i * n + k0];
+      for (int j = r0; j <= i; ++j) {
+        const double* lj = &A[(size_t)j * n + k0];
+        double s = 0;
+        for (int k = 0; k < kb; ++k) s += li[k] * lj[k];
+        A[(size_t)i * n + j] -= s;
+      }
+    }
+  }
+  for (int i = 0; i < n; ++i) {
+    double s = b[i];
+    for (int k = 0; k < i; ++k) s -= A[(size_t)i * n + k] * b[k];
+    b[i] = s / A[(size_t)i * n + i];
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    double s = b[i];
+    for (int k = i + 1; k < n; ++k) s -= A[(size_t)k * n + i] * b[k];
+    b[i] = s / A[(size_t)i * n + i];
+  }
+  return true;
+}
+
+struct ObsJ { double r[2]; double Jc[2][10]; double Jp[2][3]; int col[10]; };
+
+struct Solver {
+  Problem P;
+  Options O;
+  Layout L;
+  std::vector<long> pt_start;      // CSR by point
+  std::vector<double> scale_c, scale_p;  // Jacobi column scaling
+  std::vector<ObsJ> J;
+
+  double EvalCost(const double* q, const double* t, const double* kp, const double* X) const {
+    double cost = 0;
+#pragma omp parallel for reduction(+ : cost) schedule(static)
+    for (long o = 0; o < P.n_obs; ++o) {
+      const int i = P.obs_img[o], p = P.obs_pt[o], c = P.img_cam[i];
+      double r[2];
+      Evaluate(P.cam_model[c], q + 4 * i, t + 3 * i, X + 3 * p, kp + 4 * c, P.obs_xy + 2 * o, r, nullptr, nullptr, nullptr, nullptr);
+      cost += r[0] * r[0] + r[1] * r[1];
+    }
+    return 0.5 * cost;
+  }
+  void EvalJacobian(bool scaled) {
+#pragma omp parallel for schedule(static)
+    for (long o = 0; o < P.n_obs; ++o) {
+      const int i = P.obs_img[o], p = P.obs_pt[o], c = P.img_cam[i];
+      double Jq[6], Jt[6], JX[6], Jk[8];
+      ObsJ& e = J[o];
+      Evaluate(P.cam_model[c], P.qvec + 4 * i, P.tvec + 3 * i, P.xyz + 3 * p, P.cam_params + 4 * c, P.obs_xy + 2 * o, e.r, Jq, Jt, JX, Jk);
+      for (int k = 0; k < 6; ++k) e.col[k] = L.pose_col[6 * i + k];
+      for (int k = 0; k < 4; ++k) e.col[6 + k] = L.intr_col[4 * c + k];
+      for (int a = 0; a < 2; ++a) {
+        for (int k = 0; k < 3; ++k) { e.Jc[a][k] = Jq[3 * a + k]; e.Jc[a][3 + k] = Jt[3 * a + k]; e.Jp[a][k] = JX[3 * a + k]; }
+        for (int k = 0; k < 4; ++k) e.Jc[a][6 + k] = Jk[4 * a + k];
+        for (int k = 0; k < 10; ++k) {
+          if (e.col[k] < 0) e.Jc[a][k] = 0;
+          else if (scaled) e.Jc[a][k] *= scale_c[e.col[k]];
+        }
+        if (L.pt_col[p] < 0) { e.Jp[a][0] = e.Jp[a][1] = e.Jp[a][2] = 0; }
+        else if (scaled) for (int k = 0; k < 3; ++k) e.Jp[a][k] *= scale_p[3 * L.pt_col[p] + k];
+      }
+    }
+  }
+};
+
+static void Solve(Problem P, Options O, Summary* S) {
+  const auto t_start = std::chrono::steady_clock::now();
+  Solver sv;
+  sv.P = P;
+  sv.O = O;
+  sv.L = MakeLayout(P);
+  const Layout& L = sv.L;
+  const int D = L.n_cam_cols;
+  const int NP = L.n_pt_var;
+  // image.NormalizeQvec() (bundle_adjustment.cc:345)
+  for (int i = 0; i < P.n_img; ++i) {
+    double* q = P.qvec + 4 * i;
+    const double n = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    if (n > 0) for (int k = 0; k < 4; ++k) q[k] /= n;
+  }
+  sv.pt_start.assign(P.n_pts + 1, 0);
+  for (long o = 0; o < P.n_obs; ++o) sv.pt_start[P.obs_pt[o] + 1]++;
+  for (int p = 0; p < P.n_pts; ++p) sv.pt_start[p + 1] += sv.pt_start[p];
+  sv.J.resize(P.n_obs);
+  sv.scale_c.assign(std::max(D, 1), 1.0);
+  sv.scale_p.assign(std::max(3 * NP, 1), 1.0);
+  S->num_residuals = (int)(2 * P.n_obs);
+  S->num_effective_parameters = D + 3 * NP;
+  S->num_successful_steps = S->num_unsuccessful_steps = 0;
+  S->termination = 1;
+  if (P.n_obs == 0) { S->initial_cost = S->final_cost = 0; S->seconds = 0; return; }
+
+  // initial evaluation + Jacobi scaling (scale = 1 / (1 + column norm))
+  sv.EvalJacobian(false);
+  {
+    std::vector<double> nc(std::max(D, 1), 0.0), np(std::max(3 * NP, 1), 0.0);
+    for (long o = 0; o < P.n_obs; ++o) {
+      const ObsJ& e = sv.J[o];
+      const int pc = L.pt_col[P.obs_pt[o]];
+      for (int a = 0; a < 2; ++a) {
+        for (int k = 0; k < 10; ++k) if (e.col[k] >= 0) nc[e.col[k]] += e.Jc[a][k] * e.Jc[a][k];
+        if (pc >= 0) for (int k = 0; k < 3; ++k) np[3 * pc + k] += e.Jp[a][k] * e.Jp[a][k];
+      }
+    }
+    for (int j = 0; j < D; ++j) sv.scale_c[j] = 1.0 / (1.0 + std::sqrt(nc[j]));
+    for (int j = 0; j < 3 * NP; ++j) sv.scale_p[j] = 1.0 / (1.0 + std::sqrt(np[j]));
+  }
+  double cost = 0;
+  for (long o = 0; o < P.n_obs; ++o) cost += sv.J[o].r[0] * sv.J[o].r[0] + sv.J[o].r[1] * sv.J[o].r[1];
+  cost *= 0.5;
+  S->initial_cost = cost;
+  sv.EvalJacobian(true);
+
+  double radius = 1e4, decrease_factor = 2.0;
+  const double min_radius = 1e-32, max_radius = 1e16, min_rel_dec = 1e-3, min_diag = 1e-6, max_diag = 1e32;
+  std::vector<double> Smat, gc(std::max(D, 1)), dc(std::max(D, 1)), diag_c(std::max(D, 1)), diag_p(std::max(3 * NP, 1));
+  std::vector<double> Vinv((size_t)std::max(NP, 1) * 9), gp((size_t)std::max(3 * NP, 1)), dp((size_t)std::max(3 * NP, 1));
+  std::vector<double> qn(P.n_img * 4), tn(P.n_img * 3), kn(P.n_cam * 4), Xn(P.n_pts * 3);
+  bool need_grad_check = true;
+
+  for (int iter = 0; iter < O.max_num_iterations; ++iter) {
+    // diag(J^T J) and gradient (scaled Jacobian)
+    std::fill(diag_c.begin(), diag_c.end(), 0.0);
+    std::fill(diag_p.begin(), diag_p.end(), 0.0);
+    std::fill(gc.begin(), gc.end(), 0.0);
+    std::fill(gp.begin(), gp.end(), 0.0);
+    for (long o = 0; o < P.n_obs; ++o) {
+      const ObsJ& e = sv.J[o];
+      const int pc = L.pt_col[P.obs_pt[o]];
+      for (int a = 0; a < 2; ++a) {
+        for (int k = 0; k < 10; ++k)
+          if (e.col[k] >= 0) { diag_c[e.col[k]] += e.Jc[a][k] * e.Jc[a][k]; gc[e.col[k]] += e.Jc[a][k] * e.r[a]; }
+        if (pc >= 0) for (int k = 0; k < 3; ++k) { diag_p[3 * pc + k] += e.Jp[a][k] * e.Jp[a][k]; gp[3 * pc + k] += e.Jp[a][k] * e.r[a]; }
+      }
+    }
+    if (need_grad_check) {  // gradient_max_norm of the unscaled problem
+      double gmax = 0;
+      for (int j = 0; j < D; ++j) gmax = std::max(gmax, std::abs(gc[j] / sv.scale_c[j]));
+      for (int j = 0; j < 3 * NP; ++j) gmax = std::max(gmax, std::abs(gp[j] / sv.scale_p[j]));
+      if (gmax <= O.gradient_tolerance) { S->termination = 0; break; }
+      need_grad_check = false;
+    }
+    // LM diagonal D^2 = clamp(diag) / radius
+    std::vector<double> lm_c(D), lm_p(3 * NP);
+    for (int j = 0; j < D; ++j) lm_c[j] = std::min(std::max(diag_c[j], min_diag), max_diag) / radius;
+    for (int j = 0; j < 3 * NP; ++j) lm_p[j] = std::min(std::max(diag_p[j], min_diag), max_diag) / radius;
+    // Schur complement: S = U + D_c - sum_p W V^-1 W^T ; rhs = g_c - sum_p W V^-1 g_p
+    Smat.assign((size_t)D * D, 0.0);
+    std::vector<double> rhs(gc.begin(), gc.begin() + D);
+    for (long o = 0; o < P.n_obs; ++o) {  // U blocks
+      const ObsJ& e = sv.J[o];
+      for (int k = 0; k < 10; ++k) {
+        if (e.col[k] < 0) continue;
+        for (int l = 0; l < 10; ++l) {
+          if (e.col[l] < 0) continue;
+          Smat[(size_t)e.col[k] * D + e.col[l]] += e.Jc[0][k] * e.Jc[0][l] + e.Jc[1][k] * e.Jc[1][l];
+        }
+      }
+    }
+    for (int j = 0; j < D; ++j) Smat[(size_t)j * D + j] += lm_c[j];
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int p = 0; p < P.n_pts; ++p) {
+      const int pc = L.pt_col[p];
+      if (pc < 0) continue;
+      double V[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+      for (long o = sv.pt_start[p]; o < sv.pt_start[p + 1]; ++o) {
+        const ObsJ& e = sv.J[o];
+        for (int a = 0; a < 2; ++a)
+          for (int k = 0; k < 3; ++k)
+            for (int l = 0; l < 3; ++l) V[k][l] += e.Jp[a][k] * e.Jp[a][l];
+      }
+      for (int k = 0; k < 3; ++k) V[k][k] += lm_p[3 * pc + k];
+      // inverse of the symmetric 3x3
+      const double c00 = V[1][1] * V[2][2] - V[1][2] * V[2][1], c01 = V[1][2] * V[2][0] - V[1][0] * V[2][2],
+                   c02 = V[1][0] * V[2][1] - V[1][1] * V[2][0];
+      const double det = V[0][0] * c00 + V[0][1] * c01 + V[0][2] * c02, id = 1.0 / det;
+      double* Vi = &Vinv[(size_t)pc * 9];
+      Vi[0] = c00 * id; Vi[1] = (V[0][2] * V[2][1] - V[0][1] * V[2][2]) * id; Vi[2] = (V[0][1] * V[1][2] - V[0][2] * V[1][1]) * id;
+      Vi[3] = c01 * id; Vi[4] = (V[0][0] * V[2][2] - V[0][2] * V[2][0]) * id; Vi[5] = (V[0][2] * V[1][0] - V[0][0] * V[1][2]) * id;
+      Vi[6] = c02 * id; Vi[7] = (V[0][1] * V[2][0] - V[0][0] * V[2][1]) * id; Vi[8] = (V[0][0] * V[1][1] - V[0][1] * V[1][0]) * id;
+      double tp[3];
+      for (int k = 0; k < 3; ++k) tp[k] = Vi[3 * k] * gp[3 * pc] + Vi[3 * k + 1] * gp[3 * pc + 1] + Vi[3 * k + 2] * gp[3 * pc + 2];
+      const long o0 = sv.pt_start[p], nL = sv.pt_start[p + 1] - o0;
+      std::vector<double> W((size_t)nL * 30), Y((size_t)nL * 30);
+      for (long a = 0; a < nL; ++a) {
+        const ObsJ& e = sv.J[o0 + a];
+        double* Wa = &W[a * 30];
+        double* Ya = &Y[a * 30];
+        for (int k = 0; k < 10; ++k)
+          for (int l = 0; l < 3; ++l) Wa[3 * k + l] = e.Jc[0][k] * e.Jp[0][l] + e.Jc[1][k] * e.Jp[1][l];
+        for (int k = 0; k < 10; ++k)
+          for (int l = 0; l < 3; ++l) Ya[3 * k + l] = Wa[3 * k] * Vi[l] + Wa[3 * k + 1] * Vi[3 + l] + Wa[3 * k + 2] * Vi[6 + l];
+        for (int k = 0; k < 10; ++k) {
+          if (e.col[k] < 0) continue;
+          const double v = Wa[3 * k] * tp[0] + Wa[3 * k + 1] * tp[1] + Wa[3 * k + 2] * tp[2];
+#pragma omp atomic
+          rhs[e.col[k]] -= v;
+        }
+      }
+      for (long a = 0; a < nL; ++a) {
+        const ObsJ& ea = sv.J[o0 + a];
+        const double* Ya = &Y[a * 30];
+        for (long b = 0; b < nL; ++b) {
+          const ObsJ& eb = sv.J[o0 + b];
+          const double* Wb = &W[b * 30];
+          for (int k = 0; k < 10; ++k) {
+            if (ea.col[k] < 0) continue;
+            for (int l = 0; l < 10; ++l) {
+              if (eb.col[l] < 0) continue;
+              const double v = Ya[3 * k] * Wb[3 * l] + Ya[3 * k + 1] * Wb[3 * l + 1] + Ya[3 * k + 2] * Wb[3 * l + 2];
+#pragma omp atomic
+              Smat[(size_t)ea.col[k] * D + eb.col[l]] -= v;
+            }
+          }
+        }
+      }
+    }
+    // solve S y = rhs ; step_c = -y
+    bool ok = true;
+    if (D > 0) {
+      dc.assign(rhs.begin(), rhs.end());
+      ok = CholeskySolve(Smat, D, dc);
+      for (int j = 0; j < D; ++j) dc[j] = -dc[j];
+    }
+    if (ok) {
+      // back-substitution: dp = -V^-1 (g_p + W^T dc)
+#pragma omp parallel for schedule(static)
+      for (int p = 0; p < P.n_pts; ++p) {
+        const int pc = L.pt_col[p];
+        if (pc < 0) continue;
+        double s[3] = {gp[3 * pc], gp[3 * pc + 1], gp[3 * pc + 2]};
+        for (long o = sv.pt_start[p]; o < sv.pt_start[p + 1]; ++o) {
+          const ObsJ& e = sv.J[o];
+          for (int a = 0; a < 2; ++a) {
+            double jd = 0;
+            for (int k = 0; k < 10; ++k) if (e.col[k] >= 0) jd += e.Jc[a][k] * dc[e.col[k]];
+            for (int k = 0; k < 3; ++k) s[k] += e.Jp[a][k] * jd;
+          }
+        }
+        const double* Vi = &Vinv[(size_t)pc * 9];
+        for (int k = 0; k < 3; ++k) dp[3 * pc + k] = -(Vi[3 * k] * s[0] + Vi[3 * k + 1] * s[1] + Vi[3 * k + 2] * s[2]);
+      }
+    }
+    double model_cost_change = 0;
+    if (ok) {
+      for (long o = 0; o < P.n_obs; ++o) {
+        const ObsJ& e = sv.J[o];
+        const int pc = L.pt_col[P.obs_pt[o]];
+        for (int a = 0; a < 2; ++a) {
+          double m = 0;
+          for (int k = 0; k < 10; ++k) if (e.col[k] >= 0) m += e.Jc[a][k] * dc[e.col[k]];
+          if (pc >= 0) for (int k = 0; k < 3; ++k) m += e.Jp[a][k] * dp[3 * pc + k];
+          model_cost_change -= m * (e.r[a] + m / 2.0);
+        }
+      }
+      if (!(model_cost_change > 0)) ok = false;
+    }
+    if (!ok) {  // invalid step: shrink the trust region
+      S->num_unsuccessful_steps++;
+      radius /= decrease_factor;
+      decrease_factor *= 2.0;
+      if (radius < min_radius) { S->termination = 2; break; }
+      continue;
+    }
+    // candidate x_plus_delta (undo the Jacobi scaling)
+    double step_sq = 0, x_sq = 0;
+    qn.assign(P.qvec, P.qvec + P.n_img * 4);
+    tn.assign(P.tvec, P.tvec + P.n_img * 3);
+    kn.assign(P.cam_params, P.cam_params + P.n_cam * 4);
+    Xn.assign(P.xyz, P.xyz + P.n_pts * 3);
+    for (int i = 0; i < P.n_img; ++i) {
+      double d[3] = {0, 0, 0};
+      bool any = false;
+      for (int k = 0; k < 3; ++k) { const int c = L.pose_col[6 * i + k]; if (c >= 0) { d[k] = dc[c] * sv.scale_c[c]; any = true; step_sq += d[k] * d[k]; } }
+      if (any) QuatPlus(P.qvec + 4 * i, d, &qn[4 * i]);
+      for (int k = 0; k < 3; ++k) { const int c = L.pose_col[6 * i + 3 + k]; if (c >= 0) { const double v = dc[c] * sv.scale_c[c]; tn[3 * i + k] += v; step_sq += v * v; } }
+    }
+    for (int cm = 0; cm < P.n_cam; ++cm)
+      for (int k = 0; k < 4; ++k) { const int c = L.intr_col[4 * cm + k]; if (c >= 0) { const double v = dc[c] * sv.scale_c[c]; kn[4 * cm + k] += v; step_sq += v * v; } }
+    for (int p = 0; p < P.n_pts; ++p) {
+      const int pc = L.pt_col[p];
+      if (pc < 0) continue;
+      for (int k = 0; k < 3; ++k) { const double v = dp[3 * pc + k] * sv.scale_p[3 * pc + k]; Xn[3 * p + k] += v; step_sq += v * v; }
+    }
+    for (int i = 0; i < P.n_img * 4; ++i) x_sq += P.qvec[i] * P.qvec[i];
+    for (int i = 0; i < P.n_img * 3; ++i) x_sq += P.tvec[i] * P.tvec[i];
+    for (int i = 0; i < P.n_cam * 4; ++i) x_sq += P.cam_params[i] * P.cam_params[i];
+    for (int i = 0; i < P.n_pts * 3; ++i) x_sq += P.xyz[i] * P.xyz[i];
+    if (std::sqrt(step_sq) <= O.parameter_tolerance * (std::sqrt(x_sq) + O.parameter_tolerance)) { S->termination = 0; break; }
+    const double new_cost = sv.EvalCost(qn.data(), tn.data(), kn.data(), Xn.data());
+    const double cost_change = cost - new_cost;
+    const double rho = cost_change / model_cost_change;
+    if (rho > min_rel_dec) {  // successful step
+      memcpy(P.qvec, qn.data(), qn.size() * 8);
+      memcpy(P.tvec, tn.data(), tn.size() * 8);
+      memcpy(P.cam_params, kn.data(), kn.size() * 8);
+      memcpy(P.xyz, Xn.data(), Xn.size() * 8);
+      S->num_successful_steps++;
+      const double t = 2.0 * rho - 1.0;
+      radius = radius / std::max(1.0 / 3.0, 1.0 - t * t * t);
+      radius = std::min(max_radius, radius);
+      decrease_factor = 2.0;
+      const bool ftol = std::abs(cost_change) <= O.function_tolerance * cost;
+      cost = new_cost;
+      sv.EvalJacobian(true);
+      need_grad_check = true;
+      if (ftol) { S->termination = 0; break; }
+    } else {
+      S->num_unsuccessful_steps++;
+      radius /= decrease_factor;
+      decrease_factor *= 2.0;
+      if (radius < min_radius) { S->termination = 2; break; }
+    }
+  }
+  S->final_cost = cost;
+  S->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
+}
+
+}  // namespace ba
+
+extern "C" {
+
+struct orc_ba_problem {
+  int32_t n_img, n_cam, n_pts; int64_t n_obs;
+  double* qvec; double* tvec; const int32_t* img_cam; const uint8_t* pose_const; const uint8_t* tvec_const;
+  const int32_t* cam_model; double* cam_params; const uint8_t* cam_const;
+  int32_t refine_focal, refine_principal, refine_extra;
+  double* xyz; const uint8_t* pt_const;
+  const int32_t* obs_img; const int32_t* obs_pt; const double* obs_xy;
+};
+struct orc_ba_options { int32_t max_num_iterations; double function_tolerance, gradient_tolerance, parameter_tolerance; int32_t n_threads; };
+struct orc_ba_summary { double initial_cost, final_cost; int32_t num_successful_steps, num_unsuccessful_steps, termination, num_residuals, num_effective_parameters; double seconds; };
+
+void orc_ba_solve(const orc_ba_problem* p, const orc_ba_options* o, orc_ba_summary* s) {
+  ba::Problem P;
+  P.n_img = p->n_img; P.n_cam = p->n_cam; P.n_pts = p->n_pts; P.n_obs = (long)p->n_obs;
+  P.qvec = p->qvec; P.tvec = p->tvec; P.img_cam = p->img_cam; P.pose_const = p->pose_const; P.tvec_const = p->tvec_const;
+  P.cam_model = p->cam_model; P.cam_params = p->cam_params; P.cam_const = p->cam_const;
+  P.refine_focal = p->refine_focal; P.refine_principal = p->refine_principal; P.refine_extra = p->refine_extra;
+  P.xyz = p->xyz; P.pt_const = p->pt_const; P.obs_img = p->obs_img; P.obs_pt = p->obs_pt; P.obs_xy = p->obs_xy;
+  ba::Options O{o->max_num_iterations, o->function_tolerance, o->gradient_tolerance, o->parameter_tolerance, o->n_threads};
+  ba::Summary S;
+  ba::Solve(P, O, &S);
+  s->initial_cost = S.initial_cost; s->final_cost = S.final_cost;
+  s->num_successful_steps = S.num_successful_steps; s->num_unsuccessful_steps = S.num_unsuccessful_steps;
+  s->termination = S.termination; s->num_residuals = S.num_residuals; s->num_effective_parameters = S.num_effective_parameters;
+  s->seconds = S.seconds;
+}
+
+// residual + local Jacobians of one observation (tests: cost_functions_test.cc goldens, finite differences)
+void orc_ba_evaluate(int model, const double* q, const double* t, const double* X, const double* k, const double* obs,
+                     double* r, double* Jq, double* Jt, double* JX, double* Jk) {
+  ba::Evaluate(model, q, t, X, k, obs, r, Jq, Jt, JX, Jk);
+}
+void orc_ba_quat_plus(const double* x, const double* d, double* out) { ba::QuatPlus(x, d, out); }
+
+}  // extern "C"

@@ -268,3 +268,64 @@ def two_view(cam1, pts1, cam2, pts2, matches, opt=None, seed=0):
     _tv().orc_two_view(C.byref(cam1), pts1.ctypes.data, C.byref(cam2), pts2.ctypes.data, m.ctypes.data, len(m),
                        C.byref(opt), seed, C.byref(res), inl.ctypes.data)
     return res, inl[: res.n_inliers].copy()
+
+
+# ============================================================== bundle adjustment
+class OrcBaProblem(C.Structure):
+    _fields_ = [("n_img", C.c_int32), ("n_cam", C.c_int32), ("n_pts", C.c_int32), ("n_obs", C.c_int64),
+                ("qvec", C.c_void_p), ("tvec", C.c_void_p), ("img_cam", C.c_void_p), ("pose_const", C.c_void_p),
+                ("tvec_const", C.c_void_p), ("cam_model", C.c_void_p), ("cam_params", C.c_void_p),
+                ("cam_const", C.c_void_p), ("refine_focal", C.c_int32), ("refine_principal", C.c_int32),
+                ("refine_extra", C.c_int32), ("xyz", C.c_void_p), ("pt_const", C.c_void_p),
+                ("obs_img", C.c_void_p), ("obs_pt", C.c_void_p), ("obs_xy", C.c_void_p)]
+
+
+class OrcBaOptions(C.Structure):
+    _fields_ = [("max_num_iterations", C.c_int32), ("function_tolerance", C.c_double),
+                ("gradient_tolerance", C.c_double), ("parameter_tolerance", C.c_double), ("n_threads", C.c_int32)]
+
+
+class OrcBaSummary(C.Structure):
+    _fields_ = [("initial_cost", C.c_double), ("final_cost", C.c_double), ("num_successful_steps", C.c_int32),
+                ("num_unsuccessful_steps", C.c_int32), ("termination", C.c_int32), ("num_residuals", C.c_int32),
+                ("num_effective_parameters", C.c_int32), ("seconds", C.c_double)]
+
+
+def ba_solve(prob: dict, max_num_iterations=50, function_tolerance=0.0, gradient_tolerance=1.0,
+             parameter_tolerance=0.0):
+    """prob: dict of numpy arrays (see tests/ba_scene.py); qvec/tvec/cam_params/xyz are updated in place."""
+    L = lib()
+    L.orc_ba_solve.argtypes = [C.POINTER(OrcBaProblem), C.POINTER(OrcBaOptions), C.POINTER(OrcBaSummary)]
+    L.orc_ba_solve.restype = None
+    p = OrcBaProblem()
+    p.n_img, p.n_cam, p.n_pts, p.n_obs = len(prob["qvec"]), len(prob["cam_params"]), len(prob["xyz"]), len(prob["obs_img"])
+    for k in ("qvec", "tvec", "img_cam", "pose_const", "tvec_const", "cam_model", "cam_params", "cam_const", "xyz",
+              "pt_const", "obs_img", "obs_pt", "obs_xy"):
+        assert prob[k].flags["C_CONTIGUOUS"]
+        setattr(p, k, prob[k].ctypes.data)
+    p.refine_focal, p.refine_principal, p.refine_extra = prob.get("refine", (1, 0, 1))
+    o = OrcBaOptions(max_num_iterations, function_tolerance, gradient_tolerance, parameter_tolerance, 0)
+    s = OrcBaSummary()
+    L.orc_ba_solve(C.byref(p), C.byref(o), C.byref(s))
+    return s
+
+
+def ba_evaluate(model, q, t, X, k, obs):
+    L = lib()
+    L.orc_ba_evaluate.argtypes = [C.c_int] + [C.c_void_p] * 10
+    L.orc_ba_evaluate.restype = None
+    q, t, X, k, obs = (_p(a) for a in (q, t, X, k, obs))
+    r = np.zeros(2); Jq = np.zeros((2, 3)); Jt = np.zeros((2, 3)); JX = np.zeros((2, 3)); Jk = np.zeros((2, 4))
+    L.orc_ba_evaluate(model, q.ctypes.data, t.ctypes.data, X.ctypes.data, k.ctypes.data, obs.ctypes.data,
+                      r.ctypes.data, Jq.ctypes.data, Jt.ctypes.data, JX.ctypes.data, Jk.ctypes.data)
+    return r, Jq, Jt, JX, Jk
+
+
+def ba_quat_plus(x, d):
+    L = lib()
+    L.orc_ba_quat_plus.argtypes = [C.c_void_p] * 3
+    L.orc_ba_quat_plus.restype = None
+    x, d = _p(x), _p(d)
+    out = np.zeros(4)
+    L.orc_ba_quat_plus(x.ctypes.data, d.ctypes.data, out.ctypes.data)
+    return out

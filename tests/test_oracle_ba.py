@@ -1,0 +1,86 @@
+"""Pins of the BA oracle: the residual goldens of the reference (cost_functions_test.cc:41-98),
+the Jacobian against central differences, the structural counts the reference's BA tests
+assert (bundle_adjustment_test.cc:186-233), and convergence on a synthetic scene."""
+import numpy as np
+
+from oracle import pyoracle as orc
+from tests.ba_scene import copy_problem, make_ba_problem, reprojection_rms
+
+
+def test_cost_function_goldens():
+    # cost_functions_test.cc:41-67 (SIMPLE_PINHOLE, identity pose): params {f, cx, cy}
+    q, t = [1, 0, 0, 0], [0, 0, 0]
+    r = orc.ba_evaluate(0, q, t, [0, 0, 1], [1, 0, 0], [0, 0])[0]
+    assert r.tolist() == [0, 0]
+    r = orc.ba_evaluate(0, q, t, [0, 0, 2], [1, 0, 0], [0, 0])[0]   # "1,1,2"-style checks:
+    assert r.tolist() == [0, 0]
+    r = orc.ba_evaluate(0, q, t, [-1, 1, 1], [2, 0, 0], [0, 0])[0]  # X=(-1,1,1), f=2 -> (-2, 2)
+    assert r.tolist() == [-2, 2]
+    r = orc.ba_evaluate(0, q, [0, 0, 1], [1, 1, 1], [1, 0, 0], [0, 0])[0]
+    assert np.allclose(r, [0.5, 0.5])
+
+
+def test_jacobian_vs_central_differences():
+    rng = np.random.default_rng(0)
+    for model, k in ((2, [1200.0, 500, 510, 0.03]), (0, [900.0, 400, 300, 0]), (1, [900.0, 950, 400, 300])):
+        q = rng.normal(size=4); q /= np.linalg.norm(q)
+        t = rng.normal(size=3) + [0, 0, 6]
+        X = rng.normal(size=3)
+        obs = rng.uniform(0, 1000, 2)
+        r, Jq, Jt, JX, Jk = orc.ba_evaluate(model, q, t, X, k, obs)
+        h = 1e-6
+        for c in range(3):
+            d = np.zeros(3); d[c] = h
+            rp = orc.ba_evaluate(model, orc.ba_quat_plus(q, d), t, X, k, obs)[0]
+            rm = orc.ba_evaluate(model, orc.ba_quat_plus(q, -d), t, X, k, obs)[0]
+            assert np.allclose((rp - rm) / (2 * h), Jq[:, c], rtol=1e-5, atol=1e-4)
+            rp = orc.ba_evaluate(model, q, t + d, X, k, obs)[0]; rm = orc.ba_evaluate(model, q, t - d, X, k, obs)[0]
+            assert np.allclose((rp - rm) / (2 * h), Jt[:, c], rtol=1e-5, atol=1e-4)
+            rp = orc.ba_evaluate(model, q, t, X + d, k, obs)[0]; rm = orc.ba_evaluate(model, q, t, X - d, k, obs)[0]
+            assert np.allclose((rp - rm) / (2 * h), JX[:, c], rtol=1e-5, atol=1e-4)
+        for c in range(4 if model else 3):
+            d = np.zeros(4); d[c] = h * max(1.0, abs(k[c]))
+            rp = orc.ba_evaluate(model, q, t, X, np.array(k) + d, obs)[0]
+            rm = orc.ba_evaluate(model, q, t, X, np.array(k) - d, obs)[0]
+            assert np.allclose((rp - rm) / (2 * d[c]), Jk[:, c], rtol=1e-5, atol=1e-5)
+
+
+def test_structure_counts_two_view():
+    # bundle_adjustment_test.cc:186-233 TestTwoView: 100 points seen by 2 images ->
+    # 400 residuals, 309 effective parameters (300 + 5 [pose of image 1 minus tvec.x] + 2 * 2 intrinsics)
+    prob = make_ba_problem(n_img=2, n_pts=100, track_len=2, seed=1)
+    s = orc.ba_solve(prob, max_num_iterations=2)
+    assert s.num_residuals == 400
+    assert s.num_effective_parameters == 309
+
+
+def test_constant_blocks_stay_bit_identical():
+    # CheckConstant* macros of bundle_adjustment_test.cc:41-107
+    prob = make_ba_problem(n_img=6, n_pts=120, track_len=4, seed=2, n_const_pts=15)
+    prob["cam_const"][2] = 1
+    before = copy_problem(prob)
+    orc.ba_solve(prob, max_num_iterations=10)
+    assert (prob["qvec"][0] == before["qvec"][0] / np.linalg.norm(before["qvec"][0])).all()
+    assert (prob["tvec"][0] == before["tvec"][0]).all()
+    assert prob["tvec"][1][0] == before["tvec"][1][0] and (prob["tvec"][1][1:] != before["tvec"][1][1:]).all()
+    c = before["pt_const"].astype(bool)
+    assert (prob["xyz"][c] == before["xyz"][c]).all() and (prob["xyz"][~c] != before["xyz"][~c]).any()
+    assert (prob["cam_params"][2] == before["cam_params"][2]).all()
+    assert (prob["cam_params"][:, 1:3] == before["cam_params"][:, 1:3]).all()      # cx, cy never refined
+    assert (prob["cam_params"][[0, 1, 3], 0] != before["cam_params"][[0, 1, 3], 0]).all()
+
+
+def test_converges_to_noise_floor():
+    prob = make_ba_problem(n_img=24, n_pts=600, track_len=6, seed=3)
+    rms0 = reprojection_rms(prob)
+    s = orc.ba_solve(prob, max_num_iterations=50)
+    rms1 = reprojection_rms(prob)
+    # U(-2,2) noise has sigma 1.155 px per coordinate -> RMS ~ 1.63 px minus what the fit absorbs
+    assert rms0 > 5 and 1.2 < rms1 < 1.7
+    assert abs(np.sqrt(2 * s.final_cost / len(prob["obs_img"])) - rms1) < 1e-9
+    assert s.num_successful_steps >= 3
+    # shared intrinsics: one camera for all images
+    prob = make_ba_problem(n_img=12, n_pts=300, track_len=5, seed=4, shared_camera=True)
+    s = orc.ba_solve(prob, max_num_iterations=50)
+    assert 1.2 < reprojection_rms(prob) < 1.7
+    assert s.num_effective_parameters == 300 * 3 + 11 * 6 - 1 + 2
