@@ -9,5 +9,6 @@ from .matching import SiftMatchGPU, SiftMatchingOptions, match_sift_features_gpu
 
 from .verification import (Camera, TwoViewGeometryVerifier, TwoViewOptions,  # noqa: F401
                            TwoViewResult)
+from .bundle_adjustment import BundleAdjuster, BundleAdjustmentOptions  # noqa: F401
 
 __version__ = "0.1"

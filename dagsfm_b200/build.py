@@ -68,8 +68,11 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if verbose:
         for _, log in res:
             sys.stderr.write(log)
+    cuda_lib = str(Path(nvcc).resolve().parent.parent / "lib64")
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static",
-           "-o", str(LIB), *[str(o) for o, _ in res]]
+           "-o", str(LIB), *[str(o) for o, _ in res],
+           # dense Cholesky of the reduced camera system (bundle adjustment) only
+           f"-L{cuda_lib}", "-lcusolver", "-Xlinker", f"-rpath={cuda_lib}"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}{r.stderr}")

@@ -1,0 +1,119 @@
+"""Host-side mirror of the reference's bundle-adjustment interface.
+
+Reference names kept: BundleAdjustmentOptions / BundleAdjuster.Solve / Summary
+(src/optim/bundle_adjustment.h:48-197).  The problem is passed as flat arrays the way
+ParallelBundleAdjuster::SetUp packs a Reconstruction for PBA (bundle_adjustment.cc:654-772).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from ._lib import check, lib
+
+
+class BaProblem(C.Structure):
+    _fields_ = [("n_images", C.c_int32), ("n_cameras", C.c_int32), ("n_points", C.c_int32), ("n_obs", C.c_int64),
+                ("qvec", C.c_void_p), ("tvec", C.c_void_p), ("image_camera", C.c_void_p),
+                ("const_pose", C.c_void_p), ("const_tvec", C.c_void_p), ("camera_model", C.c_void_p),
+                ("camera_params", C.c_void_p), ("const_camera", C.c_void_p), ("xyz", C.c_void_p),
+                ("const_point", C.c_void_p), ("obs_image", C.c_void_p), ("obs_point", C.c_void_p),
+                ("obs_xy", C.c_void_p)]
+
+
+class BundleAdjustmentOptions(C.Structure):
+    """b2_ba_options; defaults = DistributedMapperController::GlobalBundleAdjustment()."""
+    _fields_ = [("max_num_iterations", C.c_int32), ("refine_focal_length", C.c_int32),
+                ("refine_principal_point", C.c_int32), ("refine_extra_params", C.c_int32),
+                ("function_tolerance", C.c_double), ("gradient_tolerance", C.c_double),
+                ("parameter_tolerance", C.c_double)]
+
+    @staticmethod
+    def default():
+        o = BundleAdjustmentOptions()
+        _L().b2_ba_default_options(C.byref(o))
+        return o
+
+
+class BaSummary(C.Structure):
+    _fields_ = [("initial_cost", C.c_double), ("final_cost", C.c_double),
+                ("num_successful_steps", C.c_int32), ("num_unsuccessful_steps", C.c_int32),
+                ("termination_type", C.c_int32), ("num_residuals_reduced", C.c_int32),
+                ("num_effective_parameters_reduced", C.c_int32), ("num_iterations", C.c_int32),
+                ("solve_seconds", C.c_double), ("schur_kernel_seconds", C.c_double),
+                ("schur_kernel_launches", C.c_int64)]
+
+
+ALLREDUCE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p)
+_bound = False
+
+
+def _L():
+    global _bound
+    L = lib()
+    if not _bound:
+        vp, P = C.c_void_p, C.POINTER
+        L.b2_ba_default_options.argtypes = [P(BundleAdjustmentOptions)]
+        L.b2_ba_default_options.restype = None
+        L.b2_ba_create.argtypes = [C.c_int, P(vp)]
+        L.b2_ba_destroy.argtypes = [vp]
+        L.b2_ba_set_allreduce.argtypes = [vp, ALLREDUCE_FN, vp]
+        L.b2_ba_solve.argtypes = [vp, P(BaProblem), P(BundleAdjustmentOptions), P(BaSummary)]
+        _bound = True
+    return L
+
+
+_KEYS = (("qvec", np.float64), ("tvec", np.float64), ("img_cam", np.int32), ("pose_const", np.uint8),
+         ("tvec_const", np.uint8), ("cam_model", np.int32), ("cam_params", np.float64), ("cam_const", np.uint8),
+         ("xyz", np.float64), ("pt_const", np.uint8), ("obs_img", np.int32), ("obs_pt", np.int32),
+         ("obs_xy", np.float64))
+
+
+class BundleAdjuster:
+    """BundleAdjuster(options).Solve(problem) -> summary; parameters are updated in place."""
+
+    def __init__(self, options: BundleAdjustmentOptions | None = None, device: int = 0):
+        self.options = options or BundleAdjustmentOptions.default()
+        self._h = C.c_void_p()
+        check(_L().b2_ba_create(device, C.byref(self._h)))
+        self._cb = None
+        self.summary = None
+
+    def close(self):
+        if self._h:
+            _L().b2_ba_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_allreduce(self, fn) -> None:
+        """fn(dev_ptr: int, n_doubles: int, op: int) reduces the device buffer in place across
+        ranks (op 0 SUM, 1 MAX) -- e.g. torch.distributed over NCCL."""
+        self._cb = ALLREDUCE_FN(lambda ptr, n, op, user: fn(ptr, n, op)) if fn else ALLREDUCE_FN(0)
+        check(_L().b2_ba_set_allreduce(self._h, self._cb, None))
+
+    def Solve(self, prob: dict) -> BaSummary:
+        """prob: dict with the arrays of tests/ba_scene.make_ba_problem (updated in place)."""
+        for k, dt in _KEYS:
+            a = prob[k]
+            assert a.dtype == dt and a.flags["C_CONTIGUOUS"], k
+        p = BaProblem()
+        p.n_images, p.n_cameras, p.n_points = len(prob["qvec"]), len(prob["cam_params"]), len(prob["xyz"])
+        p.n_obs = len(prob["obs_img"])
+        p.qvec, p.tvec = prob["qvec"].ctypes.data, prob["tvec"].ctypes.data
+        p.image_camera, p.const_pose, p.const_tvec = (prob["img_cam"].ctypes.data, prob["pose_const"].ctypes.data,
+                                                      prob["tvec_const"].ctypes.data)
+        p.camera_model, p.camera_params, p.const_camera = (prob["cam_model"].ctypes.data,
+                                                           prob["cam_params"].ctypes.data, prob["cam_const"].ctypes.data)
+        p.xyz, p.const_point = prob["xyz"].ctypes.data, prob["pt_const"].ctypes.data
+        p.obs_image, p.obs_point, p.obs_xy = (prob["obs_img"].ctypes.data, prob["obs_pt"].ctypes.data,
+                                              prob["obs_xy"].ctypes.data)
+        s = BaSummary()
+        check(_L().b2_ba_solve(self._h, C.byref(p), C.byref(self.options), C.byref(s)))
+        self.summary = s
+        return s

@@ -1,0 +1,390 @@
+// C ABI of the bundle adjuster (include/dagsfm_b200.h, BA section): packs the problem
+// into HBM, lays out the reduced camera system, and runs the Levenberg-Marquardt loop that
+// ceres::Solve runs for the reference (BundleAdjuster::Solve, bundle_adjustment.cc:258-310)
+// with the Ceres 1.14 trust-region defaults colmap leaves untouched:
+//   initial radius 1e4, max 1e16, min 1e-32; min_relative_decrease 1e-3; LM diagonal
+//   clamp [1e-6, 1e32]; Jacobi scaling 1/(1+|col|); radius /= max(1/3, 1-(2 rho-1)^3) on
+//   success, /= decrease_factor (2, doubling) on failure.
+// The reduced system is solved exactly (DENSE_SCHUR / SPARSE_SCHUR semantics) with a dense
+// Cholesky -- cuSOLVER potrf/potrs, a library call for the factorisation only; Jacobian,
+// Schur elimination and back-substitution are the hand-written kernels in ba_kernels.cu.
+#include <cuda_runtime.h>
+#include <cusolverDn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "../../include/dagsfm_b200.h"
+#include "ba_common.cuh"
+#include "common_host.h"
+
+using namespace b2;
+
+struct b2_ba {
+  int device = 0;
+  int n_sm = 148;
+  cudaStream_t stream = nullptr;
+  cusolverDnHandle_t solver = nullptr;
+  b2_allreduce_fn allreduce = nullptr;
+  void* allreduce_user = nullptr;
+  std::vector<void*> allocs;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+namespace {
+
+int num_params(int model) { return model == 0 ? 3 : 4; }
+void param_kinds(int model, int kind[4]) {  // 0 focal, 1 principal point, 2 extra (camera_models.h)
+  if (model == 0) { kind[0] = 0; kind[1] = 1; kind[2] = 1; kind[3] = -1; }
+  else if (model == 1) { kind[0] = 0; kind[1] = 0; kind[2] = 1; kind[3] = 1; }
+  else { kind[0] = 0; kind[1] = 1; kind[2] = 1; kind[3] = 2; }
+}
+
+template <typename T>
+int dev_alloc(b2_ba* h, T** p, size_t n) {
+  *p = nullptr;
+  B2_CUDA(cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)));
+  h->allocs.push_back(*p);
+  return B2_OK;
+}
+template <typename T>
+int dev_upload(b2_ba* h, T** p, const T* src, size_t n) {
+  B2_TRY(dev_alloc(h, p, n));
+  if (n) B2_CUDA(cudaMemcpyAsync(*p, src, n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+  return B2_OK;
+}
+void free_all(b2_ba* h) {
+  for (void* p : h->allocs) cudaFree(p);
+  h->allocs.clear();
+}
+
+int sync_reduce(b2_ba* h, double* buf, int64_t n, int op) {
+  if (!h->allreduce || n == 0) return B2_OK;
+  B2_CUDA(cudaStreamSynchronize(h->stream));
+  h->allreduce(buf, n, op, h->allreduce_user);
+  return B2_OK;
+}
+
+int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_ba_summary* sum) {
+  cudaStream_t s = h->stream;
+  const int n_img = pr->n_images, n_cam = pr->n_cameras, n_pts = pr->n_points;
+  const int64_t n_obs = pr->n_obs;
+  // ---------------------------------------------------------------- validation
+  for (int64_t o = 0; o < n_obs; ++o) {
+    if (pr->obs_image[o] < 0 || pr->obs_image[o] >= n_img || pr->obs_point[o] < 0 || pr->obs_point[o] >= n_pts)
+      return set_error(B2_ERR_INVALID, "observation index out of range");
+    if (o > 0 && pr->obs_point[o] < pr->obs_point[o - 1])
+      return set_error(B2_ERR_INVALID, "observations must be sorted by point");
+  }
+  for (int i = 0; i < n_img; ++i)
+    if (pr->image_camera[i] < 0 || pr->image_camera[i] >= n_cam) return set_error(B2_ERR_INVALID, "bad image_camera");
+  for (int c = 0; c < n_cam; ++c)
+    if (pr->camera_model[c] < 0 || pr->camera_model[c] > 2) return set_error(B2_ERR_INVALID, "unsupported camera model");
+  // ---------------------------------------------------------------- layout
+  // Column order: images (rotation 3, variable tvec components), then cameras (variable
+  // intrinsics) -- only blocks that appear in a residual (as Ceres' reduced program).
+  // In a multi-GPU run every rank sees all images / cameras of the job, so `used` must be
+  // the union: a rank marks everything that is not explicitly constant as used when a
+  // collective hook is installed.
+  std::vector<char> img_used(n_img, h->allreduce ? 1 : 0), cam_used(n_cam, h->allreduce ? 1 : 0), pt_used(n_pts, 0);
+  for (int64_t o = 0; o < n_obs; ++o) {
+    img_used[pr->obs_image[o]] = 1;
+    cam_used[pr->image_camera[pr->obs_image[o]]] = 1;
+    pt_used[pr->obs_point[o]] = 1;
+  }
+  std::vector<int32_t> pose_col((size_t)n_img * 6, -1), intr_col((size_t)n_cam * 4, -1), pt_col(n_pts, -1);
+  int64_t D = 0;
+  for (int i = 0; i < n_img; ++i) {
+    if (!img_used[i] || pr->const_pose[i]) continue;
+    for (int k = 0; k < 3; ++k) pose_col[6 * i + k] = (int32_t)D++;
+    for (int k = 0; k < 3; ++k)
+      if (!(pr->const_tvec[i] & (1 << k))) pose_col[6 * i + 3 + k] = (int32_t)D++;
+  }
+  for (int c = 0; c < n_cam; ++c) {
+    if (!cam_used[c] || pr->const_camera[c]) continue;
+    int kind[4];
+    param_kinds(pr->camera_model[c], kind);
+    for (int k = 0; k < num_params(pr->camera_model[c]); ++k) {
+      const bool var = (kind[k] == 0 && opt->refine_focal_length) || (kind[k] == 1 && opt->refine_principal_point) ||
+                       (kind[k] == 2 && opt->refine_extra_params);
+      if (var) intr_col[4 * c + k] = (int32_t)D++;
+    }
+  }
+  int64_t NP = 0;
+  for (int p = 0; p < n_pts; ++p)
+    if (pt_used[p] && !pr->const_point[p]) pt_col[p] = (int32_t)NP++;
+  if (D > 46000) return set_error(B2_ERR_INVALID, "reduced camera system too large for the dense Schur path");
+  std::vector<int64_t> pt_start(n_pts + 1, 0);
+  for (int64_t o = 0; o < n_obs; ++o) pt_start[pr->obs_point[o] + 1]++;
+  for (int p = 0; p < n_pts; ++p) pt_start[p + 1] += pt_start[p];
+
+  sum->num_residuals_reduced = (int32_t)(2 * n_obs);
+  sum->num_effective_parameters_reduced = (int32_t)(D + 3 * NP);
+  sum->num_successful_steps = sum->num_unsuccessful_steps = sum->num_iterations = 0;
+  sum->termination_type = 1;
+  sum->initial_cost = sum->final_cost = 0;
+  sum->solve_seconds = sum->schur_kernel_seconds = 0;
+  sum->schur_kernel_launches = 0;
+
+  // image.NormalizeQvec() (bundle_adjustment.cc:345)
+  std::vector<double> qn(pr->qvec, pr->qvec + (size_t)n_img * 4);
+  for (int i = 0; i < n_img; ++i) {
+    double* q = &qn[4 * i];
+    const double n = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    if (n > 0) for (int k = 0; k < 4; ++k) q[k] /= n;
+  }
+
+  // ---------------------------------------------------------------- upload
+  BaDev P;
+  memset(&P, 0, sizeof P);
+  P.n_img = n_img; P.n_cam = n_cam; P.n_pts = n_pts; P.n_obs = n_obs; P.D = D;
+  int32_t *d_obs_img, *d_obs_pt, *d_img_cam, *d_cam_model, *d_pose_col, *d_intr_col, *d_pt_col;
+  double* d_obs_xy;
+  int64_t* d_pt_start;
+  B2_TRY(dev_upload(h, &d_obs_img, pr->obs_image, (size_t)n_obs));
+  B2_TRY(dev_upload(h, &d_obs_pt, pr->obs_point, (size_t)n_obs));
+  B2_TRY(dev_upload(h, &d_obs_xy, pr->obs_xy, (size_t)n_obs * 2));
+  B2_TRY(dev_upload(h, &d_pt_start, pt_start.data(), pt_start.size()));
+  B2_TRY(dev_upload(h, &d_img_cam, pr->image_camera, (size_t)n_img));
+  B2_TRY(dev_upload(h, &d_cam_model, pr->camera_model, (size_t)n_cam));
+  B2_TRY(dev_upload(h, &d_pose_col, pose_col.data(), pose_col.size()));
+  B2_TRY(dev_upload(h, &d_intr_col, intr_col.data(), intr_col.size()));
+  B2_TRY(dev_upload(h, &d_pt_col, pt_col.data(), pt_col.size()));
+  P.obs_img = d_obs_img; P.obs_pt = d_obs_pt; P.obs_xy = (const double2*)d_obs_xy; P.pt_start = d_pt_start;
+  P.img_cam = d_img_cam; P.cam_model = d_cam_model; P.pose_col = d_pose_col; P.intr_col = d_intr_col; P.pt_col = d_pt_col;
+  B2_TRY(dev_upload(h, &P.qvec, qn.data(), qn.size()));
+  B2_TRY(dev_upload(h, &P.tvec, (const double*)pr->tvec, (size_t)n_img * 3));
+  B2_TRY(dev_upload(h, &P.cam_params, (const double*)pr->camera_params, (size_t)n_cam * 4));
+  B2_TRY(dev_upload(h, &P.xyz, (const double*)pr->xyz, (size_t)n_pts * 3));
+  B2_TRY(dev_alloc(h, &P.qvec_new, (size_t)n_img * 4));
+  B2_TRY(dev_alloc(h, &P.tvec_new, (size_t)n_img * 3));
+  B2_TRY(dev_alloc(h, &P.cam_new, (size_t)n_cam * 4));
+  B2_TRY(dev_alloc(h, &P.xyz_new, (size_t)n_pts * 3));
+  B2_TRY(dev_alloc(h, &P.J, (size_t)n_obs));
+  B2_TRY(dev_alloc(h, &P.scale_c, (size_t)D));
+  B2_TRY(dev_alloc(h, &P.scale_p, (size_t)NP * 3));
+  B2_TRY(dev_alloc(h, &P.colnorm_c, (size_t)D));
+  B2_TRY(dev_alloc(h, &P.colnorm_p, (size_t)NP * 3));
+  double* reduced;  // S | rhs | g_c | diag_c : one buffer, one all-reduce
+  const size_t n_reduced = (size_t)D * D + 3 * (size_t)D;
+  B2_TRY(dev_alloc(h, &reduced, n_reduced));
+  P.S = reduced; P.rhs = reduced + (size_t)D * D; P.g_c = P.rhs + D; P.diag_c = P.g_c + D;
+  B2_TRY(dev_alloc(h, &P.diag_p, (size_t)NP * 3));
+  B2_TRY(dev_alloc(h, &P.g_p, (size_t)NP * 3));
+  B2_TRY(dev_alloc(h, &P.Vinv, (size_t)NP * 9));
+  B2_TRY(dev_alloc(h, &P.dc, (size_t)D));
+  B2_TRY(dev_alloc(h, &P.dp, (size_t)NP * 3));
+  double* scal;  // [0] step^2 cams [1] x^2 cams [2] step^2 pts [3] x^2 pts [4] model change [5] new cost [6] cost [7] gmax
+  B2_TRY(dev_alloc(h, &scal, 8));
+  P.gmax = scal + 7;
+  int* d_info;
+  B2_TRY(dev_alloc(h, &d_info, 1));
+  double* work = nullptr;
+  int lwork = 0;
+  if (D > 0) {
+    if (cusolverDnDpotrf_bufferSize(h->solver, CUBLAS_FILL_MODE_LOWER, (int)D, P.S, (int)D, &lwork) != CUSOLVER_STATUS_SUCCESS)
+      return set_error(B2_ERR_CUDA, "cusolverDnDpotrf_bufferSize failed");
+    B2_TRY(dev_alloc(h, &work, (size_t)lwork));
+  }
+  if (n_obs == 0 && !h->allreduce) return B2_OK;  // BundleAdjuster::Solve returns false: nothing to do
+
+  // ---------------------------------------------------------------- Jacobi scaling + initial cost
+  B2_CUDA(cudaMemsetAsync(P.colnorm_c, 0, std::max<size_t>(D, 1) * 8, s));
+  B2_CUDA(cudaMemsetAsync(P.colnorm_p, 0, std::max<size_t>(NP * 3, 1) * 8, s));
+  B2_CUDA(cudaMemsetAsync(scal, 0, 8 * 8, s));
+  B2_CUDA(ba_launch_jacobian(P, P.qvec, P.tvec, P.cam_params, P.xyz, 2, scal + 6, s));
+  B2_TRY(sync_reduce(h, P.colnorm_c, D, 0));
+  B2_TRY(sync_reduce(h, scal + 6, 1, 0));
+  B2_CUDA(ba_launch_make_scale(P.colnorm_c, P.scale_c, D, s));
+  B2_CUDA(ba_launch_make_scale(P.colnorm_p, P.scale_p, NP * 3, s));
+  double cost = 0;
+  B2_CUDA(cudaMemcpyAsync(&cost, scal + 6, 8, cudaMemcpyDeviceToHost, s));
+  B2_CUDA(cudaStreamSynchronize(s));
+  count_launches(3);
+  sum->initial_cost = cost;
+
+  B2_CUDA(cudaEventRecord(h->ev[0], s));
+  B2_CUDA(cudaMemsetAsync(scal + 6, 0, 8, s));
+  B2_CUDA(ba_launch_jacobian(P, P.qvec, P.tvec, P.cam_params, P.xyz, 0, scal + 6, s));
+  count_launches(1);
+
+  double radius = 1e4, decrease_factor = 2.0;
+  const double min_radius = 1e-32, max_radius = 1e16, min_rel_dec = 1e-3, min_diag = 1e-6, max_diag = 1e32;
+  double schur_ms = 0;
+  int64_t schur_launches = 0;
+  for (int iter = 0; iter < opt->max_num_iterations; ++iter) {
+    // ---- normal equations of the camera block + Schur complement
+    B2_CUDA(cudaMemsetAsync(reduced, 0, n_reduced * 8, s));
+    B2_CUDA(cudaMemsetAsync(scal, 0, 6 * 8, s));
+    B2_CUDA(cudaMemsetAsync(scal + 7, 0, 8, s));
+    B2_CUDA(cudaEventRecord(h->ev[2], s));
+    B2_CUDA(ba_launch_camera_terms(P, s));
+    B2_CUDA(ba_launch_schur(P, radius, min_diag, max_diag, h->n_sm, s));
+    B2_CUDA(cudaEventRecord(h->ev[3], s));
+    schur_launches += 2;
+    B2_TRY(sync_reduce(h, reduced, (int64_t)n_reduced, 0));  // the one NVLink all-reduce of (S, rhs, g_c, diag)
+    B2_CUDA(ba_launch_add_diag(P, radius, min_diag, max_diag, s));
+    B2_TRY(sync_reduce(h, P.gmax, 1, 1));
+    // ---- reduced solve: S y = rhs, dc = -y
+    int info = 0;
+    if (D > 0) {
+      B2_CUDA(cudaMemcpyAsync(P.dc, P.rhs, D * 8, cudaMemcpyDeviceToDevice, s));
+      if (cusolverDnDpotrf(h->solver, CUBLAS_FILL_MODE_LOWER, (int)D, P.S, (int)D, work, lwork, d_info) != CUSOLVER_STATUS_SUCCESS)
+        return set_error(B2_ERR_CUDA, "cusolverDnDpotrf failed");
+      B2_CUDA(cudaMemcpyAsync(&info, d_info, sizeof(int), cudaMemcpyDeviceToHost, s));
+      if (cusolverDnDpotrs(h->solver, CUBLAS_FILL_MODE_LOWER, (int)D, 1, P.S, (int)D, P.dc, (int)D, d_info) != CUSOLVER_STATUS_SUCCESS)
+        return set_error(B2_ERR_CUDA, "cusolverDnDpotrs failed");
+      B2_CUDA(ba_launch_negate(P.dc, D, s));
+    }
+    B2_CUDA(ba_launch_backsub(P, s));
+    B2_CUDA(ba_launch_model_cost(P, scal + 4, s));
+    B2_CUDA(ba_launch_candidate(P, scal, true, s));
+    B2_CUDA(ba_launch_candidate(P, scal, false, s));
+    B2_CUDA(ba_launch_jacobian(P, P.qvec_new, P.tvec_new, P.cam_new, P.xyz_new, 1, scal + 5, s));
+    count_launches(10);
+    B2_TRY(sync_reduce(h, scal + 2, 4, 0));
+    double hs[8];
+    B2_CUDA(cudaMemcpyAsync(hs, scal, 8 * 8, cudaMemcpyDeviceToHost, s));
+    B2_CUDA(cudaStreamSynchronize(s));
+    float ms = 0;
+    B2_CUDA(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]));
+    schur_ms += ms;
+    const double gmax = hs[7];
+    if (gmax <= opt->gradient_tolerance) {  // gradient_max_norm <= gradient_tolerance at the current iterate
+      sum->termination_type = 0;
+      break;
+    }
+    const double model_cost_change = hs[4];
+    const bool ok = (info == 0) && (model_cost_change > 0) && std::isfinite(model_cost_change);
+    bool accepted = false;
+    if (ok) {
+      const double step = std::sqrt(hs[0] + hs[2]), xn = std::sqrt(hs[1] + hs[3]);
+      if (step <= opt->parameter_tolerance * (xn + opt->parameter_tolerance)) {
+        sum->termination_type = 0;
+        break;
+      }
+      const double new_cost = hs[5];
+      const double cost_change = cost - new_cost;
+      const double rho = cost_change / model_cost_change;
+      if (rho > min_rel_dec) {
+        accepted = true;
+        std::swap(P.qvec, P.qvec_new);
+        std::swap(P.tvec, P.tvec_new);
+        std::swap(P.cam_params, P.cam_new);
+        std::swap(P.xyz, P.xyz_new);
+        sum->num_successful_steps++;
+        const double t = 2.0 * rho - 1.0;
+        radius = radius / std::max(1.0 / 3.0, 1.0 - t * t * t);
+        radius = std::min(max_radius, radius);
+        decrease_factor = 2.0;
+        const bool ftol = std::abs(cost_change) <= opt->function_tolerance * cost;
+        cost = new_cost;
+        B2_CUDA(cudaMemsetAsync(scal + 6, 0, 8, s));
+        B2_CUDA(ba_launch_jacobian(P, P.qvec, P.tvec, P.cam_params, P.xyz, 0, scal + 6, s));
+        count_launches(1);
+        if (ftol) {
+          sum->termination_type = 0;
+          break;
+        }
+      }
+    }
+    if (!accepted) {
+      sum->num_unsuccessful_steps++;
+      radius /= decrease_factor;
+      decrease_factor *= 2.0;
+      if (radius < min_radius) {
+        sum->termination_type = 2;
+        break;
+      }
+    }
+  }
+  B2_CUDA(cudaEventRecord(h->ev[1], s));
+  // ---------------------------------------------------------------- download (in place)
+  B2_CUDA(cudaMemcpyAsync(pr->qvec, P.qvec, (size_t)n_img * 4 * 8, cudaMemcpyDeviceToHost, s));
+  B2_CUDA(cudaMemcpyAsync(pr->tvec, P.tvec, (size_t)n_img * 3 * 8, cudaMemcpyDeviceToHost, s));
+  B2_CUDA(cudaMemcpyAsync(pr->camera_params, P.cam_params, (size_t)n_cam * 4 * 8, cudaMemcpyDeviceToHost, s));
+  B2_CUDA(cudaMemcpyAsync(pr->xyz, P.xyz, (size_t)n_pts * 3 * 8, cudaMemcpyDeviceToHost, s));
+  B2_CUDA(cudaStreamSynchronize(s));
+  float ms = 0;
+  B2_CUDA(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+  sum->solve_seconds = ms * 1e-3;
+  sum->schur_kernel_seconds = schur_ms * 1e-3;
+  sum->schur_kernel_launches = schur_launches;
+  sum->final_cost = cost;
+  sum->num_iterations = sum->num_successful_steps + sum->num_unsuccessful_steps;
+  return B2_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void b2_ba_default_options(b2_ba_options* o) {
+  if (!o) return;
+  // DistributedMapperController::GlobalBundleAdjustment (distributed_mapper_controller.cpp:522-542)
+  o->max_num_iterations = 50;
+  o->refine_focal_length = 1;
+  o->refine_principal_point = 0;
+  o->refine_extra_params = 1;
+  o->function_tolerance = 0.0;
+  o->gradient_tolerance = 1.0;
+  o->parameter_tolerance = 0.0;
+}
+
+int b2_ba_create(int device, b2_ba** out) {
+  if (!out) return set_error(B2_ERR_INVALID, "out == NULL");
+  *out = nullptr;
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+    cudaGetLastError();
+    return set_error(B2_ERR_NO_DEVICE, "no CUDA device visible (there is no CPU fallback)");
+  }
+  if (device < 0 || device >= n_dev) return set_error(B2_ERR_INVALID, "bad device ordinal");
+  cudaDeviceProp prop;
+  B2_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return set_error(B2_ERR_NO_DEVICE, "device is not sm_100");
+  B2_CUDA(cudaSetDevice(device));
+  b2_ba* h = new b2_ba();
+  h->device = device;
+  h->n_sm = prop.multiProcessorCount;
+  B2_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  if (cusolverDnCreate(&h->solver) != CUSOLVER_STATUS_SUCCESS) return set_error(B2_ERR_CUDA, "cusolverDnCreate failed");
+  cusolverDnSetStream(h->solver, h->stream);
+  for (auto& e : h->ev) B2_CUDA(cudaEventCreate(&e));
+  *out = h;
+  return B2_OK;
+}
+
+int b2_ba_destroy(b2_ba* h) {
+  if (!h) return B2_OK;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  free_all(h);
+  if (h->solver) cusolverDnDestroy(h->solver);
+  for (auto e : h->ev) if (e) cudaEventDestroy(e);
+  cudaStreamDestroy(h->stream);
+  delete h;
+  return B2_OK;
+}
+
+int b2_ba_set_allreduce(b2_ba* h, b2_allreduce_fn fn, void* user) {
+  if (!h) return set_error(B2_ERR_INVALID, "NULL handle");
+  h->allreduce = fn;
+  h->allreduce_user = user;
+  return B2_OK;
+}
+
+int b2_ba_solve(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_ba_summary* sum) {
+  if (!h || !pr || !opt || !sum) return set_error(B2_ERR_INVALID, "NULL argument");
+  if (pr->n_images < 0 || pr->n_cameras < 0 || pr->n_points < 0 || pr->n_obs < 0 || opt->max_num_iterations < 0)
+    return set_error(B2_ERR_INVALID, "negative size");
+  B2_CUDA(cudaSetDevice(h->device));
+  const int rc = solve_impl(h, pr, opt, sum);
+  cudaStreamSynchronize(h->stream);
+  free_all(h);
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,57 @@
+// Shared declarations of the bundle adjuster (device-side problem view).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdint>
+
+namespace b2 {
+
+// Per-observation residual and Jacobi-scaled Jacobian blocks (224 bytes).
+struct ObsJac {
+  double r[2];
+  double Jc[20];  // 2 x 10: [rotation 3 | translation 3 | intrinsics 4]
+  double Jp[6];   // 2 x 3
+};
+
+struct BaDev {
+  int32_t n_img, n_cam, n_pts;
+  int64_t n_obs;
+  int64_t D;  // reduced camera system dimension
+  // problem (SoA over observations sorted by point)
+  const int32_t* obs_img;
+  const int32_t* obs_pt;
+  const double2* obs_xy;
+  const int64_t* pt_start;
+  const int32_t* img_cam;
+  const int32_t* cam_model;
+  const int32_t* pose_col;  // [n_img*6]
+  const int32_t* intr_col;  // [n_cam*4]
+  const int32_t* pt_col;    // [n_pts] index of the variable point or -1
+  // parameters and candidates
+  double *qvec, *tvec, *cam_params, *xyz;
+  double *qvec_new, *tvec_new, *cam_new, *xyz_new;
+  // Jacobian / normal equations
+  ObsJac* J;
+  double *scale_c, *scale_p, *colnorm_c, *colnorm_p;
+  double* S;       // [D*D]   | these four are contiguous: one all-reduce
+  double* rhs;     // [D]     |
+  double* g_c;     // [D]     |
+  double* diag_c;  // [D]     |
+  double *diag_p, *g_p, *Vinv;  // per variable point
+  double *dc, *dp;              // step
+  double* gmax;                 // gradient max norm (bit pattern of a non-negative double)
+};
+
+cudaError_t ba_launch_jacobian(const BaDev& P, const double* q, const double* t, const double* k, const double* X,
+                               int mode, double* cost_out, cudaStream_t s);
+cudaError_t ba_launch_camera_terms(const BaDev& P, cudaStream_t s);
+cudaError_t ba_launch_schur(const BaDev& P, double radius, double min_diag, double max_diag, int n_sm, cudaStream_t s);
+cudaError_t ba_launch_add_diag(const BaDev& P, double radius, double min_diag, double max_diag, cudaStream_t s);
+cudaError_t ba_launch_backsub(const BaDev& P, cudaStream_t s);
+cudaError_t ba_launch_model_cost(const BaDev& P, double* out, cudaStream_t s);
+cudaError_t ba_launch_candidate(const BaDev& P, double* out, bool cameras, cudaStream_t s);
+cudaError_t ba_launch_make_scale(const double* colnorm, double* scale, int64_t n, cudaStream_t s);
+cudaError_t ba_launch_negate(double* v, int64_t n, cudaStream_t s);
+
+}  // namespace b2

@@ -1,0 +1,515 @@
+// Bundle adjustment kernels: reprojection residual + analytic Jacobian, camera normal
+// blocks, the Schur-complement reduce-to-camera-block, back-substitution, step
+// application and cost evaluation.  FP64 throughout, compiled with --fmad=false.
+//
+// Reference arithmetic restated (file:line under the reference tree):
+//   BundleAdjustmentCostFunction::operator()   src/base/cost_functions.h:57-84
+//   SimpleRadialCameraModel::WorldToImage      src/base/camera_models.h:714-732,748-757
+//   ceres::UnitQuaternionRotatePoint, QuaternionParameterization (Ceres 1.14, external)
+// The reference evaluates the Jacobian by Ceres autodiff of these formulas and leaves the
+// Schur elimination to Ceres' SchurEliminator; here both are explicit.
+//
+// HBM layout (SoA over observations sorted by point = CSR):
+//   obs_img int32[n_obs], obs_xy double2[n_obs], pt_start int64[n_pts+1]
+//   qvec double[n_img*4], tvec double[n_img*3], cam_params double[n_cam*4], xyz double[n_pts*3]
+//   pose_col int32[n_img*6], intr_col int32[n_cam*4]: column in the reduced system or -1
+//   ObsJac[n_obs]: residual, 2x10 camera Jacobian, 2x3 point Jacobian (Jacobi-scaled)
+//   S double[D*D] (row-major, entries with col_row <= col_col), rhs / g_c / diag_c double[D]
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "ba_common.cuh"
+
+namespace b2 {
+namespace bak {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+// One observation: residual and Jacobian blocks.  Returns false if only the residual is wanted.
+__device__ __forceinline__ void evaluate(int model, const double* q, const double* t, const double* X,
+                                         const double* k, double ox, double oy, double* r, double* Jc /*2x10*/,
+                                         double* Jp /*2x3*/) {
+  const double w = q[0], x = q[1], y = q[2], z = q[3];
+  const double t2 = w * x, t3 = w * y, t4 = w * z, t5 = -x * x, t6 = x * y, t7 = x * z, t8 = -y * y, t9 = y * z,
+               t1 = -z * z;
+  double p0 = 2 * ((t8 + t1) * X[0] + (t6 - t4) * X[1] + (t3 + t7) * X[2]) + X[0];
+  double p1 = 2 * ((t4 + t6) * X[0] + (t5 + t1) * X[1] + (t9 - t2) * X[2]) + X[1];
+  double p2 = 2 * ((t7 - t3) * X[0] + (t2 + t9) * X[1] + (t5 + t8) * X[2]) + X[2];
+  p0 += t[0];
+  p1 += t[1];
+  p2 += t[2];
+  const double u = p0 / p2, v = p1 / p2;
+  double xi, yi, dxdu, dxdv, dydu, dydv;
+  double dk0[4] = {0, 0, 0, 0}, dk1[4] = {0, 0, 0, 0};
+  if (model == 0) {
+    xi = k[0] * u + k[1]; yi = k[0] * v + k[2];
+    dxdu = k[0]; dxdv = 0; dydu = 0; dydv = k[0];
+    dk0[0] = u; dk0[1] = 1; dk1[0] = v; dk1[2] = 1;
+  } else if (model == 1) {
+    xi = k[0] * u + k[2]; yi = k[1] * v + k[3];
+    dxdu = k[0]; dxdv = 0; dydu = 0; dydv = k[1];
+    dk0[0] = u; dk0[2] = 1; dk1[1] = v; dk1[3] = 1;
+  } else {
+    const double u2 = u * u, v2 = v * v, r2 = u2 + v2, radial = k[3] * r2;
+    const double du = u * radial, dv = v * radial;
+    const double xd = u + du, yd = v + dv;
+    xi = k[0] * xd + k[1]; yi = k[0] * yd + k[2];
+    dxdu = k[0] * (1 + radial + 2 * k[3] * u2); dxdv = k[0] * (2 * k[3] * u * v);
+    dydu = k[0] * (2 * k[3] * u * v); dydv = k[0] * (1 + radial + 2 * k[3] * v2);
+    dk0[0] = xd; dk0[1] = 1; dk0[3] = k[0] * u * r2;
+    dk1[0] = yd; dk1[2] = 1; dk1[3] = k[0] * v * r2;
+  }
+  r[0] = xi - ox;
+  r[1] = yi - oy;
+  if (!Jc) return;
+  const double ip2 = 1.0 / p2;
+  const double dudp[3] = {ip2, 0, -p0 * ip2 * ip2}, dvdp[3] = {0, ip2, -p1 * ip2 * ip2};
+  double drdp[2][3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    drdp[0][c] = dxdu * dudp[c] + dxdv * dvdp[c];
+    drdp[1][c] = dydu * dudp[c] + dydv * dvdp[c];
+  }
+  const double R[3][3] = {{2 * (t8 + t1) + 1, 2 * (t6 - t4), 2 * (t3 + t7)},
+                          {2 * (t4 + t6), 2 * (t5 + t1) + 1, 2 * (t9 - t2)},
+                          {2 * (t7 - t3), 2 * (t2 + t9), 2 * (t5 + t8) + 1}};
+  const double X0 = X[0], X1 = X[1], X2 = X[2];
+  const double dpdq[3][4] = {
+      {2 * (-z * X1 + y * X2), 2 * (y * X1 + z * X2), 2 * (-2 * y * X0 + x * X1 + w * X2), 2 * (-2 * z * X0 - w * X1 + x * X2)},
+      {2 * (z * X0 - x * X2), 2 * (y * X0 - 2 * x * X1 - w * X2), 2 * (x * X0 + z * X2), 2 * (w * X0 - 2 * z * X1 + y * X2)},
+      {2 * (-y * X0 + x * X1), 2 * (z * X0 + w * X1 - 2 * x * X2), 2 * (-w * X0 + z * X1 - 2 * y * X2), 2 * (x * X0 + y * X1)}};
+  const double JL[4][3] = {{-x, -y, -z}, {w, z, -y}, {-z, w, x}, {y, -x, w}};
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    double drdq[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) drdq[a] = drdp[i][0] * dpdq[0][a] + drdp[i][1] * dpdq[1][a] + drdp[i][2] * dpdq[2][a];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      Jc[10 * i + c] = drdq[0] * JL[0][c] + drdq[1] * JL[1][c] + drdq[2] * JL[2][c] + drdq[3] * JL[3][c];
+      Jc[10 * i + 3 + c] = drdp[i][c];
+      Jp[3 * i + c] = drdp[i][0] * R[0][c] + drdp[i][1] * R[1][c] + drdp[i][2] * R[2][c];
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) Jc[10 * i + 6 + a] = (i == 0) ? dk0[a] : dk1[a];
+  }
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+__device__ __forceinline__ void atomic_max_nonneg(double* addr, double v) {
+  atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
+}
+
+// ---------------------------------------------------------------- Jacobian
+// Thread per observation: residual, Jacobian (optionally Jacobi-scaled), cost.
+// mode 0: write ObsJac; mode 1: residual only at candidate parameters (cost);
+// mode 2: unscaled Jacobian -> squared column norms (Jacobi scaling set-up).
+__global__ void __launch_bounds__(256)
+jacobian_kernel(BaDev P, const double* __restrict__ q, const double* __restrict__ t, const double* __restrict__ kp,
+                const double* __restrict__ X, int mode, double* __restrict__ cost_out) {
+  const int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  double c = 0;
+  if (o < P.n_obs) {
+    const int i = P.obs_img[o], p = P.obs_pt[o], cm = P.img_cam[i];
+    const double2 xy = P.obs_xy[o];
+    double r[2], Jc[20], Jp[6];
+    if (mode == 1) {
+      evaluate(P.cam_model[cm], q + 4 * i, t + 3 * i, X + 3 * (int64_t)p, kp + 4 * cm, xy.x, xy.y, r, nullptr, nullptr);
+    } else {
+      evaluate(P.cam_model[cm], q + 4 * i, t + 3 * i, X + 3 * (int64_t)p, kp + 4 * cm, xy.x, xy.y, r, Jc, Jp);
+      int col[10];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) col[k] = P.pose_col[6 * i + k];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) col[6 + k] = P.intr_col[4 * cm + k];
+      const int pc = P.pt_col[p];
+      if (mode == 2) {
+#pragma unroll
+        for (int k = 0; k < 10; ++k)
+          if (col[k] >= 0) atomicAdd(P.colnorm_c + col[k], Jc[k] * Jc[k] + Jc[10 + k] * Jc[10 + k]);
+        if (pc >= 0)
+#pragma unroll
+          for (int k = 0; k < 3; ++k) atomicAdd(P.colnorm_p + 3 * (int64_t)pc + k, Jp[k] * Jp[k] + Jp[3 + k] * Jp[3 + k]);
+      } else {
+        ObsJac& e = P.J[o];
+        e.r[0] = r[0];
+        e.r[1] = r[1];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) {
+          const double s = (col[k] >= 0) ? P.scale_c[col[k]] : 0.0;
+          e.Jc[k] = Jc[k] * s;
+          e.Jc[10 + k] = Jc[10 + k] * s;
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const double s = (pc >= 0) ? P.scale_p[3 * (int64_t)pc + k] : 0.0;
+          e.Jp[k] = Jp[k] * s;
+          e.Jp[3 + k] = Jp[3 + k] * s;
+        }
+      }
+    }
+    c = r[0] * r[0] + r[1] * r[1];
+  }
+  c = warp_sum(c);
+  __shared__ double ws[8];
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) s += ws[k];
+    atomicAdd(cost_out, 0.5 * s);
+  }
+}
+
+// ------------------------------------------------------------ camera terms
+// Thread per observation: U = Jc^T Jc into S (upper entries), g_c = Jc^T r, diag_c.
+__global__ void __launch_bounds__(256) camera_terms_kernel(BaDev P) {
+  const int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (o >= P.n_obs) return;
+  const int i = P.obs_img[o], cm = P.img_cam[i];
+  int col[10];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) col[k] = P.pose_col[6 * i + k];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) col[6 + k] = P.intr_col[4 * cm + k];
+  const ObsJac& e = P.J[o];
+  const int64_t D = P.D;
+#pragma unroll
+  for (int k = 0; k < 10; ++k) {
+    if (col[k] < 0) continue;
+    const double a0 = e.Jc[k], a1 = e.Jc[10 + k];
+    atomicAdd(P.g_c + col[k], a0 * e.r[0] + a1 * e.r[1]);
+    atomicAdd(P.diag_c + col[k], a0 * a0 + a1 * a1);
+#pragma unroll
+    for (int l = 0; l < 10; ++l) {
+      if (col[l] < 0 || col[k] > col[l]) continue;
+      atomicAdd(P.S + col[k] * D + col[l], a0 * e.Jc[l] + a1 * e.Jc[10 + l]);
+    }
+  }
+}
+
+// ----------------------------------------------------------------- Schur
+// One block per point (grid-stride): V = sum Jp^T Jp + D_p, V^-1, t_p = V^-1 g_p,
+// W_a = Jc_a^T Jp_a, Y_a = W_a V^-1; rhs -= W_a t_p; S -= Y_a W_b^T for all pairs (a,b)
+// of the point's observations (only entries with col_a <= col_b: one triangle feeds the
+// Cholesky).  Tracks longer than kTile are processed in kTile x kTile tiles.
+constexpr int kTile = 32;
+constexpr int kSchurThreads = 128;
+
+__global__ void __launch_bounds__(kSchurThreads) schur_kernel(BaDev P, double radius, double min_diag, double max_diag) {
+  __shared__ double sWa[kTile][30], sYa[kTile][30], sWb[kTile][30];
+  __shared__ int sCa[kTile][10], sCb[kTile][10];
+  __shared__ double sV[9], sT[3], sG[3];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t D = P.D;
+  for (int p = blockIdx.x; p < P.n_pts; p += gridDim.x) {
+    const int pc = P.pt_col[p];
+    if (pc < 0) continue;  // constant point: contributes camera terms only
+    const int64_t o0 = P.pt_start[p];
+    const int L = (int)(P.pt_start[p + 1] - o0);
+    // ---- V, g_p (warp 0)
+    if (warp == 0) {
+      double v[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
+      for (int a = lane; a < L; a += 32) {
+        const ObsJac& e = P.J[o0 + a];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const double j0 = e.Jp[3 * i], j1 = e.Jp[3 * i + 1], j2 = e.Jp[3 * i + 2], r = e.r[i];
+          v[0] += j0 * j0; v[1] += j0 * j1; v[2] += j0 * j2; v[3] += j1 * j1; v[4] += j1 * j2; v[5] += j2 * j2;
+          g[0] += j0 * r; g[1] += j1 * r; g[2] += j2 * r;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 6; ++k) v[k] = warp_sum(v[k]);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) g[k] = warp_sum(g[k]);
+      if (lane == 0) {
+        P.diag_p[3 * (int64_t)pc] = v[0];
+        P.diag_p[3 * (int64_t)pc + 1] = v[3];
+        P.diag_p[3 * (int64_t)pc + 2] = v[5];
+        P.g_p[3 * (int64_t)pc] = g[0];
+        P.g_p[3 * (int64_t)pc + 1] = g[1];
+        P.g_p[3 * (int64_t)pc + 2] = g[2];
+        // gradient max norm of the unscaled problem
+        double gm = 0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) gm = fmax(gm, fabs(g[k] / P.scale_p[3 * (int64_t)pc + k]));
+        atomic_max_nonneg(P.gmax, gm);
+        const double V00 = v[0] + fmin(fmax(v[0], min_diag), max_diag) / radius;
+        const double V11 = v[3] + fmin(fmax(v[3], min_diag), max_diag) / radius;
+        const double V22 = v[5] + fmin(fmax(v[5], min_diag), max_diag) / radius;
+        const double V01 = v[1], V02 = v[2], V12 = v[4];
+        const double c00 = V11 * V22 - V12 * V12, c01 = V12 * V02 - V01 * V22, c02 = V01 * V12 - V11 * V02;
+        const double det = V00 * c00 + V01 * c01 + V02 * c02, id = 1.0 / det;
+        double Vi[9];
+        Vi[0] = c00 * id; Vi[1] = (V02 * V12 - V01 * V22) * id; Vi[2] = (V01 * V12 - V02 * V11) * id;
+        Vi[3] = c01 * id; Vi[4] = (V00 * V22 - V02 * V02) * id; Vi[5] = (V02 * V01 - V00 * V12) * id;
+        Vi[6] = c02 * id; Vi[7] = (V01 * V02 - V00 * V12) * id; Vi[8] = (V00 * V11 - V01 * V01) * id;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { sV[k] = Vi[k]; P.Vinv[9 * (int64_t)pc + k] = Vi[k]; }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { sT[k] = Vi[3 * k] * g[0] + Vi[3 * k + 1] * g[1] + Vi[3 * k + 2] * g[2]; sG[k] = g[k]; }
+      }
+    }
+    __syncthreads();
+    for (int a0 = 0; a0 < L; a0 += kTile) {
+      const int na = min(kTile, L - a0);
+      // W_a, Y_a, columns of the a-tile; rhs -= W_a t_p
+      for (int e = tid; e < na * 10; e += kSchurThreads) {
+        const int a = e / 10, k = e % 10;
+        const ObsJac& ob = P.J[o0 + a0 + a];
+        const int i = P.obs_img[o0 + a0 + a];
+        const int col = (k < 6) ? P.pose_col[6 * i + k] : P.intr_col[4 * P.img_cam[i] + (k - 6)];
+        sCa[a][k] = col;
+        double w[3];
+#pragma unroll
+        for (int l = 0; l < 3; ++l) w[l] = ob.Jc[k] * ob.Jp[l] + ob.Jc[10 + k] * ob.Jp[3 + l];
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+          sWa[a][3 * k + l] = w[l];
+          sYa[a][3 * k + l] = w[0] * sV[l] + w[1] * sV[3 + l] + w[2] * sV[6 + l];
+        }
+        if (col >= 0) atomicAdd(P.rhs + col, -(w[0] * sT[0] + w[1] * sT[1] + w[2] * sT[2]));
+      }
+      __syncthreads();
+      for (int b0 = 0; b0 < L; b0 += kTile) {
+        const int nb = min(kTile, L - b0);
+        if (b0 == a0) {
+          for (int e = tid; e < nb * 30; e += kSchurThreads) sWb[e / 30][e % 30] = sWa[e / 30][e % 30];
+          for (int e = tid; e < nb * 10; e += kSchurThreads) sCb[e / 10][e % 10] = sCa[e / 10][e % 10];
+        } else {
+          for (int e = tid; e < nb * 10; e += kSchurThreads) {
+            const int b = e / 10, k = e % 10;
+            const ObsJac& ob = P.J[o0 + b0 + b];
+            const int i = P.obs_img[o0 + b0 + b];
+            sCb[b][k] = (k < 6) ? P.pose_col[6 * i + k] : P.intr_col[4 * P.img_cam[i] + (k - 6)];
+#pragma unroll
+            for (int l = 0; l < 3; ++l) sWb[b][3 * k + l] = ob.Jc[k] * ob.Jp[l] + ob.Jc[10 + k] * ob.Jp[3 + l];
+          }
+        }
+        __syncthreads();
+        const int total = na * nb * 100;
+        for (int e = tid; e < total; e += kSchurThreads) {
+          const int l = e % 10, k = (e / 10) % 10, ab = e / 100, b = ab % nb, a = ab / nb;
+          const int ca = sCa[a][k], cb = sCb[b][l];
+          if (ca < 0 || cb < 0 || ca > cb) continue;
+          const double v = sYa[a][3 * k] * sWb[b][3 * l] + sYa[a][3 * k + 1] * sWb[b][3 * l + 1] +
+                           sYa[a][3 * k + 2] * sWb[b][3 * l + 2];
+          atomicAdd(P.S + ca * D + cb, -v);
+        }
+        __syncthreads();
+      }
+    }
+  }
+}
+
+// S_jj += clamp(diag_c) / radius, rhs = g_c - sum W V^-1 g_p, gradient max norm over camera columns.
+__global__ void add_diag_kernel(BaDev P, double radius, double min_diag, double max_diag) {
+  const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (j >= P.D) return;
+  P.S[j * P.D + j] += fmin(fmax(P.diag_c[j], min_diag), max_diag) / radius;
+  P.rhs[j] += P.g_c[j];  // rhs held only the Schur part -sum W V^-1 g_p so far
+  atomic_max_nonneg(P.gmax, fabs(P.g_c[j] / P.scale_c[j]));
+}
+
+// ----------------------------------------------------------- back-substitution
+// Warp per point: dp = -V^-1 (g_p + sum_a Jp_a^T (Jc_a dc)).
+__global__ void __launch_bounds__(256) backsub_kernel(BaDev P) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wid = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (wid >= P.n_pts) return;
+  const int p = (int)wid, pc = P.pt_col[p];
+  if (pc < 0) return;
+  const int64_t o0 = P.pt_start[p];
+  const int L = (int)(P.pt_start[p + 1] - o0);
+  double s[3] = {0, 0, 0};
+  for (int a = lane; a < L; a += 32) {
+    const ObsJac& e = P.J[o0 + a];
+    const int i = P.obs_img[o0 + a], cm = P.img_cam[i];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      double jd = 0;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) { const int c = P.pose_col[6 * i + k]; if (c >= 0) jd += e.Jc[10 * r + k] * P.dc[c]; }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { const int c = P.intr_col[4 * cm + k]; if (c >= 0) jd += e.Jc[10 * r + 6 + k] * P.dc[c]; }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) s[k] += e.Jp[3 * r + k] * jd;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) s[k] = warp_sum(s[k]) + P.g_p[3 * (int64_t)pc + k];
+  if (lane < 3) {
+    const double* Vi = P.Vinv + 9 * (int64_t)pc;
+    P.dp[3 * (int64_t)pc + lane] = -(Vi[3 * lane] * s[0] + Vi[3 * lane + 1] * s[1] + Vi[3 * lane + 2] * s[2]);
+  }
+}
+
+// model_cost_change = -sum m (r + m/2), m = J delta (thread per observation)
+__global__ void __launch_bounds__(256) model_cost_kernel(BaDev P, double* out) {
+  const int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  double acc = 0;
+  if (o < P.n_obs) {
+    const ObsJac& e = P.J[o];
+    const int i = P.obs_img[o], cm = P.img_cam[i], pc = P.pt_col[P.obs_pt[o]];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      double m = 0;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) { const int c = P.pose_col[6 * i + k]; if (c >= 0) m += e.Jc[10 * r + k] * P.dc[c]; }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { const int c = P.intr_col[4 * cm + k]; if (c >= 0) m += e.Jc[10 * r + 6 + k] * P.dc[c]; }
+      if (pc >= 0)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) m += e.Jp[3 * r + k] * P.dp[3 * (int64_t)pc + k];
+      acc -= m * (e.r[r] + m / 2.0);
+    }
+  }
+  acc = warp_sum(acc);
+  __shared__ double ws[8];
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) s += ws[k];
+    atomicAdd(out, s);
+  }
+}
+
+// candidate parameters x + scale * delta; accumulates |step|^2 and |x|^2 in out[0], out[1]
+__global__ void candidate_cameras_kernel(BaDev P, double* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double st = 0, xs = 0;
+  if (i < P.n_img) {
+    double d[3] = {0, 0, 0};
+    bool any = false;
+    for (int k = 0; k < 3; ++k) {
+      const int c = P.pose_col[6 * i + k];
+      if (c >= 0) { d[k] = P.dc[c] * P.scale_c[c]; any = true; st += d[k] * d[k]; }
+    }
+    const double* x = P.qvec + 4 * i;
+    double* qo = P.qvec_new + 4 * i;
+    const double nd = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    if (any && nd > 0.0) {  // QuaternionParameterization::Plus
+      const double s = sin(nd) / nd;
+      const double q0 = cos(nd), q1 = s * d[0], q2 = s * d[1], q3 = s * d[2];
+      qo[0] = q0 * x[0] - q1 * x[1] - q2 * x[2] - q3 * x[3];
+      qo[1] = q0 * x[1] + q1 * x[0] + q2 * x[3] - q3 * x[2];
+      qo[2] = q0 * x[2] - q1 * x[3] + q2 * x[0] + q3 * x[1];
+      qo[3] = q0 * x[3] + q1 * x[2] - q2 * x[1] + q3 * x[0];
+    } else {
+      for (int k = 0; k < 4; ++k) qo[k] = x[k];
+    }
+    for (int k = 0; k < 4; ++k) xs += x[k] * x[k];
+    for (int k = 0; k < 3; ++k) {
+      const int c = P.pose_col[6 * i + 3 + k];
+      double v = 0;
+      if (c >= 0) { v = P.dc[c] * P.scale_c[c]; st += v * v; }
+      P.tvec_new[3 * i + k] = P.tvec[3 * i + k] + v;
+      xs += P.tvec[3 * i + k] * P.tvec[3 * i + k];
+    }
+  }
+  if (i < P.n_cam) {
+    for (int k = 0; k < 4; ++k) {
+      const int c = P.intr_col[4 * i + k];
+      double v = 0;
+      if (c >= 0) { v = P.dc[c] * P.scale_c[c]; st += v * v; }
+      P.cam_new[4 * i + k] = P.cam_params[4 * i + k] + v;
+      xs += P.cam_params[4 * i + k] * P.cam_params[4 * i + k];
+    }
+  }
+  st = warp_sum(st);
+  xs = warp_sum(xs);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(out, st);
+    atomicAdd(out + 1, xs);
+  }
+}
+__global__ void candidate_points_kernel(BaDev P, double* out) {
+  const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;  // coordinate index
+  double st = 0, xs = 0;
+  if (j < 3 * (int64_t)P.n_pts) {
+    const int p = (int)(j / 3), k = (int)(j % 3), pc = P.pt_col[p];
+    double v = 0;
+    if (pc >= 0) { v = P.dp[3 * (int64_t)pc + k] * P.scale_p[3 * (int64_t)pc + k]; st = v * v; }
+    P.xyz_new[j] = P.xyz[j] + v;
+    xs = P.xyz[j] * P.xyz[j];
+  }
+  st = warp_sum(st);
+  xs = warp_sum(xs);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(out + 2, st);
+    atomicAdd(out + 3, xs);
+  }
+}
+__global__ void make_scale_kernel(const double* colnorm, double* scale, int64_t n) {
+  const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (j < n) scale[j] = 1.0 / (1.0 + sqrt(colnorm[j]));
+}
+__global__ void negate_kernel(double* v, int64_t n) {
+  const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (j < n) v[j] = -v[j];
+}
+
+}  // namespace bak
+
+static inline unsigned nblk(int64_t n, int b) { return (unsigned)((n + b - 1) / b); }
+
+cudaError_t ba_launch_jacobian(const BaDev& P, const double* q, const double* t, const double* k, const double* X,
+                               int mode, double* cost_out, cudaStream_t s) {
+  if (P.n_obs == 0) return cudaSuccess;
+  bak::jacobian_kernel<<<nblk(P.n_obs, 256), 256, 0, s>>>(P, q, t, k, X, mode, cost_out);
+  return cudaGetLastError();
+}
+cudaError_t ba_launch_camera_terms(const BaDev& P, cudaStream_t s) {
+  if (P.n_obs == 0) return cudaSuccess;
+  bak::camera_terms_kernel<<<nblk(P.n_obs, 256), 256, 0, s>>>(P);
+  return cudaGetLastError();
+}
+cudaError_t ba_launch_schur(const BaDev& P, double radius, double min_diag, double max_diag, int n_sm, cudaStream_t s) {
+  if (P.n_pts == 0) return cudaSuccess;
+  const int grid = (int)std::min<int64_t>(P.n_pts, (int64_t)n_sm * 8);
+  bak::schur_kernel<<<grid, bak::kSchurThreads, 0, s>>>(P, radius, min_diag, max_diag);
+  return cudaGetLastError();
+}
+cudaError_t ba_launch_add_diag(const BaDev& P, double radius, double min_diag, double max_diag, cudaStream_t s) {
+  if (P.D == 0) return cudaSuccess;
+  bak::add_diag_kernel<<<nblk(P.D, 256), 256, 0, s>>>(P, radius, min_diag, max_diag);
+  return cudaGetLastError();
+}
+cudaError_t ba_launch_backsub(const BaDev& P, cudaStream_t s) {
+  if (P.n_pts == 0) return cudaSuccess;
+  bak::backsub_kernel<<<nblk((int64_t)P.n_pts * 32, 256), 256, 0, s>>>(P);
+  return cudaGetLastError();
+}
+cudaError_t ba_launch_model_cost(const BaDev& P, double* out, cudaStream_t s) {
+  if (P.n_obs == 0) return cudaSuccess;
+  bak::model_cost_kernel<<<nblk(P.n_obs, 256), 256, 0, s>>>(P, out);
+  return cudaGetLastError();
+}
+cudaError_t ba_launch_candidate(const BaDev& P, double* out, bool cameras, cudaStream_t s) {
+  if (cameras) {
+    const int n = std::max(P.n_img, P.n_cam);
+    if (n > 0) bak::candidate_cameras_kernel<<<nblk(n, 128), 128, 0, s>>>(P, out);
+  } else if (P.n_pts > 0) {
+    bak::candidate_points_kernel<<<nblk(3 * (int64_t)P.n_pts, 256), 256, 0, s>>>(P, out);
+  }
+  return cudaGetLastError();
+}
+cudaError_t ba_launch_make_scale(const double* colnorm, double* scale, int64_t n, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  bak::make_scale_kernel<<<nblk(n, 256), 256, 0, s>>>(colnorm, scale, n);
+  return cudaGetLastError();
+}
+cudaError_t ba_launch_negate(double* v, int64_t n, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  bak::negate_kernel<<<nblk(n, 256), 256, 0, s>>>(v, n);
+  return cudaGetLastError();
+}
+
+}  // namespace b2

@@ -205,6 +205,77 @@ int b2_verify_debug_solve(b2_verifier* v, int32_t type, int32_t n, const double*
 /* Device seconds (CUDA events) of the last b2_verify_pairs* call. */
 int b2_verify_last_timing(b2_verifier* v, double* kernel_s);
 
+/* ===================================================================== BA ==
+ * Replaces: BundleAdjuster::Solve (src/optim/bundle_adjustment.h:165-197,
+ * .cc:258-310) as configured by DistributedMapperController::GlobalBundleAdjustment /
+ * AdjustGlobalBundle (src/controllers/distributed_mapper_controller.cpp:522-542,836-933)
+ * and BundleAdjustmentController::Run (src/controllers/bundle_adjustment.cc:69-103):
+ * reprojection residuals of BundleAdjustmentCostFunction / ...ConstantPoseCostFunction
+ * (src/base/cost_functions.h:44-158), QuaternionParameterization on qvec,
+ * SubsetParameterization on tvec / intrinsics, constant cameras / poses / points
+ * (bundle_adjustment.cc:338-526), and the Levenberg-Marquardt + Schur-complement solve
+ * that ceres::Solve performs with DENSE_SCHUR / SPARSE_SCHUR (exact step; the
+ * ITERATIVE_SCHUR regime above 1000 images is not covered yet).
+ * The problem is passed the way ParallelBundleAdjuster::SetUp packs it for PBA
+ * (bundle_adjustment.cc:654-772): flat arrays, observations sorted by point.
+ * All parameters are updated IN PLACE (as Ceres updates Image::Qvec/Tvec,
+ * Camera::Params, Point3D::XYZ).
+ */
+typedef struct b2_ba b2_ba;
+
+typedef struct b2_ba_problem {
+  int32_t n_images, n_cameras, n_points;
+  int64_t n_obs;
+  double* qvec;              /* [n_images][4] w,x,y,z   (normalised on entry, .cc:345) */
+  double* tvec;              /* [n_images][3] */
+  const int32_t* image_camera; /* [n_images] -> camera (intrinsics may be shared, .cc:349) */
+  const uint8_t* const_pose;   /* [n_images] 1 = BundleAdjustmentConfig::SetConstantPose     */
+  const uint8_t* const_tvec;   /* [n_images] bitmask of SetConstantTvec components           */
+  const int32_t* camera_model; /* [n_cameras] 0 SIMPLE_PINHOLE 1 PINHOLE 2 SIMPLE_RADIAL     */
+  double* camera_params;       /* [n_cameras][4] */
+  const uint8_t* const_camera; /* [n_cameras] 1 = BundleAdjustmentConfig::SetConstantCamera  */
+  double* xyz;                 /* [n_points][3] */
+  const uint8_t* const_point;  /* [n_points] 1 = AddConstantPoint */
+  const int32_t* obs_image;    /* [n_obs] */
+  const int32_t* obs_point;    /* [n_obs] non-decreasing (sorted by point => CSR) */
+  const double* obs_xy;        /* [n_obs][2] */
+} b2_ba_problem;
+
+typedef struct b2_ba_options {   /* BundleAdjustmentOptions (bundle_adjustment.h:48-103) */
+  int32_t max_num_iterations;    /* solver_options.max_num_iterations (final BA: 50)      */
+  int32_t refine_focal_length;   /* 1 */
+  int32_t refine_principal_point;/* 0 */
+  int32_t refine_extra_params;   /* 1 */
+  double function_tolerance;     /* final BA: 0   */
+  double gradient_tolerance;     /* final BA: 1.0 */
+  double parameter_tolerance;    /* final BA: 0   */
+} b2_ba_options;
+
+typedef struct b2_ba_summary {   /* the fields of ceres::Solver::Summary the reference reads */
+  double initial_cost, final_cost;      /* 1/2 sum r^2 */
+  int32_t num_successful_steps, num_unsuccessful_steps;
+  int32_t termination_type;             /* 0 CONVERGENCE, 1 NO_CONVERGENCE, 2 FAILURE */
+  int32_t num_residuals_reduced, num_effective_parameters_reduced;
+  int32_t num_iterations;               /* successful + unsuccessful */
+  double solve_seconds;                 /* device time of the LM loop (CUDA events) */
+  double schur_kernel_seconds;          /* ... of which inside the Jacobian+Schur kernels */
+  int64_t schur_kernel_launches;
+} b2_ba_summary;
+
+/* Collective hook for multi-GPU runs (points sharded across ranks, cameras replicated):
+ * called with a DEVICE buffer of n doubles that must be reduced in place across all ranks
+ * (op 0 = SUM, 1 = MAX) before returning.  NULL (default) = single GPU. */
+typedef void (*b2_allreduce_fn)(void* dev_buf, int64_t n_doubles, int32_t op, void* user);
+
+void b2_ba_default_options(b2_ba_options* opt);   /* GlobalBundleAdjustment() values */
+int b2_ba_create(int device, b2_ba** out);
+int b2_ba_destroy(b2_ba* h);
+int b2_ba_set_allreduce(b2_ba* h, b2_allreduce_fn fn, void* user);
+/* Solves the problem (HOST arrays in, parameters updated in place).  On a multi-GPU run
+ * every rank passes ALL cameras/images and ITS shard of points + observations. */
+int b2_ba_solve(b2_ba* h, const b2_ba_problem* problem, const b2_ba_options* opt,
+                b2_ba_summary* summary);
+
 #ifdef __cplusplus
 }
 #endif
