@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--desc", type=int, default=4096)
     ap.add_argument("--pairs", type=int, default=0, help="limit pairs per step (0 = exhaustive)")
     ap.add_argument("--cpu-sample", type=int, default=48, help="pairs in the CPU baseline sample")
+    ap.add_argument("--verify-pairs", type=int, default=20000, help="pairs in the verification leg (0 = skip)")
+    ap.add_argument("--ba", default="500,100000,10", help="BA leg: images,points,track (empty = skip)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -76,6 +78,24 @@ def make_descriptors_torch(n_img, n_desc, seed, device):
         perm = torch.randperm(n_desc, generator=g, device=device)
         out[i] = d[perm]
     return out
+
+
+def effective_cores() -> int:
+    """Host threads the process may actually use: affinity mask capped by the cgroup CPU quota."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = Path("/sys/fs/cgroup/cpu.max").read_text().split()
+        if q != "max":
+            n = max(1, min(n, int(float(q) / float(per) + 0.5)))
+    except Exception:
+        try:
+            q = int(Path("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read_text())
+            per = int(Path("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read_text())
+            if q > 0:
+                n = max(1, min(n, int(q / per + 0.5)))
+        except Exception:
+            pass
+    return n
 
 
 def all_pairs(n_img, limit=0):
@@ -135,12 +155,114 @@ def cpu_reference(descs_host, pairs, n_sample, threads):
     return len(sample) / secs, secs, len(sample), counts, idx
 
 
+
+def peaks_hbm():
+    try:
+        return json.loads((ROOT / "MEASURED_PEAKS.json").read_text()).get("hbm_gbs", 6650.0), "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+def bench_verify(a, local_rank, rank, world, cores, barrier):
+    """Two-view verification throughput: b2_verify_pairs (host buffers in / out) on synthetic
+    matched pairs; CPU baseline = oracle port of TwoViewGeometry::Estimate, `cores` workers."""
+    from dagsfm_b200 import Camera, TwoViewGeometryVerifier, TwoViewOptions
+    from tests.tv_scene import make_pairs
+    w = make_pairs(a.verify_pairs, seed=7 + rank)
+    n = len(w["pairs"])
+    cams = [Camera.make(params=w["cam_params"], prior_focal=bool(p)) for p in w["prior"]]
+    v = TwoViewGeometryVerifier(local_rank)
+    v.set_images(cams, w["keypoints"])
+    opt = TwoViewOptions.default()
+    seeds = (np.arange(n) * 2654435761 % (2 ** 32)).astype(np.uint32)
+    res, inl = v.verify_pairs(w["pairs"], w["match_offsets"], w["matches"], opt, seeds)   # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    res, inl = v.verify_pairs(w["pairs"], w["match_offsets"], w["matches"], opt, seeds)
+    barrier()
+    wall = time.perf_counter() - t0
+    kern = v.last_kernel_seconds()
+    out = {"pairs": n * world, "matches_per_pair": float(w["match_offsets"][-1] / n),
+           "pairs_per_s_e2e": n * world / wall, "pairs_per_s_kernel": n * world / kern,
+           "config_histogram": {int(k): int(c) for k, c in zip(*np.unique(res["config"], return_counts=True))},
+           "inlier_recall": float((res["n_inliers"] >= 0.9 * w["n_inliers_true"]).mean()),
+           "api": "b2_verify_pairs (host buffers)"}
+    if rank == 0 and not a.no_cpu:
+        from oracle import pyoracle as orc
+        import ctypes as C
+        ns = min(n, max(64, 2 * cores))
+        ocams = (orc.OrcCamera * (2 * ns))(*[orc.make_camera(params=w["cam_params"], prior=bool(p)) for p in w["prior"][:2 * ns]])
+        ptrs = (C.c_void_p * (2 * ns))(*[k.ctypes.data for k in w["keypoints"][:2 * ns]])
+        oo = orc.tv_default_options()
+        ores = (orc.OrcTvResult * ns)()
+        off = np.ascontiguousarray(w["match_offsets"][:ns + 1])
+        secs = orc._tv().orc_two_view_pairs_mt(C.cast(ocams, C.c_void_p), C.cast(ptrs, C.c_void_p),
+                                               w["pairs"].ctypes.data, ns, off.ctypes.data, w["matches"].ctypes.data,
+                                               C.byref(oo), seeds.ctypes.data, cores, C.cast(ores, C.c_void_p))
+        same = sum(int(ores[i].config == res["config"][i] and ores[i].n_inliers == res["n_inliers"][i]) for i in range(ns))
+        out["cpu_baseline"] = {"value": ns / secs, "unit": "pairs/s", "cores": cores, "kind": "port",
+                               "sample": f"{ns} pairs, {secs:.1f} s, oracle port of TwoViewGeometry::Estimate",
+                               "identical_to_gpu": f"{same}/{ns}"}
+    v.close()
+    return out
+
+
+def bench_ba(a, local_rank, rank, world, cores, barrier, hbm):
+    """Final-BA leg (BASELINE configs[3]): LM iterations per second of b2_ba_solve and the HBM
+    roofline of the Jacobian+Schur kernels; CPU baseline = the reference's vendored PBA."""
+    from dagsfm_b200 import BundleAdjuster, BundleAdjustmentOptions
+    from tests.ba_scene import copy_problem, make_ba_problem, reprojection_rms
+    n_img, n_pts, track = (int(x) for x in a.ba.split(","))
+    prob0 = make_ba_problem(n_img=n_img, n_pts=n_pts, track_len=track, seed=1)
+    n_obs = len(prob0["obs_img"])
+    opt = BundleAdjustmentOptions.default()
+    prob = copy_problem(prob0)
+    ba = BundleAdjuster(opt, device=local_rank)
+    ba.Solve(prob)                                    # warm-up (cuSOLVER workspace, clocks)
+    prob = copy_problem(prob0)
+    barrier()
+    t0 = time.perf_counter()
+    s = ba.Solve(prob)
+    barrier()
+    wall = time.perf_counter() - t0
+    iters = s.num_iterations + (1 if s.termination_type == 0 else 0)   # the converged check costs one build
+    D = 8 * n_img - 7 - 0   # pose 6 + f,k per image, minus the 7 gauge parameters
+    # algorithmic bytes per LM iteration (SURVEY 8d): 24 N_obs + 28 N_pts + 88 N_cam reads,
+    # 72 N_pts + 64 N_cam + 8 * (upper triangle of the dense reduced system) writes
+    alg_bytes = 24 * n_obs + 28 * n_pts + 88 * n_img + 72 * n_pts + 64 * n_img + 8 * (D * (D + 1) // 2)
+    schur_ms = 1e3 * s.schur_kernel_seconds / max(s.schur_kernel_launches // 2, 1)
+    achieved = alg_bytes / (schur_ms * 1e-3) / 1e9
+    out = {"workload": f"{n_img} cams / {n_pts} pts / {n_obs} obs, track {track}, SIMPLE_RADIAL, final-BA options",
+           "lm_iter_per_s": s.num_iterations / s.solve_seconds, "lm_iterations": s.num_iterations,
+           "successful": s.num_successful_steps, "unsuccessful": s.num_unsuccessful_steps,
+           "termination": s.termination_type, "solve_s": s.solve_seconds, "e2e_s": wall,
+           "rms_px_initial": reprojection_rms(prob0), "rms_px_final": reprojection_rms(prob),
+           "ceres_style_px": float(np.sqrt(s.final_cost / (2 * n_obs))),
+           "roofline": {"bound": "hbm", "kernel": "camera_terms_kernel + schur_kernel", "achieved": achieved,
+                        "peak": hbm[0], "unit": "GB/s", "frac": achieved / hbm[0], "peak_source": hbm[1],
+                        "algorithmic_bytes_per_iteration": alg_bytes, "avg_ms_per_iteration": schur_ms,
+                        "share_of_solve": s.schur_kernel_seconds / s.solve_seconds, "traffic": None,
+                        "note": "FP64 atomics into the dense reduced system dominate; see DESIGN.md"}}
+    if rank == 0 and not a.no_cpu:
+        from oracle import pyoracle as orc
+        if orc.pba_ref_available():
+            pc = copy_problem(prob0)
+            r = orc.pba_ref_solve(pc, n_threads=cores, max_iter=50)
+            out["cpu_baseline"] = {"value": r["lm_iterations"] / r["seconds"], "unit": "LM iter/s", "cores": cores,
+                                   "kind": "reference", "sample": f"vendored PBA CPU double, {r['lm_iterations']} LM iterations, {r['seconds']:.1f} s",
+                                   "final_mse_px2": float(r["final_mse"]),
+                                   "gpu_final_mse_px2": float(2 * s.final_cost / n_obs)}
+    ba.close()
+    return out
+
+
 def main():
     a = parse()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    cores = os.cpu_count() or 1
+    cores = effective_cores()
+    a.cpu_sample = max(a.cpu_sample, 2 * cores)   # every host core gets at least two pairs
     workload = f"C2: {a.images} images x {a.desc} desc, exhaustive match + ratio test"
     cfg = {"workload": workload, "n_images": a.images, "desc_per_image": a.desc,
            "options": "max_ratio 0.8, max_distance 0.7, cross_check 1",
@@ -265,6 +387,16 @@ def main():
                "api": "b2_match_set_images + b2_match_pairs (host buffers)"}
         m.set_images_device(desc.data_ptr(), row_off, n_desc)
 
+
+    # ------------------------------------------------------- verification leg (SURVEY C3 flavour)
+    verify = None
+    if a.verify_pairs > 0:
+        verify = bench_verify(a, local_rank, rank, world, cores, barrier)
+    # ------------------------------------------------------- bundle adjustment leg
+    ba = None
+    if a.ba:
+        ba = bench_ba(a, local_rank, rank, world, cores, barrier, peaks_hbm())
+
     if rank != 0:
         return
 
@@ -303,6 +435,7 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "u8 x u8 -> s32 (exact)", "data": "synthetic",
         "config": cfg, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "roofline": roofline, "cpu_baseline": cpu,
+        "verify": verify, "ba": ba,
         "wall_ms_per_step": 1e3 * wall / a.steps, "matches_per_step": int(total),
         "fixup_candidates_last_chunk_sum": int(cands),
     }))

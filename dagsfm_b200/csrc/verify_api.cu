@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -111,6 +113,13 @@ int run_device(b2_verifier* v, int64_t n_pairs, const uint32_t* pairs, const int
   a.m_cap = m_cap;
   a.work_counter = v->d_counter;
   a.err = v->d_err;
+  a.prof = nullptr;
+  unsigned long long* d_prof = nullptr;
+  if (getenv("B2_VERIFY_PROFILE")) {
+    B2_CUDA(cudaMalloc(&d_prof, 8 * sizeof(unsigned long long)));
+    B2_CUDA(cudaMemsetAsync(d_prof, 0, 8 * sizeof(unsigned long long), s));
+    a.prof = d_prof;
+  }
   B2_CUDA(cudaEventRecord(v->ev0, s));
   B2_CUDA(launch_verify_pairs(a, blocks, s));
   B2_CUDA(cudaEventRecord(v->ev1, s));
@@ -121,6 +130,13 @@ int run_device(b2_verifier* v, int64_t n_pairs, const uint32_t* pairs, const int
   float ms = 0;
   B2_CUDA(cudaEventElapsedTime(&ms, v->ev0, v->ev1));
   v->last_kernel_s = ms * 1e-3;
+  if (d_prof) {
+    unsigned long long hp[8];
+    cudaMemcpy(hp, d_prof, sizeof hp, cudaMemcpyDeviceToHost);
+    cudaFree(d_prof);
+    fprintf(stderr, "[b2 verify profile] warp-cycles: sample %.3g solve %.3g score %.3g lo %.3g | E %.3g F %.3g H %.3g T %.3g | kernel %.3f s\n",
+            (double)hp[0], (double)hp[1], (double)hp[2], (double)hp[3], (double)hp[4], (double)hp[5], (double)hp[6], (double)hp[7], v->last_kernel_s);
+  }
   if (err) return set_error(B2_ERR_INVALID, "pair references an image outside the store");
   return B2_OK;
 }

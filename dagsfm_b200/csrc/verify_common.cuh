@@ -36,6 +36,7 @@ struct VerifyArgs {
   int32_t m_cap;           // max matches of any pair in this call
   unsigned long long* work_counter;
   int* err;
+  unsigned long long* prof;  // optional [8] cycle counters: sample, solve, score, lo, gather, other (B2_VERIFY_PROFILE=1)
 };
 
 size_t verify_scratch_stride(int m_cap);

@@ -191,6 +191,12 @@ __device__ inline unsigned long long compute_num_trials(unsigned long long num_i
 __device__ void warp_jacobi9(double* G, int rows, int ld, double* V, double* sig, int lane) {
   for (int i = lane; i < 81; i += 32) V[i] = (i / 9 == i % 9) ? 1.0 : 0.0;
   __syncwarp();
+  double frob2 = 0;
+  for (int c = 0; c < 9; ++c)
+    for (int i = lane; i < rows; i += 32) frob2 += G[(size_t)c * ld + i] * G[(size_t)c * ld + i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) frob2 += __shfl_xor_sync(kFull, frob2, o);
+  const double tiny = frob2 * 1e-40;
   for (int sweep = 0; sweep < 60; ++sweep) {
     bool rotated = false;
     for (int p = 0; p < 8; ++p) {
@@ -210,7 +216,7 @@ __device__ void warp_jacobi9(double* G, int rows, int ld, double* V, double* sig
           beta += __shfl_xor_sync(kFull, beta, o);
           gamma += __shfl_xor_sync(kFull, gamma, o);
         }
-        if (gamma == 0.0 || fabs(gamma) <= kEps * sqrt(alpha * beta)) continue;
+        if (gamma == 0.0 || (alpha <= tiny || beta <= tiny) || fabs(gamma) <= kEps * sqrt(alpha * beta)) continue;
         rotated = true;
         const double zeta = (beta - alpha) / (2.0 * gamma);
         const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
@@ -390,6 +396,7 @@ struct Scratch {
   double* lomodels;                // [10][9] local models
   uint8_t* mask[3];                // E, F, H inlier masks                  [Mcap]
   uint8_t* tmask;                  // scratch mask
+  unsigned long long* prof;        // optional cycle counters
 };
 
 // LORANSAC::Estimate for one estimator over the matched points (P1,P2)[0..M).
@@ -429,6 +436,7 @@ __device__ void ransac_warp(int type, const double2* P1, const double2* P2, int 
       break;
     }
     const int nb = (int)((max_trials - t0) < 32ull ? (max_trials - t0) : 32ull);
+    const long long c0 = clock64();
     // --- lane 0: sample indices for trials t0 .. t0+nb-1 (Shuffle of the persistent vector)
     if (lane == 0) {
       const uint32_t last = (uint32_t)(M - 1);
@@ -444,6 +452,7 @@ __device__ void ransac_warp(int type, const double2* P1, const double2* P2, int 
       }
     }
     __syncwarp();
+    const long long c1 = clock64();
     // --- lane j: minimal solver of trial t0 + j
     {
       int nm = 0;
@@ -469,6 +478,8 @@ __device__ void ransac_warp(int type, const double2* P1, const double2* P2, int 
       sh.nm[lane] = nm;
     }
     __syncwarp();
+    const long long c2 = clock64();
+    long long lo_cycles = 0;
     // --- ordered replay
     for (int j = 0; j < nb; ++j) {
       const unsigned long long trial = t0 + j;
@@ -506,7 +517,9 @@ __device__ void ransac_warp(int type, const double2* P1, const double2* P2, int 
               N += __popc(bm);
             }
             __syncwarp();
+            const long long cl0 = clock64();
             const int nlm = local_estimate(type, P1, P2, sc.inl, N, sc.G, sc.ld, sh, sig_sh, sc.lomodels, lane);
+            lo_cycles += clock64() - cl0;
             for (int li = 0; li < nlm; ++li) {
               double lm[9];
               for (int k = 0; k < 9; ++k) lm[k] = sc.lomodels[9 * li + k];
@@ -532,6 +545,14 @@ __device__ void ransac_warp(int type, const double2* P1, const double2* P2, int 
           break;
         }
       }
+    }
+    if (sc.prof && lane == 0) {
+      const long long c3 = clock64();
+      atomicAdd(sc.prof + 0, (unsigned long long)(c1 - c0));
+      atomicAdd(sc.prof + 1, (unsigned long long)(c2 - c1));
+      atomicAdd(sc.prof + 2, (unsigned long long)(c3 - c2 - lo_cycles));
+      atomicAdd(sc.prof + 3, (unsigned long long)lo_cycles);
+      atomicAdd(sc.prof + 4 + (type == EST_E5 ? 0 : type == EST_F7 ? 1 : type == EST_H4 ? 2 : 3), (unsigned long long)(c3 - c0));
     }
     if (ended) break;
     t0 += nb;
@@ -649,6 +670,7 @@ verify_pairs_kernel(VerifyArgs A) {
     sc.mask[1] = base; base += mc;
     sc.mask[2] = base; base += mc;
     sc.tmask = base;
+    sc.prof = A.prof;
   }
   const b2_two_view_options& o = A.opt;
   for (;;) {

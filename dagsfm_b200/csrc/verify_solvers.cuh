@@ -29,6 +29,10 @@ template <int NMAX>
 __device__ void jacobi_svd(double* G, int m, int n, double* V, double* sig) {
   for (int i = 0; i < n; ++i)
     for (int j = 0; j < n; ++j) V[i * n + j] = (i == j) ? 1.0 : 0.0;
+  // numerically-zero (null space) column pairs are not rotated: alpha * beta would underflow
+  double frob2 = 0;
+  for (int i = 0; i < m * n; ++i) frob2 += G[i] * G[i];
+  const double tiny = frob2 * 1e-40;
   for (int sweep = 0; sweep < 60; ++sweep) {
     bool rotated = false;
     for (int p = 0; p < n - 1; ++p) {
@@ -40,7 +44,7 @@ __device__ void jacobi_svd(double* G, int m, int n, double* V, double* sig) {
           beta += gq * gq;
           gamma += gp * gq;
         }
-        if (gamma == 0.0 || fabs(gamma) <= kEps * sqrt(alpha * beta)) continue;
+        if (gamma == 0.0 || (alpha <= tiny || beta <= tiny) || fabs(gamma) <= kEps * sqrt(alpha * beta)) continue;
         rotated = true;
         const double zeta = (beta - alpha) / (2.0 * gamma);
         const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));

@@ -329,3 +329,50 @@ def ba_quat_plus(x, d):
     out = np.zeros(4)
     L.orc_ba_quat_plus(x.ctypes.data, d.ctypes.data, out.ctypes.data)
     return out
+
+
+# ------------------------------------------------- reference-owned BA (vendored PBA, oracle/_ref)
+PBA_REF_PATH = HERE / "_ref" / "libpba_ref.so"
+
+
+def pba_ref_available() -> bool:
+    return PBA_REF_PATH.exists()
+
+
+def pba_ref_solve(prob: dict, n_threads=8, max_iter=50):
+    """Runs the reference's vendored PBA (CPU double) on a tests/ba_scene problem with unshared
+    SIMPLE_RADIAL cameras.  Gauge: images with const pose become constant cameras (PBA cannot
+    fix partial extrinsics).  Returns dict(initial_mse, final_mse, lm_iterations, seconds) and
+    updates xyz in prob (float32-quantised, as PBA's interface is)."""
+    from tests.ba_scene import R_from_quat
+    L = C.CDLL(str(PBA_REF_PATH))
+    L.pba_ref_run.argtypes = [C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p,
+                                                             C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 5
+    n = len(prob["qvec"])
+    assert (prob["img_cam"] == np.arange(n)).all() and (prob["cam_model"] == 2).all()
+    f = np.ascontiguousarray(prob["cam_params"][:, 0]); k = np.ascontiguousarray(prob["cam_params"][:, 3])
+    R = np.ascontiguousarray(np.stack([R_from_quat(q) for q in prob["qvec"]]).reshape(n, 9))
+    t = np.ascontiguousarray(prob["tvec"])
+    cc = np.ascontiguousarray(prob["pose_const"])
+    xy = np.ascontiguousarray(prob["obs_xy"] - prob["cam_params"][prob["obs_img"], 1:3])
+    of, ok, oR, ot, st = np.zeros(n), np.zeros(n), np.zeros((n, 9)), np.zeros((n, 3)), np.zeros(4)
+    import os, sys
+    sys.stdout.flush()
+    saved = os.dup(1)
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    os.dup2(devnull, 1)                       # PBA prints its banner with std::cout
+    try:
+        _pba_call(L, n, f, k, R, t, cc, prob, xy, n_threads, max_iter, of, ok, oR, ot, st)
+    finally:
+        os.dup2(saved, 1)
+        os.close(saved)
+        os.close(devnull)
+    return {"initial_mse": st[0], "final_mse": st[1], "lm_iterations": int(st[2]), "seconds": st[3],
+            "focal": of, "radial": ok, "R": oR.reshape(n, 3, 3), "t": ot}
+
+
+def _pba_call(L, n, f, k, R, t, cc, prob, xy, n_threads, max_iter, of, ok, oR, ot, st):
+    L.pba_ref_run(n, f.ctypes.data, k.ctypes.data, R.ctypes.data, t.ctypes.data, cc.ctypes.data, len(prob["xyz"]),
+                  prob["xyz"].ctypes.data, len(prob["obs_img"]), xy.ctypes.data, prob["obs_pt"].ctypes.data,
+                  prob["obs_img"].ctypes.data, n_threads, max_iter, of.ctypes.data, ok.ctypes.data, oR.ctypes.data,
+                  ot.ctypes.data, st.ctypes.data)

@@ -96,6 +96,11 @@ static void jacobi_svd(const double* A, int m, int n, double* sigma, double* V, 
   std::vector<double> W((size_t)n * n, 0.0);
   for (int i = 0; i < n; ++i) W[i * n + i] = 1.0;
   const double eps = std::numeric_limits<double>::epsilon();
+  // A column whose squared norm is below 1e-40 of the matrix's is numerically zero (null
+  // space); rotating two of them against each other never converges (alpha * beta underflows).
+  double frob2 = 0;
+  for (size_t i = 0; i < G.size(); ++i) frob2 += G[i] * G[i];
+  const double tiny = frob2 * 1e-40;
   for (int sweep = 0; sweep < 60; ++sweep) {
     bool rotated = false;
     for (int p = 0; p < n - 1; ++p) {
@@ -107,7 +112,7 @@ static void jacobi_svd(const double* A, int m, int n, double* sigma, double* V, 
           beta += gq * gq;
           gamma += gp * gq;
         }
-        if (gamma == 0.0 || std::abs(gamma) <= eps * std::sqrt(alpha * beta)) continue;
+        if (gamma == 0.0 || (alpha <= tiny || beta <= tiny) || std::abs(gamma) <= eps * std::sqrt(alpha * beta)) continue;
         rotated = true;
         const double zeta = (beta - alpha) / (2.0 * gamma);
         const double t = (zeta >= 0 ? 1.0 : -1.0) / (std::abs(zeta) + std::sqrt(1.0 + zeta * zeta));

@@ -50,16 +50,17 @@ def make_ba_problem(n_img=20, n_pts=400, track_len=6, seed=0, noise_px=2.0, pose
         q_true[i] = quat_from_R(R)
         t_true[i] = -R @ C
     # points: each belongs to a ring position and is seen by the track_len nearest cameras
+    # (a contiguous window of the ring, chosen by locality) -- vectorised
     pa = rng.uniform(0, 2 * np.pi, n_pts)
     X = rng.uniform(-1, 1, (n_pts, 3)) * [2.0, 1.5, 2.0]
-    obs_img, obs_pt, obs_xy = [], [], []
-    for p in range(n_pts):
-        d = np.abs((ang - pa[p] + np.pi) % (2 * np.pi) - np.pi)
-        cams = np.sort(np.argsort(d, kind="stable")[:track_len])
-        for i in cams:
-            pc = R_from_quat(q_true[i]) @ X[p] + t_true[i]
-            uv = f * pc[:2] / pc[2] + width / 2
-            obs_img.append(i); obs_pt.append(p); obs_xy.append(uv + rng.uniform(-noise_px, noise_px, 2))
+    L = min(track_len, n_img)
+    first = np.floor(pa / (2 * np.pi) * n_img - (L - 1) / 2.0 + 0.5).astype(np.int64)
+    cams = np.sort((first[:, None] + np.arange(L)[None, :]) % n_img, axis=1)       # [n_pts, L]
+    obs_img = cams.reshape(-1).astype(np.int32)
+    obs_pt = np.repeat(np.arange(n_pts, dtype=np.int32), L)
+    R_all = np.stack([R_from_quat(q) for q in q_true])
+    pc = np.einsum("nij,nj->ni", R_all[obs_img], X[obs_pt]) + t_true[obs_img]
+    obs_xy = f * pc[:, :2] / pc[:, 2:] + width / 2 + rng.uniform(-noise_px, noise_px, (len(obs_img), 2))
     n_cam = 1 if shared_camera else n_img
     prob = {
         "qvec": q_true.copy(), "tvec": t_true.copy(),
@@ -70,8 +71,8 @@ def make_ba_problem(n_img=20, n_pts=400, track_len=6, seed=0, noise_px=2.0, pose
         "cam_const": np.zeros(n_cam, np.uint8),
         "xyz": X + rng.normal(0, pt_noise, X.shape),
         "pt_const": np.zeros(n_pts, np.uint8),
-        "obs_img": np.array(obs_img, np.int32), "obs_pt": np.array(obs_pt, np.int32),
-        "obs_xy": np.ascontiguousarray(np.array(obs_xy)),
+        "obs_img": np.ascontiguousarray(obs_img), "obs_pt": np.ascontiguousarray(obs_pt),
+        "obs_xy": np.ascontiguousarray(obs_xy),
         "refine": (1, 0, 1),
     }
     # perturb poses (not the gauge image)
