@@ -32,6 +32,9 @@ namespace b2 {
 namespace vf {
 
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kWarpsPerBlock = 4;
+constexpr int kThreads = 32 * kWarpsPerBlock;
+using LaneView = View<kThreads>;  // per-lane solver workspace in dynamic shared memory
 
 // -------------------------------------------------------------------- PRNG
 // std::mt19937 (result_type = uint_fast32_t, 32 significant bits).
@@ -403,7 +406,7 @@ struct Scratch {
 __device__ void ransac_warp(int type, const double2* P1, const double2* P2, int M, double max_error,
                             double min_inlier_ratio, double confidence, long long min_num_trials,
                             long long max_num_trials_opt, WarpShared& sh, double* sig_sh, const Scratch& sc,
-                            uint8_t* mask_out, RansacResult* out, int lane) {
+                            uint8_t* mask_out, RansacResult* out, int lane, LaneView ws) {
   const int kmin = min_samples(type), klo = local_min_samples(type);
   out->success = false;
   out->num_trials = 0;
@@ -464,9 +467,9 @@ __device__ void ransac_warp(int type, const double2* P1, const double2* P2, int 
           a[2 * i] = pa.x; a[2 * i + 1] = pa.y; b[2 * i] = pb.x; b[2 * i + 1] = pb.y;
         }
         double mm[90];
-        if (type == EST_E5) nm = solve_e5(a, b, mm);
-        else if (type == EST_F7) nm = solve_f7(a, b, mm);
-        else if (type == EST_H4) nm = solve_h4(a, b, mm);
+        if (type == EST_E5) nm = solve_e5(ws, a, b, mm);
+        else if (type == EST_F7) nm = solve_f7(ws, a, b, mm);
+        else if (type == EST_H4) nm = solve_h4(ws, a, b, mm);
         else {  // translation from one sample: mean_dst - mean_src with n = 1
           for (int k = 0; k < 9; ++k) mm[k] = 0.0;
           mm[0] = b[0] / 1.0 - a[0] / 1.0;
@@ -639,12 +642,13 @@ __device__ __forceinline__ bool in_box(double2 p, double minx, double maxx, doub
 }
 
 // ------------------------------------------------------------------ main kernel
-constexpr int kWarpsPerBlock = 4;
 
-__global__ void __launch_bounds__(32 * kWarpsPerBlock)
+__global__ void __launch_bounds__(kThreads)
 verify_pairs_kernel(VerifyArgs A) {
   __shared__ WarpShared shs[kWarpsPerBlock];
   __shared__ double sigs[kWarpsPerBlock][9];
+  extern __shared__ double lane_ws[];  // [kSvdWorkDoubles][kThreads]
+  const LaneView ws{lane_ws + threadIdx.x};
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   WarpShared& sh = shs[wib];
   double* sig_sh = sigs[wib];
@@ -717,12 +721,12 @@ verify_pairs_kernel(VerifyArgs A) {
       if (calibrated) {
         const double e_err = (image_to_world_threshold(c1, o.max_error) + image_to_world_threshold(c2, o.max_error)) / 2;
         ransac_warp(EST_E5, sc.nx1, sc.nx2, M, e_err, o.min_inlier_ratio, o.confidence, o.min_num_trials,
-                    o.max_num_trials, sh, sig_sh, sc, sc.mask[0], &E, lane);
+                    o.max_num_trials, sh, sig_sh, sc, sc.mask[0], &E, lane, ws);
       }
       ransac_warp(EST_F7, sc.px1, sc.px2, M, o.max_error, o.min_inlier_ratio, o.confidence, o.min_num_trials,
-                  o.max_num_trials, sh, sig_sh, sc, sc.mask[1], &F, lane);
+                  o.max_num_trials, sh, sig_sh, sc, sc.mask[1], &F, lane, ws);
       ransac_warp(EST_H4, sc.px1, sc.px2, M, o.max_error, o.min_inlier_ratio, o.confidence, o.min_num_trials,
-                  o.max_num_trials, sh, sig_sh, sc, sc.mask[2], &H, lane);
+                  o.max_num_trials, sh, sig_sh, sc, sc.mask[2], &H, lane, ws);
       for (int k = 0; k < 9; ++k) { res.E[k] = E.model[k]; res.F[k] = F.model[k]; res.H[k] = H.model[k]; }
       res.E_num_inliers = E.num_inliers; res.F_num_inliers = F.num_inliers; res.H_num_inliers = H.num_inliers;
       res.E_num_trials = (int)E.num_trials; res.F_num_trials = (int)F.num_trials; res.H_num_trials = (int)H.num_trials;
@@ -806,7 +810,7 @@ verify_pairs_kernel(VerifyArgs A) {
           if (!(ratio < o.watermark_min_inlier_ratio)) {
             RansacResult T;
             ransac_warp(EST_T2, sc.ip1, sc.ip2, (int)num_inliers, o.max_error, o.watermark_min_inlier_ratio,
-                        o.confidence, o.min_num_trials, o.max_num_trials, sh, sig_sh, sc, sc.tmask, &T, lane);
+                        o.confidence, o.min_num_trials, o.max_num_trials, sh, sig_sh, sc, sc.tmask, &T, lane, ws);
             const double inlier_ratio = (double)T.num_inliers / (double)num_inliers;
             if (inlier_ratio >= o.watermark_min_inlier_ratio) res.config = 7;
           }
@@ -856,6 +860,9 @@ __global__ void debug_solve_kernel(int type, int n, const double2* P1, const dou
                                    double* models, int* n_models) {
   __shared__ WarpShared sh;
   __shared__ double sig[9];
+  extern __shared__ double lane_ws[];  // same per-lane workspace layout as the production kernel
+  const LaneView ws{lane_ws + threadIdx.x};
+  if (threadIdx.x >= 32) return;        // one warp works; the block size only fixes the stride
   const int lane = threadIdx.x;
   if (type == 3) {  // F 8-point local estimator on all n points
     for (int i = lane; i < n; i += 32) inl[i] = i;
@@ -871,15 +878,18 @@ __global__ void debug_solve_kernel(int type, int n, const double2* P1, const dou
     if (lane == 0) *n_models = nm;
     return;
   }
-  if (lane == 0) {
+  {  // minimal solvers: every lane solves the same sample in its own workspace (the
+     // production instantiation pattern); lane 0 reports
     double a[14], b[14], mm[90];
     for (int i = 0; i < n; ++i) { a[2 * i] = P1[i].x; a[2 * i + 1] = P1[i].y; b[2 * i] = P2[i].x; b[2 * i + 1] = P2[i].y; }
     int nm = 0;
-    if (type == EST_E5) nm = solve_e5(a, b, mm);
-    else if (type == EST_F7) nm = solve_f7(a, b, mm, models + 45);
-    else nm = solve_h4(a, b, mm);
-    for (int k = 0; k < 9 * nm; ++k) models[k] = mm[k];
-    *n_models = nm;
+    if (type == EST_E5) nm = solve_e5(ws, a, b, mm);
+    else if (type == EST_F7) nm = solve_f7(ws, a, b, mm);
+    else nm = solve_h4(ws, a, b, mm);
+    if (lane == 0) {
+      for (int k = 0; k < 9 * nm; ++k) models[k] = mm[k];
+      *n_models = nm;
+    }
   }
 }
 
@@ -901,7 +911,10 @@ cudaError_t launch_normalize_points(const b2_camera* cams, const int64_t* img_of
   return cudaGetLastError();
 }
 cudaError_t launch_verify_pairs(const VerifyArgs& a, int n_blocks, cudaStream_t s) {
-  vf::verify_pairs_kernel<<<n_blocks, 32 * vf::kWarpsPerBlock, 0, s>>>(a);
+  const size_t dyn = (size_t)vf::kSvdWorkDoubles * vf::kThreads * sizeof(double);
+  cudaError_t e = cudaFuncSetAttribute(vf::verify_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+  if (e != cudaSuccess) return e;
+  vf::verify_pairs_kernel<<<n_blocks, vf::kThreads, dyn, s>>>(a);
   return cudaGetLastError();
 }
 cudaError_t launch_score_models(int type, int n, const double* p1, const double* p2, int n_models, const double* models,
@@ -918,7 +931,11 @@ cudaError_t launch_debug_sample_stream(uint32_t seed, int total, int k, int n_tr
 }
 cudaError_t launch_debug_solve(int type, int n, const double* p1, const double* p2, double* G, uint32_t* inl,
                                double* models, int* n_models, cudaStream_t s) {
-  vf::debug_solve_kernel<<<1, 32, 0, s>>>(type, n, (const double2*)p1, (const double2*)p2, G, inl, models, n_models);
+  const size_t dyn = (size_t)vf::kSvdWorkDoubles * vf::kThreads * sizeof(double);
+  cudaError_t e = cudaFuncSetAttribute(vf::debug_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+  if (e != cudaSuccess) return e;
+  vf::debug_solve_kernel<<<1, vf::kThreads, dyn, s>>>(type, n, (const double2*)p1, (const double2*)p2, G, inl, models,
+                                                     n_models);
   return cudaGetLastError();
 }
 

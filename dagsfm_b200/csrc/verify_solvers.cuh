@@ -22,11 +22,27 @@ namespace vf {
 
 constexpr double kEps = 2.220446049250313e-16;
 
+// The solvers are deliberately __noinline__: the production kernel and the test seam
+// (b2_verify_debug_solve) then execute the SAME machine code, so the parity tests of the seam
+// cover what production runs.  (Two optimiser-dependent miscompilations of inlined copies were
+// observed with nvcc 12.9 -- an insertion sort over a small local array, and a solver inlined
+// into a second kernel -- both absent at -G; see DESIGN.md.)
+
 // ------------------------------------------------------------------ one-sided Jacobi
 // G: m x n row-major (destroyed), V: n x n row-major out (columns = right singular
 // vectors), sig[n]: singular values, both sorted descending (stable).
-template <int NMAX>
-__device__ void jacobi_svd(double* G, int m, int n, double* V, double* sig) {
+// Per-lane working arrays live in SHARED memory, element e of lane l at ws[e * STRIDE + l]
+// (bank-conflict free across the lanes of a warp); STRIDE == 1 is an ordinary array.
+template <int STRIDE>
+struct View {
+  double* base;
+  __device__ __forceinline__ double& operator[](int i) const { return base[i * STRIDE]; }
+  __device__ __forceinline__ View operator+(int off) const { return View{base + off * STRIDE}; }
+};
+constexpr int kSvdWorkDoubles = 72 + 81;  // G (<= 8 x 9) + V (9 x 9)
+
+template <int NMAX, typename GV, typename VV>
+__device__ __noinline__ void jacobi_svd(GV G, int m, int n, VV V, double* sig) {
   for (int i = 0; i < n; ++i)
     for (int j = 0; j < n; ++j) V[i * n + j] = (i == j) ? 1.0 : 0.0;
   // numerically-zero (null space) column pairs are not rotated: alpha * beta would underflow
@@ -99,7 +115,7 @@ __device__ void jacobi_svd(double* G, int m, int n, double* V, double* sig) {
 __device__ inline void svd3_rebuild(const double* A, int mode, double* R) {
   double G[9], V[9], sig[3];
   for (int i = 0; i < 9; ++i) G[i] = A[i];
-  jacobi_svd<3>(G, 3, 3, V, sig);
+  jacobi_svd<3>(View<1>{G}, 3, 3, View<1>{V}, sig);
   double sn[3] = {sig[0], sig[1], 0.0};
   if (mode == 1) {
     sn[0] = (sig[0] + sig[1]) / 2.0;
@@ -147,7 +163,7 @@ __device__ inline void mat3_inverse(const double* a, double* r) {
 
 // ------------------------------------------------ companion-matrix eigenvalues (hqr)
 // a: n x n row-major upper Hessenberg (destroyed).  Returns false on non-convergence.
-__device__ inline bool hqr(double* a, int n, double* wr, double* wi) {
+__device__ __noinline__ bool hqr(double* a, int n, double* wr, double* wi) {
 #define HA(i, j) a[(i) * n + (j)]
   int nn = n - 1;
   double t = 0.0, p = 0, q = 0, r = 0, s = 0, w, x, y, z;
@@ -278,7 +294,7 @@ __device__ inline bool hqr(double* a, int n, double* wr, double* wi) {
 // ascending.  Follows polynomial.cc:208-279 incl. leading / trailing zero handling.
 // Returns the number of real roots, or -1 if the reference would return false.
 template <int MAXDEG>
-__device__ int real_roots(const double* coeffs_all, int nc, double* roots) {
+__device__ __noinline__ int real_roots(const double* coeffs_all, int nc, double* roots) {
   int lead = 0;
   while (lead < nc && coeffs_all[lead] == 0) ++lead;
   const double* coeffs = coeffs_all + lead;
@@ -347,11 +363,13 @@ __device__ int real_roots(const double* coeffs_all, int nc, double* roots) {
 
 // ------------------------------------------------------------------ F 7-point
 // p1, p2: 7 points each (x,y interleaved).  models: up to 3 x 9.  Returns count.
-__device__ inline int solve_f7(const double* p1, const double* p2, double* models, double* dbg = nullptr) {
-  double A[63], V[81], sig[9];
+template <int STRIDE>
+__device__ __noinline__ int solve_f7(View<STRIDE> ws, const double* p1, const double* p2, double* models) {
+  View<STRIDE> A = ws, V = ws + 72;
+  double sig[9];
   for (int i = 0; i < 7; ++i) {
     const double x0 = p1[2 * i], y0 = p1[2 * i + 1], x1 = p2[2 * i], y1 = p2[2 * i + 1];
-    double* a = A + 9 * i;
+    View<STRIDE> a = A + 9 * i;
     a[0] = x1 * x0; a[1] = x1 * y0; a[2] = x1; a[3] = y1 * x0; a[4] = y1 * y0; a[5] = y1;
     a[6] = x0; a[7] = y0; a[8] = 1;
   }
@@ -380,14 +398,6 @@ __device__ inline int solve_f7(const double* p1, const double* p2, double* model
   c[3] = f2[0] * t3 - f2[1] * t4 + f2[2] * t5;
   double roots[3];
   const int nr = real_roots<3>(c, 4, roots);
-  if (dbg) {
-    for (int i = 0; i < 4; ++i) dbg[i] = c[i];
-    dbg[4] = nr;
-    for (int i = 0; i < 3; ++i) dbg[5 + i] = roots[i];
-    for (int i = 0; i < 9; ++i) dbg[8 + i] = sig[i];
-    for (int i = 0; i < 9; ++i) dbg[17 + i] = f1[i];
-    for (int i = 0; i < 9; ++i) dbg[26 + i] = f2[i];
-  }
   int nm = 0;
   for (int i = 0; i < nr; ++i) {
     const double lambda = roots[i];
@@ -430,17 +440,19 @@ __device__ inline void center_and_normalize(const double* p, int n, double* np, 
 }
 
 // ------------------------------------------------------------------ H 4-point
-__device__ inline int solve_h4(const double* p1, const double* p2, double* model) {
+template <int STRIDE>
+__device__ __noinline__ int solve_h4(View<STRIDE> ws, const double* p1, const double* p2, double* model) {
   double n1[8], n2[8], T1[9], T2[9];
   center_and_normalize(p1, 4, n1, T1);
   center_and_normalize(p2, 4, n2, T2);
-  double A[72], V[81], sig[9];
+  View<STRIDE> A = ws, V = ws + 72;
+  double sig[9];
   for (int i = 0; i < 72; ++i) A[i] = 0.0;
   for (int i = 0, j = 4; i < 4; ++i, ++j) {
     const double s_0 = n1[2 * i], s_1 = n1[2 * i + 1], d_0 = n2[2 * i], d_1 = n2[2 * i + 1];
-    double* a = A + 9 * i;
+    View<STRIDE> a = A + 9 * i;
     a[0] = -s_0; a[1] = -s_1; a[2] = -1; a[6] = s_0 * d_0; a[7] = s_1 * d_0; a[8] = d_0;
-    double* b = A + 9 * j;
+    View<STRIDE> b = A + 9 * j;
     b[3] = -s_0; b[4] = -s_1; b[5] = -1; b[6] = s_0 * d_1; b[7] = s_1 * d_1; b[8] = d_1;
   }
   jacobi_svd<9>(A, 8, 9, V, sig);
@@ -490,7 +502,7 @@ __device__ inline void quad_mul_acc(double* c, const double* q, const double* l,
 }
 
 // Eb: 4 basis vectors X,Y,Z,W (each 9, row-major 3x3).  models: up to 10 x 9.
-__device__ inline int solve_e5_from_basis(const double* Eb, double* models) {
+__device__ __noinline__ int solve_e5_from_basis(const double* Eb, double* models) {
   // E(r,c) as a linear polynomial [x,y,z,1]
   double L[9][4];
   for (int i = 0; i < 9; ++i) {
@@ -592,7 +604,7 @@ __device__ inline int solve_e5_from_basis(const double* Eb, double* models) {
       Bz[3 * j + 1] = B[4][j] * z3 + B[5][j] * z2 + B[6][j] * z1 + B[7][j];
       Bz[3 * j + 2] = B[8][j] * z4 + B[9][j] * z3 + B[10][j] * z2 + B[11][j] * z1 + B[12][j];
     }
-    jacobi_svd<3>(Bz, 3, 3, V3, s3);
+    jacobi_svd<3>(View<1>{Bz}, 3, 3, View<1>{V3}, s3);
     const double X0 = V3[2], X1 = V3[5], X2 = V3[8];
     if (fabs(X2) < 1e-10) continue;
     double ev[9], nrm = 0;
@@ -608,11 +620,13 @@ __device__ inline int solve_e5_from_basis(const double* Eb, double* models) {
 }
 
 // Minimal 5-point: 5 x 9 epipolar constraint matrix -> 4-dim null space -> models.
-__device__ inline int solve_e5(const double* p1, const double* p2, double* models) {
-  double Q[45], V[81], sig[9];
+template <int STRIDE>
+__device__ __noinline__ int solve_e5(View<STRIDE> ws, const double* p1, const double* p2, double* models) {
+  View<STRIDE> Q = ws, V = ws + 72;
+  double sig[9];
   for (int i = 0; i < 5; ++i) {
     const double x1_0 = p1[2 * i], x1_1 = p1[2 * i + 1], x2_0 = p2[2 * i], x2_1 = p2[2 * i + 1];
-    double* q = Q + 9 * i;
+    View<STRIDE> q = Q + 9 * i;
     q[0] = x1_0 * x2_0; q[1] = x1_1 * x2_0; q[2] = x2_0; q[3] = x1_0 * x2_1; q[4] = x1_1 * x2_1;
     q[5] = x2_1; q[6] = x1_0; q[7] = x1_1; q[8] = 1;
   }
