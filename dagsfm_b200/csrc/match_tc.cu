@@ -42,7 +42,7 @@ constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kSmemX = 0;
 constexpr uint32_t kSmemY = 2 * kXBytes;
 constexpr uint32_t kSmemBar = kSmemY + kStagesY * kTileBytes;
-constexpr uint32_t kNumBars = 2 * kStagesY + 8;
+constexpr uint32_t kNumBars = 2 * kStagesY + 12;
 constexpr uint32_t kSmemTotal = kSmemBar + kNumBars * 8 + 16;
 
 __host__ size_t match_tc_smem_bytes() { return kSmemTotal + 1024; }
@@ -75,8 +75,11 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap, const MatchItem* __r
   auto y_empty = [&](uint32_t s) { return bar_base + 8 * (kStagesY + s); };
   auto x_full = [&](uint32_t s) { return bar_base + 8 * (2 * kStagesY + s); };
   auto x_empty = [&](uint32_t s) { return bar_base + 8 * (2 * kStagesY + 2 + s); };
-  auto t_full = [&](uint32_t s) { return bar_base + 8 * (2 * kStagesY + 4 + s); };
-  auto t_empty = [&](uint32_t s) { return bar_base + 8 * (2 * kStagesY + 6 + s); };
+  // accumulator barriers are per (TMEM buffer, X tile): the two epilogue warps that share an
+  // SMSP (tile 0 / tile 1 of the same lane quadrant) run half a block out of phase, so one
+  // drains TMEM while the other occupies the ALU pipe
+  auto t_full = [&](uint32_t buf, uint32_t t) { return bar_base + 8 * (2 * kStagesY + 4 + 2 * buf + t); };
+  auto t_empty = [&](uint32_t buf, uint32_t t) { return bar_base + 8 * (2 * kStagesY + 8 + 2 * buf + t); };
   const uint32_t tmem_slot = bar_base + 8 * kNumBars;
 
   const int warp = threadIdx.x >> 5;
@@ -92,8 +95,10 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap, const MatchItem* __r
     for (uint32_t s = 0; s < 2; ++s) {
       mbar_init(x_full(s), 1);
       mbar_init(x_empty(s), 1);
-      mbar_init(t_full(s), 1);
-      mbar_init(t_empty(s), kNumEpiWarps);
+      for (uint32_t t = 0; t < 2; ++t) {
+        mbar_init(t_full(s, t), 1);
+        mbar_init(t_empty(s, t), kNumEpiWarps / 2);
+      }
     }
     mbar_fence_init();
   }
@@ -144,11 +149,11 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap, const MatchItem* __r
           const uint32_t s = it % kStagesY;
           const uint32_t buf = tb & 1;
           mbar_wait(y_full(s), (it / kStagesY) & 1);
-          mbar_wait(t_empty(buf), ((tb >> 1) & 1) ^ 1);
-          tc_fence_after();
           const uint32_t ya = smem_base + kSmemY + s * kTileBytes;
 #pragma unroll
           for (uint32_t t = 0; t < 2; ++t) {
+            mbar_wait(t_empty(buf, t), ((tb >> 1) & 1) ^ 1);
+            tc_fence_after();
             const uint32_t d = tmem_base + buf * 256 + t * 128;
 #pragma unroll
             for (uint32_t k = 0; k < 4; ++k) {
@@ -156,9 +161,9 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap, const MatchItem* __r
               const uint64_t bd = make_kmajor_sw128_desc(ya + k * 32);
               mma_i8_ss(d, ad, bd, idesc, k);
             }
+            tc_commit(t_full(buf, t));  // this tile's accumulator is ready for its epilogue warps
           }
           tc_commit(y_empty(s));   // smem stage reusable once these MMAs retire
-          tc_commit(t_full(buf));  // accumulators ready for the epilogue
           ++it;
           ++tb;
         }
@@ -179,7 +184,7 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap, const MatchItem* __r
       int best = 0, second = 0, bchunk = 0;
       for (uint32_t b = 0; b < y_nblk; ++b) {
         const uint32_t buf = tb & 1;
-        mbar_wait(t_full(buf), (tb >> 1) & 1);
+        mbar_wait(t_full(buf, tile), (tb >> 1) & 1);
         tc_fence_after();
         uint32_t v[128];
         const uint32_t ta = tmem_base + lane_addr + buf * 256 + tile * 128;
@@ -187,7 +192,7 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap, const MatchItem* __r
         // values are in registers: hand the TMEM buffer back before the ALU work
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(t_empty(buf));
+        if (lane == 0) mbar_arrive(t_empty(buf, tile));
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const int m = max32(v + 32 * c);
