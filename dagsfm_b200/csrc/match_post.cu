@@ -84,7 +84,8 @@ __global__ void fill_items_kernel(const uint32_t* __restrict__ pairs, int64_t n_
                                   const int32_t* __restrict__ img_n,
                                   const uint32_t* __restrict__ img_row,
                                   const uint32_t* __restrict__ item_start,
-                                  MatchItem* __restrict__ items, PairMeta* __restrict__ meta) {
+                                  MatchItem* __restrict__ items, PairMeta* __restrict__ meta,
+                                  uint32_t y_block_rows) {
   const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (p >= n_pairs) return;
   const uint32_t i1 = pairs[2 * p], i2 = pairs[2 * p + 1];
@@ -98,9 +99,9 @@ __global__ void fill_items_kernel(const uint32_t* __restrict__ pairs, int64_t n_
     const uint32_t nt1 = (n1 + kSuperRows - 1) / kSuperRows, nt2 = (n2 + kSuperRows - 1) / kSuperRows;
     pm.nt1 = nt1;
     const uint32_t r1 = img_row[i1], r2 = img_row[i2];
-    // Y is streamed in 128-row blocks; the pool pads every image to 256 rows, so the
-    // block count may stop at the last block that still holds a real row.
-    const uint32_t yb2 = (n2 + kTileRows - 1) / kTileRows, yb1 = (n1 + kTileRows - 1) / kTileRows;
+    // Y is streamed in blocks of y_block_rows (128 for the SS kernel, 96 for the TS kernel); the
+    // pool pads every image so that the last block never reaches the next image.
+    const uint32_t yb2 = (n2 + y_block_rows - 1) / y_block_rows, yb1 = (n1 + y_block_rows - 1) / y_block_rows;
     MatchItem* it = items + pm.item_start;
     for (uint32_t t = 0; t < nt1; ++t) it[t] = MatchItem{r1 + t * kSuperRows, r2, yb2, 0u};
     for (uint32_t t = 0; t < nt2; ++t) it[nt1 + t] = MatchItem{r2 + t * kSuperRows, r1, yb1, 0u};
@@ -216,10 +217,10 @@ cudaError_t launch_scan_counts(const uint32_t* counts, int64_t n, int64_t* offse
 }
 cudaError_t launch_fill_items(const uint32_t* pairs, int64_t n_pairs, const int32_t* img_n,
                               const uint32_t* img_row, const uint32_t* item_start, MatchItem* items,
-                              PairMeta* meta, cudaStream_t s) {
+                              PairMeta* meta, uint32_t y_block_rows, cudaStream_t s) {
   if (n_pairs == 0) return cudaSuccess;
   fill_items_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, s>>>(pairs, n_pairs, img_n, img_row,
-                                                                      item_start, items, meta);
+                                                                      item_start, items, meta, y_block_rows);
   return cudaGetLastError();
 }
 cudaError_t launch_fixup(const uint8_t* pool, const MatchItem* items, const uint4* cands,

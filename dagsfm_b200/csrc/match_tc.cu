@@ -61,12 +61,15 @@ __device__ __forceinline__ int max32(const uint32_t* v) {
   return max(__vimax3_s32(a, b, c), d);
 }
 
+// PROF: per-role cycle counters (B2_MATCH_PROFILE=1); the counters cost ~15 %, so the
+// production instantiation has none.
+template <bool PROF>
 __global__ void __launch_bounds__(kThreads, 1)
 match_top2_kernel(const __grid_constant__ CUtensorMap tmap, const MatchItem* __restrict__ items,
                   const uint32_t* __restrict__ n_items_ptr, int thr_dist,
                   const int* __restrict__ ratio_lim, int* __restrict__ midx,
                   uint4* __restrict__ cands, unsigned int* __restrict__ cand_count,
-                  unsigned int cand_capacity) {
+                  unsigned int cand_capacity, unsigned long long* __restrict__ prof) {
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment.
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -82,7 +85,7 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap, const MatchItem* __r
   auto t_empty = [&](uint32_t buf, uint32_t t) { return bar_base + 8 * (2 * kStagesY + 8 + 2 * buf + t); };
   const uint32_t tmem_slot = bar_base + 8 * kNumBars;
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
   const uint32_t n_items = *n_items_ptr;
 
@@ -136,39 +139,69 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap, const MatchItem* __r
       }
     }
   } else if (warp == 1) {
-    // ======================================================= MMA issuer
-    if (lane == 0) {
+    // ======================================================= MMA issuer (whole warp converged)
+    {
       constexpr uint32_t idesc = make_idesc_u8_s32(kTileRows, kTileRows);
       uint32_t it = 0, xi = 0, tb = 0;
+      long long w_y = 0, w_t = 0, t_begin = (PROF ? clock64() : 0ll);
       for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
         const uint32_t y_nblk = items[item].y_nblk;
         const uint32_t xs = xi & 1;
         mbar_wait(x_full(xs), (xi >> 1) & 1);
         const uint32_t xa = smem_base + kSmemX + xs * kXBytes;
+        // The single issuing thread must never sit in a barrier round trip (~100 cycles) with the
+        // tensor pipe's short queue drained: the barriers of block b+1 are PROBED (test_wait) before
+        // the MMAs of block b are issued and only waited on if the probe failed.  This needs the
+        // double-buffered accumulators: t_empty of block b+1 belongs to block b-1's buffer.
+        uint32_t ok_y = 0, ok_t0 = 0, ok_t1 = 0;  // probes of the current block (0 = unknown)
         for (uint32_t b = 0; b < y_nblk; ++b) {
           const uint32_t s = it % kStagesY;
           const uint32_t buf = tb & 1;
-          mbar_wait(y_full(s), (it / kStagesY) & 1);
+          long long c0 = (PROF ? clock64() : 0ll);
+          if (!ok_y) mbar_wait(y_full(s), (it / kStagesY) & 1);
+          if (PROF) w_y += clock64() - c0;
           const uint32_t ya = smem_base + kSmemY + s * kTileBytes;
+          // probes for the next block of this item
+          uint32_t nk_y = 0, nk_t0 = 0, nk_t1 = 0;
+          if (b + 1 < y_nblk) {
+            const uint32_t itn = it + 1, tbn = tb + 1;
+            nk_y = mbar_test(y_full(itn % kStagesY), (itn / kStagesY) & 1);
+            nk_t0 = mbar_test(t_empty(tbn & 1, 0), ((tbn >> 1) & 1) ^ 1);
+            nk_t1 = mbar_test(t_empty(tbn & 1, 1), ((tbn >> 1) & 1) ^ 1);
+          }
 #pragma unroll
           for (uint32_t t = 0; t < 2; ++t) {
-            mbar_wait(t_empty(buf, t), ((tb >> 1) & 1) ^ 1);
+            c0 = (PROF ? clock64() : 0ll);
+            if (!(t == 0 ? ok_t0 : ok_t1)) mbar_wait(t_empty(buf, t), ((tb >> 1) & 1) ^ 1);
+            if (PROF) w_t += clock64() - c0;
             tc_fence_after();
             const uint32_t d = tmem_base + buf * 256 + t * 128;
+            if (elect_one()) {
 #pragma unroll
-            for (uint32_t k = 0; k < 4; ++k) {
-              const uint64_t ad = make_kmajor_sw128_desc(xa + t * kTileBytes + k * 32);
-              const uint64_t bd = make_kmajor_sw128_desc(ya + k * 32);
-              mma_i8_ss(d, ad, bd, idesc, k);
+              for (uint32_t k = 0; k < 4; ++k) {
+                const uint64_t ad = make_kmajor_sw128_desc(xa + t * kTileBytes + k * 32);
+                const uint64_t bd = make_kmajor_sw128_desc(ya + k * 32);
+                mma_i8_ss(d, ad, bd, idesc, k);
+              }
+              tc_commit(t_full(buf, t));  // this tile's accumulator is ready for its epilogue warps
+              if (t == 1) tc_commit(y_empty(s));  // smem stage reusable once these MMAs retire
             }
-            tc_commit(t_full(buf, t));  // this tile's accumulator is ready for its epilogue warps
+            __syncwarp();
           }
-          tc_commit(y_empty(s));   // smem stage reusable once these MMAs retire
+          ok_y = nk_y;
+          ok_t0 = nk_t0;
+          ok_t1 = nk_t1;
           ++it;
           ++tb;
         }
-        tc_commit(x_empty(xs));
+        if (elect_one()) tc_commit(x_empty(xs));
+        __syncwarp();
         ++xi;
+      }
+      if (PROF && prof && lane == 0) {
+        atomicAdd(prof + 0, (unsigned long long)w_y);
+        atomicAdd(prof + 1, (unsigned long long)w_t);
+        atomicAdd(prof + 2, (unsigned long long)((PROF ? clock64() : 0ll) - t_begin));
       }
     }
   } else {
@@ -179,12 +212,15 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap, const MatchItem* __r
     const uint32_t lane_addr = (quad * 32u) << 16;
     const uint32_t row_in_item = tile * 128 + quad * 32 + lane;
     uint32_t tb = 0;
+    long long e_wait = 0, e_ld = 0, e_alu = 0;
     for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
       const uint32_t y_nblk = items[item].y_nblk;
       int best = 0, second = 0, bchunk = 0;
       for (uint32_t b = 0; b < y_nblk; ++b) {
         const uint32_t buf = tb & 1;
+        const long long c0 = (PROF ? clock64() : 0ll);
         mbar_wait(t_full(buf, tile), (tb >> 1) & 1);
+        const long long c1 = (PROF ? clock64() : 0ll);
         tc_fence_after();
         uint32_t v[128];
         const uint32_t ta = tmem_base + lane_addr + buf * 256 + tile * 128;
@@ -193,6 +229,7 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap, const MatchItem* __r
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(t_empty(buf, tile));
+        const long long c2 = (PROF ? clock64() : 0ll);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const int m = max32(v + 32 * c);
@@ -202,6 +239,9 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap, const MatchItem* __r
           bchunk = (m > best) ? chunk : bchunk;
           best = max(best, m);
         }
+        e_wait += c1 - c0;
+        e_ld += c2 - c1;
+        e_alu += (PROF ? clock64() : 0ll) - c2;
         ++tb;
       }
       // distance + ratio tests in the integer domain (monotone tables, see match_api.cu)
@@ -224,6 +264,11 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap, const MatchItem* __r
         }
       }
     }
+    if (PROF && prof && lane == 0) {
+      atomicAdd(prof + 3, (unsigned long long)e_wait);
+      atomicAdd(prof + 4, (unsigned long long)e_ld);
+      atomicAdd(prof + 5, (unsigned long long)e_alu);
+    }
   }
 
   tc_fence_before();
@@ -237,18 +282,20 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap, const MatchItem* __r
 cudaError_t launch_match_top2(const CUtensorMap& tmap, const MatchItem* items,
                               const uint32_t* n_items_ptr, int thr_dist, const int* ratio_lim,
                               int* midx, uint4* cands, unsigned int* cand_count,
-                              unsigned int cand_capacity, int grid, cudaStream_t stream) {
-  static bool attr_set = false;
+                              unsigned int cand_capacity, int grid, cudaStream_t stream,
+                              unsigned long long* prof) {
   const size_t smem = match_tc_smem_bytes();
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(match_top2_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (prof) {
+    cudaError_t e = cudaFuncSetAttribute(match_top2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    match_top2_kernel<true><<<grid, kThreads, smem, stream>>>(tmap, items, n_items_ptr, thr_dist, ratio_lim, midx, cands,
+                                                               cand_count, cand_capacity, prof);
+  } else {
+    cudaError_t e = cudaFuncSetAttribute(match_top2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    match_top2_kernel<false><<<grid, kThreads, smem, stream>>>(tmap, items, n_items_ptr, thr_dist, ratio_lim, midx, cands,
+                                                                cand_count, cand_capacity, nullptr);
   }
-  match_top2_kernel<<<grid, kThreads, smem, stream>>>(tmap, items, n_items_ptr, thr_dist,
-                                                      ratio_lim, midx, cands, cand_count,
-                                                      cand_capacity);
   return cudaGetLastError();
 }
 
