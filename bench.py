@@ -271,7 +271,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     cores = effective_cores()
-    a.cpu_sample = max(a.cpu_sample, 2 * cores)   # every host core gets at least two pairs
+    a.cpu_sample = max(a.cpu_sample, 12 * cores)  # ~10 s of CPU work at one 4096x4096 pair per core-second
     workload = f"C2: {a.images} images x {a.desc} desc, exhaustive match + ratio test"
     cfg = {"workload": workload, "n_images": a.images, "desc_per_image": a.desc,
            "options": "max_ratio 0.8, max_distance 0.7, cross_check 1",
@@ -420,7 +420,7 @@ def main():
                 if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)")
     ops_per_pair = 2.0 * a.desc * a.desc * 128
     achieved = ops_per_pair * n_pairs * a.steps / t_tc / 1e12
-    roofline = {"bound": "tensor", "kernel": "match_top2_kernel (tcgen05 kind::i8)",
+    roofline = {"bound": "tensor", "kernel": "match_top2_ts_kernel (tcgen05 kind::i8, query operand in TMEM)",
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                 "peak_source": peak_src + "; i8 dense peak is nominally 2x this",
                 "algorithmic_ops_per_pair": ops_per_pair,

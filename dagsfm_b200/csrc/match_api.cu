@@ -51,7 +51,7 @@ cudaError_t launch_cross_write(const PairMeta* meta, int64_t n_pairs, const int*
                                int cross_check, const int64_t* offsets, uint32_t* out_matches,
                                int64_t capacity, cudaStream_t s);
 
-constexpr bool kDefaultTs = false;
+constexpr bool kDefaultTs = true;   // TS kernel (query operand in tensor memory) is the production kernel
 static inline uint32_t pad_up(uint32_t n, uint32_t m) { return (n + m - 1) / m * m; }
 // Rows reserved for an image of n descriptors: whole 256-row X supertiles, and enough zero
 // rows that Y blocks of 96 (TS kernel) or 128 (SS kernel) rows never reach the next image.

@@ -31,7 +31,7 @@ namespace b2 {
 namespace ts {
 
 constexpr int kN = 128;                     // UMMA N = Y rows per block
-constexpr int kStagesY = 12;
+constexpr int kStagesY = 8;
 constexpr int kNumEpiWarps = 8;
 constexpr int kThreads = 64 + 32 * kNumEpiWarps;     // 320
 constexpr uint32_t kYBytes = kN * kDescBytes;        // 16 KiB per stage
@@ -76,7 +76,7 @@ match_top2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __
   auto t_empty = [&](uint32_t t) { return bar_base + 8 * (2 * kStagesY + 6 + t); };
   const uint32_t tmem_slot = bar_base + 8 * kNumBars;
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
   const uint32_t n_items = *n_items_ptr;
 
@@ -120,8 +120,8 @@ match_top2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __
       }
     }
   } else if (warp == 1) {
-    // ======================================================= MMA issuer (TS mode)
-    if (lane == 0) {
+    // ======================================================= MMA issuer (TS mode, whole warp converged)
+    {
       constexpr uint32_t idesc = make_idesc_u8_s32(kTileRows, kN);
       uint32_t it = 0, xi = 0, tb = 0;
       for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -139,18 +139,22 @@ match_top2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __
             tc_fence_after();
             const uint32_t d = tmem_base + kAccCol + t * kN;
             const uint32_t a = tmem_base + kACol + (2 * ab + t) * 32;
+            if (elect_one()) {
 #pragma unroll
-            for (uint32_t k = 0; k < 4; ++k) {
-              const uint64_t bd = make_kmajor_sw128_desc(ya + k * 32);
-              mma_i8_ts(d, a + k * 8, bd, idesc, k);  // K = 32 bytes = 8 TMEM columns of A
+              for (uint32_t k = 0; k < 4; ++k) {
+                const uint64_t bd = make_kmajor_sw128_desc(ya + k * 32);
+                mma_i8_ts(d, a + k * 8, bd, idesc, k);  // K = 32 bytes = 8 TMEM columns of A
+              }
+              tc_commit(t_full(t));
+              if (t == 1) tc_commit(y_empty(s));
             }
-            tc_commit(t_full(t));
+            __syncwarp();
           }
-          tc_commit(y_empty(s));
           ++it;
           ++tb;
         }
-        tc_commit(a_empty(ab));  // this item's MMAs have consumed the A buffer
+        if (elect_one()) tc_commit(a_empty(ab));  // this item's MMAs have consumed the A buffer
+        __syncwarp();
         ++xi;
       }
     }

@@ -69,7 +69,10 @@ class SiftMatchGPU {
   // SiftMatchCU.cpp:99-112: features beyond max_sift are silently clamped
   void SetDescriptors(int index, int num, const unsigned char* descriptors, int /*id*/ = -1) {
     if (!h_ || index < 0 || index > 1) return;
-    b2_match_set_descriptors(h_, index, std::min(num, max_sift_), descriptors);
+    // the C ABI reads a NULL pointer as "keep the previous upload"; an explicitly empty set
+    // (Eigen's data() of a 0-row matrix may be NULL) must still replace it
+    static const unsigned char kEmpty = 0;
+    b2_match_set_descriptors(h_, index, std::min(num, max_sift_), descriptors ? descriptors : &kEmpty);
   }
   // returns the number of matches, -1 on a device error (SiftMatchCU.cpp:193-196)
   int GetSiftMatch(int max_match, uint32_t match_buffer[][2], float distmax = 0.7f, float ratiomax = 0.8f,

@@ -7,6 +7,7 @@ under profiles/ (the .ncu-rep files themselves are scratch).
 """
 import collections
 import csv
+import re
 import subprocess
 import sys
 
@@ -30,6 +31,15 @@ KEYS = [
 ]
 
 
+OURS = re.compile(r"b2::|match_top2|match_fixup|match_cross|verify_pairs|schur_kernel|camera_terms|jacobian_kernel|"
+                  r"backsub_kernel|model_cost|candidate_|block_scan|pair_items|fill_items|normalize_points|"
+                  r"make_scale|negate_kernel|add_diag|score_models|debug_s|max_matches")
+
+
+def is_ours(name):
+    return bool(OURS.search(name))
+
+
 def launches(path):
     rows = [r for r in csv.reader(open(path, errors="ignore")) if len(r) > 10]
     hdr = rows[0]
@@ -42,11 +52,11 @@ def launches(path):
         tot[name] += v
         cnt[name] += 1
     T = sum(tot.values())
-    ours = sum(v for k, v in tot.items() if "b2::" in k)
+    ours = sum(v for k, v in tot.items() if is_ours(k))
     print(f"# ncu --metrics gpu__time_duration.sum --clock-control none ; source: {path}")
     print(f"# total {T:.3f} ms over {sum(cnt.values())} launches; b2:: kernels {ours:.3f} ms")
     for k, v in tot.most_common(30):
-        tag = f" share_of_b2={v / ours:6.3f}" if "b2::" in k else ""
+        tag = f" share_of_b2={v / ours:6.3f}" if is_ours(k) else ""
         print(f"{k:72s} n={cnt[k]:5d} total_ms={v:11.3f} avg_us={1e3 * v / cnt[k]:10.2f} share={v / T:6.3f}{tag}")
 
 
