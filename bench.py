@@ -314,7 +314,19 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout at the first collective; keep stdout for the
+        # one JSON line by routing fd 1 to stderr until the communicator is up
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     from dagsfm_b200 import SiftMatchGPU, SiftMatchingOptions, lib
 
@@ -407,6 +419,8 @@ def main():
         ba = bench_ba(a, local_rank, rank, world, cores, barrier, peaks_hbm())
 
     if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
         return
 
     # --------------------------------------------------------------- roofline
@@ -447,7 +461,9 @@ def main():
         "verify": verify, "ba": ba,
         "wall_ms_per_step": 1e3 * wall / a.steps, "matches_per_step": int(total),
         "fixup_candidates_last_chunk_sum": int(cands),
-    }))
+    }), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
