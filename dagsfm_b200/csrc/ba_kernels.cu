@@ -277,7 +277,11 @@ __global__ void __launch_bounds__(kSchurThreads) schur_kernel(BaDev P, double ra
         if (col >= 0) atomicAdd(P.rhs + col, -(w[0] * sT[0] + w[1] * sT[1] + w[2] * sT[2]));
       }
       __syncthreads();
-      for (int b0 = 0; b0 < L; b0 += kTile) {
+      // Unordered observation pairs a <= b only: Y_a W_b^T and Y_b W_a^T are transposes of each other
+      // (V^-1 is symmetric), so every entry of the block is written once, at (min col, max col) --
+      // the triangle the Cholesky reads.  Thread (k, l) owns one entry of the 10 x 10 block and walks
+      // the pairs: no integer division in the loop, Y_a stays in registers across b.
+      for (int b0 = a0; b0 < L; b0 += kTile) {
         const int nb = min(kTile, L - b0);
         if (b0 == a0) {
           for (int e = tid; e < nb * 30; e += kSchurThreads) sWb[e / 30][e % 30] = sWa[e / 30][e % 30];
@@ -293,14 +297,24 @@ __global__ void __launch_bounds__(kSchurThreads) schur_kernel(BaDev P, double ra
           }
         }
         __syncthreads();
-        const int total = na * nb * 100;
-        for (int e = tid; e < total; e += kSchurThreads) {
-          const int l = e % 10, k = (e / 10) % 10, ab = e / 100, b = ab % nb, a = ab / nb;
-          const int ca = sCa[a][k], cb = sCb[b][l];
-          if (ca < 0 || cb < 0 || ca > cb) continue;
-          const double v = sYa[a][3 * k] * sWb[b][3 * l] + sYa[a][3 * k + 1] * sWb[b][3 * l + 1] +
-                           sYa[a][3 * k + 2] * sWb[b][3 * l + 2];
-          atomicAdd(P.S + ca * D + cb, -v);
+        if (tid < 100) {
+          const int k = tid / 10, l = tid - 10 * k;
+          for (int a = 0; a < na; ++a) {
+            const int ca = sCa[a][k];
+            if (ca < 0) continue;
+            const double y0 = sYa[a][3 * k], y1 = sYa[a][3 * k + 1], y2 = sYa[a][3 * k + 2];
+            const bool same_tile = (b0 == a0);
+            for (int b = same_tile ? a : 0; b < nb; ++b) {
+              const int cb = sCb[b][l];
+              if (cb < 0) continue;
+              const bool diag_pair = same_tile && (b == a);
+              if (diag_pair && ca > cb) continue;  // within one observation keep the upper entries only
+              double v = y0 * sWb[b][3 * l] + y1 * sWb[b][3 * l + 1] + y2 * sWb[b][3 * l + 2];
+              if (!diag_pair && ca == cb) v = v + v;  // shared intrinsics: (a,b) and (b,a) hit one diagonal entry
+              const int r = min(ca, cb), c = max(ca, cb);
+              atomicAdd(P.S + r * D + c, -v);
+            }
+          }
         }
         __syncthreads();
       }
