@@ -393,8 +393,11 @@ def main():
             off, mm = m.match_pairs(pairs, opt, capacity=cap)
         barrier()
         w0 = time.perf_counter()
+        t_up = 0.0
         for _ in range(e_steps):
+            u0 = time.perf_counter()
             m.set_images(hdescs)                       # H2D of the step's descriptors
+            t_up += time.perf_counter() - u0
             off, mm = m.match_pairs(pairs, opt, capacity=cap)  # H2D pairs, D2H offsets + matches
         barrier()
         w = time.perf_counter() - w0
@@ -405,6 +408,7 @@ def main():
         e2e = {"value": world * n_pairs * e_steps / w, "unit": UNIT,
                "h2d_bytes_per_step": int(hd.nbytes + pairs.nbytes),
                "d2h_bytes_per_step": int(off.nbytes + mm.nbytes), "steps": e_steps,
+               "upload_s_per_step": t_up / e_steps, "match_s_per_step": (w - t_up) / e_steps,
                "api": "b2_match_set_images + b2_match_pairs (host buffers)"}
         m.set_images_device(desc.data_ptr(), row_off, n_desc)
 

@@ -78,7 +78,7 @@ int run_device(b2_verifier* v, int64_t n_pairs, const uint32_t* pairs, const int
   B2_CUDA(cudaStreamSynchronize(s));
   m_cap = std::max(m_cap, 32);
   const int wpb = verify_warps_per_block();
-  int blocks = v->n_sm * 4;
+  int blocks = v->n_sm;  // one resident block per SM (shared-memory bound), dynamic work counter
   blocks = (int)std::min<int64_t>(blocks, (n_pairs + wpb - 1) / wpb);
   const size_t stride = verify_scratch_stride(m_cap);
   // bound the scratch (large match lists -> fewer concurrent warps)

@@ -32,22 +32,32 @@ namespace b2 {
 namespace vf {
 
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kWarpsPerBlock = 4;
+constexpr int kWarpsPerBlock = 8;
 constexpr int kThreads = 32 * kWarpsPerBlock;
 using LaneView = View<kThreads>;  // per-lane solver workspace in dynamic shared memory
 
 // -------------------------------------------------------------------- PRNG
 // std::mt19937 (result_type = uint_fast32_t, 32 significant bits).
 struct WarpShared {
+  double V[81];         // right singular vectors of the warp-level Jacobi SVD
+  double R[81];         // triangular factor of the local estimator's constraint matrix
+  double sig[9];
   uint32_t mt[624];
   uint32_t ring[512];   // FIFO of raw mt outputs; rollback = moving r back
   uint32_t samp[32][8]; // sample indices of the 32 trials of a batch
   uint32_t pos_after[32];
-  double V[81];         // right singular vectors of the warp-level Jacobi SVD
+  int cnt[320];         // support count of hypothesis (trial j, model mi) at [10 j + mi]
+  uint16_t flat[320];   // hypotheses of the batch in replay order (10 j + mi)
+  uint16_t off[34];     // first entry of trial j in flat[]
+  uint16_t lo_ids[12];  // 0..9: hypotheses of a local estimate
+  int lo_cnt[12];
   int nm[32];
   int lo_nm;
   uint32_t mti, w, r;
 };
+
+static_assert(sizeof(WarpShared) % 8 == 0, "WarpShared must keep doubles aligned");
+constexpr size_t kDynSmemBytes = (size_t)kLaneWorkDoubles * kThreads * sizeof(double) + sizeof(WarpShared) * kWarpsPerBlock;
 
 __device__ inline void mt_seed(WarpShared& s, uint32_t seed) {
   s.mt[0] = seed;
@@ -120,10 +130,60 @@ __device__ __forceinline__ double translation_res(const double* T, double a0, do
   const double e0 = (b0 - a0) - T[0], e1 = (b1 - a1) - T[1];
   return e0 * e0 + e1 * e1;
 }
-__device__ __forceinline__ double residual(int type, const double* M, double2 a, double2 b) {
-  if (type == EST_H4) return transfer(M, a.x, a.y, b.x, b.y);
-  if (type == EST_T2) return translation_res(M, a.x, a.y, b.x, b.y);
+template <int TYPE>
+__device__ __forceinline__ double residual_t(const double* M, double2 a, double2 b) {
+  if (TYPE == EST_H4) return transfer(M, a.x, a.y, b.x, b.y);
+  if (TYPE == EST_T2) return translation_res(M, a.x, a.y, b.x, b.y);
   return sampson(M, a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ double residual(int type, const double* M, double2 a, double2 b) {
+  if (type == EST_H4) return residual_t<EST_H4>(M, a, b);
+  if (type == EST_T2) return residual_t<EST_T2>(M, a, b);
+  return residual_t<EST_F7>(M, a, b);
+}
+
+// Support counts of up to four hypotheses in one pass over the matches: the counts are pure
+// functions of (model, points), so they can be taken ahead of the ordered replay; four independent
+// residual chains per lane hide the FP64 divide latency and the points are loaded once.
+constexpr int kGroup = 4;
+template <int TYPE>
+__device__ __noinline__ void score_group(const double2* __restrict__ P1, const double2* __restrict__ P2, int M,
+                                         const double* __restrict__ models, const uint16_t* ids, int n, double max_res,
+                                         int lane, int* cnt_out) {
+  double m[kGroup][9];
+#pragma unroll
+  for (int u = 0; u < kGroup; ++u) {
+    const int id = ids[u < n ? u : n - 1];
+    const double* src = models + (id / 10) * 90 + (id % 10) * 9;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) m[u][k] = src[k];
+  }
+  int c[kGroup];
+#pragma unroll
+  for (int u = 0; u < kGroup; ++u) c[u] = 0;
+  for (int i0 = 0; i0 < M; i0 += 32) {
+    const int i = i0 + lane;
+    const bool ok = i < M;
+    const double2 a = P1[ok ? i : 0], b = P2[ok ? i : 0];
+#pragma unroll
+    for (int u = 0; u < kGroup; ++u) {
+      const bool in = ok && residual_t<TYPE>(m[u], a, b) <= max_res;
+      c[u] += __popc(__ballot_sync(kFull, in));
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int u = 0; u < kGroup; ++u)
+      if (u < n) cnt_out[ids[u]] = c[u];
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void score_group_any(int type, const double2* P1, const double2* P2, int M,
+                                                const double* models, const uint16_t* ids, int n, double max_res,
+                                                int lane, int* cnt_out) {
+  if (type == EST_H4) score_group<EST_H4>(P1, P2, M, models, ids, n, max_res, lane, cnt_out);
+  else if (type == EST_T2) score_group<EST_T2>(P1, P2, M, models, ids, n, max_res, lane, cnt_out);
+  else score_group<EST_F7>(P1, P2, M, models, ids, n, max_res, lane, cnt_out);
 }
 
 // InlierSupportMeasurer::Evaluate, count only (all lanes return the same value).
@@ -267,6 +327,74 @@ __device__ void warp_jacobi9(double* G, int rows, int ld, double* V, double* sig
   __syncwarp();
 }
 
+// Householder QR of G (rows x 9, column-major in global scratch, destroyed) by the warp: R (9 x 9
+// upper triangular, column-major like G) goes to shared memory.  A and R share singular values and right
+// singular vectors, so the Jacobi sweeps then run on 81 shared doubles instead of streaming the
+// rows x 9 matrix through L2 36 times per sweep (oracle: householder_r; Eigen::JacobiSVD
+// preconditions tall input with a QR too).  rows > 9.
+__device__ void warp_qr9(double* G, int rows, int ld, double* R, int lane) {
+  for (int i = lane; i < 81; i += 32) R[i] = 0.0;
+  __syncwarp();
+  for (int k = 0; k < 9; ++k) {
+    double* gk = G + (size_t)k * ld;
+    const int nj = 8 - k;  // columns right of k
+    // one pass over the rows below k: |v|^2 and v . g_j for every remaining column (independent loads)
+    double s = 0, w[8];
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) w[jj] = 0;
+    for (int r = lane; r < rows; r += 32) {
+      if (r <= k) continue;
+      const double a = gk[r];
+      s += a * a;
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj)
+        if (jj < nj) w[jj] += a * gk[(size_t)(jj + 1) * ld + r];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(kFull, s, o);
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) w[jj] += __shfl_xor_sync(kFull, w[jj], o);
+    }
+    const double x0 = gk[k];
+    const double nrm = sqrt(x0 * x0 + s);
+    if (nrm == 0.0) {
+      if (lane == 0)
+        for (int j = k + 1; j < 9; ++j) R[j * 9 + k] = G[(size_t)j * ld + k];
+      __syncwarp();
+      continue;
+    }
+    const double v0 = x0 + (x0 >= 0 ? nrm : -nrm);
+    const double beta = 2.0 / (v0 * v0 + s);
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+      if (jj < nj) {
+        const double gkj = gk[(size_t)(jj + 1) * ld + k];
+        w[jj] = (w[jj] + v0 * gkj) * beta;
+        if (lane == 0) R[(k + 1 + jj) * 9 + k] = gkj - w[jj] * v0;
+      }
+    }
+    for (int r = lane; r < rows; r += 32) {
+      if (r <= k) continue;
+      const double a = gk[r];
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj)
+        if (jj < nj) gk[(size_t)(jj + 1) * ld + r] -= w[jj] * a;
+    }
+    if (lane == 0) R[k * 9 + k] = (x0 >= 0 ? -nrm : nrm);
+    __syncwarp();
+  }
+}
+// Right singular vectors (descending) of the rows x 9 constraint matrix of a local estimator.
+__device__ void warp_svd9(double* G, int rows, int ld, WarpShared& sh, int lane) {
+  if (rows > 9) {
+    warp_qr9(G, rows, ld, sh.R, lane);
+    warp_jacobi9(sh.R, 9, 9, sh.V, sh.sig, lane);
+  } else {
+    warp_jacobi9(G, rows, ld, sh.V, sh.sig, lane);
+  }
+}
+
 // ---------------------------------------------------------------- local estimators
 // Hartley statistics of the inlier points (index list inl[0..N)) -- warp-parallel sums.
 __device__ void warp_hartley(const double2* P, const uint32_t* inl, int N, int lane, double* T) {
@@ -331,7 +459,7 @@ __device__ int local_estimate(int type, const double2* P1, const double2* P2, co
       G[6 * (size_t)ld + k] = a.x; G[7 * (size_t)ld + k] = a.y; G[8 * (size_t)ld + k] = 1;
     }
     __syncwarp();
-    warp_jacobi9(G, N, ld, sh.V, sig_sh, lane);
+    warp_svd9(G, N, ld, sh, lane);
     if (lane == 0) {
       double Eb[36];
       for (int k = 0; k < 4; ++k)
@@ -369,7 +497,7 @@ __device__ int local_estimate(int type, const double2* P1, const double2* P2, co
     }
   }
   __syncwarp();
-  warp_jacobi9(G, rows, ld, sh.V, sig_sh, lane);
+  warp_svd9(G, rows, ld, sh, lane);
   if (lane == 0) {
     double nv[9];
     for (int k = 0; k < 9; ++k) nv[k] = sh.V[k * 9 + 8];
@@ -426,6 +554,7 @@ __device__ void ransac_warp(int type, const double2* P1, const double2* P2, int 
   double best_model[9];
   for (int k = 0; k < 9; ++k) best_model[k] = 0.0;
   bool abort = false;
+  if (lane < 12) sh.lo_ids[lane] = (uint16_t)lane;
   for (int i = lane; i < M; i += 32) sc.idx[i] = (uint32_t)i;  // sampler.Initialize
   __syncwarp();
   unsigned long long dyn_max = max_trials;
@@ -479,6 +608,17 @@ __device__ void ransac_warp(int type, const double2* P1, const double2* P2, int 
         for (int k = 0; k < 9 * nm; ++k) mymodels[k] = mm[k];
       }
       sh.nm[lane] = nm;
+      // hypotheses of the batch in replay order
+      int incl = nm;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(kFull, incl, d);
+        if (lane >= d) incl += t;
+      }
+      const int first = incl - nm;
+      sh.off[lane] = (uint16_t)first;
+      if (lane == 31) sh.off[32] = (uint16_t)incl;
+      for (int mi = 0; mi < nm; ++mi) sh.flat[first + mi] = (uint16_t)(lane * 10 + mi);
     }
     __syncwarp();
     const long long c2 = clock64();
@@ -492,11 +632,16 @@ __device__ void ransac_warp(int type, const double2* P1, const double2* P2, int 
         if (lane == 0) sh.r = sh.pos_after[j - 1];  // un-draw trials >= j (j >= 1 here)
         break;
       }
+      if ((j & 7) == 0) {  // support counts of the next eight trials' hypotheses
+        const int g1 = sh.off[min(j + 8, 32)];
+        for (int g = sh.off[j]; g < g1; g += kGroup)
+          score_group_any(type, P1, P2, M, sc.models, sh.flat + g, min(kGroup, g1 - g), max_residual, lane, sh.cnt);
+      }
       const int nm = sh.nm[j];
       for (int mi = 0; mi < nm; ++mi) {
         double model[9];
         for (int k = 0; k < 9; ++k) model[k] = sc.models[(size_t)j * 90 + 9 * mi + k];
-        const int cnt = score_count(type, P1, P2, M, model, max_residual, lane);
+        const int cnt = sh.cnt[j * 10 + mi];
         bool better = cnt > best_count;
         double sum = 0;
         if (cnt >= best_count) {
@@ -523,10 +668,13 @@ __device__ void ransac_warp(int type, const double2* P1, const double2* P2, int 
             const long long cl0 = clock64();
             const int nlm = local_estimate(type, P1, P2, sc.inl, N, sc.G, sc.ld, sh, sig_sh, sc.lomodels, lane);
             lo_cycles += clock64() - cl0;
+            for (int g = 0; g < nlm; g += kGroup)
+              score_group_any(type, P1, P2, M, sc.lomodels, sh.lo_ids + g, min(kGroup, nlm - g), max_residual, lane,
+                              sh.lo_cnt);
             for (int li = 0; li < nlm; ++li) {
               double lm[9];
               for (int k = 0; k < 9; ++k) lm[k] = sc.lomodels[9 * li + k];
-              const int lc = score_count(type, P1, P2, M, lm, max_residual, lane);
+              const int lc = sh.lo_cnt[li];
               bool lbetter = lc > best_count;
               double lsum = 0;
               if (lc >= best_count) {
@@ -645,13 +793,11 @@ __device__ __forceinline__ bool in_box(double2 p, double minx, double maxx, doub
 
 __global__ void __launch_bounds__(kThreads)
 verify_pairs_kernel(VerifyArgs A) {
-  __shared__ WarpShared shs[kWarpsPerBlock];
-  __shared__ double sigs[kWarpsPerBlock][9];
-  extern __shared__ double lane_ws[];  // [kSvdWorkDoubles][kThreads]
+  extern __shared__ double lane_ws[];  // [kLaneWorkDoubles][kThreads] then WarpShared[kWarpsPerBlock]
   const LaneView ws{lane_ws + threadIdx.x};
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  WarpShared& sh = shs[wib];
-  double* sig_sh = sigs[wib];
+  WarpShared& sh = reinterpret_cast<WarpShared*>(lane_ws + kLaneWorkDoubles * kThreads)[wib];
+  double* sig_sh = sh.sig;
   const int worker = blockIdx.x * kWarpsPerBlock + wib;
   // carve this worker's scratch
   Scratch sc;
@@ -858,10 +1004,10 @@ __global__ void debug_sample_stream_kernel(uint32_t seed, int total, int k, int 
 
 __global__ void debug_solve_kernel(int type, int n, const double2* P1, const double2* P2, double* G, uint32_t* inl,
                                    double* models, int* n_models) {
-  __shared__ WarpShared sh;
-  __shared__ double sig[9];
   extern __shared__ double lane_ws[];  // same per-lane workspace layout as the production kernel
   const LaneView ws{lane_ws + threadIdx.x};
+  WarpShared& sh = *reinterpret_cast<WarpShared*>(lane_ws + kLaneWorkDoubles * kThreads);
+  double* sig = sh.sig;
   if (threadIdx.x >= 32) return;        // one warp works; the block size only fixes the stride
   const int lane = threadIdx.x;
   if (type == 3) {  // F 8-point local estimator on all n points
@@ -911,7 +1057,7 @@ cudaError_t launch_normalize_points(const b2_camera* cams, const int64_t* img_of
   return cudaGetLastError();
 }
 cudaError_t launch_verify_pairs(const VerifyArgs& a, int n_blocks, cudaStream_t s) {
-  const size_t dyn = (size_t)vf::kSvdWorkDoubles * vf::kThreads * sizeof(double);
+  const size_t dyn = vf::kDynSmemBytes;
   cudaError_t e = cudaFuncSetAttribute(vf::verify_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
   if (e != cudaSuccess) return e;
   vf::verify_pairs_kernel<<<n_blocks, vf::kThreads, dyn, s>>>(a);
@@ -931,7 +1077,7 @@ cudaError_t launch_debug_sample_stream(uint32_t seed, int total, int k, int n_tr
 }
 cudaError_t launch_debug_solve(int type, int n, const double* p1, const double* p2, double* G, uint32_t* inl,
                                double* models, int* n_models, cudaStream_t s) {
-  const size_t dyn = (size_t)vf::kSvdWorkDoubles * vf::kThreads * sizeof(double);
+  const size_t dyn = vf::kDynSmemBytes;
   cudaError_t e = cudaFuncSetAttribute(vf::debug_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
   if (e != cudaSuccess) return e;
   vf::debug_solve_kernel<<<1, vf::kThreads, dyn, s>>>(type, n, (const double2*)p1, (const double2*)p2, G, inl, models,

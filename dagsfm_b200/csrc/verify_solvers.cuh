@@ -39,7 +39,7 @@ struct View {
   __device__ __forceinline__ double& operator[](int i) const { return base[i * STRIDE]; }
   __device__ __forceinline__ View operator+(int off) const { return View{base + off * STRIDE}; }
 };
-constexpr int kSvdWorkDoubles = 72 + 81;  // G (<= 8 x 9) + V (9 x 9)
+constexpr int kLaneWorkDoubles = 72;  // transposed constraint matrix of a minimal solver (<= 9 x 8)
 
 template <int NMAX, typename GV, typename VV>
 __device__ __noinline__ void jacobi_svd(GV G, int m, int n, VV V, double* sig) {
@@ -107,6 +107,60 @@ __device__ __noinline__ void jacobi_svd(GV G, int m, int n, VV V, double* sig) {
       const int o = order[j];
       for (int i = 0; i < m; ++i) G[i * n + j] = tmpg[i * n + o];
     }
+  }
+}
+
+// Orthonormal basis of the null space of an M x 9 constraint matrix A (M < 9): Householder QR of
+// B = A^T (9 x M, element (r, c) at B[r * M + c], destroyed); the last 9 - M columns of Q span
+// null(A) whatever the rank of A.  The reference takes the same subspace from the trailing columns
+// of Eigen::JacobiSVD's V (fundamental_matrix.cc:55-60, homography_matrix.cc:84-90,
+// essential_matrix.cc:80-84); the models derived from it are normalised afterwards (F / F(2,2),
+// E / |E|, H homogeneous), so they do not depend on the basis, and the QR costs ~1/50 of a Jacobi
+// SVD per lane.  Everything is unrolled: the workspace offsets are immediates.
+template <int M, typename BV>
+__device__ __forceinline__ void null_space_qr(BV B, double* out) {
+  double beta[M];
+#pragma unroll
+  for (int k = 0; k < M; ++k) {
+    const double x0 = B[k * M + k];
+    double s = 0;
+#pragma unroll
+    for (int r = k + 1; r < 9; ++r) s += B[r * M + k] * B[r * M + k];
+    const double nrm = sqrt(x0 * x0 + s);
+    if (nrm == 0.0) {
+      beta[k] = 0.0;
+      continue;
+    }
+    const double v0 = x0 + (x0 >= 0 ? nrm : -nrm);
+    B[k * M + k] = v0;
+    beta[k] = 2.0 / (v0 * v0 + s);
+#pragma unroll
+    for (int j = k + 1; j < M; ++j) {
+      double w = v0 * B[k * M + j];
+#pragma unroll
+      for (int r = k + 1; r < 9; ++r) w += B[r * M + k] * B[r * M + j];
+      w *= beta[k];
+      B[k * M + j] -= w * v0;
+#pragma unroll
+      for (int r = k + 1; r < 9; ++r) B[r * M + j] -= w * B[r * M + k];
+    }
+  }
+#pragma unroll
+  for (int j = M; j < 9; ++j) {
+    double q[9];
+#pragma unroll
+    for (int r = 0; r < 9; ++r) q[r] = (r == j) ? 1.0 : 0.0;
+#pragma unroll
+    for (int k = M - 1; k >= 0; --k) {
+      double w = 0;
+#pragma unroll
+      for (int r = k; r < 9; ++r) w += B[r * M + k] * q[r];
+      w *= beta[k];
+#pragma unroll
+      for (int r = k; r < 9; ++r) q[r] -= w * B[r * M + k];
+    }
+#pragma unroll
+    for (int r = 0; r < 9; ++r) out[(j - M) * 9 + r] = q[r];
   }
 }
 
@@ -361,23 +415,42 @@ __device__ __noinline__ int real_roots(const double* coeffs_all, int nc, double*
   return nr;
 }
 
+// Hypotheses of one sample in a basis- and sign-independent order (oracle: CanonicalOrder): the
+// reference's order is an artefact of Eigen's eigenvalue deflation and SVD null-space basis.
+// Rank-counting (no data-dependent shifting loops, see the toolchain note in DESIGN.md).
+__device__ inline void canonical_order(double* models, int nm) {
+  if (nm < 2) return;
+  double key[10], tmp[90];
+  for (int j = 0; j < nm; ++j) {
+    double s = 0;
+    for (int k = 0; k < 9; ++k) {
+      tmp[9 * j + k] = models[9 * j + k];
+      s += (double)(k + 1) * (models[9 * j + k] * models[9 * j + k]);
+    }
+    key[j] = s;
+  }
+  for (int j = 0; j < nm; ++j) {
+    int rank = 0;
+    for (int i = 0; i < nm; ++i) rank += (key[i] < key[j] || (key[i] == key[j] && i < j)) ? 1 : 0;
+    for (int k = 0; k < 9; ++k) models[9 * rank + k] = tmp[9 * j + k];
+  }
+}
+
 // ------------------------------------------------------------------ F 7-point
 // p1, p2: 7 points each (x,y interleaved).  models: up to 3 x 9.  Returns count.
 template <int STRIDE>
 __device__ __noinline__ int solve_f7(View<STRIDE> ws, const double* p1, const double* p2, double* models) {
-  View<STRIDE> A = ws, V = ws + 72;
-  double sig[9];
   for (int i = 0; i < 7; ++i) {
     const double x0 = p1[2 * i], y0 = p1[2 * i + 1], x1 = p2[2 * i], y1 = p2[2 * i + 1];
-    View<STRIDE> a = A + 9 * i;
-    a[0] = x1 * x0; a[1] = x1 * y0; a[2] = x1; a[3] = y1 * x0; a[4] = y1 * y0; a[5] = y1;
-    a[6] = x0; a[7] = y0; a[8] = 1;
+    const double a[9] = {x1 * x0, x1 * y0, x1, y1 * x0, y1 * y0, y1, x0, y0, 1};
+    for (int r = 0; r < 9; ++r) ws[r * 7 + i] = a[r];
   }
-  jacobi_svd<9>(A, 7, 9, V, sig);
+  double nv[18];
+  null_space_qr<7>(ws, nv);
   double f1[9], f2[9];
   for (int i = 0; i < 9; ++i) {
-    f2[i] = V[i * 9 + 8];
-    f1[i] = V[i * 9 + 7] - f2[i];
+    f2[i] = nv[9 + i];
+    f1[i] = nv[i] - f2[i];
   }
   const double t0 = f1[4] * f1[8] - f1[5] * f1[7];
   const double t1 = f1[3] * f1[8] - f1[5] * f1[6];
@@ -407,6 +480,7 @@ __device__ __noinline__ int solve_f7(View<STRIDE> ws, const double* p1, const do
     for (int k = 0; k < 9; ++k) models[9 * nm + k] = F[k] / F[8];
     ++nm;
   }
+  canonical_order(models, nm);
   return nm;
 }
 
@@ -445,19 +519,17 @@ __device__ __noinline__ int solve_h4(View<STRIDE> ws, const double* p1, const do
   double n1[8], n2[8], T1[9], T2[9];
   center_and_normalize(p1, 4, n1, T1);
   center_and_normalize(p2, 4, n2, T2);
-  View<STRIDE> A = ws, V = ws + 72;
-  double sig[9];
-  for (int i = 0; i < 72; ++i) A[i] = 0.0;
+  for (int i = 0; i < 72; ++i) ws[i] = 0.0;
   for (int i = 0, j = 4; i < 4; ++i, ++j) {
     const double s_0 = n1[2 * i], s_1 = n1[2 * i + 1], d_0 = n2[2 * i], d_1 = n2[2 * i + 1];
-    View<STRIDE> a = A + 9 * i;
-    a[0] = -s_0; a[1] = -s_1; a[2] = -1; a[6] = s_0 * d_0; a[7] = s_1 * d_0; a[8] = d_0;
-    View<STRIDE> b = A + 9 * j;
-    b[3] = -s_0; b[4] = -s_1; b[5] = -1; b[6] = s_0 * d_1; b[7] = s_1 * d_1; b[8] = d_1;
+    // equation i: (-s, -1, 0, 0, 0, s d_0, d_0); equation j: (0, 0, 0, -s, -1, s d_1, d_1); stored transposed
+    ws[0 * 8 + i] = -s_0; ws[1 * 8 + i] = -s_1; ws[2 * 8 + i] = -1;
+    ws[6 * 8 + i] = s_0 * d_0; ws[7 * 8 + i] = s_1 * d_0; ws[8 * 8 + i] = d_0;
+    ws[3 * 8 + j] = -s_0; ws[4 * 8 + j] = -s_1; ws[5 * 8 + j] = -1;
+    ws[6 * 8 + j] = s_0 * d_1; ws[7 * 8 + j] = s_1 * d_1; ws[8 * 8 + j] = d_1;
   }
-  jacobi_svd<9>(A, 8, 9, V, sig);
   double Ht[9], T2i[9], tmp[9];
-  for (int k = 0; k < 9; ++k) Ht[k] = V[k * 9 + 8];
+  null_space_qr<8>(ws, Ht);
   mat3_inverse(T2, T2i);
   mat3_mul(T2i, Ht, tmp);
   mat3_mul(tmp, T1, model);
@@ -616,24 +688,20 @@ __device__ __noinline__ int solve_e5_from_basis(const double* Eb, double* models
     for (int k = 0; k < 9; ++k) models[9 * nm + k] = ev[k] / nrm;
     ++nm;
   }
+  canonical_order(models, nm);
   return nm;
 }
 
 // Minimal 5-point: 5 x 9 epipolar constraint matrix -> 4-dim null space -> models.
 template <int STRIDE>
 __device__ __noinline__ int solve_e5(View<STRIDE> ws, const double* p1, const double* p2, double* models) {
-  View<STRIDE> Q = ws, V = ws + 72;
-  double sig[9];
   for (int i = 0; i < 5; ++i) {
     const double x1_0 = p1[2 * i], x1_1 = p1[2 * i + 1], x2_0 = p2[2 * i], x2_1 = p2[2 * i + 1];
-    View<STRIDE> q = Q + 9 * i;
-    q[0] = x1_0 * x2_0; q[1] = x1_1 * x2_0; q[2] = x2_0; q[3] = x1_0 * x2_1; q[4] = x1_1 * x2_1;
-    q[5] = x2_1; q[6] = x1_0; q[7] = x1_1; q[8] = 1;
+    const double q[9] = {x1_0 * x2_0, x1_1 * x2_0, x2_0, x1_0 * x2_1, x1_1 * x2_1, x2_1, x1_0, x1_1, 1};
+    for (int r = 0; r < 9; ++r) ws[r * 5 + i] = q[r];
   }
-  jacobi_svd<9>(Q, 5, 9, V, sig);
   double Eb[36];
-  for (int k = 0; k < 4; ++k)
-    for (int i = 0; i < 9; ++i) Eb[9 * k + i] = V[i * 9 + 5 + k];
+  null_space_qr<5>(ws, Eb);
   return solve_e5_from_basis(Eb, models);
 }
 

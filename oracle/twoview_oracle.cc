@@ -91,7 +91,41 @@ static Mat3 inverse(const Mat3& a) {
 // On return: sigma[n] descending, V (n x n, row-major, columns = right singular
 // vectors in the same order), and, if U != nullptr, the m x n matrix of left
 // singular vectors scaled by sigma (i.e. A*V, columns orthogonal).
+// Tall inputs (m > n) are first reduced to the n x n triangular factor of a Householder QR (same
+// singular values and right singular vectors, backward stable) -- Eigen::JacobiSVD preconditions
+// non-square input the same way (its default ColPivHouseholderQRPreconditioner).
+static void householder_r(const double* A, int m, int n, double* R) {
+  std::vector<double> G(A, A + (size_t)m * n);
+  std::fill(R, R + n * n, 0.0);
+  for (int k = 0; k < n; ++k) {
+    double s = 0;
+    for (int r = k + 1; r < m; ++r) s += G[(size_t)r * n + k] * G[(size_t)r * n + k];
+    const double x0 = G[(size_t)k * n + k];
+    const double nrm = std::sqrt(x0 * x0 + s);
+    if (nrm == 0.0) {
+      for (int j = k + 1; j < n; ++j) R[k * n + j] = G[(size_t)k * n + j];
+      continue;
+    }
+    const double v0 = x0 + (x0 >= 0 ? nrm : -nrm);
+    const double beta = 2.0 / (v0 * v0 + s);
+    for (int j = k + 1; j < n; ++j) {
+      double w = 0;
+      for (int r = k + 1; r < m; ++r) w += G[(size_t)r * n + k] * G[(size_t)r * n + j];
+      w = (w + v0 * G[(size_t)k * n + j]) * beta;
+      for (int r = k + 1; r < m; ++r) G[(size_t)r * n + j] -= w * G[(size_t)r * n + k];
+      R[k * n + j] = G[(size_t)k * n + j] - w * v0;
+    }
+    R[k * n + k] = (x0 >= 0 ? -nrm : nrm);
+  }
+}
+
 static void jacobi_svd(const double* A, int m, int n, double* sigma, double* V, double* AV) {
+  if (m > n && AV == nullptr) {
+    std::vector<double> R((size_t)n * n);
+    householder_r(A, m, n, R.data());
+    jacobi_svd(R.data(), n, n, sigma, V, nullptr);
+    return;
+  }
   std::vector<double> G(A, A + (size_t)m * n);
   std::vector<double> W((size_t)n * n, 0.0);
   for (int i = 0; i < n; ++i) W[i * n + i] = 1.0;
@@ -426,6 +460,64 @@ static void HomographyResiduals(const std::vector<Vec2>& p1, const std::vector<V
 }
 
 // ------------------------------------------------------------------ F 7-point
+// Null space of an exactly under-determined constraint matrix A (m x 9 row-major, m < 9): the last
+// 9 - m columns of Q in the Householder QR of A^T; out = (9 - m) unit vectors of 9.
+// The reference reads the same subspace off the trailing columns of Eigen::JacobiSVD's V
+// (fundamental_matrix.cc:55-60, homography_matrix.cc:84-90, essential_matrix.cc:80-84).  Which basis
+// of an exact null space a particular SVD returns is an artefact of that SVD (Eigen itself starts
+// from a QR preconditioner for non-square input); the models built from the basis are normalised
+// and therefore basis-independent up to rounding.  QR was chosen over the one-sided Jacobi used for
+// the over-determined cases because it is ~50x cheaper and leaves smaller constraint residuals on
+// the 5-point problem.  Operation order matches dagsfm_b200/csrc/verify_solvers.cuh: null_space_qr.
+static void NullSpaceQR(const double* A, int m, double* out) {
+  double B[9 * 8], beta[8];
+  for (int r = 0; r < 9; ++r)
+    for (int c = 0; c < m; ++c) B[r * m + c] = A[c * 9 + r];
+  for (int k = 0; k < m; ++k) {
+    const double x0 = B[k * m + k];
+    double s = 0;
+    for (int r = k + 1; r < 9; ++r) s += B[r * m + k] * B[r * m + k];
+    const double nrm = std::sqrt(x0 * x0 + s);
+    if (nrm == 0.0) { beta[k] = 0.0; continue; }
+    const double v0 = x0 + (x0 >= 0 ? nrm : -nrm);
+    B[k * m + k] = v0;
+    beta[k] = 2.0 / (v0 * v0 + s);
+    for (int j = k + 1; j < m; ++j) {
+      double w = v0 * B[k * m + j];
+      for (int r = k + 1; r < 9; ++r) w += B[r * m + k] * B[r * m + j];
+      w *= beta[k];
+      B[k * m + j] -= w * v0;
+      for (int r = k + 1; r < 9; ++r) B[r * m + j] -= w * B[r * m + k];
+    }
+  }
+  for (int j = m; j < 9; ++j) {
+    double q[9];
+    for (int r = 0; r < 9; ++r) q[r] = (r == j) ? 1.0 : 0.0;
+    for (int k = m - 1; k >= 0; --k) {
+      double w = 0;
+      for (int r = k; r < 9; ++r) w += B[r * m + k] * q[r];
+      w *= beta[k];
+      for (int r = k; r < 9; ++r) q[r] -= w * B[r * m + k];
+    }
+    for (int r = 0; r < 9; ++r) out[(j - m) * 9 + r] = q[r];
+  }
+}
+
+// Order of the hypotheses of ONE sample.  The reference emits them in the order Eigen's
+// EigenSolver deflates the companion matrix's eigenvalues and in the (algorithm-defined) basis
+// JacobiSVD happens to return for an exactly rank-deficient constraint matrix: neither can be
+// restated without Eigen, and the order only matters for exact support ties.  This restatement and
+// the CUDA path (which takes the null space from a Householder QR, a different but equally valid
+// basis) therefore sort the normalised models by a basis- and sign-independent key.
+static void CanonicalOrder(std::vector<Mat3>* models) {
+  auto key = [](const Mat3& M) {
+    double s = 0;
+    for (int k = 0; k < 9; ++k) s += (double)(k + 1) * (M.m[k] * M.m[k]);
+    return s;
+  };
+  std::stable_sort(models->begin(), models->end(), [&](const Mat3& a, const Mat3& b) { return key(a) < key(b); });
+}
+
 static std::vector<Mat3> F7(const std::vector<Vec2>& p1, const std::vector<Vec2>& p2) {
   double A[7 * 9];
   for (int i = 0; i < 7; ++i) {
@@ -433,10 +525,10 @@ static std::vector<Mat3> F7(const std::vector<Vec2>& p1, const std::vector<Vec2>
     double* a = A + 9 * i;
     a[0] = x1 * x0; a[1] = x1 * y0; a[2] = x1; a[3] = y1 * x0; a[4] = y1 * y0; a[5] = y1; a[6] = x0; a[7] = y0; a[8] = 1;
   }
-  double sig[9], V[81];
-  jacobi_svd(A, 7, 9, sig, V, nullptr);
+  double nv[18];
+  NullSpaceQR(A, 7, nv);
   double f1[9], f2[9];
-  for (int i = 0; i < 9; ++i) { f1[i] = V[i * 9 + 7]; f2[i] = V[i * 9 + 8]; }
+  for (int i = 0; i < 9; ++i) { f1[i] = nv[i]; f2[i] = nv[9 + i]; }
   for (int i = 0; i < 9; ++i) f1[i] -= f2[i];
   const double t0 = f1[4] * f1[8] - f1[5] * f1[7];
   const double t1 = f1[3] * f1[8] - f1[5] * f1[6];
@@ -468,6 +560,7 @@ static std::vector<Mat3> F7(const std::vector<Vec2>& p1, const std::vector<Vec2>
     for (int k = 0; k < 9; ++k) M.m[k] = F[k] / F[8];  // reshape + transpose == row-major
     models.push_back(M);
   }
+  CanonicalOrder(&models);
   return models;
 }
 
@@ -515,10 +608,14 @@ static std::vector<Mat3> HomographyDLT(const std::vector<Vec2>& p1, const std::v
     double* b = A.data() + 9 * j;
     b[3] = -s_0; b[4] = -s_1; b[5] = -1; b[6] = s_0 * d_1; b[7] = s_1 * d_1; b[8] = d_1;
   }
-  double sig[9], V[81];
-  jacobi_svd(A.data(), (int)(2 * N), 9, sig, V, nullptr);
   Mat3 Ht;  // H_t.transpose() == row-major reshape
-  for (int k = 0; k < 9; ++k) Ht.m[k] = V[k * 9 + 8];
+  if (N == 4) {
+    NullSpaceQR(A.data(), 8, Ht.m);
+  } else {
+    double sig[9], V[81];
+    jacobi_svd(A.data(), (int)(2 * N), 9, sig, V, nullptr);
+    for (int k = 0; k < 9; ++k) Ht.m[k] = V[k * 9 + 8];
+  }
   return {mul(mul(inverse(T2), Ht), T1)};
 }
 
@@ -658,11 +755,15 @@ static std::vector<Mat3> E5(const std::vector<Vec2>& p1, const std::vector<Vec2>
     double* q = Q.data() + 9 * i;
     q[0] = x1_0 * x2_0; q[1] = x1_1 * x2_0; q[2] = x2_0; q[3] = x1_0 * x2_1; q[4] = x1_1 * x2_1; q[5] = x2_1; q[6] = x1_0; q[7] = x1_1; q[8] = 1;
   }
-  double sig[9], V[81];
-  jacobi_svd(Q.data(), n, 9, sig, V, nullptr);
   double Eb[4][9];
-  for (int k = 0; k < 4; ++k)
-    for (int i = 0; i < 9; ++i) Eb[k][i] = V[i * 9 + 5 + k];
+  if (n == 5) {
+    NullSpaceQR(Q.data(), 5, &Eb[0][0]);
+  } else {
+    double sig[9], V[81];
+    jacobi_svd(Q.data(), n, 9, sig, V, nullptr);
+    for (int k = 0; k < 4; ++k)
+      for (int i = 0; i < 9; ++i) Eb[k][i] = V[i * 9 + 5 + k];
+  }
   double A[200];
   E5BuildSystem(Eb, A);
   if (A_out) memcpy(A_out, A, sizeof A);
@@ -707,6 +808,7 @@ static std::vector<Mat3> E5(const std::vector<Vec2>& p1, const std::vector<Vec2>
     for (int k = 0; k < 9; ++k) M.m[k] = ev[k] / nrm;
     models.push_back(M);
   }
+  CanonicalOrder(&models);
   return models;
 }
 

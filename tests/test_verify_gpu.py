@@ -11,6 +11,7 @@ import numpy as np
 import pytest
 
 from oracle import pyoracle as orc
+from tests.tv_scene import scene
 
 pytestmark = pytest.mark.gpu
 
@@ -21,20 +22,6 @@ def ver():
     v = TwoViewGeometryVerifier(0)
     yield v
     v.close()
-
-
-def scene(rng, n_in, n_out, planar=False, noise=0.3, f=1200.0, ang=0.15, t=(-1.0, 0.1, 0.2)):
-    c = 500.0
-    X = rng.uniform(-1, 1, (n_in, 3)) * [2, 2, 1] + [0, 0, 8]
-    if planar:
-        X[:, 2] = 8 + 0.1 * X[:, 0]
-    R = np.array([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]])
-    x1 = f * X[:, :2] / X[:, 2:] + c + rng.normal(0, noise, (n_in, 2))
-    Xc = X @ R.T + np.array(t)
-    x2 = f * Xc[:, :2] / Xc[:, 2:] + c + rng.normal(0, noise, (n_in, 2))
-    o1 = rng.uniform(0, 1000, (n_out, 2))
-    o2 = rng.uniform(0, 1000, (n_out, 2))
-    return np.r_[x1, o1], np.r_[x2, o2]
 
 
 @pytest.mark.parametrize("total,k", [(50, 7), (7, 7), (1000, 5), (33, 4), (20, 1)])

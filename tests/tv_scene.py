@@ -48,3 +48,17 @@ def make_pairs(n_pairs=1000, n_in=(120, 400), n_out=(40, 250), seed=0, noise=0.5
     pairs = np.stack([2 * np.arange(n_pairs), 2 * np.arange(n_pairs) + 1], 1).astype(np.uint32)
     return {"keypoints": keypoints, "pairs": pairs, "match_offsets": off, "matches": matches, "prior": prior,
             "cam_params": (f, c, c, 0.0), "width": width, "n_inliers_true": ni}
+
+
+def scene(rng, n_in, n_out, planar=False, noise=0.3, f=1200.0, ang=0.15, t=(-1.0, 0.1, 0.2)):
+    c = 500.0
+    X = rng.uniform(-1, 1, (n_in, 3)) * [2, 2, 1] + [0, 0, 8]
+    if planar:
+        X[:, 2] = 8 + 0.1 * X[:, 0]
+    R = np.array([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]])
+    x1 = f * X[:, :2] / X[:, 2:] + c + rng.normal(0, noise, (n_in, 2))
+    Xc = X @ R.T + np.array(t)
+    x2 = f * Xc[:, :2] / Xc[:, 2:] + c + rng.normal(0, noise, (n_in, 2))
+    o1 = rng.uniform(0, 1000, (n_out, 2))
+    o2 = rng.uniform(0, 1000, (n_out, 2))
+    return np.r_[x1, o1], np.r_[x2, o2]
