@@ -190,7 +190,7 @@ def bench_verify(a, local_rank, rank, world, cores, barrier):
     if rank == 0 and not a.no_cpu:
         from oracle import pyoracle as orc
         import ctypes as C
-        ns = min(n, max(64, 2 * cores))
+        ns = min(n, max(64, 1000 * cores))   # ~10-15 s of host work at ~80 pairs/s per core
         ocams = (orc.OrcCamera * (2 * ns))(*[orc.make_camera(params=w["cam_params"], prior=bool(p)) for p in w["prior"][:2 * ns]])
         ptrs = (C.c_void_p * (2 * ns))(*[k.ctypes.data for k in w["keypoints"][:2 * ns]])
         oo = orc.tv_default_options()

@@ -116,8 +116,11 @@ struct ImageStore {
   }
   // Lays the images out (each padded to 256 rows), allocates a zeroed pool.
   int layout(int32_t n, const int32_t* n_desc, cudaStream_t s) {
-    release();
     if (n < 0) return set_error(B2_ERR_INVALID, "n_images < 0");
+    // Same image sizes as the previous upload (the per-step re-upload of a fixed job): keep the
+    // pool, its padding rows are still zero and every descriptor row is about to be overwritten.
+    if (pool && n == n_images && n > 0 && std::equal(n_desc, n_desc + n, h_img_n.begin())) return B2_OK;
+    release();
     h_img_n.assign(n_desc, n_desc + n);
     h_img_row.resize(n);
     uint64_t rows = 0;

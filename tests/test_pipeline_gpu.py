@@ -1,0 +1,94 @@
+"""Match -> verify with the match lists staying on the device (the reference
+round-trips every pair through host queues, feature/matching.cc:749-839).
+
+b2_match_pairs_device writes (offsets, matches) straight into the buffers b2_verify_pairs_device
+reads; the result must equal (a) the host-buffer path of the same library and (b) the oracle's
+MatchSiftFeaturesCPU -> TwoViewGeometry::Estimate chain on the same inputs and seeds."""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as orc
+from tests.tv_scene import scene
+
+pytestmark = pytest.mark.gpu
+
+
+def _descriptors(rng, n):
+    d = rng.gamma(0.6, 1.0, (n, 128)).astype(np.float32)
+    return np.stack([orc.l2_normalize_to_u8(v) for v in d])
+
+
+def _images(rng, n_pairs):
+    kps, descs, pairs = [], [], []
+    for k in range(n_pairs):
+        n_in, n_out = 150 + 20 * k, 40 + 10 * k
+        p1, p2 = scene(rng, n_in, n_out, planar=(k % 3 == 2), noise=0.4)
+        base = _descriptors(rng, n_in)
+        d1 = np.r_[base, _descriptors(rng, n_out)]
+        jit = base.astype(np.float32) + rng.normal(0, 2.0, base.shape).astype(np.float32)
+        d2 = np.r_[np.stack([orc.l2_normalize_to_u8(np.maximum(v, 0)) for v in jit]), _descriptors(rng, n_out)]
+        perm = rng.permutation(len(p2))
+        kps += [p1, p2[perm]]
+        descs += [d1, d2[perm]]
+        pairs.append((2 * k, 2 * k + 1))
+    return kps, descs, np.array(pairs, np.uint32)
+
+
+def test_device_resident_match_then_verify_equals_host_path_and_oracle():
+    import torch
+    from dagsfm_b200 import Camera, SiftMatchGPU, SiftMatchingOptions, TwoViewGeometryVerifier, TwoViewOptions
+    from dagsfm_b200.verification import RESULT_DTYPE
+
+    rng = np.random.default_rng(42)
+    n_pairs = 6
+    kps, descs, pairs = _images(rng, n_pairs)
+    seeds = np.arange(100, 100 + n_pairs, dtype=np.uint32)
+    mo, vo = SiftMatchingOptions(), TwoViewOptions.default()
+    m, v = SiftMatchGPU(0), TwoViewGeometryVerifier(0)
+    try:
+        m.set_images(descs)
+        v.set_images([Camera.make(prior_focal=False)] * len(kps), kps)
+        # host-buffer path
+        off_h, mt_h = m.match_pairs(pairs, mo)
+        res_h, inl_h = v.verify_pairs(pairs, off_h, mt_h, vo, seeds)
+        assert all(off_h[k + 1] - off_h[k] >= 100 for k in range(n_pairs))
+        # device-resident path: nothing but the final results crosses PCIe
+        dev = torch.device("cuda:0")
+        cap = int(sum(min(len(descs[a]), len(descs[b])) for a, b in pairs))
+        pairs_d = torch.from_numpy(pairs.astype(np.int32).reshape(-1)).to(dev)
+        off_d = torch.zeros(n_pairs + 1, dtype=torch.int64, device=dev)
+        mt_d = torch.zeros(cap * 2, dtype=torch.int32, device=dev)
+        total = m.match_pairs_device(n_pairs, pairs_d.data_ptr(), mo, off_d.data_ptr(), mt_d.data_ptr(), cap)
+        assert total == len(mt_h)
+        seeds_d = torch.from_numpy(seeds.astype(np.int32)).to(dev)
+        res_d = torch.zeros(n_pairs * RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+        inl_d = torch.zeros(cap * 2, dtype=torch.int32, device=dev)
+        v.verify_pairs_device(n_pairs, pairs_d.data_ptr(), off_d.data_ptr(), mt_d.data_ptr(), vo, seeds_d.data_ptr(),
+                              res_d.data_ptr(), inl_d.data_ptr())
+        torch.cuda.synchronize()
+        res_g = res_d.cpu().numpy().view(RESULT_DTYPE)
+        inl_g = inl_d.cpu().numpy().view(np.uint32).reshape(-1, 2)
+        assert off_d.cpu().numpy().tolist() == off_h.tolist()
+        assert mt_d.cpu().numpy().view(np.uint32).reshape(-1, 2)[:total].tolist() == mt_h.tolist()
+        assert res_g.tobytes() == res_h.tobytes()          # same kernels, same seeds: bit-identical
+        for k in range(n_pairs):
+            n = res_h["n_inliers"][k]
+            assert inl_g[off_h[k]:off_h[k] + n].tolist() == inl_h[off_h[k]:off_h[k] + n].tolist()
+    finally:
+        m.close()
+        v.close()
+    # oracle chain on the same inputs
+    oopt = orc.tv_default_options()
+    cam = orc.make_camera(prior=False)
+    cfgs = set()
+    for k, (a, b) in enumerate(pairs):
+        mc = orc.match_sift(descs[a], descs[b], max_ratio=mo.max_ratio, max_distance=mo.max_distance,
+                            cross_check=mo.cross_check)
+        assert mc.tolist() == mt_h[off_h[k]:off_h[k + 1]].tolist()
+        r, oi = orc.two_view(cam, kps[a], cam, kps[b], mc, oopt, seed=int(seeds[k]))
+        g = res_h[k]
+        assert (g["config"], g["n_inliers"], g["E_num_inliers"], g["F_num_inliers"], g["H_num_inliers"]) == \
+               (r.config, r.n_inliers, r.E_inl, r.F_inl, r.H_inl)
+        assert inl_h[off_h[k]:off_h[k] + r.n_inliers].tolist() == oi.tolist()
+        cfgs.add(int(g["config"]))
+    assert cfgs & {3, 4, 6}     # UNCALIBRATED and planar configurations both occur
