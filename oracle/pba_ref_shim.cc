@@ -11,7 +11,14 @@
 #include <cstring>
 #include <vector>
 
+#ifdef B2_PBA_SHIM
+// The same driver compiled against include/dagsfm_b200/pba_shim.hpp instead of the reference's
+// pba.h (tests/test_pba_shim.py): shows that code written for PBA's interface drives b2_ba_solve.
+#include "dagsfm_b200/pba_shim.hpp"
+namespace pba = dagsfm_b200::pba;
+#else
 #include "pba.h"
+#endif
 
 extern "C" int pba_ref_run(int n_cam, const double* focal, const double* radial, const double* R_rowmajor /*[n][9]*/,
                            const double* t /*[n][3]*/, const unsigned char* cam_const, int n_pts, double* xyz,

@@ -339,13 +339,13 @@ def pba_ref_available() -> bool:
     return PBA_REF_PATH.exists()
 
 
-def pba_ref_solve(prob: dict, n_threads=8, max_iter=50):
+def pba_ref_solve(prob: dict, n_threads=8, max_iter=50, lib_path=None):
     """Runs the reference's vendored PBA (CPU double) on a tests/ba_scene problem with unshared
     SIMPLE_RADIAL cameras.  Gauge: images with const pose become constant cameras (PBA cannot
     fix partial extrinsics).  Returns dict(initial_mse, final_mse, lm_iterations, seconds) and
     updates xyz in prob (float32-quantised, as PBA's interface is)."""
     from tests.ba_scene import R_from_quat
-    L = C.CDLL(str(PBA_REF_PATH))
+    L = C.CDLL(str(lib_path or PBA_REF_PATH))
     L.pba_ref_run.argtypes = [C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p,
                                                              C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 5
     n = len(prob["qvec"])
