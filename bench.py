@@ -275,7 +275,9 @@ def main():
     workload = f"C2: {a.images} images x {a.desc} desc, exhaustive match + ratio test"
     cfg = {"workload": workload, "n_images": a.images, "desc_per_image": a.desc,
            "options": "max_ratio 0.8, max_distance 0.7, cross_check 1",
-           "l2": "descriptor pool 512 MiB > 126 MB L2 (inputs larger than L2)",
+           "l2": (lambda mib: f"descriptor pool {mib:.0f} MiB " + ("> 126 MB L2 (inputs larger than L2)" if mib > 126
+                                                                     else "<= 126 MB L2 (NOT a valid timing configuration)"))(
+               a.images * a.desc * 128 / 2**20),
            "sharding": "pairs replicated per rank, no collective"}
 
     import torch

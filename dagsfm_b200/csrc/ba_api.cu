@@ -27,6 +27,7 @@ struct b2_ba {
   int n_sm = 148;
   cudaStream_t stream = nullptr;
   cusolverDnHandle_t solver = nullptr;
+  cusolverDnParams_t solver_params = nullptr;
   b2_allreduce_fn allreduce = nullptr;
   void* allreduce_user = nullptr;
   std::vector<void*> allocs;
@@ -115,7 +116,13 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
   int64_t NP = 0;
   for (int p = 0; p < n_pts; ++p)
     if (pt_used[p] && !pr->const_point[p]) pt_col[p] = (int32_t)NP++;
-  if (D > 46000) return set_error(B2_ERR_INVALID, "reduced camera system too large for the dense Schur path");
+  {  // the reduced camera system is dense: D x D doubles must fit in this GPU's memory
+    size_t free_b = 0, total_b = 0;
+    B2_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const double need = ((double)D * (double)D + 3.0 * (double)D) * 8.0 + (double)n_obs * sizeof(ObsJac);
+    if (need > 0.9 * (double)free_b)
+      return set_error(B2_ERR_INVALID, "reduced camera system too large for the dense Schur path on this GPU");
+  }
   std::vector<int64_t> pt_start(n_pts + 1, 0);
   for (int64_t o = 0; o < n_obs; ++o) pt_start[pr->obs_point[o] + 1]++;
   for (int p = 0; p < n_pts; ++p) pt_start[p + 1] += pt_start[p];
@@ -181,12 +188,16 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
   P.gmax = scal + 7;
   int* d_info;
   B2_TRY(dev_alloc(h, &d_info, 1));
-  double* work = nullptr;
-  int lwork = 0;
+  // 64-bit cuSOLVER entry points: D * D exceeds 2^31 elements from D = 46 341 on
+  uint8_t* work = nullptr;
+  size_t work_dev = 0, work_host = 0;
+  std::vector<uint8_t> work_h;
   if (D > 0) {
-    if (cusolverDnDpotrf_bufferSize(h->solver, CUBLAS_FILL_MODE_LOWER, (int)D, P.S, (int)D, &lwork) != CUSOLVER_STATUS_SUCCESS)
-      return set_error(B2_ERR_CUDA, "cusolverDnDpotrf_bufferSize failed");
-    B2_TRY(dev_alloc(h, &work, (size_t)lwork));
+    if (cusolverDnXpotrf_bufferSize(h->solver, h->solver_params, CUBLAS_FILL_MODE_LOWER, D, CUDA_R_64F, P.S, D,
+                                    CUDA_R_64F, &work_dev, &work_host) != CUSOLVER_STATUS_SUCCESS)
+      return set_error(B2_ERR_CUDA, "cusolverDnXpotrf_bufferSize failed");
+    B2_TRY(dev_alloc(h, &work, std::max<size_t>(work_dev, 8)));
+    work_h.resize(std::max<size_t>(work_host, 8));
   }
   if (n_obs == 0 && !h->allreduce) return B2_OK;  // BundleAdjuster::Solve returns false: nothing to do
 
@@ -231,11 +242,13 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
     int info = 0;
     if (D > 0) {
       B2_CUDA(cudaMemcpyAsync(P.dc, P.rhs, D * 8, cudaMemcpyDeviceToDevice, s));
-      if (cusolverDnDpotrf(h->solver, CUBLAS_FILL_MODE_LOWER, (int)D, P.S, (int)D, work, lwork, d_info) != CUSOLVER_STATUS_SUCCESS)
-        return set_error(B2_ERR_CUDA, "cusolverDnDpotrf failed");
+      if (cusolverDnXpotrf(h->solver, h->solver_params, CUBLAS_FILL_MODE_LOWER, D, CUDA_R_64F, P.S, D, CUDA_R_64F,
+                           work, work_dev, work_h.data(), work_host, d_info) != CUSOLVER_STATUS_SUCCESS)
+        return set_error(B2_ERR_CUDA, "cusolverDnXpotrf failed");
       B2_CUDA(cudaMemcpyAsync(&info, d_info, sizeof(int), cudaMemcpyDeviceToHost, s));
-      if (cusolverDnDpotrs(h->solver, CUBLAS_FILL_MODE_LOWER, (int)D, 1, P.S, (int)D, P.dc, (int)D, d_info) != CUSOLVER_STATUS_SUCCESS)
-        return set_error(B2_ERR_CUDA, "cusolverDnDpotrs failed");
+      if (cusolverDnXpotrs(h->solver, h->solver_params, CUBLAS_FILL_MODE_LOWER, D, 1, CUDA_R_64F, P.S, D, CUDA_R_64F,
+                           P.dc, D, d_info) != CUSOLVER_STATUS_SUCCESS)
+        return set_error(B2_ERR_CUDA, "cusolverDnXpotrs failed");
       B2_CUDA(ba_launch_negate(P.dc, D, s));
     }
     B2_CUDA(ba_launch_backsub(P, s));
@@ -352,6 +365,7 @@ int b2_ba_create(int device, b2_ba** out) {
   B2_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   if (cusolverDnCreate(&h->solver) != CUSOLVER_STATUS_SUCCESS) return set_error(B2_ERR_CUDA, "cusolverDnCreate failed");
   cusolverDnSetStream(h->solver, h->stream);
+  if (cusolverDnCreateParams(&h->solver_params) != CUSOLVER_STATUS_SUCCESS) return set_error(B2_ERR_CUDA, "cusolverDnCreateParams failed");
   for (auto& e : h->ev) B2_CUDA(cudaEventCreate(&e));
   *out = h;
   return B2_OK;
@@ -362,6 +376,7 @@ int b2_ba_destroy(b2_ba* h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   free_all(h);
+  if (h->solver_params) cusolverDnDestroyParams(h->solver_params);
   if (h->solver) cusolverDnDestroy(h->solver);
   for (auto e : h->ev) if (e) cudaEventDestroy(e);
   cudaStreamDestroy(h->stream);
