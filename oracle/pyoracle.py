@@ -23,11 +23,33 @@ def build(force: bool = False) -> Path:
     return LIB_PATH
 
 
+def _usable_cores() -> int:
+    """Affinity mask capped by the cgroup CPU quota (a box may show 128 CPUs and grant 16)."""
+    import os
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = Path("/sys/fs/cgroup/cpu.max").read_text().split()
+        if q != "max":
+            n = max(1, min(n, int(float(q) / float(per) + 0.5)))
+    except Exception:
+        pass
+    return n
+
+
+def _cap_openmp() -> None:
+    # libgomp would otherwise start one spinning thread per visible CPU; under a cgroup quota
+    # that turns every parallel region of ba_oracle.cc into a throttled busy-wait.
+    import os
+    os.environ.setdefault("OMP_NUM_THREADS", str(_usable_cores()))
+    os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
+
+
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
         if not LIB_PATH.exists():
             build()
+        _cap_openmp()
         L = C.CDLL(str(LIB_PATH))
         vp = C.c_void_p
         L.orc_match_sift.argtypes = [vp, C.c_int, vp, C.c_int, C.c_float, C.c_float, C.c_int, vp, C.c_int]
