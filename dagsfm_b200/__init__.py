@@ -5,7 +5,8 @@ bundle-adjuster interfaces over the C ABI (include/dagsfm_b200.h); all numeric
 work runs in the hand-written sm_100a CUDA library.
 """
 from ._lib import B2Error, MatchOptions, lib  # noqa: F401
-from .matching import SiftMatchGPU, SiftMatchingOptions, match_sift_features_gpu  # noqa: F401
+from .matching import (SiftMatchGPU, SiftMatchingOptions, match_guided_sift_features_gpu,  # noqa: F401
+                       match_sift_features_gpu)
 
 from .verification import (Camera, TwoViewGeometryVerifier, TwoViewOptions,  # noqa: F401
                            TwoViewResult)

@@ -53,6 +53,8 @@ def lib() -> C.CDLL:
     L.b2_match_set_descriptors.argtypes = [vp, C.c_int, i32, vp]
     L.b2_match_run.argtypes = [vp, P(MatchOptions), vp, P(i32)]
     L.b2_match_last_timing.argtypes = [vp, P(C.c_double), P(C.c_double), P(i64), P(i64)]
+    L.b2_match_set_keypoints.argtypes = [vp, i32, P(vp), P(i32)]
+    L.b2_match_guided_pairs.argtypes = [vp, i64, vp, vp, C.c_double, P(MatchOptions), vp, vp, i64, P(i64)]
     _lib = L
     return L
 

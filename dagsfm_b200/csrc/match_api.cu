@@ -20,6 +20,8 @@
 #include "../../include/dagsfm_b200.h"
 #include "common_host.h"
 #include "match_common.cuh"
+#include "match_guided.cuh"
+#include "match_thresholds.h"
 
 namespace b2 {
 
@@ -50,6 +52,11 @@ cudaError_t launch_cross_count(const PairMeta* meta, int64_t n_pairs, const int*
 cudaError_t launch_cross_write(const PairMeta* meta, int64_t n_pairs, const int* midx,
                                int cross_check, const int64_t* offsets, uint32_t* out_matches,
                                int64_t capacity, cudaStream_t s);
+cudaError_t launch_guided_item_pairs(const PairMeta* meta, int64_t n_pairs, uint32_t* item_pair, cudaStream_t s);
+cudaError_t launch_guided_match(const uint8_t* pool, const float* kp_pool, const MatchItem* items,
+                                const uint32_t* item_pair, const uint32_t* n_items_ptr, const PairMeta* meta,
+                                const GuidedGeom* geoms, float max_residual, int thr_dist, const int* ratio_lim,
+                                int* midx, int n_sm, cudaStream_t s);
 
 constexpr bool kDefaultTs = true;   // TS kernel (query operand in tensor memory) is the production kernel
 static inline uint32_t pad_up(uint32_t n, uint32_t m) { return (n + m - 1) / m * m; }
@@ -91,6 +98,7 @@ static int make_pool_tmap(CUtensorMap* tm, void* pool, uint64_t rows, uint32_t b
 // --------------------------------------------------------------- image store
 struct ImageStore {
   uint8_t* pool = nullptr;
+  float* kp_pool = nullptr;  // (x, y) per pool row, guided matching only
   uint64_t pool_rows = 0;
   int32_t n_images = 0;
   int32_t* d_img_n = nullptr;
@@ -103,6 +111,8 @@ struct ImageStore {
 
   void release() {
     if (pool) cudaFree(pool);
+    if (kp_pool) cudaFree(kp_pool);
+    kp_pool = nullptr;
     if (d_img_n) cudaFree(d_img_n);
     if (d_img_row) cudaFree(d_img_row);
     pool = nullptr;
@@ -149,46 +159,21 @@ struct ImageStore {
 };
 
 // ------------------------------------------------------------ threshold tables
-// FindBestMatchesOneWay (sift.cc:111-162) evaluates, in float32,
-//     a(v)   = acos(min(kDistNorm * v, 1))
-//     reject   if a(best) >  max_distance
-//     reject   if a(best) >= max_ratio * a(second)
-// a() is monotone non-increasing in the integer dot v, so both tests are threshold
-// tests on integers.  The tables are built with the host's own acosf -- the very
-// function the reference CPU path calls -- so the device decision is identical.
+// Device copy of the integer threshold tables of match_thresholds.h.
 struct ThresholdTables {
   float max_ratio = -1.f, max_distance = -1.f;
   int thr_dist = 0;
   int* d_ratio_lim = nullptr;  // [kDotClamp + 1]
-  std::vector<float> a;
+  HostThresholds host;
 
   int build(float ratio, float dist, cudaStream_t s) {
     if (ratio == max_ratio && dist == max_distance && d_ratio_lim) return B2_OK;
-    const float kDistNorm = 1.0f / (512.0f * 512.0f);
-    if (a.empty()) {
-      a.resize(kDotClamp + 1);
-      for (int v = 0; v <= kDotClamp; ++v) a[v] = std::acos(std::min(kDistNorm * (float)v, 1.0f));
-      for (int v = 1; v <= kDotClamp; ++v)
-        if (a[v] > a[v - 1]) return set_error(B2_ERR_INTERNAL, "host acosf is not monotone");
-    }
-    int td = kDotClamp + 1;
-    for (int v = 1; v <= kDotClamp; ++v)
-      if (!(a[v] > dist)) { td = v; break; }
-    std::vector<int> lim(kDotClamp + 1, -1);
-    for (int b = std::max(td, 1); b <= kDotClamp; ++b) {
-      // largest s in [0, b] with NOT (a[b] >= ratio * a[s]); pass(s) is monotone (true first)
-      int lo = -1, hi = b;  // invariant: pass(lo) (or lo == -1), search in (lo, hi]
-      while (lo < hi) {
-        const int mid = lo + (hi - lo + 1) / 2;
-        const bool pass = !(a[b] >= ratio * a[mid]);
-        if (pass) lo = mid; else hi = mid - 1;
-      }
-      lim[b] = lo;
-    }
+    if (!host.build(ratio, dist, kDotClamp)) return set_error(B2_ERR_INTERNAL, "host acosf is not monotone");
     if (!d_ratio_lim) B2_CUDA(cudaMalloc(&d_ratio_lim, (kDotClamp + 1) * sizeof(int)));
-    B2_CUDA(cudaMemcpyAsync(d_ratio_lim, lim.data(), lim.size() * sizeof(int), cudaMemcpyHostToDevice, s));
-    B2_CUDA(cudaStreamSynchronize(s));  // lim is a stack-lifetime host buffer
-    thr_dist = td;
+    B2_CUDA(cudaMemcpyAsync(d_ratio_lim, host.ratio_lim.data(), host.ratio_lim.size() * sizeof(int),
+                            cudaMemcpyHostToDevice, s));
+    B2_CUDA(cudaStreamSynchronize(s));
+    thr_dist = host.thr_dist;
     max_ratio = ratio;
     max_distance = dist;
     return B2_OK;
@@ -216,6 +201,8 @@ struct b2_matcher {
   PairMeta* d_meta = nullptr;        // [cap_pairs]
   uint32_t* d_counts = nullptr;      // [cap_pairs]
   MatchItem* d_items = nullptr;      // [row_budget/256]
+  uint32_t* d_item_pair = nullptr;   // [row_budget/256] (pair << 1 | direction), guided matching
+  GuidedGeom* d_geoms = nullptr; int64_t d_geoms_cap = 0;
   int* d_midx = nullptr;             // [row_budget]
   uint4* d_cands = nullptr;          // [row_budget]
   unsigned int* d_cand_count = nullptr;
@@ -242,7 +229,8 @@ static int ensure_scratch(b2_matcher* m, uint32_t max_n) {
     return B2_OK;
   }
   auto fr = [](void* p) { if (p) cudaFree(p); };
-  fr(m->d_nitems); fr(m->d_item_start); fr(m->d_meta); fr(m->d_counts); fr(m->d_items);
+  fr(m->d_nitems); fr(m->d_item_start); fr(m->d_meta); fr(m->d_counts); fr(m->d_items); fr(m->d_item_pair);
+  m->d_item_pair = nullptr;
   fr(m->d_midx); fr(m->d_cands);
   m->d_nitems = m->d_item_start = m->d_counts = nullptr;
   m->d_meta = nullptr; m->d_items = nullptr; m->d_midx = nullptr; m->d_cands = nullptr;
@@ -251,6 +239,7 @@ static int ensure_scratch(b2_matcher* m, uint32_t max_n) {
   B2_CUDA(cudaMalloc(&m->d_meta, cap_pairs * sizeof(PairMeta)));
   B2_CUDA(cudaMalloc(&m->d_counts, cap_pairs * sizeof(uint32_t)));
   B2_CUDA(cudaMalloc(&m->d_items, (budget / kSuperRows + 1) * sizeof(MatchItem)));
+  B2_CUDA(cudaMalloc(&m->d_item_pair, (budget / kSuperRows + 1) * sizeof(uint32_t)));
   B2_CUDA(cudaMalloc(&m->d_midx, budget * sizeof(int)));
   B2_CUDA(cudaMalloc(&m->d_cands, budget * sizeof(uint4)));
   m->row_budget = budget;
@@ -360,6 +349,67 @@ static int run_pairs_device(b2_matcher* m, ImageStore& st, int64_t n_pairs,
   return B2_OK;
 }
 
+// Guided variant of the pipeline: the tensor-core kernel + fix-up are replaced by the thread-per-row
+// guided kernel (match_guided.cu); items, cross-check and compaction are shared.
+static int run_guided_device(b2_matcher* m, ImageStore& st, int64_t n_pairs, const uint32_t* pairs_dev,
+                             const GuidedGeom* geoms_dev, double max_error, const b2_match_options* opt,
+                             int64_t* out_offsets_dev, uint32_t* out_matches_dev, int64_t capacity,
+                             int64_t* n_total) {
+  if (!opt) return set_error(B2_ERR_INVALID, "options == NULL");
+  if (!(opt->max_ratio > 0) || !(opt->max_distance > 0) || opt->max_num_matches <= 0 || !(max_error > 0))
+    return set_error(B2_ERR_INVALID, "SiftMatchingOptions::Check failed");
+  if (n_pairs < 0 || capacity < 0) return set_error(B2_ERR_INVALID, "negative size");
+  if (!st.kp_pool) return set_error(B2_ERR_INVALID, "guided matching needs b2_match_set_keypoints first");
+  B2_CUDA(cudaSetDevice(m->device));
+  cudaStream_t s = m->stream;
+  B2_TRY(m->tables.build(opt->max_ratio, opt->max_distance, s));
+  B2_TRY(ensure_scratch(m, st.max_n));
+  B2_CUDA(cudaMemsetAsync(m->d_carry, 0, sizeof(int64_t), s));
+  B2_CUDA(cudaMemsetAsync(m->d_err, 0, sizeof(int), s));
+  B2_CUDA(cudaMemsetAsync(out_offsets_dev, 0, sizeof(int64_t), s));
+  const float max_residual = (float)(max_error * max_error);  // sift.cc:833
+  const int64_t n_chunks = (n_pairs + m->cap_pairs - 1) / std::max<int64_t>(m->cap_pairs, 1);
+  while ((int64_t)m->ev.size() < 2) {
+    cudaEvent_t e;
+    B2_CUDA(cudaEventCreate(&e));
+    m->ev.push_back(e);
+  }
+  B2_CUDA(cudaEventRecord(m->ev[0], s));
+  for (int64_t c = 0; c < n_chunks; ++c) {
+    const int64_t p0 = c * m->cap_pairs, np = std::min(m->cap_pairs, n_pairs - p0);
+    const uint32_t* pr = pairs_dev + 2 * p0;
+    B2_CUDA(launch_pair_items(pr, np, st.d_img_n, st.n_images, m->d_nitems, m->d_err, s));
+    B2_CUDA(launch_scan_u32(m->d_nitems, np, m->d_item_start, m->d_total_items, s));
+    B2_CUDA(launch_fill_items(pr, np, st.d_img_n, st.d_img_row, m->d_item_start, m->d_items, m->d_meta,
+                              (uint32_t)kTileRows, s));
+    B2_CUDA(launch_guided_item_pairs(m->d_meta, np, m->d_item_pair, s));
+    B2_CUDA(launch_guided_match(st.pool, st.kp_pool, m->d_items, m->d_item_pair, m->d_total_items, m->d_meta,
+                                geoms_dev + p0, max_residual, m->tables.thr_dist, m->tables.d_ratio_lim, m->d_midx,
+                                m->n_sm, s));
+    B2_CUDA(launch_cross_count(m->d_meta, np, m->d_midx, opt->cross_check, m->d_counts, s));
+    B2_CUDA(launch_scan_counts(m->d_counts, np, out_offsets_dev + p0, m->d_carry, true, s));
+    B2_CUDA(launch_cross_write(m->d_meta, np, m->d_midx, opt->cross_check, out_offsets_dev + p0,
+                               out_matches_dev, capacity, s));
+    count_launches(np > 0 ? 8 : 3);
+  }
+  B2_CUDA(cudaEventRecord(m->ev[1], s));
+  int64_t total = 0;
+  int err = 0;
+  B2_CUDA(cudaMemcpyAsync(&total, m->d_carry, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  B2_CUDA(cudaMemcpyAsync(&err, m->d_err, sizeof(int), cudaMemcpyDeviceToHost, s));
+  B2_CUDA(cudaStreamSynchronize(s));
+  float ms = 0;
+  B2_CUDA(cudaEventElapsedTime(&ms, m->ev[0], m->ev[1]));
+  m->last_all_s = ms * 1e-3;
+  m->last_tc_s = 0;
+  m->last_tc_launches = 0;
+  m->last_cands = 0;
+  if (n_total) *n_total = total;
+  if (err == 1) return set_error(B2_ERR_INVALID, "pair references an image outside the store");
+  if (total > capacity) return set_error(B2_ERR_CAPACITY, "out_matches capacity too small");
+  return B2_OK;
+}
+
 extern "C" {
 
 void b2_match_default_options(b2_match_options* opt) {
@@ -406,7 +456,7 @@ int b2_match_destroy(b2_matcher* m) {
   fr(m->tables.d_ratio_lim);
   fr(m->d_nitems); fr(m->d_item_start); fr(m->d_total_items); fr(m->d_meta); fr(m->d_counts);
   fr(m->d_items); fr(m->d_midx); fr(m->d_cands); fr(m->d_cand_count); fr(m->d_carry); fr(m->d_err);
-  fr(m->d_pairs); fr(m->d_offsets); fr(m->d_matches);
+  fr(m->d_pairs); fr(m->d_offsets); fr(m->d_matches); fr(m->d_item_pair); fr(m->d_geoms);
   for (auto e : m->ev) cudaEventDestroy(e);
   cudaStreamDestroy(m->stream);
   delete m;
@@ -492,6 +542,56 @@ int b2_match_pairs(b2_matcher* m, int64_t n_pairs, const uint32_t* pairs, const 
   if (!m || !out_offsets || (n_pairs > 0 && !pairs) || (capacity > 0 && !out_matches))
     return set_error(B2_ERR_INVALID, "NULL argument");
   return run_pairs_host(m, m->store, n_pairs, pairs, opt, out_offsets, out_matches, capacity, n_total);
+}
+
+int b2_match_set_keypoints(b2_matcher* m, int32_t n_images, const float* const* xy, const int32_t* n_keypoints) {
+  if (!m || (n_images > 0 && (!xy || !n_keypoints))) return set_error(B2_ERR_INVALID, "NULL argument");
+  ImageStore& st = m->store;
+  if (n_images != st.n_images || !st.pool) return set_error(B2_ERR_INVALID, "keypoints must follow b2_match_set_images of the same images");
+  for (int32_t i = 0; i < n_images; ++i)
+    if (n_keypoints[i] != st.h_img_n[i])  // sift.cc:82-87 CHECK_EQ(keypoints->size(), descriptors.rows())
+      return set_error(B2_ERR_INVALID, "keypoint count differs from descriptor count");
+  B2_CUDA(cudaSetDevice(m->device));
+  if (!st.kp_pool) B2_CUDA(cudaMalloc(&st.kp_pool, st.pool_rows * 2 * sizeof(float)));
+  B2_CUDA(cudaMemsetAsync(st.kp_pool, 0, st.pool_rows * 2 * sizeof(float), m->stream));
+  for (int32_t i = 0; i < n_images; ++i) {
+    if (n_keypoints[i] == 0) continue;
+    if (!xy[i]) return set_error(B2_ERR_INVALID, "NULL keypoint pointer");
+    B2_CUDA(cudaMemcpyAsync(st.kp_pool + 2 * (size_t)st.h_img_row[i], xy[i], (size_t)n_keypoints[i] * 2 * sizeof(float),
+                            cudaMemcpyHostToDevice, m->stream));
+  }
+  B2_CUDA(cudaStreamSynchronize(m->stream));
+  return B2_OK;
+}
+
+int b2_match_guided_pairs(b2_matcher* m, int64_t n_pairs, const uint32_t* pairs, const b2_guided_geometry* geoms,
+                          double max_error, const b2_match_options* opt, int64_t* out_offsets,
+                          uint32_t* out_matches, int64_t capacity, int64_t* n_total) {
+  if (!m || !out_offsets || (n_pairs > 0 && (!pairs || !geoms)) || (capacity > 0 && !out_matches))
+    return set_error(B2_ERR_INVALID, "NULL argument");
+  if (n_pairs < 0 || capacity < 0) return set_error(B2_ERR_INVALID, "negative size");
+  B2_CUDA(cudaSetDevice(m->device));
+  B2_TRY(grow((void**)&m->d_pairs, &m->d_pairs_cap, n_pairs, 2 * sizeof(uint32_t)));
+  B2_TRY(grow((void**)&m->d_offsets, &m->d_offsets_cap, n_pairs + 1, sizeof(int64_t)));
+  B2_TRY(grow((void**)&m->d_matches, &m->d_matches_cap, capacity, 2 * sizeof(uint32_t)));
+  B2_TRY(grow((void**)&m->d_geoms, &m->d_geoms_cap, n_pairs, sizeof(GuidedGeom)));
+  std::vector<GuidedGeom> hg((size_t)n_pairs);
+  for (int64_t p = 0; p < n_pairs; ++p) hg[p] = make_guided_geom(geoms[p].config, geoms[p].F, geoms[p].H);
+  if (n_pairs > 0) {
+    B2_CUDA(cudaMemcpyAsync(m->d_pairs, pairs, n_pairs * 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, m->stream));
+    B2_CUDA(cudaMemcpyAsync(m->d_geoms, hg.data(), n_pairs * sizeof(GuidedGeom), cudaMemcpyHostToDevice, m->stream));
+    B2_CUDA(cudaStreamSynchronize(m->stream));  // hg is a stack-lifetime host buffer
+  }
+  int64_t total = 0;
+  const int rc = run_guided_device(m, m->store, n_pairs, m->d_pairs, m->d_geoms, max_error, opt, m->d_offsets,
+                                   m->d_matches, capacity, &total);
+  if (n_total) *n_total = total;
+  if (rc != B2_OK) return rc;
+  B2_CUDA(cudaMemcpyAsync(out_offsets, m->d_offsets, (n_pairs + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, m->stream));
+  if (total > 0)
+    B2_CUDA(cudaMemcpyAsync(out_matches, m->d_matches, total * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, m->stream));
+  B2_CUDA(cudaStreamSynchronize(m->stream));
+  return B2_OK;
 }
 
 int b2_match_set_descriptors(b2_matcher* m, int slot, int32_t n, const uint8_t* desc) {

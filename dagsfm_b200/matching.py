@@ -22,13 +22,18 @@ class SiftMatchingOptions:
     max_distance: float = 0.7
     cross_check: bool = True
     max_num_matches: int = 32768
+    max_error: float = 4.0          # guided matching only (sift.h:143)
 
     def check(self) -> bool:  # SiftMatchingOptions::Check, sift.cc:236-250
-        return self.max_ratio > 0 and self.max_distance > 0 and self.max_num_matches > 0
+        return self.max_ratio > 0 and self.max_distance > 0 and self.max_num_matches > 0 and self.max_error > 0
 
     def to_c(self) -> MatchOptions:
         return MatchOptions(np.float32(self.max_ratio), np.float32(self.max_distance),
                             1 if self.cross_check else 0, int(self.max_num_matches))
+
+
+# b2_guided_geometry
+GUIDED_GEOMETRY_DTYPE = np.dtype([("config", "<i4"), ("reserved", "<i4"), ("F", "<f8", (9,)), ("H", "<f8", (9,))])
 
 
 def _as_desc(d) -> np.ndarray:
@@ -111,6 +116,38 @@ class SiftMatchGPU:
                                    matches.ctypes.data_as(C.c_void_p), capacity, C.byref(total)))
         return offsets, matches[: total.value]
 
+    # ---- guided matching (MatchGuidedSiftFeaturesGPU, sift.cc:987-1066) ----
+    def set_keypoints(self, keypoints_xy: list) -> None:
+        """(x, y) of every keypoint of the images of the last set_images call."""
+        ks = [np.ascontiguousarray(k, dtype=np.float32).reshape(-1, 2) for k in keypoints_xy]
+        n = len(ks)
+        ptrs = (C.c_void_p * max(n, 1))(*[k.ctypes.data for k in ks])
+        cnt = (C.c_int32 * max(n, 1))(*[k.shape[0] for k in ks])
+        check(lib().b2_match_set_keypoints(self._h, n, ptrs, cnt))
+
+    def match_guided_pairs(self, pairs, geometries, options: SiftMatchingOptions, capacity: int | None = None):
+        """geometries: per pair (config, F 3x3 or None, H 3x3 or None), TwoViewGeometry fields.
+        Returns (offsets int64[n+1], matches uint32[total,2]); a pair whose config has no guided
+        filter gets no matches (the reference leaves inlier_matches untouched there)."""
+        pr = np.ascontiguousarray(pairs, dtype=np.uint32).reshape(-1, 2)
+        n = pr.shape[0]
+        assert len(geometries) == n
+        geo = np.zeros(n, dtype=GUIDED_GEOMETRY_DTYPE)
+        for k, (cfg, F, H) in enumerate(geometries):
+            geo["config"][k] = int(cfg)
+            geo["F"][k] = np.zeros(9) if F is None else np.asarray(F, dtype=np.float64).reshape(9)
+            geo["H"][k] = np.zeros(9) if H is None else np.asarray(H, dtype=np.float64).reshape(9)
+        if capacity is None:
+            capacity = n * min(self._max_n, options.max_num_matches)
+        opt = options.to_c()
+        offsets = np.zeros(n + 1, dtype=np.int64)
+        matches = np.empty((max(capacity, 1), 2), dtype=np.uint32)
+        total = C.c_int64(0)
+        check(lib().b2_match_guided_pairs(self._h, n, pr.ctypes.data_as(C.c_void_p), geo.ctypes.data_as(C.c_void_p),
+                                          float(options.max_error), C.byref(opt), offsets.ctypes.data_as(C.c_void_p),
+                                          matches.ctypes.data_as(C.c_void_p), capacity, C.byref(total)))
+        return offsets, matches[: total.value]
+
     def match_pairs_device(self, n_pairs: int, pairs_dev_ptr: int, options: SiftMatchingOptions,
                            offsets_dev_ptr: int, matches_dev_ptr: int, capacity: int) -> int:
         opt = options.to_c()
@@ -126,6 +163,23 @@ class SiftMatchGPU:
         check(lib().b2_match_last_timing(self._h, C.byref(tc), C.byref(al), C.byref(nl), C.byref(nc)))
         return {"tc_kernel_s": tc.value, "all_kernels_s": al.value, "tc_launches": nl.value,
                 "fixup_candidates": nc.value}
+
+
+def match_guided_sift_features_gpu(options: SiftMatchingOptions, keypoints1, keypoints2, descriptors1, descriptors2,
+                                   sift_match_gpu: SiftMatchGPU, config: int, F=None, H=None):
+    """MatchGuidedSiftFeaturesGPU (sift.cc:987-1066) for one pair: returns the new inlier_matches
+    (uint32 [n,2]) or None when `config` has no guided filter (inlier_matches stay as they were)."""
+    assert options.check()
+    if int(config) not in (2, 3, 4, 5, 6):
+        return None
+    d1 = _as_desc(descriptors1)[: options.max_num_matches]
+    d2 = _as_desc(descriptors2)[: options.max_num_matches]
+    k1 = np.asarray(keypoints1, dtype=np.float32).reshape(-1, 2)[: options.max_num_matches]
+    k2 = np.asarray(keypoints2, dtype=np.float32).reshape(-1, 2)[: options.max_num_matches]
+    sift_match_gpu.set_images([d1, d2])
+    sift_match_gpu.set_keypoints([k1, k2])
+    _, m = sift_match_gpu.match_guided_pairs([(0, 1)], [(config, F, H)], options)
+    return m.copy()
 
 
 def match_sift_features_gpu(options: SiftMatchingOptions, descriptors1, descriptors2,

@@ -119,6 +119,32 @@ int b2_match_run(b2_matcher* m, const b2_match_options* opt,
 int b2_match_last_timing(b2_matcher* m, double* tc_kernel_s, double* all_kernels_s,
                          int64_t* tc_launches, int64_t* fixup_candidates);
 
+/* -- guided matching ----------------------------------------------------------
+ * Replaces: MatchGuidedSiftFeaturesGPU / MatchGuidedSiftFeaturesCPU (src/feature/sift.h:241-253,
+ * sift.cc:824-875, :987-1066) as called by SiftGPUFeatureMatcher / GuidedSiftGPUFeatureMatcher
+ * for a verified pair (src/feature/matching.cc:429-477, :683-742): descriptor matching restricted
+ * to keypoint pairs whose float32 residual under the pair's geometry is <= max_error^2
+ * (Sampson error w.r.t. F for CALIBRATED / UNCALIBRATED, transfer error w.r.t. H for PLANAR /
+ * PANORAMIC / PLANAR_OR_PANORAMIC); everything else as in b2_match_pairs.
+ * A pair whose `config` has no guided filter yields no matches (the reference returns without
+ * touching two_view_geometry->inlier_matches, sift.cc:866-868: the caller keeps what it had). */
+typedef struct b2_guided_geometry {
+  int32_t config;   /* TwoViewGeometry::ConfigurationType (two_view_geometry.h:48-58) */
+  int32_t reserved;
+  double F[9];      /* row-major, TwoViewGeometry::F */
+  double H[9];      /* row-major, TwoViewGeometry::H */
+} b2_guided_geometry;
+
+/* Keypoint locations (FeatureKeypoint::x, ::y, src/feature/types.h:44-45) of the images of the
+ * last b2_match_set_images* call: xy[i] -> n_keypoints[i] (x, y) float pairs, which must equal
+ * that image's descriptor count (sift.cc:82-87). */
+int b2_match_set_keypoints(b2_matcher* m, int32_t n_images, const float* const* xy,
+                           const int32_t* n_keypoints);
+/* geoms[p] belongs to pairs[p]; `max_error` = SiftMatchingOptions::max_error (pixels, default 4). */
+int b2_match_guided_pairs(b2_matcher* m, int64_t n_pairs, const uint32_t* pairs,
+                          const b2_guided_geometry* geoms, double max_error, const b2_match_options* opt,
+                          int64_t* out_offsets, uint32_t* out_matches, int64_t capacity, int64_t* n_total);
+
 
 /* ================================================================= VERIFY ==
  * Replaces: TwoViewGeometry::Estimate (src/estimators/two_view_geometry.h:180-184,

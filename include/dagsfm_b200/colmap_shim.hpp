@@ -37,7 +37,8 @@ struct SiftMatchingOptions {  // src/feature/sift.h:116-165 (fields the matcher 
   double max_distance = 0.7;
   bool cross_check = true;
   int max_num_matches = 32768;
-  bool Check() const { return max_ratio > 0 && max_distance > 0 && max_num_matches > 0; }
+  double max_error = 4.0;  // guided matching
+  bool Check() const { return max_ratio > 0 && max_distance > 0 && max_num_matches > 0 && max_error > 0; }
 };
 
 // The slice of SiftMatchGPU that colmap's sift.cc drives.
@@ -84,6 +85,12 @@ class SiftMatchGPU {
     if (b2_match_run(h_, &o, &match_buffer[0][0], &n) != B2_OK) return -1;
     return n;
   }
+
+  // Guided matching keeps host copies of the two slots: a NULL descriptor / keypoint pointer of
+  // MatchGuidedSiftFeaturesGPU means "same image as the previous call" (sift.cc:1009-1035).
+  b2_matcher* handle() const { return h_; }
+  std::vector<unsigned char> guided_desc[2];
+  std::vector<float> guided_xy[2];
 
  private:
   b2_matcher* h_ = nullptr;
@@ -135,6 +142,71 @@ void MatchSiftFeaturesGPU(const SiftMatchingOptions& match_options, const Descri
     matches->clear();
   } else {
     matches->resize(num_matches);
+  }
+}
+
+// sift.cc:987-1066.  Keypoints: any container of structs with float members x, y (FeatureKeypoint);
+// Geometry: any struct with `config`, `F`, `H` (3x3, indexable as M(r, c)) and `inlier_matches`
+// (TwoViewGeometry, two_view_geometry.h:43-113).  Configurations without a guided filter leave
+// inlier_matches untouched, as the reference does (:1049-1051).
+template <class Keypoints, class Descriptors, class Geometry>
+void MatchGuidedSiftFeaturesGPU(const SiftMatchingOptions& match_options, const Keypoints* keypoints1,
+                                const Keypoints* keypoints2, const Descriptors* descriptors1,
+                                const Descriptors* descriptors2, SiftMatchGPU* sift_match_gpu,
+                                Geometry* two_view_geometry) {
+  auto stage = [&](int slot, const Keypoints* kp, const Descriptors* d) {
+    if (d == nullptr) return;
+    const size_t n = std::min<size_t>((size_t)d->rows(), (size_t)sift_match_gpu->GetMaxSift());
+    sift_match_gpu->guided_desc[slot].assign(d->data(), d->data() + n * 128);
+    sift_match_gpu->guided_xy[slot].resize(2 * n);
+    for (size_t i = 0; i < n; ++i) {
+      sift_match_gpu->guided_xy[slot][2 * i] = (*kp)[i].x;
+      sift_match_gpu->guided_xy[slot][2 * i + 1] = (*kp)[i].y;
+    }
+  };
+  stage(0, keypoints1, descriptors1);
+  stage(1, keypoints2, descriptors2);
+  const int cfg = (int)two_view_geometry->config;
+  if (!(cfg == 2 || cfg == 3 || cfg == 4 || cfg == 5 || cfg == 6)) return;
+  b2_guided_geometry g;
+  g.config = cfg;
+  g.reserved = 0;
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) {
+      g.F[3 * r + c] = two_view_geometry->F(r, c);
+      g.H[3 * r + c] = two_view_geometry->H(r, c);
+    }
+  static const unsigned char kEmptyDesc = 0;
+  static const float kEmptyXy = 0;
+  const unsigned char* dp[2];
+  const float* kp[2];
+  int32_t cnt[2];
+  for (int k = 0; k < 2; ++k) {
+    cnt[k] = (int32_t)(sift_match_gpu->guided_desc[k].size() / 128);
+    dp[k] = cnt[k] ? sift_match_gpu->guided_desc[k].data() : &kEmptyDesc;
+    kp[k] = cnt[k] ? sift_match_gpu->guided_xy[k].data() : &kEmptyXy;
+  }
+  b2_match_options o;
+  o.max_ratio = (float)match_options.max_ratio;
+  o.max_distance = (float)match_options.max_distance;
+  o.cross_check = match_options.cross_check;
+  o.max_num_matches = match_options.max_num_matches;
+  const uint32_t pair[2] = {0, 1};
+  int64_t offsets[2] = {0, 0}, total = 0;
+  const int64_t cap = std::min(cnt[0], cnt[1]) > 0 ? (int64_t)cnt[0] : 0;
+  two_view_geometry->inlier_matches.resize((size_t)std::max<int64_t>(cap, 1));
+  b2_matcher* h = sift_match_gpu->handle();
+  const bool ok = h != nullptr && b2_match_set_images(h, 2, dp, cnt) == B2_OK &&
+                  b2_match_set_keypoints(h, 2, kp, cnt) == B2_OK &&
+                  b2_match_guided_pairs(h, 1, pair, &g, match_options.max_error, &o, offsets,
+                                        reinterpret_cast<uint32_t*>(two_view_geometry->inlier_matches.data()), cap,
+                                        &total) == B2_OK;
+  if (!ok) {
+    std::fprintf(stderr, "ERROR: Feature matching failed. This is probably caused by insufficient GPU memory. "
+                         "Consider reducing the maximum number of features and/or matches.\n");
+    two_view_geometry->inlier_matches.clear();
+  } else {
+    two_view_geometry->inlier_matches.resize((size_t)total);
   }
 }
 

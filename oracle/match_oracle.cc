@@ -7,6 +7,7 @@
 //   src/feature/sift.cc:111-162  FindBestMatchesOneWay
 //   src/feature/sift.cc:164-198  FindBestMatches
 //   src/feature/sift.cc:810-822  MatchSiftFeaturesCPU
+//   src/feature/sift.cc:824-875  MatchGuidedSiftFeaturesCPU (+ the guided_filter branch of :96-103)
 //   src/feature/utils.cc:47-76   L2NormalizeFeatureDescriptors / FeatureDescriptorsToUnsignedByte
 //   src/feature/sift_test.cc:243-253 CreateRandomFeatureDescriptors (the test fixture)
 //   src/util/random.{h,cc}       SetPRNGSeed / RandomReal (std::mt19937 +
@@ -81,11 +82,22 @@ size_t FindBestMatchesOneWay(const int* dists, int rows, int cols, const float m
 }
 
 // sift.cc:164-198 + 810-822.
+void FindBestMatches(const std::vector<int>& dists, int n1, int n2, float max_ratio, float max_distance,
+                     int cross_check, std::vector<uint32_t>* out);
+
 int MatchSiftFeaturesCPU(const uint8_t* d1, int n1, const uint8_t* d2, int n2, float max_ratio,
                          float max_distance, int cross_check, std::vector<uint32_t>* out) {
   out->clear();
   std::vector<int> dists;
   ComputeSiftDistanceMatrix(d1, n1, d2, n2, &dists);
+  FindBestMatches(dists, n1, n2, max_ratio, max_distance, cross_check, out);
+  return (int)(out->size() / 2);
+}
+
+// sift.cc:164-198 FindBestMatches on a row-major n1 x n2 matrix.
+void FindBestMatches(const std::vector<int>& dists, int n1, int n2, float max_ratio, float max_distance,
+                     int cross_check, std::vector<uint32_t>* out) {
+  out->clear();
   std::vector<int> m12;
   FindBestMatchesOneWay(dists.data(), n1, n2, max_ratio, max_distance, &m12);
   if (cross_check) {
@@ -109,6 +121,56 @@ int MatchSiftFeaturesCPU(const uint8_t* d1, int n1, const uint8_t* d2, int n2, f
       }
     }
   }
+}
+
+// sift.cc:824-875 MatchGuidedSiftFeaturesCPU with the guided_filter branch of
+// ComputeSiftDistanceMatrix (:96-103): dists(i1, i2) = 0 where the float32 geometric residual of
+// (keypoint1[i1], keypoint2[i2]) exceeds max_error^2, else the descriptor dot.  config follows
+// TwoViewGeometry::ConfigurationType: 2/3 (CALIBRATED/UNCALIBRATED) -> Sampson error w.r.t. F,
+// 4/5/6 (PLANAR/PANORAMIC/PLANAR_OR_PANORAMIC) -> transfer error w.r.t. H, anything else: the
+// reference returns without touching inlier_matches (here: returns -1, output empty).
+// The filter is evaluated in float32 like the reference's Eigen::Matrix3f expressions, sums
+// left to right, no FMA contraction (the reference's own rounding depends on how Eigen was
+// compiled, so parity of a residual within one ulp of the threshold is unpinned).
+int MatchGuidedSiftFeaturesCPU(const float* kp1 /*[n1][2]*/, const float* kp2, const uint8_t* d1, int n1,
+                               const uint8_t* d2, int n2, int config, const double* F_rm, const double* H_rm,
+                               double max_error, float max_ratio, float max_distance, int cross_check,
+                               std::vector<uint32_t>* out) {
+  out->clear();
+  const float max_residual = (float)(max_error * max_error);
+  float F[9], H[9];
+  for (int k = 0; k < 9; ++k) {
+    F[k] = (float)F_rm[k];
+    H[k] = (float)H_rm[k];
+  }
+  const bool use_f = (config == 2 || config == 3), use_h = (config == 4 || config == 5 || config == 6);
+  if (!use_f && !use_h) return -1;
+  std::vector<int> dists;
+  ComputeSiftDistanceMatrix(d1, n1, d2, n2, &dists);
+  for (int i1 = 0; i1 < n1; ++i1) {
+    const float x1 = kp1[2 * i1], y1 = kp1[2 * i1 + 1];
+    for (int i2 = 0; i2 < n2; ++i2) {
+      const float x2 = kp2[2 * i2], y2 = kp2[2 * i2 + 1];
+      bool skip;
+      if (use_f) {
+        const float Fx1_0 = F[0] * x1 + F[1] * y1 + F[2] * 1.0f;
+        const float Fx1_1 = F[3] * x1 + F[4] * y1 + F[5] * 1.0f;
+        const float Fx1_2 = F[6] * x1 + F[7] * y1 + F[8] * 1.0f;
+        const float Ftx2_0 = F[0] * x2 + F[3] * y2 + F[6] * 1.0f;
+        const float Ftx2_1 = F[1] * x2 + F[4] * y2 + F[7] * 1.0f;
+        const float x2tFx1 = x2 * Fx1_0 + y2 * Fx1_1 + 1.0f * Fx1_2;
+        skip = x2tFx1 * x2tFx1 / (Fx1_0 * Fx1_0 + Fx1_1 * Fx1_1 + Ftx2_0 * Ftx2_0 + Ftx2_1 * Ftx2_1) > max_residual;
+      } else {
+        const float h0 = H[0] * x1 + H[1] * y1 + H[2] * 1.0f;
+        const float h1 = H[3] * x1 + H[4] * y1 + H[5] * 1.0f;
+        const float h2 = H[6] * x1 + H[7] * y1 + H[8] * 1.0f;
+        const float e0 = h0 / h2 - x2, e1 = h1 / h2 - y2;
+        skip = e0 * e0 + e1 * e1 > max_residual;
+      }
+      if (skip) dists[(size_t)i1 * n2 + i2] = 0;
+    }
+  }
+  FindBestMatches(dists, n1, n2, max_ratio, max_distance, cross_check, out);
   return (int)(out->size() / 2);
 }
 
@@ -122,6 +184,20 @@ int orc_match_sift(const uint8_t* d1, int n1, const uint8_t* d2, int n2, float m
   std::vector<uint32_t> m;
   const int n = MatchSiftFeaturesCPU(d1, n1, d2, n2, max_ratio, max_distance, cross_check, &m);
   if (n > cap) return -n;
+  if (n > 0) memcpy(out, m.data(), (size_t)n * 2 * sizeof(uint32_t));
+  return n;
+}
+
+// MatchGuidedSiftFeaturesCPU.  Returns #matches, -1 when the configuration has no guided filter,
+// INT_MIN + needed if cap is too small.
+int orc_match_guided(const float* kp1, const float* kp2, const uint8_t* d1, int n1, const uint8_t* d2, int n2,
+                     int config, const double* F, const double* H, double max_error, float max_ratio,
+                     float max_distance, int cross_check, uint32_t* out, int cap) {
+  std::vector<uint32_t> m;
+  const int n = MatchGuidedSiftFeaturesCPU(kp1, kp2, d1, n1, d2, n2, config, F, H, max_error, max_ratio,
+                                           max_distance, cross_check, &m);
+  if (n < 0) return -1;
+  if (n > cap) return -2147483647 + n;
   if (n > 0) memcpy(out, m.data(), (size_t)n * 2 * sizeof(uint32_t));
   return n;
 }

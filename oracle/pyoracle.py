@@ -53,6 +53,8 @@ def lib() -> C.CDLL:
         L = C.CDLL(str(LIB_PATH))
         vp = C.c_void_p
         L.orc_match_sift.argtypes = [vp, C.c_int, vp, C.c_int, C.c_float, C.c_float, C.c_int, vp, C.c_int]
+        L.orc_match_guided.argtypes = [vp, vp, vp, C.c_int, vp, C.c_int, C.c_int, vp, vp, C.c_double, C.c_float,
+                                       C.c_float, C.c_int, vp, C.c_int]
         L.orc_best_one_way.argtypes = [vp, C.c_int, vp, C.c_int, C.c_float, C.c_float, vp]
         L.orc_best_one_way.restype = None
         L.orc_create_random_descriptors.argtypes = [C.c_int, C.c_uint, vp]
@@ -78,6 +80,27 @@ def match_sift(d1, d2, max_ratio=0.8, max_distance=0.7, cross_check=True) -> np.
     n = lib().orc_match_sift(d1.ctypes.data, d1.shape[0], d2.ctypes.data, d2.shape[0],
                              np.float32(max_ratio), np.float32(max_distance), int(cross_check),
                              out.ctypes.data, cap)
+    assert n >= 0
+    return out[:n].copy()
+
+
+def match_guided(kp1, kp2, d1, d2, config, F=None, H=None, max_error=4.0, max_ratio=0.8, max_distance=0.7,
+                 cross_check=True):
+    """MatchGuidedSiftFeaturesCPU (sift.cc:824-875) -> uint32 [n,2], or None when `config` has no
+    guided filter (the reference then leaves inlier_matches untouched)."""
+    d1, d2 = _d(d1), _d(d2)
+    k1 = np.ascontiguousarray(kp1, dtype=np.float32).reshape(-1, 2)
+    k2 = np.ascontiguousarray(kp2, dtype=np.float32).reshape(-1, 2)
+    assert len(k1) == len(d1) and len(k2) == len(d2)
+    Fm = np.ascontiguousarray(np.eye(3) if F is None else F, dtype=np.float64).reshape(9)
+    Hm = np.ascontiguousarray(np.eye(3) if H is None else H, dtype=np.float64).reshape(9)
+    cap = max(1, min(d1.shape[0], d2.shape[0]) if cross_check else d1.shape[0])
+    out = np.empty((cap, 2), dtype=np.uint32)
+    n = lib().orc_match_guided(k1.ctypes.data, k2.ctypes.data, d1.ctypes.data, d1.shape[0], d2.ctypes.data,
+                               d2.shape[0], int(config), Fm.ctypes.data, Hm.ctypes.data, float(max_error),
+                               np.float32(max_ratio), np.float32(max_distance), int(cross_check), out.ctypes.data, cap)
+    if n == -1:
+        return None
     assert n >= 0
     return out[:n].copy()
 

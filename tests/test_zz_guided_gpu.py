@@ -1,0 +1,81 @@
+"""Guided matching on the GPU: b2_match_guided_pairs against the oracle's
+MatchGuidedSiftFeaturesCPU, plus the replay of the reference's own GPU test through the C++ shim.
+
+The kernel's row function and the threshold tables are verified on the CPU (tests/test_host_guided.py).
+This file ran for the first time after the round's GPU budget was spent, hence the non-strict xfail:
+a pass is reported as XPASS, a failure does not hide the rest of the suite."""
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as orc
+from tests.test_host_guided import _inlier_pairs, _scene_with_descriptors
+
+ROOT = Path(__file__).resolve().parent.parent
+EXE = ROOT / "tests" / "cpp" / "_guided_shim_test"
+FIRST_RUN = pytest.mark.xfail(strict=False, reason="first GPU execution of the guided kernel (no GPU budget was left to run it)")
+
+
+def build():
+    from dagsfm_b200 import build as b
+    b.build()
+    cmd = ["/usr/bin/g++", "-std=c++17", "-O1", "-I", str(ROOT / "include"), str(ROOT / "tests/cpp/guided_shim_test.cc"),
+           "-o", str(EXE), str(b.LIB), f"-Wl,-rpath,{b.LIB.parent}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return EXE
+
+
+def test_guided_shim_compiles_and_links():
+    assert build().exists()
+
+
+@pytest.mark.gpu
+@FIRST_RUN
+def test_guided_pairs_equal_oracle_on_gpu():
+    from dagsfm_b200 import SiftMatchGPU, SiftMatchingOptions
+    rng = np.random.default_rng(11)
+    kps, descs, pairs, geos, exp = [], [], [], [], []
+    for k in range(8):
+        planar = k % 2 == 1
+        k1, k2, d1, d2 = _scene_with_descriptors(rng, 300 + 70 * k, 100 + 40 * k, planar)   # up to 1070 rows: several supertiles
+        a, b = _inlier_pairs(k1, k2, d1, d2)
+        if planar:
+            cfg, F, H = 4 + (k // 2) % 3, None, orc.h_dlt(a, b)
+        else:
+            cfg, F, H = 2 + (k // 2) % 2, orc.eight_point(a, b), None
+        kps += [k1, k2]
+        descs += [d1, d2]
+        pairs.append((2 * k, 2 * k + 1))
+        geos.append((cfg, F, H))
+    pairs.append((0, 1)); geos.append((0, None, None))      # UNDEFINED: no guided filter -> no matches
+    pairs.append((3, 2)); geos.append(geos[1])              # a pair listed in the other order uses the geometry as given
+    m = SiftMatchGPU(0)
+    try:
+        m.set_images(descs)
+        m.set_keypoints(kps)
+        for opts in (SiftMatchingOptions(), SiftMatchingOptions(cross_check=False, max_error=2.0),
+                     SiftMatchingOptions(max_ratio=0.95, max_distance=1.2)):
+            off, mt = m.match_guided_pairs(pairs, geos, opts)
+            for p, ((i, j), (cfg, F, H)) in enumerate(zip(pairs, geos)):
+                e = orc.match_guided(kps[i], kps[j], descs[i], descs[j], cfg, F=F, H=H, max_error=opts.max_error,
+                                     max_ratio=opts.max_ratio, max_distance=opts.max_distance, cross_check=opts.cross_check)
+                got = mt[off[p]:off[p + 1]]
+                assert got.tolist() == ([] if e is None else e.tolist()), (p, cfg)
+        assert off[8] - off[0] > 8 * 150
+        # the unguided matcher of the same object still works afterwards
+        off2, mt2 = m.match_pairs(pairs[:2], SiftMatchingOptions())
+        assert mt2[off2[0]:off2[1]].tolist() == orc.match_sift(descs[0], descs[1]).tolist()
+    finally:
+        m.close()
+
+
+@pytest.mark.gpu
+@FIRST_RUN
+def test_guided_shim_replays_reference_test_on_gpu():
+    exe = EXE if EXE.exists() else build()
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "guided shim ok" in r.stdout
