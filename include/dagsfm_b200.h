@@ -120,9 +120,9 @@ int b2_match_last_timing(b2_matcher* m, double* tc_kernel_s, double* all_kernels
                          int64_t* tc_launches, int64_t* fixup_candidates);
 
 /* -- guided matching ----------------------------------------------------------
- * Replaces: MatchGuidedSiftFeaturesGPU / MatchGuidedSiftFeaturesCPU (src/feature/sift.h:241-253,
+ * Replaces: MatchGuidedSiftFeaturesGPU / MatchGuidedSiftFeaturesCPU (src/feature/sift.h:240-246,
  * sift.cc:824-875, :987-1066) as called by SiftGPUFeatureMatcher / GuidedSiftGPUFeatureMatcher
- * for a verified pair (src/feature/matching.cc:429-477, :683-742): descriptor matching restricted
+ * for a verified pair (src/feature/matching.cc:438-534): descriptor matching restricted
  * to keypoint pairs whose float32 residual under the pair's geometry is <= max_error^2
  * (Sampson error w.r.t. F for CALIBRATED / UNCALIBRATED, transfer error w.r.t. H for PLANAR /
  * PANORAMIC / PLANAR_OR_PANORAMIC); everything else as in b2_match_pairs.
