@@ -13,6 +13,7 @@
 #include "../../include/dagsfm_b200.h"
 #include "common_host.h"
 #include "verify_common.cuh"
+#include "verify_multiple.h"
 
 using namespace b2;
 
@@ -284,6 +285,28 @@ int b2_verify_pairs(b2_verifier* v, int64_t n_pairs, const uint32_t* pairs, cons
   if (total > 0) B2_CUDA(cudaMemcpyAsync(inlier_matches, d_inl, total * 8, cudaMemcpyDeviceToHost, s));
   B2_CUDA(cudaStreamSynchronize(s));
   return B2_OK;
+}
+
+int b2_verify_pairs_multiple(b2_verifier* v, int64_t n_pairs, const uint32_t* pairs, const int64_t* match_offsets,
+                             const uint32_t* matches, const b2_two_view_options* opt, int32_t multiple_ignore_watermark,
+                             const uint32_t* seeds, b2_two_view_result* results, uint32_t* inlier_matches) {
+  if (!v || n_pairs < 0 || (n_pairs > 0 && (!pairs || !match_offsets || !seeds || !results)))
+    return set_error(B2_ERR_INVALID, "NULL argument");
+  if (n_pairs == 0) return check_options(opt);
+  const int64_t total = match_offsets[n_pairs];
+  if (total < 0 || (total > 0 && (!matches || !inlier_matches))) return set_error(B2_ERR_INVALID, "NULL match buffers");
+  // one round = one ordinary batched Estimate of the still-active pairs
+  auto round = [&](int64_t na, const int64_t* ids, const int64_t* off, const uint32_t* m, const uint32_t* sd,
+                   b2_two_view_result* res, uint32_t* inl) -> int {
+    std::vector<uint32_t> pr((size_t)na * 2);
+    for (int64_t k = 0; k < na; ++k) {
+      pr[2 * k] = pairs[2 * ids[k]];
+      pr[2 * k + 1] = pairs[2 * ids[k] + 1];
+    }
+    return b2_verify_pairs(v, na, pr.data(), off, m, opt, sd, res, inl);
+  };
+  return estimate_multiple(n_pairs, match_offsets, matches, seeds, multiple_ignore_watermark != 0, round, results,
+                           inlier_matches);
 }
 
 int b2_score_models(b2_verifier* v, int32_t type, int32_t n, const double* xy1, const double* xy2, int32_t n_models,

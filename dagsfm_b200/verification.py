@@ -74,6 +74,7 @@ def _L():
         L.b2_verify_set_images.argtypes = [vp, i32, vp, P(vp), P(i32)]
         L.b2_verify_pairs.argtypes = [vp, i64, vp, vp, vp, P(TwoViewOptions), vp, vp, vp]
         L.b2_verify_pairs_device.argtypes = [vp, i64, vp, vp, vp, P(TwoViewOptions), vp, vp, vp]
+        L.b2_verify_pairs_multiple.argtypes = [vp, i64, vp, vp, vp, P(TwoViewOptions), i32, vp, vp, vp]
         L.b2_score_models.argtypes = [vp, i32, i32, vp, vp, i32, vp, C.c_double, vp, vp, vp]
         L.b2_verify_debug_sample_stream.argtypes = [vp, C.c_uint32, i32, i32, i32, vp]
         L.b2_verify_debug_solve.argtypes = [vp, i32, i32, vp, vp, vp, P(i32)]
@@ -122,6 +123,24 @@ class TwoViewGeometryVerifier:
         inl = np.zeros((max(len(mt), 1), 2), dtype=np.uint32)
         check(_L().b2_verify_pairs(self._h, n, pr.ctypes.data, off.ctypes.data, mt.ctypes.data, C.byref(options),
                                    sd.ctypes.data, res.ctypes.data, inl.ctypes.data))
+        return res, inl[: len(mt)]
+
+    def verify_pairs_multiple(self, pairs, match_offsets, matches, options: TwoViewOptions | None = None, seeds=None,
+                              multiple_ignore_watermark: bool = True):
+        """TwoViewGeometry::EstimateMultiple for every pair (options.multiple_models of the reference's
+        verifier, matching.cc:595-598).  Same layout as verify_pairs; config 8 = MULTIPLE."""
+        options = options or TwoViewOptions.default()
+        pr = np.ascontiguousarray(pairs, dtype=np.uint32).reshape(-1, 2)
+        off = np.ascontiguousarray(match_offsets, dtype=np.int64)
+        mt = np.ascontiguousarray(matches, dtype=np.uint32).reshape(-1, 2)
+        n = len(pr)
+        assert len(off) == n + 1 and off[-1] == len(mt)
+        sd = np.ascontiguousarray(seeds if seeds is not None else np.arange(n), dtype=np.uint32)
+        res = np.zeros(n, dtype=RESULT_DTYPE)
+        inl = np.zeros((max(len(mt), 1), 2), dtype=np.uint32)
+        check(_L().b2_verify_pairs_multiple(self._h, n, pr.ctypes.data, off.ctypes.data, mt.ctypes.data,
+                                            C.byref(options), 1 if multiple_ignore_watermark else 0, sd.ctypes.data,
+                                            res.ctypes.data, inl.ctypes.data))
         return res, inl[: len(mt)]
 
     def verify_pairs_device(self, n_pairs, pairs_ptr, off_ptr, matches_ptr, options, seeds_ptr, results_ptr, inl_ptr):

@@ -185,7 +185,8 @@ typedef struct b2_two_view_options { /* TwoViewGeometry::Options + RANSACOptions
 
 typedef struct b2_two_view_result {  /* public fields of TwoViewGeometry (two_view_geometry.h:278-301) */
   int32_t config;                    /* ConfigurationType: 1 DEGENERATE 2 CALIBRATED 3 UNCALIBRATED
-                                        6 PLANAR_OR_PANORAMIC 7 WATERMARK */
+                                        6 PLANAR_OR_PANORAMIC 7 WATERMARK
+                                        8 MULTIPLE (b2_verify_pairs_multiple only) */
   int32_t n_inliers;                 /* inlier_matches.size() */
   int32_t E_num_inliers, F_num_inliers, H_num_inliers;
   int32_t E_num_trials, F_num_trials, H_num_trials;
@@ -209,6 +210,16 @@ int b2_verify_pairs(b2_verifier* v, int64_t n_pairs, const uint32_t* pairs,
                     const int64_t* match_offsets, const uint32_t* matches,
                     const b2_two_view_options* opt, const uint32_t* seeds,
                     b2_two_view_result* results, uint32_t* inlier_matches);
+/* TwoViewGeometry::EstimateMultiple (two_view_geometry.cc:128-167; TwoViewGeometryVerifier::Run with
+ * options.multiple_models, matching.cc:595-598): rounds of b2_verify_pairs on the matches that remain
+ * after removing the inliers of the previous round, until a round is DEGENERATE.  Exactly one
+ * geometry -> that result; several -> config 8 (MULTIPLE), inlier lists concatenated in round order,
+ * E/F/H zero.  `multiple_ignore_watermark` = TwoViewGeometry::Options::multiple_ignore_watermark
+ * (default true).  Round r of pair p is seeded with seeds[p] + r * 0x9E3779B9 (mod 2^32). */
+int b2_verify_pairs_multiple(b2_verifier* v, int64_t n_pairs, const uint32_t* pairs,
+                             const int64_t* match_offsets, const uint32_t* matches,
+                             const b2_two_view_options* opt, int32_t multiple_ignore_watermark,
+                             const uint32_t* seeds, b2_two_view_result* results, uint32_t* inlier_matches);
 /* Same with every buffer in DEVICE memory (chains onto b2_match_pairs_device). */
 int b2_verify_pairs_device(b2_verifier* v, int64_t n_pairs, const uint32_t* pairs_dev,
                            const int64_t* match_offsets_dev, const uint32_t* matches_dev,

@@ -315,6 +315,30 @@ def two_view(cam1, pts1, cam2, pts2, matches, opt=None, seed=0):
     return res, inl[: res.n_inliers].copy()
 
 
+def two_view_multiple(cam1, pts1, cam2, pts2, matches, opt=None, seed=0, multiple_ignore_watermark=True):
+    """TwoViewGeometry::EstimateMultiple (two_view_geometry.cc:128-167) restated on top of `two_view`:
+    estimate, drop the inliers BY VALUE (ExtractOutlierMatches, :67-88), repeat until DEGENERATE.
+    Round r is seeded with seed + r * 0x9E3779B9 (the reference continues an unseeded thread-local
+    PRNG).  Returns (config, list of per-geometry results, inlier matches uint32 [n,2])."""
+    remaining = np.ascontiguousarray(matches, dtype=np.uint32).reshape(-1, 2)
+    geos, inliers, rnd = [], [], 0
+    while True:
+        res, inl = two_view(cam1, pts1, cam2, pts2, remaining, opt, seed=(int(seed) + rnd * 0x9E3779B9) & 0xFFFFFFFF)
+        rnd += 1
+        if res.config == 1:        # DEGENERATE
+            break
+        if not (multiple_ignore_watermark and res.config == 7):
+            geos.append(res)
+            inliers.append(inl)
+        gone = {(int(a), int(b)) for a, b in inl}
+        remaining = np.array([m for m in remaining if (int(m[0]), int(m[1])) not in gone], dtype=np.uint32).reshape(-1, 2)
+    if not geos:
+        return 1, geos, np.zeros((0, 2), np.uint32)
+    if len(geos) == 1:
+        return geos[0].config, geos, inliers[0]
+    return 8, geos, np.concatenate(inliers)
+
+
 # ============================================================== bundle adjustment
 class OrcBaProblem(C.Structure):
     _fields_ = [("n_img", C.c_int32), ("n_cam", C.c_int32), ("n_pts", C.c_int32), ("n_obs", C.c_int64),

@@ -79,3 +79,40 @@ def test_guided_shim_replays_reference_test_on_gpu():
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "guided shim ok" in r.stdout
+
+
+@pytest.mark.gpu
+@FIRST_RUN
+def test_estimate_multiple_equals_oracle_on_gpu():
+    """b2_verify_pairs_multiple = the round loop of verify_multiple.h (checked on the CPU with the oracle
+    plugged in, tests/test_host_multiple.py) around the verified GPU Estimate."""
+    from dagsfm_b200 import Camera, TwoViewGeometryVerifier, TwoViewOptions
+    from tests.test_host_multiple import two_motion_pair
+    from tests.tv_scene import scene
+    rng = np.random.default_rng(3)
+    kps, pairs, offs, ms = [], [], [0], []
+    for k, (na, nb, no) in enumerate([(160, 120, 40), (200, 0, 60), (90, 90, 90), (12, 0, 0), (150, 100, 0)]):
+        if nb:
+            p1, p2, m = two_motion_pair(rng, na, nb, no)
+        else:
+            p1, p2 = scene(rng, na, no, noise=0.3)
+            m = np.stack([np.arange(len(p1))] * 2, 1).astype(np.uint32)
+        kps += [p1, p2]
+        pairs.append((2 * k, 2 * k + 1))
+        ms.append(m)
+        offs.append(offs[-1] + len(m))
+    seeds = np.arange(5, dtype=np.uint32) + 40
+    v = TwoViewGeometryVerifier(0)
+    try:
+        v.set_images([Camera.make(prior_focal=False)] * len(kps), kps)
+        res, inl = v.verify_pairs_multiple(pairs, offs, np.concatenate(ms), TwoViewOptions.default(), seeds)
+    finally:
+        v.close()
+    cam = orc.make_camera(prior=False)
+    configs = []
+    for k, (i, j) in enumerate(pairs):
+        cfg, geos, exp_inl = orc.two_view_multiple(cam, kps[i], cam, kps[j], ms[k], seed=int(seeds[k]))
+        configs.append(cfg)
+        assert res["config"][k] == cfg and res["n_inliers"][k] == len(exp_inl)
+        assert inl[offs[k]:offs[k] + len(exp_inl)].tolist() == exp_inl.tolist()
+    assert configs.count(8) >= 2
