@@ -27,7 +27,10 @@ class BundleAdjustmentOptions(C.Structure):
     _fields_ = [("max_num_iterations", C.c_int32), ("refine_focal_length", C.c_int32),
                 ("refine_principal_point", C.c_int32), ("refine_extra_params", C.c_int32),
                 ("function_tolerance", C.c_double), ("gradient_tolerance", C.c_double),
-                ("parameter_tolerance", C.c_double)]
+                ("parameter_tolerance", C.c_double),
+                ("loss_function_type", C.c_int32), ("reserved", C.c_int32), ("loss_function_scale", C.c_double)]
+
+    TRIVIAL, SOFT_L1, CAUCHY = 0, 1, 2   # BundleAdjustmentOptions::LossFunctionType
 
     @staticmethod
     def default():

@@ -70,6 +70,8 @@ int sync_reduce(b2_ba* h, double* buf, int64_t n, int op) {
 
 int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_ba_summary* sum) {
   cudaStream_t s = h->stream;
+  const int loss_type = opt->loss_function_type;
+  const double loss_scale = opt->loss_function_scale;
   const int n_img = pr->n_images, n_cam = pr->n_cameras, n_pts = pr->n_points;
   const int64_t n_obs = pr->n_obs;
   // ---------------------------------------------------------------- validation
@@ -205,7 +207,7 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
   B2_CUDA(cudaMemsetAsync(P.colnorm_c, 0, std::max<size_t>(D, 1) * 8, s));
   B2_CUDA(cudaMemsetAsync(P.colnorm_p, 0, std::max<size_t>(NP * 3, 1) * 8, s));
   B2_CUDA(cudaMemsetAsync(scal, 0, 8 * 8, s));
-  B2_CUDA(ba_launch_jacobian(P, P.qvec, P.tvec, P.cam_params, P.xyz, 2, scal + 6, s));
+  B2_CUDA(ba_launch_jacobian(P, P.qvec, P.tvec, P.cam_params, P.xyz, 2, scal + 6, s, loss_type, loss_scale));
   B2_TRY(sync_reduce(h, P.colnorm_c, D, 0));
   B2_TRY(sync_reduce(h, scal + 6, 1, 0));
   B2_CUDA(ba_launch_make_scale(P.colnorm_c, P.scale_c, D, s));
@@ -218,7 +220,7 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
 
   B2_CUDA(cudaEventRecord(h->ev[0], s));
   B2_CUDA(cudaMemsetAsync(scal + 6, 0, 8, s));
-  B2_CUDA(ba_launch_jacobian(P, P.qvec, P.tvec, P.cam_params, P.xyz, 0, scal + 6, s));
+  B2_CUDA(ba_launch_jacobian(P, P.qvec, P.tvec, P.cam_params, P.xyz, 0, scal + 6, s, loss_type, loss_scale));
   count_launches(1);
 
   double radius = 1e4, decrease_factor = 2.0;
@@ -255,7 +257,7 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
     B2_CUDA(ba_launch_model_cost(P, scal + 4, s));
     B2_CUDA(ba_launch_candidate(P, scal, true, s));
     B2_CUDA(ba_launch_candidate(P, scal, false, s));
-    B2_CUDA(ba_launch_jacobian(P, P.qvec_new, P.tvec_new, P.cam_new, P.xyz_new, 1, scal + 5, s));
+    B2_CUDA(ba_launch_jacobian(P, P.qvec_new, P.tvec_new, P.cam_new, P.xyz_new, 1, scal + 5, s, loss_type, loss_scale));
     count_launches(10);
     B2_TRY(sync_reduce(h, scal + 2, 4, 0));
     double hs[8];
@@ -295,7 +297,7 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
         const bool ftol = std::abs(cost_change) <= opt->function_tolerance * cost;
         cost = new_cost;
         B2_CUDA(cudaMemsetAsync(scal + 6, 0, 8, s));
-        B2_CUDA(ba_launch_jacobian(P, P.qvec, P.tvec, P.cam_params, P.xyz, 0, scal + 6, s));
+        B2_CUDA(ba_launch_jacobian(P, P.qvec, P.tvec, P.cam_params, P.xyz, 0, scal + 6, s, loss_type, loss_scale));
         count_launches(1);
         if (ftol) {
           sum->termination_type = 0;
@@ -344,6 +346,9 @@ void b2_ba_default_options(b2_ba_options* o) {
   o->function_tolerance = 0.0;
   o->gradient_tolerance = 1.0;
   o->parameter_tolerance = 0.0;
+  o->loss_function_type = 0;  // TRIVIAL
+  o->reserved = 0;
+  o->loss_function_scale = 1.0;
 }
 
 int b2_ba_create(int device, b2_ba** out) {
@@ -393,6 +398,8 @@ int b2_ba_set_allreduce(b2_ba* h, b2_allreduce_fn fn, void* user) {
 
 int b2_ba_solve(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_ba_summary* sum) {
   if (!h || !pr || !opt || !sum) return set_error(B2_ERR_INVALID, "NULL argument");
+  if (opt->loss_function_type < 0 || opt->loss_function_type > 2 || !(opt->loss_function_scale > 0))
+    return set_error(B2_ERR_INVALID, "unknown loss_function_type or non-positive loss_function_scale");
   if (pr->n_images < 0 || pr->n_cameras < 0 || pr->n_points < 0 || pr->n_obs < 0 || opt->max_num_iterations < 0)
     return set_error(B2_ERR_INVALID, "negative size");
   B2_CUDA(cudaSetDevice(h->device));

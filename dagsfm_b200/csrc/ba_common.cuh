@@ -44,7 +44,7 @@ struct BaDev {
 };
 
 cudaError_t ba_launch_jacobian(const BaDev& P, const double* q, const double* t, const double* k, const double* X,
-                               int mode, double* cost_out, cudaStream_t s);
+                               int mode, double* cost_out, cudaStream_t s, int loss_type = 0, double loss_scale = 1.0);
 cudaError_t ba_launch_camera_terms(const BaDev& P, cudaStream_t s);
 cudaError_t ba_launch_schur(const BaDev& P, double radius, double min_diag, double max_diag, int n_sm, cudaStream_t s);
 cudaError_t ba_launch_add_diag(const BaDev& P, double radius, double min_diag, double max_diag, cudaStream_t s);

@@ -17,6 +17,8 @@
 //   S double[D*D] (row-major, entries with col_row <= col_col), rhs / g_c / diag_c double[D]
 #include <cuda_runtime.h>
 
+#include <cfloat>
+
 #include <cstdint>
 
 #include "ba_common.cuh"
@@ -109,19 +111,56 @@ __device__ __forceinline__ void atomic_max_nonneg(double* addr, double v) {
 // Thread per observation: residual, Jacobian (optionally Jacobi-scaled), cost.
 // mode 0: write ObsJac; mode 1: residual only at candidate parameters (cost);
 // mode 2: unscaled Jacobian -> squared column norms (Jacobi scaling set-up).
+//
+// LOSS (BundleAdjustmentOptions::LossFunctionType, bundle_adjustment.cc:53-68): 0 TRIVIAL, 1 SOFT_L1,
+// 2 CAUCHY with scale a.  Ceres' ResidualBlock::Evaluate corrects the block's Jacobians and
+// residuals with Corrector (corrector.cc): for rho'' <= 0 -- always true for these two losses --
+// both are scaled by sqrt(rho'(s)), s = |r|^2, and the block's cost is rho(s) / 2.  LOSS == 0
+// compiles to exactly the code it was before the template parameter existed.
+template <int LOSS>
+__device__ __forceinline__ void loss_eval(double a, double s, double* rho0, double* sqrt_rho1) {
+  const double b = a * a, c = 1.0 / b;
+  const double sum = 1.0 + s * c;
+  if (LOSS == 1) {  // ceres::SoftLOneLoss
+    const double tmp = sqrt(sum);
+    *rho0 = 2.0 * b * (tmp - 1.0);
+    *sqrt_rho1 = sqrt(fmax(DBL_MIN, 1.0 / tmp));
+  } else {          // ceres::CauchyLoss
+    const double inv = 1.0 / sum;
+    *rho0 = b * log(sum);
+    *sqrt_rho1 = sqrt(fmax(DBL_MIN, inv));
+  }
+}
+
+template <int LOSS>
 __global__ void __launch_bounds__(256)
 jacobian_kernel(BaDev P, const double* __restrict__ q, const double* __restrict__ t, const double* __restrict__ kp,
-                const double* __restrict__ X, int mode, double* __restrict__ cost_out) {
+                const double* __restrict__ X, int mode, double* __restrict__ cost_out, double loss_scale) {
   const int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   double c = 0;
   if (o < P.n_obs) {
     const int i = P.obs_img[o], p = P.obs_pt[o], cm = P.img_cam[i];
     const double2 xy = P.obs_xy[o];
     double r[2], Jc[20], Jp[6];
+    double rho0 = 0;
     if (mode == 1) {
       evaluate(P.cam_model[cm], q + 4 * i, t + 3 * i, X + 3 * (int64_t)p, kp + 4 * cm, xy.x, xy.y, r, nullptr, nullptr);
+      if (LOSS != 0) {
+        double w;
+        loss_eval<LOSS>(loss_scale, r[0] * r[0] + r[1] * r[1], &rho0, &w);
+      }
     } else {
       evaluate(P.cam_model[cm], q + 4 * i, t + 3 * i, X + 3 * (int64_t)p, kp + 4 * cm, xy.x, xy.y, r, Jc, Jp);
+      if (LOSS != 0) {
+        double w;
+        loss_eval<LOSS>(loss_scale, r[0] * r[0] + r[1] * r[1], &rho0, &w);
+        r[0] *= w;
+        r[1] *= w;
+#pragma unroll
+        for (int k = 0; k < 20; ++k) Jc[k] *= w;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) Jp[k] *= w;
+      }
       int col[10];
 #pragma unroll
       for (int k = 0; k < 6; ++k) col[k] = P.pose_col[6 * i + k];
@@ -153,7 +192,7 @@ jacobian_kernel(BaDev P, const double* __restrict__ q, const double* __restrict_
         }
       }
     }
-    c = r[0] * r[0] + r[1] * r[1];
+    c = (LOSS != 0) ? rho0 : r[0] * r[0] + r[1] * r[1];
   }
   c = warp_sum(c);
   __shared__ double ws[8];
@@ -475,9 +514,14 @@ __global__ void negate_kernel(double* v, int64_t n) {
 static inline unsigned nblk(int64_t n, int b) { return (unsigned)((n + b - 1) / b); }
 
 cudaError_t ba_launch_jacobian(const BaDev& P, const double* q, const double* t, const double* k, const double* X,
-                               int mode, double* cost_out, cudaStream_t s) {
+                               int mode, double* cost_out, cudaStream_t s, int loss_type, double loss_scale) {
   if (P.n_obs == 0) return cudaSuccess;
-  bak::jacobian_kernel<<<nblk(P.n_obs, 256), 256, 0, s>>>(P, q, t, k, X, mode, cost_out);
+  if (loss_type == 1)
+    bak::jacobian_kernel<1><<<nblk(P.n_obs, 256), 256, 0, s>>>(P, q, t, k, X, mode, cost_out, loss_scale);
+  else if (loss_type == 2)
+    bak::jacobian_kernel<2><<<nblk(P.n_obs, 256), 256, 0, s>>>(P, q, t, k, X, mode, cost_out, loss_scale);
+  else
+    bak::jacobian_kernel<0><<<nblk(P.n_obs, 256), 256, 0, s>>>(P, q, t, k, X, mode, cost_out, loss_scale);
   return cudaGetLastError();
 }
 cudaError_t ba_launch_camera_terms(const BaDev& P, cudaStream_t s) {

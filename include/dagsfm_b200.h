@@ -286,6 +286,11 @@ typedef struct b2_ba_options {   /* BundleAdjustmentOptions (bundle_adjustment.h
   double function_tolerance;     /* final BA: 0   */
   double gradient_tolerance;     /* final BA: 1.0 */
   double parameter_tolerance;    /* final BA: 0   */
+  int32_t loss_function_type;    /* BundleAdjustmentOptions::LossFunctionType (bundle_adjustment.h:49-51):
+                                    0 TRIVIAL (final / global BA), 1 SOFT_L1 (the mapper's local BA,
+                                    incremental_mapper_controller.cc:252-253), 2 CAUCHY */
+  int32_t reserved;
+  double loss_function_scale;    /* 1.0 */
 } b2_ba_options;
 
 typedef struct b2_ba_summary {   /* the fields of ceres::Solver::Summary the reference reads */

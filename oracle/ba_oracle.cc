@@ -29,6 +29,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <limits>
 #include <cstdint>
 #include <cstring>
 #include <vector>
@@ -155,7 +156,47 @@ struct Options {
   int max_num_iterations;
   double function_tolerance, gradient_tolerance, parameter_tolerance;
   int n_threads;
+  int loss_type = 0;        // BundleAdjustmentOptions::LossFunctionType: 0 TRIVIAL, 1 SOFT_L1, 2 CAUCHY
+  double loss_scale = 1.0;  // loss_function_scale
 };
+
+// ceres::LossFunction::Evaluate (Ceres 1.14 loss_function.cc) for the three types
+// BundleAdjustmentOptions::CreateLossFunction can build (bundle_adjustment.cc:53-68):
+// rho[0] = rho(s), rho[1] = rho'(s), rho[2] = rho''(s) with s = |r|^2 of one observation.
+static void LossEvaluate(int type, double a, double s, double rho[3]) {
+  if (type == 1) {  // SoftLOneLoss(a): b = a^2, c = 1 / b
+    const double b = a * a, c = 1.0 / b;
+    const double sum = 1.0 + s * c;
+    const double tmp = std::sqrt(sum);
+    rho[0] = 2.0 * b * (tmp - 1.0);
+    rho[1] = std::max(std::numeric_limits<double>::min(), 1.0 / tmp);
+    rho[2] = -(c * rho[1]) / (2.0 * sum);
+  } else if (type == 2) {  // CauchyLoss(a)
+    const double b = a * a, c = 1.0 / b;
+    const double sum = 1.0 + s * c;
+    const double inv = 1.0 / sum;
+    rho[0] = b * std::log(sum);
+    rho[1] = std::max(std::numeric_limits<double>::min(), inv);
+    rho[2] = -c * (inv * inv);
+  } else {
+    rho[0] = s; rho[1] = 1.0; rho[2] = 0.0;
+  }
+}
+// ceres::internal::Corrector (corrector.cc): for rho'' <= 0 -- always the case for SoftLOne and
+// Cauchy -- residual and Jacobian of the block are both scaled by sqrt(rho'); otherwise the
+// Triggs correction with alpha = 1 - sqrt(1 + 2 s rho''/rho').  Returns the residual scaling and
+// writes sqrt(rho') and alpha / s.
+static double Corrector(double s, const double rho[3], double* sqrt_rho1, double* alpha_sq_norm) {
+  *sqrt_rho1 = std::sqrt(rho[1]);
+  if (s == 0.0 || rho[2] <= 0.0) {
+    *alpha_sq_norm = 0.0;
+    return *sqrt_rho1;
+  }
+  const double D = 1.0 + 2.0 * s * rho[2] / rho[1];
+  const double alpha = 1.0 - std::sqrt(D);
+  *alpha_sq_norm = alpha / s;
+  return *sqrt_rho1 / (1 - alpha);
+}
 struct Summary {
   double initial_cost, final_cost;
   int num_successful_steps, num_unsuccessful_steps, termination;  // 0 convergence, 1 no convergence, 2 failure
@@ -245,7 +286,7 @@ static bool CholeskySolve(std::vector<double>& A, int n, std::vector<double>& b)
   return true;
 }
 
-struct ObsJ { double r[2]; double Jc[2][10]; double Jp[2][3]; int col[10]; };
+struct ObsJ { double r[2]; double Jc[2][10]; double Jp[2][3]; int col[10]; double rho0; };
 
 struct Solver {
   Problem P;
@@ -262,7 +303,13 @@ struct Solver {
       const int i = P.obs_img[o], p = P.obs_pt[o], c = P.img_cam[i];
       double r[2];
       Evaluate(P.cam_model[c], q + 4 * i, t + 3 * i, X + 3 * p, kp + 4 * c, P.obs_xy + 2 * o, r, nullptr, nullptr, nullptr, nullptr);
-      cost += r[0] * r[0] + r[1] * r[1];
+      if (O.loss_type == 0) {
+        cost += r[0] * r[0] + r[1] * r[1];
+      } else {
+        double rho[3];
+        LossEvaluate(O.loss_type, O.loss_scale, r[0] * r[0] + r[1] * r[1], rho);
+        cost += rho[0];
+      }
     }
     return 0.5 * cost;
   }
@@ -275,9 +322,22 @@ struct Solver {
       Evaluate(P.cam_model[c], P.qvec + 4 * i, P.tvec + 3 * i, P.xyz + 3 * p, P.cam_params + 4 * c, P.obs_xy + 2 * o, e.r, Jq, Jt, JX, Jk);
       for (int k = 0; k < 6; ++k) e.col[k] = L.pose_col[6 * i + k];
       for (int k = 0; k < 4; ++k) e.col[6 + k] = L.intr_col[4 * c + k];
+      e.rho0 = e.r[0] * e.r[0] + e.r[1] * e.r[1];
+      double jscale = 1.0;
+      if (O.loss_type != 0) {  // ResidualBlock::Evaluate: correct the Jacobians, then the residuals
+        double rho[3], sqrt_rho1, alpha_sq_norm;
+        const double sq = e.rho0;
+        LossEvaluate(O.loss_type, O.loss_scale, sq, rho);
+        const double rscale = Corrector(sq, rho, &sqrt_rho1, &alpha_sq_norm);
+        // rho'' <= 0 for both robust types, so alpha_sq_norm == 0: a pure scaling by sqrt(rho')
+        jscale = sqrt_rho1;
+        e.r[0] *= rscale;
+        e.r[1] *= rscale;
+        e.rho0 = rho[0];
+      }
       for (int a = 0; a < 2; ++a) {
-        for (int k = 0; k < 3; ++k) { e.Jc[a][k] = Jq[3 * a + k]; e.Jc[a][3 + k] = Jt[3 * a + k]; e.Jp[a][k] = JX[3 * a + k]; }
-        for (int k = 0; k < 4; ++k) e.Jc[a][6 + k] = Jk[4 * a + k];
+        for (int k = 0; k < 3; ++k) { e.Jc[a][k] = jscale * Jq[3 * a + k]; e.Jc[a][3 + k] = jscale * Jt[3 * a + k]; e.Jp[a][k] = jscale * JX[3 * a + k]; }
+        for (int k = 0; k < 4; ++k) e.Jc[a][6 + k] = jscale * Jk[4 * a + k];
         for (int k = 0; k < 10; ++k) {
           if (e.col[k] < 0) e.Jc[a][k] = 0;
           else if (scaled) e.Jc[a][k] *= scale_c[e.col[k]];
@@ -332,7 +392,7 @@ static void Solve(Problem P, Options O, Summary* S) {
     for (int j = 0; j < 3 * NP; ++j) sv.scale_p[j] = 1.0 / (1.0 + std::sqrt(np[j]));
   }
   double cost = 0;
-  for (long o = 0; o < P.n_obs; ++o) cost += sv.J[o].r[0] * sv.J[o].r[0] + sv.J[o].r[1] * sv.J[o].r[1];
+  for (long o = 0; o < P.n_obs; ++o) cost += sv.J[o].rho0;  // |r|^2, or rho(|r|^2) under a robust loss
   cost *= 0.5;
   S->initial_cost = cost;
   sv.EvalJacobian(true);
@@ -554,7 +614,7 @@ struct orc_ba_problem {
   double* xyz; const uint8_t* pt_const;
   const int32_t* obs_img; const int32_t* obs_pt; const double* obs_xy;
 };
-struct orc_ba_options { int32_t max_num_iterations; double function_tolerance, gradient_tolerance, parameter_tolerance; int32_t n_threads; };
+struct orc_ba_options { int32_t max_num_iterations; double function_tolerance, gradient_tolerance, parameter_tolerance; int32_t n_threads; int32_t loss_type; double loss_scale; };
 struct orc_ba_summary { double initial_cost, final_cost; int32_t num_successful_steps, num_unsuccessful_steps, termination, num_residuals, num_effective_parameters; double seconds; };
 
 void orc_ba_solve(const orc_ba_problem* p, const orc_ba_options* o, orc_ba_summary* s) {
@@ -564,7 +624,10 @@ void orc_ba_solve(const orc_ba_problem* p, const orc_ba_options* o, orc_ba_summa
   P.cam_model = p->cam_model; P.cam_params = p->cam_params; P.cam_const = p->cam_const;
   P.refine_focal = p->refine_focal; P.refine_principal = p->refine_principal; P.refine_extra = p->refine_extra;
   P.xyz = p->xyz; P.pt_const = p->pt_const; P.obs_img = p->obs_img; P.obs_pt = p->obs_pt; P.obs_xy = p->obs_xy;
-  ba::Options O{o->max_num_iterations, o->function_tolerance, o->gradient_tolerance, o->parameter_tolerance, o->n_threads};
+  ba::Options O;
+  O.max_num_iterations = o->max_num_iterations; O.function_tolerance = o->function_tolerance;
+  O.gradient_tolerance = o->gradient_tolerance; O.parameter_tolerance = o->parameter_tolerance; O.n_threads = o->n_threads;
+  O.loss_type = o->loss_type; O.loss_scale = o->loss_scale;
   ba::Summary S;
   ba::Solve(P, O, &S);
   s->initial_cost = S.initial_cost; s->final_cost = S.final_cost;

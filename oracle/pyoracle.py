@@ -351,7 +351,8 @@ class OrcBaProblem(C.Structure):
 
 class OrcBaOptions(C.Structure):
     _fields_ = [("max_num_iterations", C.c_int32), ("function_tolerance", C.c_double),
-                ("gradient_tolerance", C.c_double), ("parameter_tolerance", C.c_double), ("n_threads", C.c_int32)]
+                ("gradient_tolerance", C.c_double), ("parameter_tolerance", C.c_double), ("n_threads", C.c_int32),
+                ("loss_type", C.c_int32), ("loss_scale", C.c_double)]
 
 
 class OrcBaSummary(C.Structure):
@@ -361,7 +362,7 @@ class OrcBaSummary(C.Structure):
 
 
 def ba_solve(prob: dict, max_num_iterations=50, function_tolerance=0.0, gradient_tolerance=1.0,
-             parameter_tolerance=0.0):
+             parameter_tolerance=0.0, loss_type=0, loss_scale=1.0):
     """prob: dict of numpy arrays (see tests/ba_scene.py); qvec/tvec/cam_params/xyz are updated in place."""
     L = lib()
     L.orc_ba_solve.argtypes = [C.POINTER(OrcBaProblem), C.POINTER(OrcBaOptions), C.POINTER(OrcBaSummary)]
@@ -373,7 +374,8 @@ def ba_solve(prob: dict, max_num_iterations=50, function_tolerance=0.0, gradient
         assert prob[k].flags["C_CONTIGUOUS"]
         setattr(p, k, prob[k].ctypes.data)
     p.refine_focal, p.refine_principal, p.refine_extra = prob.get("refine", (1, 0, 1))
-    o = OrcBaOptions(max_num_iterations, function_tolerance, gradient_tolerance, parameter_tolerance, 0)
+    o = OrcBaOptions(max_num_iterations, function_tolerance, gradient_tolerance, parameter_tolerance, 0,
+                     int(loss_type), float(loss_scale))
     s = OrcBaSummary()
     L.orc_ba_solve(C.byref(p), C.byref(o), C.byref(s))
     return s

@@ -116,3 +116,33 @@ def test_estimate_multiple_equals_oracle_on_gpu():
         assert res["config"][k] == cfg and res["n_inliers"][k] == len(exp_inl)
         assert inl[offs[k]:offs[k] + len(exp_inl)].tolist() == exp_inl.tolist()
     assert configs.count(8) >= 2
+
+
+@pytest.mark.gpu
+@FIRST_RUN
+@pytest.mark.parametrize("loss_type,scale", [(1, 1.0), (2, 1.0), (1, 2.5)])
+def test_ba_robust_loss_matches_oracle_on_gpu(loss_type, scale):
+    """SOFT_L1 / CAUCHY (BundleAdjustmentOptions::CreateLossFunction; the mapper's local BA): the Jacobian
+    kernel's LOSS != 0 instantiations against the oracle's Ceres Corrector restatement, which the CPU suite
+    pins to an independent evaluation of 1/2 sum rho(|r|^2) (tests/test_oracle_ba_loss.py)."""
+    from dagsfm_b200 import BundleAdjuster, BundleAdjustmentOptions
+    from tests.ba_scene import copy_problem, make_ba_problem, reprojection_rms
+    p_gpu = make_ba_problem(n_img=12, n_pts=300, track_len=5, seed=4, noise_px=1.0)
+    rng = np.random.default_rng(1)
+    idx = rng.choice(len(p_gpu["obs_xy"]), 60, replace=False)
+    p_gpu["obs_xy"][idx] += rng.normal(0, 40, (60, 2))
+    p_cpu = copy_problem(p_gpu)
+    o = BundleAdjustmentOptions.default()
+    o.max_num_iterations, o.gradient_tolerance, o.function_tolerance = 200, 1e-9, 1e-12
+    o.loss_function_type, o.loss_function_scale = loss_type, scale
+    ba = BundleAdjuster(o)
+    try:
+        s_gpu = ba.Solve(p_gpu)
+    finally:
+        ba.close()
+    s_cpu = orc.ba_solve(p_cpu, max_num_iterations=200, gradient_tolerance=1e-9, function_tolerance=1e-12,
+                         loss_type=loss_type, loss_scale=scale)
+    assert s_gpu.initial_cost == pytest.approx(s_cpu.initial_cost, rel=1e-12)
+    assert s_gpu.final_cost == pytest.approx(s_cpu.final_cost, rel=1e-9)
+    assert abs(reprojection_rms(p_gpu) - reprojection_rms(p_cpu)) < 1e-6
+    assert np.abs(p_gpu["xyz"] - p_cpu["xyz"]).max() < 1e-5
