@@ -163,6 +163,22 @@ def peaks_hbm():
         return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
 
 
+def verify_work_rates(res, match_offsets, kernel_s):
+    """SURVEY 8(d) unit of the verification stage: hypothesis-match evaluations (33 flop Sampson for E / F,
+    25 flop for H).  Lower bound from the trial counts the kernel reports: every trial scores at least one
+    hypothesis against all M matches (the 7-point solver yields up to 3, the 5-point up to 10), LO and
+    tie-breaking passes not counted."""
+    m = np.diff(np.asarray(match_offsets, dtype=np.int64)).astype(np.float64)
+    ef = (res["E_num_trials"].astype(np.float64) + res["F_num_trials"].astype(np.float64)) * m
+    h = res["H_num_trials"].astype(np.float64) * m
+    evals = float(ef.sum() + h.sum())
+    flops = float(33.0 * ef.sum() + 25.0 * h.sum())
+    return {"hypothesis_match_evals_per_s_min": evals / kernel_s, "fp64_gflops_min": flops / kernel_s / 1e9,
+            "fp64_peak_note": "lower bound (>= 1 hypothesis per trial); FP64 vector peak not in MEASURED_PEAKS.json, "
+                              "public B200 figure ~40 TFLOP/s",
+            "trials_per_pair": {k: float(res[k + "_num_trials"].mean()) for k in ("E", "F", "H")}}
+
+
 def bench_verify(a, local_rank, rank, world, cores, barrier):
     """Two-view verification throughput: b2_verify_pairs (host buffers in / out) on synthetic
     matched pairs; CPU baseline = oracle port of TwoViewGeometry::Estimate, `cores` workers."""
@@ -187,6 +203,10 @@ def bench_verify(a, local_rank, rank, world, cores, barrier):
            "config_histogram": {int(k): int(c) for k, c in zip(*np.unique(res["config"], return_counts=True))},
            "inlier_recall": float((res["n_inliers"] >= 0.9 * w["n_inliers_true"]).mean()),
            "api": "b2_verify_pairs (host buffers)"}
+    try:
+        out["roofline"] = verify_work_rates(res, w["match_offsets"], kern)
+    except Exception as e:   # a reporting extra must never cost the bench line
+        out["roofline"] = {"error": repr(e)}
     if rank == 0 and not a.no_cpu:
         from oracle import pyoracle as orc
         import ctypes as C
