@@ -227,6 +227,14 @@ def bench_verify(a, local_rank, rank, world, cores, barrier):
     return out
 
 
+def _mean_reproj(prob):
+    try:
+        from tests.ba_scene import mean_reprojection_error
+        return mean_reprojection_error(prob)
+    except Exception:
+        return None
+
+
 def bench_ba(a, local_rank, rank, world, cores, barrier, hbm):
     """Final-BA leg (BASELINE configs[3]): LM iterations per second of b2_ba_solve and the HBM
     roofline of the Jacobian+Schur kernels; CPU baseline = the reference's vendored PBA."""
@@ -264,6 +272,7 @@ def bench_ba(a, local_rank, rank, world, cores, barrier, hbm):
            "successful": s.num_successful_steps, "unsuccessful": s.num_unsuccessful_steps,
            "termination": s.termination_type, "solve_s": s.solve_seconds, "e2e_s": wall,
            "rms_px_initial": reprojection_rms(prob0), "rms_px_final": reprojection_rms(prob),
+           "mean_reproj_error_px_final": _mean_reproj(prob),
            "rms_note": "this rank's point shard" if world > 1 else "all observations",
            "sharding": f"points over {world} ranks, 1 all-reduce of the reduced camera system per LM iteration" if world > 1 else "single GPU",
            "ceres_style_px": float(np.sqrt(s.final_cost / (2 * n_obs))),

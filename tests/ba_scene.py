@@ -109,3 +109,19 @@ def reprojection_rms(prob):
     r2 = (uv ** 2).sum(1, keepdims=True)
     xy = k[:, :1] * uv * (1 + k[:, 3:4] * r2) + k[:, 1:3]
     return float(np.sqrt(((xy - prob["obs_xy"]) ** 2).sum() / len(i)))
+
+
+def mean_reprojection_error(prob):
+    """Mean ||r|| in px: Reconstruction::ComputeMeanReprojectionError (base/reconstruction.cc:814-858)."""
+    q = prob["qvec"] / np.linalg.norm(prob["qvec"], axis=1, keepdims=True)
+    w, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    R = np.stack([np.stack([1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)], 1),
+                  np.stack([2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)], 1),
+                  np.stack([2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)], 1)], 1)
+    i, p = prob["obs_img"], prob["obs_pt"]
+    pc = np.einsum("nij,nj->ni", R[i], prob["xyz"][p]) + prob["tvec"][i]
+    uv = pc[:, :2] / pc[:, 2:]
+    k = prob["cam_params"][prob["img_cam"][i]]
+    r2 = (uv ** 2).sum(1, keepdims=True)
+    xy = k[:, :1] * uv * (1 + k[:, 3:4] * r2) + k[:, 1:3]
+    return float(np.sqrt(((xy - prob["obs_xy"]) ** 2).sum(1)).mean())
