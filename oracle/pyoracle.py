@@ -279,6 +279,39 @@ def svd(A):
     return s, V
 
 
+def center_and_normalize(pts):
+    p = _p(pts); out = np.zeros_like(p); T = np.zeros((3, 3))
+    f = _tv().orc_center_and_normalize
+    f.argtypes = [C.c_int] + [C.c_void_p] * 3
+    f.restype = None
+    f(len(p), p.ctypes.data, out.ctypes.data, T.ctypes.data)
+    return out, T
+
+
+def support_evaluate(residuals, max_residual):
+    r = _p(residuals); n = C.c_long(0); s = C.c_double(0)
+    f = _tv().orc_support_evaluate
+    f.argtypes = [C.c_void_p, C.c_int, C.c_double, C.POINTER(C.c_long), C.POINTER(C.c_double)]
+    f.restype = None
+    f(r.ctypes.data, len(r), float(max_residual), C.byref(n), C.byref(s))
+    return n.value, s.value
+
+
+def support_compare(n1, s1, n2, s2) -> bool:
+    f = _tv().orc_support_compare
+    f.argtypes = [C.c_long, C.c_double, C.c_long, C.c_double]
+    return bool(f(int(n1), float(s1), int(n2), float(s2)))
+
+
+def translation_estimate(src, dst):
+    a, b = _p(src), _p(dst); t = np.zeros(2); r = np.zeros(len(a))
+    f = _tv().orc_translation_estimate
+    f.argtypes = [C.c_int] + [C.c_void_p] * 4
+    f.restype = None
+    f(len(a), a.ctypes.data, b.ctypes.data, t.ctypes.data, r.ctypes.data)
+    return t, r
+
+
 def sample_stream(seed, total, k, n_trials):
     out = np.zeros((n_trials, k), dtype=np.int32)
     _tv().orc_sample_stream(seed, total, k, n_trials, out.ctypes.data)

@@ -1237,6 +1237,35 @@ int orc_poly_roots(int n_coeffs, const double* coeffs, double* re, double* im) {
   return (int)r.size();
 }
 void orc_svd(const double* A, int m, int n, double* sigma, double* V) { tv::jacobi_svd(A, m, n, sigma, V, nullptr); }
+// estimators/utils.cc:38-85 (pinned by utils_test.cc:40-61, exact doubles)
+void orc_center_and_normalize(int n, const double* pts, double* normed, double* T) {
+  std::vector<tv::Vec2> p = to_vec(pts, n), out;
+  tv::Mat3 M;
+  tv::CenterAndNormalizeImagePoints(p, &out, &M);
+  for (int i = 0; i < n; ++i) { normed[2 * i] = out[i].x; normed[2 * i + 1] = out[i].y; }
+  memcpy(T, M.m, sizeof M.m);
+}
+// optim/support_measurement.cc:36-60 (pinned by support_measurement_test.cc:42-70)
+void orc_support_evaluate(const double* residuals, int n, double max_residual, long* num_inliers, double* residual_sum) {
+  const tv::Support s = tv::Evaluate(std::vector<double>(residuals, residuals + n), max_residual);
+  *num_inliers = (long)s.num_inliers;
+  *residual_sum = s.residual_sum;
+}
+int orc_support_compare(long n1, double s1, long n2, double s2) {
+  tv::Support a, b;
+  a.num_inliers = (size_t)n1; a.residual_sum = s1;
+  b.num_inliers = (size_t)n2; b.residual_sum = s2;
+  return tv::Compare(a, b) ? 1 : 0;
+}
+// translation_transform.h:53-116, kDim = 2 (pinned by translation_transform_test.cc:41-69)
+void orc_translation_estimate(int n, const double* src, const double* dst, double* t, double* residuals) {
+  const std::vector<tv::Vec2> a = to_vec(src, n), b = to_vec(dst, n);
+  const tv::Mat3 M = tv::Translation2(a, b)[0];
+  t[0] = M.m[0]; t[1] = M.m[1];
+  std::vector<double> r;
+  tv::TranslationResiduals(a, b, M, &r);
+  memcpy(residuals, r.data(), (size_t)n * 8);
+}
 // The sampler's index stream: n_trials x k indices for a population of `total`.
 void orc_sample_stream(unsigned seed, int total, int k, int n_trials, int32_t* out) {
   std::mt19937 prng(seed);
