@@ -13,3 +13,4 @@ from .verification import (Camera, TwoViewGeometryVerifier, TwoViewOptions,  # n
 from .bundle_adjustment import BundleAdjuster, BundleAdjustmentOptions  # noqa: F401
 
 __version__ = "0.1"
+from .ba_config import BundleAdjustmentConfig, Reconstruction, pack_problem, unpack_problem  # noqa: F401,E402

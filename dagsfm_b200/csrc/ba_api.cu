@@ -129,7 +129,17 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
   for (int64_t o = 0; o < n_obs; ++o) pt_start[pr->obs_point[o] + 1]++;
   for (int p = 0; p < n_pts; ++p) pt_start[p + 1] += pt_start[p];
 
-  sum->num_residuals_reduced = (int32_t)(2 * n_obs);
+  // Ceres' reduced program drops residual blocks whose parameter blocks are all constant
+  // (bundle_adjustment_test.cc:360-364 counts 402, not 404, for exactly that reason)
+  int64_t n_obs_reduced = 0;
+  for (int64_t o = 0; o < n_obs; ++o) {
+    const int i = pr->obs_image[o], c = pr->image_camera[i];
+    bool free_block = pt_col[pr->obs_point[o]] >= 0;
+    for (int k = 0; k < 6 && !free_block; ++k) free_block = pose_col[6 * i + k] >= 0;
+    for (int k = 0; k < 4 && !free_block; ++k) free_block = intr_col[4 * c + k] >= 0;
+    n_obs_reduced += free_block ? 1 : 0;
+  }
+  sum->num_residuals_reduced = (int32_t)(2 * n_obs_reduced);
   sum->num_effective_parameters_reduced = (int32_t)(D + 3 * NP);
   sum->num_successful_steps = sum->num_unsuccessful_steps = sum->num_iterations = 0;
   sum->termination_type = 1;

@@ -370,7 +370,17 @@ static void Solve(Problem P, Options O, Summary* S) {
   sv.J.resize(P.n_obs);
   sv.scale_c.assign(std::max(D, 1), 1.0);
   sv.scale_p.assign(std::max(3 * NP, 1), 1.0);
-  S->num_residuals = (int)(2 * P.n_obs);
+  {  // Ceres' reduced program drops residual blocks whose parameter blocks are all constant
+    long n = 0;
+    for (long o = 0; o < P.n_obs; ++o) {
+      const int i = P.obs_img[o], c = P.img_cam[i];
+      bool free_block = L.pt_col[P.obs_pt[o]] >= 0;
+      for (int k = 0; k < 6 && !free_block; ++k) free_block = L.pose_col[6 * i + k] >= 0;
+      for (int k = 0; k < 4 && !free_block; ++k) free_block = L.intr_col[4 * c + k] >= 0;
+      n += free_block ? 1 : 0;
+    }
+    S->num_residuals = (int)(2 * n);
+  }
   S->num_effective_parameters = D + 3 * NP;
   S->num_successful_steps = S->num_unsuccessful_steps = 0;
   S->termination = 1;

@@ -146,3 +146,46 @@ def test_ba_robust_loss_matches_oracle_on_gpu(loss_type, scale):
     assert s_gpu.final_cost == pytest.approx(s_cpu.final_cost, rel=1e-9)
     assert abs(reprojection_rms(p_gpu) - reprojection_rms(p_cpu)) < 1e-6
     assert np.abs(p_gpu["xyz"] - p_cpu["xyz"]).max() < 1e-5
+
+
+@pytest.mark.gpu
+@FIRST_RUN
+@pytest.mark.parametrize("case", ["two_view", "partial_tracks_forced_points", "variable_image"])
+def test_reference_ba_config_cases_on_gpu(case):
+    """bundle_adjustment_test.cc cases packed by dagsfm_b200.ba_config (the mirror of BundleAdjuster::SetUp,
+    checked against the reference's expected counts on the CPU in tests/test_ba_config.py), solved by b2_ba_solve."""
+    from dagsfm_b200 import BundleAdjuster, BundleAdjustmentOptions
+    from dagsfm_b200.ba_config import BundleAdjustmentConfig, pack_problem
+    from tests.test_ba_config import generate_reconstruction
+    c = BundleAdjustmentConfig()
+    if case == "two_view":
+        r = generate_reconstruction(2, 100)
+        c.AddImage(0); c.AddImage(1); c.SetConstantPose(0); c.SetConstantTvec(1, [0])
+        exp = (400, 309)
+    elif case == "partial_tracks_forced_points":
+        r = generate_reconstruction(3, 100)
+        vp, cp = r.images[2]["points2D"][1][2], r.images[2]["points2D"][2][2]
+        r.delete_observation(2, 0)
+        c.AddImage(0); c.AddImage(1); c.SetConstantPose(0); c.SetConstantPose(1)
+        c.AddVariablePoint(vp); c.AddConstantPoint(cp)
+        exp = (402, 10)
+    else:
+        r = generate_reconstruction(3, 100)
+        c.AddImage(0); c.AddImage(1); c.AddImage(2); c.SetConstantPose(0); c.SetConstantTvec(1, [0])
+        exp = (600, 317)
+    p_gpu, _ = pack_problem(r, c)
+    p_cpu = {k: v.copy() for k, v in p_gpu.items()}
+    o = BundleAdjustmentOptions.default()
+    o.max_num_iterations, o.function_tolerance, o.gradient_tolerance, o.parameter_tolerance = 100, 0.0, 0.0, 0.0
+    ba = BundleAdjuster(o)
+    try:
+        s = ba.Solve(p_gpu)
+    finally:
+        ba.close()
+    sc = orc.ba_solve(p_cpu, max_num_iterations=100, function_tolerance=0.0, gradient_tolerance=0.0, parameter_tolerance=0.0)
+    assert (s.num_residuals_reduced, s.num_effective_parameters_reduced) == exp == (sc.num_residuals, sc.num_effective_parameters)
+    assert s.final_cost == pytest.approx(sc.final_cost, rel=1e-9)
+    for k in ("qvec", "tvec", "cam_params", "xyz"):
+        const = {"qvec": p_gpu["pose_const"], "tvec": p_gpu["pose_const"], "cam_params": p_gpu["cam_const"], "xyz": p_gpu["pt_const"]}[k]
+        assert np.abs(p_gpu[k] - p_cpu[k]).max() < 1e-5
+        assert (p_gpu[k][const == 1] == p_cpu[k][const == 1]).all()        # constant blocks stay bit-identical
