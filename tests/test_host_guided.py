@@ -118,3 +118,64 @@ def test_integer_threshold_tables_equal_float_decisions(hg):
             asn = np.arccos(np.minimum(kn * np.float32(s), np.float32(1.0)), dtype=np.float32)
             exp = (not ab > d32) and (not ab >= r32 * asn)
             assert bool(hg.host_threshold_accept(ratio, dist, b, s)) == bool(exp), (ratio, dist, b, s)
+
+
+# ----------------------------------------------------------------------------------------------
+# The CUDA kernels themselves (match_guided_kernels.cuh), executed on the host block by block and
+# thread by thread inside a re-statement of the library's pipeline (tests/cpp/host_guided_kernel.cc).
+@pytest.fixture(scope="module")
+def hk():
+    src = os.path.join(HERE, "cpp", "host_guided_kernel.cc")
+    out = os.path.join(HERE, "cpp", "_host_guided_kernel.so")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.run([cxx, "-O2", "-ffp-contract=off", "-std=c++17", "-shared", "-fPIC", "-o", out, src], check=True)
+    lib = ctypes.CDLL(out)
+    vp, ci = ctypes.c_void_p, ctypes.c_int
+    lib.host_guided_pipeline.argtypes = [ci, vp, vp, vp, ci, vp, vp, vp, vp, ctypes.c_double, ctypes.c_float,
+                                         ctypes.c_float, ci, ci, vp, vp, ctypes.c_int64]
+    return lib
+
+
+def run_kernels(lib, descs, kps, pairs, geos, grid_blocks, max_error=4.0, max_ratio=0.8, max_distance=0.7, cross_check=True):
+    n = len(descs)
+    ds = [np.ascontiguousarray(d, np.uint8).reshape(-1, 128) for d in descs]
+    ks = [np.ascontiguousarray(k, np.float32).reshape(-1, 2) for k in kps]
+    dptr = (ctypes.c_void_p * n)(*[d.ctypes.data for d in ds])
+    kptr = (ctypes.c_void_p * n)(*[k.ctypes.data for k in ks])
+    cnt = np.array([len(d) for d in ds], np.int32)
+    pr = np.ascontiguousarray(pairs, np.uint32).reshape(-1, 2)
+    cfg = np.array([g[0] for g in geos], np.int32)
+    F = np.ascontiguousarray([np.zeros(9) if g[1] is None else np.asarray(g[1], np.float64).reshape(9) for g in geos])
+    H = np.ascontiguousarray([np.zeros(9) if g[2] is None else np.asarray(g[2], np.float64).reshape(9) for g in geos])
+    off = np.zeros(len(pr) + 1, np.int64)
+    cap = int(sum(len(ds[a]) for a, _ in pr)) + 1
+    out = np.zeros((cap, 2), np.uint32)
+    total = lib.host_guided_pipeline(n, dptr, kptr, cnt.ctypes.data, len(pr), pr.ctypes.data, cfg.ctypes.data,
+                                     F.ctypes.data, H.ctypes.data, max_error, max_ratio, max_distance, int(cross_check),
+                                     grid_blocks, off.ctypes.data, out.ctypes.data, cap)
+    assert total == off[-1] >= 0
+    return off, out
+
+
+@pytest.mark.parametrize("grid_blocks", [1, 3, 64])
+def test_cuda_kernels_on_host_equal_oracle(hk, grid_blocks):
+    rng = np.random.default_rng(21)
+    kps, descs, pairs, geos = [], [], [], []
+    for k, (n_in, n_out) in enumerate([(120, 40), (260, 90), (300, 240), (90, 10)]):   # 160 .. 540 rows: 1-3 supertiles
+        planar = k % 2 == 1
+        k1, k2, d1, d2 = _scene_with_descriptors(rng, n_in, n_out, planar)
+        a, b = _inlier_pairs(k1, k2, d1, d2)
+        geos.append((4 + k, None, orc.h_dlt(a, b)) if planar else (2 + (k // 2), orc.eight_point(a, b), None))
+        kps += [k1, k2[: len(k2) - 7 * k]]                 # ragged: the two images of a pair differ in size
+        descs += [d1, d2[: len(d2) - 7 * k]]
+        pairs.append((2 * k, 2 * k + 1))
+    kps.append(np.zeros((0, 2), np.float32)); descs.append(np.zeros((0, 128), np.uint8))       # an empty image
+    pairs += [(0, 8), (8, 1), (3, 2), (0, 1)]
+    geos += [geos[0], geos[0], geos[1], (7, None, None)]    # empty image twice, swapped order, WATERMARK = no filter
+    for opts in (dict(), dict(cross_check=False, max_error=2.0), dict(max_ratio=0.95, max_distance=1.2)):
+        off, out = run_kernels(hk, descs, kps, pairs, geos, grid_blocks, **opts)
+        for p, ((i, j), (cfg, F, H)) in enumerate(zip(pairs, geos)):
+            e = orc.match_guided(kps[i], kps[j], descs[i], descs[j], cfg, F=F, H=H, **opts)
+            exp = [] if (e is None or len(descs[i]) == 0 or len(descs[j]) == 0) else e.tolist()
+            assert out[off[p]:off[p + 1]].tolist() == exp, (p, cfg, opts)
+        assert off[4] > 500
