@@ -22,6 +22,7 @@
 #include <cstdint>
 
 #include "ba_common.cuh"
+#include "ba_loss.cuh"
 
 namespace b2 {
 namespace bak {
@@ -117,21 +118,6 @@ __device__ __forceinline__ void atomic_max_nonneg(double* addr, double v) {
 // residuals with Corrector (corrector.cc): for rho'' <= 0 -- always true for these two losses --
 // both are scaled by sqrt(rho'(s)), s = |r|^2, and the block's cost is rho(s) / 2.  LOSS == 0
 // compiles to exactly the code it was before the template parameter existed.
-template <int LOSS>
-__device__ __forceinline__ void loss_eval(double a, double s, double* rho0, double* sqrt_rho1) {
-  const double b = a * a, c = 1.0 / b;
-  const double sum = 1.0 + s * c;
-  if (LOSS == 1) {  // ceres::SoftLOneLoss
-    const double tmp = sqrt(sum);
-    *rho0 = 2.0 * b * (tmp - 1.0);
-    *sqrt_rho1 = sqrt(fmax(DBL_MIN, 1.0 / tmp));
-  } else {          // ceres::CauchyLoss
-    const double inv = 1.0 / sum;
-    *rho0 = b * log(sum);
-    *sqrt_rho1 = sqrt(fmax(DBL_MIN, inv));
-  }
-}
-
 template <int LOSS>
 __global__ void __launch_bounds__(256)
 jacobian_kernel(BaDev P, const double* __restrict__ q, const double* __restrict__ t, const double* __restrict__ kp,

@@ -651,6 +651,11 @@ void orc_ba_evaluate(int model, const double* q, const double* t, const double* 
                      double* r, double* Jq, double* Jt, double* JX, double* Jk) {
   ba::Evaluate(model, q, t, X, k, obs, r, Jq, Jt, JX, Jk);
 }
+// loss value / derivatives and the corrector's scalings (tests: tests/test_oracle_ba_loss.py, host_ba_loss.cc)
+void orc_ba_loss(int type, double a, double s, double* rho, double* residual_scaling, double* sqrt_rho1, double* alpha_sq_norm) {
+  ba::LossEvaluate(type, a, s, rho);
+  *residual_scaling = ba::Corrector(s, rho, sqrt_rho1, alpha_sq_norm);
+}
 void orc_ba_quat_plus(const double* x, const double* d, double* out) { ba::QuatPlus(x, d, out); }
 
 }  // extern "C"

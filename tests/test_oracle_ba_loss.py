@@ -67,3 +67,35 @@ def test_robust_loss_resists_outliers():
         e = np.hypot(k[:, 0] * u * d + k[:, 1] - p["obs_xy"][clean, 0], k[:, 0] * v * d + k[:, 2] - p["obs_xy"][clean, 1])
         errs[typ] = np.sqrt((e ** 2).mean())
     assert errs[1] < 0.5 * errs[0]        # inlier reprojection RMS: SOFT_L1 ignores the outliers, L2 does not
+
+
+def test_kernel_loss_function_equals_oracle_corrector():
+    """dagsfm_b200/csrc/ba_loss.cuh (what jacobian_kernel<LOSS> applies) compiled for the host, against the
+    oracle's LossEvaluate + Corrector: same rho(s), same scaling sqrt(rho'), and the corrector never leaves
+    its rho'' <= 0 branch for these two losses (alpha = 0), which is what the kernel relies on."""
+    import ctypes
+    import os
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    out = os.path.join(here, "cpp", "_host_ba_loss.so")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.run([cxx, "-O2", "-ffp-contract=off", "-std=c++17", "-shared", "-fPIC", "-o", out,
+                    os.path.join(here, "cpp", "host_ba_loss.cc")], check=True)
+    dev = ctypes.CDLL(out)
+    dp = ctypes.POINTER(ctypes.c_double)
+    dev.host_ba_loss.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_double, dp, dp]
+    dev.host_ba_loss.restype = None
+    f = orc.lib().orc_ba_loss
+    f.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_double, dp, dp, dp, dp]
+    f.restype = None
+    rng = np.random.default_rng(0)
+    for typ in (1, 2):
+        for a in (0.5, 1.0, 2.5):
+            for s in np.r_[0.0, 1e-300, 10.0 ** rng.uniform(-12, 12, 300)]:
+                rho = (ctypes.c_double * 3)()
+                rs, sq, al = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+                f(typ, a, float(s), rho, ctypes.byref(rs), ctypes.byref(sq), ctypes.byref(al))
+                r0, w = ctypes.c_double(), ctypes.c_double()
+                dev.host_ba_loss(typ, a, float(s), ctypes.byref(r0), ctypes.byref(w))
+                assert al.value == 0.0 and rs.value == sq.value          # pure scaling
+                assert r0.value == rho[0] and w.value == sq.value        # bit-identical
