@@ -1,0 +1,387 @@
+// cuda_emu.h -- a small CUDA-on-CPU execution model for the CPU test-suite.  TEST INFRASTRUCTURE ONLY:
+// nothing under dagsfm_b200/ includes it, the product has no CPU path.
+//
+// tests/cuda_emu/build_emu.py rewrites the `kernel<<<grid, block, smem, stream>>>(args)` statements of the
+// library's .cu files into cuda_emu::launch(...) calls and compiles the SAME sources with g++ against
+// this header, so that the kernels (minus the tcgen05 matcher, which has no CPU meaning) and the host
+// code around them can be exercised against the oracle without a GPU.
+//
+// Execution model: blocks run one after the other; the threads of a block are ucontext fibers on the
+// calling OS thread, scheduled round-robin and switched only at synchronisation points
+// (__syncthreads, __syncwarp, warp shuffles / votes), i.e. deterministically.  A fiber that returns
+// simply leaves its barriers (like an exited CUDA thread).  Device memory is host memory.
+#pragma once
+#include <ucontext.h>
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <type_traits>
+#include <vector>
+
+// ------------------------------------------------------------------ qualifiers / built-in types
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __noinline__ /* must stay empty: libstdc++ spells __attribute__((__noinline__)) */
+#define __restrict__
+#define __launch_bounds__(...)
+#define __constant__ static const
+#define __shared__ static
+#define __grid_constant__
+
+struct uint3_emu { unsigned x = 0, y = 0, z = 0; };
+struct dim3 {
+  unsigned x = 1, y = 1, z = 1;
+  dim3() {}
+  dim3(unsigned X, unsigned Y = 1, unsigned Z = 1) : x(X), y(Y), z(Z) {}
+};
+struct double2 { double x, y; };
+struct float2 { float x, y; };
+struct uint4 { unsigned x, y, z, w; };
+struct int4 { int x, y, z, w; };
+inline double2 make_double2(double x, double y) { return double2{x, y}; }
+inline float2 make_float2(float x, float y) { return float2{x, y}; }
+inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
+constexpr int warpSize = 32;
+// CUDA's global-namespace min / max (mixed integer types allowed)
+template <class A, class B> inline typename std::common_type<A, B>::type min(A a, B b) {
+  typedef typename std::common_type<A, B>::type T;
+  return (T)a < (T)b ? (T)a : (T)b;
+}
+template <class A, class B> inline typename std::common_type<A, B>::type max(A a, B b) {
+  typedef typename std::common_type<A, B>::type T;
+  return (T)a > (T)b ? (T)a : (T)b;
+}
+
+namespace cuda_emu {
+
+struct Fiber {
+  ucontext_t ctx;
+  std::vector<char> stack;
+  bool done = false;
+  int wait_kind = 0;  // 0 runnable, 1 waiting at the block barrier, 2 waiting at its warp barrier
+  unsigned tid = 0;
+};
+
+struct BlockState {
+  std::vector<Fiber> fibers;
+  ucontext_t sched;
+  int current = -1;
+  unsigned n_threads = 0;
+  // warp exchange buffers (one 64-bit slot per lane) and arrival counters
+  std::vector<uint64_t> slot;
+  std::vector<int> warp_arrived;
+  int block_arrived = 0;
+  std::function<void()> body;
+};
+
+inline BlockState*& cur() {
+  static thread_local BlockState* b = nullptr;
+  return b;
+}
+struct Idx { uint3_emu threadIdx, blockIdx; dim3 blockDim, gridDim; };
+inline Idx& idx() {
+  static thread_local Idx i;
+  return i;
+}
+inline void*& dyn_smem() {
+  static thread_local void* p = nullptr;
+  return p;
+}
+
+inline void yield_to_scheduler() {
+  BlockState* b = cur();
+  Fiber& f = b->fibers[b->current];
+  swapcontext(&f.ctx, &b->sched);
+}
+inline int alive_in_warp(BlockState* b, unsigned warp) {
+  int n = 0;
+  for (unsigned t = warp * 32; t < std::min(b->n_threads, warp * 32 + 32); ++t) n += b->fibers[t].done ? 0 : 1;
+  return n;
+}
+inline int alive_in_block(BlockState* b) {
+  int n = 0;
+  for (auto& f : b->fibers) n += f.done ? 0 : 1;
+  return n;
+}
+// Blocks the calling fiber until every live fiber of its warp has arrived.
+inline void warp_barrier() {
+  BlockState* b = cur();
+  Fiber& f = b->fibers[b->current];
+  f.wait_kind = 2;
+  b->warp_arrived[f.tid / 32] += 1;
+  yield_to_scheduler();
+}
+inline void block_barrier() {
+  BlockState* b = cur();
+  Fiber& f = b->fibers[b->current];
+  f.wait_kind = 1;
+  b->block_arrived += 1;
+  yield_to_scheduler();
+}
+
+inline void fiber_entry() {
+  BlockState* b = cur();
+  b->body();
+  b->fibers[b->current].done = true;
+  swapcontext(&b->fibers[b->current].ctx, &b->sched);
+}
+
+inline void run_block(BlockState& b, unsigned n_threads, const std::function<void()>& body) {
+  constexpr size_t kStack = 256u << 10;  // the verification kernel keeps several 10 KB of locals
+  b.n_threads = n_threads;
+  b.body = body;
+  if (b.fibers.size() < n_threads) b.fibers.resize(n_threads);
+  b.slot.assign(n_threads, 0);
+  b.warp_arrived.assign((n_threads + 31) / 32, 0);
+  b.block_arrived = 0;
+  cur() = &b;
+  for (unsigned t = 0; t < n_threads; ++t) {
+    Fiber& f = b.fibers[t];
+    if (f.stack.size() != kStack) f.stack.resize(kStack);
+    f.done = false;
+    f.wait_kind = 0;
+    f.tid = t;
+    getcontext(&f.ctx);
+    f.ctx.uc_stack.ss_sp = f.stack.data();
+    f.ctx.uc_stack.ss_size = f.stack.size();
+    f.ctx.uc_link = nullptr;
+    makecontext(&f.ctx, (void (*)())fiber_entry, 0);
+  }
+  for (;;) {
+    bool progressed = false, any_alive = false;
+    for (unsigned t = 0; t < n_threads; ++t) {
+      Fiber& f = b.fibers[t];
+      if (f.done) continue;
+      any_alive = true;
+      if (f.wait_kind != 0) continue;
+      b.current = (int)t;
+      idx().threadIdx.x = t;
+      swapcontext(&b.sched, &f.ctx);
+      progressed = true;
+    }
+    if (!any_alive) break;
+    // release barriers whose live participants have all arrived
+    for (unsigned w = 0; w < b.warp_arrived.size(); ++w) {
+      const int alive = alive_in_warp(&b, w);
+      if (b.warp_arrived[w] > 0 && b.warp_arrived[w] >= alive) {
+        b.warp_arrived[w] = 0;
+        for (unsigned t = w * 32; t < std::min(n_threads, w * 32 + 32); ++t)
+          if (!b.fibers[t].done && b.fibers[t].wait_kind == 2) { b.fibers[t].wait_kind = 0; progressed = true; }
+      }
+    }
+    if (b.block_arrived > 0 && b.block_arrived >= alive_in_block(&b)) {
+      b.block_arrived = 0;
+      for (auto& f : b.fibers)
+        if (!f.done && f.wait_kind == 1) { f.wait_kind = 0; progressed = true; }
+    }
+    if (!progressed) {
+      std::fprintf(stderr, "cuda_emu: deadlock (threads wait at different barriers)\n");
+      std::abort();
+    }
+  }
+  cur() = nullptr;
+}
+
+// kernel launch: blocks sequentially, threads as fibers.  `smem_bytes` backs `extern __shared__`.
+inline void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()>& body) {
+  static thread_local BlockState state;
+  std::vector<uint64_t> smem((smem_bytes + 7) / 8 + 1, 0);
+  dyn_smem() = smem.data();
+  idx().gridDim = grid;
+  idx().blockDim = block;
+  for (unsigned bz = 0; bz < grid.z; ++bz)
+    for (unsigned by = 0; by < grid.y; ++by)
+      for (unsigned bx = 0; bx < grid.x; ++bx) {
+        idx().blockIdx.x = bx; idx().blockIdx.y = by; idx().blockIdx.z = bz;
+        run_block(state, block.x * block.y * block.z, body);
+      }
+  dyn_smem() = nullptr;
+}
+
+}  // namespace cuda_emu
+
+#define threadIdx (cuda_emu::idx().threadIdx)
+#define blockIdx (cuda_emu::idx().blockIdx)
+#define blockDim (cuda_emu::idx().blockDim)
+#define gridDim (cuda_emu::idx().gridDim)
+
+// ------------------------------------------------------------------ synchronisation / warp intrinsics
+inline void __syncthreads() { cuda_emu::block_barrier(); }
+inline void __syncwarp(unsigned = 0xffffffffu) { cuda_emu::warp_barrier(); }
+
+namespace cuda_emu {
+template <class T>
+inline T warp_exchange(T v, int src_lane_of_me) {  // every live lane publishes v, then reads the lane it asks for
+  static_assert(sizeof(T) <= 8, "warp_exchange moves at most 64 bits");
+  BlockState* b = cur();
+  const unsigned tid = b->fibers[b->current].tid;
+  uint64_t bits = 0;
+  std::memcpy(&bits, &v, sizeof(T));
+  b->slot[tid] = bits;
+  warp_barrier();
+  const unsigned base = tid / 32 * 32;
+  unsigned src = base + (unsigned)(src_lane_of_me & 31);
+  if (src >= b->n_threads) src = tid;
+  const uint64_t got = b->slot[src];
+  warp_barrier();  // nobody overwrites its slot before everyone has read
+  T out;
+  std::memcpy(&out, &got, sizeof(T));
+  return out;
+}
+}  // namespace cuda_emu
+
+template <class T> inline T __shfl_sync(unsigned, T v, int src, int = 32) { return cuda_emu::warp_exchange(v, src); }
+template <class T> inline T __shfl_xor_sync(unsigned, T v, int mask, int = 32) {
+  return cuda_emu::warp_exchange(v, (int)(threadIdx.x & 31) ^ mask);
+}
+template <class T> inline T __shfl_up_sync(unsigned, T v, unsigned d, int = 32) {
+  const int lane = (int)(threadIdx.x & 31);
+  return cuda_emu::warp_exchange(v, lane >= (int)d ? lane - (int)d : lane);
+}
+template <class T> inline T __shfl_down_sync(unsigned, T v, unsigned d, int = 32) {
+  const int lane = (int)(threadIdx.x & 31);
+  return cuda_emu::warp_exchange(v, lane + (int)d < 32 ? lane + (int)d : lane);
+}
+inline unsigned __ballot_sync(unsigned, int pred) {
+  cuda_emu::BlockState* b = cuda_emu::cur();
+  const unsigned tid = b->fibers[b->current].tid;
+  b->slot[tid] = pred ? 1u : 0u;
+  cuda_emu::warp_barrier();
+  unsigned m = 0;
+  const unsigned base = tid / 32 * 32;
+  for (unsigned l = 0; l < 32 && base + l < b->n_threads; ++l)
+    if (!b->fibers[base + l].done && b->slot[base + l]) m |= 1u << l;
+  cuda_emu::warp_barrier();
+  return m;
+}
+inline int __any_sync(unsigned m, int p) { return __ballot_sync(m, p) != 0; }
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __ffs(int v) { return __builtin_ffs(v); }
+inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
+inline long long clock64() { return 0; }
+template <class T> inline T __ldg(const T* p) { return *p; }
+inline long long __double_as_longlong(double d) { long long r; std::memcpy(&r, &d, 8); return r; }
+inline double __longlong_as_double(long long v) { double r; std::memcpy(&r, &v, 8); return r; }
+inline unsigned __dp4a(unsigned a, unsigned b, unsigned c) {
+  for (int q = 0; q < 4; ++q) c += ((a >> (8 * q)) & 255u) * ((b >> (8 * q)) & 255u);
+  return c;
+}
+inline int __dp4a(int a, int b, int c) {
+  for (int q = 0; q < 4; ++q) c += (int)(signed char)((a >> (8 * q)) & 255) * (int)(signed char)((b >> (8 * q)) & 255);
+  return c;
+}
+
+// ------------------------------------------------------------------ atomics (fibers of one OS thread: plain RMW;
+// std::atomic_ref keeps them correct should blocks ever run on several OS threads)
+template <class T> inline T atomicAdd(T* p, T v) { T old = *p; *p = old + v; return old; }
+inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { auto o = *p; *p = o + v; return o; }
+inline unsigned atomicAdd(unsigned* p, int v) { auto o = *p; *p = o + (unsigned)v; return o; }
+template <class T> inline T atomicMax(T* p, T v) { T old = *p; if (v > old) *p = v; return old; }
+template <class T> inline T atomicMin(T* p, T v) { T old = *p; if (v < old) *p = v; return old; }
+template <class T> inline T atomicExch(T* p, T v) { T old = *p; *p = v; return old; }
+template <class T> inline T atomicCAS(T* p, T cmp, T v) { T old = *p; if (old == cmp) *p = v; return old; }
+
+// ------------------------------------------------------------------ runtime API (device memory = host memory)
+typedef int cudaError_t;
+constexpr cudaError_t cudaSuccess = 0;
+typedef struct emu_stream_* cudaStream_t;
+struct emu_event_ { std::chrono::steady_clock::time_point t; };
+typedef emu_event_* cudaEvent_t;
+enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
+constexpr unsigned cudaStreamNonBlocking = 1;
+constexpr int cudaFuncAttributeMaxDynamicSharedMemorySize = 8;
+struct cudaDeviceProp { int major = 10, minor = 0, multiProcessorCount = 2; char name[64] = "cuda_emu"; size_t totalGlobalMem = (size_t)64 << 30; };
+
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+inline cudaError_t cudaPeekAtLastError() { return cudaSuccess; }
+inline const char* cudaGetErrorString(cudaError_t) { return "cuda_emu: no error"; }
+inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) { *p = cudaDeviceProp(); return cudaSuccess; }
+inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+template <class T> inline cudaError_t cudaMalloc(T** p, size_t n) { *p = (T*)std::calloc(std::max<size_t>(n, 1), 1); return *p ? cudaSuccess : 2; }
+inline cudaError_t cudaFree(void* p) { std::free(p); return cudaSuccess; }
+inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { if (n) std::memmove(d, s, n); return cudaSuccess; }
+inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind k, cudaStream_t = nullptr) { return cudaMemcpy(d, s, n, k); }
+inline cudaError_t cudaMemset(void* d, int v, size_t n) { if (n) std::memset(d, v, n); return cudaSuccess; }
+inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = nullptr) { return cudaMemset(d, v, n); }
+inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = nullptr; return cudaSuccess; }
+inline cudaError_t cudaStreamCreate(cudaStream_t* s) { *s = nullptr; return cudaSuccess; }
+inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new emu_event_(); return cudaSuccess; }
+inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
+inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr) { e->t = std::chrono::steady_clock::now(); return cudaSuccess; }
+inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) {
+  *ms = std::max(1e-3f, std::chrono::duration<float, std::milli>(b->t - a->t).count());
+  return cudaSuccess;
+}
+inline cudaError_t cudaMemGetInfo(size_t* f, size_t* t) { *f = *t = (size_t)64 << 30; return cudaSuccess; }
+template <class F> inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
+
+// ------------------------------------------------------------------ cuSOLVER dense Cholesky (column-major, 64-bit API)
+typedef struct emu_solver_* cusolverDnHandle_t;
+typedef struct emu_params_* cusolverDnParams_t;
+typedef int cusolverStatus_t;
+constexpr cusolverStatus_t CUSOLVER_STATUS_SUCCESS = 0;
+enum cublasFillMode_t { CUBLAS_FILL_MODE_LOWER = 0, CUBLAS_FILL_MODE_UPPER = 1 };
+enum cudaDataType { CUDA_R_64F = 1 };
+inline cusolverStatus_t cusolverDnCreate(cusolverDnHandle_t* h) { *h = nullptr; return 0; }
+inline cusolverStatus_t cusolverDnDestroy(cusolverDnHandle_t) { return 0; }
+inline cusolverStatus_t cusolverDnSetStream(cusolverDnHandle_t, cudaStream_t) { return 0; }
+inline cusolverStatus_t cusolverDnCreateParams(cusolverDnParams_t* p) { *p = nullptr; return 0; }
+inline cusolverStatus_t cusolverDnDestroyParams(cusolverDnParams_t) { return 0; }
+inline cusolverStatus_t cusolverDnXpotrf_bufferSize(cusolverDnHandle_t, cusolverDnParams_t, cublasFillMode_t, int64_t, cudaDataType,
+                                                    const void*, int64_t, cudaDataType, size_t* dev, size_t* host) {
+  *dev = 8; *host = 8; return 0;
+}
+// A = L L^T, lower triangle of a column-major n x n matrix, in place; info = 0 or the failing column (1-based).
+inline cusolverStatus_t cusolverDnXpotrf(cusolverDnHandle_t, cusolverDnParams_t, cublasFillMode_t uplo, int64_t n, cudaDataType,
+                                         void* Av, int64_t lda, cudaDataType, void*, size_t, void*, size_t, int* info) {
+  double* A = (double*)Av;
+  *info = 0;
+  if (uplo != CUBLAS_FILL_MODE_LOWER) return 1;
+  for (int64_t j = 0; j < n; ++j) {
+    double d = A[j + j * lda];
+    for (int64_t k = 0; k < j; ++k) d -= A[j + k * lda] * A[j + k * lda];
+    if (!(d > 0)) { *info = (int)(j + 1); return 0; }
+    d = std::sqrt(d);
+    A[j + j * lda] = d;
+    for (int64_t i = j + 1; i < n; ++i) {
+      double s = A[i + j * lda];
+      for (int64_t k = 0; k < j; ++k) s -= A[i + k * lda] * A[j + k * lda];
+      A[i + j * lda] = s / d;
+    }
+  }
+  return 0;
+}
+inline cusolverStatus_t cusolverDnXpotrs(cusolverDnHandle_t, cusolverDnParams_t, cublasFillMode_t, int64_t n, int64_t nrhs, cudaDataType,
+                                         const void* Av, int64_t lda, cudaDataType, void* Bv, int64_t ldb, int* info) {
+  const double* A = (const double*)Av;
+  double* B = (double*)Bv;
+  *info = 0;
+  for (int64_t r = 0; r < nrhs; ++r) {
+    double* b = B + r * ldb;
+    for (int64_t i = 0; i < n; ++i) {
+      double s = b[i];
+      for (int64_t k = 0; k < i; ++k) s -= A[i + k * lda] * b[k];
+      b[i] = s / A[i + i * lda];
+    }
+    for (int64_t i = n - 1; i >= 0; --i) {
+      double s = b[i];
+      for (int64_t k = i + 1; k < n; ++k) s -= A[k + i * lda] * b[k];
+      b[i] = s / A[i + i * lda];
+    }
+  }
+  return 0;
+}

@@ -1,0 +1,140 @@
+"""The matcher's host code and CUDA-core kernels (match_api.cu, match_post.cu, match_guided.cu) compiled for
+the HOST against tests/cuda_emu/cuda_emu.h.  The two tcgen05 kernels have no CPU meaning; their place is
+taken by tests/cuda_emu/match_tc_emu.cc, which produces what they are contracted to produce (best dot,
+first 32-column chunk attaining it, best other-chunk maximum, candidate list).  Everything downstream --
+items, fix-up (exact index + in-chunk second-best), cross-check, ordered compaction, chunking of long
+pair lists, the two-slot seam, and the whole guided path -- is the real code, checked index-for-index
+against the oracle.  TEST of the CUDA sources; the product library is not involved."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as orc
+from tests.test_host_guided import _inlier_pairs, _scene_with_descriptors
+
+
+@pytest.fixture(scope="module")
+def mm():
+    from tests.cuda_emu.build_emu import HERE, build
+    import dagsfm_b200._lib as lm
+    import dagsfm_b200.matching as mt
+    L = C.CDLL(str(build("match", ["common.cu", "match_post.cu", "match_guided.cu", "match_api.cu"],
+                         extra=[str(HERE / "match_tc_emu.cc")])))
+    saved = (lm._lib, mt.check)
+    lm._lib = None
+    real_path = lm.LIB_PATH
+    lm.LIB_PATH = type(real_path)(L._name)          # lib() binds the argtypes of the C ABI on the emulated library
+    L2 = lm.lib()
+
+    def check(rc):
+        if rc != 0:
+            raise RuntimeError(f"emulated library error {rc}: {L2.b2_last_error().decode()}")
+    mt.check = check
+    yield mt
+    lm._lib, lm.LIB_PATH, mt.check = None, real_path, saved[1]
+
+
+def test_reference_cpu_vs_gpu_cases(mm):
+    # sift_test.cc:496-557 through the two-slot seam (SetDescriptors / GetSiftMatch)
+    gpu = mm.SiftMatchGPU(0)
+    try:
+        def both(o, d1, d2):
+            exp = orc.match_sift(d1, d2, max_ratio=o.max_ratio, max_distance=o.max_distance, cross_check=o.cross_check)
+            got = mm.match_sift_features_gpu(o, d1, d2, gpu)
+            assert got.tolist() == exp.tolist()
+            return len(exp)
+        d1 = orc.create_random_descriptors(100)
+        assert both(mm.SiftMatchingOptions(), d1, d1[::-1].copy()) == 100
+        d2 = d1.copy()
+        d2[99] = d2[0]
+        r = d2[0].astype(np.float32); r[0] += 50.0; d2[0] = orc.l2_normalize_to_u8(r)
+        r = d2[99].astype(np.float32); r[0] += 100.0; d2[99] = orc.l2_normalize_to_u8(r)
+        assert both(mm.SiftMatchingOptions(max_ratio=0.4), d1[:99], d2) == 98
+        assert both(mm.SiftMatchingOptions(max_ratio=0.5), d1, d2) == 99
+        d1 = orc.create_random_descriptors(100); d2 = d1.copy(); d1[0] = d1[1]
+        assert both(mm.SiftMatchingOptions(cross_check=False), d1, d2) == 100
+        assert both(mm.SiftMatchingOptions(cross_check=True), d1, d2) == 98
+        e = np.zeros((0, 128), np.uint8)
+        assert len(mm.match_sift_features_gpu(mm.SiftMatchingOptions(), e, d2, gpu)) == 0
+        # None keeps the previous upload of that slot (sift.h:232-234): slot 1 still holds d2
+        assert mm.match_sift_features_gpu(mm.SiftMatchingOptions(), d1, None, gpu).tolist() == orc.match_sift(d1, d2).tolist()
+    finally:
+        gpu.close()
+
+
+def test_batched_pairs_ragged_and_chunked(mm, monkeypatch):
+    monkeypatch.setenv("B2_MATCH_ROW_BUDGET", "65536")        # forces several chunks of pairs per call
+    rng = np.random.default_rng(3)
+    sizes = [300, 17, 0, 257, 64, 511]
+    base = orc.create_random_descriptors(600, seed=4)
+    descs = []
+    for n in sizes:
+        d = base[rng.permutation(600)[:n]].copy() if n else np.zeros((0, 128), np.uint8)
+        descs.append(d)
+    pairs = [(i, j) for i in range(len(sizes)) for j in range(len(sizes)) if i != j]
+    gpu = mm.SiftMatchGPU(0)
+    try:
+        gpu.set_images(descs)
+        for o in (mm.SiftMatchingOptions(), mm.SiftMatchingOptions(cross_check=False, max_ratio=0.95, max_distance=1.3)):
+            off, m = gpu.match_pairs(pairs, o)
+            for p, (i, j) in enumerate(pairs):
+                exp = orc.match_sift(descs[i], descs[j], max_ratio=o.max_ratio, max_distance=o.max_distance,
+                                     cross_check=o.cross_check)
+                assert m[off[p]:off[p + 1]].tolist() == exp.tolist(), (p, i, j)
+        with pytest.raises(RuntimeError):
+            gpu.match_pairs([(0, 99)], mm.SiftMatchingOptions())
+    finally:
+        gpu.close()
+
+
+def test_ties_and_duplicates(mm):
+    d = orc.create_random_descriptors(40, seed=9)
+    a = np.r_[d, d[:5]]                  # duplicated rows: ties for best -> the lowest index wins, ratio test fails
+    b = np.r_[d[::-1], d[:3]].copy()
+    gpu = mm.SiftMatchGPU(0)
+    try:
+        gpu.set_images([a, b])
+        for cc in (True, False):
+            o = mm.SiftMatchingOptions(cross_check=cc)
+            off, m = gpu.match_pairs([(0, 1), (1, 0)], o)
+            assert m[off[0]:off[1]].tolist() == orc.match_sift(a, b, cross_check=cc).tolist()
+            assert m[off[1]:off[2]].tolist() == orc.match_sift(b, a, cross_check=cc).tolist()
+    finally:
+        gpu.close()
+
+
+def test_guided_pairs_through_the_c_abi(mm):
+    rng = np.random.default_rng(11)
+    kps, descs, pairs, geos = [], [], [], []
+    for k in range(4):
+        planar = k % 2 == 1
+        k1, k2, d1, d2 = _scene_with_descriptors(rng, 150 + 60 * k, 60 + 30 * k, planar)
+        a, b = _inlier_pairs(k1, k2, d1, d2)
+        geos.append((4 + k, None, orc.h_dlt(a, b)) if planar else (2 + k // 2, orc.eight_point(a, b), None))
+        kps += [k1, k2]; descs += [d1, d2]; pairs.append((2 * k, 2 * k + 1))
+    pairs += [(0, 1), (3, 2)]
+    geos += [(0, None, None), geos[1]]
+    gpu = mm.SiftMatchGPU(0)
+    try:
+        gpu.set_images(descs)
+        with pytest.raises(RuntimeError):                      # keypoints are mandatory for the guided path
+            gpu.match_guided_pairs(pairs, geos, mm.SiftMatchingOptions())
+        with pytest.raises(RuntimeError):                      # and must match the descriptor counts (sift.cc:82-87)
+            gpu.set_keypoints([k[:-1] for k in kps])
+        gpu.set_keypoints(kps)
+        for o in (mm.SiftMatchingOptions(), mm.SiftMatchingOptions(cross_check=False, max_error=2.0)):
+            off, m = gpu.match_guided_pairs(pairs, geos, o)
+            for p, ((i, j), (cfg, F, H)) in enumerate(zip(pairs, geos)):
+                e = orc.match_guided(kps[i], kps[j], descs[i], descs[j], cfg, F=F, H=H, max_error=o.max_error,
+                                     max_ratio=o.max_ratio, max_distance=o.max_distance, cross_check=o.cross_check)
+                assert m[off[p]:off[p + 1]].tolist() == ([] if e is None else e.tolist()), (p, cfg)
+        # guided and unguided share the object: the plain matcher still works afterwards
+        off2, m2 = gpu.match_pairs(pairs[:1], mm.SiftMatchingOptions())
+        assert m2[off2[0]:off2[1]].tolist() == orc.match_sift(descs[0], descs[1]).tolist()
+        one = mm.match_guided_sift_features_gpu(mm.SiftMatchingOptions(), kps[0], kps[1], descs[0], descs[1], gpu,
+                                                geos[0][0], F=geos[0][1])
+        assert one.tolist() == orc.match_guided(kps[0], kps[1], descs[0], descs[1], geos[0][0], F=geos[0][1]).tolist()
+    finally:
+        gpu.close()

@@ -1,0 +1,137 @@
+"""The two-view verification CUDA sources (verify_kernel.cu, verify_solvers.cuh, verify_api.cu) compiled for the
+HOST against tests/cuda_emu/cuda_emu.h (warps as groups of fibers, shuffles / ballots / __syncwarp emulated)
+and driven through the C ABI: the same checks as tests/test_verify_gpu.py at small sizes, without a GPU.
+TEST of the CUDA code -- the product library is not involved."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as orc
+from tests.tv_scene import scene
+
+
+@pytest.fixture(scope="module")
+def ver():
+    from tests.cuda_emu.build_emu import build
+    import dagsfm_b200.verification as vm
+    L = C.CDLL(str(build("verify", ["common.cu", "verify_kernel.cu", "verify_api.cu"])))
+    L.b2_last_error.restype = C.c_char_p
+    saved = (vm._L, vm.check, vm._bound)
+    vm._bound = False
+    real_lib = vm.lib
+
+    def check(rc):
+        if rc != 0:
+            raise RuntimeError(f"emulated library error {rc}: {L.b2_last_error().decode()}")
+    vm.lib = lambda: L            # _L() binds argtypes on whatever lib() returns
+    vm.check = check
+    v = vm.TwoViewGeometryVerifier(0)
+    yield v
+    v.close()
+    vm.lib, vm.check, vm._bound = real_lib, saved[1], False
+
+
+@pytest.mark.parametrize("total,k", [(50, 7), (7, 7), (200, 5), (33, 4), (20, 1)])
+def test_sample_stream_bit_exact(ver, total, k):
+    for seed in (0, 12345):
+        assert (ver.debug_sample_stream(seed, total, k, 40) == orc.sample_stream(seed, total, k, 40)).all()
+
+
+def _match(got, exp, tol):
+    assert len(got) == len(exp)
+    for g, e in zip(got, exp):
+        assert min(np.abs(g - e).max(), np.abs(g + e).max()) < tol * max(1.0, np.abs(e).max())
+
+
+def test_minimal_and_local_solvers(ver):
+    rng = np.random.default_rng(0)
+    for it in range(4):
+        p1, p2 = scene(rng, 40, 0, noise=0.5)
+        _match(ver.debug_solve(1, p1[:7], p2[:7]), orc.f7(p1[:7], p2[:7]), 1e-7)
+        _match(ver.debug_solve(2, p1[:4], p2[:4]), [orc.h_dlt(p1[:4], p2[:4])], 1e-7)
+        n1, n2 = (p1 - 500) / 1200, (p2 - 500) / 1200
+        _match(ver.debug_solve(0, n1[:5], n2[:5]), orc.e5(n1[:5], n2[:5]), 1e-6)
+        _match(ver.debug_solve(3, p1, p2), [orc.eight_point(p1, p2)], 1e-7)          # warp QR + Jacobi on R
+        _match(ver.debug_solve(2, p1, p2), [orc.h_dlt(p1, p2)], 1e-7)
+        _match(ver.debug_solve(0, n1, n2), orc.e5(n1, n2), 1e-5)
+
+
+def test_score_models_bit_exact(ver):
+    rng = np.random.default_rng(2)
+    p1, p2 = scene(rng, 70, 30, noise=1.0)
+    F = orc.eight_point(p1[:70], p2[:70])
+    for typ, models, thr in ((1, np.stack([F, F * 3.0, rng.normal(size=(3, 3))]), 16.0),
+                             (2, np.stack([orc.h_dlt(p1[:30], p2[:30]), np.eye(3)]), 16.0)):
+        counts, sums, masks = ver.score_models(typ, p1, p2, models, thr)
+        for k, M in enumerate(models):
+            r = orc.residuals(typ, p1, p2, M)
+            m = r <= thr
+            s = 0.0
+            for v in r[m]:
+                s += v
+            assert counts[k] == m.sum() and (masks[k] == m).all() and sums[k] == s
+
+
+def test_two_view_decisions_equal_oracle(ver):
+    from dagsfm_b200 import Camera, TwoViewOptions
+    rng = np.random.default_rng(9)
+    specs = [(60, 12, False, True), (50, 10, True, False), (48, 20, False, False), (9, 0, False, True)]
+    cams, kps, pairs, offs, ms, priors = [], [], [], [0], [], []
+    for i, (n_in, n_out, planar, prior) in enumerate(specs):
+        p1, p2 = scene(rng, n_in, n_out, planar=planar, noise=0.3)
+        perm = np.random.default_rng(100 + i).permutation(len(p2))
+        kps += [p1, p2[perm]]
+        ms.append(np.stack([np.arange(len(p1)), np.argsort(perm)], 1))
+        cams += [Camera.make(prior_focal=prior), Camera.make(prior_focal=prior)]
+        priors.append(prior)
+        pairs.append((2 * i, 2 * i + 1))
+        offs.append(offs[-1] + len(p1))
+    ver.set_images(cams, kps)
+    seeds = np.arange(len(specs), dtype=np.uint32) + 77
+    opt = TwoViewOptions.default()
+    opt.max_num_trials = 300          # keep the emulated H-RANSAC of the non-planar pairs short
+    oopt = orc.tv_default_options()
+    oopt.max_num_trials = 300
+    res, inl = ver.verify_pairs(pairs, offs, np.concatenate(ms), opt, seeds)
+    cfgs = []
+    for i in range(len(specs)):
+        c = orc.make_camera(prior=priors[i])
+        r, oi = orc.two_view(c, kps[2 * i], c, kps[2 * i + 1], ms[i], oopt, seed=int(seeds[i]))
+        g = res[i]
+        assert (g["config"], g["n_inliers"], g["E_num_inliers"], g["F_num_inliers"], g["H_num_inliers"]) == \
+               (r.config, r.n_inliers, r.E_inl, r.F_inl, r.H_inl), i
+        assert (g["E_num_trials"], g["F_num_trials"], g["H_num_trials"]) == (r.E_trials, r.F_trials, r.H_trials)
+        assert inl[offs[i]:offs[i] + r.n_inliers].tolist() == oi.tolist()
+        cfgs.append(int(g["config"]))
+    assert cfgs[3] == 1 and 6 in cfgs and (2 in cfgs or 3 in cfgs)
+
+
+def test_estimate_multiple_through_the_c_abi(ver):
+    """b2_verify_pairs_multiple (rounds of the batched Estimate, verify_multiple.h) on the emulated kernel."""
+    from dagsfm_b200 import Camera, TwoViewOptions
+    from tests.test_host_multiple import two_motion_pair
+    rng = np.random.default_rng(3)
+    kps, pairs, offs, ms = [], [], [0], []
+    for k, (na, nb, no) in enumerate([(60, 50, 10), (70, 0, 20), (10, 0, 0)]):
+        if nb:
+            p1, p2, m = two_motion_pair(rng, na, nb, no)
+        else:
+            p1, p2 = scene(rng, na, no, noise=0.3)
+            m = np.stack([np.arange(len(p1))] * 2, 1).astype(np.uint32)
+        kps += [p1, p2]; pairs.append((2 * k, 2 * k + 1)); ms.append(m); offs.append(offs[-1] + len(m))
+    ver.set_images([Camera.make(prior_focal=False)] * len(kps), kps)
+    seeds = np.arange(3, dtype=np.uint32) + 40
+    opt = TwoViewOptions.default()
+    opt.max_num_trials = 300
+    oopt = orc.tv_default_options()
+    oopt.max_num_trials = 300
+    res, inl = ver.verify_pairs_multiple(pairs, offs, np.concatenate(ms), opt, seeds)
+    cam = orc.make_camera(prior=False)
+    cfgs = []
+    for k, (i, j) in enumerate(pairs):
+        cfg, geos, exp_inl = orc.two_view_multiple(cam, kps[i], cam, kps[j], ms[k], oopt, seed=int(seeds[k]))
+        cfgs.append(cfg)
+        assert res["config"][k] == cfg and res["n_inliers"][k] == len(exp_inl)
+        assert inl[offs[k]:offs[k] + len(exp_inl)].tolist() == exp_inl.tolist()
+    assert cfgs[0] == 8 and cfgs[2] == 1
