@@ -22,6 +22,10 @@
 
 using namespace b2;
 
+namespace b2 {  // exclusive scan kernel shared with the matcher (match_post.cu)
+cudaError_t launch_scan_u32(const uint32_t* in, int64_t n, uint32_t* out, uint32_t* total, cudaStream_t s);
+}
+
 struct b2_ba {
   int device = 0;
   int n_sm = 148;
@@ -233,6 +237,39 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
   B2_CUDA(ba_launch_jacobian(P, P.qvec, P.tvec, P.cam_params, P.xyz, 0, scal + 6, s, loss_type, loss_scale));
   count_launches(1);
 
+  // Experimental pair-major Schur accumulation (B2_BA_SCHUR=blocks): the (lo, hi) observation tuples of
+  // every (image, image) block are gathered once -- the structure is fixed across LM iterations --
+  // by a counting sort on the device; per iteration the point-major kernel then only stores W / Y
+  // per observation and pm_blocks_kernel sums each block before touching S.  Default: the
+  // production kernel with per-tuple atomics.
+  bool pair_major = false;
+  uint32_t *pm_count = nullptr, *pm_start = nullptr;
+  uint64_t* pm_tuples = nullptr;
+  double *pm_W = nullptr, *pm_Y = nullptr;
+  if (const char* e = getenv("B2_BA_SCHUR")) pair_major = strcmp(e, "blocks") == 0 && n_img > 0 && n_img <= 4096 && n_obs > 0;
+  if (pair_major) {
+    uint64_t n_tuples = 0;
+    for (int p = 0; p < n_pts; ++p) {
+      const uint64_t L = (uint64_t)(pt_start[p + 1] - pt_start[p]);
+      if (pt_col[p] >= 0) n_tuples += L * (L + 1) / 2;
+    }
+    if (n_tuples == 0 || n_tuples >= 0xFFFFFFF0ull) pair_major = false;
+    if (pair_major) {
+      const int64_t n_keys = (int64_t)n_img * n_img;
+      B2_TRY(dev_alloc(h, &pm_count, (size_t)n_keys));
+      B2_TRY(dev_alloc(h, &pm_start, (size_t)n_keys + 1));
+      B2_TRY(dev_alloc(h, &pm_tuples, (size_t)n_tuples));
+      B2_TRY(dev_alloc(h, &pm_W, (size_t)n_obs * 30));
+      B2_TRY(dev_alloc(h, &pm_Y, (size_t)n_obs * 30));
+      B2_CUDA(cudaMemsetAsync(pm_count, 0, (size_t)n_keys * sizeof(uint32_t), s));
+      B2_CUDA(ba_launch_pm_enumerate(P, n_img, false, pm_count, nullptr, nullptr, h->n_sm, s));
+      B2_CUDA(launch_scan_u32(pm_count, n_keys, pm_start, pm_start + n_keys, s));
+      B2_CUDA(cudaMemsetAsync(pm_count, 0, (size_t)n_keys * sizeof(uint32_t), s));
+      B2_CUDA(ba_launch_pm_enumerate(P, n_img, true, pm_count, pm_start, pm_tuples, h->n_sm, s));
+      count_launches(3);
+    }
+  }
+
   double radius = 1e4, decrease_factor = 2.0;
   const double min_radius = 1e-32, max_radius = 1e16, min_rel_dec = 1e-3, min_diag = 1e-6, max_diag = 1e32;
   double schur_ms = 0;
@@ -244,7 +281,10 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
     B2_CUDA(cudaMemsetAsync(scal + 7, 0, 8, s));
     B2_CUDA(cudaEventRecord(h->ev[2], s));
     B2_CUDA(ba_launch_camera_terms(P, s));
-    B2_CUDA(ba_launch_schur(P, radius, min_diag, max_diag, h->n_sm, s));
+    if (pair_major)
+      B2_CUDA(ba_launch_schur_pm(P, radius, min_diag, max_diag, n_img, pm_start, pm_tuples, pm_W, pm_Y, h->n_sm, s));
+    else
+      B2_CUDA(ba_launch_schur(P, radius, min_diag, max_diag, h->n_sm, s));
     B2_CUDA(cudaEventRecord(h->ev[3], s));
     schur_launches += 2;
     B2_TRY(sync_reduce(h, reduced, (int64_t)n_reduced, 0));  // the one NVLink all-reduce of (S, rhs, g_c, diag)

@@ -47,6 +47,11 @@ cudaError_t ba_launch_jacobian(const BaDev& P, const double* q, const double* t,
                                int mode, double* cost_out, cudaStream_t s, int loss_type = 0, double loss_scale = 1.0);
 cudaError_t ba_launch_camera_terms(const BaDev& P, cudaStream_t s);
 cudaError_t ba_launch_schur(const BaDev& P, double radius, double min_diag, double max_diag, int n_sm, cudaStream_t s);
+cudaError_t ba_launch_pm_enumerate(const BaDev& P, int n_img, bool fill, uint32_t* count_or_cursor, const uint32_t* start,
+                                   void* tuples, int n_sm, cudaStream_t s);
+cudaError_t ba_launch_schur_pm(const BaDev& P, double radius, double min_diag, double max_diag, int n_img,
+                               const uint32_t* start, const void* tuples, double* Wg, double* Yg, int n_sm,
+                               cudaStream_t s);
 cudaError_t ba_launch_add_diag(const BaDev& P, double radius, double min_diag, double max_diag, cudaStream_t s);
 cudaError_t ba_launch_backsub(const BaDev& P, cudaStream_t s);
 cudaError_t ba_launch_model_cost(const BaDev& P, double* out, cudaStream_t s);

@@ -226,7 +226,13 @@ __global__ void __launch_bounds__(256) camera_terms_kernel(BaDev P) {
 constexpr int kTile = 32;
 constexpr int kSchurThreads = 128;
 
-__global__ void __launch_bounds__(kSchurThreads) schur_kernel(BaDev P, double radius, double min_diag, double max_diag) {
+// PM (pair-major variant, B2_BA_SCHUR=blocks): the kernel stops after W_a / Y_a, stores them per
+// observation (Wg, Yg: [n_obs][30]) and leaves S -= Y_a W_b^T to pm_blocks_kernel, which sums the
+// contributions of one (image, image) block over all points before touching S.  PM == false is the
+// production kernel, unchanged.
+template <bool PM>
+__global__ void __launch_bounds__(kSchurThreads) schur_kernel(BaDev P, double radius, double min_diag, double max_diag,
+                                                              double* __restrict__ Wg, double* __restrict__ Yg) {
   __shared__ double sWa[kTile][30], sYa[kTile][30], sWb[kTile][30];
   __shared__ int sCa[kTile][10], sCb[kTile][10];
   __shared__ double sV[9], sT[3], sG[3];
@@ -300,7 +306,15 @@ __global__ void __launch_bounds__(kSchurThreads) schur_kernel(BaDev P, double ra
           sYa[a][3 * k + l] = w[0] * sV[l] + w[1] * sV[3 + l] + w[2] * sV[6 + l];
         }
         if (col >= 0) atomicAdd(P.rhs + col, -(w[0] * sT[0] + w[1] * sT[1] + w[2] * sT[2]));
+        if (PM) {
+#pragma unroll
+          for (int l = 0; l < 3; ++l) {
+            Wg[(o0 + a0 + a) * 30 + 3 * k + l] = w[l];
+            Yg[(o0 + a0 + a) * 30 + 3 * k + l] = w[0] * sV[l] + w[1] * sV[3 + l] + w[2] * sV[6 + l];
+          }
+        }
       }
+      if (PM) continue;
       __syncthreads();
       // Unordered observation pairs a <= b only: Y_a W_b^T and Y_b W_a^T are transposes of each other
       // (V^-1 is symmetric), so every entry of the block is written once, at (min col, max col) --
@@ -343,6 +357,105 @@ __global__ void __launch_bounds__(kSchurThreads) schur_kernel(BaDev P, double ra
         }
         __syncthreads();
       }
+    }
+    if (PM) __syncthreads();  // sV / sT are rewritten by warp 0 for the next point
+  }
+}
+
+// ------------------------------------------------------------ pair-major Schur (experimental)
+// The observation pairs (a <= b) of every variable point, keyed by their (image, image) block with
+// the smaller image index first.  FILL == false counts the tuples of each block, FILL == true writes
+// them behind the block's start offset (counting sort; the order inside a block is arbitrary).  The
+// structure does not change across LM iterations, so both run once per solve.  One warp per point.
+template <bool FILL>
+__global__ void __launch_bounds__(256)
+pm_enumerate_kernel(BaDev P, int n_img, uint32_t* __restrict__ count_or_cursor, const uint32_t* __restrict__ start,
+                    int2* __restrict__ tuples) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t p = warp0; p < P.n_pts; p += n_warps) {
+    if (P.pt_col[p] < 0) continue;
+    const int64_t o0 = P.pt_start[p];
+    const int L = (int)(P.pt_start[p + 1] - o0);
+    for (int a = 0; a < L; ++a) {
+      const int ia = P.obs_img[o0 + a];
+      for (int b = a + lane; b < L; b += 32) {
+        const int ib = P.obs_img[o0 + b];
+        const bool swap = ib < ia;
+        const int lo_img = swap ? ib : ia, hi_img = swap ? ia : ib;
+        const int lo_obs = (int)(o0 + (swap ? b : a)), hi_obs = (int)(o0 + (swap ? a : b));
+        const int64_t key = (int64_t)lo_img * n_img + hi_img;
+        const uint32_t pos = atomicAdd(count_or_cursor + key, 1u);
+        if (FILL) tuples[start[key] + pos] = make_int2(lo_obs, hi_obs);
+      }
+    }
+  }
+}
+
+// One warp per (image i <= image j) block: B = sum over the block's tuples of Y_lo W_hi^T (10 x 10, lane
+// e owns entries e, e + 32, e + 64, e + 96), then one atomicAdd per entry into S instead of one per tuple
+// and entry.  Same-image blocks are symmetric: a tuple of two different observations of one image adds
+// its transpose too, and only the upper entries are written.  Different images that share a camera:
+// the intrinsics entries (k, l) and (l, k) land on the same upper slot, the diagonal ones are doubled
+// (their (hi, lo) counterpart is not enumerated) -- as in schur_kernel's pair loop.
+__global__ void __launch_bounds__(256)
+pm_blocks_kernel(BaDev P, int n_img, const uint32_t* __restrict__ start, const int2* __restrict__ tuples,
+                 const double* __restrict__ Wg, const double* __restrict__ Yg) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t n_keys = (int64_t)n_img * n_img;
+  const int64_t D = P.D;
+  int kk[4], ll[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int e = lane + 32 * u;
+    kk[u] = e / 10;
+    ll[u] = e - 10 * kk[u];
+  }
+  for (int64_t key = warp0; key < n_keys; key += n_warps) {
+    const uint32_t t0 = start[key], t1 = start[key + 1];
+    if (t0 == t1) continue;
+    const int i = (int)(key / n_img), j = (int)(key - (int64_t)i * n_img);
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (uint32_t t = t0; t < t1; ++t) {
+      const int2 tp = tuples[t];
+      const double* y = Yg + (int64_t)tp.x * 30;
+      const double* w = Wg + (int64_t)tp.y * 30;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (lane + 32 * u >= 100) continue;
+        const int k = kk[u], l = ll[u];
+        acc[u] += y[3 * k] * w[3 * l] + y[3 * k + 1] * w[3 * l + 1] + y[3 * k + 2] * w[3 * l + 2];
+      }
+      if (i == j && tp.x != tp.y) {
+        const double* y2 = Yg + (int64_t)tp.y * 30;
+        const double* w2 = Wg + (int64_t)tp.x * 30;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (lane + 32 * u >= 100) continue;
+          const int k = kk[u], l = ll[u];
+          acc[u] += y2[3 * k] * w2[3 * l] + y2[3 * k + 1] * w2[3 * l + 1] + y2[3 * k + 2] * w2[3 * l + 2];
+        }
+      }
+    }
+    const int cam_i = P.img_cam[i], cam_j = P.img_cam[j];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (lane + 32 * u >= 100) continue;
+      const int k = kk[u], l = ll[u];
+      const int ca = (k < 6) ? P.pose_col[6 * i + k] : P.intr_col[4 * cam_i + (k - 6)];
+      const int cb = (l < 6) ? P.pose_col[6 * j + l] : P.intr_col[4 * cam_j + (l - 6)];
+      if (ca < 0 || cb < 0) continue;
+      double v = acc[u];
+      if (i == j) {
+        if (ca > cb) continue;
+      } else if (ca == cb) {
+        v = v + v;
+      }
+      const int r = min(ca, cb), c = max(ca, cb);
+      atomicAdd(P.S + r * D + c, -v);
     }
   }
 }
@@ -518,7 +631,28 @@ cudaError_t ba_launch_camera_terms(const BaDev& P, cudaStream_t s) {
 cudaError_t ba_launch_schur(const BaDev& P, double radius, double min_diag, double max_diag, int n_sm, cudaStream_t s) {
   if (P.n_pts == 0) return cudaSuccess;
   const int grid = (int)std::min<int64_t>(P.n_pts, (int64_t)n_sm * 8);
-  bak::schur_kernel<<<grid, bak::kSchurThreads, 0, s>>>(P, radius, min_diag, max_diag);
+  bak::schur_kernel<false><<<grid, bak::kSchurThreads, 0, s>>>(P, radius, min_diag, max_diag, nullptr, nullptr);
+  return cudaGetLastError();
+}
+// pair-major variant: structure once per solve ...
+cudaError_t ba_launch_pm_enumerate(const BaDev& P, int n_img, bool fill, uint32_t* count_or_cursor, const uint32_t* start,
+                                   void* tuples, int n_sm, cudaStream_t s) {
+  if (P.n_pts == 0) return cudaSuccess;
+  const int grid = (int)std::min<int64_t>((P.n_pts + 7) / 8, (int64_t)n_sm * 8);
+  if (fill)
+    bak::pm_enumerate_kernel<true><<<grid, 256, 0, s>>>(P, n_img, count_or_cursor, start, (int2*)tuples);
+  else
+    bak::pm_enumerate_kernel<false><<<grid, 256, 0, s>>>(P, n_img, count_or_cursor, start, (int2*)tuples);
+  return cudaGetLastError();
+}
+// ... and per LM iteration: W / Y per observation (point-major), then the block sums
+cudaError_t ba_launch_schur_pm(const BaDev& P, double radius, double min_diag, double max_diag, int n_img,
+                               const uint32_t* start, const void* tuples, double* Wg, double* Yg, int n_sm,
+                               cudaStream_t s) {
+  if (P.n_pts == 0) return cudaSuccess;
+  const int grid = (int)std::min<int64_t>(P.n_pts, (int64_t)n_sm * 8);
+  bak::schur_kernel<true><<<grid, bak::kSchurThreads, 0, s>>>(P, radius, min_diag, max_diag, Wg, Yg);
+  bak::pm_blocks_kernel<<<n_sm * 8, 256, 0, s>>>(P, n_img, start, (const int2*)tuples, Wg, Yg);
   return cudaGetLastError();
 }
 cudaError_t ba_launch_add_diag(const BaDev& P, double radius, double min_diag, double max_diag, cudaStream_t s) {

@@ -47,6 +47,8 @@ struct double2 { double x, y; };
 struct float2 { float x, y; };
 struct uint4 { unsigned x, y, z, w; };
 struct int4 { int x, y, z, w; };
+struct int2 { int x, y; };
+inline int2 make_int2(int x, int y) { return int2{x, y}; }
 inline double2 make_double2(double x, double y) { return double2{x, y}; }
 inline float2 make_float2(float x, float y) { return float2{x, y}; }
 inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }

@@ -17,7 +17,7 @@ from tests.ba_scene import copy_problem, make_ba_problem, reprojection_rms
 def emu(request):
     from tests.cuda_emu.build_emu import build
     import dagsfm_b200.bundle_adjustment as ba
-    L = C.CDLL(str(build("ba", ["common.cu", "ba_kernels.cu", "ba_api.cu"])))
+    L = C.CDLL(str(build("ba", ["common.cu", "match_post.cu", "ba_kernels.cu", "ba_api.cu"])))
     vp, P = C.c_void_p, C.POINTER
     L.b2_ba_default_options.argtypes = [P(ba.BundleAdjustmentOptions)]
     L.b2_ba_default_options.restype = None
@@ -120,3 +120,52 @@ def test_invalid_loss_is_rejected(emu):
         emu_solve(emu, p, loss_function_type=5)
     with pytest.raises(RuntimeError):
         emu_solve(emu, p, loss_function_scale=0.0)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(n_img=6, n_pts=60, track_len=4, seed=5),
+    dict(n_img=8, n_pts=80, track_len=5, seed=3, shared_camera=True),      # intrinsics columns shared by all blocks
+    dict(n_img=40, n_pts=30, track_len=36, seed=6),
+    dict(n_img=8, n_pts=90, track_len=4, seed=7, n_const_pts=20),
+])
+def test_pair_major_schur_variant(emu, kw, monkeypatch):
+    """B2_BA_SCHUR=blocks: counting-sorted (image, image) blocks, W / Y per observation, one atomic per block
+    entry.  Must follow the same LM path as the production kernel and the oracle."""
+    p_pm = make_ba_problem(**kw)
+    p_ref, p_cpu = copy_problem(p_pm), copy_problem(p_pm)
+    s_ref = emu_solve(emu, p_ref, **TIGHT)
+    monkeypatch.setenv("B2_BA_SCHUR", "blocks")
+    s_pm = emu_solve(emu, p_pm, **TIGHT)
+    monkeypatch.delenv("B2_BA_SCHUR")
+    s_cpu = orc.ba_solve(p_cpu, **TIGHT)
+    assert s_pm.final_cost == pytest.approx(s_cpu.final_cost, rel=1e-9) and s_pm.final_cost == pytest.approx(s_ref.final_cost, rel=1e-9)
+    assert abs(reprojection_rms(p_pm) - reprojection_rms(p_cpu)) < 1e-6
+    assert np.abs(p_pm["xyz"] - p_ref["xyz"]).max() < 1e-5
+    # with the reference's own stopping rule (gradient_tolerance 1.0) the accept / reject sequence is the oracle's;
+    # at the 1e-16 noise floor above it depends on the summation order inside S
+    q_pm = make_ba_problem(**kw)
+    q_cpu = copy_problem(q_pm)
+    monkeypatch.setenv("B2_BA_SCHUR", "blocks")
+    t_pm = emu_solve(emu, q_pm)
+    monkeypatch.delenv("B2_BA_SCHUR")
+    t_cpu = orc.ba_solve(q_cpu)
+    assert (t_pm.num_successful_steps, t_pm.num_unsuccessful_steps, t_pm.termination_type) == \
+           (t_cpu.num_successful_steps, t_cpu.num_unsuccessful_steps, t_cpu.termination)
+    assert t_pm.final_cost == pytest.approx(t_cpu.final_cost, rel=1e-9)
+
+
+def test_pair_major_with_two_observations_of_one_image_in_a_track(emu, monkeypatch):
+    p_pm = make_ba_problem(n_img=7, n_pts=70, track_len=4, seed=9)
+    for pt in range(0, 70, 5):                       # point pt is seen twice by the image of its first observation
+        o = np.searchsorted(p_pm["obs_pt"], pt)
+        p_pm["obs_img"][o + 1] = p_pm["obs_img"][o]
+        p_pm["obs_xy"][o + 1] = p_pm["obs_xy"][o] + 0.3
+    p_ref, p_cpu = copy_problem(p_pm), copy_problem(p_pm)
+    s_ref = emu_solve(emu, p_ref, **TIGHT)
+    monkeypatch.setenv("B2_BA_SCHUR", "blocks")
+    s_pm = emu_solve(emu, p_pm, **TIGHT)
+    monkeypatch.delenv("B2_BA_SCHUR")
+    s_cpu = orc.ba_solve(p_cpu, **TIGHT)
+    assert s_ref.final_cost == pytest.approx(s_cpu.final_cost, rel=1e-9)
+    assert s_pm.final_cost == pytest.approx(s_cpu.final_cost, rel=1e-9)
+    assert np.abs(p_pm["xyz"] - p_cpu["xyz"]).max() < 1e-5
