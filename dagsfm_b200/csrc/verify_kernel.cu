@@ -23,6 +23,7 @@
 
 #include <cfloat>
 #include <cstdint>
+#include <cstdlib>
 
 #include "../../include/dagsfm_b200.h"
 #include "verify_common.cuh"
@@ -146,44 +147,73 @@ __device__ __forceinline__ double residual(int type, const double* M, double2 a,
 // functions of (model, points), so they can be taken ahead of the ordered replay; four independent
 // residual chains per lane hide the FP64 divide latency and the points are loaded once.
 constexpr int kGroup = 4;
-template <int TYPE>
+
+// Inlier decision of one Sampson residual.  NODIV == false is the reference expression
+// `x2tEx1^2 / den <= max_res` (estimators/utils.cc:87-131 + support_measurement.cc:38-41).
+// NODIV == true (experimental, B2_VERIFY_VARIANT=1) decides the same thing without the FP64 divide on the
+// dependency chain: with q = num / den exact and r = fl(q) correctly rounded, r <= T holds for every
+// q <= T and fails for every q > T (1 + 2^-52); products carry a relative error of 2^-53, so
+// num < fl(T den) (1 - 2^-50) implies q < T and num > fl(T den) (1 + 2^-50) implies q > T (1 + 2^-52).
+// Anything in between (probability ~1e-15 per residual, plus 0/0, inf/inf and NaN inputs) falls back to
+// the division itself, so the decision is the reference's in every case.
+template <bool NODIV>
+__device__ __forceinline__ bool sampson_inlier(const double* E, double2 p1, double2 p2, double max_res) {
+  const double x1_0 = p1.x, x1_1 = p1.y, x2_0 = p2.x, x2_1 = p2.y;
+  const double Ex1_0 = E[0] * x1_0 + E[1] * x1_1 + E[2];
+  const double Ex1_1 = E[3] * x1_0 + E[4] * x1_1 + E[5];
+  const double Ex1_2 = E[6] * x1_0 + E[7] * x1_1 + E[8];
+  const double Etx2_0 = E[0] * x2_0 + E[3] * x2_1 + E[6];
+  const double Etx2_1 = E[1] * x2_0 + E[4] * x2_1 + E[7];
+  const double x2tEx1 = x2_0 * Ex1_0 + x2_1 * Ex1_1 + Ex1_2;
+  const double num = x2tEx1 * x2tEx1;
+  const double den = Ex1_0 * Ex1_0 + Ex1_1 * Ex1_1 + Etx2_0 * Etx2_0 + Etx2_1 * Etx2_1;
+  return ratio_at_most<NODIV>(num, den, max_res);
+}
+
+template <int TYPE, int G, bool NODIV>
 __device__ __noinline__ void score_group(const double2* __restrict__ P1, const double2* __restrict__ P2, int M,
                                          const double* __restrict__ models, const uint16_t* ids, int n, double max_res,
                                          int lane, int* cnt_out) {
-  double m[kGroup][9];
+  double m[G][9];
 #pragma unroll
-  for (int u = 0; u < kGroup; ++u) {
+  for (int u = 0; u < G; ++u) {
     const int id = ids[u < n ? u : n - 1];
     const double* src = models + (id / 10) * 90 + (id % 10) * 9;
 #pragma unroll
     for (int k = 0; k < 9; ++k) m[u][k] = src[k];
   }
-  int c[kGroup];
+  int c[G];
 #pragma unroll
-  for (int u = 0; u < kGroup; ++u) c[u] = 0;
+  for (int u = 0; u < G; ++u) c[u] = 0;
   for (int i0 = 0; i0 < M; i0 += 32) {
     const int i = i0 + lane;
     const bool ok = i < M;
     const double2 a = P1[ok ? i : 0], b = P2[ok ? i : 0];
 #pragma unroll
-    for (int u = 0; u < kGroup; ++u) {
-      const bool in = ok && residual_t<TYPE>(m[u], a, b) <= max_res;
+    for (int u = 0; u < G; ++u) {
+      bool in;
+      if (NODIV) in = ok && sampson_inlier<true>(m[u], a, b, max_res);
+      else in = ok && residual_t<TYPE>(m[u], a, b) <= max_res;
       c[u] += __popc(__ballot_sync(kFull, in));
     }
   }
   if (lane == 0) {
 #pragma unroll
-    for (int u = 0; u < kGroup; ++u)
+    for (int u = 0; u < G; ++u)
       if (u < n) cnt_out[ids[u]] = c[u];
   }
   __syncwarp();
 }
+// VAR == 0: production (groups of four, reference residual expression).  VAR == 1: groups of eight and the
+// division-free Sampson decision (H and the translation model keep their expressions).
+template <int VAR>
 __device__ __forceinline__ void score_group_any(int type, const double2* P1, const double2* P2, int M,
                                                 const double* models, const uint16_t* ids, int n, double max_res,
                                                 int lane, int* cnt_out) {
-  if (type == EST_H4) score_group<EST_H4>(P1, P2, M, models, ids, n, max_res, lane, cnt_out);
-  else if (type == EST_T2) score_group<EST_T2>(P1, P2, M, models, ids, n, max_res, lane, cnt_out);
-  else score_group<EST_F7>(P1, P2, M, models, ids, n, max_res, lane, cnt_out);
+  constexpr int G = VAR ? 8 : kGroup;
+  if (type == EST_H4) score_group<EST_H4, G, false>(P1, P2, M, models, ids, n, max_res, lane, cnt_out);
+  else if (type == EST_T2) score_group<EST_T2, G, false>(P1, P2, M, models, ids, n, max_res, lane, cnt_out);
+  else score_group<EST_F7, G, VAR != 0>(P1, P2, M, models, ids, n, max_res, lane, cnt_out);
 }
 
 // InlierSupportMeasurer::Evaluate, count only (all lanes return the same value).
@@ -531,6 +561,7 @@ struct Scratch {
 };
 
 // LORANSAC::Estimate for one estimator over the matched points (P1,P2)[0..M).
+template <int VAR>
 __device__ void ransac_warp(int type, const double2* P1, const double2* P2, int M, double max_error,
                             double min_inlier_ratio, double confidence, long long min_num_trials,
                             long long max_num_trials_opt, WarpShared& sh, double* sig_sh, const Scratch& sc,
@@ -634,8 +665,9 @@ __device__ void ransac_warp(int type, const double2* P1, const double2* P2, int 
       }
       if ((j & 7) == 0) {  // support counts of the next eight trials' hypotheses
         const int g1 = sh.off[min(j + 8, 32)];
-        for (int g = sh.off[j]; g < g1; g += kGroup)
-          score_group_any(type, P1, P2, M, sc.models, sh.flat + g, min(kGroup, g1 - g), max_residual, lane, sh.cnt);
+        constexpr int GS = VAR ? 8 : kGroup;
+        for (int g = sh.off[j]; g < g1; g += GS)
+          score_group_any<VAR>(type, P1, P2, M, sc.models, sh.flat + g, min(GS, g1 - g), max_residual, lane, sh.cnt);
       }
       const int nm = sh.nm[j];
       for (int mi = 0; mi < nm; ++mi) {
@@ -668,8 +700,9 @@ __device__ void ransac_warp(int type, const double2* P1, const double2* P2, int 
             const long long cl0 = clock64();
             const int nlm = local_estimate(type, P1, P2, sc.inl, N, sc.G, sc.ld, sh, sig_sh, sc.lomodels, lane);
             lo_cycles += clock64() - cl0;
-            for (int g = 0; g < nlm; g += kGroup)
-              score_group_any(type, P1, P2, M, sc.lomodels, sh.lo_ids + g, min(kGroup, nlm - g), max_residual, lane,
+            constexpr int GL = VAR ? 8 : kGroup;
+            for (int g = 0; g < nlm; g += GL)
+              score_group_any<VAR>(type, P1, P2, M, sc.lomodels, sh.lo_ids + g, min(GL, nlm - g), max_residual, lane,
                               sh.lo_cnt);
             for (int li = 0; li < nlm; ++li) {
               double lm[9];
@@ -791,8 +824,9 @@ __device__ __forceinline__ bool in_box(double2 p, double minx, double maxx, doub
 
 // ------------------------------------------------------------------ main kernel
 
+template <int VAR>
 __global__ void __launch_bounds__(kThreads)
-verify_pairs_kernel(VerifyArgs A) {
+verify_pairs_kernel(VerifyArgs A) {  // VAR: see score_group_any
   extern __shared__ double lane_ws[];  // [kLaneWorkDoubles][kThreads] then WarpShared[kWarpsPerBlock]
   const LaneView ws{lane_ws + threadIdx.x};
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -866,12 +900,12 @@ verify_pairs_kernel(VerifyArgs A) {
       for (int k = 0; k < 9; ++k) E.model[k] = 0.0;
       if (calibrated) {
         const double e_err = (image_to_world_threshold(c1, o.max_error) + image_to_world_threshold(c2, o.max_error)) / 2;
-        ransac_warp(EST_E5, sc.nx1, sc.nx2, M, e_err, o.min_inlier_ratio, o.confidence, o.min_num_trials,
+        ransac_warp<VAR>(EST_E5, sc.nx1, sc.nx2, M, e_err, o.min_inlier_ratio, o.confidence, o.min_num_trials,
                     o.max_num_trials, sh, sig_sh, sc, sc.mask[0], &E, lane, ws);
       }
-      ransac_warp(EST_F7, sc.px1, sc.px2, M, o.max_error, o.min_inlier_ratio, o.confidence, o.min_num_trials,
+      ransac_warp<VAR>(EST_F7, sc.px1, sc.px2, M, o.max_error, o.min_inlier_ratio, o.confidence, o.min_num_trials,
                   o.max_num_trials, sh, sig_sh, sc, sc.mask[1], &F, lane, ws);
-      ransac_warp(EST_H4, sc.px1, sc.px2, M, o.max_error, o.min_inlier_ratio, o.confidence, o.min_num_trials,
+      ransac_warp<VAR>(EST_H4, sc.px1, sc.px2, M, o.max_error, o.min_inlier_ratio, o.confidence, o.min_num_trials,
                   o.max_num_trials, sh, sig_sh, sc, sc.mask[2], &H, lane, ws);
       for (int k = 0; k < 9; ++k) { res.E[k] = E.model[k]; res.F[k] = F.model[k]; res.H[k] = H.model[k]; }
       res.E_num_inliers = E.num_inliers; res.F_num_inliers = F.num_inliers; res.H_num_inliers = H.num_inliers;
@@ -955,7 +989,7 @@ verify_pairs_kernel(VerifyArgs A) {
           const double ratio = (double)nb_border / (double)num_inliers;
           if (!(ratio < o.watermark_min_inlier_ratio)) {
             RansacResult T;
-            ransac_warp(EST_T2, sc.ip1, sc.ip2, (int)num_inliers, o.max_error, o.watermark_min_inlier_ratio,
+            ransac_warp<VAR>(EST_T2, sc.ip1, sc.ip2, (int)num_inliers, o.max_error, o.watermark_min_inlier_ratio,
                         o.confidence, o.min_num_trials, o.max_num_trials, sh, sig_sh, sc, sc.tmask, &T, lane, ws);
             const double inlier_ratio = (double)T.num_inliers / (double)num_inliers;
             if (inlier_ratio >= o.watermark_min_inlier_ratio) res.config = 7;
@@ -1058,9 +1092,19 @@ cudaError_t launch_normalize_points(const b2_camera* cams, const int64_t* img_of
 }
 cudaError_t launch_verify_pairs(const VerifyArgs& a, int n_blocks, cudaStream_t s) {
   const size_t dyn = vf::kDynSmemBytes;
-  cudaError_t e = cudaFuncSetAttribute(vf::verify_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+  // B2_VERIFY_VARIANT=1 selects the experimental instance (groups of eight hypotheses, division-free
+  // Sampson decision); the default instance is the measured production kernel
+  const char* venv = getenv("B2_VERIFY_VARIANT");
+  const int variant = venv ? atoi(venv) : 0;
+  if (variant == 1) {
+    cudaError_t e = cudaFuncSetAttribute(vf::verify_pairs_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    if (e != cudaSuccess) return e;
+    vf::verify_pairs_kernel<1><<<n_blocks, vf::kThreads, dyn, s>>>(a);
+    return cudaGetLastError();
+  }
+  cudaError_t e = cudaFuncSetAttribute(vf::verify_pairs_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
   if (e != cudaSuccess) return e;
-  vf::verify_pairs_kernel<<<n_blocks, vf::kThreads, dyn, s>>>(a);
+  vf::verify_pairs_kernel<0><<<n_blocks, vf::kThreads, dyn, s>>>(a);
   return cudaGetLastError();
 }
 cudaError_t launch_score_models(int type, int n, const double* p1, const double* p2, int n_models, const double* models,

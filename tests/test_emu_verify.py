@@ -135,3 +135,34 @@ def test_estimate_multiple_through_the_c_abi(ver):
         assert res["config"][k] == cfg and res["n_inliers"][k] == len(exp_inl)
         assert inl[offs[k]:offs[k] + len(exp_inl)].tolist() == exp_inl.tolist()
     assert cfgs[0] == 8 and cfgs[2] == 1
+
+
+def test_experimental_variant_keeps_every_decision(ver, monkeypatch):
+    """B2_VERIFY_VARIANT=1 (groups of eight hypotheses, division-free Sampson decision with an exact fallback in
+    the rounding band): decisions, inlier lists and trial counts must stay those of the oracle."""
+    from dagsfm_b200 import Camera, TwoViewOptions
+    rng = np.random.default_rng(19)
+    specs = [(70, 15, False, True), (55, 12, True, False), (50, 25, False, False), (64, 0, False, True)]
+    cams, kps, pairs, offs, ms, priors = [], [], [], [0], [], []
+    for i, (n_in, n_out, planar, prior) in enumerate(specs):
+        p1, p2 = scene(rng, n_in, n_out, planar=planar, noise=0.3)
+        perm = np.random.default_rng(200 + i).permutation(len(p2))
+        kps += [p1, p2[perm]]
+        ms.append(np.stack([np.arange(len(p1)), np.argsort(perm)], 1))
+        cams += [Camera.make(prior_focal=prior), Camera.make(prior_focal=prior)]
+        priors.append(prior); pairs.append((2 * i, 2 * i + 1)); offs.append(offs[-1] + len(p1))
+    ver.set_images(cams, kps)
+    seeds = np.arange(len(specs), dtype=np.uint32) + 5
+    opt = TwoViewOptions.default(); opt.max_num_trials = 300
+    oopt = orc.tv_default_options(); oopt.max_num_trials = 300
+    base, inl0 = ver.verify_pairs(pairs, offs, np.concatenate(ms), opt, seeds)
+    monkeypatch.setenv("B2_VERIFY_VARIANT", "1")
+    res, inl = ver.verify_pairs(pairs, offs, np.concatenate(ms), opt, seeds)
+    monkeypatch.delenv("B2_VERIFY_VARIANT")
+    assert res.tobytes() == base.tobytes() and (inl == inl0).all()        # bit-identical to the production instance
+    for i in range(len(specs)):
+        c = orc.make_camera(prior=priors[i])
+        r, oi = orc.two_view(c, kps[2 * i], c, kps[2 * i + 1], ms[i], oopt, seed=int(seeds[i]))
+        assert (res["config"][i], res["n_inliers"][i], res["E_num_trials"][i], res["F_num_trials"][i], res["H_num_trials"][i]) == \
+               (r.config, r.n_inliers, r.E_trials, r.F_trials, r.H_trials)
+        assert inl[offs[i]:offs[i] + r.n_inliers].tolist() == oi.tolist()
