@@ -189,3 +189,52 @@ def test_reference_ba_config_cases_on_gpu(case):
         const = {"qvec": p_gpu["pose_const"], "tvec": p_gpu["pose_const"], "cam_params": p_gpu["cam_const"], "xyz": p_gpu["pt_const"]}[k]
         assert np.abs(p_gpu[k] - p_cpu[k]).max() < 1e-5
         assert (p_gpu[k][const == 1] == p_cpu[k][const == 1]).all()        # constant blocks stay bit-identical
+
+
+@pytest.mark.gpu
+@FIRST_RUN
+def test_verify_variant_is_bit_identical_on_gpu(monkeypatch):
+    """B2_VERIFY_VARIANT=1 (groups of eight + division-free Sampson decision): same bytes as the production instance."""
+    from dagsfm_b200 import Camera, TwoViewGeometryVerifier, TwoViewOptions
+    from tests.tv_scene import make_pairs
+    w = make_pairs(64, seed=5)
+    cams = [Camera.make(params=w["cam_params"], prior_focal=bool(p)) for p in w["prior"]]
+    seeds = np.arange(64, dtype=np.uint32) * 7 + 1
+    v = TwoViewGeometryVerifier(0)
+    try:
+        v.set_images(cams, w["keypoints"])
+        base, inl0 = v.verify_pairs(w["pairs"], w["match_offsets"], w["matches"], TwoViewOptions.default(), seeds)
+        monkeypatch.setenv("B2_VERIFY_VARIANT", "1")
+        res, inl = v.verify_pairs(w["pairs"], w["match_offsets"], w["matches"], TwoViewOptions.default(), seeds)
+    finally:
+        monkeypatch.delenv("B2_VERIFY_VARIANT", raising=False)
+        v.close()
+    assert res.tobytes() == base.tobytes() and (inl == inl0).all()
+
+
+@pytest.mark.gpu
+@FIRST_RUN
+def test_pair_major_schur_matches_production_on_gpu(monkeypatch):
+    """B2_BA_SCHUR=blocks: same LM path and optimum as the production Schur kernel and the oracle."""
+    from dagsfm_b200 import BundleAdjuster, BundleAdjustmentOptions
+    from tests.ba_scene import copy_problem, make_ba_problem, reprojection_rms
+
+    def solve(prob):
+        ba = BundleAdjuster(BundleAdjustmentOptions.default())
+        try:
+            return ba.Solve(prob)
+        finally:
+            ba.close()
+    for kw in (dict(n_img=24, n_pts=600, track_len=6, seed=3), dict(n_img=12, n_pts=300, track_len=5, seed=4, shared_camera=True),
+               dict(n_img=48, n_pts=400, track_len=40, seed=6)):
+        p_ref = make_ba_problem(**kw)
+        p_pm, p_cpu = copy_problem(p_ref), copy_problem(p_ref)
+        s_ref = solve(p_ref)
+        monkeypatch.setenv("B2_BA_SCHUR", "blocks")
+        s_pm = solve(p_pm)
+        monkeypatch.delenv("B2_BA_SCHUR")
+        s_cpu = orc.ba_solve(p_cpu)
+        assert (s_pm.num_successful_steps, s_pm.num_unsuccessful_steps) == (s_ref.num_successful_steps, s_ref.num_unsuccessful_steps) \
+               == (s_cpu.num_successful_steps, s_cpu.num_unsuccessful_steps)
+        assert s_pm.final_cost == pytest.approx(s_cpu.final_cost, rel=1e-9)
+        assert abs(reprojection_rms(p_pm) - reprojection_rms(p_cpu)) < 1e-6
