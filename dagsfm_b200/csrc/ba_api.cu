@@ -251,7 +251,7 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
     uint64_t n_tuples = 0;
     for (int p = 0; p < n_pts; ++p) {
       const uint64_t L = (uint64_t)(pt_start[p + 1] - pt_start[p]);
-      if (pt_col[p] >= 0) n_tuples += L * (L + 1) / 2;
+      n_tuples += (pt_col[p] >= 0) ? L * (L + 1) / 2 : L;  // constant points: diagonal tuples only (camera terms)
     }
     if (n_tuples == 0 || n_tuples >= 0xFFFFFFF0ull) pair_major = false;
     if (pair_major) {
@@ -261,6 +261,8 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
       B2_TRY(dev_alloc(h, &pm_tuples, (size_t)n_tuples));
       B2_TRY(dev_alloc(h, &pm_W, (size_t)n_obs * 30));
       B2_TRY(dev_alloc(h, &pm_Y, (size_t)n_obs * 30));
+      B2_CUDA(cudaMemsetAsync(pm_W, 0, (size_t)n_obs * 30 * 8, s));  // observations of constant points keep W = Y = 0
+      B2_CUDA(cudaMemsetAsync(pm_Y, 0, (size_t)n_obs * 30 * 8, s));
       B2_CUDA(cudaMemsetAsync(pm_count, 0, (size_t)n_keys * sizeof(uint32_t), s));
       B2_CUDA(ba_launch_pm_enumerate(P, n_img, false, pm_count, nullptr, nullptr, h->n_sm, s));
       B2_CUDA(launch_scan_u32(pm_count, n_keys, pm_start, pm_start + n_keys, s));
@@ -280,7 +282,7 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
     B2_CUDA(cudaMemsetAsync(scal, 0, 6 * 8, s));
     B2_CUDA(cudaMemsetAsync(scal + 7, 0, 8, s));
     B2_CUDA(cudaEventRecord(h->ev[2], s));
-    B2_CUDA(ba_launch_camera_terms(P, s));
+    if (!pair_major) B2_CUDA(ba_launch_camera_terms(P, s));  // folded into the (i, i) blocks in pair-major mode
     if (pair_major)
       B2_CUDA(ba_launch_schur_pm(P, radius, min_diag, max_diag, n_img, pm_start, pm_tuples, pm_W, pm_Y, h->n_sm, s));
     else

@@ -375,12 +375,14 @@ pm_enumerate_kernel(BaDev P, int n_img, uint32_t* __restrict__ count_or_cursor, 
   const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t p = warp0; p < P.n_pts; p += n_warps) {
-    if (P.pt_col[p] < 0) continue;
+    const bool variable = P.pt_col[p] >= 0;
     const int64_t o0 = P.pt_start[p];
     const int L = (int)(P.pt_start[p + 1] - o0);
     for (int a = 0; a < L; ++a) {
       const int ia = P.obs_img[o0 + a];
-      for (int b = a + lane; b < L; b += 32) {
+      // a constant point has no Schur term (W = 0) but its observations still carry camera terms:
+      // only the diagonal tuple (a, a)
+      for (int b = a + lane; b < (variable ? L : a + 1); b += 32) {
         const int ib = P.obs_img[o0 + b];
         const bool swap = ib < ia;
         const int lo_img = swap ? ib : ia, hi_img = swap ? ia : ib;
@@ -396,7 +398,9 @@ pm_enumerate_kernel(BaDev P, int n_img, uint32_t* __restrict__ count_or_cursor, 
 // One warp per (image i <= image j) block: B = sum over the block's tuples of Y_lo W_hi^T (10 x 10, lane
 // e owns entries e, e + 32, e + 64, e + 96), then one atomicAdd per entry into S instead of one per tuple
 // and entry.  Same-image blocks are symmetric: a tuple of two different observations of one image adds
-// its transpose too, and only the upper entries are written.  Different images that share a camera:
+// its transpose too, and only the upper entries are written; their diagonal tuples (a, a) also carry the
+// observation's camera terms U = Jc^T Jc, g_c, diag_c, so camera_terms_kernel is not run in this mode.
+// Different images that share a camera:
 // the intrinsics entries (k, l) and (l, k) land on the same upper slot, the diagonal ones are doubled
 // (their (hi, lo) counterpart is not enumerated) -- as in schur_kernel's pair loop.
 __global__ void __launch_bounds__(256)
@@ -419,8 +423,24 @@ pm_blocks_kernel(BaDev P, int n_img, const uint32_t* __restrict__ start, const i
     if (t0 == t1) continue;
     const int i = (int)(key / n_img), j = (int)(key - (int64_t)i * n_img);
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    double gsum = 0.0, dsum = 0.0;  // lanes 0..9 of an (i, i) block: g_c and diag_c of column k = lane
     for (uint32_t t = t0; t < t1; ++t) {
       const int2 tp = tuples[t];
+      if (tp.x == tp.y) {
+        // the observation's own camera terms (what camera_terms_kernel adds with one atomic per entry):
+        // U = Jc^T Jc enters S with the opposite sign of the Schur term, g_c = Jc^T r, diag_c = diag(U)
+        const ObsJac& e = P.J[tp.x];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (lane + 32 * u >= 100) continue;
+          const int k = kk[u], l = ll[u];
+          acc[u] -= e.Jc[k] * e.Jc[l] + e.Jc[10 + k] * e.Jc[10 + l];
+        }
+        if (lane < 10) {
+          gsum += e.Jc[lane] * e.r[0] + e.Jc[10 + lane] * e.r[1];
+          dsum += e.Jc[lane] * e.Jc[lane] + e.Jc[10 + lane] * e.Jc[10 + lane];
+        }
+      }
       const double* y = Yg + (int64_t)tp.x * 30;
       const double* w = Wg + (int64_t)tp.y * 30;
 #pragma unroll
@@ -441,6 +461,13 @@ pm_blocks_kernel(BaDev P, int n_img, const uint32_t* __restrict__ start, const i
       }
     }
     const int cam_i = P.img_cam[i], cam_j = P.img_cam[j];
+    if (i == j && lane < 10) {
+      const int col = (lane < 6) ? P.pose_col[6 * i + lane] : P.intr_col[4 * cam_i + (lane - 6)];
+      if (col >= 0) {
+        atomicAdd(P.g_c + col, gsum);
+        atomicAdd(P.diag_c + col, dsum);
+      }
+    }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       if (lane + 32 * u >= 100) continue;

@@ -95,7 +95,9 @@ def build(name: str, sources: list[str], extra: list[str] | None = None) -> Path
         gen.append(str(g))
     lib = OUT / f"libemu_{name}.so"
     cxx = "/usr/bin/g++" if Path("/usr/bin/g++").exists() else "g++"
-    cmd = [cxx, "-std=c++17", "-O1", "-g", "-ffp-contract=off", "-U_FORTIFY_SOURCE", "-shared", "-fPIC", "-w",
+    import os
+    san = ["-fsanitize=address", "-fno-omit-frame-pointer"] if os.environ.get("B2_EMU_ASAN") else []   # debugging aid
+    cmd = [cxx, "-std=c++17", "-O1", "-g", "-ffp-contract=off", "-U_FORTIFY_SOURCE", "-fno-gnu-unique", "-shared", "-fPIC", "-w"] + san + [
            "-I", str(HERE / "include"), "-I", str(CSRC), "-I", str(ROOT / "include"), "-o", str(lib)] + gen + (extra or [])
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

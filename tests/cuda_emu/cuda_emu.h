@@ -11,6 +11,7 @@
 // (__syncthreads, __syncwarp, warp shuffles / votes), i.e. deterministically.  A fiber that returns
 // simply leaves its barriers (like an exited CUDA thread).  Device memory is host memory.
 #pragma once
+#include <setjmp.h>
 #include <ucontext.h>
 
 #include <algorithm>
@@ -66,7 +67,9 @@ template <class A, class B> inline typename std::common_type<A, B>::type max(A a
 namespace cuda_emu {
 
 struct Fiber {
-  ucontext_t ctx;
+  ucontext_t ctx;   // only to enter the fiber the first time (makecontext); afterwards _setjmp / _longjmp,
+  jmp_buf jb;       // which switch stacks without the sigprocmask system call swapcontext makes
+  bool started = false;
   std::vector<char> stack;
   bool done = false;
   int wait_kind = 0;  // 0 runnable, 1 waiting at the block barrier, 2 waiting at its warp barrier
@@ -75,7 +78,7 @@ struct Fiber {
 
 struct BlockState {
   std::vector<Fiber> fibers;
-  ucontext_t sched;
+  jmp_buf sched;
   int current = -1;
   unsigned n_threads = 0;
   // warp exchange buffers (one 64-bit slot per lane) and arrival counters
@@ -102,7 +105,7 @@ inline void*& dyn_smem() {
 inline void yield_to_scheduler() {
   BlockState* b = cur();
   Fiber& f = b->fibers[b->current];
-  swapcontext(&f.ctx, &b->sched);
+  if (!_setjmp(f.jb)) _longjmp(b->sched, 1);
 }
 inline int alive_in_warp(BlockState* b, unsigned warp) {
   int n = 0;
@@ -134,10 +137,11 @@ inline void fiber_entry() {
   BlockState* b = cur();
   b->body();
   b->fibers[b->current].done = true;
-  swapcontext(&b->fibers[b->current].ctx, &b->sched);
+  _longjmp(b->sched, 1);
 }
 
-inline void run_block(BlockState& b, unsigned n_threads, const std::function<void()>& body) {
+// noinline + volatile loop state: the loop is re-entered through _longjmp (setjmp's rules for automatic variables)
+__attribute__((noinline)) inline void run_block(BlockState& b, unsigned n_threads, const std::function<void()>& body) {
   constexpr size_t kStack = 256u << 10;  // the verification kernel keeps several 10 KB of locals
   b.n_threads = n_threads;
   b.body = body;
@@ -150,6 +154,7 @@ inline void run_block(BlockState& b, unsigned n_threads, const std::function<voi
     Fiber& f = b.fibers[t];
     if (f.stack.size() != kStack) f.stack.resize(kStack);
     f.done = false;
+    f.started = false;
     f.wait_kind = 0;
     f.tid = t;
     getcontext(&f.ctx);
@@ -159,15 +164,19 @@ inline void run_block(BlockState& b, unsigned n_threads, const std::function<voi
     makecontext(&f.ctx, (void (*)())fiber_entry, 0);
   }
   for (;;) {
-    bool progressed = false, any_alive = false;
-    for (unsigned t = 0; t < n_threads; ++t) {
+    volatile bool progressed = false, any_alive = false;
+    for (volatile unsigned t = 0; t < n_threads; ++t) {
       Fiber& f = b.fibers[t];
       if (f.done) continue;
       any_alive = true;
       if (f.wait_kind != 0) continue;
       b.current = (int)t;
       idx().threadIdx.x = t;
-      swapcontext(&b.sched, &f.ctx);
+      if (!_setjmp(b.sched)) {
+        if (f.started) _longjmp(f.jb, 1);
+        f.started = true;
+        setcontext(&f.ctx);
+      }
       progressed = true;
     }
     if (!any_alive) break;
