@@ -37,7 +37,7 @@ cudaError_t launch_scan_u32(const uint32_t* in, int64_t n, uint32_t* out, uint32
                             cudaStream_t s);
 cudaError_t launch_scan_counts(const uint32_t* counts, int64_t n, int64_t* offsets,
                                int64_t* carry_inout, bool write_last, cudaStream_t s);
-cudaError_t launch_fill_items(const uint32_t* pairs, int64_t n_pairs, const int32_t* img_n,
+cudaError_t launch_fill_items(const uint32_t* pairs, int64_t n_pairs, const int32_t* img_n, int32_t n_images,
                               const uint32_t* img_row, const uint32_t* item_start, MatchItem* items,
                               PairMeta* meta, uint32_t y_block_rows, cudaStream_t s);
 cudaError_t launch_match_top2_ts(const CUtensorMap& tmap, const uint8_t* pool, const MatchItem* items,
@@ -290,7 +290,7 @@ static int run_pairs_device(b2_matcher* m, ImageStore& st, int64_t n_pairs,
     const uint32_t* pr = pairs_dev + 2 * p0;
     B2_CUDA(launch_pair_items(pr, np, st.d_img_n, st.n_images, m->d_nitems, m->d_err, s));
     B2_CUDA(launch_scan_u32(m->d_nitems, np, m->d_item_start, m->d_total_items, s));
-    B2_CUDA(launch_fill_items(pr, np, st.d_img_n, st.d_img_row, m->d_item_start, m->d_items, m->d_meta,
+    B2_CUDA(launch_fill_items(pr, np, st.d_img_n, st.n_images, st.d_img_row, m->d_item_start, m->d_items, m->d_meta,
                               (uint32_t)kTileRows, s));
     B2_CUDA(cudaMemsetAsync(m->d_cand_count, 0, sizeof(unsigned int), s));
     B2_CUDA(cudaEventRecord(m->ev[2 + 2 * c], s));
@@ -380,7 +380,7 @@ static int run_guided_device(b2_matcher* m, ImageStore& st, int64_t n_pairs, con
     const uint32_t* pr = pairs_dev + 2 * p0;
     B2_CUDA(launch_pair_items(pr, np, st.d_img_n, st.n_images, m->d_nitems, m->d_err, s));
     B2_CUDA(launch_scan_u32(m->d_nitems, np, m->d_item_start, m->d_total_items, s));
-    B2_CUDA(launch_fill_items(pr, np, st.d_img_n, st.d_img_row, m->d_item_start, m->d_items, m->d_meta,
+    B2_CUDA(launch_fill_items(pr, np, st.d_img_n, st.n_images, st.d_img_row, m->d_item_start, m->d_items, m->d_meta,
                               (uint32_t)kTileRows, s));
     B2_CUDA(launch_guided_item_pairs(m->d_meta, np, m->d_item_pair, s));
     B2_CUDA(launch_guided_match(st.pool, st.kp_pool, m->d_items, m->d_item_pair, m->d_total_items, m->d_meta,

@@ -81,7 +81,7 @@ __global__ void block_scan_kernel(const TIn* __restrict__ in, int64_t n, TOut* _
 
 // One thread per pair: write its items and its PairMeta.
 __global__ void fill_items_kernel(const uint32_t* __restrict__ pairs, int64_t n_pairs,
-                                  const int32_t* __restrict__ img_n,
+                                  const int32_t* __restrict__ img_n, int32_t n_images,
                                   const uint32_t* __restrict__ img_row,
                                   const uint32_t* __restrict__ item_start,
                                   MatchItem* __restrict__ items, PairMeta* __restrict__ meta,
@@ -89,7 +89,10 @@ __global__ void fill_items_kernel(const uint32_t* __restrict__ pairs, int64_t n_
   const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (p >= n_pairs) return;
   const uint32_t i1 = pairs[2 * p], i2 = pairs[2 * p + 1];
-  const uint32_t n1 = img_n[i1], n2 = img_n[i2];
+  // a pair that names an image outside the store was given no items (pair_items_kernel raised the error
+  // flag): it must not index img_n / img_row either
+  const bool valid = i1 < (uint32_t)n_images && i2 < (uint32_t)n_images;
+  const uint32_t n1 = valid ? img_n[i1] : 0u, n2 = valid ? img_n[i2] : 0u;
   PairMeta pm;
   pm.item_start = item_start[p];
   pm.n1 = n1;
@@ -215,11 +218,11 @@ cudaError_t launch_scan_counts(const uint32_t* counts, int64_t n, int64_t* offse
                                                           carry_inout, write_last);
   return cudaGetLastError();
 }
-cudaError_t launch_fill_items(const uint32_t* pairs, int64_t n_pairs, const int32_t* img_n,
+cudaError_t launch_fill_items(const uint32_t* pairs, int64_t n_pairs, const int32_t* img_n, int32_t n_images,
                               const uint32_t* img_row, const uint32_t* item_start, MatchItem* items,
                               PairMeta* meta, uint32_t y_block_rows, cudaStream_t s) {
   if (n_pairs == 0) return cudaSuccess;
-  fill_items_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, s>>>(pairs, n_pairs, img_n, img_row,
+  fill_items_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, s>>>(pairs, n_pairs, img_n, n_images, img_row,
                                                                       item_start, items, meta, y_block_rows);
   return cudaGetLastError();
 }

@@ -86,6 +86,10 @@ def rewrite(src: str) -> str:
 
 
 def build(name: str, sources: list[str], extra: list[str] | None = None) -> Path:
+    import os
+    # every "device" allocation of the emulated libraries ends at an inaccessible page: an out-of-bounds access
+    # fails at the access (with a native backtrace) instead of depending on the heap layout
+    os.environ.setdefault("B2_EMU_GUARD", "1")
     OUT.mkdir(exist_ok=True)
     gen = []
     for s in sources:

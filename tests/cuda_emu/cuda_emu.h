@@ -6,13 +6,16 @@
 // this header, so that the kernels (minus the tcgen05 matcher, which has no CPU meaning) and the host
 // code around them can be exercised against the oracle without a GPU.
 //
-// Execution model: blocks run one after the other; the threads of a block are ucontext fibers on the
-// calling OS thread, scheduled round-robin and switched only at synchronisation points
+// Execution model: blocks run one after the other; the threads of a block are fibers (own stacks, a hand-written context
+// switch) on the calling OS thread, scheduled round-robin and switched only at synchronisation points
 // (__syncthreads, __syncwarp, warp shuffles / votes), i.e. deterministically.  A fiber that returns
 // simply leaves its barriers (like an exited CUDA thread).  Device memory is host memory.
 #pragma once
-#include <setjmp.h>
-#include <ucontext.h>
+
+#include <execinfo.h>
+#include <signal.h>
+#include <sys/mman.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <atomic>
@@ -24,6 +27,8 @@
 #include <cstring>
 #include <functional>
 #include <type_traits>
+#include <unordered_map>
+#include <utility>
 #include <vector>
 
 // ------------------------------------------------------------------ qualifiers / built-in types
@@ -64,12 +69,41 @@ template <class A, class B> inline typename std::common_type<A, B>::type max(A a
   return (T)a > (T)b ? (T)a : (T)b;
 }
 
+#if !defined(__x86_64__)
+#error "cuda_emu.h switches fibers with a few lines of x86-64 assembly"
+#endif
+// cuda_emu_switch(&save_sp, load_sp): pushes the callee-saved registers, stores the stack pointer, adopts
+// load_sp, pops that context's registers and returns into it.  (glibc's swapcontext costs a system call
+// per switch and longjmp across stacks trips its cleanup-handler bookkeeping.)
+extern "C" void cuda_emu_switch(void** save_sp, void* load_sp);
+asm(R"(
+.pushsection .text
+.weak cuda_emu_switch
+.type cuda_emu_switch,@function
+cuda_emu_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+.size cuda_emu_switch,.-cuda_emu_switch
+.popsection
+)");
+
 namespace cuda_emu {
 
 struct Fiber {
-  ucontext_t ctx;   // only to enter the fiber the first time (makecontext); afterwards _setjmp / _longjmp,
-  jmp_buf jb;       // which switch stacks without the sigprocmask system call swapcontext makes
-  bool started = false;
+  void* sp = nullptr;  // saved stack pointer while the fiber is switched out
   std::vector<char> stack;
   bool done = false;
   int wait_kind = 0;  // 0 runnable, 1 waiting at the block barrier, 2 waiting at its warp barrier
@@ -78,7 +112,7 @@ struct Fiber {
 
 struct BlockState {
   std::vector<Fiber> fibers;
-  jmp_buf sched;
+  void* sched_sp = nullptr;
   int current = -1;
   unsigned n_threads = 0;
   // warp exchange buffers (one 64-bit slot per lane) and arrival counters
@@ -105,7 +139,7 @@ inline void*& dyn_smem() {
 inline void yield_to_scheduler() {
   BlockState* b = cur();
   Fiber& f = b->fibers[b->current];
-  if (!_setjmp(f.jb)) _longjmp(b->sched, 1);
+  cuda_emu_switch(&f.sp, b->sched_sp);
 }
 inline int alive_in_warp(BlockState* b, unsigned warp) {
   int n = 0;
@@ -136,12 +170,13 @@ inline void block_barrier() {
 inline void fiber_entry() {
   BlockState* b = cur();
   b->body();
-  b->fibers[b->current].done = true;
-  _longjmp(b->sched, 1);
+  Fiber& f = b->fibers[b->current];
+  f.done = true;
+  cuda_emu_switch(&f.sp, b->sched_sp);  // never resumed
+  std::abort();
 }
 
-// noinline + volatile loop state: the loop is re-entered through _longjmp (setjmp's rules for automatic variables)
-__attribute__((noinline)) inline void run_block(BlockState& b, unsigned n_threads, const std::function<void()>& body) {
+inline void run_block(BlockState& b, unsigned n_threads, const std::function<void()>& body) {
   constexpr size_t kStack = 256u << 10;  // the verification kernel keeps several 10 KB of locals
   b.n_threads = n_threads;
   b.body = body;
@@ -154,29 +189,26 @@ __attribute__((noinline)) inline void run_block(BlockState& b, unsigned n_thread
     Fiber& f = b.fibers[t];
     if (f.stack.size() != kStack) f.stack.resize(kStack);
     f.done = false;
-    f.started = false;
     f.wait_kind = 0;
     f.tid = t;
-    getcontext(&f.ctx);
-    f.ctx.uc_stack.ss_sp = f.stack.data();
-    f.ctx.uc_stack.ss_size = f.stack.size();
-    f.ctx.uc_link = nullptr;
-    makecontext(&f.ctx, (void (*)())fiber_entry, 0);
+    // initial frame: six zeroed callee-saved registers, then the entry point as return address; after the
+    // `ret` the stack pointer is 8 modulo 16, as at any function entry
+    uintptr_t top = ((uintptr_t)f.stack.data() + f.stack.size()) & ~(uintptr_t)15;
+    void** sp = (void**)(top - 8);
+    *--sp = (void*)+[] { fiber_entry(); };
+    for (int r = 0; r < 6; ++r) *--sp = nullptr;
+    f.sp = sp;
   }
   for (;;) {
-    volatile bool progressed = false, any_alive = false;
-    for (volatile unsigned t = 0; t < n_threads; ++t) {
+    bool progressed = false, any_alive = false;
+    for (unsigned t = 0; t < n_threads; ++t) {
       Fiber& f = b.fibers[t];
       if (f.done) continue;
       any_alive = true;
       if (f.wait_kind != 0) continue;
       b.current = (int)t;
       idx().threadIdx.x = t;
-      if (!_setjmp(b.sched)) {
-        if (f.started) _longjmp(f.jb, 1);
-        f.started = true;
-        setcontext(&f.ctx);
-      }
+      cuda_emu_switch(&b.sched_sp, f.sp);
       progressed = true;
     }
     if (!any_alive) break;
@@ -319,8 +351,59 @@ inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
 inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) { *p = cudaDeviceProp(); return cudaSuccess; }
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
-template <class T> inline cudaError_t cudaMalloc(T** p, size_t n) { *p = (T*)std::calloc(std::max<size_t>(n, 1), 1); return *p ? cudaSuccess : 2; }
-inline cudaError_t cudaFree(void* p) { std::free(p); return cudaSuccess; }
+// B2_EMU_GUARD=1: every "device" allocation ends right before an inaccessible page, so an overrun of the kind
+// compute-sanitizer reports on the GPU faults at the offending access (debugging aid for the emulator).
+namespace cuda_emu {
+inline void guard_segv(int, siginfo_t* si, void*) {
+  void* bt[48];
+  const int n = backtrace(bt, 48);
+  std::fprintf(stderr, "cuda_emu: access violation at %p (B2_EMU_GUARD)\n", si->si_addr);
+  backtrace_symbols_fd(bt, n, 2);
+  _exit(139);
+}
+inline bool guard_mode() {
+  static const bool g = [] {
+    const bool on = std::getenv("B2_EMU_GUARD") != nullptr;
+    if (on) {
+      struct sigaction sa;
+      std::memset(&sa, 0, sizeof sa);
+      sa.sa_sigaction = guard_segv;
+      sa.sa_flags = SA_SIGINFO;
+      sigaction(SIGSEGV, &sa, nullptr);
+    }
+    return on;
+  }();
+  return g;
+}
+inline std::unordered_map<void*, std::pair<void*, size_t>>& guard_registry() {
+  static std::unordered_map<void*, std::pair<void*, size_t>> r;
+  return r;
+}
+inline void* guarded_alloc(size_t n) {
+  const size_t page = 4096, body = (n + 15) / 16 * 16, span = (body + page - 1) / page * page + page;
+  char* base = (char*)mmap(nullptr, span, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+  if (base == (char*)MAP_FAILED) return nullptr;
+  mprotect(base + span - page, page, PROT_NONE);
+  void* p = base + span - page - body;   // the allocation ends where the inaccessible page begins
+  guard_registry()[p] = {base, span};
+  return p;
+}
+inline void guarded_free(void* p) {
+  auto it = guard_registry().find(p);
+  if (it == guard_registry().end()) return;
+  munmap(it->second.first, it->second.second);
+  guard_registry().erase(it);
+}
+}  // namespace cuda_emu
+template <class T> inline cudaError_t cudaMalloc(T** p, size_t n) {
+  n = std::max<size_t>(n, 1);
+  *p = (T*)(cuda_emu::guard_mode() ? cuda_emu::guarded_alloc(n) : std::calloc(n, 1));
+  return *p ? cudaSuccess : 2;
+}
+inline cudaError_t cudaFree(void* p) {
+  if (cuda_emu::guard_mode()) cuda_emu::guarded_free(p); else std::free(p);
+  return cudaSuccess;
+}
 inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { if (n) std::memmove(d, s, n); return cudaSuccess; }
 inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind k, cudaStream_t = nullptr) { return cudaMemcpy(d, s, n, k); }
 inline cudaError_t cudaMemset(void* d, int v, size_t n) { if (n) std::memset(d, v, n); return cudaSuccess; }

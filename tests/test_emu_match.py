@@ -138,3 +138,20 @@ def test_guided_pairs_through_the_c_abi(mm):
         assert one.tolist() == orc.match_guided(kps[0], kps[1], descs[0], descs[1], geos[0][0], F=geos[0][1]).tolist()
     finally:
         gpu.close()
+
+
+def test_pair_naming_an_unknown_image_is_rejected_without_touching_memory(mm):
+    """A pair that references an image outside the store must come back as an error.  fill_items_kernel used to
+    index img_n / img_row with the bad id (found by the emulator's guard pages; on the GPU it read whatever
+    followed the allocation and could emit items for it)."""
+    d = orc.create_random_descriptors(40, seed=2)
+    gpu = mm.SiftMatchGPU(0)
+    try:
+        gpu.set_images([d, d[::-1].copy()])
+        for bad in ([(0, 2)], [(7, 1)], [(0, 1), (1, 4000000000)]):
+            with pytest.raises(RuntimeError):
+                gpu.match_pairs(bad, mm.SiftMatchingOptions())
+        off, m = gpu.match_pairs([(0, 1)], mm.SiftMatchingOptions())       # the handle stays usable
+        assert m[off[0]:off[1]].tolist() == orc.match_sift(d, d[::-1].copy()).tolist()
+    finally:
+        gpu.close()
