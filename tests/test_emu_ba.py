@@ -169,3 +169,28 @@ def test_pair_major_with_two_observations_of_one_image_in_a_track(emu, monkeypat
     assert s_ref.final_cost == pytest.approx(s_cpu.final_cost, rel=1e-9)
     assert s_pm.final_cost == pytest.approx(s_cpu.final_cost, rel=1e-9)
     assert np.abs(p_pm["xyz"] - p_cpu["xyz"]).max() < 1e-5
+
+
+def test_edge_cases_nothing_to_optimise(emu):
+    p = make_ba_problem(n_img=4, n_pts=20, track_len=3, seed=1)
+    q = copy_problem(p)
+    q["pose_const"][:] = 1; q["cam_const"][:] = 1; q["pt_const"][:] = 1          # everything constant
+    before = {k: q[k].copy() for k in ("qvec", "tvec", "cam_params", "xyz")}
+    s = emu_solve(emu, q)
+    assert s.num_effective_parameters_reduced == 0 and s.num_residuals_reduced == 0
+    assert all((q[k] == before[k]).all() for k in ("tvec", "cam_params", "xyz"))
+    assert np.abs(q["qvec"] - before["qvec"]).max() < 1e-15          # image.NormalizeQvec() (bundle_adjustment.cc:345) still runs
+    e = copy_problem(p)                                                           # no observations at all
+    for k in ("obs_img", "obs_pt"):
+        e[k] = e[k][:0].copy()
+    e["obs_xy"] = e["obs_xy"][:0].copy()
+    s = emu_solve(emu, e)
+    assert s.num_residuals_reduced == 0 and s.initial_cost == 0.0
+    bad = copy_problem(p)
+    bad["obs_img"][0] = 99                                                        # observation of an unknown image
+    with pytest.raises(RuntimeError):
+        emu_solve(emu, bad)
+    unsorted = copy_problem(p)
+    unsorted["obs_pt"][0], unsorted["obs_pt"][-1] = unsorted["obs_pt"][-1], unsorted["obs_pt"][0]
+    with pytest.raises(RuntimeError):                                             # observations must be sorted by point
+        emu_solve(emu, unsorted)

@@ -155,3 +155,21 @@ def test_pair_naming_an_unknown_image_is_rejected_without_touching_memory(mm):
         assert m[off[0]:off[1]].tolist() == orc.match_sift(d, d[::-1].copy()).tolist()
     finally:
         gpu.close()
+
+
+def test_saturating_and_zero_descriptors(mm):
+    hi = np.full((70, 128), 255, np.uint8)          # every dot = 128 * 255^2: clamped distance, everything ties
+    zero = np.zeros((33, 128), np.uint8)            # dots 0: no match at all (sift.cc:136-138)
+    mix = np.r_[orc.create_random_descriptors(50, seed=3), zero[:5], hi[:2]]
+    gpu = mm.SiftMatchGPU(0)
+    try:
+        gpu.set_images([hi, zero, mix])
+        pairs = [(0, 0), (0, 1), (1, 1), (2, 2), (2, 0), (1, 2)]
+        for o in (mm.SiftMatchingOptions(), mm.SiftMatchingOptions(cross_check=False, max_ratio=1.0, max_distance=1.5707964)):
+            off, m = gpu.match_pairs(pairs, o)
+            ds = [hi, zero, mix]
+            for p, (i, j) in enumerate(pairs):
+                exp = orc.match_sift(ds[i], ds[j], max_ratio=o.max_ratio, max_distance=o.max_distance, cross_check=o.cross_check)
+                assert m[off[p]:off[p + 1]].tolist() == exp.tolist(), (p, i, j)
+    finally:
+        gpu.close()

@@ -166,3 +166,31 @@ def test_experimental_variant_keeps_every_decision(ver, monkeypatch):
         assert (res["config"][i], res["n_inliers"][i], res["E_num_trials"][i], res["F_num_trials"][i], res["H_num_trials"][i]) == \
                (r.config, r.n_inliers, r.E_trials, r.F_trials, r.H_trials)
         assert inl[offs[i]:offs[i] + r.n_inliers].tolist() == oi.tolist()
+
+
+def test_edge_cases_empty_tiny_and_invalid_pairs(ver):
+    from dagsfm_b200 import Camera, TwoViewOptions
+    rng = np.random.default_rng(4)
+    p1, p2 = scene(rng, 40, 5, noise=0.3)
+    kps = [p1, p2, np.zeros((0, 2)), p1[:3]]
+    ver.set_images([Camera.make(prior_focal=False)] * 4, kps)
+    full = np.stack([np.arange(45)] * 2, 1).astype(np.uint32)
+    pairs = [(0, 1), (0, 1), (0, 1), (3, 1)]
+    ms = [full, full[:0], full[:6], full[:3]]                    # all, none, fewer than any minimal sample needs, 3
+    offs = np.r_[0, np.cumsum([len(m) for m in ms])]
+    opt = TwoViewOptions.default(); opt.max_num_trials = 200
+    oopt = orc.tv_default_options(); oopt.max_num_trials = 200
+    seeds = np.array([1, 2, 3, 4], np.uint32)
+    res, inl = ver.verify_pairs(pairs, offs, np.concatenate(ms), opt, seeds)
+    cam = orc.make_camera(prior=False)
+    for k, (i, j) in enumerate(pairs):
+        r, oi = orc.two_view(cam, kps[i], cam, kps[j], ms[k], oopt, seed=int(seeds[k]))
+        assert (res["config"][k], res["n_inliers"][k]) == (r.config, r.n_inliers)
+    assert res["config"][1] == 1 and res["config"][2] == 1 and res["config"][3] == 1      # DEGENERATE
+    with pytest.raises(RuntimeError):                                                     # image id outside the store
+        ver.verify_pairs([(0, 9)], [0, 45], full, opt, seeds[:1])
+    with pytest.raises(RuntimeError):                                                     # TwoViewGeometry::Options::Check
+        bad = TwoViewOptions.default(); bad.min_num_inliers = -1
+        ver.verify_pairs(pairs[:1], offs[:2], full, bad, seeds[:1])
+    r0, _ = ver.verify_pairs([], [0], np.zeros((0, 2), np.uint32), opt, np.zeros(0, np.uint32))
+    assert len(r0) == 0
