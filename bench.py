@@ -281,6 +281,12 @@ def bench_ba(a, local_rank, rank, world, cores, barrier, hbm):
                         "algorithmic_bytes_per_iteration": alg_bytes, "avg_ms_per_iteration": schur_ms,
                         "share_of_solve": s.schur_kernel_seconds / s.solve_seconds, "traffic": None,
                         "note": "FP64 atomics into the dense reduced system dominate; see DESIGN.md"}}
+    if (n_img, n_pts, track) == (500, 100000, 10) and world == 1:
+        # committed ncu captures of one iteration at exactly this workload: schur_kernel 234.7 + 11.8 MB
+        # (profiles/r1_ba_schur_ncu_full.txt), camera_terms_kernel 228.8 + 3.5 MB (r1_ba_camera_terms_ncu_full.txt);
+        # 4.9x the algorithmic bytes because both kernels re-read the 224 B/observation Jacobian blocks
+        out["roofline"]["traffic"] = 478.8e6
+        out["roofline"]["traffic_source"] = "profiles/r1_ba_schur_ncu_full.txt + r1_ba_camera_terms_ncu_full.txt (bytes per LM iteration)"
     if rank == 0 and not a.no_cpu:
         from oracle import pyoracle as orc
         if orc.pba_ref_available():
@@ -475,6 +481,13 @@ def main():
                 "algorithmic_ops_per_pair": ops_per_pair,
                 "avg_launch_ms": 1e3 * t_tc / max(n_tc, 1), "launches": n_tc,
                 "share_of_step": t_tc / t_dev, "traffic": None}
+    # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the committed `ncu --set full` capture
+    # (profiles/r1_match_ts_ncu_full.txt: 4.257 GB + 0.277 GB for a full 8 192-pair launch of 4096 x 4096 images);
+    # only quoted when this run's launches have that shape.  Algorithmic bytes of such a launch: 8192 x 1.1 MB = 9.0 GB
+    # -- the images are shared by many pairs, so L2 serves more than half of them.
+    if a.desc == 4096 and n_tc > 0 and abs(n_pairs * a.steps / n_tc - 8192) < 64:
+        roofline["traffic"] = 4.534e9
+        roofline["traffic_source"] = "profiles/r1_match_ts_ncu_full.txt (bytes per 8192-pair launch)"
 
     cpu = None
     if not a.no_cpu:
