@@ -28,9 +28,13 @@ class BundleAdjustmentOptions(C.Structure):
                 ("refine_principal_point", C.c_int32), ("refine_extra_params", C.c_int32),
                 ("function_tolerance", C.c_double), ("gradient_tolerance", C.c_double),
                 ("parameter_tolerance", C.c_double),
-                ("loss_function_type", C.c_int32), ("reserved", C.c_int32), ("loss_function_scale", C.c_double)]
+                ("loss_function_type", C.c_int32), ("linear_solver_type", C.c_int32),
+                ("loss_function_scale", C.c_double),
+                ("max_linear_solver_iterations", C.c_int32), ("reserved", C.c_int32)]
 
     TRIVIAL, SOFT_L1, CAUCHY = 0, 1, 2   # BundleAdjustmentOptions::LossFunctionType
+    # linear_solver_type: the reference's rule on the image count (bundle_adjustment.cc:274-284), or forced
+    SOLVER_BY_NUM_IMAGES, EXACT_SCHUR, ITERATIVE_SCHUR = 0, 1, 2
 
     @staticmethod
     def default():
@@ -45,7 +49,8 @@ class BaSummary(C.Structure):
                 ("termination_type", C.c_int32), ("num_residuals_reduced", C.c_int32),
                 ("num_effective_parameters_reduced", C.c_int32), ("num_iterations", C.c_int32),
                 ("solve_seconds", C.c_double), ("schur_kernel_seconds", C.c_double),
-                ("schur_kernel_launches", C.c_int64)]
+                ("schur_kernel_launches", C.c_int64), ("num_linear_solver_iterations", C.c_int64),
+                ("linear_solver_type_used", C.c_int32), ("reserved", C.c_int32)]
 
 
 ALLREDUCE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p)

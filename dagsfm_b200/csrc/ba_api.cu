@@ -5,9 +5,12 @@
 //   initial radius 1e4, max 1e16, min 1e-32; min_relative_decrease 1e-3; LM diagonal
 //   clamp [1e-6, 1e32]; Jacobi scaling 1/(1+|col|); radius /= max(1/3, 1-(2 rho-1)^3) on
 //   success, /= decrease_factor (2, doubling) on failure.
-// The reduced system is solved exactly (DENSE_SCHUR / SPARSE_SCHUR semantics) with a dense
-// Cholesky -- cuSOLVER potrf/potrs, a library call for the factorisation only; Jacobian,
-// Schur elimination and back-substitution are the hand-written kernels in ba_kernels.cu.
+// Up to 1000 images (the reference's rule, bundle_adjustment.cc:274-284) the reduced system is
+// solved exactly (DENSE_SCHUR / SPARSE_SCHUR semantics) with a dense Cholesky -- cuSOLVER
+// potrf/potrs, a library call for the factorisation only; Jacobian, Schur elimination and
+// back-substitution are the hand-written kernels in ba_kernels.cu.  Above, ITERATIVE_SCHUR +
+// SCHUR_JACOBI: Ceres' ConjugateGradientsSolver loop (restated in cg_solve below) over the
+// matrix-free Schur product and block-Jacobi preconditioner of ba_iterative.cu.
 #include <cuda_runtime.h>
 #include <cusolverDn.h>
 
@@ -72,6 +75,93 @@ int sync_reduce(b2_ba* h, double* buf, int64_t n, int op) {
   return B2_OK;
 }
 
+// Sum of n per-block partial sums (fixed order => the same value on every run and every rank).
+int sum_partials(b2_ba* h, const double* d_partial, int n, double* out) {
+  double hp[kBaIterMaxPartials];
+  B2_CUDA(cudaMemcpyAsync(hp, d_partial, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream));
+  B2_CUDA(cudaStreamSynchronize(h->stream));
+  double s = 0;
+  for (int k = 0; k < n; ++k) s += hp[k];
+  *out = s;
+  return B2_OK;
+}
+
+struct CgVectors { double *x, *r, *p, *q, *tmp, *partial; };
+
+// ceres::internal::ConjugateGradientsSolver::Solve (Ceres 1.14 conjugate_gradients_solver.cc, external)
+// on S x = rhs as IterativeSchurComplementSolver drives it: x0 = 0, min_num_iterations 0,
+// r_tolerance -1 (off), q_tolerance = eta = 0.1 (LevenbergMarquardtStrategy), residual reset every
+// 10 iterations, preconditioner SCHUR_JACOBI.  *usable = false <=> LINEAR_SOLVER_FAILURE (the LM
+// step is then invalid); hitting max_iter or p'Sp <= 0 keeps the current x (NO_CONVERGENCE).
+// S p = D_c^2 p + [all-reduce over ranks of] F'(F p - E (E'E)^-1 E'F p): the only collective of the loop.
+int cg_solve(b2_ba* h, const BaDev& P, const BaIter& I, const CgVectors& V, int max_iter, int64_t* n_iter, bool* usable) {
+  const int64_t D = P.D;
+  cudaStream_t s = h->stream;
+  *usable = true;
+  B2_CUDA(cudaMemsetAsync(V.x, 0, (size_t)D * 8, s));
+  int np = 0;
+  double v = 0;
+  B2_CUDA(bai_launch_dot(D, P.rhs, P.rhs, V.partial, &np, s));
+  B2_TRY(sum_partials(h, V.partial, np, &v));
+  count_launches(1);
+  const double norm_b = std::sqrt(v);
+  if (norm_b == 0.0) return B2_OK;
+  B2_CUDA(cudaMemcpyAsync(V.r, P.rhs, (size_t)D * 8, cudaMemcpyDeviceToDevice, s));  // r = b - S 0
+  const double q_tolerance = 0.1;
+  const int residual_reset_period = 10;
+  double rho = 1.0, Q0 = -1.0 * 0.0;
+  for (int it = 1;; ++it) {
+    ++*n_iter;
+    double* z = V.q;  // Ceres aliases z and q the same way
+    B2_CUDA(bai_launch_cg_precond(D, I, V.r, z, V.partial, &np, s));
+    const double last_rho = rho;
+    B2_TRY(sum_partials(h, V.partial, np, &rho));
+    if (rho == 0.0 || std::isinf(rho)) { *usable = false; break; }
+    double beta = 0;
+    if (it > 1) {
+      beta = rho / last_rho;
+      if (beta == 0.0 || std::isinf(beta)) { *usable = false; break; }
+    }
+    B2_CUDA(bai_launch_cg_update_p(D, z, V.p, beta, it == 1, s));
+    B2_CUDA(bai_launch_matvec(P, I, V.p, V.q, s));
+    B2_TRY(sync_reduce(h, V.q, D, 0));
+    B2_CUDA(bai_launch_cg_finish_q(D, I.lm_c, V.p, V.q, V.partial, &np, s));
+    double pq = 0;
+    B2_TRY(sum_partials(h, V.partial, np, &pq));
+    count_launches(5);
+    if (pq <= 0 || std::isinf(pq)) break;
+    const double alpha = rho / pq;
+    if (std::isinf(alpha)) { *usable = false; break; }
+    if (it % residual_reset_period == 0) {
+      B2_CUDA(bai_launch_cg_update_xr(D, V.x, V.p, V.r, V.q, P.rhs, alpha, 1, V.partial, &np, s));
+      B2_CUDA(bai_launch_matvec(P, I, V.x, V.tmp, s));
+      B2_TRY(sync_reduce(h, V.tmp, D, 0));
+      B2_CUDA(bai_launch_cg_finish_q(D, I.lm_c, V.x, V.tmp, V.partial, &np, s));
+      B2_CUDA(bai_launch_cg_update_xr(D, V.x, V.p, V.r, V.tmp, P.rhs, alpha, 2, V.partial, &np, s));
+      count_launches(5);
+    } else {
+      B2_CUDA(bai_launch_cg_update_xr(D, V.x, V.p, V.r, V.q, P.rhs, alpha, 0, V.partial, &np, s));
+      count_launches(1);
+    }
+    double xq = 0, rr = 0;
+    B2_TRY(sum_partials(h, V.partial, np, &xq));
+    B2_TRY(sum_partials(h, V.partial + kBaIterMaxPartials, np, &rr));
+    const double Q1 = -1.0 * xq;
+    const double zeta = it * (Q1 - Q0) / Q1;
+    if (zeta < q_tolerance) break;
+    Q0 = Q1;
+    (void)rr;  // residual-based termination is disabled (r_tolerance = -1 => tol_r < 0 <= |r|)
+    if (it >= max_iter) break;
+  }
+  if (*usable) {  // IsArrayValid(step): a non-finite entry makes the step a linear-solver failure
+    B2_CUDA(bai_launch_dot(D, V.x, V.x, V.partial, &np, s));
+    B2_TRY(sum_partials(h, V.partial, np, &v));
+    count_launches(1);
+    if (!std::isfinite(v)) *usable = false;
+  }
+  return B2_OK;
+}
+
 int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_ba_summary* sum) {
   cudaStream_t s = h->stream;
   const int loss_type = opt->loss_function_type;
@@ -122,13 +212,22 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
   int64_t NP = 0;
   for (int p = 0; p < n_pts; ++p)
     if (pt_used[p] && !pr->const_point[p]) pt_col[p] = (int32_t)NP++;
-  {  // the reduced camera system is dense: D x D doubles must fit in this GPU's memory
+  // BundleAdjuster::Solve's "empirical choice" (bundle_adjustment.cc:274-284): direct solvers up to
+  // kMaxNumImagesDirectSparseSolver = 1000 images, ITERATIVE_SCHUR + SCHUR_JACOBI above
+  const bool iterative = opt->linear_solver_type == 2 || (opt->linear_solver_type == 0 && n_img > 1000);
+  sum->linear_solver_type_used = iterative ? 2 : 1;
+  sum->num_linear_solver_iterations = 0;
+  {  // exact path: the reduced camera system is dense, D x D doubles must fit in this GPU's memory
     size_t free_b = 0, total_b = 0;
     B2_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    const double need = ((double)D * (double)D + 3.0 * (double)D) * 8.0 + (double)n_obs * sizeof(ObsJac);
+    const double need = (iterative ? 16.0 * (double)D : (double)D * (double)D + 3.0 * (double)D) * 8.0 +
+                        (double)n_obs * (sizeof(ObsJac) + (iterative ? 4.0 : 0.0));
     if (need > 0.9 * (double)free_b)
-      return set_error(B2_ERR_INVALID, "reduced camera system too large for the dense Schur path on this GPU");
+      return set_error(B2_ERR_INVALID, iterative ? "problem too large for this GPU's memory"
+                                                 : "reduced camera system too large for the dense Schur path on this GPU "
+                                                   "(linear_solver_type = 2 selects ITERATIVE_SCHUR)");
   }
+  if (iterative && n_obs >= 0x7fffffffLL) return set_error(B2_ERR_INVALID, "too many observations for ITERATIVE_SCHUR");
   std::vector<int64_t> pt_start(n_pts + 1, 0);
   for (int64_t o = 0; o < n_obs; ++o) pt_start[pr->obs_point[o] + 1]++;
   for (int p = 0; p < n_pts; ++p) pt_start[p + 1] += pt_start[p];
@@ -191,9 +290,9 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
   B2_TRY(dev_alloc(h, &P.colnorm_c, (size_t)D));
   B2_TRY(dev_alloc(h, &P.colnorm_p, (size_t)NP * 3));
   double* reduced;  // S | rhs | g_c | diag_c : one buffer, one all-reduce
-  const size_t n_reduced = (size_t)D * D + 3 * (size_t)D;
+  const size_t n_reduced = (iterative ? 0 : (size_t)D * D) + 3 * (size_t)D;  // S is never formed by ITERATIVE_SCHUR
   B2_TRY(dev_alloc(h, &reduced, n_reduced));
-  P.S = reduced; P.rhs = reduced + (size_t)D * D; P.g_c = P.rhs + D; P.diag_c = P.g_c + D;
+  P.S = iterative ? nullptr : reduced; P.rhs = reduced + (n_reduced - 3 * (size_t)D); P.g_c = P.rhs + D; P.diag_c = P.g_c + D;
   B2_TRY(dev_alloc(h, &P.diag_p, (size_t)NP * 3));
   B2_TRY(dev_alloc(h, &P.g_p, (size_t)NP * 3));
   B2_TRY(dev_alloc(h, &P.Vinv, (size_t)NP * 9));
@@ -208,12 +307,56 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
   uint8_t* work = nullptr;
   size_t work_dev = 0, work_host = 0;
   std::vector<uint8_t> work_h;
-  if (D > 0) {
+  if (D > 0 && !iterative) {
     if (cusolverDnXpotrf_bufferSize(h->solver, h->solver_params, CUBLAS_FILL_MODE_LOWER, D, CUDA_R_64F, P.S, D,
                                     CUDA_R_64F, &work_dev, &work_host) != CUSOLVER_STATUS_SUCCESS)
       return set_error(B2_ERR_CUDA, "cusolverDnXpotrf_bufferSize failed");
     B2_TRY(dev_alloc(h, &work, std::max<size_t>(work_dev, 8)));
     work_h.resize(std::max<size_t>(work_host, 8));
+  }
+  // ---------------------------------------------------------------- ITERATIVE_SCHUR state
+  BaIter I;
+  memset(&I, 0, sizeof I);
+  CgVectors V;
+  memset(&V, 0, sizeof V);
+  if (iterative) {
+    // observations grouped by image (counting sort of the point-major order) for the image-major pass
+    std::vector<int64_t> img_start(n_img + 1, 0);
+    for (int64_t o = 0; o < n_obs; ++o) img_start[pr->obs_image[o] + 1]++;
+    for (int i = 0; i < n_img; ++i) img_start[i + 1] += img_start[i];
+    std::vector<int32_t> img_obs((size_t)n_obs);
+    {
+      std::vector<int64_t> cur(img_start.begin(), img_start.end() - 1);
+      for (int64_t o = 0; o < n_obs; ++o) img_obs[(size_t)cur[pr->obs_image[o]]++] = (int32_t)o;
+    }
+    // Ceres parameter blocks of the camera side: qvec (3 local columns), tvec (its variable components),
+    // camera parameters (the variable ones) -- bundle_adjustment.cc:383-418 adds them as separate blocks
+    std::vector<int32_t> blk_first((size_t)std::max<int64_t>(D, 1), 0), blk_size((size_t)std::max<int64_t>(D, 1), 0);
+    auto mark = [&](const int32_t* cols, int n) {
+      int f = -1, cnt = 0;
+      for (int k = 0; k < n; ++k) if (cols[k] >= 0) { if (f < 0) f = cols[k]; ++cnt; }
+      for (int k = 0; k < n; ++k) if (cols[k] >= 0) { blk_first[cols[k]] = f; blk_size[cols[k]] = cnt; }
+    };
+    for (int i = 0; i < n_img; ++i) { mark(&pose_col[6 * (size_t)i], 3); mark(&pose_col[6 * (size_t)i + 3], 3); }
+    for (int c = 0; c < n_cam; ++c) mark(&intr_col[4 * (size_t)c], 4);
+    int64_t* d_img_start; int32_t *d_img_obs, *d_blk_first, *d_blk_size;
+    B2_TRY(dev_upload(h, &d_img_start, img_start.data(), img_start.size()));
+    B2_TRY(dev_upload(h, &d_img_obs, img_obs.data(), img_obs.size()));
+    B2_TRY(dev_upload(h, &d_blk_first, blk_first.data(), (size_t)D));
+    B2_TRY(dev_upload(h, &d_blk_size, blk_size.data(), (size_t)D));
+    I.img_start = d_img_start; I.img_obs = d_img_obs; I.blk_first = d_blk_first; I.blk_size = d_blk_size;
+    B2_TRY(dev_alloc(h, &I.tp, (size_t)NP * 3));
+    B2_TRY(dev_alloc(h, &I.zp, (size_t)NP * 3));
+    B2_TRY(dev_alloc(h, &I.lm_c, (size_t)D));
+    B2_TRY(dev_alloc(h, &I.M, (size_t)D * 4));
+    B2_TRY(dev_alloc(h, &I.flag, 1));
+    V.x = P.dc;
+    B2_TRY(dev_alloc(h, &V.r, (size_t)D));
+    B2_TRY(dev_alloc(h, &V.p, (size_t)D));
+    B2_TRY(dev_alloc(h, &V.q, (size_t)D));
+    B2_TRY(dev_alloc(h, &V.tmp, (size_t)D));
+    B2_TRY(dev_alloc(h, &V.partial, (size_t)2 * kBaIterMaxPartials));
+    B2_CUDA(cudaStreamSynchronize(s));  // the host vectors above go out of scope
   }
   if (n_obs == 0 && !h->allreduce) return B2_OK;  // BundleAdjuster::Solve returns false: nothing to do
 
@@ -246,7 +389,7 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
   uint32_t *pm_count = nullptr, *pm_start = nullptr;
   uint64_t* pm_tuples = nullptr;
   double *pm_W = nullptr, *pm_Y = nullptr;
-  if (const char* e = getenv("B2_BA_SCHUR")) pair_major = strcmp(e, "blocks") == 0 && n_img > 0 && n_img <= 4096 && n_obs > 0;
+  if (const char* e = getenv("B2_BA_SCHUR")) pair_major = !iterative && strcmp(e, "blocks") == 0 && n_img > 0 && n_img <= 4096 && n_obs > 0;
   if (pair_major) {
     uint64_t n_tuples = 0;
     for (int p = 0; p < n_pts; ++p) {
@@ -281,6 +424,45 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
     B2_CUDA(cudaMemsetAsync(reduced, 0, n_reduced * 8, s));
     B2_CUDA(cudaMemsetAsync(scal, 0, 6 * 8, s));
     B2_CUDA(cudaMemsetAsync(scal + 7, 0, 8, s));
+    int info = 0;
+    if (iterative) {
+      // ---- ITERATIVE_SCHUR: point blocks, rhs / g_c / diag_c, SCHUR_JACOBI blocks, then CG on S x = rhs
+      B2_CUDA(cudaEventRecord(h->ev[2], s));
+      B2_CUDA(bai_launch_point_prepare(P, I, radius, min_diag, max_diag, s));
+      B2_CUDA(bai_launch_rhs(P, I, s));
+      B2_TRY(sync_reduce(h, reduced, (int64_t)n_reduced, 0));  // (rhs, g_c, diag_c)
+      B2_CUDA(bai_launch_cam_diag(P, I, radius, min_diag, max_diag, s));
+      B2_TRY(sync_reduce(h, P.gmax, 1, 1));
+      {  // gradient_max_norm <= gradient_tolerance: converged before another inner solve is spent
+        double gmax_now = 0;
+        B2_CUDA(cudaMemcpyAsync(&gmax_now, P.gmax, 8, cudaMemcpyDeviceToHost, s));
+        B2_CUDA(cudaStreamSynchronize(s));
+        count_launches(3);
+        if (gmax_now <= opt->gradient_tolerance) {
+          sum->termination_type = 0;
+          break;
+        }
+      }
+      B2_CUDA(cudaMemsetAsync(I.M, 0, std::max<size_t>((size_t)D * 4, 1) * 8, s));
+      B2_CUDA(cudaMemsetAsync(I.flag, 0, sizeof(int), s));
+      B2_CUDA(bai_launch_precond(P, I, s));
+      B2_TRY(sync_reduce(h, I.M, D * 4, 0));
+      B2_CUDA(bai_launch_precond_invert(P, I, s));
+      count_launches(2);
+      if (D > 0) {
+        B2_CUDA(cudaMemcpyAsync(&info, I.flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+        B2_CUDA(cudaStreamSynchronize(s));
+        bool usable = info == 0;  // a preconditioner block that is not PD = LINEAR_SOLVER_FAILURE
+        if (usable) B2_TRY(cg_solve(h, P, I, V, opt->max_linear_solver_iterations, &sum->num_linear_solver_iterations, &usable));
+        if (!usable) {
+          info = 1;
+          B2_CUDA(cudaMemsetAsync(P.dc, 0, (size_t)D * 8, s));
+        }
+        B2_CUDA(ba_launch_negate(P.dc, D, s));  // dc = -x
+      }
+      B2_CUDA(cudaEventRecord(h->ev[3], s));
+      schur_launches += 2;
+    } else {
     B2_CUDA(cudaEventRecord(h->ev[2], s));
     if (!pair_major) B2_CUDA(ba_launch_camera_terms(P, s));  // folded into the (i, i) blocks in pair-major mode
     if (pair_major)
@@ -293,7 +475,6 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
     B2_CUDA(ba_launch_add_diag(P, radius, min_diag, max_diag, s));
     B2_TRY(sync_reduce(h, P.gmax, 1, 1));
     // ---- reduced solve: S y = rhs, dc = -y
-    int info = 0;
     if (D > 0) {
       B2_CUDA(cudaMemcpyAsync(P.dc, P.rhs, D * 8, cudaMemcpyDeviceToDevice, s));
       if (cusolverDnXpotrf(h->solver, h->solver_params, CUBLAS_FILL_MODE_LOWER, D, CUDA_R_64F, P.S, D, CUDA_R_64F,
@@ -304,6 +485,7 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
                            P.dc, D, d_info) != CUSOLVER_STATUS_SUCCESS)
         return set_error(B2_ERR_CUDA, "cusolverDnXpotrs failed");
       B2_CUDA(ba_launch_negate(P.dc, D, s));
+    }
     }
     B2_CUDA(ba_launch_backsub(P, s));
     B2_CUDA(ba_launch_model_cost(P, scal + 4, s));
@@ -399,8 +581,10 @@ void b2_ba_default_options(b2_ba_options* o) {
   o->gradient_tolerance = 1.0;
   o->parameter_tolerance = 0.0;
   o->loss_function_type = 0;  // TRIVIAL
-  o->reserved = 0;
+  o->linear_solver_type = 0;  // by the number of images, as BundleAdjuster::Solve chooses
   o->loss_function_scale = 1.0;
+  o->max_linear_solver_iterations = 100;  // distributed_mapper_controller.cpp:529
+  o->reserved = 0;
 }
 
 int b2_ba_create(int device, b2_ba** out) {
@@ -452,6 +636,8 @@ int b2_ba_solve(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_
   if (!h || !pr || !opt || !sum) return set_error(B2_ERR_INVALID, "NULL argument");
   if (opt->loss_function_type < 0 || opt->loss_function_type > 2 || !(opt->loss_function_scale > 0))
     return set_error(B2_ERR_INVALID, "unknown loss_function_type or non-positive loss_function_scale");
+  if (opt->linear_solver_type < 0 || opt->linear_solver_type > 2 || opt->max_linear_solver_iterations < 0)
+    return set_error(B2_ERR_INVALID, "bad linear_solver_type / max_linear_solver_iterations");
   if (pr->n_images < 0 || pr->n_cameras < 0 || pr->n_points < 0 || pr->n_obs < 0 || opt->max_num_iterations < 0)
     return set_error(B2_ERR_INVALID, "negative size");
   B2_CUDA(cudaSetDevice(h->device));

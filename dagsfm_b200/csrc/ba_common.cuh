@@ -59,4 +59,30 @@ cudaError_t ba_launch_candidate(const BaDev& P, double* out, bool cameras, cudaS
 cudaError_t ba_launch_make_scale(const double* colnorm, double* scale, int64_t n, cudaStream_t s);
 cudaError_t ba_launch_negate(double* v, int64_t n, cudaStream_t s);
 
+// ---- ITERATIVE_SCHUR (ba_iterative.cu): state of the conjugate-gradient solve of the reduced system
+constexpr int kBaIterMaxPartials = 128;  // blocks of the vector kernels = partial sums per dot product
+struct BaIter {
+  const int64_t* img_start;  // [n_img + 1] observations grouped by image ...
+  const int32_t* img_obs;    // [n_obs]     ... as indices into the point-major arrays
+  const int32_t* blk_first;  // [D] first column of the column's parameter block (rotation / tvec / intrinsics)
+  const int32_t* blk_size;   // [D] its number of columns (<= 4)
+  double* tp;                // [NP * 3] V^-1 g_p
+  double* zp;                // [NP * 3] V^-1 E'F x of the current product
+  double* lm_c;              // [D] LM diagonal of the camera columns
+  double* M;                 // [D * 4] block diagonal of S, then its inverse (SCHUR_JACOBI)
+  int* flag;                 // raised by precond_invert_kernel on a block that is not positive definite
+};
+cudaError_t bai_launch_point_prepare(const BaDev& P, const BaIter& I, double radius, double min_diag, double max_diag, cudaStream_t s);
+cudaError_t bai_launch_rhs(const BaDev& P, const BaIter& I, cudaStream_t s);
+cudaError_t bai_launch_cam_diag(const BaDev& P, const BaIter& I, double radius, double min_diag, double max_diag, cudaStream_t s);
+cudaError_t bai_launch_precond(const BaDev& P, const BaIter& I, cudaStream_t s);
+cudaError_t bai_launch_precond_invert(const BaDev& P, const BaIter& I, cudaStream_t s);
+cudaError_t bai_launch_matvec(const BaDev& P, const BaIter& I, const double* x, double* out, cudaStream_t s);
+cudaError_t bai_launch_dot(int64_t D, const double* a, const double* b, double* partial, int* n_partial, cudaStream_t s);
+cudaError_t bai_launch_cg_precond(int64_t D, const BaIter& I, const double* r, double* z, double* partial, int* n_partial, cudaStream_t s);
+cudaError_t bai_launch_cg_update_p(int64_t D, const double* z, double* p, double beta, bool first, cudaStream_t s);
+cudaError_t bai_launch_cg_finish_q(int64_t D, const double* lm_c, const double* p, double* q, double* partial, int* n_partial, cudaStream_t s);
+cudaError_t bai_launch_cg_update_xr(int64_t D, double* x, const double* p, double* r, const double* q, const double* b,
+                                    double alpha, int mode, double* partial, int* n_partial, cudaStream_t s);
+
 }  // namespace b2

@@ -251,8 +251,10 @@ int b2_verify_last_timing(b2_verifier* v, double* kernel_s);
  * (src/base/cost_functions.h:44-158), QuaternionParameterization on qvec,
  * SubsetParameterization on tvec / intrinsics, constant cameras / poses / points
  * (bundle_adjustment.cc:338-526), and the Levenberg-Marquardt + Schur-complement solve
- * that ceres::Solve performs with DENSE_SCHUR / SPARSE_SCHUR (exact step; the
- * ITERATIVE_SCHUR regime above 1000 images is not covered yet).
+ * that ceres::Solve performs: DENSE_SCHUR / SPARSE_SCHUR (exact step, dense Cholesky of the
+ * reduced camera system) up to 1000 images and ITERATIVE_SCHUR + SCHUR_JACOBI (conjugate
+ * gradients on the implicit Schur complement, block-Jacobi preconditioner) above, the rule of
+ * bundle_adjustment.cc:274-284.
  * The problem is passed the way ParallelBundleAdjuster::SetUp packs it for PBA
  * (bundle_adjustment.cc:654-772): flat arrays, observations sorted by point.
  * All parameters are updated IN PLACE (as Ceres updates Image::Qvec/Tvec,
@@ -289,8 +291,13 @@ typedef struct b2_ba_options {   /* BundleAdjustmentOptions (bundle_adjustment.h
   int32_t loss_function_type;    /* BundleAdjustmentOptions::LossFunctionType (bundle_adjustment.h:49-51):
                                     0 TRIVIAL (final / global BA), 1 SOFT_L1 (the mapper's local BA,
                                     incremental_mapper_controller.cc:252-253), 2 CAUCHY */
-  int32_t reserved;
+  int32_t linear_solver_type;    /* 0 = the reference's rule on n_images (bundle_adjustment.cc:274-284:
+                                    <= 1000 exact Schur step, else ITERATIVE_SCHUR + SCHUR_JACOBI),
+                                    1 = exact (DENSE_SCHUR / SPARSE_SCHUR), 2 = ITERATIVE_SCHUR */
   double loss_function_scale;    /* 1.0 */
+  int32_t max_linear_solver_iterations; /* CG iterations per LM step (ITERATIVE_SCHUR); final BA: 100
+                                    (distributed_mapper_controller.cpp:529), BundleAdjustmentOptions: 200 */
+  int32_t reserved;
 } b2_ba_options;
 
 typedef struct b2_ba_summary {   /* the fields of ceres::Solver::Summary the reference reads */
@@ -302,6 +309,9 @@ typedef struct b2_ba_summary {   /* the fields of ceres::Solver::Summary the ref
   double solve_seconds;                 /* device time of the LM loop (CUDA events) */
   double schur_kernel_seconds;          /* ... of which inside the Jacobian+Schur kernels */
   int64_t schur_kernel_launches;
+  int64_t num_linear_solver_iterations; /* CG iterations over all LM steps (0 on the exact path) */
+  int32_t linear_solver_type_used;      /* 1 exact, 2 ITERATIVE_SCHUR */
+  int32_t reserved;
 } b2_ba_summary;
 
 /* Collective hook for multi-GPU runs (points sharded across ranks, cameras replicated):

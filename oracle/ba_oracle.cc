@@ -158,6 +158,10 @@ struct Options {
   int n_threads;
   int loss_type = 0;        // BundleAdjustmentOptions::LossFunctionType: 0 TRIVIAL, 1 SOFT_L1, 2 CAUCHY
   double loss_scale = 1.0;  // loss_function_scale
+  // 0 = exact Schur step (DENSE_SCHUR / SPARSE_SCHUR), 1 = ITERATIVE_SCHUR + SCHUR_JACOBI, which
+  // BundleAdjuster::Solve selects above 1000 images (bundle_adjustment.cc:274-284)
+  int linear_solver = 0;
+  int max_linear_solver_iterations = 100;  // GlobalBundleAdjustment(): distributed_mapper_controller.cpp:529
 };
 
 // ceres::LossFunction::Evaluate (Ceres 1.14 loss_function.cc) for the three types
@@ -202,6 +206,7 @@ struct Summary {
   int num_successful_steps, num_unsuccessful_steps, termination;  // 0 convergence, 1 no convergence, 2 failure
   int num_residuals, num_effective_parameters;
   double seconds;
+  long num_linear_iterations = 0;  // CG iterations over all LM iterations (ITERATIVE_SCHUR)
 };
 
 struct Layout {
@@ -349,6 +354,79 @@ struct Solver {
   }
 };
 
+
+// ------------------------------------------------------------------ ITERATIVE_SCHUR
+// Ceres 1.14 (external; restated from its published sources): iterative_schur_complement_solver.cc
+// runs ConjugateGradientsSolver on the ImplicitSchurComplement operator
+//   S x = (F'F + D_f^2) x - F'E (E'E + D_e^2)^-1 E'F x        (implicit_schur_complement.cc)
+// (E = point columns, F = camera-side columns of the Jacobian, never forming S), preconditioned by
+// SCHUR_JACOBI = the inverse of the block diagonal of S, one block per camera-side PARAMETER BLOCK
+// (schur_jacobi_preconditioner.cc).  colmap adds qvec, tvec and the camera parameters as three
+// separate blocks (bundle_adjustment.cc:383-418), so the blocks are 3x3 (rotation, local), <=3x3
+// (variable tvec components) and <=4x4 (variable intrinsics, possibly shared by many images).
+// The start vector is zero, r_tolerance = -1 (off) and q_tolerance = eta = 0.1
+// (levenberg_marquardt_strategy.cc, Solver::Options::eta default), residual_reset_period = 10.
+struct BlockDiag {
+  std::vector<int> first, size;  // per column: first column and size of its parameter block
+  std::vector<double> M;         // [D][4]: row `col`, entries (col, first + j)
+};
+static BlockDiag MakeBlocks(const Problem& P, const Layout& L) {
+  BlockDiag B;
+  const int D = L.n_cam_cols;
+  B.first.assign(std::max(D, 1), 0);
+  B.size.assign(std::max(D, 1), 0);
+  auto mark = [&](const int* cols, int n) {
+    int f = -1, cnt = 0;
+    for (int k = 0; k < n; ++k) if (cols[k] >= 0) { if (f < 0) f = cols[k]; ++cnt; }
+    for (int k = 0; k < n; ++k) if (cols[k] >= 0) { B.first[cols[k]] = f; B.size[cols[k]] = cnt; }
+  };
+  for (int i = 0; i < P.n_img; ++i) { mark(&L.pose_col[6 * i], 3); mark(&L.pose_col[6 * i + 3], 3); }
+  for (int c = 0; c < P.n_cam; ++c) mark(&L.intr_col[4 * c], 4);
+  B.M.assign((size_t)std::max(D, 1) * 4, 0.0);
+  return B;
+}
+// BlockRandomAccessDiagonalMatrix::Invert: block.llt().solve(Identity); returns false if a block is not PD
+static bool InvertBlocks(BlockDiag& B, int D) {
+  for (int f = 0; f < D; f += B.size[f]) {
+    const int n = B.size[f];
+    double A[4][4], Lc[4][4] = {{0}}, Inv[4][4];
+    for (int r = 0; r < n; ++r) for (int c = 0; c < n; ++c) A[r][c] = B.M[(size_t)(f + r) * 4 + c];
+    for (int j = 0; j < n; ++j) {
+      double d = A[j][j];
+      for (int k = 0; k < j; ++k) d -= Lc[j][k] * Lc[j][k];
+      if (!(d > 0)) return false;
+      Lc[j][j] = std::sqrt(d);
+      for (int i = j + 1; i < n; ++i) {
+        double v = A[i][j];
+        for (int k = 0; k < j; ++k) v -= Lc[i][k] * Lc[j][k];
+        Lc[i][j] = v / Lc[j][j];
+      }
+    }
+    for (int c = 0; c < n; ++c) {  // solve L L^T x = e_c
+      double y[4];
+      for (int i = 0; i < n; ++i) {
+        double v = (i == c) ? 1.0 : 0.0;
+        for (int k = 0; k < i; ++k) v -= Lc[i][k] * y[k];
+        y[i] = v / Lc[i][i];
+      }
+      for (int i = n - 1; i >= 0; --i) {
+        double v = y[i];
+        for (int k = i + 1; k < n; ++k) v -= Lc[k][i] * Inv[k][c];
+        Inv[i][c] = v / Lc[i][i];
+      }
+    }
+    for (int r = 0; r < n; ++r) for (int c = 0; c < n; ++c) B.M[(size_t)(f + r) * 4 + c] = Inv[r][c];
+  }
+  return true;
+}
+static void ApplyBlocks(const BlockDiag& B, int D, const double* r, double* z) {
+  for (int j = 0; j < D; ++j) {
+    double v = 0;
+    for (int k = 0; k < B.size[j]; ++k) v += B.M[(size_t)j * 4 + k] * r[B.first[j] + k];
+    z[j] = v;
+  }
+}
+
 static void Solve(Problem P, Options O, Summary* S) {
   const auto t_start = std::chrono::steady_clock::now();
   Solver sv;
@@ -440,6 +518,174 @@ static void Solve(Problem P, Options O, Summary* S) {
     std::vector<double> lm_c(D), lm_p(3 * NP);
     for (int j = 0; j < D; ++j) lm_c[j] = std::min(std::max(diag_c[j], min_diag), max_diag) / radius;
     for (int j = 0; j < 3 * NP; ++j) lm_p[j] = std::min(std::max(diag_p[j], min_diag), max_diag) / radius;
+    bool ok = true;
+    if (O.linear_solver == 1) {
+      // ---- ITERATIVE_SCHUR: (E'E + D_e^2)^-1 per point, then CG on the implicit operator
+#pragma omp parallel for schedule(static)
+      for (int p = 0; p < P.n_pts; ++p) {
+        const int pc = L.pt_col[p];
+        if (pc < 0) continue;
+        double V[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+        for (long o = sv.pt_start[p]; o < sv.pt_start[p + 1]; ++o) {
+          const ObsJ& e = sv.J[o];
+          for (int a = 0; a < 2; ++a)
+            for (int k = 0; k < 3; ++k)
+              for (int l = 0; l < 3; ++l) V[k][l] += e.Jp[a][k] * e.Jp[a][l];
+        }
+        for (int k = 0; k < 3; ++k) V[k][k] += lm_p[3 * pc + k];
+        const double c00 = V[1][1] * V[2][2] - V[1][2] * V[2][1], c01 = V[1][2] * V[2][0] - V[1][0] * V[2][2],
+                     c02 = V[1][0] * V[2][1] - V[1][1] * V[2][0];
+        const double det = V[0][0] * c00 + V[0][1] * c01 + V[0][2] * c02, id = 1.0 / det;
+        double* Vi = &Vinv[(size_t)pc * 9];
+        Vi[0] = c00 * id; Vi[1] = (V[0][2] * V[2][1] - V[0][1] * V[2][2]) * id; Vi[2] = (V[0][1] * V[1][2] - V[0][2] * V[1][1]) * id;
+        Vi[3] = c01 * id; Vi[4] = (V[0][0] * V[2][2] - V[0][2] * V[2][0]) * id; Vi[5] = (V[0][2] * V[1][0] - V[0][0] * V[1][2]) * id;
+        Vi[6] = c02 * id; Vi[7] = (V[0][1] * V[2][0] - V[0][0] * V[2][1]) * id; Vi[8] = (V[0][0] * V[1][1] - V[0][1] * V[1][0]) * id;
+      }
+      // S x in residual space (ImplicitSchurComplement::RightMultiply): y1 = F x; y3 = -(E'E)^-1 E' y1;
+      // y1 += E y3; out = D_f^2 x + F' y1
+      auto SchurMul = [&](const std::vector<double>& x, std::vector<double>& out) {
+        for (int j = 0; j < D; ++j) out[j] = lm_c[j] * x[j];
+        for (int p = 0; p < P.n_pts; ++p) {
+          const int pc = L.pt_col[p];
+          const long o0 = sv.pt_start[p], o1 = sv.pt_start[p + 1];
+          double y2[3] = {0, 0, 0}, z[3] = {0, 0, 0};
+          if (pc >= 0) {
+            for (long o = o0; o < o1; ++o) {
+              const ObsJ& e = sv.J[o];
+              for (int a = 0; a < 2; ++a) {
+                double u = 0;
+                for (int k = 0; k < 10; ++k) if (e.col[k] >= 0) u += e.Jc[a][k] * x[e.col[k]];
+                for (int k = 0; k < 3; ++k) y2[k] += e.Jp[a][k] * u;
+              }
+            }
+            const double* Vi = &Vinv[(size_t)pc * 9];
+            for (int k = 0; k < 3; ++k) z[k] = Vi[3 * k] * y2[0] + Vi[3 * k + 1] * y2[1] + Vi[3 * k + 2] * y2[2];
+          }
+          for (long o = o0; o < o1; ++o) {
+            const ObsJ& e = sv.J[o];
+            for (int a = 0; a < 2; ++a) {
+              double u = 0;
+              for (int k = 0; k < 10; ++k) if (e.col[k] >= 0) u += e.Jc[a][k] * x[e.col[k]];
+              u -= e.Jp[a][0] * z[0] + e.Jp[a][1] * z[1] + e.Jp[a][2] * z[2];
+              for (int k = 0; k < 10; ++k) if (e.col[k] >= 0) out[e.col[k]] += e.Jc[a][k] * u;
+            }
+          }
+        }
+      };
+      // rhs = F'(b - E (E'E)^-1 E'b)   (ImplicitSchurComplement::UpdateRhs; b = the residual vector here)
+      std::vector<double> rhs(std::max(D, 1), 0.0);
+      for (int p = 0; p < P.n_pts; ++p) {
+        const int pc = L.pt_col[p];
+        double tp[3] = {0, 0, 0};
+        if (pc >= 0) {
+          const double* Vi = &Vinv[(size_t)pc * 9];
+          for (int k = 0; k < 3; ++k) tp[k] = Vi[3 * k] * gp[3 * pc] + Vi[3 * k + 1] * gp[3 * pc + 1] + Vi[3 * k + 2] * gp[3 * pc + 2];
+        }
+        for (long o = sv.pt_start[p]; o < sv.pt_start[p + 1]; ++o) {
+          const ObsJ& e = sv.J[o];
+          for (int a = 0; a < 2; ++a) {
+            const double u = e.r[a] - (e.Jp[a][0] * tp[0] + e.Jp[a][1] * tp[1] + e.Jp[a][2] * tp[2]);
+            for (int k = 0; k < 10; ++k) if (e.col[k] >= 0) rhs[e.col[k]] += e.Jc[a][k] * u;
+          }
+        }
+      }
+      // SCHUR_JACOBI: block diagonal of S, inverted
+      BlockDiag B = MakeBlocks(P, L);
+      for (int j = 0; j < D; ++j) B.M[(size_t)j * 4 + (j - B.first[j])] += lm_c[j];
+      for (int p = 0; p < P.n_pts; ++p) {
+        const int pc = L.pt_col[p];
+        const long o0 = sv.pt_start[p], o1 = sv.pt_start[p + 1];
+        const double* Vi = pc >= 0 ? &Vinv[(size_t)pc * 9] : nullptr;
+        for (long oa = o0; oa < o1; ++oa) {
+          const ObsJ& ea = sv.J[oa];
+          for (int k = 0; k < 10; ++k) {  // U = F'F restricted to the blocks
+            if (ea.col[k] < 0) continue;
+            for (int l = 0; l < 10; ++l)
+              if (ea.col[l] >= 0 && B.first[ea.col[l]] == B.first[ea.col[k]])
+                B.M[(size_t)ea.col[k] * 4 + (ea.col[l] - B.first[ea.col[l]])] += ea.Jc[0][k] * ea.Jc[0][l] + ea.Jc[1][k] * ea.Jc[1][l];
+          }
+          if (!Vi) continue;
+          double Ya[30];
+          for (int k = 0; k < 10; ++k) {
+            double w[3];
+            for (int l = 0; l < 3; ++l) w[l] = ea.Jc[0][k] * ea.Jp[0][l] + ea.Jc[1][k] * ea.Jp[1][l];
+            for (int l = 0; l < 3; ++l) Ya[3 * k + l] = w[0] * Vi[l] + w[1] * Vi[3 + l] + w[2] * Vi[6 + l];
+          }
+          for (long ob = o0; ob < o1; ++ob) {
+            const ObsJ& eb = sv.J[ob];
+            for (int k = 0; k < 10; ++k) {
+              if (ea.col[k] < 0) continue;
+              for (int l = 0; l < 10; ++l) {
+                if (eb.col[l] < 0 || B.first[eb.col[l]] != B.first[ea.col[k]]) continue;
+                double wb[3];
+                for (int m = 0; m < 3; ++m) wb[m] = eb.Jc[0][l] * eb.Jp[0][m] + eb.Jc[1][l] * eb.Jp[1][m];
+                B.M[(size_t)ea.col[k] * 4 + (eb.col[l] - B.first[eb.col[l]])] -= Ya[3 * k] * wb[0] + Ya[3 * k + 1] * wb[1] + Ya[3 * k + 2] * wb[2];
+              }
+            }
+          }
+        }
+      }
+      ok = InvertBlocks(B, D);
+      // ConjugateGradientsSolver::Solve (conjugate_gradients_solver.cc), x0 = 0
+      std::vector<double> x(std::max(D, 1), 0.0);
+      if (ok && D > 0) {
+        std::vector<double> r(D), pvec(D), z(D), tmp(D);
+        double norm_b = 0;
+        for (int j = 0; j < D; ++j) norm_b += rhs[j] * rhs[j];
+        norm_b = std::sqrt(norm_b);
+        if (norm_b != 0.0) {
+          const double q_tolerance = 0.1, tol_r = -1.0 * norm_b;
+          const int residual_reset_period = 10, min_num_iterations = 0;
+          SchurMul(x, tmp);
+          for (int j = 0; j < D; ++j) r[j] = rhs[j] - tmp[j];
+          double rho = 1.0, Q0 = 0;
+          for (int j = 0; j < D; ++j) Q0 += x[j] * (rhs[j] + r[j]);
+          Q0 = -1.0 * Q0;
+          for (int it = 1;; ++it) {
+            S->num_linear_iterations++;
+            ApplyBlocks(B, D, r.data(), z.data());
+            const double last_rho = rho;
+            rho = 0;
+            for (int j = 0; j < D; ++j) rho += r[j] * z[j];
+            if (rho == 0.0 || std::isinf(rho)) { ok = false; break; }  // LINEAR_SOLVER_FAILURE
+            if (it == 1) {
+              pvec = z;
+            } else {
+              const double beta = rho / last_rho;
+              if (beta == 0.0 || std::isinf(beta)) { ok = false; break; }
+              for (int j = 0; j < D; ++j) pvec[j] = z[j] + beta * pvec[j];
+            }
+            std::vector<double>& q = z;
+            SchurMul(pvec, q);
+            double pq = 0;
+            for (int j = 0; j < D; ++j) pq += pvec[j] * q[j];
+            if (pq <= 0 || std::isinf(pq)) break;  // NO_CONVERGENCE: the current x is still used
+            const double alpha = rho / pq;
+            if (std::isinf(alpha)) { ok = false; break; }
+            for (int j = 0; j < D; ++j) x[j] = x[j] + alpha * pvec[j];
+            if (it % residual_reset_period == 0) {
+              SchurMul(x, tmp);
+              for (int j = 0; j < D; ++j) r[j] = rhs[j] - tmp[j];
+            } else {
+              for (int j = 0; j < D; ++j) r[j] = r[j] - alpha * q[j];
+            }
+            double Q1 = 0;
+            for (int j = 0; j < D; ++j) Q1 += x[j] * (rhs[j] + r[j]);
+            Q1 = -1.0 * Q1;
+            const double zeta = it * (Q1 - Q0) / Q1;
+            if (zeta < q_tolerance && it >= min_num_iterations) break;
+            Q0 = Q1;
+            double norm_r = 0;
+            for (int j = 0; j < D; ++j) norm_r += r[j] * r[j];
+            norm_r = std::sqrt(norm_r);
+            if (norm_r <= tol_r && it >= min_num_iterations) break;
+            if (it >= O.max_linear_solver_iterations) break;
+          }
+        }
+        for (int j = 0; j < D; ++j) if (!std::isfinite(x[j])) ok = false;  // IsArrayValid
+      }
+      for (int j = 0; j < D; ++j) dc[j] = -x[j];
+    } else {
     // Schur complement: S = U + D_c - sum_p W V^-1 W^T ; rhs = g_c - sum_p W V^-1 g_p
     Smat.assign((size_t)D * D, 0.0);
     std::vector<double> rhs(gc.begin(), gc.begin() + D);
@@ -512,12 +758,12 @@ static void Solve(Problem P, Options O, Summary* S) {
       }
     }
     // solve S y = rhs ; step_c = -y
-    bool ok = true;
     if (D > 0) {
       dc.assign(rhs.begin(), rhs.end());
       ok = CholeskySolve(Smat, D, dc);
       for (int j = 0; j < D; ++j) dc[j] = -dc[j];
     }
+    }  // exact Schur step
     if (ok) {
       // back-substitution: dp = -V^-1 (g_p + W^T dc)
 #pragma omp parallel for schedule(static)
@@ -624,8 +870,8 @@ struct orc_ba_problem {
   double* xyz; const uint8_t* pt_const;
   const int32_t* obs_img; const int32_t* obs_pt; const double* obs_xy;
 };
-struct orc_ba_options { int32_t max_num_iterations; double function_tolerance, gradient_tolerance, parameter_tolerance; int32_t n_threads; int32_t loss_type; double loss_scale; };
-struct orc_ba_summary { double initial_cost, final_cost; int32_t num_successful_steps, num_unsuccessful_steps, termination, num_residuals, num_effective_parameters; double seconds; };
+struct orc_ba_options { int32_t max_num_iterations; double function_tolerance, gradient_tolerance, parameter_tolerance; int32_t n_threads; int32_t loss_type; double loss_scale; int32_t linear_solver, max_linear_solver_iterations; };
+struct orc_ba_summary { double initial_cost, final_cost; int32_t num_successful_steps, num_unsuccessful_steps, termination, num_residuals, num_effective_parameters; double seconds; int64_t num_linear_iterations; };
 
 void orc_ba_solve(const orc_ba_problem* p, const orc_ba_options* o, orc_ba_summary* s) {
   ba::Problem P;
@@ -638,12 +884,14 @@ void orc_ba_solve(const orc_ba_problem* p, const orc_ba_options* o, orc_ba_summa
   O.max_num_iterations = o->max_num_iterations; O.function_tolerance = o->function_tolerance;
   O.gradient_tolerance = o->gradient_tolerance; O.parameter_tolerance = o->parameter_tolerance; O.n_threads = o->n_threads;
   O.loss_type = o->loss_type; O.loss_scale = o->loss_scale;
+  O.linear_solver = o->linear_solver; O.max_linear_solver_iterations = o->max_linear_solver_iterations;
   ba::Summary S;
   ba::Solve(P, O, &S);
   s->initial_cost = S.initial_cost; s->final_cost = S.final_cost;
   s->num_successful_steps = S.num_successful_steps; s->num_unsuccessful_steps = S.num_unsuccessful_steps;
   s->termination = S.termination; s->num_residuals = S.num_residuals; s->num_effective_parameters = S.num_effective_parameters;
   s->seconds = S.seconds;
+  s->num_linear_iterations = S.num_linear_iterations;
 }
 
 // residual + local Jacobians of one observation (tests: cost_functions_test.cc goldens, finite differences)

@@ -385,18 +385,21 @@ class OrcBaProblem(C.Structure):
 class OrcBaOptions(C.Structure):
     _fields_ = [("max_num_iterations", C.c_int32), ("function_tolerance", C.c_double),
                 ("gradient_tolerance", C.c_double), ("parameter_tolerance", C.c_double), ("n_threads", C.c_int32),
-                ("loss_type", C.c_int32), ("loss_scale", C.c_double)]
+                ("loss_type", C.c_int32), ("loss_scale", C.c_double),
+                ("linear_solver", C.c_int32), ("max_linear_solver_iterations", C.c_int32)]
 
 
 class OrcBaSummary(C.Structure):
     _fields_ = [("initial_cost", C.c_double), ("final_cost", C.c_double), ("num_successful_steps", C.c_int32),
                 ("num_unsuccessful_steps", C.c_int32), ("termination", C.c_int32), ("num_residuals", C.c_int32),
-                ("num_effective_parameters", C.c_int32), ("seconds", C.c_double)]
+                ("num_effective_parameters", C.c_int32), ("seconds", C.c_double),
+                ("num_linear_iterations", C.c_int64)]
 
 
 def ba_solve(prob: dict, max_num_iterations=50, function_tolerance=0.0, gradient_tolerance=1.0,
-             parameter_tolerance=0.0, loss_type=0, loss_scale=1.0):
-    """prob: dict of numpy arrays (see tests/ba_scene.py); qvec/tvec/cam_params/xyz are updated in place."""
+             parameter_tolerance=0.0, loss_type=0, loss_scale=1.0, linear_solver=0, max_linear_solver_iterations=100):
+    """prob: dict of numpy arrays (see tests/ba_scene.py); qvec/tvec/cam_params/xyz are updated in place.
+    linear_solver: 0 exact Schur step (DENSE/SPARSE_SCHUR), 1 ITERATIVE_SCHUR + SCHUR_JACOBI."""
     L = lib()
     L.orc_ba_solve.argtypes = [C.POINTER(OrcBaProblem), C.POINTER(OrcBaOptions), C.POINTER(OrcBaSummary)]
     L.orc_ba_solve.restype = None
@@ -408,7 +411,7 @@ def ba_solve(prob: dict, max_num_iterations=50, function_tolerance=0.0, gradient
         setattr(p, k, prob[k].ctypes.data)
     p.refine_focal, p.refine_principal, p.refine_extra = prob.get("refine", (1, 0, 1))
     o = OrcBaOptions(max_num_iterations, function_tolerance, gradient_tolerance, parameter_tolerance, 0,
-                     int(loss_type), float(loss_scale))
+                     int(loss_type), float(loss_scale), int(linear_solver), int(max_linear_solver_iterations))
     s = OrcBaSummary()
     L.orc_ba_solve(C.byref(p), C.byref(o), C.byref(s))
     return s

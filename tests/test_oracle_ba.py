@@ -84,3 +84,27 @@ def test_converges_to_noise_floor():
     s = orc.ba_solve(prob, max_num_iterations=50)
     assert 1.2 < reprojection_rms(prob) < 1.7
     assert s.num_effective_parameters == 300 * 3 + 11 * 6 - 1 + 2
+
+
+def test_iterative_schur_restatement_reaches_the_exact_schur_optimum():
+    """ITERATIVE_SCHUR + SCHUR_JACOBI (what BundleAdjuster::Solve selects above 1000 images,
+    bundle_adjustment.cc:274-284): the matrix-free Schur product, the block-Jacobi preconditioner and Ceres'
+    CG loop are restated independently of the dense exact-step branch; both must stop at the same optimum, the
+    inexact steps must never increase the cost, and the inner-iteration cap must hold."""
+    T = dict(max_num_iterations=200, gradient_tolerance=1e-9, function_tolerance=1e-16)
+    for kw in (dict(n_img=12, n_pts=300, track_len=5, seed=4), dict(n_img=8, n_pts=80, track_len=5, seed=3, shared_camera=True),
+               dict(n_img=9, n_pts=120, track_len=4, seed=8, n_const_pts=30)):
+        p_ex = make_ba_problem(**kw)
+        p_it = copy_problem(p_ex)
+        s_ex, s_it = orc.ba_solve(p_ex, **T), orc.ba_solve(p_it, linear_solver=1, **T)
+        assert s_it.num_linear_iterations > 0
+        assert s_it.final_cost == __import__("pytest").approx(s_ex.final_cost, rel=1e-10)
+        assert abs(reprojection_rms(p_ex) - reprojection_rms(p_it)) < 1e-9
+        assert np.abs(p_ex["xyz"] - p_it["xyz"]).max() < 1e-6
+    costs = []
+    for n in range(1, 6):   # cost after n LM iterations is non-increasing; at most 4 inner iterations per step
+        p = make_ba_problem(n_img=12, n_pts=300, track_len=5, seed=4)
+        s = orc.ba_solve(p, linear_solver=1, max_num_iterations=n, max_linear_solver_iterations=4)
+        assert s.num_linear_iterations <= 4 * n
+        costs.append(s.final_cost)
+    assert all(b <= a for a, b in zip(costs, costs[1:])) and costs[-1] < costs[0]

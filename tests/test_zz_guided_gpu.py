@@ -238,3 +238,71 @@ def test_pair_major_schur_matches_production_on_gpu(monkeypatch):
                == (s_cpu.num_successful_steps, s_cpu.num_unsuccessful_steps)
         assert s_pm.final_cost == pytest.approx(s_cpu.final_cost, rel=1e-9)
         assert abs(reprojection_rms(p_pm) - reprojection_rms(p_cpu)) < 1e-6
+
+
+FIRST_RUN_ITER = pytest.mark.xfail(strict=False, reason="first GPU execution of the ITERATIVE_SCHUR kernels (written after the "
+                                   "round's GPU budget was spent; verified on the CUDA emulator, tests/test_emu_ba.py)")
+
+
+@pytest.mark.gpu
+@FIRST_RUN_ITER
+@pytest.mark.parametrize("kw", [
+    dict(n_img=12, n_pts=300, track_len=5, seed=4),
+    dict(n_img=8, n_pts=80, track_len=5, seed=3, shared_camera=True),
+    dict(n_img=40, n_pts=30, track_len=36, seed=6),
+    dict(n_img=60, n_pts=4000, track_len=6, seed=9, n_const_pts=100),
+])
+def test_iterative_schur_matches_oracle_on_gpu(kw):
+    """ITERATIVE_SCHUR + SCHUR_JACOBI (bundle_adjustment.cc:274-284, the regime of the 10k-image final BA): the
+    matrix-free Schur product / block-Jacobi / CG kernels of ba_iterative.cu against the oracle's restatement of
+    Ceres' inexact-step loop: same optimum within 1e-6 px, and with the final-BA options the same LM path."""
+    from dagsfm_b200 import BundleAdjuster, BundleAdjustmentOptions
+    from tests.ba_scene import copy_problem, make_ba_problem, reprojection_rms
+    p_gpu = make_ba_problem(**kw)
+    p_cpu = copy_problem(p_gpu)
+    o = BundleAdjustmentOptions.default()
+    o.max_num_iterations, o.gradient_tolerance, o.function_tolerance = 200, 1e-9, 1e-16
+    o.linear_solver_type = BundleAdjustmentOptions.ITERATIVE_SCHUR
+    ba = BundleAdjuster(o)
+    try:
+        s_gpu = ba.Solve(p_gpu)
+    finally:
+        ba.close()
+    s_cpu = orc.ba_solve(p_cpu, max_num_iterations=200, gradient_tolerance=1e-9, function_tolerance=1e-16, linear_solver=1)
+    assert s_gpu.linear_solver_type_used == 2 and s_gpu.num_linear_solver_iterations > 0
+    assert s_gpu.initial_cost == pytest.approx(s_cpu.initial_cost, rel=1e-12)
+    assert s_gpu.final_cost == pytest.approx(s_cpu.final_cost, rel=1e-9)
+    assert abs(reprojection_rms(p_gpu) - reprojection_rms(p_cpu)) < 1e-6
+    # final-BA options: same accepted / rejected steps and termination
+    p_gpu = make_ba_problem(**kw)
+    p_cpu = copy_problem(p_gpu)
+    o = BundleAdjustmentOptions.default()
+    o.linear_solver_type = BundleAdjustmentOptions.ITERATIVE_SCHUR
+    ba = BundleAdjuster(o)
+    try:
+        s_gpu = ba.Solve(p_gpu)
+    finally:
+        ba.close()
+    s_cpu = orc.ba_solve(p_cpu, linear_solver=1)
+    assert (s_gpu.num_successful_steps, s_gpu.num_unsuccessful_steps, s_gpu.termination_type) == \
+           (s_cpu.num_successful_steps, s_cpu.num_unsuccessful_steps, s_cpu.termination)
+    assert abs(s_gpu.num_linear_solver_iterations - s_cpu.num_linear_iterations) <= 0.25 * s_cpu.num_linear_iterations + 2
+    assert abs(reprojection_rms(p_gpu) - reprojection_rms(p_cpu)) < 1e-6
+
+
+@pytest.mark.gpu
+@FIRST_RUN_ITER
+def test_iterative_schur_is_selected_above_1000_images_on_gpu():
+    from dagsfm_b200 import BundleAdjuster, BundleAdjustmentOptions
+    from tests.ba_scene import copy_problem, make_ba_problem, reprojection_rms
+    p_gpu = make_ba_problem(n_img=1200, n_pts=20000, track_len=6, seed=5)
+    p_cpu = copy_problem(p_gpu)
+    ba = BundleAdjuster(BundleAdjustmentOptions.default())
+    try:
+        s_gpu = ba.Solve(p_gpu)
+    finally:
+        ba.close()
+    s_cpu = orc.ba_solve(p_cpu, linear_solver=1)
+    assert s_gpu.linear_solver_type_used == 2
+    assert s_gpu.final_cost == pytest.approx(s_cpu.final_cost, rel=1e-6)
+    assert abs(reprojection_rms(p_gpu) - reprojection_rms(p_cpu)) < 1e-6
