@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=48, help="pairs in the CPU baseline sample")
     ap.add_argument("--verify-pairs", type=int, default=20000, help="pairs in the verification leg (0 = skip)")
     ap.add_argument("--ba", default="500,100000,10", help="BA leg: images,points,track (empty = skip)")
+    ap.add_argument("--ba-solver", default="auto", choices=["auto", "exact", "iterative"],
+                    help="BA leg: linear solver (auto = the reference's rule: ITERATIVE_SCHUR above 1000 images)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -245,6 +247,7 @@ def bench_ba(a, local_rank, rank, world, cores, barrier, hbm):
     n_obs = len(prob0["obs_img"])
     n_obs_total = n_obs
     opt = BundleAdjustmentOptions.default()
+    opt.linear_solver_type = {"auto": 0, "exact": 1, "iterative": 2}[a.ba_solver]
     ba = BundleAdjuster(opt, device=local_rank)
     full0 = prob0
     if world > 1:   # points sharded over the ranks, one NCCL all-reduce of (S, rhs, g_c, diag) per LM iteration
@@ -281,7 +284,21 @@ def bench_ba(a, local_rank, rank, world, cores, barrier, hbm):
                         "algorithmic_bytes_per_iteration": alg_bytes, "avg_ms_per_iteration": schur_ms,
                         "share_of_solve": s.schur_kernel_seconds / s.solve_seconds, "traffic": None,
                         "note": "FP64 atomics into the dense reduced system dominate; see DESIGN.md"}}
-    if (n_img, n_pts, track) == (500, 100000, 10) and world == 1:
+    out["linear_solver"] = "ITERATIVE_SCHUR + SCHUR_JACOBI" if s.linear_solver_type_used == 2 else "exact Schur step (dense Cholesky)"
+    if s.linear_solver_type_used == 2:
+        # matrix-free Schur product: both passes stream the 224 B Jacobian block of every observation once per CG
+        # iteration (+ 12 B of indices), z_p is written and read once
+        cg = max(int(s.num_linear_solver_iterations), 1)
+        alg_cg = (2 * 224 + 12) * n_obs + 2 * 24 * n_pts
+        lin_ms = 1e3 * s.schur_kernel_seconds / cg
+        out["cg_iterations"] = int(s.num_linear_solver_iterations)
+        out["roofline"] = {"bound": "hbm", "kernel": "matvec_point_kernel + image_pass_kernel<0> (per CG iteration; includes the "
+                           "preconditioner set-up and the host-side reductions of the inner solve)",
+                           "achieved": alg_cg / (lin_ms * 1e-3) / 1e9, "peak": hbm[0], "unit": "GB/s",
+                           "frac": alg_cg / (lin_ms * 1e-3) / 1e9 / hbm[0], "peak_source": hbm[1],
+                           "algorithmic_bytes_per_cg_iteration": alg_cg, "avg_ms_per_cg_iteration": lin_ms,
+                           "share_of_solve": s.schur_kernel_seconds / s.solve_seconds, "traffic": None}
+    if (n_img, n_pts, track) == (500, 100000, 10) and world == 1 and s.linear_solver_type_used == 1:
         # committed ncu captures of one iteration at exactly this workload: schur_kernel 234.7 + 11.8 MB
         # (profiles/r1_ba_schur_ncu_full.txt), camera_terms_kernel 228.8 + 3.5 MB (r1_ba_camera_terms_ncu_full.txt);
         # 4.9x the algorithmic bytes because both kernels re-read the 224 B/observation Jacobian blocks

@@ -288,3 +288,23 @@ def test_iterative_schur_allreduce_hook_two_shards(emu):
     assert s_a.final_cost == s_b.final_cost and s_a.num_linear_solver_iterations == s_b.num_linear_solver_iterations
     D = s_a.num_effective_parameters_reduced - 3 * 100
     assert (D, 0) in calls and (4 * D, 0) in calls and (3 * D, 0) in calls and (1, 1) in calls
+
+
+@pytest.mark.parametrize("solver", ["auto", "iterative"])
+def test_bench_ba_leg_runs_on_the_emulated_library(emu, solver):
+    """bench.py's BA leg (the code the driver runs on the GPU box) end to end on the emulated library: both solver
+    settings produce a complete result dictionary with a finite roofline entry."""
+    import sys
+    import types
+    argv, sys.argv = sys.argv, ["bench.py"]
+    try:
+        import bench
+    finally:
+        sys.argv = argv
+    a = types.SimpleNamespace(ba="8,60,4", ba_solver=solver, no_cpu=True)
+    out = bench.bench_ba(a, 0, 0, 1, 1, lambda: None, (6490.5, "test"))
+    assert out["rms_px_final"] < out["rms_px_initial"] and out["termination"] == 0
+    assert np.isfinite(out["roofline"]["achieved"]) and out["roofline"]["frac"] > 0
+    assert ("ITERATIVE" in out["linear_solver"]) == (solver == "iterative")
+    if solver == "iterative":
+        assert out["cg_iterations"] > 0
