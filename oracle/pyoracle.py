@@ -438,6 +438,90 @@ def ba_quat_plus(x, d):
     return out
 
 
+
+# ------------------------------------------------- relative pose
+class OrcRelPose(C.Structure):
+    _fields_ = [("qvec", C.c_double * 4), ("tvec", C.c_double * 3), ("tri_angle", C.c_double),
+                ("config", C.c_int32), ("n_points3D", C.c_int32)]
+
+
+def decompose_essential(E):
+    E = _p(E); R1 = np.zeros((3, 3)); R2 = np.zeros((3, 3)); t = np.zeros(3)
+    _tv().orc_decompose_essential(C.c_void_p(E.ctypes.data), C.c_void_p(R1.ctypes.data), C.c_void_p(R2.ctypes.data), C.c_void_p(t.ctypes.data))
+    return R1, R2, t
+
+
+def pose_from_essential(E, p1, p2):
+    E, p1, p2 = _p(E), _p(p1), _p(p2)
+    R = np.zeros((3, 3)); t = np.zeros(3); X = np.zeros((max(len(p1), 1), 3))
+    f = _tv().orc_pose_from_essential
+    f.restype = C.c_int
+    n = f(C.c_void_p(E.ctypes.data), len(p1), C.c_void_p(p1.ctypes.data), C.c_void_p(p2.ctypes.data), C.c_void_p(R.ctypes.data),
+          C.c_void_p(t.ctypes.data), C.c_void_p(X.ctypes.data))
+    return R, t, X[:n]
+
+
+def decompose_homography(H, K1, K2):
+    H, K1, K2 = _p(H), _p(K1), _p(K2)
+    R = np.zeros((4, 3, 3)); t = np.zeros((4, 3)); nrm = np.zeros((4, 3))
+    f = _tv().orc_decompose_homography
+    f.restype = C.c_int
+    n = f(C.c_void_p(H.ctypes.data), C.c_void_p(K1.ctypes.data), C.c_void_p(K2.ctypes.data), C.c_void_p(R.ctypes.data),
+          C.c_void_p(t.ctypes.data), C.c_void_p(nrm.ctypes.data))
+    return R[:n], t[:n], nrm[:n]
+
+
+def pose_from_homography(H, K1, K2, p1, p2):
+    H, K1, K2, p1, p2 = _p(H), _p(K1), _p(K2), _p(p1), _p(p2)
+    R = np.zeros((3, 3)); t = np.zeros(3); nrm = np.zeros(3); X = np.zeros((max(len(p1), 1), 3))
+    f = _tv().orc_pose_from_homography
+    f.restype = C.c_int
+    n = f(C.c_void_p(H.ctypes.data), C.c_void_p(K1.ctypes.data), C.c_void_p(K2.ctypes.data), len(p1), C.c_void_p(p1.ctypes.data),
+          C.c_void_p(p2.ctypes.data), C.c_void_p(R.ctypes.data), C.c_void_p(t.ctypes.data), C.c_void_p(nrm.ctypes.data),
+          C.c_void_p(X.ctypes.data))
+    return R, t, nrm, X[:n]
+
+
+def triangulate_point(R, t, p1, p2):
+    R, t, p1, p2 = _p(R), _p(t), _p(p1), _p(p2)
+    X = np.zeros(3)
+    _tv().orc_triangulate_point(C.c_void_p(R.ctypes.data), C.c_void_p(t.ctypes.data), C.c_void_p(p1.ctypes.data),
+                                C.c_void_p(p2.ctypes.data), C.c_void_p(X.ctypes.data))
+    return X
+
+
+def triangulation_angles(R, t, points3D):
+    R, t, X = _p(R), _p(t), _p(points3D)
+    a = np.zeros(len(X))
+    _tv().orc_triangulation_angles(C.c_void_p(R.ctypes.data), C.c_void_p(t.ctypes.data), len(X), C.c_void_p(X.ctypes.data),
+                                   C.c_void_p(a.ctypes.data))
+    return a
+
+
+def median(v):
+    v = _p(v)
+    f = _tv().orc_median
+    f.restype = C.c_double
+    return f(len(v), C.c_void_p(v.ctypes.data))
+
+
+def rotation_to_quaternion(R):
+    R = _p(R); q = np.zeros(4)
+    _tv().orc_rotation_to_quaternion(C.c_void_p(R.ctypes.data), C.c_void_p(q.ctypes.data))
+    return q
+
+
+def relative_pose(cam1, pts1, cam2, pts2, config, E, H, inlier_matches) -> OrcRelPose:
+    """The part of TwoViewGeometry::EstimateWithRelativePose after EstimateCalibrated (two_view_geometry.cc:239-289)."""
+    pts1, pts2, E, H = _p(pts1), _p(pts2), _p(E), _p(H)
+    m = np.ascontiguousarray(inlier_matches, dtype=np.uint32).reshape(-1, 2)
+    out = OrcRelPose()
+    f = _tv().orc_relative_pose
+    f.restype = None
+    f(C.byref(cam1), C.c_void_p(pts1.ctypes.data), C.byref(cam2), C.c_void_p(pts2.ctypes.data), int(config),
+      C.c_void_p(E.ctypes.data), C.c_void_p(H.ctypes.data), C.c_void_p(m.ctypes.data), len(m), C.byref(out))
+    return out
+
 # ------------------------------------------------- reference-owned BA (vendored PBA, oracle/_ref)
 PBA_REF_PATH = HERE / "_ref" / "libpba_ref.so"
 

@@ -1167,6 +1167,268 @@ static void EstimateTwoView(const Camera& c1, const Vec2* pts1, const Camera& c2
   }
 }
 
+// ============================================================ relative pose
+// TwoViewGeometry::EstimateWithRelativePose (two_view_geometry.cc:232-290) after EstimateCalibrated:
+//   DecomposeEssentialMatrix / PoseFromEssentialMatrix    src/base/essential_matrix.cc:41-88
+//   DecomposeHomographyMatrix / PoseFromHomographyMatrix  src/base/homography_matrix.cc:44-197
+//   CheckCheirality                                       src/base/pose.cc:225-248
+//   TriangulatePoint, CalculateTriangulationAnglesWithPM  src/base/triangulation.cc:38-51,183-215
+//   CalculateDepth                                        src/base/projection.cc:193-197
+//   Camera::CalibrationMatrix                             src/base/camera.cc:75-94
+//   RotationMatrixToQuaternion (Eigen::Quaterniond(R))    src/base/pose.cc:70-73
+//   Median                                                src/util/math.h:212-229
+// Eigen::JacobiSVD is replaced by the one-sided Jacobi SVD above.  A singular-vector pair (u_k, v_k)
+// is defined up to a common sign and, for E, the singular subspace of the double singular value up to a
+// rotation; the SET of four (R, t) candidates does not depend on either, their ORDER may, and the order
+// only matters when two candidates tie on the cheirality count (">=" keeps the later one).
+struct Vec3 { double v[3]; };
+static double det3(const Mat3& a) {
+  return a(0, 0) * (a(1, 1) * a(2, 2) - a(1, 2) * a(2, 1)) - a(0, 1) * (a(1, 0) * a(2, 2) - a(1, 2) * a(2, 0)) +
+         a(0, 2) * (a(1, 0) * a(2, 1) - a(1, 1) * a(2, 0));
+}
+static void DecomposeEssentialMatrix(const Mat3& E, Mat3* R1, Mat3* R2, Vec3* t) {
+  double sig[3], V[9], AV[9];
+  jacobi_svd(E.m, 3, 3, sig, V, AV);
+  Mat3 U, Vt;
+  // left singular vectors: columns of A V / sigma; the third (sigma ~ 0 for an essential matrix) completes
+  // the right-handed frame, as the det(U) < 0 => U *= -1 correction of the reference does
+  for (int k = 0; k < 2; ++k) {
+    double n = 0;
+    for (int r = 0; r < 3; ++r) n += AV[3 * r + k] * AV[3 * r + k];
+    n = std::sqrt(n);
+    for (int r = 0; r < 3; ++r) U(r, k) = n > 0 ? AV[3 * r + k] / n : (r == k ? 1.0 : 0.0);
+  }
+  U(0, 2) = U(1, 0) * U(2, 1) - U(2, 0) * U(1, 1);
+  U(1, 2) = U(2, 0) * U(0, 1) - U(0, 0) * U(2, 1);
+  U(2, 2) = U(0, 0) * U(1, 1) - U(1, 0) * U(0, 1);
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) Vt(r, c) = V[3 * c + r];
+  if (det3(U) < 0) for (double& x : U.m) x = -x;
+  if (det3(Vt) < 0) for (double& x : Vt.m) x = -x;
+  Mat3 W;
+  const double w[9] = {0, 1, 0, -1, 0, 0, 0, 0, 1};
+  memcpy(W.m, w, 72);
+  *R1 = mul(mul(U, W), Vt);
+  *R2 = mul(mul(U, transpose(W)), Vt);
+  const double n = std::sqrt(U(0, 2) * U(0, 2) + U(1, 2) * U(1, 2) + U(2, 2) * U(2, 2));
+  for (int r = 0; r < 3; ++r) t->v[r] = U(r, 2) / n;
+}
+// proj_matrix1 = [I | 0], proj_matrix2 = [R | t]
+static Vec3 TriangulatePoint(const Mat3& R, const Vec3& t, const Vec2& p1, const Vec2& p2) {
+  double A[16];
+  const double P1[3][4] = {{1, 0, 0, 0}, {0, 1, 0, 0}, {0, 0, 1, 0}};
+  double P2[3][4];
+  for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) P2[r][c] = R(r, c); P2[r][3] = t.v[r]; }
+  for (int c = 0; c < 4; ++c) {
+    A[c] = p1.x * P1[2][c] - P1[0][c];
+    A[4 + c] = p1.y * P1[2][c] - P1[1][c];
+    A[8 + c] = p2.x * P2[2][c] - P2[0][c];
+    A[12 + c] = p2.y * P2[2][c] - P2[1][c];
+  }
+  double sig[4], V[16];
+  jacobi_svd(A, 4, 4, sig, V, nullptr);
+  Vec3 X;
+  for (int r = 0; r < 3; ++r) X.v[r] = V[4 * r + 3] / V[4 * 3 + 3];
+  return X;
+}
+static bool CheckCheirality(const Mat3& R, const Vec3& t, const std::vector<Vec2>& p1, const std::vector<Vec2>& p2,
+                            std::vector<Vec3>* points3D) {
+  const double kMinDepth = std::numeric_limits<double>::epsilon();
+  double rt[3];
+  for (int c = 0; c < 3; ++c) rt[c] = R(0, c) * t.v[0] + R(1, c) * t.v[1] + R(2, c) * t.v[2];
+  const double max_depth = 1000.0f * std::sqrt(rt[0] * rt[0] + rt[1] * rt[1] + rt[2] * rt[2]);
+  // CalculateDepth: proj_z * |third column of the projection matrix|
+  const double n1 = 1.0;  // |(0, 0, 1)|
+  const double n2 = std::sqrt(R(0, 2) * R(0, 2) + R(1, 2) * R(1, 2) + R(2, 2) * R(2, 2));
+  points3D->clear();
+  for (size_t i = 0; i < p1.size(); ++i) {
+    const Vec3 X = TriangulatePoint(R, t, p1[i], p2[i]);
+    const double depth1 = (X.v[2]) * n1;
+    if (depth1 > kMinDepth && depth1 < max_depth) {
+      const double depth2 = (R(2, 0) * X.v[0] + R(2, 1) * X.v[1] + R(2, 2) * X.v[2] + t.v[2]) * n2;
+      if (depth2 > kMinDepth && depth2 < max_depth) points3D->push_back(X);
+    }
+  }
+  return !points3D->empty();
+}
+static void PoseFromEssentialMatrix(const Mat3& E, const std::vector<Vec2>& p1, const std::vector<Vec2>& p2, Mat3* R, Vec3* t,
+                                    std::vector<Vec3>* points3D) {
+  Mat3 R1, R2;
+  DecomposeEssentialMatrix(E, &R1, &R2, t);
+  const Mat3 Rc[4] = {R1, R2, R1, R2};
+  const Vec3 neg = {{-t->v[0], -t->v[1], -t->v[2]}};
+  const Vec3 tc[4] = {*t, *t, neg, neg};
+  points3D->clear();
+  for (int i = 0; i < 4; ++i) {
+    std::vector<Vec3> cmb;
+    CheckCheirality(Rc[i], tc[i], p1, p2, &cmb);
+    if (cmb.size() >= points3D->size()) { *R = Rc[i]; *t = tc[i]; *points3D = cmb; }
+  }
+}
+static int SignOfNumber(double v) { return (0.0 < v) - (v < 0.0); }
+static double OppositeOfMinor(const Mat3& m, int row, int col) {
+  const int col1 = col == 0 ? 1 : 0, col2 = col == 2 ? 1 : 2, row1 = row == 0 ? 1 : 0, row2 = row == 2 ? 1 : 2;
+  return m(row1, col2) * m(row2, col1) - m(row1, col1) * m(row2, col2);
+}
+static Mat3 CalibrationMatrix(const Camera& c) {
+  Mat3 K;
+  memset(K.m, 0, 72);
+  K(2, 2) = 1;
+  if (c.model == 1) { K(0, 0) = c.params[0]; K(1, 1) = c.params[1]; K(0, 2) = c.params[2]; K(1, 2) = c.params[3]; }
+  else { K(0, 0) = K(1, 1) = c.params[0]; K(0, 2) = c.params[1]; K(1, 2) = c.params[2]; }
+  return K;
+}
+static void DecomposeHomographyMatrix(const Mat3& H, const Mat3& K1, const Mat3& K2, std::vector<Mat3>* R, std::vector<Vec3>* t,
+                                      std::vector<Vec3>* n) {
+  Mat3 Hn = mul(mul(inverse(K2), H), K1);
+  double sig[3], V[9];
+  jacobi_svd(Hn.m, 3, 3, sig, V, nullptr);
+  for (double& x : Hn.m) x /= sig[1];
+  Mat3 S = mul(transpose(Hn), Hn);
+  S(0, 0) -= 1; S(1, 1) -= 1; S(2, 2) -= 1;
+  double inf_norm = 0;  // lpNorm<Infinity> of a matrix = max |coefficient|
+  for (double x : S.m) inf_norm = std::max(inf_norm, std::abs(x));
+  const Vec3 zero = {{0, 0, 0}};
+  if (inf_norm < 1e-3) { *R = {Hn}; *t = {zero}; *n = {zero}; return; }
+  const double M00 = OppositeOfMinor(S, 0, 0), M11 = OppositeOfMinor(S, 1, 1), M22 = OppositeOfMinor(S, 2, 2);
+  const double rtM00 = std::sqrt(M00), rtM11 = std::sqrt(M11), rtM22 = std::sqrt(M22);
+  const double M01 = OppositeOfMinor(S, 0, 1), M12 = OppositeOfMinor(S, 1, 2), M02 = OppositeOfMinor(S, 0, 2);
+  const int e12 = SignOfNumber(M12), e02 = SignOfNumber(M02), e01 = SignOfNumber(M01);
+  const double nS[3] = {std::abs(S(0, 0)), std::abs(S(1, 1)), std::abs(S(2, 2))};
+  int idx = 0;  // std::max_element: first maximum
+  for (int k = 1; k < 3; ++k) if (nS[k] > nS[idx]) idx = k;
+  double np1[3], np2[3];
+  if (idx == 0) {
+    np1[0] = S(0, 0); np2[0] = S(0, 0);
+    np1[1] = S(0, 1) + rtM22; np2[1] = S(0, 1) - rtM22;
+    np1[2] = S(0, 2) + e12 * rtM11; np2[2] = S(0, 2) - e12 * rtM11;
+  } else if (idx == 1) {
+    np1[0] = S(0, 1) + rtM22; np2[0] = S(0, 1) - rtM22;
+    np1[1] = S(1, 1); np2[1] = S(1, 1);
+    np1[2] = S(1, 2) - e02 * rtM00; np2[2] = S(1, 2) + e02 * rtM00;
+  } else {
+    np1[0] = S(0, 2) + e01 * rtM11; np2[0] = S(0, 2) - e01 * rtM11;
+    np1[1] = S(1, 2) + rtM00; np2[1] = S(1, 2) - rtM00;
+    np1[2] = S(2, 2); np2[2] = S(2, 2);
+  }
+  const double traceS = S(0, 0) + S(1, 1) + S(2, 2);
+  const double v = 2.0 * std::sqrt(1.0 + traceS - M00 - M11 - M22);
+  const double ESii = SignOfNumber(S(idx, idx));
+  const double r_2 = 2 + traceS + v, nt_2 = 2 + traceS - v;
+  const double r = std::sqrt(r_2), n_t = std::sqrt(nt_2);
+  auto normalized = [](const double* a, double* o) {
+    const double nn = std::sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+    for (int k = 0; k < 3; ++k) o[k] = a[k] / nn;
+  };
+  double n1[3], n2[3];
+  normalized(np1, n1);
+  normalized(np2, n2);
+  const double half_nt = 0.5 * n_t, esii_t_r = ESii * r;
+  double t1s[3], t2s[3];
+  for (int k = 0; k < 3; ++k) { t1s[k] = half_nt * (esii_t_r * n2[k] - n_t * n1[k]); t2s[k] = half_nt * (esii_t_r * n1[k] - n_t * n2[k]); }
+  auto rotation = [&](const double* ts, const double* nn) {  // H_normalized * (I - (2 / v) tstar n^T)
+    Mat3 B;
+    for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) B(a, b) = (a == b ? 1.0 : 0.0) - (2.0 / v) * ts[a] * nn[b];
+    return mul(Hn, B);
+  };
+  const Mat3 R1 = rotation(t1s, n1), R2 = rotation(t2s, n2);
+  Vec3 t1, t2, nt1, nt2, mn1, mn2, pn1, pn2;
+  for (int a = 0; a < 3; ++a) {
+    t1.v[a] = R1(a, 0) * t1s[0] + R1(a, 1) * t1s[1] + R1(a, 2) * t1s[2];
+    t2.v[a] = R2(a, 0) * t2s[0] + R2(a, 1) * t2s[1] + R2(a, 2) * t2s[2];
+  }
+  for (int a = 0; a < 3; ++a) { nt1.v[a] = -t1.v[a]; nt2.v[a] = -t2.v[a]; mn1.v[a] = -n1[a]; mn2.v[a] = -n2[a]; pn1.v[a] = n1[a]; pn2.v[a] = n2[a]; }
+  *R = {R1, R1, R2, R2};
+  *t = {t1, nt1, t2, nt2};
+  *n = {mn1, pn1, mn2, pn2};
+}
+static void PoseFromHomographyMatrix(const Mat3& H, const Mat3& K1, const Mat3& K2, const std::vector<Vec2>& p1,
+                                     const std::vector<Vec2>& p2, Mat3* R, Vec3* t, Vec3* n, std::vector<Vec3>* points3D) {
+  std::vector<Mat3> Rc;
+  std::vector<Vec3> tc, nc;
+  DecomposeHomographyMatrix(H, K1, K2, &Rc, &tc, &nc);
+  points3D->clear();
+  for (size_t i = 0; i < Rc.size(); ++i) {
+    std::vector<Vec3> cmb;
+    CheckCheirality(Rc[i], tc[i], p1, p2, &cmb);
+    if (cmb.size() >= points3D->size()) { *R = Rc[i]; *t = tc[i]; *n = nc[i]; *points3D = cmb; }
+  }
+}
+// Eigen::Quaterniond(rot_mat) (Eigen/src/Geometry/Quaternion.h, "quaternionbase_assign_impl<Other,3,3>"), as (w, x, y, z)
+static void RotationMatrixToQuaternion(const Mat3& m, double q[4]) {
+  double tr = m(0, 0) + m(1, 1) + m(2, 2);
+  if (tr > 0) {
+    double t = std::sqrt(tr + 1.0);
+    q[0] = 0.5 * t;
+    t = 0.5 / t;
+    q[1] = (m(2, 1) - m(1, 2)) * t;
+    q[2] = (m(0, 2) - m(2, 0)) * t;
+    q[3] = (m(1, 0) - m(0, 1)) * t;
+  } else {
+    int i = 0;
+    if (m(1, 1) > m(0, 0)) i = 1;
+    if (m(2, 2) > m(i, i)) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    double t = std::sqrt(m(i, i) - m(j, j) - m(k, k) + 1.0);
+    q[1 + i] = 0.5 * t;
+    t = 0.5 / t;
+    q[0] = (m(k, j) - m(j, k)) * t;
+    q[1 + j] = (m(j, i) + m(i, j)) * t;
+    q[1 + k] = (m(k, i) + m(i, k)) * t;
+  }
+}
+// proj_matrix1 = [I | 0]: centre 0; proj_matrix2 = [R | t]: centre -R^T t
+static std::vector<double> CalculateTriangulationAnglesWithPM(const Mat3& R, const Vec3& t, const std::vector<Vec3>& pts) {
+  double c2[3];
+  for (int c = 0; c < 3; ++c) c2[c] = -(R(0, c) * t.v[0] + R(1, c) * t.v[1] + R(2, c) * t.v[2]);
+  const double baseline2 = c2[0] * c2[0] + c2[1] * c2[1] + c2[2] * c2[2];
+  std::vector<double> angles(pts.size());
+  for (size_t i = 0; i < pts.size(); ++i) {
+    const double* X = pts[i].v;
+    const double ray1 = std::sqrt(X[0] * X[0] + X[1] * X[1] + X[2] * X[2]);
+    const double d[3] = {X[0] - c2[0], X[1] - c2[1], X[2] - c2[2]};
+    const double ray2 = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    const double angle = std::abs(std::acos((ray1 * ray1 + ray2 * ray2 - baseline2) / (2 * ray1 * ray2)));
+    angles[i] = std::isnan(angle) ? 0 : std::min(angle, M_PI - angle);
+  }
+  return angles;
+}
+static double Median(const std::vector<double>& elems) {
+  const size_t mid = elems.size() / 2;
+  std::vector<double> o = elems;
+  std::nth_element(o.begin(), o.begin() + mid, o.end());
+  if (elems.size() % 2 == 0) return (o[mid] + *std::max_element(o.begin(), o.begin() + mid)) / 2.0;
+  return o[mid];
+}
+struct RelPose { double qvec[4] = {1, 0, 0, 0}; double tvec[3] = {0, 0, 0}; double tri_angle = 0; int config = UNDEFINED; int n_points3D = 0; };
+// The part of EstimateWithRelativePose after EstimateCalibrated (two_view_geometry.cc:239-289).  A DEGENERATE result
+// (empty inlier list, H possibly never estimated) makes the reference decompose H = 0 into NaNs that nobody reads
+// (the pair is dropped, matching.cc:824-831); here such pairs keep the identity pose.
+static RelPose RelativePose(const Camera& c1, const Vec2* pts1, const Camera& c2, const Vec2* pts2, int config, const Mat3& E,
+                            const Mat3& H, const uint32_t* inlier_matches, size_t n_inl) {
+  RelPose out;
+  out.config = config;
+  if (config == DEGENERATE || config == UNDEFINED) return out;
+  std::vector<Vec2> n1(n_inl), n2(n_inl);
+  for (size_t i = 0; i < n_inl; ++i) {
+    n1[i] = ImageToWorld(c1, pts1[inlier_matches[2 * i]]);
+    n2[i] = ImageToWorld(c2, pts2[inlier_matches[2 * i + 1]]);
+  }
+  Mat3 R;
+  Vec3 t = {{0, 0, 0}}, n;
+  std::vector<Vec3> points3D;
+  if (config == CALIBRATED || config == UNCALIBRATED) PoseFromEssentialMatrix(E, n1, n2, &R, &t, &points3D);
+  else PoseFromHomographyMatrix(H, CalibrationMatrix(c1), CalibrationMatrix(c2), n1, n2, &R, &t, &n, &points3D);
+  RotationMatrixToQuaternion(R, out.qvec);
+  memcpy(out.tvec, t.v, 24);
+  out.n_points3D = (int)points3D.size();
+  out.tri_angle = points3D.empty() ? 0 : Median(CalculateTriangulationAnglesWithPM(R, t, points3D));
+  if (config == PLANAR_OR_PANORAMIC) {
+    if (std::sqrt(t.v[0] * t.v[0] + t.v[1] * t.v[1] + t.v[2] * t.v[2]) == 0) { out.config = PANORAMIC; out.tri_angle = 0; }
+    else out.config = PLANAR;
+  }
+  return out;
+}
+
 }  // namespace tv
 
 // ===================================================================== C API
@@ -1365,6 +1627,60 @@ double orc_two_view_pairs_mt(const orc_camera* cams, const double* const* pts, c
   }
   for (auto& x : th) x.join();
   return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+
+// ---- relative pose (V4): seams for the reference's own unit tests and the full post-processing step
+struct orc_rel_pose { double qvec[4], tvec[3], tri_angle; int32_t config, n_points3D; };
+static tv::Mat3 to_mat3(const double* m) { tv::Mat3 r; memcpy(r.m, m, 72); return r; }
+void orc_decompose_essential(const double* E, double* R1, double* R2, double* t) {
+  tv::Mat3 a, b; tv::Vec3 tt;
+  tv::DecomposeEssentialMatrix(to_mat3(E), &a, &b, &tt);
+  memcpy(R1, a.m, 72); memcpy(R2, b.m, 72); memcpy(t, tt.v, 24);
+}
+int orc_pose_from_essential(const double* E, int n, const double* p1, const double* p2, double* R, double* t, double* points3D) {
+  tv::Mat3 r; tv::Vec3 tt; std::vector<tv::Vec3> pts;
+  tv::PoseFromEssentialMatrix(to_mat3(E), to_vec(p1, n), to_vec(p2, n), &r, &tt, &pts);
+  memcpy(R, r.m, 72); memcpy(t, tt.v, 24);
+  for (size_t i = 0; i < pts.size(); ++i) memcpy(points3D + 3 * i, pts[i].v, 24);
+  return (int)pts.size();
+}
+int orc_decompose_homography(const double* H, const double* K1, const double* K2, double* R /*4x9*/, double* t /*4x3*/, double* n /*4x3*/) {
+  std::vector<tv::Mat3> r; std::vector<tv::Vec3> tt, nn;
+  tv::DecomposeHomographyMatrix(to_mat3(H), to_mat3(K1), to_mat3(K2), &r, &tt, &nn);
+  for (size_t i = 0; i < r.size(); ++i) { memcpy(R + 9 * i, r[i].m, 72); memcpy(t + 3 * i, tt[i].v, 24); memcpy(n + 3 * i, nn[i].v, 24); }
+  return (int)r.size();
+}
+int orc_pose_from_homography(const double* H, const double* K1, const double* K2, int n, const double* p1, const double* p2,
+                             double* R, double* t, double* nrm, double* points3D) {
+  tv::Mat3 r; tv::Vec3 tt = {{0, 0, 0}}, nn = {{0, 0, 0}}; std::vector<tv::Vec3> pts;
+  tv::PoseFromHomographyMatrix(to_mat3(H), to_mat3(K1), to_mat3(K2), to_vec(p1, n), to_vec(p2, n), &r, &tt, &nn, &pts);
+  memcpy(R, r.m, 72); memcpy(t, tt.v, 24); memcpy(nrm, nn.v, 24);
+  for (size_t i = 0; i < pts.size(); ++i) memcpy(points3D + 3 * i, pts[i].v, 24);
+  return (int)pts.size();
+}
+void orc_triangulate_point(const double* R, const double* t, const double* p1, const double* p2, double* X) {
+  tv::Vec3 tt; memcpy(tt.v, t, 24);
+  const tv::Vec3 x = tv::TriangulatePoint(to_mat3(R), tt, tv::Vec2{p1[0], p1[1]}, tv::Vec2{p2[0], p2[1]});
+  memcpy(X, x.v, 24);
+}
+void orc_triangulation_angles(const double* R, const double* t, int n, const double* points3D, double* angles) {
+  tv::Vec3 tt; memcpy(tt.v, t, 24);
+  std::vector<tv::Vec3> pts(n);
+  for (int i = 0; i < n; ++i) memcpy(pts[i].v, points3D + 3 * i, 24);
+  const std::vector<double> a = tv::CalculateTriangulationAnglesWithPM(to_mat3(R), tt, pts);
+  memcpy(angles, a.data(), 8 * (size_t)n);
+}
+double orc_median(int n, const double* v) { return tv::Median(std::vector<double>(v, v + n)); }
+void orc_rotation_to_quaternion(const double* R, double* q) { tv::RotationMatrixToQuaternion(to_mat3(R), q); }
+// EstimateWithRelativePose's post-processing of an EstimateCalibrated result (config, E, H, inlier_matches)
+void orc_relative_pose(const orc_camera* cam1, const double* pts1, const orc_camera* cam2, const double* pts2, int config,
+                       const double* E, const double* H, const uint32_t* inlier_matches, int n_inliers, orc_rel_pose* out) {
+  const tv::RelPose r = tv::RelativePose(to_cam(cam1), reinterpret_cast<const tv::Vec2*>(pts1), to_cam(cam2),
+                                         reinterpret_cast<const tv::Vec2*>(pts2), config, to_mat3(E), to_mat3(H), inlier_matches,
+                                         (size_t)n_inliers);
+  memcpy(out->qvec, r.qvec, 32); memcpy(out->tvec, r.tvec, 24);
+  out->tri_angle = r.tri_angle; out->config = r.config; out->n_points3D = r.n_points3D;
 }
 
 }  // extern "C"
