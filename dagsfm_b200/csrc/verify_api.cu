@@ -39,6 +39,9 @@ struct b2_verifier {
   // host-call staging
   void* d_stage = nullptr;
   size_t stage_bytes = 0;
+  // relative-pose scratch (triangulation angles, one double per match)
+  double* d_angles = nullptr;
+  size_t angles_count = 0;
 };
 
 namespace {
@@ -203,7 +206,7 @@ int b2_verify_destroy(b2_verifier* v) {
   cudaStreamSynchronize(v->stream);
   auto fr = [](void* p) { if (p) cudaFree(p); };
   fr(v->d_cams); fr(v->d_img_off); fr(v->d_xy); fr(v->d_nxy); fr(v->d_scratch); fr(v->d_counter);
-  fr(v->d_err); fr(v->d_maxm); fr(v->d_stage);
+  fr(v->d_err); fr(v->d_maxm); fr(v->d_stage); fr(v->d_angles);
   cudaEventDestroy(v->ev0);
   cudaEventDestroy(v->ev1);
   cudaStreamDestroy(v->stream);
@@ -283,6 +286,79 @@ int b2_verify_pairs(b2_verifier* v, int64_t n_pairs, const uint32_t* pairs, cons
   B2_TRY(run_device(v, n_pairs, d_pairs, d_off, d_m, opt, d_seed, d_res, d_inl));
   B2_CUDA(cudaMemcpyAsync(results, d_res, n_pairs * sizeof(b2_two_view_result), cudaMemcpyDeviceToHost, s));
   if (total > 0) B2_CUDA(cudaMemcpyAsync(inlier_matches, d_inl, total * 8, cudaMemcpyDeviceToHost, s));
+  B2_CUDA(cudaStreamSynchronize(s));
+  return B2_OK;
+}
+
+
+}  // extern "C"
+namespace {
+int pose_device(b2_verifier* v, int64_t n_pairs, int64_t total, const uint32_t* pairs, const int64_t* off,
+                const b2_two_view_result* results, const uint32_t* inl, b2_relative_pose* poses) {
+  cudaStream_t s = v->stream;
+  const size_t need = (size_t)std::max<int64_t>(total, 1);
+  if (need > v->angles_count) {
+    if (v->d_angles) cudaFree(v->d_angles);
+    v->d_angles = nullptr;
+    v->angles_count = 0;
+    B2_CUDA(cudaMalloc(&v->d_angles, need * sizeof(double)));
+    v->angles_count = need;
+  }
+  B2_CUDA(cudaMemsetAsync(v->d_err, 0, sizeof(int), s));
+  B2_CUDA(launch_relative_pose(v->d_cams, v->d_img_off, v->n_images, v->d_nxy, n_pairs, pairs, off, results, inl, poses,
+                               v->d_angles, v->d_err, v->n_sm, s));
+  count_launches(1);
+  int err = 0;
+  B2_CUDA(cudaMemcpyAsync(&err, v->d_err, sizeof(int), cudaMemcpyDeviceToHost, s));
+  B2_CUDA(cudaStreamSynchronize(s));
+  if (err) return set_error(B2_ERR_INVALID, "pair references an image outside the store");
+  return B2_OK;
+}
+}  // namespace
+extern "C" {
+
+int b2_verify_relative_pose_device(b2_verifier* v, int64_t n_pairs, const uint32_t* pairs_dev, const int64_t* match_offsets_dev,
+                                   const b2_two_view_result* results_dev, const uint32_t* inlier_matches_dev,
+                                   b2_relative_pose* poses_dev) {
+  if (!v || n_pairs < 0 || (n_pairs > 0 && (!pairs_dev || !match_offsets_dev || !results_dev || !poses_dev)))
+    return set_error(B2_ERR_INVALID, "NULL argument");
+  if (n_pairs == 0) return B2_OK;
+  B2_CUDA(cudaSetDevice(v->device));
+  int64_t total = 0;
+  B2_CUDA(cudaMemcpyAsync(&total, match_offsets_dev + n_pairs, sizeof(int64_t), cudaMemcpyDeviceToHost, v->stream));
+  B2_CUDA(cudaStreamSynchronize(v->stream));
+  if (total < 0 || (total > 0 && !inlier_matches_dev)) return set_error(B2_ERR_INVALID, "bad match offsets / NULL inlier buffer");
+  return pose_device(v, n_pairs, total, pairs_dev, match_offsets_dev, results_dev, inlier_matches_dev, poses_dev);
+}
+
+int b2_verify_relative_pose(b2_verifier* v, int64_t n_pairs, const uint32_t* pairs, const int64_t* match_offsets,
+                            const b2_two_view_result* results, const uint32_t* inlier_matches, b2_relative_pose* poses) {
+  if (!v || n_pairs < 0 || (n_pairs > 0 && (!pairs || !match_offsets || !results || !poses)))
+    return set_error(B2_ERR_INVALID, "NULL argument");
+  if (n_pairs == 0) return B2_OK;
+  B2_CUDA(cudaSetDevice(v->device));
+  const int64_t total = match_offsets[n_pairs];
+  if (total < 0 || (total > 0 && !inlier_matches)) return set_error(B2_ERR_INVALID, "bad match offsets / NULL inlier buffer");
+  for (int64_t p = 0; p < n_pairs; ++p)
+    if (results[p].n_inliers < 0 || results[p].n_inliers > match_offsets[p + 1] - match_offsets[p])
+      return set_error(B2_ERR_INVALID, "n_inliers exceeds the pair's match count");
+  auto al = [](size_t b) { return (b + 255) / 256 * 256; };
+  const size_t b_pairs = al(n_pairs * 8), b_off = al((n_pairs + 1) * 8), b_m = al((size_t)std::max<int64_t>(total, 1) * 8),
+               b_res = al(n_pairs * sizeof(b2_two_view_result)), b_pose = al(n_pairs * sizeof(b2_relative_pose));
+  B2_TRY(stage(v, b_pairs + b_off + b_m + b_res + b_pose));
+  uint8_t* q = (uint8_t*)v->d_stage;
+  uint32_t* d_pairs = (uint32_t*)q; q += b_pairs;
+  int64_t* d_off = (int64_t*)q; q += b_off;
+  uint32_t* d_inl = (uint32_t*)q; q += b_m;
+  b2_two_view_result* d_res = (b2_two_view_result*)q; q += b_res;
+  b2_relative_pose* d_pose = (b2_relative_pose*)q;
+  cudaStream_t s = v->stream;
+  B2_CUDA(cudaMemcpyAsync(d_pairs, pairs, n_pairs * 8, cudaMemcpyHostToDevice, s));
+  B2_CUDA(cudaMemcpyAsync(d_off, match_offsets, (n_pairs + 1) * 8, cudaMemcpyHostToDevice, s));
+  if (total > 0) B2_CUDA(cudaMemcpyAsync(d_inl, inlier_matches, total * 8, cudaMemcpyHostToDevice, s));
+  B2_CUDA(cudaMemcpyAsync(d_res, results, n_pairs * sizeof(b2_two_view_result), cudaMemcpyHostToDevice, s));
+  B2_TRY(pose_device(v, n_pairs, total, d_pairs, d_off, d_res, d_inl, d_pose));
+  B2_CUDA(cudaMemcpyAsync(poses, d_pose, n_pairs * sizeof(b2_relative_pose), cudaMemcpyDeviceToHost, s));
   B2_CUDA(cudaStreamSynchronize(s));
   return B2_OK;
 }

@@ -44,6 +44,10 @@ int verify_warps_per_block();
 cudaError_t launch_normalize_points(const b2_camera* cams, const int64_t* img_off, int n_images, const double* xy,
                                     double* nxy, int64_t n_total, cudaStream_t s);
 cudaError_t launch_verify_pairs(const VerifyArgs& a, int n_blocks, cudaStream_t s);
+cudaError_t launch_relative_pose(const b2_camera* cams, const int64_t* img_off, int n_images, const double* nxy,
+                                 int64_t n_pairs, const uint32_t* pairs, const int64_t* match_off,
+                                 const b2_two_view_result* results, const uint32_t* inliers, b2_relative_pose* poses,
+                                 double* angles, int* err, int n_sm, cudaStream_t s);
 cudaError_t launch_score_models(int type, int n, const double* p1, const double* p2, int n_models, const double* models,
                                 double max_res, int* counts, double* sums, uint8_t* masks, cudaStream_t s);
 cudaError_t launch_debug_sample_stream(uint32_t seed, int total, int k, int n_trials, uint32_t* idx, int* out,

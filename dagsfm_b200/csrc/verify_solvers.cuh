@@ -232,7 +232,7 @@ __device__ inline void mat3_inverse(const double* a, double* r) {
 
 // ------------------------------------------------ companion-matrix eigenvalues (hqr)
 // a: n x n row-major upper Hessenberg (destroyed).  Returns false on non-convergence.
-__device__ __noinline__ bool hqr(double* a, int n, double* wr, double* wi) {
+inline __device__ __noinline__ bool hqr(double* a, int n, double* wr, double* wi) {
 #define HA(i, j) a[(i) * n + (j)]
   int nn = n - 1;
   double t = 0.0, p = 0, q = 0, r = 0, s = 0, w, x, y, z;
@@ -589,7 +589,7 @@ __device__ inline void quad_mul_acc(double* c, const double* q, const double* l,
 }
 
 // Eb: 4 basis vectors X,Y,Z,W (each 9, row-major 3x3).  models: up to 10 x 9.
-__device__ __noinline__ int solve_e5_from_basis(const double* Eb, double* models) {
+inline __device__ __noinline__ int solve_e5_from_basis(const double* Eb, double* models) {
   // E(r,c) as a linear polynomial [x,y,z,1]
   double L[9][4];
   for (int i = 0; i < 9; ++i) {

@@ -56,6 +56,9 @@ RESULT_DTYPE = np.dtype([("config", "<i4"), ("n_inliers", "<i4"), ("E_num_inlier
                          ("E", "<f8", (9,)), ("F", "<f8", (9,)), ("H", "<f8", (9,))])
 assert RESULT_DTYPE.itemsize == C.sizeof(TwoViewResult)
 
+POSE_DTYPE = np.dtype([("qvec", "<f8", (4,)), ("tvec", "<f8", (3,)), ("tri_angle", "<f8"), ("config", "<i4"),
+                       ("n_points3D", "<i4")])   # b2_relative_pose
+
 # TwoViewGeometry::ConfigurationType
 UNDEFINED, DEGENERATE, CALIBRATED, UNCALIBRATED, PLANAR, PANORAMIC, PLANAR_OR_PANORAMIC, WATERMARK, MULTIPLE = range(9)
 
@@ -75,6 +78,8 @@ def _L():
         L.b2_verify_pairs.argtypes = [vp, i64, vp, vp, vp, P(TwoViewOptions), vp, vp, vp]
         L.b2_verify_pairs_device.argtypes = [vp, i64, vp, vp, vp, P(TwoViewOptions), vp, vp, vp]
         L.b2_verify_pairs_multiple.argtypes = [vp, i64, vp, vp, vp, P(TwoViewOptions), i32, vp, vp, vp]
+        L.b2_verify_relative_pose.argtypes = [vp, i64, vp, vp, vp, vp, vp]
+        L.b2_verify_relative_pose_device.argtypes = [vp, i64, vp, vp, vp, vp, vp]
         L.b2_score_models.argtypes = [vp, i32, i32, vp, vp, i32, vp, C.c_double, vp, vp, vp]
         L.b2_verify_debug_sample_stream.argtypes = [vp, C.c_uint32, i32, i32, i32, vp]
         L.b2_verify_debug_solve.argtypes = [vp, i32, i32, vp, vp, vp, P(i32)]
@@ -142,6 +147,26 @@ class TwoViewGeometryVerifier:
                                             C.byref(options), 1 if multiple_ignore_watermark else 0, sd.ctypes.data,
                                             res.ctypes.data, inl.ctypes.data))
         return res, inl[: len(mt)]
+
+    def relative_pose(self, pairs, match_offsets, results, inlier_matches):
+        """TwoViewGeometry::EstimateWithRelativePose's post-processing (two_view_geometry.cc:239-289) of the output
+        of verify_pairs: structured array [n_pairs] with qvec (w,x,y,z), tvec, tri_angle, config (PLANAR_OR_PANORAMIC
+        resolved), n_points3D.  Pairs with a camera lacking a prior focal length keep the identity pose, exactly
+        the pairs for which TwoViewGeometry::Estimate takes the uncalibrated path."""
+        pr = np.ascontiguousarray(pairs, dtype=np.uint32).reshape(-1, 2)
+        off = np.ascontiguousarray(match_offsets, dtype=np.int64)
+        res = np.ascontiguousarray(results, dtype=RESULT_DTYPE)
+        inl = np.ascontiguousarray(inlier_matches, dtype=np.uint32).reshape(-1, 2)
+        n = len(pr)
+        assert len(off) == n + 1 and len(res) == n and off[-1] <= max(len(inl), 0) + (0 if len(inl) else off[-1])
+        poses = np.zeros(n, dtype=POSE_DTYPE)
+        check(_L().b2_verify_relative_pose(self._h, n, pr.ctypes.data, off.ctypes.data, res.ctypes.data,
+                                           inl.ctypes.data if len(inl) else None, poses.ctypes.data))
+        return poses
+
+    def relative_pose_device(self, n_pairs, pairs_ptr, off_ptr, results_ptr, inl_ptr, poses_ptr):
+        check(_L().b2_verify_relative_pose_device(self._h, n_pairs, C.c_void_p(pairs_ptr), C.c_void_p(off_ptr),
+                                                  C.c_void_p(results_ptr), C.c_void_p(inl_ptr), C.c_void_p(poses_ptr)))
 
     def verify_pairs_device(self, n_pairs, pairs_ptr, off_ptr, matches_ptr, options, seeds_ptr, results_ptr, inl_ptr):
         check(_L().b2_verify_pairs_device(self._h, n_pairs, C.c_void_p(pairs_ptr), C.c_void_p(off_ptr),

@@ -153,8 +153,9 @@ int b2_match_guided_pairs(b2_matcher* m, int64_t n_pairs, const uint32_t* pairs,
  * E 5-point, F 7-point (LO 8-point) and H 4-point DLT with Sampson / transfer
  * residuals, the configuration decision of EstimateCalibrated / EstimateUncalibrated
  * (two_view_geometry.cc:292-489) and DetectWatermark (:491-555).
- * NOT included (stays with the caller): the relative pose / triangulation
- * angle of EstimateWithRelativePose (:232-290).
+ * The relative pose / triangulation angle that DAGSfM's Estimate adds for pairs of two
+ * prior-focal-length cameras (EstimateWithRelativePose, :232-290) is the separate
+ * call b2_verify_relative_pose on the results of b2_verify_pairs.
  *
  * The reference's verifier threads never seed their PRNG (src/util/random.cc:46-49), so
  * it is itself run-to-run random; here every pair carries an explicit seed that
@@ -225,6 +226,29 @@ int b2_verify_pairs_device(b2_verifier* v, int64_t n_pairs, const uint32_t* pair
                            const int64_t* match_offsets_dev, const uint32_t* matches_dev,
                            const b2_two_view_options* opt, const uint32_t* seeds_dev,
                            b2_two_view_result* results_dev, uint32_t* inlier_matches_dev);
+/* TwoViewGeometry::EstimateWithRelativePose after EstimateCalibrated (two_view_geometry.cc:239-289): for every
+ * pair whose two cameras have a prior focal length (the dispatch of TwoViewGeometry::Estimate, :113-126) and whose
+ * config is CALIBRATED / UNCALIBRATED (pose from E, base/essential_matrix.cc:41-88) or PLANAR_OR_PANORAMIC / WATERMARK
+ * (pose from H, base/homography_matrix.cc:65-197): the (R, t) candidate with the most inliers in front of both
+ * cameras (CheckCheirality, base/pose.cc:225-248; ties keep the later candidate), qvec = RotationMatrixToQuaternion(R),
+ * tri_angle = median triangulation angle of those points (base/triangulation.cc:183-215), and PLANAR_OR_PANORAMIC
+ * resolved to PANORAMIC (|t| == 0, tri_angle 0) or PLANAR.  Every other pair (a camera without prior focal length,
+ * DEGENERATE, MULTIPLE) gets qvec (1,0,0,0), tvec 0, tri_angle 0 and its config unchanged -- the defaults of
+ * TwoViewGeometry (two_view_geometry.h:278-301).  HOST buffers; results / inlier_matches exactly as b2_verify_pairs
+ * wrote them. */
+typedef struct b2_relative_pose {
+  double qvec[4];                    /* w, x, y, z */
+  double tvec[3];
+  double tri_angle;                  /* radians */
+  int32_t config;                    /* as b2_two_view_result::config, with 6 resolved to 4 PLANAR / 5 PANORAMIC */
+  int32_t n_points3D;                /* inliers that passed the cheirality test of the chosen candidate */
+} b2_relative_pose;
+int b2_verify_relative_pose(b2_verifier* v, int64_t n_pairs, const uint32_t* pairs, const int64_t* match_offsets,
+                            const b2_two_view_result* results, const uint32_t* inlier_matches, b2_relative_pose* poses);
+/* Same with every buffer in DEVICE memory (chains onto b2_verify_pairs_device). */
+int b2_verify_relative_pose_device(b2_verifier* v, int64_t n_pairs, const uint32_t* pairs_dev,
+                                   const int64_t* match_offsets_dev, const b2_two_view_result* results_dev,
+                                   const uint32_t* inlier_matches_dev, b2_relative_pose* poses_dev);
 /* Kernel-level seam == Estimator::Residuals + InlierSupportMeasurer::Evaluate
  * (src/optim/support_measurement.cc:36-48) for n_models models over n points (HOST buffers).
  * type: 0/1 Sampson (E/F), 2 homography transfer.  counts[n_models], sums[n_models]

@@ -15,7 +15,7 @@ from tests.tv_scene import scene
 def ver():
     from tests.cuda_emu.build_emu import build
     import dagsfm_b200.verification as vm
-    L = C.CDLL(str(build("verify", ["common.cu", "verify_kernel.cu", "verify_api.cu"])))
+    L = C.CDLL(str(build("verify", ["common.cu", "verify_kernel.cu", "verify_pose.cu", "verify_api.cu"])))
     L.b2_last_error.restype = C.c_char_p
     saved = (vm._L, vm.check, vm._bound)
     vm._bound = False
@@ -194,3 +194,22 @@ def test_edge_cases_empty_tiny_and_invalid_pairs(ver):
         ver.verify_pairs(pairs[:1], offs[:2], full, bad, seeds[:1])
     r0, _ = ver.verify_pairs([], [0], np.zeros((0, 2), np.uint32), opt, np.zeros(0, np.uint32))
     assert len(r0) == 0
+
+
+# ---------------------------------------------------------------- relative pose (verify_pose.cu)
+def test_relative_pose_kernel_equals_the_oracle(ver):
+    """b2_verify_relative_pose on the emulated warp kernel against the oracle's EstimateWithRelativePose
+    restatement (pinned to the reference's essential / homography / triangulation unit tests in
+    tests/test_oracle_relative_pose.py): same candidate, same surviving points, quaternion / translation equal to
+    rounding, the median triangulation angle the same element -- for E-based, H-based (planar), panoramic,
+    uncalibrated-camera and degenerate pairs."""
+    from tests.pose_cases import check_relative_pose_against_oracle
+    check_relative_pose_against_oracle(ver)
+
+
+def test_relative_pose_rejects_inconsistent_input(ver):
+    from dagsfm_b200.verification import RESULT_DTYPE
+    res = np.zeros(1, dtype=RESULT_DTYPE)
+    res["config"], res["n_inliers"] = 2, 50          # more inliers than matches
+    with pytest.raises(RuntimeError):
+        ver.relative_pose([(0, 1)], [0, 10], res, np.zeros((10, 2), np.uint32))
