@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(128) relative_pose_kernel(PoseArgs a) {
     const b2_two_view_result& res = a.results[p];
     const uint32_t i1 = a.pairs[2 * p], i2 = a.pairs[2 * p + 1];
     b2_relative_pose out;
-    out.qvec[0] = 1; out.qvec[1] = out.qvec[2] = out.qvec[3] = 0;
+    out.qvec[0] = out.qvec[1] = out.qvec[2] = out.qvec[3] = 0;  // TwoViewGeometry() leaves qvec = tvec = 0 (two_view_geometry.h:159-166)
     out.tvec[0] = out.tvec[1] = out.tvec[2] = 0;
     out.tri_angle = 0;
     out.config = res.config;

@@ -151,7 +151,7 @@ class TwoViewGeometryVerifier:
     def relative_pose(self, pairs, match_offsets, results, inlier_matches):
         """TwoViewGeometry::EstimateWithRelativePose's post-processing (two_view_geometry.cc:239-289) of the output
         of verify_pairs: structured array [n_pairs] with qvec (w,x,y,z), tvec, tri_angle, config (PLANAR_OR_PANORAMIC
-        resolved), n_points3D.  Pairs with a camera lacking a prior focal length keep the identity pose, exactly
+        resolved), n_points3D.  Pairs with a camera lacking a prior focal length keep qvec = tvec = 0 (TwoViewGeometry()), exactly
         the pairs for which TwoViewGeometry::Estimate takes the uncalibrated path."""
         pr = np.ascontiguousarray(pairs, dtype=np.uint32).reshape(-1, 2)
         off = np.ascontiguousarray(match_offsets, dtype=np.int64)

@@ -233,8 +233,8 @@ int b2_verify_pairs_device(b2_verifier* v, int64_t n_pairs, const uint32_t* pair
  * cameras (CheckCheirality, base/pose.cc:225-248; ties keep the later candidate), qvec = RotationMatrixToQuaternion(R),
  * tri_angle = median triangulation angle of those points (base/triangulation.cc:183-215), and PLANAR_OR_PANORAMIC
  * resolved to PANORAMIC (|t| == 0, tri_angle 0) or PLANAR.  Every other pair (a camera without prior focal length,
- * DEGENERATE, MULTIPLE) gets qvec (1,0,0,0), tvec 0, tri_angle 0 and its config unchanged -- the defaults of
- * TwoViewGeometry (two_view_geometry.h:278-301).  HOST buffers; results / inlier_matches exactly as b2_verify_pairs
+ * DEGENERATE, MULTIPLE) gets qvec 0, tvec 0, tri_angle 0 and its config unchanged -- the values TwoViewGeometry's
+ * constructor sets (two_view_geometry.h:159-166).  HOST buffers; results / inlier_matches exactly as b2_verify_pairs
  * wrote them. */
 typedef struct b2_relative_pose {
   double qvec[4];                    /* w, x, y, z */

