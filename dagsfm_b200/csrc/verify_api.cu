@@ -220,8 +220,8 @@ int b2_verify_set_images(b2_verifier* v, int32_t n_images, const b2_camera* cams
   B2_CUDA(cudaSetDevice(v->device));
   for (int32_t i = 0; i < n_images; ++i) {
     if (n_pts[i] < 0) return set_error(B2_ERR_INVALID, "negative keypoint count");
-    if (cams[i].model < 0 || cams[i].model > 2)
-      return set_error(B2_ERR_INVALID, "camera model not supported (0 SIMPLE_PINHOLE, 1 PINHOLE, 2 SIMPLE_RADIAL)");
+    if (cams[i].model < 0 || cams[i].model > 10)
+      return set_error(B2_ERR_INVALID, "unknown camera model id (0 SIMPLE_PINHOLE ... 10 THIN_PRISM_FISHEYE, camera_models.h:117-129)");
   }
   auto fr = [](void* p) { if (p) cudaFree(p); };
   fr(v->d_cams); fr(v->d_img_off); fr(v->d_xy); fr(v->d_nxy);
@@ -236,16 +236,47 @@ int b2_verify_set_images(b2_verifier* v, int32_t n_images, const b2_camera* cams
   B2_CUDA(cudaMalloc(&v->d_xy, np * 16));
   B2_CUDA(cudaMalloc(&v->d_nxy, np * 16));
   cudaStream_t s = v->stream;
-  if (n_images > 0) B2_CUDA(cudaMemcpyAsync(v->d_cams, cams, n_images * sizeof(b2_camera), cudaMemcpyHostToDevice, s));
+  // Keypoints are normalised with the camera's own model.  The array the verification kernels keep afterwards only
+  // serves ImageToWorldThreshold / CalibrationMatrix, which depend on the parameter LAYOUT alone: every model with
+  // two focal lengths (fx, fy, cx, cy first) is stored there as PINHOLE (id 1), so those kernels need one test.
+  b2_camera* d_true = nullptr;
+  std::vector<b2_camera> view(cams, cams + n_images);
+  bool any_general = false;
+  for (auto& c : view)
+    if (c.model > 2) {
+      any_general = true;
+      const bool two = c.model == 4 || c.model == 5 || c.model == 6 || c.model == 7 || c.model == 10;
+      c.model = two ? 1 : 0;
+    }
+  if (n_images > 0) {
+    B2_CUDA(cudaMemcpyAsync(v->d_cams, view.data(), n_images * sizeof(b2_camera), cudaMemcpyHostToDevice, s));
+    if (any_general) {
+      B2_CUDA(cudaMalloc(&d_true, n_images * sizeof(b2_camera)));
+      B2_CUDA(cudaMemcpyAsync(d_true, cams, n_images * sizeof(b2_camera), cudaMemcpyHostToDevice, s));
+    }
+  }
   B2_CUDA(cudaMemcpyAsync(v->d_img_off, off.data(), (n_images + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
   for (int32_t i = 0; i < n_images; ++i) {
     if (n_pts[i] == 0) continue;
-    if (!xy[i]) return set_error(B2_ERR_INVALID, "NULL keypoint pointer");
+    if (!xy[i]) {
+      if (d_true) cudaFree(d_true);
+      return set_error(B2_ERR_INVALID, "NULL keypoint pointer");
+    }
     B2_CUDA(cudaMemcpyAsync(v->d_xy + 2 * off[i], xy[i], (size_t)n_pts[i] * 16, cudaMemcpyHostToDevice, s));
   }
-  B2_CUDA(launch_normalize_points(v->d_cams, v->d_img_off, n_images, v->d_xy, v->d_nxy, v->n_pts_total, s));
+  B2_CUDA(launch_normalize_points(d_true ? d_true : v->d_cams, v->d_img_off, n_images, v->d_xy, v->d_nxy, v->n_pts_total, s));
   count_launches(1);
   B2_CUDA(cudaStreamSynchronize(s));
+  if (d_true) cudaFree(d_true);
+  return B2_OK;
+}
+
+int b2_verify_debug_normalized(b2_verifier* v, int32_t image, double* out_xy) {
+  if (!v || !out_xy || image < 0 || image >= v->n_images) return set_error(B2_ERR_INVALID, "bad argument");
+  B2_CUDA(cudaSetDevice(v->device));
+  int64_t off[2];
+  B2_CUDA(cudaMemcpy(off, v->d_img_off + image, sizeof off, cudaMemcpyDeviceToHost));
+  if (off[1] > off[0]) B2_CUDA(cudaMemcpy(out_xy, v->d_nxy + 2 * off[0], (size_t)(off[1] - off[0]) * 16, cudaMemcpyDeviceToHost));
   return B2_OK;
 }
 

@@ -28,6 +28,7 @@
 #include "../../include/dagsfm_b200.h"
 #include "verify_common.cuh"
 #include "verify_solvers.cuh"
+#include "camera_models.cuh"
 
 namespace b2 {
 namespace vf {
@@ -768,6 +769,8 @@ __device__ inline double2 image_to_world(const b2_camera& c, double2 p) {
   } else if (c.model == 1) {
     u = (p.x - c.params[2]) / c.params[0];
     v = (p.y - c.params[3]) / c.params[1];
+  } else if (c.model != 2) {  // RADIAL ... THIN_PRISM_FISHEYE: the general table (camera_models.cuh)
+    cam::image_to_world(c.model, c.params, p.x, p.y, &u, &v);
   } else {
     u = (p.x - c.params[1]) / c.params[0];
     v = (p.y - c.params[2]) / c.params[0];
@@ -801,6 +804,8 @@ __device__ inline double2 image_to_world(const b2_camera& c, double2 p) {
   return make_double2(u, v);
 }
 __device__ inline double image_to_world_threshold(const b2_camera& c, double thr) {
+  // b2_verify_set_images stores every two-focal-length model (PINHOLE, OPENCV, OPENCV_FISHEYE, FULL_OPENCV, FOV,
+  // THIN_PRISM_FISHEYE: fx, fy at params[0], params[1]) with model id 1 in this array, see verify_api.cu
   const double mf = (c.model == 1) ? (c.params[0] + c.params[1]) / 2 : c.params[0];
   return thr / mf;
 }

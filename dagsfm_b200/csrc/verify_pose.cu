@@ -24,6 +24,7 @@
 #include "../../include/dagsfm_b200.h"
 #include "verify_common.cuh"
 #include "verify_solvers.cuh"
+#include "camera_models.cuh"
 
 namespace b2 {
 namespace vp {
@@ -77,7 +78,7 @@ __device__ inline double opposite_of_minor(const double* m, int row, int col) {
 __device__ inline void calibration_matrix(const b2_camera& c, double* K) {
   for (int i = 0; i < 9; ++i) K[i] = 0;
   K[8] = 1;
-  if (c.model == 1) { K[0] = c.params[0]; K[4] = c.params[1]; K[2] = c.params[2]; K[5] = c.params[3]; }
+  if (cam::two_focal(c.model)) { K[0] = c.params[0]; K[4] = c.params[1]; K[2] = c.params[2]; K[5] = c.params[3]; }
   else { K[0] = K[4] = c.params[0]; K[2] = c.params[1]; K[5] = c.params[2]; }
 }
 

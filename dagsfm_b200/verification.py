@@ -15,7 +15,7 @@ from ._lib import check, lib
 
 
 class Camera(C.Structure):
-    """b2_camera.  model: 0 SIMPLE_PINHOLE, 1 PINHOLE, 2 SIMPLE_RADIAL (camera_models.h)."""
+    """b2_camera.  model: the ids of camera_models.h:117-129 (0 SIMPLE_PINHOLE ... 10 THIN_PRISM_FISHEYE)."""
     _fields_ = [("model", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
                 ("has_prior_focal_length", C.c_int32), ("params", C.c_double * 12)]
 
@@ -84,6 +84,7 @@ def _L():
         L.b2_verify_debug_sample_stream.argtypes = [vp, C.c_uint32, i32, i32, i32, vp]
         L.b2_verify_debug_solve.argtypes = [vp, i32, i32, vp, vp, vp, P(i32)]
         L.b2_verify_last_timing.argtypes = [vp, P(C.c_double)]
+        L.b2_verify_debug_normalized.argtypes = [vp, i32, vp]
         _bound = True
     return L
 
@@ -198,6 +199,12 @@ class TwoViewGeometryVerifier:
         check(_L().b2_verify_debug_solve(self._h, est_type, len(a), a.ctypes.data, b.ctypes.data, out.ctypes.data,
                                          C.byref(nm)))
         return out[: nm.value]
+
+    def debug_normalized(self, image: int):
+        """Camera::ImageToWorld of the image's keypoints as the verifier holds them (test hook)."""
+        out = np.zeros((max(len(self._xy[image]), 1), 2))
+        check(_L().b2_verify_debug_normalized(self._h, image, out.ctypes.data))
+        return out[: len(self._xy[image])]
 
     def last_kernel_seconds(self) -> float:
         t = C.c_double(0)

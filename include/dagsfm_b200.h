@@ -164,7 +164,11 @@ int b2_match_guided_pairs(b2_matcher* m, int64_t n_pairs, const uint32_t* pairs,
 typedef struct b2_verifier b2_verifier;
 
 typedef struct b2_camera {          /* Camera (src/base/camera.h) reduced to what the path reads */
-  int32_t model;                    /* 0 SIMPLE_PINHOLE f,cx,cy | 1 PINHOLE fx,fy,cx,cy | 2 SIMPLE_RADIAL f,cx,cy,k */
+  int32_t model;                    /* camera_models.h:117-129: 0 SIMPLE_PINHOLE f,cx,cy | 1 PINHOLE fx,fy,cx,cy |
+                                       2 SIMPLE_RADIAL f,cx,cy,k | 3 RADIAL f,cx,cy,k1,k2 | 4 OPENCV fx,fy,cx,cy,k1,k2,p1,p2 |
+                                       5 OPENCV_FISHEYE fx,fy,cx,cy,k1..k4 | 6 FULL_OPENCV ..,k1,k2,p1,p2,k3..k6 |
+                                       7 FOV fx,fy,cx,cy,omega | 8 SIMPLE_RADIAL_FISHEYE f,cx,cy,k |
+                                       9 RADIAL_FISHEYE f,cx,cy,k1,k2 | 10 THIN_PRISM_FISHEYE ..,k1,k2,p1,p2,k3,k4,sx1,sy1 */
   int32_t width, height;
   int32_t has_prior_focal_length;   /* Camera::HasPriorFocalLength() */
   double params[12];
@@ -263,6 +267,8 @@ int b2_verify_debug_sample_stream(b2_verifier* v, uint32_t seed, int32_t total, 
  * models_out [10][9]; returns the model count in *n_models. */
 int b2_verify_debug_solve(b2_verifier* v, int32_t type, int32_t n, const double* xy1,
                           const double* xy2, double* models_out, int32_t* n_models);
+/* Test hook: the normalised coordinates (Camera::ImageToWorld) the verifier holds for the keypoints of one image. */
+int b2_verify_debug_normalized(b2_verifier* v, int32_t image, double* out_xy);
 /* Device seconds (CUDA events) of the last b2_verify_pairs* call. */
 int b2_verify_last_timing(b2_verifier* v, double* kernel_s);
 

@@ -324,6 +324,23 @@ def image_to_world(cam: OrcCamera, xy):
     return out
 
 
+def world_to_image(cam: OrcCamera, uv):
+    uv = _p(uv); out = np.zeros_like(uv)
+    _tv().orc_world_to_image(C.byref(cam), len(uv), C.c_void_p(uv.ctypes.data), C.c_void_p(out.ctypes.data))
+    return out
+
+
+def image_to_world_threshold(cam: OrcCamera, thr: float) -> float:
+    f = _tv().orc_image_to_world_threshold
+    f.restype = C.c_double
+    f.argtypes = [C.POINTER(OrcCamera), C.c_double]
+    return f(C.byref(cam), float(thr))
+
+
+def camera_num_params(model: int) -> int:
+    return _tv().orc_camera_num_params(int(model))
+
+
 def ransac(est_type, X, Y, max_error, min_inlier_ratio=0.1, confidence=0.99, min_num_trials=0,
            max_num_trials=2**62, seed=0, use_lo=True):
     X, Y = _p(X), _p(Y)

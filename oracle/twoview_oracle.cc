@@ -977,27 +977,111 @@ static Report RunRansac(int type, bool use_lo, RansacOptions opt, const std::vec
 }
 
 // ------------------------------------------------------------------ camera
-// model ids as in camera_models.h: 0 SIMPLE_PINHOLE (f,cx,cy), 1 PINHOLE (fx,fy,cx,cy),
-// 2 SIMPLE_RADIAL (f,cx,cy,k).
+// All eleven models of src/base/camera_models.h (ids :117-129): parameter layouts, Distortion functions,
+// ImageToWorld incl. IterativeUndistortion (:547-590), WorldToImage, ImageToWorldThreshold (:535-543).
+//   0 SIMPLE_PINHOLE f,cx,cy | 1 PINHOLE fx,fy,cx,cy | 2 SIMPLE_RADIAL f,cx,cy,k | 3 RADIAL f,cx,cy,k1,k2
+//   4 OPENCV fx,fy,cx,cy,k1,k2,p1,p2 | 5 OPENCV_FISHEYE fx,fy,cx,cy,k1..k4
+//   6 FULL_OPENCV fx,fy,cx,cy,k1,k2,p1,p2,k3..k6 | 7 FOV fx,fy,cx,cy,omega
+//   8 SIMPLE_RADIAL_FISHEYE f,cx,cy,k | 9 RADIAL_FISHEYE f,cx,cy,k1,k2
+//   10 THIN_PRISM_FISHEYE fx,fy,cx,cy,k1,k2,p1,p2,k3,k4,sx1,sy1
 struct Camera { int model; int width, height; double params[12]; int has_prior_focal; };
 
-static void SimpleRadialDistortion(double k, double u, double v, double* du, double* dv) {
-  const double u2 = u * u, v2 = v * v, r2 = u2 + v2, radial = k * r2;
-  *du = u * radial;
-  *dv = v * radial;
+static bool TwoFocal(int model) { return model == 1 || model == 4 || model == 5 || model == 6 || model == 7 || model == 10; }
+static int NumCameraParams(int model) {
+  static const int n[11] = {3, 4, 4, 5, 8, 8, 12, 5, 4, 5, 12};
+  return (model >= 0 && model <= 10) ? n[model] : -1;
 }
-static void IterativeUndistortionSR(double k, double* u, double* v) {
+// CameraModel::Distortion(extra_params, u, v, du, dv); e = the parameters after focal length(s) and principal point
+static void Distortion(int model, const double* e, double u, double v, double* du, double* dv) {
+  const double eps = std::numeric_limits<double>::epsilon();
+  if (model == 2) {          // camera_models.h:747-757
+    const double u2 = u * u, v2 = v * v, r2 = u2 + v2, radial = e[0] * r2;
+    *du = u * radial; *dv = v * radial;
+  } else if (model == 3) {   // :816-828
+    const double u2 = u * u, v2 = v * v, r2 = u2 + v2, radial = e[0] * r2 + e[1] * r2 * r2;
+    *du = u * radial; *dv = v * radial;
+  } else if (model == 4) {   // :888-903
+    const double k1 = e[0], k2 = e[1], p1 = e[2], p2 = e[3];
+    const double u2 = u * u, uv = u * v, v2 = v * v, r2 = u2 + v2, radial = k1 * r2 + k2 * r2 * r2;
+    *du = u * radial + 2.0 * p1 * uv + p2 * (r2 + 2.0 * u2);
+    *dv = v * radial + 2.0 * p2 * uv + p1 * (r2 + 2.0 * v2);
+  } else if (model == 5 || model == 8 || model == 9) {   // :963-986, :1272-1290, :1348-1368
+    const double r = std::sqrt(u * u + v * v);
+    if (r > eps) {
+      const double theta = std::atan(r), theta2 = theta * theta, theta4 = theta2 * theta2;
+      double thetad;
+      if (model == 5) {
+        const double theta6 = theta4 * theta2, theta8 = theta4 * theta4;
+        thetad = theta * (1.0 + e[0] * theta2 + e[1] * theta4 + e[2] * theta6 + e[3] * theta8);
+      } else if (model == 8) {
+        thetad = theta * (1.0 + e[0] * theta2);
+      } else {
+        thetad = theta * (1.0 + e[0] * theta2 + e[1] * theta4);
+      }
+      *du = u * thetad / r - u;
+      *dv = v * thetad / r - v;
+    } else {
+      *du = 0; *dv = 0;
+    }
+  } else if (model == 6) {   // :1058-1080
+    const double k1 = e[0], k2 = e[1], p1 = e[2], p2 = e[3], k3 = e[4], k4 = e[5], k5 = e[6], k6 = e[7];
+    const double u2 = u * u, uv = u * v, v2 = v * v, r2 = u2 + v2, r4 = r2 * r2, r6 = r4 * r2;
+    const double radial = (1.0 + k1 * r2 + k2 * r4 + k3 * r6) / (1.0 + k4 * r2 + k5 * r4 + k6 * r6);
+    *du = u * radial + 2.0 * p1 * uv + p2 * (r2 + 2.0 * u2) - u;
+    *dv = v * radial + 2.0 * p2 * uv + p1 * (r2 + 2.0 * v2) - v;
+  } else if (model == 10) {  // :1460-1482
+    const double k1 = e[0], k2 = e[1], p1 = e[2], p2 = e[3], k3 = e[4], k4 = e[5], sx1 = e[6], sy1 = e[7];
+    const double u2 = u * u, uv = u * v, v2 = v * v, r2 = u2 + v2, r4 = r2 * r2, r6 = r4 * r2, r8 = r6 * r2;
+    const double radial = k1 * r2 + k2 * r4 + k3 * r6 + k4 * r8;
+    *du = u * radial + 2.0 * p1 * uv + p2 * (r2 + 2.0 * u2) + sx1 * r2;
+    *dv = v * radial + 2.0 * p2 * uv + p1 * (r2 + 2.0 * v2) + sy1 * r2;
+  } else {
+    *du = 0; *dv = 0;
+  }
+}
+// FOVCameraModel::Distortion / Undistortion (:1137-1210): these return the distorted / undistorted point itself
+static void FovDistortion(double omega, double u, double v, double* du, double* dv) {
+  const double kEpsilon = 1e-4, radius2 = u * u + v * v, omega2 = omega * omega;
+  double factor;
+  if (omega2 < kEpsilon) {
+    factor = (omega2 * radius2) / 3.0 - omega2 / 12.0 + 1.0;
+  } else if (radius2 < kEpsilon) {
+    const double tan_half_omega = std::tan(omega / 2.0);
+    factor = (-2.0 * tan_half_omega * (4.0 * radius2 * tan_half_omega * tan_half_omega - 3.0)) / (3.0 * omega);
+  } else {
+    const double radius = std::sqrt(radius2);
+    const double numerator = std::atan(radius * 2.0 * std::tan(omega / 2.0));
+    factor = numerator / (radius * omega);
+  }
+  *du = u * factor; *dv = v * factor;
+}
+static void FovUndistortion(double omega, double u, double v, double* du, double* dv) {
+  const double kEpsilon = 1e-4, radius2 = u * u + v * v, omega2 = omega * omega;
+  double factor;
+  if (omega2 < kEpsilon) {
+    factor = (omega2 * radius2) / 3.0 - omega2 / 12.0 + 1.0;
+  } else if (radius2 < kEpsilon) {
+    factor = (omega * (omega * omega * radius2 + 3.0)) / (6.0 * std::tan(omega / 2.0));
+  } else {
+    const double radius = std::sqrt(radius2);
+    const double numerator = std::tan(radius * omega);
+    factor = numerator / (radius * 2.0 * std::tan(omega / 2.0));
+  }
+  *du = u * factor; *dv = v * factor;
+}
+// BaseCameraModel::IterativeUndistortion (:547-590)
+static void IterativeUndistortion(int model, const double* e, double* u, double* v) {
   const double x0_0 = *u, x0_1 = *v;
   double x_0 = *u, x_1 = *v;
   for (size_t i = 0; i < 100; ++i) {
     const double step0 = std::max(std::numeric_limits<double>::epsilon(), std::abs(1e-6 * x_0));
     const double step1 = std::max(std::numeric_limits<double>::epsilon(), std::abs(1e-6 * x_1));
     double dx0, dx1, b00, b01, f00, f01, b10, b11, f10, f11;
-    SimpleRadialDistortion(k, x_0, x_1, &dx0, &dx1);
-    SimpleRadialDistortion(k, x_0 - step0, x_1, &b00, &b01);
-    SimpleRadialDistortion(k, x_0 + step0, x_1, &f00, &f01);
-    SimpleRadialDistortion(k, x_0, x_1 - step1, &b10, &b11);
-    SimpleRadialDistortion(k, x_0, x_1 + step1, &f10, &f11);
+    Distortion(model, e, x_0, x_1, &dx0, &dx1);
+    Distortion(model, e, x_0 - step0, x_1, &b00, &b01);
+    Distortion(model, e, x_0 + step0, x_1, &f00, &f01);
+    Distortion(model, e, x_0, x_1 - step1, &b10, &b11);
+    Distortion(model, e, x_0, x_1 + step1, &f10, &f11);
     const double J00 = 1 + (f00 - b00) / (2 * step0);
     const double J01 = (f10 - b10) / (2 * step1);
     const double J10 = (f01 - b01) / (2 * step0);
@@ -1016,17 +1100,60 @@ static void IterativeUndistortionSR(double k, double* u, double* v) {
 }
 static Vec2 ImageToWorld(const Camera& c, Vec2 p) {
   Vec2 w;
-  if (c.model == 0) { w.x = (p.x - c.params[1]) / c.params[0]; w.y = (p.y - c.params[2]) / c.params[0]; }
-  else if (c.model == 1) { w.x = (p.x - c.params[2]) / c.params[0]; w.y = (p.y - c.params[3]) / c.params[1]; }
-  else {
-    w.x = (p.x - c.params[1]) / c.params[0];
-    w.y = (p.y - c.params[2]) / c.params[0];
-    IterativeUndistortionSR(c.params[3], &w.x, &w.y);
+  const double* k = c.params;
+  const bool two = TwoFocal(c.model);
+  const int ne = two ? 4 : 3;  // index of the first extra parameter
+  if (two) { w.x = (p.x - k[2]) / k[0]; w.y = (p.y - k[3]) / k[1]; }
+  else { w.x = (p.x - k[1]) / k[0]; w.y = (p.y - k[2]) / k[0]; }
+  if (c.model == 0 || c.model == 1) return w;
+  if (c.model == 7) {  // FOV: closed-form undistortion (:1121-1135)
+    Vec2 o;
+    FovUndistortion(k[4], w.x, w.y, &o.x, &o.y);
+    return o;
+  }
+  IterativeUndistortion(c.model, k + ne, &w.x, &w.y);
+  if (c.model == 10) {  // THIN_PRISM_FISHEYE: equidistant un-mapping after the undistortion (:1452-1458)
+    const double theta = std::sqrt(w.x * w.x + w.y * w.y);
+    const double theta_cos_theta = theta * std::cos(theta);
+    if (theta_cos_theta > std::numeric_limits<double>::epsilon()) {
+      const double scale = std::sin(theta) / theta_cos_theta;
+      w.x *= scale;
+      w.y *= scale;
+    }
   }
   return w;
 }
+// CameraModel::WorldToImage of every model (round-trip tests; camera_models_test.cc:39-61)
+static Vec2 WorldToImage(const Camera& c, Vec2 w) {
+  const double* k = c.params;
+  const bool two = TwoFocal(c.model);
+  const int ne = two ? 4 : 3;
+  double x = w.x, y = w.y;
+  if (c.model == 7) {
+    FovDistortion(k[4], w.x, w.y, &x, &y);
+  } else if (c.model == 10) {  // :1406-1435: equidistant mapping first
+    const double r = std::sqrt(w.x * w.x + w.y * w.y);
+    double uu = w.x, vv = w.y;
+    if (r > std::numeric_limits<double>::epsilon()) {
+      const double theta = std::atan(r);
+      uu = theta * w.x / r;
+      vv = theta * w.y / r;
+    }
+    double du, dv;
+    Distortion(10, k + ne, uu, vv, &du, &dv);
+    x = uu + du; y = vv + dv;
+  } else if (c.model >= 2) {
+    double du, dv;
+    Distortion(c.model, k + ne, w.x, w.y, &du, &dv);
+    x = w.x + du; y = w.y + dv;
+  }
+  Vec2 p;
+  if (two) { p.x = k[0] * x + k[2]; p.y = k[1] * y + k[3]; }
+  else { p.x = k[0] * x + k[1]; p.y = k[0] * y + k[2]; }
+  return p;
+}
 static double ImageToWorldThreshold(const Camera& c, double thr) {
-  const double mf = (c.model == 1) ? (c.params[0] + c.params[1]) / 2 : c.params[0];
+  const double mf = TwoFocal(c.model) ? (c.params[0] + c.params[1]) / 2 : c.params[0];
   return thr / mf;
 }
 
@@ -1273,7 +1400,7 @@ static Mat3 CalibrationMatrix(const Camera& c) {
   Mat3 K;
   memset(K.m, 0, 72);
   K(2, 2) = 1;
-  if (c.model == 1) { K(0, 0) = c.params[0]; K(1, 1) = c.params[1]; K(0, 2) = c.params[2]; K(1, 2) = c.params[3]; }
+  if (TwoFocal(c.model)) { K(0, 0) = c.params[0]; K(1, 1) = c.params[1]; K(0, 2) = c.params[2]; K(1, 2) = c.params[3]; }
   else { K(0, 0) = K(1, 1) = c.params[0]; K(0, 2) = c.params[1]; K(1, 2) = c.params[2]; }
   return K;
 }
@@ -1549,6 +1676,23 @@ void orc_image_to_world(const orc_camera* cam, int n, const double* xy, double* 
     out[2 * i + 1] = w.y;
   }
 }
+void orc_world_to_image(const orc_camera* cam, int n, const double* uv, double* out) {
+  tv::Camera c;
+  c.model = cam->model; c.width = cam->width; c.height = cam->height; c.has_prior_focal = cam->has_prior_focal;
+  memcpy(c.params, cam->params, sizeof c.params);
+  for (int i = 0; i < n; ++i) {
+    const tv::Vec2 p = tv::WorldToImage(c, tv::Vec2{uv[2 * i], uv[2 * i + 1]});
+    out[2 * i] = p.x;
+    out[2 * i + 1] = p.y;
+  }
+}
+double orc_image_to_world_threshold(const orc_camera* cam, double thr) {
+  tv::Camera c;
+  c.model = cam->model; c.width = cam->width; c.height = cam->height; c.has_prior_focal = cam->has_prior_focal;
+  memcpy(c.params, cam->params, sizeof c.params);
+  return tv::ImageToWorldThreshold(c, thr);
+}
+int orc_camera_num_params(int model) { return tv::NumCameraParams(model); }
 // One (LO-)RANSAC run.  mask: n bytes.  Returns success.
 int orc_ransac(int type, int use_lo, int n, const double* X, const double* Y, double max_error, double min_inlier_ratio,
                double confidence, int64_t min_num_trials, int64_t max_num_trials, unsigned seed, double* model,

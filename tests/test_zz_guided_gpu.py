@@ -325,3 +325,24 @@ def test_relative_pose_matches_oracle_on_gpu():
         check_relative_pose_against_oracle(ver)
     finally:
         ver.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="first GPU execution of the general camera-model table (written after the round's GPU budget "
+                   "was spent; verified on the CUDA emulator and compiled for the host, tests/test_camera_models.py)")
+def test_every_camera_model_is_normalised_like_the_oracle_on_gpu():
+    """Camera::ImageToWorld (incl. IterativeUndistortion) of all eleven reference models, with the parameter sets of the
+    reference's camera_models_test.cc, as the verifier computes it on the device."""
+    from dagsfm_b200 import Camera, TwoViewGeometryVerifier
+    from tests.camera_cases import CAMERA_CASES
+    from tests.test_camera_models import _grids
+    ver = TwoViewGeometryVerifier(0)
+    try:
+        kps = [_grids(model, params)[1] for model, params in CAMERA_CASES]
+        ver.set_images([Camera.make(model=m, width=800, height=800, params=p) for m, p in CAMERA_CASES], kps)
+        for i, (model, params) in enumerate(CAMERA_CASES):
+            exp = orc.image_to_world(orc.make_camera(model=model, width=800, height=800, params=params), kps[i])
+            # device libm (atan, tan, sin, cos) may differ from the host's in the last place
+            assert np.abs(ver.debug_normalized(i) - exp).max() < 1e-12, (model, params)
+    finally:
+        ver.close()
