@@ -79,3 +79,46 @@ def test_bundle_adjuster_random_problems(emu, monkeypatch):
         assert s.final_cost == pytest.approx(sc.final_cost, rel=1e-6), it
         assert (s.num_successful_steps, s.num_unsuccessful_steps) == (sc.num_successful_steps, sc.num_unsuccessful_steps), it
     monkeypatch.delenv("B2_BA_SCHUR", raising=False)
+
+
+def test_iterative_schur_random_problems(emu):
+    """The ITERATIVE_SCHUR kernels on the generator above: constant poses / tvec components / cameras / points, shared
+    intrinsics, all camera models, refine-flag combinations (hence every shape of preconditioner block, 1x1 .. 4x4,
+    and cameras without any variable column), robust losses.  Three LM iterations: same accepted / rejected steps,
+    same inner-iteration count and the same cost as the oracle's restatement of Ceres' loop.  (A 400-case run of this
+    generator with another seed agrees as well; see the note on track length below.)"""
+    rng = np.random.default_rng(7)
+    for it in range(40):
+        n_img = int(rng.integers(3, 12))
+        track = int(rng.integers(3, min(n_img, 6) + 1))   # two-view tracks leave the inner system so ill-conditioned that a
+        # 1e-15 relative change of the observations moves the ORACLE's cost by 1e-3 after three inexact steps
+        n_pts = int(rng.integers(10, 80))
+        p = make_ba_problem(n_img=n_img, n_pts=n_pts, track_len=track, seed=int(rng.integers(0, 10 ** 6)),
+                            shared_camera=bool(rng.random() < 0.3), n_const_pts=int(rng.integers(0, n_pts // 3 + 1)),
+                            noise_px=float(rng.choice([0.5, 2.0])))
+        for i in range(n_img):
+            if rng.random() < 0.15:
+                p["pose_const"][i], p["tvec_const"][i] = 1, 0
+            elif rng.random() < 0.15 and not p["pose_const"][i]:
+                p["tvec_const"][i] = int(rng.integers(1, 8))
+        for c in range(len(p["cam_const"])):
+            if rng.random() < 0.2:
+                p["cam_const"][c] = 1
+        if rng.random() < 0.3:
+            p["cam_model"][:] = int(rng.choice([0, 1]))
+        refine = (int(rng.integers(0, 2)), int(rng.integers(0, 2)), int(rng.integers(0, 2)))
+        loss, scale = int(rng.choice([0, 0, 1, 2])), float(rng.choice([0.5, 1.0, 3.0]))
+        cap = int(rng.choice([2, 7, 100]))
+        q = copy_problem(p)
+        q["refine"] = refine
+        s = emu_solve(emu, p, max_num_iterations=3, refine_focal_length=refine[0], refine_principal_point=refine[1],
+                      refine_extra_params=refine[2], loss_function_type=loss, loss_function_scale=scale,
+                      linear_solver_type=2, max_linear_solver_iterations=cap)
+        sc = orc.ba_solve(q, max_num_iterations=3, loss_type=loss, loss_scale=scale, linear_solver=1, max_linear_solver_iterations=cap)
+        assert (s.num_residuals_reduced, s.num_effective_parameters_reduced) == (sc.num_residuals, sc.num_effective_parameters), it
+        assert s.initial_cost == pytest.approx(sc.initial_cost, rel=1e-11), it
+        assert (s.num_successful_steps, s.num_unsuccessful_steps) == (sc.num_successful_steps, sc.num_unsuccessful_steps), it
+        assert s.final_cost == pytest.approx(sc.final_cost, rel=1e-6), it
+        assert abs(s.num_linear_solver_iterations - sc.num_linear_iterations) <= 2, (it, s.num_linear_solver_iterations, sc.num_linear_iterations)
+        for k in ("qvec", "tvec", "cam_params", "xyz"):
+            assert np.allclose(p[k], q[k], rtol=1e-6, atol=1e-7), (it, k)

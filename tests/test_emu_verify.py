@@ -213,3 +213,82 @@ def test_relative_pose_rejects_inconsistent_input(ver):
     res["config"], res["n_inliers"] = 2, 50          # more inliers than matches
     with pytest.raises(RuntimeError):
         ver.relative_pose([(0, 1)], [0, 10], res, np.zeros((10, 2), np.uint32))
+
+
+def test_relative_pose_random_geometries(ver):
+    """Seeded differential fuzz of relative_pose_kernel against the oracle on hand-made verification results: exact and
+    perturbed essential matrices, homographies of planes and of pure rotations, inlier counts around the warp size (the
+    ballot compaction and the even / odd median), points behind a camera, every camera layout."""
+    from dagsfm_b200.verification import Camera, RESULT_DTYPE
+    rng = np.random.default_rng(21)
+
+    def euler(a):
+        cx, sx, cy, sy, cz, sz = np.cos(a[0]), np.sin(a[0]), np.cos(a[1]), np.sin(a[1]), np.cos(a[2]), np.sin(a[2])
+        return (np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]]) @ np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]]) @
+                np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]]))
+    cams, ocams, kps, pairs, offs, inl_all, res = [], [], [], [], [0], [], []
+    models = [(2, [1200.0, 500.0, 500.0, 0.02]), (1, [1180.0, 1220.0, 510.0, 490.0]), (0, [1200.0, 500.0, 500.0]),
+              (4, [1190.0, 1205.0, 500.0, 505.0, -0.05, 0.01, 0.001, -0.001]), (9, [1200.0, 500.0, 500.0, 0.03, -0.01])]
+    counts = [0, 1, 2, 3, 15, 31, 32, 33, 63, 64, 65, 100, 129]
+    n_cases = 48
+    for k in range(n_cases):
+        model, params = models[k % len(models)]
+        n = counts[k % len(counts)]
+        kind = ["E", "E_noisy", "H_plane", "H_rot", "E_behind"][k % 5]
+        R = euler(rng.uniform(-0.3, 0.3, 3))
+        t = rng.normal(size=3); t /= np.linalg.norm(t)
+        X = rng.uniform(-1, 1, (max(n, 1), 3)) * [2, 2, 1] + [0, 0, 7]
+        if kind == "H_plane":
+            X[:, 2] = 7 + 0.1 * X[:, 0] - 0.05 * X[:, 1]
+        if kind == "E_behind":
+            X[::3, 2] *= -1           # a third of the points behind the first camera
+        if kind == "H_rot":
+            t = np.zeros(3)
+        Xc = X @ R.T + t
+        ocam = orc.make_camera(model=model, params=params, prior=(k % 7 != 6))
+        cam = Camera.make(model=model, params=params, prior_focal=(k % 7 != 6))
+        p1 = orc.world_to_image(ocam, X[:, :2] / X[:, 2:])
+        p2 = orc.world_to_image(ocam, Xc[:, :2] / Xc[:, 2:])
+        r = np.zeros(1, RESULT_DTYPE)
+        tx = np.array([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]])
+        E = tx @ R
+        if kind == "E_noisy":
+            E = E + rng.normal(0, 1e-3, (3, 3))
+        K = np.array([[params[0], 0, params[2 if model in (1, 4) else 1]], [0, params[1 if model in (1, 4) else 0], params[3 if model in (1, 4) else 2]], [0, 0, 1.0]])
+        if kind == "H_plane":
+            # plane n.X = d in camera 1: z = 7 + 0.1 x - 0.05 y  <=>  (-0.1, 0.05, 1).X = 7
+            nrm = np.array([-0.1, 0.05, 1.0])
+            Hn = R + np.outer(t, nrm) / 7.0
+            H = K @ Hn @ np.linalg.inv(K)
+        else:
+            H = K @ R @ np.linalg.inv(K)
+        r["E"][0], r["H"][0] = E.ravel(), H.ravel()
+        r["config"][0] = {"E": 2, "E_noisy": 3, "H_plane": 6, "H_rot": 6, "E_behind": 2}[kind] if k % 11 != 10 else 7
+        r["n_inliers"][0] = n
+        perm = rng.permutation(max(n, 1))
+        kp2 = np.empty_like(p2); kp2[perm] = p2
+        inl = np.stack([np.arange(n), perm[:n]], 1).astype(np.uint32) if n else np.zeros((0, 2), np.uint32)
+        cams += [cam, cam]; ocams += [ocam, ocam]; kps += [p1, kp2]
+        pairs.append((2 * k, 2 * k + 1))
+        pad = int(rng.integers(0, 4))                         # the inlier list is a prefix of the pair's match slice
+        inl_all.append(np.vstack([inl, np.zeros((pad, 2), np.uint32)]))
+        offs.append(offs[-1] + n + pad)
+        res.append(r)
+    res = np.concatenate(res)
+    inl_all = np.concatenate(inl_all)
+    ver.set_images(cams, kps)
+    poses = ver.relative_pose(pairs, offs, res, inl_all)
+    n_checked = 0
+    for k in range(n_cases):
+        a, n = offs[k], int(res["n_inliers"][k])
+        if not ocams[2 * k].has_prior_focal:
+            assert poses["qvec"][k].tolist() == [0, 0, 0, 0] and poses["config"][k] == res["config"][k]
+            continue
+        exp = orc.relative_pose(ocams[2 * k], kps[2 * k], ocams[2 * k + 1], kps[2 * k + 1], int(res["config"][k]),
+                                res["E"][k].reshape(3, 3), res["H"][k].reshape(3, 3), inl_all[a:a + n])
+        assert poses["config"][k] == exp.config and poses["n_points3D"][k] == exp.n_points3D, k
+        assert np.abs(poses["qvec"][k] - np.array(exp.qvec)).max() < 1e-11, k
+        assert np.abs(poses["tvec"][k] - np.array(exp.tvec)).max() < 1e-11, k
+        assert poses["tri_angle"][k] == pytest.approx(exp.tri_angle, abs=1e-12), k
+        n_checked += 1
+    assert n_checked >= 35 and (poses["config"] == 5).any() and (poses["config"] == 4).any()
