@@ -3,7 +3,18 @@
 # experimental kernel instances against the production ones (all flag-gated, default off).
 set -x
 cd ${GRAFT_REPO_ROOT:-.}
-python -m pytest tests/test_zz_guided_gpu.py -m gpu -q -rxXs 2>&1 | tail -15 > gpurun_out/zz_first_run.log
+python -m pytest tests/test_zz_guided_gpu.py tests/test_two_view_shim.py -m gpu -q -rxXs 2>&1 | tail -25 > gpurun_out/zz_first_run.log
+# ITERATIVE_SCHUR (ba_iterative.cu) and relative pose (verify_pose.cu) were written after the round-1 GPU budget was spent:
+# time the inner solve at 2 000 and 10 000 images (C5 shape), and take the launch list + one full capture of the matvec pair
+python bench.py --pairs 2000 --verify-pairs 0 --no-cpu --no-e2e --steps 3 --warmup 3 --ba 2000,400000,10 --ba-solver iterative \
+  > gpurun_out/ba_iter_2k.json 2> gpurun_out/ba_iter_2k.err
+python bench.py --pairs 2000 --verify-pairs 0 --no-cpu --no-e2e --steps 3 --warmup 3 --ba 10000,2000000,10 --ba-solver iterative \
+  > gpurun_out/ba_iter_10k.json 2> gpurun_out/ba_iter_10k.err
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/ba_iter_launches.csv \
+  python bench.py --pairs 2000 --verify-pairs 0 --no-cpu --no-e2e --steps 1 --warmup 1 --ba 2000,400000,10 --ba-solver iterative > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'image_pass_kernel|matvec_point_kernel' -s 40 -c 2 \
+  -o gpurun_out/ba_iter_matvec python bench.py --pairs 2000 --verify-pairs 0 --no-cpu --no-e2e --steps 1 --warmup 1 \
+  --ba 2000,400000,10 --ba-solver iterative > /dev/null 2>&1
 for v in 0 1; do
   B2_VERIFY_VARIANT=$v B2_VERIFY_PROFILE=1 python bench.py --pairs 20000 --ba "" --no-cpu --no-e2e --steps 3 --warmup 3 \
     > gpurun_out/ab_verify_$v.json 2> gpurun_out/ab_verify_$v.err
