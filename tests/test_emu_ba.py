@@ -308,3 +308,60 @@ def test_bench_ba_leg_runs_on_the_emulated_library(emu, solver):
     assert ("ITERATIVE" in out["linear_solver"]) == (solver == "iterative")
     if solver == "iterative":
         assert out["cg_iterations"] > 0
+
+
+def test_one_handle_serves_alternating_solver_types_and_problem_sizes(emu):
+    """b2_ba_solve frees everything it allocated, so one handle can alternate between the exact and the iterative path and
+    between problem sizes; every solve equals a solve on a fresh handle."""
+    o = emu.BundleAdjustmentOptions()
+    emu._L().b2_ba_default_options(C.byref(o))
+    adj = emu.BundleAdjuster(o)
+    try:
+        for k, (solver, kw) in enumerate([(2, dict(n_img=7, n_pts=70, track_len=4, seed=1)), (1, dict(n_img=5, n_pts=40, track_len=3, seed=2)),
+                                          (2, dict(n_img=9, n_pts=30, track_len=5, seed=3)), (1, dict(n_img=7, n_pts=70, track_len=4, seed=1))]):
+            p_a = make_ba_problem(**kw)
+            p_b = copy_problem(p_a)
+            adj.options.linear_solver_type = solver
+            s_a = adj.Solve(p_a)
+            s_b = emu_solve(emu, p_b, linear_solver_type=solver)
+            assert s_a.linear_solver_type_used == solver
+            assert (s_a.final_cost, s_a.num_iterations, s_a.num_linear_solver_iterations) == \
+                   (s_b.final_cost, s_b.num_iterations, s_b.num_linear_solver_iterations), k
+            assert (p_a["xyz"] == p_b["xyz"]).all() and (p_a["qvec"] == p_b["qvec"]).all()
+    finally:
+        adj.close()
+
+
+def test_iterative_schur_degenerate_inputs(emu):
+    """No observations (BundleAdjuster::Solve returns false: nothing moves), every camera-side block constant (D = 0: only
+    the points move), a single point, and a point observed twice by the same image (cross terms inside one block)."""
+    p = make_ba_problem(n_img=4, n_pts=10, track_len=3, seed=1)
+    for k in ("obs_img", "obs_pt"):
+        p[k] = p[k][:0].copy()
+    p["obs_xy"] = p["obs_xy"][:0].copy()
+    q0 = p["qvec"].copy()
+    s = emu_solve(emu, p, **ITER)
+    assert s.num_iterations == 0 and (p["qvec"] == q0).all()
+    # all poses and cameras constant
+    p = make_ba_problem(n_img=5, n_pts=40, track_len=3, seed=3)
+    p["pose_const"][:] = 1
+    p["cam_const"][:] = 1
+    pc = copy_problem(p)
+    s, sc = emu_solve(emu, p, **ITER), orc.ba_solve(pc, linear_solver=1)
+    assert s.num_effective_parameters_reduced == sc.num_effective_parameters == 3 * 40
+    assert s.final_cost == pytest.approx(sc.final_cost, rel=1e-9) and s.final_cost < s.initial_cost
+    assert s.num_linear_solver_iterations == 0
+    # one point only
+    p = make_ba_problem(n_img=4, n_pts=1, track_len=4, seed=5)
+    pc = copy_problem(p)
+    s, sc = emu_solve(emu, p, max_num_iterations=5, **ITER), orc.ba_solve(pc, max_num_iterations=5, linear_solver=1)
+    assert s.final_cost == pytest.approx(sc.final_cost, rel=1e-6, abs=1e-12)
+    # the same image twice in one track
+    p = make_ba_problem(n_img=6, n_pts=50, track_len=4, seed=9)
+    p["obs_img"][1] = p["obs_img"][0]
+    p["obs_img"][5] = p["obs_img"][4]
+    pc = copy_problem(p)
+    s, sc = emu_solve(emu, p, max_num_iterations=4, **ITER), orc.ba_solve(pc, max_num_iterations=4, linear_solver=1)
+    assert (s.num_successful_steps, s.num_unsuccessful_steps) == (sc.num_successful_steps, sc.num_unsuccessful_steps)
+    assert s.num_linear_solver_iterations == sc.num_linear_iterations
+    assert s.final_cost == pytest.approx(sc.final_cost, rel=1e-8)

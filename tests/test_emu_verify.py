@@ -292,3 +292,33 @@ def test_relative_pose_random_geometries(ver):
         assert poses["tri_angle"][k] == pytest.approx(exp.tri_angle, abs=1e-12), k
         n_checked += 1
     assert n_checked >= 35 and (poses["config"] == 5).any() and (poses["config"] == 4).any()
+
+
+def test_device_pointer_chain_verify_then_relative_pose(ver):
+    """b2_verify_pairs_device -> b2_verify_relative_pose_device on the same buffers (device pointers are host pointers on
+    the emulator) equals the host-buffer calls: the device-resident chain of SURVEY 8f rank 1 extended by the pose step."""
+    from dagsfm_b200.verification import POSE_DTYPE, RESULT_DTYPE, Camera, TwoViewOptions
+    rng = np.random.default_rng(4)
+    kps, pairs, offs, matches = [], [], [0], []
+    for k in range(4):
+        p1, p2 = scene(rng, 60 + 15 * k, 12, planar=(k == 2), noise=0.4)
+        kps += [p1, p2]
+        pairs.append((2 * k, 2 * k + 1))
+        matches.append(np.stack([np.arange(len(p1))] * 2, 1))
+        offs.append(offs[-1] + len(p1))
+    pairs = np.array(pairs, np.uint32)
+    offs = np.array(offs, np.int64)
+    matches = np.concatenate(matches).astype(np.uint32)
+    seeds = np.arange(4, dtype=np.uint32) + 40
+    ver.set_images([Camera.make(prior_focal=True)] * 8, kps)
+    vo = TwoViewOptions.default()
+    res_h, inl_h = ver.verify_pairs(pairs, offs, matches, vo, seeds)
+    pose_h = ver.relative_pose(pairs, offs, res_h, inl_h)
+    res_d = np.zeros(4, RESULT_DTYPE)
+    inl_d = np.zeros_like(matches)
+    pose_d = np.zeros(4, POSE_DTYPE)
+    ver.verify_pairs_device(4, pairs.ctypes.data, offs.ctypes.data, matches.ctypes.data, vo, seeds.ctypes.data,
+                            res_d.ctypes.data, inl_d.ctypes.data)
+    ver.relative_pose_device(4, pairs.ctypes.data, offs.ctypes.data, res_d.ctypes.data, inl_d.ctypes.data, pose_d.ctypes.data)
+    assert res_d.tobytes() == res_h.tobytes() and pose_d.tobytes() == pose_h.tobytes()
+    assert (pose_d["config"] == [2, 2, 4, 2]).all() and (pose_d["n_points3D"] > 50).all()
