@@ -21,6 +21,9 @@
 // min_relative_decrease 1e-3, exact Schur-complement step (DENSE/SPARSE_SCHUR).
 // The Jacobian is analytic (Ceres uses autodiff of the same formulas); tests check it
 // against central differences.
+// ITERATIVE_SCHUR + SCHUR_JACOBI (selected above 1000 images, bundle_adjustment.cc:274-284) is restated further down
+// from Ceres 1.14's implicit_schur_complement.cc / schur_jacobi_preconditioner.cc / conjugate_gradients_solver.cc /
+// iterative_schur_complement_solver.cc; like the exact path it has no golden vectors in the reference.
 // PARITY UNPINNED: the reference's tests pin only structure (num_residuals_reduced,
 // num_effective_parameters_reduced, which blocks move: bundle_adjustment_test.cc:186-645)
 // and four residual values (cost_functions_test.cc:41-98) -- replayed in

@@ -1304,6 +1304,10 @@ static void EstimateTwoView(const Camera& c1, const Vec2* pts1, const Camera& c2
 //   Camera::CalibrationMatrix                             src/base/camera.cc:75-94
 //   RotationMatrixToQuaternion (Eigen::Quaterniond(R))    src/base/pose.cc:70-73
 //   Median                                                src/util/math.h:212-229
+// Pinned to the reference's unit tests of these helpers (base/essential_matrix_test.cc, base/homography_matrix_test.cc
+// with its OpenCV goldens, base/triangulation_test.cc, util/math_test.cc: tests/test_oracle_relative_pose.py).  The
+// composed EstimateWithRelativePose output itself is PARITY UNPINNED: two_view_geometry_test.cc covers the constructor
+// and Invert() only.
 // Eigen::JacobiSVD is replaced by the one-sided Jacobi SVD above.  A singular-vector pair (u_k, v_k)
 // is defined up to a common sign and, for E, the singular subspace of the double singular value up to a
 // rotation; the SET of four (R, t) candidates does not depend on either, their ORDER may, and the order
