@@ -40,17 +40,124 @@
 namespace ba {
 
 // ----------------------------------------------------------------- camera models
-static int NumParams(int model) { return model == 0 ? 3 : 4; }
-// focal / principal / extra parameter index sets (camera_models.h Initialize*Idxs)
-static void ParamKinds(int model, int kind[4]) {  // 0 focal, 1 principal point, 2 extra
-  if (model == 0) { kind[0] = 0; kind[1] = 1; kind[2] = 1; kind[3] = -1; }
-  else if (model == 1) { kind[0] = 0; kind[1] = 0; kind[2] = 1; kind[3] = 1; }
-  else { kind[0] = 0; kind[1] = 1; kind[2] = 1; kind[3] = 2; }
+// src/base/camera_models.h:117-129; parameter layouts and the focal / principal point / extra index sets of every
+// model's Initialize*Idxs.  kMaxParams = 12 (FULL_OPENCV, THIN_PRISM_FISHEYE).
+static const int kMaxParams = 12;
+static const int kNC = 6 + kMaxParams;  // camera-side columns per observation: rotation 3, translation 3, intrinsics <= 12
+static int NumParams(int model) {
+  static const int n[11] = {3, 4, 4, 5, 8, 8, 12, 5, 4, 5, 12};
+  return (model >= 0 && model <= 10) ? n[model] : 0;
+}
+static bool TwoFocal(int model) { return model == 1 || model == 4 || model == 5 || model == 6 || model == 7 || model == 10; }
+// 0 focal, 1 principal point, 2 extra, -1 unused
+static void ParamKinds(int model, int kind[kMaxParams]) {
+  const int nf = TwoFocal(model) ? 2 : 1, n = NumParams(model);
+  for (int k = 0; k < kMaxParams; ++k) kind[k] = k >= n ? -1 : k < nf ? 0 : k < nf + 2 ? 1 : 2;
+}
+
+// Forward-mode dual numbers: what Ceres' AutoDiffCostFunction does with Jets for the models without hand-derived
+// formulas below (cost_functions.h:50-55).  d[0], d[1]: d/du, d/dv; d[2 + k]: d/dparams[k].
+struct Dual {
+  double a;
+  double d[2 + kMaxParams];
+  Dual() : a(0) { for (double& x : d) x = 0; }
+  Dual(double c) : a(c) { for (double& x : d) x = 0; }
+};
+static Dual operator+(const Dual& x, const Dual& y) { Dual r; r.a = x.a + y.a; for (int i = 0; i < 2 + kMaxParams; ++i) r.d[i] = x.d[i] + y.d[i]; return r; }
+static Dual operator-(const Dual& x, const Dual& y) { Dual r; r.a = x.a - y.a; for (int i = 0; i < 2 + kMaxParams; ++i) r.d[i] = x.d[i] - y.d[i]; return r; }
+static Dual operator*(const Dual& x, const Dual& y) { Dual r; r.a = x.a * y.a; for (int i = 0; i < 2 + kMaxParams; ++i) r.d[i] = x.a * y.d[i] + x.d[i] * y.a; return r; }
+static Dual operator/(const Dual& x, const Dual& y) {
+  Dual r;
+  const double inv = 1.0 / y.a;
+  r.a = x.a * inv;
+  for (int i = 0; i < 2 + kMaxParams; ++i) r.d[i] = (x.d[i] - r.a * y.d[i]) * inv;
+  return r;
+}
+static Dual dsqrt(const Dual& x) { Dual r; r.a = std::sqrt(x.a); for (int i = 0; i < 2 + kMaxParams; ++i) r.d[i] = x.d[i] / (2.0 * r.a); return r; }
+static Dual datan(const Dual& x) { Dual r; r.a = std::atan(x.a); for (int i = 0; i < 2 + kMaxParams; ++i) r.d[i] = x.d[i] / (1.0 + x.a * x.a); return r; }
+static Dual dtan(const Dual& x) { Dual r; r.a = std::tan(x.a); for (int i = 0; i < 2 + kMaxParams; ++i) r.d[i] = x.d[i] * (1.0 + r.a * r.a); return r; }
+static double dsqrt(double x) { return std::sqrt(x); }
+static double datan(double x) { return std::atan(x); }
+static double dtan(double x) { return std::tan(x); }
+static double Val(double x) { return x; }
+static double Val(const Dual& x) { return x.a; }
+
+// CameraModel::WorldToImage (camera_models.h) for T = double or Dual, every model
+template <typename T>
+static void WorldToImageT(int model, const T* params, const T& u, const T& v, T* x, T* y) {
+  const double eps = std::numeric_limits<double>::epsilon();
+  const bool two = TwoFocal(model);
+  const T* e = params + (two ? 4 : 3);
+  T a = u, b = v;
+  if (model == 7) {  // :1105-1175
+    const T omega = e[0];
+    const T radius2 = u * u + v * v, omega2 = omega * omega;
+    T factor;
+    if (Val(omega2) < 1e-4) {
+      factor = (omega2 * radius2) / T(3) - omega2 / T(12) + T(1);
+    } else if (Val(radius2) < 1e-4) {
+      const T tan_half_omega = dtan(omega / T(2));
+      factor = (T(-2) * tan_half_omega * (T(4) * radius2 * tan_half_omega * tan_half_omega - T(3))) / (T(3) * omega);
+    } else {
+      const T radius = dsqrt(radius2);
+      const T numerator = datan(radius * T(2) * dtan(omega / T(2)));
+      factor = numerator / (radius * omega);
+    }
+    a = u * factor;
+    b = v * factor;
+  } else if (model >= 2) {
+    if (model == 10) {  // :1406-1422
+      const T r = dsqrt(u * u + v * v);
+      if (Val(r) > eps) {
+        const T theta = datan(r);
+        a = theta * u / r;
+        b = theta * v / r;
+      }
+    }
+    const T u2 = a * a, uv = a * b, v2 = b * b, r2 = u2 + v2;
+    T du = T(0), dv = T(0);
+    if (model == 2) {  // :747-757
+      const T radial = e[0] * r2;
+      du = a * radial; dv = b * radial;
+    } else if (model == 3) {  // :816-828
+      const T radial = e[0] * r2 + e[1] * r2 * r2;
+      du = a * radial; dv = b * radial;
+    } else if (model == 4) {  // :888-903
+      const T radial = e[0] * r2 + e[1] * r2 * r2;
+      du = a * radial + T(2) * e[2] * uv + e[3] * (r2 + T(2) * u2);
+      dv = b * radial + T(2) * e[3] * uv + e[2] * (r2 + T(2) * v2);
+    } else if (model == 5 || model == 8 || model == 9) {  // :963-986, :1272-1290, :1348-1368
+      const T r = dsqrt(a * a + b * b);
+      if (Val(r) > eps) {
+        const T theta = datan(r), theta2 = theta * theta, theta4 = theta2 * theta2;
+        T thetad;
+        if (model == 5) thetad = theta * (T(1) + e[0] * theta2 + e[1] * theta4 + e[2] * (theta4 * theta2) + e[3] * (theta4 * theta4));
+        else if (model == 8) thetad = theta * (T(1) + e[0] * theta2);
+        else thetad = theta * (T(1) + e[0] * theta2 + e[1] * theta4);
+        du = a * thetad / r - a;
+        dv = b * thetad / r - b;
+      }
+    } else if (model == 6) {  // :1058-1080
+      const T r4 = r2 * r2, r6 = r4 * r2;
+      const T radial = (T(1) + e[0] * r2 + e[1] * r4 + e[4] * r6) / (T(1) + e[5] * r2 + e[6] * r4 + e[7] * r6);
+      du = a * radial + T(2) * e[2] * uv + e[3] * (r2 + T(2) * u2) - a;
+      dv = b * radial + T(2) * e[3] * uv + e[2] * (r2 + T(2) * v2) - b;
+    } else if (model == 10) {  // :1460-1482
+      const T r4 = r2 * r2, r6 = r4 * r2, r8 = r6 * r2;
+      const T radial = e[0] * r2 + e[1] * r4 + e[4] * r6 + e[5] * r8;
+      du = a * radial + T(2) * e[2] * uv + e[3] * (r2 + T(2) * u2) + e[6] * r2;
+      dv = b * radial + T(2) * e[3] * uv + e[2] * (r2 + T(2) * v2) + e[7] * r2;
+    }
+    a = a + du;
+    b = b + dv;
+  }
+  if (two) { *x = params[0] * a + params[2]; *y = params[1] * b + params[3]; }
+  else { *x = params[0] * a + params[1]; *y = params[0] * b + params[2]; }
 }
 
 // residual + Jacobians of one observation.
 // q (w,x,y,z), t, X, params -> r[2]; Jq 2x3 (local, after the 4x3 parameterization Jacobian),
-// Jt 2x3, JX 2x3, Jk 2x4.
+// Jt 2x3, JX 2x3, Jk 2x12 (row stride kMaxParams).
 static void Evaluate(int model, const double* q, const double* t, const double* X, const double* k, const double* obs,
                      double* r, double* Jq, double* Jt, double* JX, double* Jk) {
   const double w = q[0], x = q[1], y = q[2], z = q[3];
@@ -67,7 +174,8 @@ static void Evaluate(int model, const double* q, const double* t, const double* 
   const double u = p[0] / p[2], v = p[1] / p[2];
   double xi, yi;          // image point
   double dxdu, dxdv, dydu, dydv;
-  double dk[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+  double dk[2][kMaxParams];
+  for (int a = 0; a < 2; ++a) for (int b = 0; b < kMaxParams; ++b) dk[a][b] = 0;
   if (model == 0) {
     xi = k[0] * u + k[1]; yi = k[0] * v + k[2];
     dxdu = k[0]; dxdv = 0; dydu = 0; dydv = k[0];
@@ -76,7 +184,7 @@ static void Evaluate(int model, const double* q, const double* t, const double* 
     xi = k[0] * u + k[2]; yi = k[1] * v + k[3];
     dxdu = k[0]; dxdv = 0; dydu = 0; dydv = k[1];
     dk[0][0] = u; dk[0][2] = 1; dk[1][1] = v; dk[1][3] = 1;
-  } else {
+  } else if (model == 2) {
     const double u2 = u * u, v2 = v * v, r2 = u2 + v2, radial = k[3] * r2;
     const double du = u * radial, dv = v * radial;
     const double xd = u + du, yd = v + dv;
@@ -85,6 +193,16 @@ static void Evaluate(int model, const double* q, const double* t, const double* 
     dydu = k[0] * (2 * k[3] * u * v); dydv = k[0] * (1 + radial + 2 * k[3] * v2);
     dk[0][0] = xd; dk[0][1] = 1; dk[0][3] = k[0] * u * r2;
     dk[1][0] = yd; dk[1][2] = 1; dk[1][3] = k[0] * v * r2;
+  } else {  // the other eight models: WorldToImage on dual numbers (Ceres differentiates the same template with Jets)
+    Dual pj[kMaxParams], uj(u), vj(v), xj, yj;
+    const int np = NumParams(model);
+    for (int a = 0; a < np; ++a) { pj[a] = Dual(k[a]); pj[a].d[2 + a] = 1.0; }
+    uj.d[0] = 1.0;
+    vj.d[1] = 1.0;
+    WorldToImageT<Dual>(model, pj, uj, vj, &xj, &yj);
+    xi = xj.a; yi = yj.a;
+    dxdu = xj.d[0]; dxdv = xj.d[1]; dydu = yj.d[0]; dydv = yj.d[1];
+    for (int a = 0; a < np; ++a) { dk[0][a] = xj.d[2 + a]; dk[1][a] = yj.d[2 + a]; }
   }
   r[0] = xi - obs[0];
   r[1] = yi - obs[1];
@@ -119,7 +237,7 @@ static void Evaluate(int model, const double* q, const double* t, const double* 
     for (int a = 0; a < 4; ++a) drdq[a] = drdp[i][0] * dpdq[0][a] + drdp[i][1] * dpdq[1][a] + drdp[i][2] * dpdq[2][a];
     for (int c = 0; c < 3; ++c)
       Jq[3 * i + c] = drdq[0] * JL[0][c] + drdq[1] * JL[1][c] + drdq[2] * JL[2][c] + drdq[3] * JL[3][c];
-    for (int a = 0; a < 4; ++a) Jk[4 * i + a] = dk[i][a];
+    for (int a = 0; a < kMaxParams; ++a) Jk[kMaxParams * i + a] = dk[i][a];
   }
 }
 
@@ -147,7 +265,8 @@ struct Problem {
   const uint8_t* pose_const;  // 1 = constant pose
   const uint8_t* tvec_const;  // bitmask of constant tvec components
   const int* cam_model;
-  double* cam_params;         // [n_cam*4]
+  double* cam_params;         // [n_cam*cam_stride]
+  int cam_stride = 4;         // doubles per camera in cam_params (>= NumParams of every model used)
   const uint8_t* cam_const;   // 1 = whole camera constant
   int refine_focal, refine_principal, refine_extra;
   double* xyz;
@@ -214,7 +333,7 @@ struct Summary {
 
 struct Layout {
   std::vector<int> pose_col;  // [n_img*6], -1 = constant
-  std::vector<int> intr_col;  // [n_cam*4]
+  std::vector<int> intr_col;  // [n_cam*kMaxParams]
   std::vector<int> pt_col;    // [n_pts] first of 3, -1 = constant (relative to the point block)
   int n_cam_cols = 0, n_pt_var = 0;
 };
@@ -222,7 +341,7 @@ struct Layout {
 static Layout MakeLayout(const Problem& P) {
   Layout L;
   L.pose_col.assign((size_t)P.n_img * 6, -1);
-  L.intr_col.assign((size_t)P.n_cam * 4, -1);
+  L.intr_col.assign((size_t)P.n_cam * kMaxParams, -1);
   L.pt_col.assign(P.n_pts, -1);
   int c = 0;
   // which cameras / images / points actually appear
@@ -236,11 +355,11 @@ static Layout MakeLayout(const Problem& P) {
   }
   for (int cm = 0; cm < P.n_cam; ++cm) {
     if (!cam_used[cm] || P.cam_const[cm]) continue;
-    int kind[4];
+    int kind[kMaxParams];
     ParamKinds(P.cam_model[cm], kind);
     for (int k = 0; k < NumParams(P.cam_model[cm]); ++k) {
       const bool var = (kind[k] == 0 && P.refine_focal) || (kind[k] == 1 && P.refine_principal) || (kind[k] == 2 && P.refine_extra);
-      if (var) L.intr_col[4 * cm + k] = c++;
+      if (var) L.intr_col[kMaxParams * cm + k] = c++;
     }
   }
   L.n_cam_cols = c;
@@ -294,7 +413,7 @@ static bool CholeskySolve(std::vector<double>& A, int n, std::vector<double>& b)
   return true;
 }
 
-struct ObsJ { double r[2]; double Jc[2][10]; double Jp[2][3]; int col[10]; double rho0; };
+struct ObsJ { double r[2]; double Jc[2][kNC]; double Jp[2][3]; int col[kNC]; double rho0; };
 
 struct Solver {
   Problem P;
@@ -310,7 +429,7 @@ struct Solver {
     for (long o = 0; o < P.n_obs; ++o) {
       const int i = P.obs_img[o], p = P.obs_pt[o], c = P.img_cam[i];
       double r[2];
-      Evaluate(P.cam_model[c], q + 4 * i, t + 3 * i, X + 3 * p, kp + 4 * c, P.obs_xy + 2 * o, r, nullptr, nullptr, nullptr, nullptr);
+      Evaluate(P.cam_model[c], q + 4 * i, t + 3 * i, X + 3 * p, kp + P.cam_stride * c, P.obs_xy + 2 * o, r, nullptr, nullptr, nullptr, nullptr);
       if (O.loss_type == 0) {
         cost += r[0] * r[0] + r[1] * r[1];
       } else {
@@ -325,11 +444,11 @@ struct Solver {
 #pragma omp parallel for schedule(static)
     for (long o = 0; o < P.n_obs; ++o) {
       const int i = P.obs_img[o], p = P.obs_pt[o], c = P.img_cam[i];
-      double Jq[6], Jt[6], JX[6], Jk[8];
+      double Jq[6], Jt[6], JX[6], Jk[2 * kMaxParams];
       ObsJ& e = J[o];
-      Evaluate(P.cam_model[c], P.qvec + 4 * i, P.tvec + 3 * i, P.xyz + 3 * p, P.cam_params + 4 * c, P.obs_xy + 2 * o, e.r, Jq, Jt, JX, Jk);
+      Evaluate(P.cam_model[c], P.qvec + 4 * i, P.tvec + 3 * i, P.xyz + 3 * p, P.cam_params + P.cam_stride * c, P.obs_xy + 2 * o, e.r, Jq, Jt, JX, Jk);
       for (int k = 0; k < 6; ++k) e.col[k] = L.pose_col[6 * i + k];
-      for (int k = 0; k < 4; ++k) e.col[6 + k] = L.intr_col[4 * c + k];
+      for (int k = 0; k < kMaxParams; ++k) e.col[6 + k] = L.intr_col[kMaxParams * c + k];
       e.rho0 = e.r[0] * e.r[0] + e.r[1] * e.r[1];
       double jscale = 1.0;
       if (O.loss_type != 0) {  // ResidualBlock::Evaluate: correct the Jacobians, then the residuals
@@ -345,8 +464,8 @@ struct Solver {
       }
       for (int a = 0; a < 2; ++a) {
         for (int k = 0; k < 3; ++k) { e.Jc[a][k] = jscale * Jq[3 * a + k]; e.Jc[a][3 + k] = jscale * Jt[3 * a + k]; e.Jp[a][k] = jscale * JX[3 * a + k]; }
-        for (int k = 0; k < 4; ++k) e.Jc[a][6 + k] = jscale * Jk[4 * a + k];
-        for (int k = 0; k < 10; ++k) {
+        for (int k = 0; k < kMaxParams; ++k) e.Jc[a][6 + k] = jscale * Jk[kMaxParams * a + k];
+        for (int k = 0; k < kNC; ++k) {
           if (e.col[k] < 0) e.Jc[a][k] = 0;
           else if (scaled) e.Jc[a][k] *= scale_c[e.col[k]];
         }
@@ -371,7 +490,7 @@ struct Solver {
 // (levenberg_marquardt_strategy.cc, Solver::Options::eta default), residual_reset_period = 10.
 struct BlockDiag {
   std::vector<int> first, size;  // per column: first column and size of its parameter block
-  std::vector<double> M;         // [D][4]: row `col`, entries (col, first + j)
+  std::vector<double> M;         // [D][kMaxParams]: row `col`, entries (col, first + j)
 };
 static BlockDiag MakeBlocks(const Problem& P, const Layout& L) {
   BlockDiag B;
@@ -384,16 +503,16 @@ static BlockDiag MakeBlocks(const Problem& P, const Layout& L) {
     for (int k = 0; k < n; ++k) if (cols[k] >= 0) { B.first[cols[k]] = f; B.size[cols[k]] = cnt; }
   };
   for (int i = 0; i < P.n_img; ++i) { mark(&L.pose_col[6 * i], 3); mark(&L.pose_col[6 * i + 3], 3); }
-  for (int c = 0; c < P.n_cam; ++c) mark(&L.intr_col[4 * c], 4);
-  B.M.assign((size_t)std::max(D, 1) * 4, 0.0);
+  for (int c = 0; c < P.n_cam; ++c) mark(&L.intr_col[kMaxParams * c], kMaxParams);
+  B.M.assign((size_t)std::max(D, 1) * kMaxParams, 0.0);
   return B;
 }
 // BlockRandomAccessDiagonalMatrix::Invert: block.llt().solve(Identity); returns false if a block is not PD
 static bool InvertBlocks(BlockDiag& B, int D) {
   for (int f = 0; f < D; f += B.size[f]) {
     const int n = B.size[f];
-    double A[4][4], Lc[4][4] = {{0}}, Inv[4][4];
-    for (int r = 0; r < n; ++r) for (int c = 0; c < n; ++c) A[r][c] = B.M[(size_t)(f + r) * 4 + c];
+    double A[kMaxParams][kMaxParams], Lc[kMaxParams][kMaxParams] = {{0}}, Inv[kMaxParams][kMaxParams];
+    for (int r = 0; r < n; ++r) for (int c = 0; c < n; ++c) A[r][c] = B.M[(size_t)(f + r) * kMaxParams + c];
     for (int j = 0; j < n; ++j) {
       double d = A[j][j];
       for (int k = 0; k < j; ++k) d -= Lc[j][k] * Lc[j][k];
@@ -406,7 +525,7 @@ static bool InvertBlocks(BlockDiag& B, int D) {
       }
     }
     for (int c = 0; c < n; ++c) {  // solve L L^T x = e_c
-      double y[4];
+      double y[kMaxParams];
       for (int i = 0; i < n; ++i) {
         double v = (i == c) ? 1.0 : 0.0;
         for (int k = 0; k < i; ++k) v -= Lc[i][k] * y[k];
@@ -418,14 +537,14 @@ static bool InvertBlocks(BlockDiag& B, int D) {
         Inv[i][c] = v / Lc[i][i];
       }
     }
-    for (int r = 0; r < n; ++r) for (int c = 0; c < n; ++c) B.M[(size_t)(f + r) * 4 + c] = Inv[r][c];
+    for (int r = 0; r < n; ++r) for (int c = 0; c < n; ++c) B.M[(size_t)(f + r) * kMaxParams + c] = Inv[r][c];
   }
   return true;
 }
 static void ApplyBlocks(const BlockDiag& B, int D, const double* r, double* z) {
   for (int j = 0; j < D; ++j) {
     double v = 0;
-    for (int k = 0; k < B.size[j]; ++k) v += B.M[(size_t)j * 4 + k] * r[B.first[j] + k];
+    for (int k = 0; k < B.size[j]; ++k) v += B.M[(size_t)j * kMaxParams + k] * r[B.first[j] + k];
     z[j] = v;
   }
 }
@@ -457,7 +576,7 @@ static void Solve(Problem P, Options O, Summary* S) {
       const int i = P.obs_img[o], c = P.img_cam[i];
       bool free_block = L.pt_col[P.obs_pt[o]] >= 0;
       for (int k = 0; k < 6 && !free_block; ++k) free_block = L.pose_col[6 * i + k] >= 0;
-      for (int k = 0; k < 4 && !free_block; ++k) free_block = L.intr_col[4 * c + k] >= 0;
+      for (int k = 0; k < kMaxParams && !free_block; ++k) free_block = L.intr_col[kMaxParams * c + k] >= 0;
       n += free_block ? 1 : 0;
     }
     S->num_residuals = (int)(2 * n);
@@ -475,7 +594,7 @@ static void Solve(Problem P, Options O, Summary* S) {
       const ObsJ& e = sv.J[o];
       const int pc = L.pt_col[P.obs_pt[o]];
       for (int a = 0; a < 2; ++a) {
-        for (int k = 0; k < 10; ++k) if (e.col[k] >= 0) nc[e.col[k]] += e.Jc[a][k] * e.Jc[a][k];
+        for (int k = 0; k < kNC; ++k) if (e.col[k] >= 0) nc[e.col[k]] += e.Jc[a][k] * e.Jc[a][k];
         if (pc >= 0) for (int k = 0; k < 3; ++k) np[3 * pc + k] += e.Jp[a][k] * e.Jp[a][k];
       }
     }
@@ -492,7 +611,7 @@ static void Solve(Problem P, Options O, Summary* S) {
   const double min_radius = 1e-32, max_radius = 1e16, min_rel_dec = 1e-3, min_diag = 1e-6, max_diag = 1e32;
   std::vector<double> Smat, gc(std::max(D, 1)), dc(std::max(D, 1)), diag_c(std::max(D, 1)), diag_p(std::max(3 * NP, 1));
   std::vector<double> Vinv((size_t)std::max(NP, 1) * 9), gp((size_t)std::max(3 * NP, 1)), dp((size_t)std::max(3 * NP, 1));
-  std::vector<double> qn(P.n_img * 4), tn(P.n_img * 3), kn(P.n_cam * 4), Xn(P.n_pts * 3);
+  std::vector<double> qn(P.n_img * 4), tn(P.n_img * 3), kn(P.n_cam * P.cam_stride), Xn(P.n_pts * 3);
   bool need_grad_check = true;
 
   for (int iter = 0; iter < O.max_num_iterations; ++iter) {
@@ -505,7 +624,7 @@ static void Solve(Problem P, Options O, Summary* S) {
       const ObsJ& e = sv.J[o];
       const int pc = L.pt_col[P.obs_pt[o]];
       for (int a = 0; a < 2; ++a) {
-        for (int k = 0; k < 10; ++k)
+        for (int k = 0; k < kNC; ++k)
           if (e.col[k] >= 0) { diag_c[e.col[k]] += e.Jc[a][k] * e.Jc[a][k]; gc[e.col[k]] += e.Jc[a][k] * e.r[a]; }
         if (pc >= 0) for (int k = 0; k < 3; ++k) { diag_p[3 * pc + k] += e.Jp[a][k] * e.Jp[a][k]; gp[3 * pc + k] += e.Jp[a][k] * e.r[a]; }
       }
@@ -557,7 +676,7 @@ static void Solve(Problem P, Options O, Summary* S) {
               const ObsJ& e = sv.J[o];
               for (int a = 0; a < 2; ++a) {
                 double u = 0;
-                for (int k = 0; k < 10; ++k) if (e.col[k] >= 0) u += e.Jc[a][k] * x[e.col[k]];
+                for (int k = 0; k < kNC; ++k) if (e.col[k] >= 0) u += e.Jc[a][k] * x[e.col[k]];
                 for (int k = 0; k < 3; ++k) y2[k] += e.Jp[a][k] * u;
               }
             }
@@ -568,9 +687,9 @@ static void Solve(Problem P, Options O, Summary* S) {
             const ObsJ& e = sv.J[o];
             for (int a = 0; a < 2; ++a) {
               double u = 0;
-              for (int k = 0; k < 10; ++k) if (e.col[k] >= 0) u += e.Jc[a][k] * x[e.col[k]];
+              for (int k = 0; k < kNC; ++k) if (e.col[k] >= 0) u += e.Jc[a][k] * x[e.col[k]];
               u -= e.Jp[a][0] * z[0] + e.Jp[a][1] * z[1] + e.Jp[a][2] * z[2];
-              for (int k = 0; k < 10; ++k) if (e.col[k] >= 0) out[e.col[k]] += e.Jc[a][k] * u;
+              for (int k = 0; k < kNC; ++k) if (e.col[k] >= 0) out[e.col[k]] += e.Jc[a][k] * u;
             }
           }
         }
@@ -588,41 +707,41 @@ static void Solve(Problem P, Options O, Summary* S) {
           const ObsJ& e = sv.J[o];
           for (int a = 0; a < 2; ++a) {
             const double u = e.r[a] - (e.Jp[a][0] * tp[0] + e.Jp[a][1] * tp[1] + e.Jp[a][2] * tp[2]);
-            for (int k = 0; k < 10; ++k) if (e.col[k] >= 0) rhs[e.col[k]] += e.Jc[a][k] * u;
+            for (int k = 0; k < kNC; ++k) if (e.col[k] >= 0) rhs[e.col[k]] += e.Jc[a][k] * u;
           }
         }
       }
       // SCHUR_JACOBI: block diagonal of S, inverted
       BlockDiag B = MakeBlocks(P, L);
-      for (int j = 0; j < D; ++j) B.M[(size_t)j * 4 + (j - B.first[j])] += lm_c[j];
+      for (int j = 0; j < D; ++j) B.M[(size_t)j * kMaxParams + (j - B.first[j])] += lm_c[j];
       for (int p = 0; p < P.n_pts; ++p) {
         const int pc = L.pt_col[p];
         const long o0 = sv.pt_start[p], o1 = sv.pt_start[p + 1];
         const double* Vi = pc >= 0 ? &Vinv[(size_t)pc * 9] : nullptr;
         for (long oa = o0; oa < o1; ++oa) {
           const ObsJ& ea = sv.J[oa];
-          for (int k = 0; k < 10; ++k) {  // U = F'F restricted to the blocks
+          for (int k = 0; k < kNC; ++k) {  // U = F'F restricted to the blocks
             if (ea.col[k] < 0) continue;
-            for (int l = 0; l < 10; ++l)
+            for (int l = 0; l < kNC; ++l)
               if (ea.col[l] >= 0 && B.first[ea.col[l]] == B.first[ea.col[k]])
-                B.M[(size_t)ea.col[k] * 4 + (ea.col[l] - B.first[ea.col[l]])] += ea.Jc[0][k] * ea.Jc[0][l] + ea.Jc[1][k] * ea.Jc[1][l];
+                B.M[(size_t)ea.col[k] * kMaxParams + (ea.col[l] - B.first[ea.col[l]])] += ea.Jc[0][k] * ea.Jc[0][l] + ea.Jc[1][k] * ea.Jc[1][l];
           }
           if (!Vi) continue;
-          double Ya[30];
-          for (int k = 0; k < 10; ++k) {
+          double Ya[3 * kNC];
+          for (int k = 0; k < kNC; ++k) {
             double w[3];
             for (int l = 0; l < 3; ++l) w[l] = ea.Jc[0][k] * ea.Jp[0][l] + ea.Jc[1][k] * ea.Jp[1][l];
             for (int l = 0; l < 3; ++l) Ya[3 * k + l] = w[0] * Vi[l] + w[1] * Vi[3 + l] + w[2] * Vi[6 + l];
           }
           for (long ob = o0; ob < o1; ++ob) {
             const ObsJ& eb = sv.J[ob];
-            for (int k = 0; k < 10; ++k) {
+            for (int k = 0; k < kNC; ++k) {
               if (ea.col[k] < 0) continue;
-              for (int l = 0; l < 10; ++l) {
+              for (int l = 0; l < kNC; ++l) {
                 if (eb.col[l] < 0 || B.first[eb.col[l]] != B.first[ea.col[k]]) continue;
                 double wb[3];
                 for (int m = 0; m < 3; ++m) wb[m] = eb.Jc[0][l] * eb.Jp[0][m] + eb.Jc[1][l] * eb.Jp[1][m];
-                B.M[(size_t)ea.col[k] * 4 + (eb.col[l] - B.first[eb.col[l]])] -= Ya[3 * k] * wb[0] + Ya[3 * k + 1] * wb[1] + Ya[3 * k + 2] * wb[2];
+                B.M[(size_t)ea.col[k] * kMaxParams + (eb.col[l] - B.first[eb.col[l]])] -= Ya[3 * k] * wb[0] + Ya[3 * k + 1] * wb[1] + Ya[3 * k + 2] * wb[2];
               }
             }
           }
@@ -694,9 +813,9 @@ static void Solve(Problem P, Options O, Summary* S) {
     std::vector<double> rhs(gc.begin(), gc.begin() + D);
     for (long o = 0; o < P.n_obs; ++o) {  // U blocks
       const ObsJ& e = sv.J[o];
-      for (int k = 0; k < 10; ++k) {
+      for (int k = 0; k < kNC; ++k) {
         if (e.col[k] < 0) continue;
-        for (int l = 0; l < 10; ++l) {
+        for (int l = 0; l < kNC; ++l) {
           if (e.col[l] < 0) continue;
           Smat[(size_t)e.col[k] * D + e.col[l]] += e.Jc[0][k] * e.Jc[0][l] + e.Jc[1][k] * e.Jc[1][l];
         }
@@ -726,16 +845,16 @@ static void Solve(Problem P, Options O, Summary* S) {
       double tp[3];
       for (int k = 0; k < 3; ++k) tp[k] = Vi[3 * k] * gp[3 * pc] + Vi[3 * k + 1] * gp[3 * pc + 1] + Vi[3 * k + 2] * gp[3 * pc + 2];
       const long o0 = sv.pt_start[p], nL = sv.pt_start[p + 1] - o0;
-      std::vector<double> W((size_t)nL * 30), Y((size_t)nL * 30);
+      std::vector<double> W((size_t)nL * 3 * kNC), Y((size_t)nL * 3 * kNC);
       for (long a = 0; a < nL; ++a) {
         const ObsJ& e = sv.J[o0 + a];
-        double* Wa = &W[a * 30];
-        double* Ya = &Y[a * 30];
-        for (int k = 0; k < 10; ++k)
+        double* Wa = &W[a * 3 * kNC];
+        double* Ya = &Y[a * 3 * kNC];
+        for (int k = 0; k < kNC; ++k)
           for (int l = 0; l < 3; ++l) Wa[3 * k + l] = e.Jc[0][k] * e.Jp[0][l] + e.Jc[1][k] * e.Jp[1][l];
-        for (int k = 0; k < 10; ++k)
+        for (int k = 0; k < kNC; ++k)
           for (int l = 0; l < 3; ++l) Ya[3 * k + l] = Wa[3 * k] * Vi[l] + Wa[3 * k + 1] * Vi[3 + l] + Wa[3 * k + 2] * Vi[6 + l];
-        for (int k = 0; k < 10; ++k) {
+        for (int k = 0; k < kNC; ++k) {
           if (e.col[k] < 0) continue;
           const double v = Wa[3 * k] * tp[0] + Wa[3 * k + 1] * tp[1] + Wa[3 * k + 2] * tp[2];
 #pragma omp atomic
@@ -744,13 +863,13 @@ static void Solve(Problem P, Options O, Summary* S) {
       }
       for (long a = 0; a < nL; ++a) {
         const ObsJ& ea = sv.J[o0 + a];
-        const double* Ya = &Y[a * 30];
+        const double* Ya = &Y[a * 3 * kNC];
         for (long b = 0; b < nL; ++b) {
           const ObsJ& eb = sv.J[o0 + b];
-          const double* Wb = &W[b * 30];
-          for (int k = 0; k < 10; ++k) {
+          const double* Wb = &W[b * 3 * kNC];
+          for (int k = 0; k < kNC; ++k) {
             if (ea.col[k] < 0) continue;
-            for (int l = 0; l < 10; ++l) {
+            for (int l = 0; l < kNC; ++l) {
               if (eb.col[l] < 0) continue;
               const double v = Ya[3 * k] * Wb[3 * l] + Ya[3 * k + 1] * Wb[3 * l + 1] + Ya[3 * k + 2] * Wb[3 * l + 2];
 #pragma omp atomic
@@ -778,7 +897,7 @@ static void Solve(Problem P, Options O, Summary* S) {
           const ObsJ& e = sv.J[o];
           for (int a = 0; a < 2; ++a) {
             double jd = 0;
-            for (int k = 0; k < 10; ++k) if (e.col[k] >= 0) jd += e.Jc[a][k] * dc[e.col[k]];
+            for (int k = 0; k < kNC; ++k) if (e.col[k] >= 0) jd += e.Jc[a][k] * dc[e.col[k]];
             for (int k = 0; k < 3; ++k) s[k] += e.Jp[a][k] * jd;
           }
         }
@@ -793,7 +912,7 @@ static void Solve(Problem P, Options O, Summary* S) {
         const int pc = L.pt_col[P.obs_pt[o]];
         for (int a = 0; a < 2; ++a) {
           double m = 0;
-          for (int k = 0; k < 10; ++k) if (e.col[k] >= 0) m += e.Jc[a][k] * dc[e.col[k]];
+          for (int k = 0; k < kNC; ++k) if (e.col[k] >= 0) m += e.Jc[a][k] * dc[e.col[k]];
           if (pc >= 0) for (int k = 0; k < 3; ++k) m += e.Jp[a][k] * dp[3 * pc + k];
           model_cost_change -= m * (e.r[a] + m / 2.0);
         }
@@ -811,7 +930,7 @@ static void Solve(Problem P, Options O, Summary* S) {
     double step_sq = 0, x_sq = 0;
     qn.assign(P.qvec, P.qvec + P.n_img * 4);
     tn.assign(P.tvec, P.tvec + P.n_img * 3);
-    kn.assign(P.cam_params, P.cam_params + P.n_cam * 4);
+    kn.assign(P.cam_params, P.cam_params + P.n_cam * P.cam_stride);
     Xn.assign(P.xyz, P.xyz + P.n_pts * 3);
     for (int i = 0; i < P.n_img; ++i) {
       double d[3] = {0, 0, 0};
@@ -821,7 +940,7 @@ static void Solve(Problem P, Options O, Summary* S) {
       for (int k = 0; k < 3; ++k) { const int c = L.pose_col[6 * i + 3 + k]; if (c >= 0) { const double v = dc[c] * sv.scale_c[c]; tn[3 * i + k] += v; step_sq += v * v; } }
     }
     for (int cm = 0; cm < P.n_cam; ++cm)
-      for (int k = 0; k < 4; ++k) { const int c = L.intr_col[4 * cm + k]; if (c >= 0) { const double v = dc[c] * sv.scale_c[c]; kn[4 * cm + k] += v; step_sq += v * v; } }
+      for (int k = 0; k < kMaxParams; ++k) { const int c = L.intr_col[kMaxParams * cm + k]; if (c >= 0) { const double v = dc[c] * sv.scale_c[c]; kn[P.cam_stride * cm + k] += v; step_sq += v * v; } }
     for (int p = 0; p < P.n_pts; ++p) {
       const int pc = L.pt_col[p];
       if (pc < 0) continue;
@@ -829,7 +948,7 @@ static void Solve(Problem P, Options O, Summary* S) {
     }
     for (int i = 0; i < P.n_img * 4; ++i) x_sq += P.qvec[i] * P.qvec[i];
     for (int i = 0; i < P.n_img * 3; ++i) x_sq += P.tvec[i] * P.tvec[i];
-    for (int i = 0; i < P.n_cam * 4; ++i) x_sq += P.cam_params[i] * P.cam_params[i];
+    for (int i = 0; i < P.n_cam * P.cam_stride; ++i) x_sq += P.cam_params[i] * P.cam_params[i];
     for (int i = 0; i < P.n_pts * 3; ++i) x_sq += P.xyz[i] * P.xyz[i];
     if (std::sqrt(step_sq) <= O.parameter_tolerance * (std::sqrt(x_sq) + O.parameter_tolerance)) { S->termination = 0; break; }
     const double new_cost = sv.EvalCost(qn.data(), tn.data(), kn.data(), Xn.data());
@@ -872,6 +991,7 @@ struct orc_ba_problem {
   int32_t refine_focal, refine_principal, refine_extra;
   double* xyz; const uint8_t* pt_const;
   const int32_t* obs_img; const int32_t* obs_pt; const double* obs_xy;
+  int32_t cam_stride;  // doubles per camera in cam_params; 0 = 4
 };
 struct orc_ba_options { int32_t max_num_iterations; double function_tolerance, gradient_tolerance, parameter_tolerance; int32_t n_threads; int32_t loss_type; double loss_scale; int32_t linear_solver, max_linear_solver_iterations; };
 struct orc_ba_summary { double initial_cost, final_cost; int32_t num_successful_steps, num_unsuccessful_steps, termination, num_residuals, num_effective_parameters; double seconds; int64_t num_linear_iterations; };
@@ -883,6 +1003,7 @@ void orc_ba_solve(const orc_ba_problem* p, const orc_ba_options* o, orc_ba_summa
   P.cam_model = p->cam_model; P.cam_params = p->cam_params; P.cam_const = p->cam_const;
   P.refine_focal = p->refine_focal; P.refine_principal = p->refine_principal; P.refine_extra = p->refine_extra;
   P.xyz = p->xyz; P.pt_const = p->pt_const; P.obs_img = p->obs_img; P.obs_pt = p->obs_pt; P.obs_xy = p->obs_xy;
+  P.cam_stride = p->cam_stride > 0 ? p->cam_stride : 4;
   ba::Options O;
   O.max_num_iterations = o->max_num_iterations; O.function_tolerance = o->function_tolerance;
   O.gradient_tolerance = o->gradient_tolerance; O.parameter_tolerance = o->parameter_tolerance; O.n_threads = o->n_threads;

@@ -396,7 +396,7 @@ class OrcBaProblem(C.Structure):
                 ("tvec_const", C.c_void_p), ("cam_model", C.c_void_p), ("cam_params", C.c_void_p),
                 ("cam_const", C.c_void_p), ("refine_focal", C.c_int32), ("refine_principal", C.c_int32),
                 ("refine_extra", C.c_int32), ("xyz", C.c_void_p), ("pt_const", C.c_void_p),
-                ("obs_img", C.c_void_p), ("obs_pt", C.c_void_p), ("obs_xy", C.c_void_p)]
+                ("obs_img", C.c_void_p), ("obs_pt", C.c_void_p), ("obs_xy", C.c_void_p), ("cam_stride", C.c_int32)]
 
 
 class OrcBaOptions(C.Structure):
@@ -427,6 +427,7 @@ def ba_solve(prob: dict, max_num_iterations=50, function_tolerance=0.0, gradient
         assert prob[k].flags["C_CONTIGUOUS"]
         setattr(p, k, prob[k].ctypes.data)
     p.refine_focal, p.refine_principal, p.refine_extra = prob.get("refine", (1, 0, 1))
+    p.cam_stride = prob["cam_params"].shape[1]     # 4 (SIMPLE_PINHOLE / PINHOLE / SIMPLE_RADIAL) or up to 12
     o = OrcBaOptions(max_num_iterations, function_tolerance, gradient_tolerance, parameter_tolerance, 0,
                      int(loss_type), float(loss_scale), int(linear_solver), int(max_linear_solver_iterations))
     s = OrcBaSummary()
@@ -438,11 +439,12 @@ def ba_evaluate(model, q, t, X, k, obs):
     L = lib()
     L.orc_ba_evaluate.argtypes = [C.c_int] + [C.c_void_p] * 10
     L.orc_ba_evaluate.restype = None
-    q, t, X, k, obs = (_p(a) for a in (q, t, X, k, obs))
-    r = np.zeros(2); Jq = np.zeros((2, 3)); Jt = np.zeros((2, 3)); JX = np.zeros((2, 3)); Jk = np.zeros((2, 4))
+    q, t, X, obs = (_p(a) for a in (q, t, X, obs))
+    k = np.concatenate([_p(k), np.zeros(12)])[:12].copy()
+    r = np.zeros(2); Jq = np.zeros((2, 3)); Jt = np.zeros((2, 3)); JX = np.zeros((2, 3)); Jk = np.zeros((2, 12))
     L.orc_ba_evaluate(model, q.ctypes.data, t.ctypes.data, X.ctypes.data, k.ctypes.data, obs.ctypes.data,
                       r.ctypes.data, Jq.ctypes.data, Jt.ctypes.data, JX.ctypes.data, Jk.ctypes.data)
-    return r, Jq, Jt, JX, Jk
+    return r, Jq, Jt, JX, Jk[:, : (4 if model <= 2 else 12)].copy()   # 2 x 4 for the three 4-parameter-slot models
 
 
 def ba_quat_plus(x, d):

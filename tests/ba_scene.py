@@ -35,7 +35,10 @@ def R_from_quat(q):
 
 
 def make_ba_problem(n_img=20, n_pts=400, track_len=6, seed=0, noise_px=2.0, pose_noise=(0.005, 0.02),
-                    pt_noise=0.02, shared_camera=False, n_const_pts=0, width=1000):
+                    pt_noise=0.02, shared_camera=False, n_const_pts=0, width=1000, camera=None):
+    """camera: None = the fixture's SIMPLE_RADIAL (cam_params [n_cam, 4]); or (model_id, params) of any model of
+    camera_models.h -- observations are then projected with that model (the oracle's WorldToImage) and cam_params is
+    [n_cam, 12] (the C ABI's camera_params_stride = 12), extra parameters starting 10 % off."""
     rng = np.random.default_rng(seed)
     f = 1.2 * width
     ang = np.linspace(0, 2 * np.pi, n_img, endpoint=False)
@@ -60,7 +63,12 @@ def make_ba_problem(n_img=20, n_pts=400, track_len=6, seed=0, noise_px=2.0, pose
     obs_pt = np.repeat(np.arange(n_pts, dtype=np.int32), L)
     R_all = np.stack([R_from_quat(q) for q in q_true])
     pc = np.einsum("nij,nj->ni", R_all[obs_img], X[obs_pt]) + t_true[obs_img]
-    obs_xy = f * pc[:, :2] / pc[:, 2:] + width / 2 + rng.uniform(-noise_px, noise_px, (len(obs_img), 2))
+    if camera is None:
+        obs_xy = f * pc[:, :2] / pc[:, 2:] + width / 2
+    else:
+        from oracle import pyoracle as orc
+        obs_xy = orc.world_to_image(orc.make_camera(model=camera[0], width=width, height=width, params=camera[1]), pc[:, :2] / pc[:, 2:])
+    obs_xy = obs_xy + rng.uniform(-noise_px, noise_px, (len(obs_img), 2))
     n_cam = 1 if shared_camera else n_img
     prob = {
         "qvec": q_true.copy(), "tvec": t_true.copy(),
@@ -75,6 +83,13 @@ def make_ba_problem(n_img=20, n_pts=400, track_len=6, seed=0, noise_px=2.0, pose
         "obs_xy": np.ascontiguousarray(obs_xy),
         "refine": (1, 0, 1),
     }
+    if camera is not None:
+        kp = np.zeros(12)
+        kp[:len(camera[1])] = camera[1]
+        n_lin = 4 if camera[0] in (1, 4, 5, 6, 7, 10) else 3
+        kp[n_lin:] *= 0.9
+        prob["cam_model"][:] = camera[0]
+        prob["cam_params"] = np.tile(kp, (n_cam, 1))
     # perturb poses (not the gauge image)
     for i in range(1, n_img):
         dq = np.r_[1.0, rng.normal(0, pose_noise[0], 3)]
@@ -95,8 +110,9 @@ def copy_problem(prob):
     return {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in prob.items()}
 
 
-def reprojection_rms(prob):
-    """sqrt(sum ||r||^2 / N_obs) in px, evaluated independently in numpy (SIMPLE_RADIAL)."""
+def _project(prob):
+    """WorldToImage of every observation with the problem's current parameters (numpy; general camera models through
+    the oracle's WorldToImage, camera by camera)."""
     q = prob["qvec"] / np.linalg.norm(prob["qvec"], axis=1, keepdims=True)
     w, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
     R = np.stack([np.stack([1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)], 1),
@@ -105,23 +121,28 @@ def reprojection_rms(prob):
     i, p = prob["obs_img"], prob["obs_pt"]
     pc = np.einsum("nij,nj->ni", R[i], prob["xyz"][p]) + prob["tvec"][i]
     uv = pc[:, :2] / pc[:, 2:]
-    k = prob["cam_params"][prob["img_cam"][i]]
-    r2 = (uv ** 2).sum(1, keepdims=True)
-    xy = k[:, :1] * uv * (1 + k[:, 3:4] * r2) + k[:, 1:3]
-    return float(np.sqrt(((xy - prob["obs_xy"]) ** 2).sum() / len(i)))
+    cam = prob["img_cam"][i]
+    model = prob["cam_model"]
+    if (model == 2).all():
+        k = prob["cam_params"][cam]
+        r2 = (uv ** 2).sum(1, keepdims=True)
+        return k[:, :1] * uv * (1 + k[:, 3:4] * r2) + k[:, 1:3]
+    from oracle import pyoracle as orc
+    xy = np.zeros_like(uv)
+    for c in range(len(model)):
+        sel = cam == c
+        if sel.any():
+            xy[sel] = orc.world_to_image(orc.make_camera(model=int(model[c]), params=list(prob["cam_params"][c])), uv[sel])
+    return xy
+
+
+def reprojection_rms(prob):
+    """sqrt(sum ||r||^2 / N_obs) in px, evaluated independently of the solvers."""
+    xy = _project(prob)
+    return float(np.sqrt(((xy - prob["obs_xy"]) ** 2).sum() / len(xy)))
 
 
 def mean_reprojection_error(prob):
     """Mean ||r|| in px: Reconstruction::ComputeMeanReprojectionError (base/reconstruction.cc:814-858)."""
-    q = prob["qvec"] / np.linalg.norm(prob["qvec"], axis=1, keepdims=True)
-    w, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
-    R = np.stack([np.stack([1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)], 1),
-                  np.stack([2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)], 1),
-                  np.stack([2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)], 1)], 1)
-    i, p = prob["obs_img"], prob["obs_pt"]
-    pc = np.einsum("nij,nj->ni", R[i], prob["xyz"][p]) + prob["tvec"][i]
-    uv = pc[:, :2] / pc[:, 2:]
-    k = prob["cam_params"][prob["img_cam"][i]]
-    r2 = (uv ** 2).sum(1, keepdims=True)
-    xy = k[:, :1] * uv * (1 + k[:, 3:4] * r2) + k[:, 1:3]
+    xy = _project(prob)
     return float(np.sqrt(((xy - prob["obs_xy"]) ** 2).sum(1)).mean())

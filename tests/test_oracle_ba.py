@@ -108,3 +108,52 @@ def test_iterative_schur_restatement_reaches_the_exact_schur_optimum():
         assert s.num_linear_iterations <= 4 * n
         costs.append(s.final_cost)
     assert all(b <= a for a, b in zip(costs, costs[1:])) and costs[-1] < costs[0]
+
+
+def test_jacobian_of_every_camera_model_vs_central_differences():
+    """BundleAdjustmentCostFunction on all eleven models: the three hand-derived ones and the eight evaluated on dual
+    numbers (what Ceres' autodiff does with the reference's templated WorldToImage)."""
+    from tests.camera_cases import CAMERA_CASES, NUM_PARAMS
+    rng = np.random.default_rng(0)
+    for model, params in CAMERA_CASES:
+        K = NUM_PARAMS[model]
+        q = rng.normal(size=4); q /= np.linalg.norm(q)
+        t = rng.normal(size=3) + [0, 0, 6]
+        X = rng.normal(size=3)
+        obs = rng.uniform(0, 800, 2)
+        k = np.array(params, float)
+        r, Jq, Jt, JX, Jk = orc.ba_evaluate(model, q, t, X, k, obs)
+
+        def res(q_, t_, X_, k_):
+            return orc.ba_evaluate(model, q_, t_, X_, k_, obs)[0]
+        h = 1e-6
+        for c in range(3):
+            e = np.zeros(3); e[c] = h
+            assert np.allclose(Jt[:, c], (res(q, t + e, X, k) - res(q, t - e, X, k)) / (2 * h), rtol=1e-5, atol=1e-5)
+            assert np.allclose(JX[:, c], (res(q, t, X + e, k) - res(q, t, X - e, k)) / (2 * h), rtol=1e-5, atol=1e-5)
+            qp, qm = orc.ba_quat_plus(q, e), orc.ba_quat_plus(q, -e)
+            assert np.allclose(Jq[:, c], (res(qp, t, X, k) - res(qm, t, X, k)) / (2 * h), rtol=1e-5, atol=1e-4)
+        for c in range(K):
+            if model == 7 and abs(k[4] ** 2 - 1e-4) < 1e-9:
+                continue                                   # omega^2 == kEpsilon: the difference would straddle two branches
+            hp = 1e-6 * max(1.0, abs(k[c]))
+            e = np.zeros(K); e[c] = hp
+            num = (res(q, t, X, k + e) - res(q, t, X, k - e)) / (2 * hp)
+            assert np.allclose(Jk[:, c], num, rtol=2e-5, atol=1e-5 * max(1.0, np.abs(num).max())), (model, c)
+
+
+def test_general_camera_models_exact_and_iterative_reach_the_same_optimum():
+    T = dict(max_num_iterations=100, gradient_tolerance=1e-9, function_tolerance=1e-14)
+    for cam in ((3, [1200.0, 500, 500, 0.05, -0.01]), (4, [1180.0, 1210.0, 505.0, 495.0, -0.12, 0.03, 0.001, -0.0015]),
+                (5, [1200.0, 1200.0, 500, 500, 0.02, -0.005, 0.001, 0.0]), (7, [1200.0, 1200.0, 500, 500, 0.3]),
+                (8, [1200.0, 500, 500, 0.04])):
+        p = make_ba_problem(n_img=10, n_pts=200, track_len=5, seed=3, camera=cam, noise_px=0.5)
+        a, b = copy_problem(p), copy_problem(p)
+        s_ex, s_it = orc.ba_solve(a, **T), orc.ba_solve(b, linear_solver=1, **T)
+        n_extra = len(cam[1]) - (4 if cam[0] in (4, 5, 7) else 3)
+        n_focal = 2 if cam[0] in (4, 5, 7) else 1
+        assert s_ex.num_effective_parameters == 3 * 200 + (6 * 10 - 7) + 10 * (n_focal + n_extra)   # focal + extra refined, pp fixed
+        assert reprojection_rms(a) < 0.36 < 5 < reprojection_rms(p)
+        assert abs(reprojection_rms(a) - reprojection_rms(b)) < 1e-6
+        assert s_it.final_cost == __import__("pytest").approx(s_ex.final_cost, rel=1e-8)
+        assert (a["cam_params"][:, len(cam[1]):] == 0).all()
