@@ -19,7 +19,7 @@ class BaProblem(C.Structure):
                 ("const_pose", C.c_void_p), ("const_tvec", C.c_void_p), ("camera_model", C.c_void_p),
                 ("camera_params", C.c_void_p), ("const_camera", C.c_void_p), ("xyz", C.c_void_p),
                 ("const_point", C.c_void_p), ("obs_image", C.c_void_p), ("obs_point", C.c_void_p),
-                ("obs_xy", C.c_void_p)]
+                ("obs_xy", C.c_void_p), ("camera_params_stride", C.c_int32), ("reserved", C.c_int32)]
 
 
 class BundleAdjustmentOptions(C.Structure):
@@ -121,6 +121,8 @@ class BundleAdjuster:
         p.xyz, p.const_point = prob["xyz"].ctypes.data, prob["pt_const"].ctypes.data
         p.obs_image, p.obs_point, p.obs_xy = (prob["obs_img"].ctypes.data, prob["obs_pt"].ctypes.data,
                                               prob["obs_xy"].ctypes.data)
+        assert prob["cam_params"].ndim == 2 and 4 <= prob["cam_params"].shape[1] <= 12
+        p.camera_params_stride = prob["cam_params"].shape[1]     # 4, or up to 12 for the wider camera models
         s = BaSummary()
         check(_L().b2_ba_solve(self._h, C.byref(p), C.byref(self.options), C.byref(s)))
         self.summary = s

@@ -43,11 +43,16 @@ struct b2_ba {
 
 namespace {
 
-int num_params(int model) { return model == 0 ? 3 : 4; }
-void param_kinds(int model, int kind[4]) {  // 0 focal, 1 principal point, 2 extra (camera_models.h)
-  if (model == 0) { kind[0] = 0; kind[1] = 1; kind[2] = 1; kind[3] = -1; }
-  else if (model == 1) { kind[0] = 0; kind[1] = 0; kind[2] = 1; kind[3] = 1; }
-  else { kind[0] = 0; kind[1] = 1; kind[2] = 1; kind[3] = 2; }
+// camera_models.h:117-129 and every model's Initialize{FocalLength,PrincipalPoint,ExtraParams}Idxs
+constexpr int kMaxParams = 12;
+int num_params(int model) {
+  static const int n[11] = {3, 4, 4, 5, 8, 8, 12, 5, 4, 5, 12};
+  return (model >= 0 && model <= 10) ? n[model] : 0;
+}
+bool two_focal(int model) { return model == 1 || (model >= 4 && model <= 7) || model == 10; }
+void param_kinds(int model, int kind[kMaxParams]) {  // 0 focal, 1 principal point, 2 extra, -1 unused
+  const int nf = two_focal(model) ? 2 : 1, n = num_params(model);
+  for (int k = 0; k < kMaxParams; ++k) kind[k] = k >= n ? -1 : k < nf ? 0 : k < nf + 2 ? 1 : 2;
 }
 
 template <typename T>
@@ -177,8 +182,16 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
   }
   for (int i = 0; i < n_img; ++i)
     if (pr->image_camera[i] < 0 || pr->image_camera[i] >= n_cam) return set_error(B2_ERR_INVALID, "bad image_camera");
-  for (int c = 0; c < n_cam; ++c)
-    if (pr->camera_model[c] < 0 || pr->camera_model[c] > 2) return set_error(B2_ERR_INVALID, "unsupported camera model");
+  // SIMPLE_PINHOLE / PINHOLE / SIMPLE_RADIAL (<= 4 parameters) run on the 224-byte Jacobian layout; any other model of
+  // camera_models.h switches the whole problem to the wide layout (12 intrinsics slots, dual-number derivatives)
+  const int cs = pr->camera_params_stride > 0 ? pr->camera_params_stride : 4;
+  bool wide = false;
+  for (int c = 0; c < n_cam; ++c) {
+    if (pr->camera_model[c] < 0 || pr->camera_model[c] > 10) return set_error(B2_ERR_INVALID, "unknown camera model id");
+    if (num_params(pr->camera_model[c]) > cs) return set_error(B2_ERR_INVALID, "camera_params_stride smaller than the model's parameter count");
+    wide = wide || pr->camera_model[c] > 2;
+  }
+  const int KI = wide ? kMaxParams : 4;
   // ---------------------------------------------------------------- layout
   // Column order: images (rotation 3, variable tvec components), then cameras (variable
   // intrinsics) -- only blocks that appear in a residual (as Ceres' reduced program).
@@ -191,7 +204,7 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
     cam_used[pr->image_camera[pr->obs_image[o]]] = 1;
     pt_used[pr->obs_point[o]] = 1;
   }
-  std::vector<int32_t> pose_col((size_t)n_img * 6, -1), intr_col((size_t)n_cam * 4, -1), pt_col(n_pts, -1);
+  std::vector<int32_t> pose_col((size_t)n_img * 6, -1), intr_col((size_t)n_cam * KI, -1), pt_col(n_pts, -1);
   int64_t D = 0;
   for (int i = 0; i < n_img; ++i) {
     if (!img_used[i] || pr->const_pose[i]) continue;
@@ -201,12 +214,12 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
   }
   for (int c = 0; c < n_cam; ++c) {
     if (!cam_used[c] || pr->const_camera[c]) continue;
-    int kind[4];
+    int kind[kMaxParams];
     param_kinds(pr->camera_model[c], kind);
     for (int k = 0; k < num_params(pr->camera_model[c]); ++k) {
       const bool var = (kind[k] == 0 && opt->refine_focal_length) || (kind[k] == 1 && opt->refine_principal_point) ||
                        (kind[k] == 2 && opt->refine_extra_params);
-      if (var) intr_col[4 * c + k] = (int32_t)D++;
+      if (var) intr_col[(size_t)KI * c + k] = (int32_t)D++;
     }
   }
   int64_t NP = 0;
@@ -220,8 +233,8 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
   {  // exact path: the reduced camera system is dense, D x D doubles must fit in this GPU's memory
     size_t free_b = 0, total_b = 0;
     B2_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    const double need = (iterative ? 16.0 * (double)D : (double)D * (double)D + 3.0 * (double)D) * 8.0 +
-                        (double)n_obs * (sizeof(ObsJac) + (iterative ? 4.0 : 0.0));
+    const double need = (iterative ? 24.0 * (double)D : (double)D * (double)D + 3.0 * (double)D) * 8.0 +
+                        (double)n_obs * ((wide ? sizeof(ObsJacW) : sizeof(ObsJac)) + (iterative ? 4.0 : 0.0));
     if (need > 0.9 * (double)free_b)
       return set_error(B2_ERR_INVALID, iterative ? "problem too large for this GPU's memory"
                                                  : "reduced camera system too large for the dense Schur path on this GPU "
@@ -239,7 +252,7 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
     const int i = pr->obs_image[o], c = pr->image_camera[i];
     bool free_block = pt_col[pr->obs_point[o]] >= 0;
     for (int k = 0; k < 6 && !free_block; ++k) free_block = pose_col[6 * i + k] >= 0;
-    for (int k = 0; k < 4 && !free_block; ++k) free_block = intr_col[4 * c + k] >= 0;
+    for (int k = 0; k < KI && !free_block; ++k) free_block = intr_col[(size_t)KI * c + k] >= 0;
     n_obs_reduced += free_block ? 1 : 0;
   }
   sum->num_residuals_reduced = (int32_t)(2 * n_obs_reduced);
@@ -262,6 +275,11 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
   BaDev P;
   memset(&P, 0, sizeof P);
   P.n_img = n_img; P.n_cam = n_cam; P.n_pts = n_pts; P.n_obs = n_obs; P.D = D;
+  P.wide = wide ? 1 : 0;
+  // camera parameters on the device: KI doubles per camera, zero-padded (the host array has its own stride)
+  std::vector<double> cam_dev((size_t)n_cam * KI, 0.0);
+  for (int c = 0; c < n_cam; ++c)
+    for (int k = 0; k < num_params(pr->camera_model[c]); ++k) cam_dev[(size_t)KI * c + k] = pr->camera_params[(size_t)cs * c + k];
   int32_t *d_obs_img, *d_obs_pt, *d_img_cam, *d_cam_model, *d_pose_col, *d_intr_col, *d_pt_col;
   double* d_obs_xy;
   int64_t* d_pt_start;
@@ -278,13 +296,14 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
   P.img_cam = d_img_cam; P.cam_model = d_cam_model; P.pose_col = d_pose_col; P.intr_col = d_intr_col; P.pt_col = d_pt_col;
   B2_TRY(dev_upload(h, &P.qvec, qn.data(), qn.size()));
   B2_TRY(dev_upload(h, &P.tvec, (const double*)pr->tvec, (size_t)n_img * 3));
-  B2_TRY(dev_upload(h, &P.cam_params, (const double*)pr->camera_params, (size_t)n_cam * 4));
+  B2_TRY(dev_upload(h, &P.cam_params, (const double*)cam_dev.data(), cam_dev.size()));
   B2_TRY(dev_upload(h, &P.xyz, (const double*)pr->xyz, (size_t)n_pts * 3));
   B2_TRY(dev_alloc(h, &P.qvec_new, (size_t)n_img * 4));
   B2_TRY(dev_alloc(h, &P.tvec_new, (size_t)n_img * 3));
-  B2_TRY(dev_alloc(h, &P.cam_new, (size_t)n_cam * 4));
+  B2_TRY(dev_alloc(h, &P.cam_new, (size_t)n_cam * KI));
   B2_TRY(dev_alloc(h, &P.xyz_new, (size_t)n_pts * 3));
-  B2_TRY(dev_alloc(h, &P.J, (size_t)n_obs));
+  if (wide) B2_TRY(dev_alloc(h, &P.JW, (size_t)n_obs));
+  else B2_TRY(dev_alloc(h, &P.J, (size_t)n_obs));
   B2_TRY(dev_alloc(h, &P.scale_c, (size_t)D));
   B2_TRY(dev_alloc(h, &P.scale_p, (size_t)NP * 3));
   B2_TRY(dev_alloc(h, &P.colnorm_c, (size_t)D));
@@ -338,7 +357,7 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
       for (int k = 0; k < n; ++k) if (cols[k] >= 0) { blk_first[cols[k]] = f; blk_size[cols[k]] = cnt; }
     };
     for (int i = 0; i < n_img; ++i) { mark(&pose_col[6 * (size_t)i], 3); mark(&pose_col[6 * (size_t)i + 3], 3); }
-    for (int c = 0; c < n_cam; ++c) mark(&intr_col[4 * (size_t)c], 4);
+    for (int c = 0; c < n_cam; ++c) mark(&intr_col[(size_t)KI * c], KI);
     int64_t* d_img_start; int32_t *d_img_obs, *d_blk_first, *d_blk_size;
     B2_TRY(dev_upload(h, &d_img_start, img_start.data(), img_start.size()));
     B2_TRY(dev_upload(h, &d_img_obs, img_obs.data(), img_obs.size()));
@@ -348,7 +367,8 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
     B2_TRY(dev_alloc(h, &I.tp, (size_t)NP * 3));
     B2_TRY(dev_alloc(h, &I.zp, (size_t)NP * 3));
     B2_TRY(dev_alloc(h, &I.lm_c, (size_t)D));
-    B2_TRY(dev_alloc(h, &I.M, (size_t)D * 4));
+    B2_TRY(dev_alloc(h, &I.M, (size_t)D * KI));
+    I.m_stride = KI;
     B2_TRY(dev_alloc(h, &I.flag, 1));
     V.x = P.dc;
     B2_TRY(dev_alloc(h, &V.r, (size_t)D));
@@ -389,7 +409,7 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
   uint32_t *pm_count = nullptr, *pm_start = nullptr;
   uint64_t* pm_tuples = nullptr;
   double *pm_W = nullptr, *pm_Y = nullptr;
-  if (const char* e = getenv("B2_BA_SCHUR")) pair_major = !iterative && strcmp(e, "blocks") == 0 && n_img > 0 && n_img <= 4096 && n_obs > 0;
+  if (const char* e = getenv("B2_BA_SCHUR")) pair_major = !iterative && !wide && strcmp(e, "blocks") == 0 && n_img > 0 && n_img <= 4096 && n_obs > 0;
   if (pair_major) {
     uint64_t n_tuples = 0;
     for (int p = 0; p < n_pts; ++p) {
@@ -443,10 +463,10 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
           break;
         }
       }
-      B2_CUDA(cudaMemsetAsync(I.M, 0, std::max<size_t>((size_t)D * 4, 1) * 8, s));
+      B2_CUDA(cudaMemsetAsync(I.M, 0, std::max<size_t>((size_t)D * KI, 1) * 8, s));
       B2_CUDA(cudaMemsetAsync(I.flag, 0, sizeof(int), s));
       B2_CUDA(bai_launch_precond(P, I, s));
-      B2_TRY(sync_reduce(h, I.M, D * 4, 0));
+      B2_TRY(sync_reduce(h, I.M, D * KI, 0));
       B2_CUDA(bai_launch_precond_invert(P, I, s));
       count_launches(2);
       if (D > 0) {
@@ -553,9 +573,11 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
   // ---------------------------------------------------------------- download (in place)
   B2_CUDA(cudaMemcpyAsync(pr->qvec, P.qvec, (size_t)n_img * 4 * 8, cudaMemcpyDeviceToHost, s));
   B2_CUDA(cudaMemcpyAsync(pr->tvec, P.tvec, (size_t)n_img * 3 * 8, cudaMemcpyDeviceToHost, s));
-  B2_CUDA(cudaMemcpyAsync(pr->camera_params, P.cam_params, (size_t)n_cam * 4 * 8, cudaMemcpyDeviceToHost, s));
+  B2_CUDA(cudaMemcpyAsync(cam_dev.data(), P.cam_params, cam_dev.size() * 8, cudaMemcpyDeviceToHost, s));
   B2_CUDA(cudaMemcpyAsync(pr->xyz, P.xyz, (size_t)n_pts * 3 * 8, cudaMemcpyDeviceToHost, s));
   B2_CUDA(cudaStreamSynchronize(s));
+  for (int c = 0; c < n_cam; ++c)
+    for (int k = 0; k < num_params(pr->camera_model[c]); ++k) pr->camera_params[(size_t)cs * c + k] = cam_dev[(size_t)KI * c + k];
   float ms = 0;
   B2_CUDA(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
   sum->solve_seconds = ms * 1e-3;

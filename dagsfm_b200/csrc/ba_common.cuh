@@ -7,11 +7,24 @@
 
 namespace b2 {
 
-// Per-observation residual and Jacobi-scaled Jacobian blocks (224 bytes).
+// Per-observation residual and Jacobi-scaled Jacobian blocks (224 bytes): the layout of the three camera models with
+// at most four parameters (SIMPLE_PINHOLE, PINHOLE, SIMPLE_RADIAL) -- the reference's defaults and the fast path.
 struct ObsJac {
+  static constexpr int kKI = 4;    // intrinsics slots per camera
+  static constexpr int kNC = 10;   // camera-side columns per observation
   double r[2];
   double Jc[20];  // 2 x 10: [rotation 3 | translation 3 | intrinsics 4]
   double Jp[6];   // 2 x 3
+};
+// The wide layout (352 bytes) for problems that contain any other model of camera_models.h (up to 12 parameters:
+// FULL_OPENCV, THIN_PRISM_FISHEYE).  Every kernel that touches Jacobian blocks is a template over the layout; the
+// 4-slot instantiations are the production kernels, unchanged.
+struct ObsJacW {
+  static constexpr int kKI = 12;
+  static constexpr int kNC = 18;
+  double r[2];
+  double Jc[36];  // 2 x 18: [rotation 3 | translation 3 | intrinsics 12]
+  double Jp[6];
 };
 
 struct BaDev {
@@ -41,7 +54,14 @@ struct BaDev {
   double *diag_p, *g_p, *Vinv;  // per variable point
   double *dc, *dp;              // step
   double* gmax;                 // gradient max norm (bit pattern of a non-negative double)
+  // (appended: the offsets above are what the production kernels were compiled and validated with)
+  ObsJacW* JW;                  // Jacobian blocks in the wide layout, when wide != 0 (then J == nullptr)
+  int32_t wide;                 // 0: ObsJac, intrinsics stride 4; 1: ObsJacW, stride 12 (cam_params, cam_new, intr_col)
+  int32_t reserved_;
 };
+template <class J> __host__ __device__ inline J* jac(const BaDev& P);
+template <> __host__ __device__ inline ObsJac* jac<ObsJac>(const BaDev& P) { return P.J; }
+template <> __host__ __device__ inline ObsJacW* jac<ObsJacW>(const BaDev& P) { return P.JW; }
 
 cudaError_t ba_launch_jacobian(const BaDev& P, const double* q, const double* t, const double* k, const double* X,
                                int mode, double* cost_out, cudaStream_t s, int loss_type = 0, double loss_scale = 1.0);
@@ -69,8 +89,9 @@ struct BaIter {
   double* tp;                // [NP * 3] V^-1 g_p
   double* zp;                // [NP * 3] V^-1 E'F x of the current product
   double* lm_c;              // [D] LM diagonal of the camera columns
-  double* M;                 // [D * 4] block diagonal of S, then its inverse (SCHUR_JACOBI)
+  double* M;                 // [D * m_stride] block diagonal of S, then its inverse (SCHUR_JACOBI)
   int* flag;                 // raised by precond_invert_kernel on a block that is not positive definite
+  int32_t m_stride;          // 4, or 12 in the wide layout (largest parameter block = a camera's intrinsics)
 };
 cudaError_t bai_launch_point_prepare(const BaDev& P, const BaIter& I, double radius, double min_diag, double max_diag, cudaStream_t s);
 cudaError_t bai_launch_rhs(const BaDev& P, const BaIter& I, cudaStream_t s);

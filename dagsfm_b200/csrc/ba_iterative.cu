@@ -58,6 +58,7 @@ __device__ __forceinline__ void atomic_max_nonneg(double* addr, double v) {
 // ------------------------------------------------------------------ per LM iteration
 // Eight lanes per point: V = E'E + D_p^2, V^-1, g_p, diag_p, t_p = V^-1 g_p, gradient max norm of
 // the point columns.  (The exact path computes the same quantities inside schur_kernel.)
+template <class J>
 __global__ void __launch_bounds__(256)
 point_prepare_kernel(BaDev P, BaIter I, double radius, double min_diag, double max_diag) {
   const int64_t gt = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -69,7 +70,7 @@ point_prepare_kernel(BaDev P, BaIter I, double radius, double min_diag, double m
     const int64_t o0 = P.pt_start[p];
     const int L = (int)(P.pt_start[p + 1] - o0);
     for (int a = sub; a < L; a += kLanesPerPoint) {
-      const ObsJac& e = P.J[o0 + a];
+      const J& e = jac<J>(P)[o0 + a];
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         const double j0 = e.Jp[3 * i], j1 = e.Jp[3 * i + 1], j2 = e.Jp[3 * i + 2], r = e.r[i];
@@ -112,32 +113,34 @@ point_prepare_kernel(BaDev P, BaIter I, double radius, double min_diag, double m
 //           out2 = sum_o Jc_o' r_o = g_c,  out3 = diag(F'F)
 // Pose columns belong to this block alone (plain stores into zeroed vectors); intrinsics may be
 // shared between images and are added atomically.
-template <int MODE>
+template <int MODE, class J>
 __global__ void __launch_bounds__(kImageThreads)
 image_pass_kernel(BaDev P, BaIter I, const double* __restrict__ x, const double* __restrict__ zp,
                   double* __restrict__ out, double* __restrict__ out2, double* __restrict__ out3) {
-  constexpr int NV = (MODE == 0) ? 10 : 30;
+  constexpr int KI = J::kKI, NC = J::kNC;
+  constexpr int NV = (MODE == 0) ? NC : 3 * NC;
+  static_assert(NV <= kImageThreads, "one thread per reduced value");
   __shared__ double sh[kImageThreads / 32][NV];
   const int i = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int cm = P.img_cam[i];
-  int col[10];
+  int col[NC];
   bool any = false;
 #pragma unroll
   for (int k = 0; k < 6; ++k) { col[k] = P.pose_col[6 * i + k]; any |= col[k] >= 0; }
 #pragma unroll
-  for (int k = 0; k < 4; ++k) { col[6 + k] = P.intr_col[4 * cm + k]; any |= col[6 + k] >= 0; }
+  for (int k = 0; k < KI; ++k) { col[6 + k] = P.intr_col[KI * cm + k]; any |= col[6 + k] >= 0; }
   if (!any) return;  // uniform over the block
-  double xl[10];
+  double xl[NC];
 #pragma unroll
-  for (int k = 0; k < 10; ++k) xl[k] = (MODE == 0 && col[k] >= 0) ? x[col[k]] : 0.0;
+  for (int k = 0; k < NC; ++k) xl[k] = (MODE == 0 && col[k] >= 0) ? x[col[k]] : 0.0;
   double acc[NV];
 #pragma unroll
   for (int k = 0; k < NV; ++k) acc[k] = 0.0;
   const int64_t s0 = I.img_start[i], s1 = I.img_start[i + 1];
   for (int64_t s = s0 + tid; s < s1; s += kImageThreads) {
     const int o = I.img_obs[s];
-    const ObsJac& e = P.J[o];
+    const J& e = jac<J>(P)[o];
     const int pc = P.pt_col[P.obs_pt[o]];
     double z0 = 0, z1 = 0, z2 = 0;
     if (pc >= 0) { z0 = zp[3 * (int64_t)pc]; z1 = zp[3 * (int64_t)pc + 1]; z2 = zp[3 * (int64_t)pc + 2]; }
@@ -148,19 +151,19 @@ image_pass_kernel(BaDev P, BaIter I, const double* __restrict__ x, const double*
       if (MODE == 0) {
         ua = 0;
 #pragma unroll
-        for (int k = 0; k < 10; ++k) ua += e.Jc[10 * a + k] * xl[k];
+        for (int k = 0; k < NC; ++k) ua += e.Jc[NC * a + k] * xl[k];
       } else {
         ua = e.r[a];
       }
       u[a] = ua - (e.Jp[3 * a] * z0 + e.Jp[3 * a + 1] * z1 + e.Jp[3 * a + 2] * z2);
     }
 #pragma unroll
-    for (int k = 0; k < 10; ++k) {
-      const double j0 = e.Jc[k], j1 = e.Jc[10 + k];
+    for (int k = 0; k < NC; ++k) {
+      const double j0 = e.Jc[k], j1 = e.Jc[NC + k];
       acc[k] += j0 * u[0] + j1 * u[1];
       if (MODE == 1) {
-        acc[10 + k] += j0 * e.r[0] + j1 * e.r[1];
-        acc[20 + k] += j0 * j0 + j1 * j1;
+        acc[NC + k] += j0 * e.r[0] + j1 * e.r[1];
+        acc[2 * NC + k] += j0 * j0 + j1 * j1;
       }
     }
   }
@@ -174,7 +177,7 @@ image_pass_kernel(BaDev P, BaIter I, const double* __restrict__ x, const double*
     double s = 0;
 #pragma unroll
     for (int w = 0; w < kImageThreads / 32; ++w) s += sh[w][tid];
-    const int k = tid % 10, which = tid / 10;
+    const int k = tid % NC, which = tid / NC;
     const int c = col[k];
     if (c >= 0) {
       double* dst = (which == 0) ? out : (which == 1) ? out2 : out3;
@@ -197,71 +200,73 @@ __global__ void cam_diag_kernel(BaDev P, BaIter I, double radius, double min_dia
 //   the parameter block: W_b)' |blk
 // for its three camera-side parameter blocks (rotation, tvec, intrinsics).  Summed over a this is
 // the (blk, blk) block of S = F'F - F'E (E'E)^-1 E'F; the LM diagonal is added by the inversion.
+template <class J>
 __global__ void __launch_bounds__(128) precond_kernel(BaDev P, BaIter I) {
+  constexpr int KI = J::kKI, NC = J::kNC;
   const int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (o >= P.n_obs) return;
   const int i = P.obs_img[o], cm = P.img_cam[i], p = P.obs_pt[o], pc = P.pt_col[p];
-  const ObsJac& e = P.J[o];
-  int col[10];
+  const J& e = jac<J>(P)[o];
+  int col[NC];
 #pragma unroll
   for (int k = 0; k < 6; ++k) col[k] = P.pose_col[6 * i + k];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) col[6 + k] = P.intr_col[4 * cm + k];
-  // A[k][l] for k, l inside one group: rotation 0..2, tvec 3..5, intrinsics 6..9
-  double A[10][4];
+  for (int k = 0; k < KI; ++k) col[6 + k] = P.intr_col[KI * cm + k];
+  // A[k][l] for k, l inside one group: rotation 0..2, tvec 3..5, intrinsics 6..6+KI-1
+  double A[NC][KI];
 #pragma unroll
-  for (int k = 0; k < 10; ++k) {
-    const int g0 = (k < 3) ? 0 : (k < 6) ? 3 : 6, gn = (k < 6) ? 3 : 4;
+  for (int k = 0; k < NC; ++k) {
+    const int g0 = (k < 3) ? 0 : (k < 6) ? 3 : 6, gn = (k < 6) ? 3 : KI;
 #pragma unroll
-    for (int l = 0; l < 4; ++l)
-      A[k][l] = (l < gn) ? e.Jc[k] * e.Jc[g0 + l] + e.Jc[10 + k] * e.Jc[10 + g0 + l] : 0.0;
+    for (int l = 0; l < KI; ++l)
+      A[k][l] = (l < gn) ? e.Jc[k] * e.Jc[g0 + l] + e.Jc[NC + k] * e.Jc[NC + g0 + l] : 0.0;
   }
   if (pc >= 0) {
-    double T[10][3];  // sum of W_b over the observations of this point in the same image (rows 0..5) / camera (6..9)
+    double T[NC][3];  // sum of W_b over the observations of this point in the same image (rows 0..5) / camera (6..)
 #pragma unroll
-    for (int k = 0; k < 10; ++k) T[k][0] = T[k][1] = T[k][2] = 0.0;
+    for (int k = 0; k < NC; ++k) T[k][0] = T[k][1] = T[k][2] = 0.0;
     const int64_t o0 = P.pt_start[p], o1 = P.pt_start[p + 1];
     for (int64_t b = o0; b < o1; ++b) {
       const int ib = P.obs_img[b];
       const bool same_img = ib == i, same_cam = same_img || P.img_cam[ib] == cm;
       if (!same_cam) continue;
-      const ObsJac& eb = P.J[b];
+      const J& eb = jac<J>(P)[b];
 #pragma unroll
-      for (int k = 0; k < 10; ++k) {
+      for (int k = 0; k < NC; ++k) {
         if (k < 6 && !same_img) continue;
 #pragma unroll
-        for (int m = 0; m < 3; ++m) T[k][m] += eb.Jc[k] * eb.Jp[m] + eb.Jc[10 + k] * eb.Jp[3 + m];
+        for (int m = 0; m < 3; ++m) T[k][m] += eb.Jc[k] * eb.Jp[m] + eb.Jc[NC + k] * eb.Jp[3 + m];
       }
     }
     const double* Vi = P.Vinv + 9 * (int64_t)pc;
 #pragma unroll
-    for (int k = 0; k < 10; ++k) {
+    for (int k = 0; k < NC; ++k) {
       double w[3], y[3];
 #pragma unroll
-      for (int m = 0; m < 3; ++m) w[m] = e.Jc[k] * e.Jp[m] + e.Jc[10 + k] * e.Jp[3 + m];
+      for (int m = 0; m < 3; ++m) w[m] = e.Jc[k] * e.Jp[m] + e.Jc[NC + k] * e.Jp[3 + m];
 #pragma unroll
       for (int m = 0; m < 3; ++m) y[m] = w[0] * Vi[m] + w[1] * Vi[3 + m] + w[2] * Vi[6 + m];
-      const int g0 = (k < 3) ? 0 : (k < 6) ? 3 : 6, gn = (k < 6) ? 3 : 4;
+      const int g0 = (k < 3) ? 0 : (k < 6) ? 3 : 6, gn = (k < 6) ? 3 : KI;
 #pragma unroll
-      for (int l = 0; l < 4; ++l)
+      for (int l = 0; l < KI; ++l)
         if (l < gn) A[k][l] -= y[0] * T[g0 + l][0] + y[1] * T[g0 + l][1] + y[2] * T[g0 + l][2];
     }
   }
 #pragma unroll
   for (int g = 0; g < 3; ++g) {
-    const int g0 = (g == 0) ? 0 : (g == 1) ? 3 : 6, gn = (g == 2) ? 4 : 3;
+    const int g0 = (g == 0) ? 0 : (g == 1) ? 3 : 6, gn = (g == 2) ? KI : 3;
     int first = -1;
 #pragma unroll
-    for (int l = 0; l < 4; ++l)
+    for (int l = 0; l < KI; ++l)
       if (l < gn && first < 0 && col[g0 + l] >= 0) first = col[g0 + l];  // columns of a block are consecutive
     if (first < 0) continue;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < KI; ++k) {
       if (k >= gn || col[g0 + k] < 0) continue;
 #pragma unroll
-      for (int l = 0; l < 4; ++l) {
+      for (int l = 0; l < KI; ++l) {
         if (l >= gn || col[g0 + l] < 0) continue;
-        atomicAdd(I.M + 4 * (int64_t)col[g0 + k] + (col[g0 + l] - first), A[g0 + k][l]);
+        atomicAdd(I.M + KI * (int64_t)col[g0 + k] + (col[g0 + l] - first), A[g0 + k][l]);
       }
     }
   }
@@ -269,13 +274,14 @@ __global__ void __launch_bounds__(128) precond_kernel(BaDev P, BaIter I) {
 
 // Thread per parameter block: M_blk + D_c^2 -> its inverse by Cholesky (BlockRandomAccessDiagonalMatrix::Invert).
 // A block that is not positive definite raises *flag (the step is then treated as a linear-solver failure).
+template <int KI>
 __global__ void precond_invert_kernel(BaDev P, BaIter I) {
   const int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (f >= P.D || I.blk_first[f] != f) return;
   const int n = I.blk_size[f];
-  double A[4][4], Lc[4][4], Inv[4][4];
+  double A[KI][KI], Lc[KI][KI], Inv[KI][KI];
   for (int r = 0; r < n; ++r)
-    for (int c = 0; c < n; ++c) { A[r][c] = I.M[4 * (f + r) + c]; Lc[r][c] = 0.0; }
+    for (int c = 0; c < n; ++c) { A[r][c] = I.M[KI * (f + r) + c]; Lc[r][c] = 0.0; }
   for (int r = 0; r < n; ++r) A[r][r] += I.lm_c[f + r];
   for (int j = 0; j < n; ++j) {
     double d = A[j][j];
@@ -289,7 +295,7 @@ __global__ void precond_invert_kernel(BaDev P, BaIter I) {
     }
   }
   for (int c = 0; c < n; ++c) {
-    double y[4];
+    double y[KI];
     for (int r = 0; r < n; ++r) {
       double v = (r == c) ? 1.0 : 0.0;
       for (int k = 0; k < r; ++k) v -= Lc[r][k] * y[k];
@@ -302,13 +308,15 @@ __global__ void precond_invert_kernel(BaDev P, BaIter I) {
     }
   }
   for (int r = 0; r < n; ++r)
-    for (int c = 0; c < n; ++c) I.M[4 * (f + r) + c] = Inv[r][c];
+    for (int c = 0; c < n; ++c) I.M[KI * (f + r) + c] = Inv[r][c];
 }
 
 // ------------------------------------------------------------------ per CG iteration
 // x -> z_p = V^-1 sum_a Jp_a' (Jc_a x)   (eight lanes per point)
+template <class J>
 __global__ void __launch_bounds__(256)
 matvec_point_kernel(BaDev P, const double* __restrict__ x, double* __restrict__ zp) {
+  constexpr int KI = J::kKI, NC = J::kNC;
   const int64_t gt = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t p = gt / kLanesPerPoint;
   const int sub = threadIdx.x & (kLanesPerPoint - 1);
@@ -318,18 +326,18 @@ matvec_point_kernel(BaDev P, const double* __restrict__ x, double* __restrict__ 
     const int64_t o0 = P.pt_start[p];
     const int L = (int)(P.pt_start[p + 1] - o0);
     for (int a = sub; a < L; a += kLanesPerPoint) {
-      const ObsJac& e = P.J[o0 + a];
+      const J& e = jac<J>(P)[o0 + a];
       const int i = P.obs_img[o0 + a], cm = P.img_cam[i];
       double u0 = 0, u1 = 0;
 #pragma unroll
       for (int k = 0; k < 6; ++k) {
         const int c = P.pose_col[6 * i + k];
-        if (c >= 0) { const double xv = x[c]; u0 += e.Jc[k] * xv; u1 += e.Jc[10 + k] * xv; }
+        if (c >= 0) { const double xv = x[c]; u0 += e.Jc[k] * xv; u1 += e.Jc[NC + k] * xv; }
       }
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int c = P.intr_col[4 * cm + k];
-        if (c >= 0) { const double xv = x[c]; u0 += e.Jc[6 + k] * xv; u1 += e.Jc[16 + k] * xv; }
+      for (int k = 0; k < KI; ++k) {
+        const int c = P.intr_col[KI * cm + k];
+        if (c >= 0) { const double xv = x[c]; u0 += e.Jc[6 + k] * xv; u1 += e.Jc[NC + 6 + k] * xv; }
       }
 #pragma unroll
       for (int k = 0; k < 3; ++k) y[k] += e.Jp[k] * u0 + e.Jp[3 + k] * u1;
@@ -371,7 +379,7 @@ __global__ void __launch_bounds__(256) cg_precond_kernel(int64_t D, BaIter I, co
   for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < D; j += (int64_t)gridDim.x * blockDim.x) {
     const int f = I.blk_first[j], n = I.blk_size[j];
     double v = 0;
-    for (int k = 0; k < n; ++k) v += I.M[4 * j + k] * r[f + k];
+    for (int k = 0; k < n; ++k) v += I.M[I.m_stride * j + k] * r[f + k];
     z[j] = v;
     s += r[j] * v;
   }
@@ -418,12 +426,14 @@ static inline int vec_grid(int64_t D) { return (int)std::max<int64_t>(1, std::mi
 
 cudaError_t bai_launch_point_prepare(const BaDev& P, const BaIter& I, double radius, double min_diag, double max_diag, cudaStream_t s) {
   if (P.n_pts == 0) return cudaSuccess;
-  bit::point_prepare_kernel<<<nblk((int64_t)P.n_pts * bit::kLanesPerPoint, 256), 256, 0, s>>>(P, I, radius, min_diag, max_diag);
+  if (P.wide) bit::point_prepare_kernel<ObsJacW><<<nblk((int64_t)P.n_pts * bit::kLanesPerPoint, 256), 256, 0, s>>>(P, I, radius, min_diag, max_diag);
+  else bit::point_prepare_kernel<ObsJac><<<nblk((int64_t)P.n_pts * bit::kLanesPerPoint, 256), 256, 0, s>>>(P, I, radius, min_diag, max_diag);
   return cudaGetLastError();
 }
 cudaError_t bai_launch_rhs(const BaDev& P, const BaIter& I, cudaStream_t s) {
   if (P.n_img == 0 || P.n_obs == 0) return cudaSuccess;
-  bit::image_pass_kernel<1><<<P.n_img, bit::kImageThreads, 0, s>>>(P, I, nullptr, I.tp, P.rhs, P.g_c, P.diag_c);
+  if (P.wide) bit::image_pass_kernel<1, ObsJacW><<<P.n_img, bit::kImageThreads, 0, s>>>(P, I, nullptr, I.tp, P.rhs, P.g_c, P.diag_c);
+  else bit::image_pass_kernel<1, ObsJac><<<P.n_img, bit::kImageThreads, 0, s>>>(P, I, nullptr, I.tp, P.rhs, P.g_c, P.diag_c);
   return cudaGetLastError();
 }
 cudaError_t bai_launch_cam_diag(const BaDev& P, const BaIter& I, double radius, double min_diag, double max_diag, cudaStream_t s) {
@@ -433,12 +443,14 @@ cudaError_t bai_launch_cam_diag(const BaDev& P, const BaIter& I, double radius, 
 }
 cudaError_t bai_launch_precond(const BaDev& P, const BaIter& I, cudaStream_t s) {
   if (P.n_obs == 0) return cudaSuccess;
-  bit::precond_kernel<<<nblk(P.n_obs, 128), 128, 0, s>>>(P, I);
+  if (P.wide) bit::precond_kernel<ObsJacW><<<nblk(P.n_obs, 128), 128, 0, s>>>(P, I);
+  else bit::precond_kernel<ObsJac><<<nblk(P.n_obs, 128), 128, 0, s>>>(P, I);
   return cudaGetLastError();
 }
 cudaError_t bai_launch_precond_invert(const BaDev& P, const BaIter& I, cudaStream_t s) {
   if (P.D == 0) return cudaSuccess;
-  bit::precond_invert_kernel<<<nblk(P.D, 128), 128, 0, s>>>(P, I);
+  if (P.wide) bit::precond_invert_kernel<12><<<nblk(P.D, 128), 128, 0, s>>>(P, I);
+  else bit::precond_invert_kernel<4><<<nblk(P.D, 128), 128, 0, s>>>(P, I);
   return cudaGetLastError();
 }
 // out = F'(F x - E (E'E)^-1 E'F x): zeroes `out`, two kernels.  The caller all-reduces `out` and adds D_c^2 x.
@@ -447,8 +459,13 @@ cudaError_t bai_launch_matvec(const BaDev& P, const BaIter& I, const double* x, 
   cudaError_t e = cudaMemsetAsync(out, 0, (size_t)P.D * sizeof(double), s);
   if (e != cudaSuccess) return e;
   if (P.n_obs == 0 || P.n_img == 0) return cudaSuccess;
-  bit::matvec_point_kernel<<<nblk((int64_t)P.n_pts * bit::kLanesPerPoint, 256), 256, 0, s>>>(P, x, I.zp);
-  bit::image_pass_kernel<0><<<P.n_img, bit::kImageThreads, 0, s>>>(P, I, x, I.zp, out, nullptr, nullptr);
+  if (P.wide) {
+    bit::matvec_point_kernel<ObsJacW><<<nblk((int64_t)P.n_pts * bit::kLanesPerPoint, 256), 256, 0, s>>>(P, x, I.zp);
+    bit::image_pass_kernel<0, ObsJacW><<<P.n_img, bit::kImageThreads, 0, s>>>(P, I, x, I.zp, out, nullptr, nullptr);
+  } else {
+    bit::matvec_point_kernel<ObsJac><<<nblk((int64_t)P.n_pts * bit::kLanesPerPoint, 256), 256, 0, s>>>(P, x, I.zp);
+    bit::image_pass_kernel<0, ObsJac><<<P.n_img, bit::kImageThreads, 0, s>>>(P, I, x, I.zp, out, nullptr, nullptr);
+  }
   return cudaGetLastError();
 }
 cudaError_t bai_launch_dot(int64_t D, const double* a, const double* b, double* partial, int* n_partial, cudaStream_t s) {

@@ -23,16 +23,21 @@
 
 #include "ba_common.cuh"
 #include "ba_loss.cuh"
+#include "camera_jets.cuh"
 
 namespace b2 {
 namespace bak {
 
 constexpr unsigned kFull = 0xffffffffu;
 
-// One observation: residual and Jacobian blocks.  Returns false if only the residual is wanted.
+// One observation: residual and Jacobian blocks (only the residual if Jc == nullptr).  KI = intrinsics slots: 4 =
+// the production instantiation (SIMPLE_PINHOLE / PINHOLE / SIMPLE_RADIAL, hand-derived formulas); 12 adds the other
+// eight models of camera_models.h, differentiated on dual numbers (camera_jets.cuh) as Ceres' autodiff does.
+template <int KI>
 __device__ __forceinline__ void evaluate(int model, const double* q, const double* t, const double* X,
-                                         const double* k, double ox, double oy, double* r, double* Jc /*2x10*/,
+                                         const double* k, double ox, double oy, double* r, double* Jc /*2 x (6+KI)*/,
                                          double* Jp /*2x3*/) {
+  constexpr int NC = 6 + KI;
   const double w = q[0], x = q[1], y = q[2], z = q[3];
   const double t2 = w * x, t3 = w * y, t4 = w * z, t5 = -x * x, t6 = x * y, t7 = x * z, t8 = -y * y, t9 = y * z,
                t1 = -z * z;
@@ -44,7 +49,7 @@ __device__ __forceinline__ void evaluate(int model, const double* q, const doubl
   p2 += t[2];
   const double u = p0 / p2, v = p1 / p2;
   double xi, yi, dxdu, dxdv, dydu, dydv;
-  double dk0[4] = {0, 0, 0, 0}, dk1[4] = {0, 0, 0, 0};
+  double dk0[KI] = {0, 0, 0, 0}, dk1[KI] = {0, 0, 0, 0};  // remaining slots (KI = 12) are zero-initialised too
   if (model == 0) {
     xi = k[0] * u + k[1]; yi = k[0] * v + k[2];
     dxdu = k[0]; dxdv = 0; dydu = 0; dydv = k[0];
@@ -53,7 +58,7 @@ __device__ __forceinline__ void evaluate(int model, const double* q, const doubl
     xi = k[0] * u + k[2]; yi = k[1] * v + k[3];
     dxdu = k[0]; dxdv = 0; dydu = 0; dydv = k[1];
     dk0[0] = u; dk0[2] = 1; dk1[1] = v; dk1[3] = 1;
-  } else {
+  } else if (KI == 4 || model == 2) {
     const double u2 = u * u, v2 = v * v, r2 = u2 + v2, radial = k[3] * r2;
     const double du = u * radial, dv = v * radial;
     const double xd = u + du, yd = v + dv;
@@ -62,6 +67,13 @@ __device__ __forceinline__ void evaluate(int model, const double* q, const doubl
     dydu = k[0] * (2 * k[3] * u * v); dydv = k[0] * (1 + radial + 2 * k[3] * v2);
     dk0[0] = xd; dk0[1] = 1; dk0[3] = k[0] * u * r2;
     dk1[0] = yd; dk1[2] = 1; dk1[3] = k[0] * v * r2;
+  } else {
+    cam::Jet<2 + KI> xj, yj;
+    cam::world_to_image_jet<2 + KI>(model, k, u, v, &xj, &yj);
+    xi = xj.a; yi = yj.a;
+    dxdu = xj.v[0]; dxdv = xj.v[1]; dydu = yj.v[0]; dydv = yj.v[1];
+#pragma unroll
+    for (int a = 0; a < KI; ++a) { dk0[a] = xj.v[2 + a]; dk1[a] = yj.v[2 + a]; }
   }
   r[0] = xi - ox;
   r[1] = yi - oy;
@@ -90,12 +102,12 @@ __device__ __forceinline__ void evaluate(int model, const double* q, const doubl
     for (int a = 0; a < 4; ++a) drdq[a] = drdp[i][0] * dpdq[0][a] + drdp[i][1] * dpdq[1][a] + drdp[i][2] * dpdq[2][a];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      Jc[10 * i + c] = drdq[0] * JL[0][c] + drdq[1] * JL[1][c] + drdq[2] * JL[2][c] + drdq[3] * JL[3][c];
-      Jc[10 * i + 3 + c] = drdp[i][c];
+      Jc[NC * i + c] = drdq[0] * JL[0][c] + drdq[1] * JL[1][c] + drdq[2] * JL[2][c] + drdq[3] * JL[3][c];
+      Jc[NC * i + 3 + c] = drdp[i][c];
       Jp[3 * i + c] = drdp[i][0] * R[0][c] + drdp[i][1] * R[1][c] + drdp[i][2] * R[2][c];
     }
 #pragma unroll
-    for (int a = 0; a < 4; ++a) Jc[10 * i + 6 + a] = (i == 0) ? dk0[a] : dk1[a];
+    for (int a = 0; a < KI; ++a) Jc[NC * i + 6 + a] = (i == 0) ? dk0[a] : dk1[a];
   }
 }
 
@@ -118,7 +130,7 @@ __device__ __forceinline__ void atomic_max_nonneg(double* addr, double v) {
 // residuals with Corrector (corrector.cc): for rho'' <= 0 -- always true for these two losses --
 // both are scaled by sqrt(rho'(s)), s = |r|^2, and the block's cost is rho(s) / 2.  LOSS == 0
 // compiles to exactly the code it was before the template parameter existed.
-template <int LOSS>
+template <int LOSS, class J>
 __global__ void __launch_bounds__(256)
 jacobian_kernel(BaDev P, const double* __restrict__ q, const double* __restrict__ t, const double* __restrict__ kp,
                 const double* __restrict__ X, int mode, double* __restrict__ cost_out, double loss_scale) {
@@ -127,48 +139,49 @@ jacobian_kernel(BaDev P, const double* __restrict__ q, const double* __restrict_
   if (o < P.n_obs) {
     const int i = P.obs_img[o], p = P.obs_pt[o], cm = P.img_cam[i];
     const double2 xy = P.obs_xy[o];
-    double r[2], Jc[20], Jp[6];
+    constexpr int KI = J::kKI, NC = J::kNC;
+    double r[2], Jc[2 * NC], Jp[6];
     double rho0 = 0;
     if (mode == 1) {
-      evaluate(P.cam_model[cm], q + 4 * i, t + 3 * i, X + 3 * (int64_t)p, kp + 4 * cm, xy.x, xy.y, r, nullptr, nullptr);
+      evaluate<KI>(P.cam_model[cm], q + 4 * i, t + 3 * i, X + 3 * (int64_t)p, kp + KI * cm, xy.x, xy.y, r, nullptr, nullptr);
       if (LOSS != 0) {
         double w;
         loss_eval<LOSS>(loss_scale, r[0] * r[0] + r[1] * r[1], &rho0, &w);
       }
     } else {
-      evaluate(P.cam_model[cm], q + 4 * i, t + 3 * i, X + 3 * (int64_t)p, kp + 4 * cm, xy.x, xy.y, r, Jc, Jp);
+      evaluate<KI>(P.cam_model[cm], q + 4 * i, t + 3 * i, X + 3 * (int64_t)p, kp + KI * cm, xy.x, xy.y, r, Jc, Jp);
       if (LOSS != 0) {
         double w;
         loss_eval<LOSS>(loss_scale, r[0] * r[0] + r[1] * r[1], &rho0, &w);
         r[0] *= w;
         r[1] *= w;
 #pragma unroll
-        for (int k = 0; k < 20; ++k) Jc[k] *= w;
+        for (int k = 0; k < 2 * NC; ++k) Jc[k] *= w;
 #pragma unroll
         for (int k = 0; k < 6; ++k) Jp[k] *= w;
       }
-      int col[10];
+      int col[NC];
 #pragma unroll
       for (int k = 0; k < 6; ++k) col[k] = P.pose_col[6 * i + k];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) col[6 + k] = P.intr_col[4 * cm + k];
+      for (int k = 0; k < KI; ++k) col[6 + k] = P.intr_col[KI * cm + k];
       const int pc = P.pt_col[p];
       if (mode == 2) {
 #pragma unroll
-        for (int k = 0; k < 10; ++k)
-          if (col[k] >= 0) atomicAdd(P.colnorm_c + col[k], Jc[k] * Jc[k] + Jc[10 + k] * Jc[10 + k]);
+        for (int k = 0; k < NC; ++k)
+          if (col[k] >= 0) atomicAdd(P.colnorm_c + col[k], Jc[k] * Jc[k] + Jc[NC + k] * Jc[NC + k]);
         if (pc >= 0)
 #pragma unroll
           for (int k = 0; k < 3; ++k) atomicAdd(P.colnorm_p + 3 * (int64_t)pc + k, Jp[k] * Jp[k] + Jp[3 + k] * Jp[3 + k]);
       } else {
-        ObsJac& e = P.J[o];
+        J& e = jac<J>(P)[o];
         e.r[0] = r[0];
         e.r[1] = r[1];
 #pragma unroll
-        for (int k = 0; k < 10; ++k) {
+        for (int k = 0; k < NC; ++k) {
           const double s = (col[k] >= 0) ? P.scale_c[col[k]] : 0.0;
           e.Jc[k] = Jc[k] * s;
-          e.Jc[10 + k] = Jc[10 + k] * s;
+          e.Jc[NC + k] = Jc[NC + k] * s;
         }
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -193,27 +206,29 @@ jacobian_kernel(BaDev P, const double* __restrict__ q, const double* __restrict_
 
 // ------------------------------------------------------------ camera terms
 // Thread per observation: U = Jc^T Jc into S (upper entries), g_c = Jc^T r, diag_c.
+template <class J>
 __global__ void __launch_bounds__(256) camera_terms_kernel(BaDev P) {
+  constexpr int KI = J::kKI, NC = J::kNC;
   const int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (o >= P.n_obs) return;
   const int i = P.obs_img[o], cm = P.img_cam[i];
-  int col[10];
+  int col[NC];
 #pragma unroll
   for (int k = 0; k < 6; ++k) col[k] = P.pose_col[6 * i + k];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) col[6 + k] = P.intr_col[4 * cm + k];
-  const ObsJac& e = P.J[o];
+  for (int k = 0; k < KI; ++k) col[6 + k] = P.intr_col[KI * cm + k];
+  const J& e = jac<J>(P)[o];
   const int64_t D = P.D;
 #pragma unroll
-  for (int k = 0; k < 10; ++k) {
+  for (int k = 0; k < NC; ++k) {
     if (col[k] < 0) continue;
-    const double a0 = e.Jc[k], a1 = e.Jc[10 + k];
+    const double a0 = e.Jc[k], a1 = e.Jc[NC + k];
     atomicAdd(P.g_c + col[k], a0 * e.r[0] + a1 * e.r[1]);
     atomicAdd(P.diag_c + col[k], a0 * a0 + a1 * a1);
 #pragma unroll
-    for (int l = 0; l < 10; ++l) {
+    for (int l = 0; l < NC; ++l) {
       if (col[l] < 0 || col[k] > col[l]) continue;
-      atomicAdd(P.S + col[k] * D + col[l], a0 * e.Jc[l] + a1 * e.Jc[10 + l]);
+      atomicAdd(P.S + col[k] * D + col[l], a0 * e.Jc[l] + a1 * e.Jc[NC + l]);
     }
   }
 }
@@ -230,11 +245,12 @@ constexpr int kSchurThreads = 128;
 // observation (Wg, Yg: [n_obs][30]) and leaves S -= Y_a W_b^T to pm_blocks_kernel, which sums the
 // contributions of one (image, image) block over all points before touching S.  PM == false is the
 // production kernel, unchanged.
-template <bool PM>
+template <bool PM, class J>
 __global__ void __launch_bounds__(kSchurThreads) schur_kernel(BaDev P, double radius, double min_diag, double max_diag,
                                                               double* __restrict__ Wg, double* __restrict__ Yg) {
-  __shared__ double sWa[kTile][30], sYa[kTile][30], sWb[kTile][30];
-  __shared__ int sCa[kTile][10], sCb[kTile][10];
+  constexpr int KI = J::kKI, NC = J::kNC, NW = 3 * NC;
+  __shared__ double sWa[kTile][NW], sYa[kTile][NW], sWb[kTile][NW];
+  __shared__ int sCa[kTile][NC], sCb[kTile][NC];
   __shared__ double sV[9], sT[3], sG[3];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t D = P.D;
@@ -247,7 +263,7 @@ __global__ void __launch_bounds__(kSchurThreads) schur_kernel(BaDev P, double ra
     if (warp == 0) {
       double v[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
       for (int a = lane; a < L; a += 32) {
-        const ObsJac& e = P.J[o0 + a];
+        const J& e = jac<J>(P)[o0 + a];
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           const double j0 = e.Jp[3 * i], j1 = e.Jp[3 * i + 1], j2 = e.Jp[3 * i + 2], r = e.r[i];
@@ -291,15 +307,15 @@ __global__ void __launch_bounds__(kSchurThreads) schur_kernel(BaDev P, double ra
     for (int a0 = 0; a0 < L; a0 += kTile) {
       const int na = min(kTile, L - a0);
       // W_a, Y_a, columns of the a-tile; rhs -= W_a t_p
-      for (int e = tid; e < na * 10; e += kSchurThreads) {
-        const int a = e / 10, k = e % 10;
-        const ObsJac& ob = P.J[o0 + a0 + a];
+      for (int e = tid; e < na * NC; e += kSchurThreads) {
+        const int a = e / NC, k = e % NC;
+        const J& ob = jac<J>(P)[o0 + a0 + a];
         const int i = P.obs_img[o0 + a0 + a];
-        const int col = (k < 6) ? P.pose_col[6 * i + k] : P.intr_col[4 * P.img_cam[i] + (k - 6)];
+        const int col = (k < 6) ? P.pose_col[6 * i + k] : P.intr_col[KI * P.img_cam[i] + (k - 6)];
         sCa[a][k] = col;
         double w[3];
 #pragma unroll
-        for (int l = 0; l < 3; ++l) w[l] = ob.Jc[k] * ob.Jp[l] + ob.Jc[10 + k] * ob.Jp[3 + l];
+        for (int l = 0; l < 3; ++l) w[l] = ob.Jc[k] * ob.Jp[l] + ob.Jc[NC + k] * ob.Jp[3 + l];
 #pragma unroll
         for (int l = 0; l < 3; ++l) {
           sWa[a][3 * k + l] = w[l];
@@ -309,8 +325,8 @@ __global__ void __launch_bounds__(kSchurThreads) schur_kernel(BaDev P, double ra
         if (PM) {
 #pragma unroll
           for (int l = 0; l < 3; ++l) {
-            Wg[(o0 + a0 + a) * 30 + 3 * k + l] = w[l];
-            Yg[(o0 + a0 + a) * 30 + 3 * k + l] = w[0] * sV[l] + w[1] * sV[3 + l] + w[2] * sV[6 + l];
+            Wg[(o0 + a0 + a) * NW + 3 * k + l] = w[l];
+            Yg[(o0 + a0 + a) * NW + 3 * k + l] = w[0] * sV[l] + w[1] * sV[3 + l] + w[2] * sV[6 + l];
           }
         }
       }
@@ -323,21 +339,22 @@ __global__ void __launch_bounds__(kSchurThreads) schur_kernel(BaDev P, double ra
       for (int b0 = a0; b0 < L; b0 += kTile) {
         const int nb = min(kTile, L - b0);
         if (b0 == a0) {
-          for (int e = tid; e < nb * 30; e += kSchurThreads) sWb[e / 30][e % 30] = sWa[e / 30][e % 30];
-          for (int e = tid; e < nb * 10; e += kSchurThreads) sCb[e / 10][e % 10] = sCa[e / 10][e % 10];
+          for (int e = tid; e < nb * NW; e += kSchurThreads) sWb[e / NW][e % NW] = sWa[e / NW][e % NW];
+          for (int e = tid; e < nb * NC; e += kSchurThreads) sCb[e / NC][e % NC] = sCa[e / NC][e % NC];
         } else {
-          for (int e = tid; e < nb * 10; e += kSchurThreads) {
-            const int b = e / 10, k = e % 10;
-            const ObsJac& ob = P.J[o0 + b0 + b];
+          for (int e = tid; e < nb * NC; e += kSchurThreads) {
+            const int b = e / NC, k = e % NC;
+            const J& ob = jac<J>(P)[o0 + b0 + b];
             const int i = P.obs_img[o0 + b0 + b];
-            sCb[b][k] = (k < 6) ? P.pose_col[6 * i + k] : P.intr_col[4 * P.img_cam[i] + (k - 6)];
+            sCb[b][k] = (k < 6) ? P.pose_col[6 * i + k] : P.intr_col[KI * P.img_cam[i] + (k - 6)];
 #pragma unroll
-            for (int l = 0; l < 3; ++l) sWb[b][3 * k + l] = ob.Jc[k] * ob.Jp[l] + ob.Jc[10 + k] * ob.Jp[3 + l];
+            for (int l = 0; l < 3; ++l) sWb[b][3 * k + l] = ob.Jc[k] * ob.Jp[l] + ob.Jc[NC + k] * ob.Jp[3 + l];
           }
         }
         __syncthreads();
-        if (tid < 100) {
-          const int k = tid / 10, l = tid - 10 * k;
+        // NC = 10: the first 100 threads own one entry each; NC = 18: 324 entries, up to three per thread
+        for (int ent = tid; ent < NC * NC; ent += kSchurThreads) {
+          const int k = ent / NC, l = ent - NC * k;
           for (int a = 0; a < na; ++a) {
             const int ca = sCa[a][k];
             if (ca < 0) continue;
@@ -498,7 +515,9 @@ __global__ void add_diag_kernel(BaDev P, double radius, double min_diag, double 
 
 // ----------------------------------------------------------- back-substitution
 // Warp per point: dp = -V^-1 (g_p + sum_a Jp_a^T (Jc_a dc)).
+template <class J>
 __global__ void __launch_bounds__(256) backsub_kernel(BaDev P) {
+  constexpr int KI = J::kKI, NC = J::kNC;
   const int lane = threadIdx.x & 31;
   const int64_t wid = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   if (wid >= P.n_pts) return;
@@ -508,15 +527,15 @@ __global__ void __launch_bounds__(256) backsub_kernel(BaDev P) {
   const int L = (int)(P.pt_start[p + 1] - o0);
   double s[3] = {0, 0, 0};
   for (int a = lane; a < L; a += 32) {
-    const ObsJac& e = P.J[o0 + a];
+    const J& e = jac<J>(P)[o0 + a];
     const int i = P.obs_img[o0 + a], cm = P.img_cam[i];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       double jd = 0;
 #pragma unroll
-      for (int k = 0; k < 6; ++k) { const int c = P.pose_col[6 * i + k]; if (c >= 0) jd += e.Jc[10 * r + k] * P.dc[c]; }
+      for (int k = 0; k < 6; ++k) { const int c = P.pose_col[6 * i + k]; if (c >= 0) jd += e.Jc[NC * r + k] * P.dc[c]; }
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { const int c = P.intr_col[4 * cm + k]; if (c >= 0) jd += e.Jc[10 * r + 6 + k] * P.dc[c]; }
+      for (int k = 0; k < KI; ++k) { const int c = P.intr_col[KI * cm + k]; if (c >= 0) jd += e.Jc[NC * r + 6 + k] * P.dc[c]; }
 #pragma unroll
       for (int k = 0; k < 3; ++k) s[k] += e.Jp[3 * r + k] * jd;
     }
@@ -530,19 +549,21 @@ __global__ void __launch_bounds__(256) backsub_kernel(BaDev P) {
 }
 
 // model_cost_change = -sum m (r + m/2), m = J delta (thread per observation)
+template <class J>
 __global__ void __launch_bounds__(256) model_cost_kernel(BaDev P, double* out) {
+  constexpr int KI = J::kKI, NC = J::kNC;
   const int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   double acc = 0;
   if (o < P.n_obs) {
-    const ObsJac& e = P.J[o];
+    const J& e = jac<J>(P)[o];
     const int i = P.obs_img[o], cm = P.img_cam[i], pc = P.pt_col[P.obs_pt[o]];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       double m = 0;
 #pragma unroll
-      for (int k = 0; k < 6; ++k) { const int c = P.pose_col[6 * i + k]; if (c >= 0) m += e.Jc[10 * r + k] * P.dc[c]; }
+      for (int k = 0; k < 6; ++k) { const int c = P.pose_col[6 * i + k]; if (c >= 0) m += e.Jc[NC * r + k] * P.dc[c]; }
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { const int c = P.intr_col[4 * cm + k]; if (c >= 0) m += e.Jc[10 * r + 6 + k] * P.dc[c]; }
+      for (int k = 0; k < KI; ++k) { const int c = P.intr_col[KI * cm + k]; if (c >= 0) m += e.Jc[NC * r + 6 + k] * P.dc[c]; }
       if (pc >= 0)
 #pragma unroll
         for (int k = 0; k < 3; ++k) m += e.Jp[3 * r + k] * P.dp[3 * (int64_t)pc + k];
@@ -561,6 +582,7 @@ __global__ void __launch_bounds__(256) model_cost_kernel(BaDev P, double* out) {
 }
 
 // candidate parameters x + scale * delta; accumulates |step|^2 and |x|^2 in out[0], out[1]
+template <int KI>
 __global__ void candidate_cameras_kernel(BaDev P, double* out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   double st = 0, xs = 0;
@@ -594,12 +616,12 @@ __global__ void candidate_cameras_kernel(BaDev P, double* out) {
     }
   }
   if (i < P.n_cam) {
-    for (int k = 0; k < 4; ++k) {
-      const int c = P.intr_col[4 * i + k];
+    for (int k = 0; k < KI; ++k) {
+      const int c = P.intr_col[KI * i + k];
       double v = 0;
       if (c >= 0) { v = P.dc[c] * P.scale_c[c]; st += v * v; }
-      P.cam_new[4 * i + k] = P.cam_params[4 * i + k] + v;
-      xs += P.cam_params[4 * i + k] * P.cam_params[4 * i + k];
+      P.cam_new[KI * i + k] = P.cam_params[KI * i + k] + v;
+      xs += P.cam_params[KI * i + k] * P.cam_params[KI * i + k];
     }
   }
   st = warp_sum(st);
@@ -642,23 +664,34 @@ static inline unsigned nblk(int64_t n, int b) { return (unsigned)((n + b - 1) / 
 cudaError_t ba_launch_jacobian(const BaDev& P, const double* q, const double* t, const double* k, const double* X,
                                int mode, double* cost_out, cudaStream_t s, int loss_type, double loss_scale) {
   if (P.n_obs == 0) return cudaSuccess;
+  if (P.wide) {  // problems with a camera model beyond the three 4-slot ones
+    if (loss_type == 1)
+      bak::jacobian_kernel<1, ObsJacW><<<nblk(P.n_obs, 128), 128, 0, s>>>(P, q, t, k, X, mode, cost_out, loss_scale);
+    else if (loss_type == 2)
+      bak::jacobian_kernel<2, ObsJacW><<<nblk(P.n_obs, 128), 128, 0, s>>>(P, q, t, k, X, mode, cost_out, loss_scale);
+    else
+      bak::jacobian_kernel<0, ObsJacW><<<nblk(P.n_obs, 128), 128, 0, s>>>(P, q, t, k, X, mode, cost_out, loss_scale);
+    return cudaGetLastError();
+  }
   if (loss_type == 1)
-    bak::jacobian_kernel<1><<<nblk(P.n_obs, 256), 256, 0, s>>>(P, q, t, k, X, mode, cost_out, loss_scale);
+    bak::jacobian_kernel<1, ObsJac><<<nblk(P.n_obs, 256), 256, 0, s>>>(P, q, t, k, X, mode, cost_out, loss_scale);
   else if (loss_type == 2)
-    bak::jacobian_kernel<2><<<nblk(P.n_obs, 256), 256, 0, s>>>(P, q, t, k, X, mode, cost_out, loss_scale);
+    bak::jacobian_kernel<2, ObsJac><<<nblk(P.n_obs, 256), 256, 0, s>>>(P, q, t, k, X, mode, cost_out, loss_scale);
   else
-    bak::jacobian_kernel<0><<<nblk(P.n_obs, 256), 256, 0, s>>>(P, q, t, k, X, mode, cost_out, loss_scale);
+    bak::jacobian_kernel<0, ObsJac><<<nblk(P.n_obs, 256), 256, 0, s>>>(P, q, t, k, X, mode, cost_out, loss_scale);
   return cudaGetLastError();
 }
 cudaError_t ba_launch_camera_terms(const BaDev& P, cudaStream_t s) {
   if (P.n_obs == 0) return cudaSuccess;
-  bak::camera_terms_kernel<<<nblk(P.n_obs, 256), 256, 0, s>>>(P);
+  if (P.wide) bak::camera_terms_kernel<ObsJacW><<<nblk(P.n_obs, 256), 256, 0, s>>>(P);
+  else bak::camera_terms_kernel<ObsJac><<<nblk(P.n_obs, 256), 256, 0, s>>>(P);
   return cudaGetLastError();
 }
 cudaError_t ba_launch_schur(const BaDev& P, double radius, double min_diag, double max_diag, int n_sm, cudaStream_t s) {
   if (P.n_pts == 0) return cudaSuccess;
   const int grid = (int)std::min<int64_t>(P.n_pts, (int64_t)n_sm * 8);
-  bak::schur_kernel<false><<<grid, bak::kSchurThreads, 0, s>>>(P, radius, min_diag, max_diag, nullptr, nullptr);
+  if (P.wide) bak::schur_kernel<false, ObsJacW><<<grid, bak::kSchurThreads, 0, s>>>(P, radius, min_diag, max_diag, nullptr, nullptr);
+  else bak::schur_kernel<false, ObsJac><<<grid, bak::kSchurThreads, 0, s>>>(P, radius, min_diag, max_diag, nullptr, nullptr);
   return cudaGetLastError();
 }
 // pair-major variant: structure once per solve ...
@@ -678,7 +711,7 @@ cudaError_t ba_launch_schur_pm(const BaDev& P, double radius, double min_diag, d
                                cudaStream_t s) {
   if (P.n_pts == 0) return cudaSuccess;
   const int grid = (int)std::min<int64_t>(P.n_pts, (int64_t)n_sm * 8);
-  bak::schur_kernel<true><<<grid, bak::kSchurThreads, 0, s>>>(P, radius, min_diag, max_diag, Wg, Yg);
+  bak::schur_kernel<true, ObsJac><<<grid, bak::kSchurThreads, 0, s>>>(P, radius, min_diag, max_diag, Wg, Yg);
   bak::pm_blocks_kernel<<<n_sm * 8, 256, 0, s>>>(P, n_img, start, (const int2*)tuples, Wg, Yg);
   return cudaGetLastError();
 }
@@ -689,18 +722,21 @@ cudaError_t ba_launch_add_diag(const BaDev& P, double radius, double min_diag, d
 }
 cudaError_t ba_launch_backsub(const BaDev& P, cudaStream_t s) {
   if (P.n_pts == 0) return cudaSuccess;
-  bak::backsub_kernel<<<nblk((int64_t)P.n_pts * 32, 256), 256, 0, s>>>(P);
+  if (P.wide) bak::backsub_kernel<ObsJacW><<<nblk((int64_t)P.n_pts * 32, 256), 256, 0, s>>>(P);
+  else bak::backsub_kernel<ObsJac><<<nblk((int64_t)P.n_pts * 32, 256), 256, 0, s>>>(P);
   return cudaGetLastError();
 }
 cudaError_t ba_launch_model_cost(const BaDev& P, double* out, cudaStream_t s) {
   if (P.n_obs == 0) return cudaSuccess;
-  bak::model_cost_kernel<<<nblk(P.n_obs, 256), 256, 0, s>>>(P, out);
+  if (P.wide) bak::model_cost_kernel<ObsJacW><<<nblk(P.n_obs, 256), 256, 0, s>>>(P, out);
+  else bak::model_cost_kernel<ObsJac><<<nblk(P.n_obs, 256), 256, 0, s>>>(P, out);
   return cudaGetLastError();
 }
 cudaError_t ba_launch_candidate(const BaDev& P, double* out, bool cameras, cudaStream_t s) {
   if (cameras) {
     const int n = std::max(P.n_img, P.n_cam);
-    if (n > 0) bak::candidate_cameras_kernel<<<nblk(n, 128), 128, 0, s>>>(P, out);
+    if (n > 0 && P.wide) bak::candidate_cameras_kernel<12><<<nblk(n, 128), 128, 0, s>>>(P, out);
+    else if (n > 0) bak::candidate_cameras_kernel<4><<<nblk(n, 128), 128, 0, s>>>(P, out);
   } else if (P.n_pts > 0) {
     bak::candidate_points_kernel<<<nblk(3 * (int64_t)P.n_pts, 256), 256, 0, s>>>(P, out);
   }

@@ -300,14 +300,17 @@ typedef struct b2_ba_problem {
   const int32_t* image_camera; /* [n_images] -> camera (intrinsics may be shared, .cc:349) */
   const uint8_t* const_pose;   /* [n_images] 1 = BundleAdjustmentConfig::SetConstantPose     */
   const uint8_t* const_tvec;   /* [n_images] bitmask of SetConstantTvec components           */
-  const int32_t* camera_model; /* [n_cameras] 0 SIMPLE_PINHOLE 1 PINHOLE 2 SIMPLE_RADIAL     */
-  double* camera_params;       /* [n_cameras][4] */
+  const int32_t* camera_model; /* [n_cameras] model ids of camera_models.h:117-129 (0 SIMPLE_PINHOLE ... 10
+                                  THIN_PRISM_FISHEYE, layouts as in b2_camera); 0 / 1 / 2 run the fast path */
+  double* camera_params;       /* [n_cameras][camera_params_stride] */
   const uint8_t* const_camera; /* [n_cameras] 1 = BundleAdjustmentConfig::SetConstantCamera  */
   double* xyz;                 /* [n_points][3] */
   const uint8_t* const_point;  /* [n_points] 1 = AddConstantPoint */
   const int32_t* obs_image;    /* [n_obs] */
   const int32_t* obs_point;    /* [n_obs] non-decreasing (sorted by point => CSR) */
   const double* obs_xy;        /* [n_obs][2] */
+  int32_t camera_params_stride;/* doubles per camera in camera_params; 0 = 4 (enough for models 0-2), up to 12 */
+  int32_t reserved;
 } b2_ba_problem;
 
 typedef struct b2_ba_options {   /* BundleAdjustmentOptions (bundle_adjustment.h:48-103) */

@@ -161,7 +161,7 @@ class ParallelBA {
       oimg[k] = cidx_[k]; opt[k] = pidx_[k];
       oxy[2 * k] = proj_[k].x; oxy[2 * k + 1] = proj_[k].y;
     }
-    b2_ba_problem p;
+    b2_ba_problem p = {};  // camera_params_stride = 0 means 4 doubles per camera
     p.n_images = nc; p.n_cameras = nc; p.n_points = np; p.n_obs = (int64_t)nproj_;
     p.qvec = q.data(); p.tvec = t.data(); p.image_camera = icam.data();
     p.const_pose = cpose.data(); p.const_tvec = ctvec.data();

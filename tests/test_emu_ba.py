@@ -365,3 +365,78 @@ def test_iterative_schur_degenerate_inputs(emu):
     assert (s.num_successful_steps, s.num_unsuccessful_steps) == (sc.num_successful_steps, sc.num_unsuccessful_steps)
     assert s.num_linear_solver_iterations == sc.num_linear_iterations
     assert s.final_cost == pytest.approx(sc.final_cost, rel=1e-8)
+
+
+# ---------------------------------------------------------------- general camera models (wide Jacobian layout)
+GENERAL_CAMERAS = [
+    (3, [1200.0, 500, 500, 0.05, -0.01]),                                              # RADIAL
+    (4, [1180.0, 1210.0, 505.0, 495.0, -0.12, 0.03, 0.001, -0.0015]),                  # OPENCV
+    (5, [1200.0, 1200.0, 500, 500, 0.02, -0.005, 0.001, 0.0]),                         # OPENCV_FISHEYE
+    (7, [1200.0, 1200.0, 500, 500, 0.3]),                                              # FOV
+    (8, [1200.0, 500, 500, 0.04]),                                                     # SIMPLE_RADIAL_FISHEYE
+    (9, [1200.0, 500, 500, 0.04, -0.01]),                                              # RADIAL_FISHEYE
+]
+
+
+@pytest.mark.parametrize("camera", GENERAL_CAMERAS)
+@pytest.mark.parametrize("solver", [1, 2])
+def test_general_camera_models_follow_the_oracle(emu, camera, solver):
+    """Problems with a camera model beyond SIMPLE_PINHOLE / PINHOLE / SIMPLE_RADIAL run on the wide Jacobian layout
+    (ObsJacW: 12 intrinsics slots, dual-number derivatives of WorldToImage) through both linear solvers: same LM path
+    and cost as the oracle with the final-BA options, same optimum when run to convergence."""
+    kw = dict(n_img=8, n_pts=120, track_len=5, seed=3, camera=camera, noise_px=0.5)
+    p_dev = make_ba_problem(**kw)
+    p_cpu = copy_problem(p_dev)
+    s_dev = emu_solve(emu, p_dev, linear_solver_type=solver, max_num_iterations=6)
+    s_cpu = orc.ba_solve(p_cpu, linear_solver=solver - 1, max_num_iterations=6)
+    assert (s_dev.num_residuals_reduced, s_dev.num_effective_parameters_reduced) == (s_cpu.num_residuals, s_cpu.num_effective_parameters)
+    assert s_dev.initial_cost == pytest.approx(s_cpu.initial_cost, rel=1e-12)
+    assert (s_dev.num_successful_steps, s_dev.num_unsuccessful_steps) == (s_cpu.num_successful_steps, s_cpu.num_unsuccessful_steps)
+    assert s_dev.final_cost == pytest.approx(s_cpu.final_cost, rel=1e-7)
+    if solver == 2:
+        assert abs(s_dev.num_linear_solver_iterations - s_cpu.num_linear_iterations) <= 2
+    n = len(camera[1])
+    if solver == 1:   # (the truncated inner solves of ITERATIVE_SCHUR leave the unobservable high-order coefficients free)
+        assert np.allclose(p_dev["cam_params"][:, :n], p_cpu["cam_params"][:, :n], rtol=1e-6, atol=1e-8)
+    assert (p_dev["cam_params"][:, n:] == 0).all()                      # unused slots stay untouched
+    p_dev = make_ba_problem(**kw)
+    start = reprojection_rms(p_dev)
+    emu_solve(emu, p_dev, linear_solver_type=solver, **TIGHT)
+    assert reprojection_rms(p_dev) < 0.36 < 4 < start
+
+
+def test_mixed_camera_models_and_shared_general_camera(emu):
+    """One problem with SIMPLE_RADIAL and OPENCV cameras side by side (everything moves to the wide layout), and a single
+    OPENCV camera shared by all images (an 8 x 8 preconditioner block fed by every observation)."""
+    cam = (4, [1180.0, 1210.0, 505.0, 495.0, -0.12, 0.03, 0.001, -0.0015])
+    p = make_ba_problem(n_img=8, n_pts=100, track_len=4, seed=5, camera=cam, noise_px=0.5)
+    # images 0..3 keep the OPENCV camera; 4..7 get a SIMPLE_RADIAL with the same (undistorted-ish) parameters and their
+    # observations re-projected accordingly
+    for c in range(4, 8):
+        p["cam_model"][c] = 2
+        p["cam_params"][c] = 0
+        p["cam_params"][c, :4] = [1195.0, 505.0, 495.0, 0.0]
+    for solver in (1, 2):
+        a, b = copy_problem(p), copy_problem(p)
+        s_dev = emu_solve(emu, a, linear_solver_type=solver, max_num_iterations=5)
+        s_cpu = orc.ba_solve(b, linear_solver=solver - 1, max_num_iterations=5)
+        assert s_dev.num_effective_parameters_reduced == s_cpu.num_effective_parameters == 3 * 100 + (6 * 8 - 7) + 4 * 6 + 4 * 2
+        assert (s_dev.num_successful_steps, s_dev.num_unsuccessful_steps) == (s_cpu.num_successful_steps, s_cpu.num_unsuccessful_steps)
+        assert s_dev.final_cost == pytest.approx(s_cpu.final_cost, rel=1e-7)
+    q = make_ba_problem(n_img=8, n_pts=100, track_len=4, seed=6, camera=cam, noise_px=0.5, shared_camera=True)
+    for solver in (1, 2):
+        a, b = copy_problem(q), copy_problem(q)
+        s_dev = emu_solve(emu, a, linear_solver_type=solver, max_num_iterations=5)
+        s_cpu = orc.ba_solve(b, linear_solver=solver - 1, max_num_iterations=5)
+        assert s_dev.num_effective_parameters_reduced == s_cpu.num_effective_parameters == 3 * 100 + (6 * 8 - 7) + 6
+        assert s_dev.final_cost == pytest.approx(s_cpu.final_cost, rel=1e-7)
+
+
+def test_camera_params_stride_is_checked(emu):
+    p = make_ba_problem(n_img=4, n_pts=20, track_len=3, seed=1)
+    p["cam_model"][:] = 4                      # OPENCV needs 8 parameters, the array has 4 per camera
+    with pytest.raises(RuntimeError):
+        emu_solve(emu, p)
+    p["cam_model"][:] = 11
+    with pytest.raises(RuntimeError):
+        emu_solve(emu, p)
