@@ -15,6 +15,10 @@ from tests.test_emu_ba import emu, emu_solve          # noqa: F401  (fixture)
 from tests.test_emu_match import mm                   # noqa: F401  (fixture)
 
 
+GENERAL = [(3, [1200.0, 500, 500, 0.05, -0.01]), (4, [1180.0, 1210.0, 505.0, 495.0, -0.12, 0.03, 0.001, -0.0015]),
+           (7, [1200.0, 1200.0, 500, 500, 0.3]), (9, [1200.0, 500, 500, 0.04, -0.01])]   # RADIAL, OPENCV, FOV, RADIAL_FISHEYE
+
+
 def test_matcher_random_cases(mm, monkeypatch):
     rng = np.random.default_rng(1)
     base = orc.create_random_descriptors(800, seed=5)
@@ -50,9 +54,10 @@ def test_bundle_adjuster_random_problems(emu, monkeypatch):
         n_img = int(rng.integers(3, 12))
         track = int(rng.integers(2, min(n_img, 6) + 1))
         n_pts = int(rng.integers(10, 80))
+        general = GENERAL[int(rng.integers(0, len(GENERAL)))] if rng.random() < 0.25 else None   # wide Jacobian layout
         p = make_ba_problem(n_img=n_img, n_pts=n_pts, track_len=track, seed=int(rng.integers(0, 10 ** 6)),
                             shared_camera=bool(rng.random() < 0.3), n_const_pts=int(rng.integers(0, n_pts // 3 + 1)),
-                            noise_px=float(rng.choice([0.5, 2.0])))
+                            noise_px=float(rng.choice([0.5, 2.0])), camera=general)
         for i in range(n_img):
             if rng.random() < 0.15:
                 p["pose_const"][i], p["tvec_const"][i] = 1, 0
@@ -61,7 +66,7 @@ def test_bundle_adjuster_random_problems(emu, monkeypatch):
         for c in range(len(p["cam_const"])):
             if rng.random() < 0.2:
                 p["cam_const"][c] = 1
-        if rng.random() < 0.3:
+        if general is None and rng.random() < 0.3:
             p["cam_model"][:] = int(rng.choice([0, 1]))           # SIMPLE_PINHOLE / PINHOLE
         refine = (int(rng.integers(0, 2)), int(rng.integers(0, 2)), int(rng.integers(0, 2)))
         loss, scale = int(rng.choice([0, 0, 1, 2])), float(rng.choice([0.5, 1.0, 3.0]))
@@ -94,9 +99,10 @@ def test_iterative_schur_random_problems(emu):
         track = int(rng.integers(3, min(n_img, 6) + 1))   # two-view tracks leave the inner system so ill-conditioned that a
         # 1e-15 relative change of the observations moves the ORACLE's cost by 1e-3 after three inexact steps
         n_pts = int(rng.integers(10, 80))
+        general = GENERAL[int(rng.integers(0, len(GENERAL)))] if rng.random() < 0.25 else None   # wide Jacobian layout
         p = make_ba_problem(n_img=n_img, n_pts=n_pts, track_len=track, seed=int(rng.integers(0, 10 ** 6)),
                             shared_camera=bool(rng.random() < 0.3), n_const_pts=int(rng.integers(0, n_pts // 3 + 1)),
-                            noise_px=float(rng.choice([0.5, 2.0])))
+                            noise_px=float(rng.choice([0.5, 2.0])), camera=general)
         for i in range(n_img):
             if rng.random() < 0.15:
                 p["pose_const"][i], p["tvec_const"][i] = 1, 0
@@ -105,7 +111,7 @@ def test_iterative_schur_random_problems(emu):
         for c in range(len(p["cam_const"])):
             if rng.random() < 0.2:
                 p["cam_const"][c] = 1
-        if rng.random() < 0.3:
+        if general is None and rng.random() < 0.3:
             p["cam_model"][:] = int(rng.choice([0, 1]))
         refine = (int(rng.integers(0, 2)), int(rng.integers(0, 2)), int(rng.integers(0, 2)))
         loss, scale = int(rng.choice([0, 0, 1, 2])), float(rng.choice([0.5, 1.0, 3.0]))
