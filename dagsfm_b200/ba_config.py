@@ -13,7 +13,8 @@ from __future__ import annotations
 
 import numpy as np
 
-MODEL_ID = {"SIMPLE_PINHOLE": 0, "PINHOLE": 1, "SIMPLE_RADIAL": 2}   # camera_models.h model ids
+MODEL_ID = {"SIMPLE_PINHOLE": 0, "PINHOLE": 1, "SIMPLE_RADIAL": 2, "RADIAL": 3, "OPENCV": 4, "OPENCV_FISHEYE": 5,
+            "FULL_OPENCV": 6, "FOV": 7, "SIMPLE_RADIAL_FISHEYE": 8, "RADIAL_FISHEYE": 9, "THIN_PRISM_FISHEYE": 10}   # camera_models.h
 
 
 class Reconstruction:
@@ -159,6 +160,7 @@ def pack_problem(recon: Reconstruction, config: BundleAdjustmentConfig, refine_e
     pt_idx = {p: k for k, p in enumerate(point_ids)}
     obs.sort(key=lambda o: pt_idx[o[0]])               # CSR by point (stable: keeps the order within a point)
     n_img, n_cam, n_pts = len(prob_images), len(used_cams), len(point_ids)
+    stride = max([4] + [len(recon.cameras[c]["params"]) for c in used_cams])    # b2_ba_problem::camera_params_stride
     prob = {
         "qvec": np.stack([recon.images[i]["qvec"] for i in prob_images]) if n_img else np.zeros((0, 4)),
         "tvec": np.stack([recon.images[i]["tvec"] for i in prob_images]) if n_img else np.zeros((0, 3)),
@@ -168,7 +170,7 @@ def pack_problem(recon: Reconstruction, config: BundleAdjustmentConfig, refine_e
                                 if (config.HasConstantTvec(i) and not const_pose[i]) else 0 for i in prob_images],
                                dtype=np.uint8),
         "cam_model": np.array([recon.cameras[c]["model"] for c in used_cams], dtype=np.int32),
-        "cam_params": np.stack([np.r_[recon.cameras[c]["params"], np.zeros(4)][:4] for c in used_cams]) if n_cam else np.zeros((0, 4)),
+        "cam_params": np.stack([np.r_[recon.cameras[c]["params"], np.zeros(stride)][:stride] for c in used_cams]) if n_cam else np.zeros((0, 4)),
         # ParameterizeCameras (.cc:474-512): constant if flagged -- cameras that never entered camera_ids_
         # have no residuals and stay untouched either way
         "cam_const": np.array([1 if (c in config_const_cameras or c not in camera_ids) else 0 for c in used_cams], dtype=np.uint8),
