@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=48, help="pairs in the CPU baseline sample")
     ap.add_argument("--verify-pairs", type=int, default=20000, help="pairs in the verification leg (0 = skip)")
     ap.add_argument("--ba", default="500,100000,10", help="BA leg: images,points,track (empty = skip)")
+    ap.add_argument("--verify-pose", action="store_true",
+                    help="verification leg: also time b2_verify_relative_pose (EstimateWithRelativePose) on the verified pairs")
     ap.add_argument("--ba-solver", default="auto", choices=["auto", "exact", "iterative"],
                     help="BA leg: linear solver (auto = the reference's rule: ITERATIVE_SCHUR above 1000 images)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -209,6 +211,20 @@ def bench_verify(a, local_rank, rank, world, cores, barrier):
         out["roofline"] = verify_work_rates(res, w["match_offsets"], kern)
     except Exception as e:   # a reporting extra must never cost the bench line
         out["roofline"] = {"error": repr(e)}
+    if getattr(a, "verify_pose", False):   # opt-in: the pose kernel has not been validated on a GPU yet
+        try:
+            v.relative_pose(w["pairs"], w["match_offsets"], res, inl)      # warm-up
+            barrier()
+            t1 = time.perf_counter()
+            poses = v.relative_pose(w["pairs"], w["match_offsets"], res, inl)
+            barrier()
+            dt = time.perf_counter() - t1
+            posed = int((np.abs(poses["qvec"]).sum(1) > 0).sum())
+            out["relative_pose"] = {"pairs_per_s_e2e": n * world / dt, "pairs_with_pose": posed * world,
+                                    "median_tri_angle_deg": float(np.degrees(np.median(poses["tri_angle"][poses["tri_angle"] > 0]))) if posed else 0.0,
+                                    "api": "b2_verify_relative_pose (host buffers)"}
+        except Exception as e:
+            out["relative_pose"] = {"error": repr(e)}
     if rank == 0 and not a.no_cpu:
         from oracle import pyoracle as orc
         import ctypes as C

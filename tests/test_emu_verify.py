@@ -322,3 +322,19 @@ def test_device_pointer_chain_verify_then_relative_pose(ver):
     ver.relative_pose_device(4, pairs.ctypes.data, offs.ctypes.data, res_d.ctypes.data, inl_d.ctypes.data, pose_d.ctypes.data)
     assert res_d.tobytes() == res_h.tobytes() and pose_d.tobytes() == pose_h.tobytes()
     assert (pose_d["config"] == [2, 2, 4, 2]).all() and (pose_d["n_points3D"] > 50).all()
+
+
+def test_bench_verification_leg_runs_on_the_emulated_library(ver):
+    """bench.py's verification leg, with the opt-in relative-pose timing, end to end on the emulated library."""
+    import sys
+    import types
+    argv, sys.argv = sys.argv, ["bench.py"]
+    try:
+        import bench
+    finally:
+        sys.argv = argv
+    a = types.SimpleNamespace(verify_pairs=6, no_cpu=True, verify_pose=True)
+    out = bench.bench_verify(a, 0, 0, 1, 1, lambda: None)
+    assert out["pairs"] == 6 and out["pairs_per_s_e2e"] > 0 and "error" not in out["roofline"]
+    assert "error" not in out["relative_pose"] and out["relative_pose"]["pairs_per_s_e2e"] > 0
+    assert 0 <= out["relative_pose"]["pairs_with_pose"] <= 6
