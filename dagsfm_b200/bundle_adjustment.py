@@ -68,6 +68,7 @@ def _L():
         L.b2_ba_destroy.argtypes = [vp]
         L.b2_ba_set_allreduce.argtypes = [vp, ALLREDUCE_FN, vp]
         L.b2_ba_solve.argtypes = [vp, P(BaProblem), P(BundleAdjustmentOptions), P(BaSummary)]
+        L.b2_ba_reprojection_errors.argtypes = [vp, P(BaProblem), vp, P(C.c_double)]
         _bound = True
     return L
 
@@ -105,8 +106,24 @@ class BundleAdjuster:
         self._cb = ALLREDUCE_FN(lambda ptr, n, op, user: fn(ptr, n, op)) if fn else ALLREDUCE_FN(0)
         check(_L().b2_ba_set_allreduce(self._h, self._cb, None))
 
+    def ComputeMeanReprojectionError(self, prob: dict):
+        """Reconstruction::ComputeMeanReprojectionError over the problem's tracks -> (mean error in px, per-point errors
+        as Point3D::SetError receives them)."""
+        p = self._pack(prob)
+        err = np.zeros(max(p.n_points, 1))
+        mean = C.c_double(0)
+        check(_L().b2_ba_reprojection_errors(self._h, C.byref(p), err.ctypes.data, C.byref(mean)))
+        return mean.value, err[: p.n_points]
+
     def Solve(self, prob: dict) -> BaSummary:
         """prob: dict with the arrays of tests/ba_scene.make_ba_problem (updated in place)."""
+        p = self._pack(prob)
+        s = BaSummary()
+        check(_L().b2_ba_solve(self._h, C.byref(p), C.byref(self.options), C.byref(s)))
+        self.summary = s
+        return s
+
+    def _pack(self, prob: dict) -> BaProblem:
         for k, dt in _KEYS:
             a = prob[k]
             assert a.dtype == dt and a.flags["C_CONTIGUOUS"], k
@@ -123,7 +140,4 @@ class BundleAdjuster:
                                               prob["obs_xy"].ctypes.data)
         assert prob["cam_params"].ndim == 2 and 4 <= prob["cam_params"].shape[1] <= 12
         p.camera_params_stride = prob["cam_params"].shape[1]     # 4, or up to 12 for the wider camera models
-        s = BaSummary()
-        check(_L().b2_ba_solve(self._h, C.byref(p), C.byref(self.options), C.byref(s)))
-        self.summary = s
-        return s
+        return p

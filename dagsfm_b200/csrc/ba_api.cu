@@ -654,6 +654,64 @@ int b2_ba_set_allreduce(b2_ba* h, b2_allreduce_fn fn, void* user) {
   return B2_OK;
 }
 
+int b2_ba_reprojection_errors(b2_ba* h, const b2_ba_problem* pr, double* point_errors, double* mean_reprojection_error) {
+  if (!h || !pr || !mean_reprojection_error) return set_error(B2_ERR_INVALID, "NULL argument");
+  if (pr->n_images < 0 || pr->n_cameras < 0 || pr->n_points < 0 || pr->n_obs < 0) return set_error(B2_ERR_INVALID, "negative size");
+  const int n_img = pr->n_images, n_cam = pr->n_cameras, n_pts = pr->n_points;
+  const int64_t n_obs = pr->n_obs;
+  const int cs = pr->camera_params_stride > 0 ? pr->camera_params_stride : 4;
+  for (int64_t o = 0; o < n_obs; ++o) {
+    if (pr->obs_image[o] < 0 || pr->obs_image[o] >= n_img || pr->obs_point[o] < 0 || pr->obs_point[o] >= n_pts)
+      return set_error(B2_ERR_INVALID, "observation index out of range");
+    if (o > 0 && pr->obs_point[o] < pr->obs_point[o - 1]) return set_error(B2_ERR_INVALID, "observations must be sorted by point");
+  }
+  for (int i = 0; i < n_img; ++i)
+    if (pr->image_camera[i] < 0 || pr->image_camera[i] >= n_cam) return set_error(B2_ERR_INVALID, "bad image_camera");
+  for (int c = 0; c < n_cam; ++c)
+    if (pr->camera_model[c] < 0 || pr->camera_model[c] > 10 || num_params(pr->camera_model[c]) > cs)
+      return set_error(B2_ERR_INVALID, "unknown camera model id or camera_params_stride too small");
+  *mean_reprojection_error = 0.0;
+  if (n_pts == 0 || n_obs == 0) return B2_OK;  // the reference divides 0 / 0 here; callers only log the value
+  B2_CUDA(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  std::vector<int64_t> pt_start(n_pts + 1, 0);
+  for (int64_t o = 0; o < n_obs; ++o) pt_start[pr->obs_point[o] + 1]++;
+  for (int p = 0; p < n_pts; ++p) pt_start[p + 1] += pt_start[p];
+  auto run = [&]() -> int {
+    int32_t *d_obs_img, *d_img_cam, *d_cam_model;
+    int64_t* d_pt_start;
+    double *d_obs_xy, *d_cam, *d_q, *d_t, *d_xyz, *d_err, *d_partial;
+    const int n_blocks_max = (int)(((int64_t)n_pts * 32 + 255) / 256);
+    B2_TRY(dev_upload(h, &d_obs_img, pr->obs_image, (size_t)n_obs));
+    B2_TRY(dev_upload(h, &d_obs_xy, pr->obs_xy, (size_t)n_obs * 2));
+    B2_TRY(dev_upload(h, &d_pt_start, pt_start.data(), pt_start.size()));
+    B2_TRY(dev_upload(h, &d_img_cam, pr->image_camera, (size_t)n_img));
+    B2_TRY(dev_upload(h, &d_cam_model, pr->camera_model, (size_t)n_cam));
+    B2_TRY(dev_upload(h, &d_cam, (const double*)pr->camera_params, (size_t)n_cam * cs));
+    B2_TRY(dev_upload(h, &d_q, (const double*)pr->qvec, (size_t)n_img * 4));
+    B2_TRY(dev_upload(h, &d_t, (const double*)pr->tvec, (size_t)n_img * 3));
+    B2_TRY(dev_upload(h, &d_xyz, (const double*)pr->xyz, (size_t)n_pts * 3));
+    B2_TRY(dev_alloc(h, &d_err, (size_t)n_pts));
+    B2_TRY(dev_alloc(h, &d_partial, (size_t)n_blocks_max));
+    int n_blocks = 0;
+    B2_CUDA(bam_launch_reprojection_errors(n_pts, d_pt_start, d_obs_img, d_obs_xy, d_img_cam, d_cam_model, d_cam, cs, d_q, d_t,
+                                           d_xyz, d_err, d_partial, &n_blocks, s));
+    count_launches(1);
+    std::vector<double> partial((size_t)n_blocks);
+    B2_CUDA(cudaMemcpyAsync(partial.data(), d_partial, (size_t)n_blocks * 8, cudaMemcpyDeviceToHost, s));
+    if (point_errors) B2_CUDA(cudaMemcpyAsync(point_errors, d_err, (size_t)n_pts * 8, cudaMemcpyDeviceToHost, s));
+    B2_CUDA(cudaStreamSynchronize(s));
+    double sum = 0;
+    for (double v : partial) sum += v;
+    *mean_reprojection_error = sum / (double)n_obs;  // total_reprojected_points = sum of track lengths
+    return B2_OK;
+  };
+  const int rc = run();
+  cudaStreamSynchronize(s);
+  free_all(h);
+  return rc;
+}
+
 int b2_ba_solve(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_ba_summary* sum) {
   if (!h || !pr || !opt || !sum) return set_error(B2_ERR_INVALID, "NULL argument");
   if (opt->loss_function_type < 0 || opt->loss_function_type > 2 || !(opt->loss_function_scale > 0))

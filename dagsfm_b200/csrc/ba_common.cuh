@@ -79,6 +79,12 @@ cudaError_t ba_launch_candidate(const BaDev& P, double* out, bool cameras, cudaS
 cudaError_t ba_launch_make_scale(const double* colnorm, double* scale, int64_t n, cudaStream_t s);
 cudaError_t ba_launch_negate(double* v, int64_t n, cudaStream_t s);
 
+// ---- result metrics (ba_metrics.cu)
+cudaError_t bam_launch_reprojection_errors(int n_pts, const int64_t* pt_start, const int32_t* obs_img, const double* obs_xy,
+                                           const int32_t* img_cam, const int32_t* cam_model, const double* cam_params,
+                                           int cam_stride, const double* qvec, const double* tvec, const double* xyz,
+                                           double* point_error, double* partial_sum, int* n_blocks, cudaStream_t s);
+
 // ---- ITERATIVE_SCHUR (ba_iterative.cu): state of the conjugate-gradient solve of the reduced system
 constexpr int kBaIterMaxPartials = 128;  // blocks of the vector kernels = partial sums per dot product
 struct BaIter {

@@ -361,6 +361,15 @@ int b2_ba_set_allreduce(b2_ba* h, b2_allreduce_fn fn, void* user);
 int b2_ba_solve(b2_ba* h, const b2_ba_problem* problem, const b2_ba_options* opt,
                 b2_ba_summary* summary);
 
+/* Result metrics the reference reports after a bundle adjustment:
+ * Reconstruction::ComputeMeanReprojectionError (src/base/reconstruction.cc:814-858) with
+ * CalculateSquaredReprojectionError (src/base/projection.cc:119-136) over the problem's tracks (its CSR rows):
+ * per observation |WorldToImage(R(q) X + t) - xy| unless the point is not in front of the camera (skipped);
+ * point_errors[p] (may be NULL) = the track's error sum / track length, the value the reference stores with
+ * Point3D::SetError; *mean_reprojection_error = total error sum / total track length.  HOST arrays, nothing is modified. */
+int b2_ba_reprojection_errors(b2_ba* h, const b2_ba_problem* problem, double* point_errors,
+                              double* mean_reprojection_error);
+
 #ifdef __cplusplus
 }
 #endif

@@ -980,6 +980,45 @@ static void Solve(Problem P, Options O, Summary* S) {
   S->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
 }
 
+// B8: Reconstruction::ComputeMeanReprojectionError (base/reconstruction.cc:814-858) with
+// CalculateSquaredReprojectionError (base/projection.cc:119-136) and QuaternionRotatePoint (base/pose.cc:110-116:
+// Eigen::Quaterniond * Vector3d on the normalised qvec) over the tracks of the problem (its CSR rows), points in
+// ascending id order as the sequential sums of the reference run.
+static double MeanReprojectionError(const Problem& P, double* point_errors) {
+  std::vector<long> pt_start(P.n_pts + 1, 0);
+  for (long o = 0; o < P.n_obs; ++o) pt_start[P.obs_pt[o] + 1]++;
+  for (int p = 0; p < P.n_pts; ++p) pt_start[p + 1] += pt_start[p];
+  long total_reprojected_points = 0;
+  double mean_reproj_error = 0.0;
+  for (int p = 0; p < P.n_pts; ++p) {
+    double reproj_error_sum = 0.0;
+    const double* X = P.xyz + 3 * p;
+    for (long o = pt_start[p]; o < pt_start[p + 1]; ++o) {
+      const int i = P.obs_img[o], c = P.img_cam[i];
+      double q[4] = {P.qvec[4 * i], P.qvec[4 * i + 1], P.qvec[4 * i + 2], P.qvec[4 * i + 3]};
+      const double n = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+      if (n == 0) q[0] = 1.0;  // NormalizeQuaternion
+      else for (double& v : q) v /= n;
+      // Eigen's QuaternionBase::_transformVector: uv = 2 * vec x v; v + w * uv + vec x uv
+      const double uv[3] = {2.0 * (q[2] * X[2] - q[3] * X[1]), 2.0 * (q[3] * X[0] - q[1] * X[2]), 2.0 * (q[1] * X[1] - q[2] * X[0])};
+      const double pw[3] = {X[0] + q[0] * uv[0] + (q[2] * uv[2] - q[3] * uv[1]) + P.tvec[3 * i],
+                            X[1] + q[0] * uv[1] + (q[3] * uv[0] - q[1] * uv[2]) + P.tvec[3 * i + 1],
+                            X[2] + q[0] * uv[2] + (q[1] * uv[1] - q[2] * uv[0]) + P.tvec[3 * i + 2]};
+      if (pw[2] < std::numeric_limits<double>::epsilon()) continue;  // squared error = max(): skipped
+      double x, y;
+      const double u = pw[0] / pw[2], v = pw[1] / pw[2];
+      WorldToImageT<double>(P.cam_model[c], P.cam_params + (long)P.cam_stride * c, u, v, &x, &y);
+      const double dx = x - P.obs_xy[2 * o], dy = y - P.obs_xy[2 * o + 1];
+      reproj_error_sum += std::sqrt(dx * dx + dy * dy);
+    }
+    const long L = pt_start[p + 1] - pt_start[p];
+    if (point_errors) point_errors[p] = L > 0 ? reproj_error_sum / L : 0.0;
+    total_reprojected_points += L;
+    mean_reproj_error += reproj_error_sum;
+  }
+  return total_reprojected_points ? mean_reproj_error / static_cast<double>(total_reprojected_points) : 0.0;
+}
+
 }  // namespace ba
 
 extern "C" {
@@ -1016,6 +1055,15 @@ void orc_ba_solve(const orc_ba_problem* p, const orc_ba_options* o, orc_ba_summa
   s->termination = S.termination; s->num_residuals = S.num_residuals; s->num_effective_parameters = S.num_effective_parameters;
   s->seconds = S.seconds;
   s->num_linear_iterations = S.num_linear_iterations;
+}
+
+double orc_ba_mean_reprojection_error(const orc_ba_problem* p, double* point_errors) {
+  ba::Problem P;
+  P.n_img = p->n_img; P.n_cam = p->n_cam; P.n_pts = p->n_pts; P.n_obs = (long)p->n_obs;
+  P.qvec = p->qvec; P.tvec = p->tvec; P.img_cam = p->img_cam; P.cam_model = p->cam_model; P.cam_params = p->cam_params;
+  P.xyz = p->xyz; P.obs_img = p->obs_img; P.obs_pt = p->obs_pt; P.obs_xy = p->obs_xy;
+  P.cam_stride = p->cam_stride > 0 ? p->cam_stride : 4;
+  return ba::MeanReprojectionError(P, point_errors);
 }
 
 // residual + local Jacobians of one observation (tests: cost_functions_test.cc goldens, finite differences)

@@ -435,6 +435,23 @@ def ba_solve(prob: dict, max_num_iterations=50, function_tolerance=0.0, gradient
     return s
 
 
+def ba_mean_reprojection_error(prob: dict):
+    """Reconstruction::ComputeMeanReprojectionError over the problem's tracks -> (mean error, per-point errors)."""
+    L = lib()
+    L.orc_ba_mean_reprojection_error.argtypes = [C.POINTER(OrcBaProblem), C.c_void_p]
+    L.orc_ba_mean_reprojection_error.restype = C.c_double
+    p = OrcBaProblem()
+    p.n_img, p.n_cam, p.n_pts, p.n_obs = len(prob["qvec"]), len(prob["cam_params"]), len(prob["xyz"]), len(prob["obs_img"])
+    for k in ("qvec", "tvec", "img_cam", "pose_const", "tvec_const", "cam_model", "cam_params", "cam_const", "xyz",
+              "pt_const", "obs_img", "obs_pt", "obs_xy"):
+        assert prob[k].flags["C_CONTIGUOUS"]
+        setattr(p, k, prob[k].ctypes.data)
+    p.cam_stride = prob["cam_params"].shape[1]
+    err = np.zeros(max(p.n_pts, 1))
+    mean = L.orc_ba_mean_reprojection_error(C.byref(p), err.ctypes.data)
+    return mean, err[: p.n_pts]
+
+
 def ba_evaluate(model, q, t, X, k, obs):
     L = lib()
     L.orc_ba_evaluate.argtypes = [C.c_int] + [C.c_void_p] * 10

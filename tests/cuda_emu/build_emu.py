@@ -17,6 +17,11 @@ CSRC = ROOT / "dagsfm_b200" / "csrc"
 OUT = HERE / "_build"
 
 
+# the translation units of each emulated library (the product's own sources)
+BA_SOURCES = ["common.cu", "match_post.cu", "ba_kernels.cu", "ba_iterative.cu", "ba_metrics.cu", "ba_api.cu"]
+VERIFY_SOURCES = ["common.cu", "verify_kernel.cu", "verify_pose.cu", "verify_api.cu"]
+
+
 def _matching(s: str, i: int, open_c: str, close_c: str) -> int:
     depth = 0
     for k in range(i, len(s)):

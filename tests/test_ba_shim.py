@@ -30,8 +30,8 @@ def test_config_container_and_num_residuals_replayed():
 
 
 def test_reference_structure_tests_through_the_adaptor_on_the_emulated_library():
-    from tests.cuda_emu.build_emu import build
-    lib = build("ba", ["common.cu", "match_post.cu", "ba_kernels.cu", "ba_iterative.cu", "ba_api.cu"])
+    from tests.cuda_emu.build_emu import BA_SOURCES, VERIFY_SOURCES, build
+    lib = build("ba", BA_SOURCES)
     exe = _build(lib, ROOT / "tests" / "cuda_emu" / "_build" / "ba_shim_test_emu")
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=1800)
     assert r.returncode == 0 and "ba shim ok" in r.stdout, r.stdout + r.stderr

@@ -60,9 +60,9 @@ def test_host_compiled_models_round_trip_and_equal_the_oracle(host, model, param
 
 @pytest.fixture(scope="module")
 def ver():
-    from tests.cuda_emu.build_emu import build
+    from tests.cuda_emu.build_emu import BA_SOURCES, VERIFY_SOURCES, build
     import dagsfm_b200.verification as vm
-    L = C.CDLL(str(build("verify", ["common.cu", "verify_kernel.cu", "verify_pose.cu", "verify_api.cu"])))
+    L = C.CDLL(str(build("verify", VERIFY_SOURCES)))
     L.b2_last_error.restype = C.c_char_p
     saved = (vm.lib, vm.check)
     vm._bound = False

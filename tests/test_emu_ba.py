@@ -15,9 +15,9 @@ from tests.ba_scene import copy_problem, make_ba_problem, reprojection_rms
 
 @pytest.fixture(scope="module")
 def emu(request):
-    from tests.cuda_emu.build_emu import build
+    from tests.cuda_emu.build_emu import BA_SOURCES, VERIFY_SOURCES, build
     import dagsfm_b200.bundle_adjustment as ba
-    L = C.CDLL(str(build("ba", ["common.cu", "match_post.cu", "ba_kernels.cu", "ba_iterative.cu", "ba_api.cu"])))
+    L = C.CDLL(str(build("ba", BA_SOURCES)))
     vp, P = C.c_void_p, C.POINTER
     L.b2_ba_default_options.argtypes = [P(ba.BundleAdjustmentOptions)]
     L.b2_ba_default_options.restype = None
@@ -441,3 +441,32 @@ def test_camera_params_stride_is_checked(emu):
     p["cam_model"][:] = 11
     with pytest.raises(RuntimeError):
         emu_solve(emu, p)
+
+
+def test_mean_reprojection_error_metric(emu):
+    """SURVEY row B8: b2_ba_reprojection_errors (Reconstruction::ComputeMeanReprojectionError + Point3D errors) on the
+    emulated kernel against the oracle's restatement and an independent numpy evaluation; points behind a camera are
+    skipped but still count in the denominators, as in the reference."""
+    from tests.ba_scene import mean_reprojection_error
+    L = emu._L()
+    L.b2_ba_reprojection_errors.argtypes = [C.c_void_p, C.POINTER(emu.BaProblem), C.c_void_p, C.POINTER(C.c_double)]
+    adj = emu.BundleAdjuster(emu.BundleAdjustmentOptions())
+    try:
+        for cam in (None, (4, [1180.0, 1210.0, 505.0, 495.0, -0.12, 0.03, 0.001, -0.0015]), (8, [1200.0, 500, 500, 0.04])):
+            p = make_ba_problem(n_img=9, n_pts=150, track_len=5, seed=12, camera=cam)
+            p["qvec"][3] *= 1.7                        # the metric normalises quaternions itself
+            mean, err = adj.ComputeMeanReprojectionError(p)
+            omean, oerr = orc.ba_mean_reprojection_error(p)
+            assert mean == pytest.approx(omean, rel=1e-13) and np.allclose(err, oerr, rtol=1e-13, atol=1e-15)
+            p["qvec"][3] /= 1.7
+            assert mean == pytest.approx(mean_reprojection_error(p), rel=1e-10)
+            assert err.shape == (150,) and (err > 0).all()
+        p = make_ba_problem(n_img=6, n_pts=40, track_len=4, seed=2)
+        p["xyz"][5] = [0, 0, -50.0]                    # far behind every camera on the ring? not all: use the oracle as reference
+        mean, err = adj.ComputeMeanReprojectionError(p)
+        omean, oerr = orc.ba_mean_reprojection_error(p)
+        assert mean == pytest.approx(omean, rel=1e-13) and np.allclose(err, oerr, rtol=1e-13, atol=1e-15)
+        p["obs_img"] = p["obs_img"][:0].copy(); p["obs_pt"] = p["obs_pt"][:0].copy(); p["obs_xy"] = p["obs_xy"][:0].copy()
+        assert adj.ComputeMeanReprojectionError(p)[0] == 0.0
+    finally:
+        adj.close()

@@ -78,8 +78,8 @@ def _worker(rank, world, port, lib_path, solver, out_dir):
 
 @pytest.fixture(scope="module")
 def emu_lib():
-    from tests.cuda_emu.build_emu import build
-    return build("ba", ["common.cu", "match_post.cu", "ba_kernels.cu", "ba_iterative.cu", "ba_api.cu"])
+    from tests.cuda_emu.build_emu import BA_SOURCES, VERIFY_SOURCES, build
+    return build("ba", BA_SOURCES)
 
 
 @pytest.mark.parametrize("solver", [1, 2])

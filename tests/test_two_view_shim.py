@@ -33,8 +33,8 @@ def test_reference_default_and_invert_tests_replayed_on_the_adaptor():
 
 
 def test_estimate_through_the_adaptor_on_the_emulated_library():
-    from tests.cuda_emu.build_emu import build
-    lib = build("verify", ["common.cu", "verify_kernel.cu", "verify_pose.cu", "verify_api.cu"])
+    from tests.cuda_emu.build_emu import BA_SOURCES, VERIFY_SOURCES, build
+    lib = build("verify", VERIFY_SOURCES)
     exe = _build(lib, ROOT / "tests" / "cuda_emu" / "_build" / "two_view_shim_test_emu")
     r = subprocess.run([str(exe), "estimate"], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout + r.stderr

@@ -374,3 +374,19 @@ def test_ba_general_camera_models_match_oracle_on_gpu(camera, solver):
     assert (s_gpu.num_successful_steps, s_gpu.num_unsuccessful_steps) == (s_cpu.num_successful_steps, s_cpu.num_unsuccessful_steps)
     assert s_gpu.final_cost == pytest.approx(s_cpu.final_cost, rel=1e-6)
     assert abs(reprojection_rms(p_gpu) - reprojection_rms(p_cpu)) < 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="first GPU execution of reprojection_error_kernel (verified on the CUDA emulator)")
+def test_mean_reprojection_error_matches_oracle_on_gpu():
+    from dagsfm_b200 import BundleAdjuster, BundleAdjustmentOptions
+    from tests.ba_scene import make_ba_problem
+    ba = BundleAdjuster(BundleAdjustmentOptions.default())
+    try:
+        for cam in (None, (4, [1180.0, 1210.0, 505.0, 495.0, -0.12, 0.03, 0.001, -0.0015])):
+            p = make_ba_problem(n_img=20, n_pts=3000, track_len=6, seed=12, camera=cam)
+            mean, err = ba.ComputeMeanReprojectionError(p)
+            omean, oerr = orc.ba_mean_reprojection_error(p)
+            assert mean == pytest.approx(omean, rel=1e-12) and np.allclose(err, oerr, rtol=1e-11, atol=1e-13)
+    finally:
+        ba.close()
