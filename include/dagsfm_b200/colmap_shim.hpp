@@ -13,9 +13,12 @@
 // `#include "SiftGPU/SiftGPU.h"` and link libdagsfm_b200.so -- see INTEGRATION.md.
 #pragma once
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../dagsfm_b200.h"
@@ -51,6 +54,7 @@ class SiftMatchGPU {
   SiftMatchGPU(const SiftMatchGPU&) = delete;
   SiftMatchGPU& operator=(SiftMatchGPU&& o) noexcept {
     std::swap(h_, o.h_); std::swap(max_sift_, o.max_sift_); std::swap(device_, o.device_); gpu_index = o.gpu_index;
+    for (int k = 0; k < 2; ++k) { guided_desc[k].swap(o.guided_desc[k]); guided_xy[k].swap(o.guided_xy[k]); }
     return *this;
   }
   ~SiftMatchGPU() { if (h_) b2_match_destroy(h_); }
@@ -73,7 +77,12 @@ class SiftMatchGPU {
     // the C ABI reads a NULL pointer as "keep the previous upload"; an explicitly empty set
     // (Eigen's data() of a 0-row matrix may be NULL) must still replace it
     static const unsigned char kEmpty = 0;
-    b2_match_set_descriptors(h_, index, std::min(num, max_sift_), descriptors ? descriptors : &kEmpty);
+    const int n = std::max(0, std::min(num, max_sift_));
+    b2_match_set_descriptors(h_, index, n, descriptors ? descriptors : &kEmpty);
+    if (descriptors || n == 0) {  // host copy for GetGuidedSiftMatch, whose filter needs both images in one call
+      guided_desc[index].assign(descriptors ? descriptors : &kEmpty, (descriptors ? descriptors : &kEmpty) + (size_t)n * 128);
+      guided_xy[index].clear();
+    }
   }
   // returns the number of matches, -1 on a device error (SiftMatchCU.cpp:193-196)
   int GetSiftMatch(int max_match, uint32_t match_buffer[][2], float distmax = 0.7f, float ratiomax = 0.8f,
@@ -86,10 +95,71 @@ class SiftMatchGPU {
     return n;
   }
 
-  // Guided matching keeps host copies of the two slots: a NULL descriptor / keypoint pointer of
-  // MatchGuidedSiftFeaturesGPU means "same image as the previous call" (sift.cc:1009-1035).
+  int CreateContextGL() { return VerifyContextGL(); }
+  // "-cuda [device_id]" (SiftGPU.h:308-312); other switches are OpenGL-only and ignored
+  void SetDeviceParam(int argc, char** argv) {
+    for (int i = 0; i + 1 < argc; ++i)
+      if (std::string(argv[i]) == "-cuda") device_ = std::max(0, std::atoi(argv[i + 1]));
+  }
+
+  // Guided matching (SiftGPU.h:339-362): per image SetDescriptors, then SetFeautreLocation [sic]; then
+  // GetGuidedSiftMatch.  `locations` is a vector of [float x, float y, float skip[gap]]; colmap passes its
+  // FeatureKeypoint array with gap = 4 (sift.cc:1016-1018).  The two slots are kept on the host: the C ABI takes
+  // the images of a guided call together.
+  void SetFeautreLocation(int index, const float* locations, int gap = 0) {
+    if (index < 0 || index > 1) return;
+    const size_t n = guided_desc[index].size() / 128;
+    guided_xy[index].resize(2 * n);
+    for (size_t i = 0; i < n; ++i) {
+      guided_xy[index][2 * i] = locations[i * (size_t)(2 + gap)];
+      guided_xy[index][2 * i + 1] = locations[i * (size_t)(2 + gap) + 1];
+    }
+  }
+  struct SiftKeypoint { float x, y, s, o; };  // SiftGPU::SiftKeypoint (SiftGPU.h:112-115)
+  void SetFeatureLocation(int index, const SiftKeypoint* keys) { SetFeautreLocation(index, reinterpret_cast<const float*>(keys), 2); }
+
+  // H / F: row-major float[9] or NULL (exactly one of them, as colmap calls it; both NULL = plain GetSiftMatch).
+  // hdistmax / fdistmax are SQUARED pixel thresholds (colmap passes max_error^2 for both, sift.cc:1058-1062).
+  // Returns the number of matches, -1 on a device error.
+  int GetGuidedSiftMatch(int max_match, uint32_t match_buffer[][2], float* H, float* F, float distmax = 0.7f,
+                         float ratiomax = 0.8f, float hdistmax = 32, float fdistmax = 16, int mutual_best_match = 1) {
+    if (!h_) return -1;
+    if (!H && !F) return GetSiftMatch(max_match, match_buffer, distmax, ratiomax, mutual_best_match);
+    if (H && F) {
+      std::fprintf(stderr, "ERROR: GetGuidedSiftMatch with both H and F is not supported (colmap passes one)\n");
+      return -1;
+    }
+    b2_guided_geometry g;
+    g.config = H ? 4 /* PLANAR */ : 3 /* UNCALIBRATED */;
+    g.reserved = 0;
+    for (int i = 0; i < 9; ++i) { g.F[i] = F ? (double)F[i] : 0.0; g.H[i] = H ? (double)H[i] : 0.0; }
+    static const unsigned char kEmptyDesc = 0;
+    static const float kEmptyXy = 0;
+    const unsigned char* dp[2];
+    const float* kp[2];
+    int32_t cnt[2];
+    for (int k = 0; k < 2; ++k) {
+      cnt[k] = (int32_t)(guided_desc[k].size() / 128);
+      if (guided_xy[k].size() != 2 * (size_t)cnt[k]) return -1;  // SetFeautreLocation missing for this slot
+      dp[k] = cnt[k] ? guided_desc[k].data() : &kEmptyDesc;
+      kp[k] = cnt[k] ? guided_xy[k].data() : &kEmptyXy;
+    }
+    b2_match_options o;
+    o.max_ratio = ratiomax; o.max_distance = distmax; o.cross_check = mutual_best_match; o.max_num_matches = max_match;
+    const uint32_t pair[2] = {0, 1};
+    int64_t offsets[2] = {0, 0}, total = 0;
+    const double max_error = std::sqrt((double)(H ? hdistmax : fdistmax));
+    std::vector<uint32_t> buf(2 * (size_t)std::max(cnt[0], 1));
+    if (b2_match_set_images(h_, 2, dp, cnt) != B2_OK || b2_match_set_keypoints(h_, 2, kp, cnt) != B2_OK ||
+        b2_match_guided_pairs(h_, 1, pair, &g, max_error, &o, offsets, buf.data(), (int64_t)std::max(cnt[0], 1), &total) != B2_OK)
+      return -1;
+    const int n = (int)std::min<int64_t>(total, max_match);
+    for (int i = 0; i < n; ++i) { match_buffer[i][0] = buf[2 * i]; match_buffer[i][1] = buf[2 * i + 1]; }
+    return n;
+  }
+
   b2_matcher* handle() const { return h_; }
-  std::vector<unsigned char> guided_desc[2];
+  std::vector<unsigned char> guided_desc[2];  // host copies of the two slots (guided matching)
   std::vector<float> guided_xy[2];
 
  private:
@@ -145,69 +215,58 @@ void MatchSiftFeaturesGPU(const SiftMatchingOptions& match_options, const Descri
   }
 }
 
-// sift.cc:987-1066.  Keypoints: any container of structs with float members x, y (FeatureKeypoint);
-// Geometry: any struct with `config`, `F`, `H` (3x3, indexable as M(r, c)) and `inlier_matches`
-// (TwoViewGeometry, two_view_geometry.h:43-113).  Configurations without a guided filter leave
-// inlier_matches untouched, as the reference does (:1049-1051).
+// sift.cc:987-1079.  Keypoints: a contiguous container (data(), size()) of FeatureKeypoint-like structs whose first two
+// floats are x, y, sizeof a multiple of 4 (colmap: 6 floats, passed with gap = 4); Geometry: any struct with `config`,
+// `F`, `H` (3x3, indexable as M(r, c)) and `inlier_matches` (TwoViewGeometry, two_view_geometry.h:43-113).
+// Configurations without a guided filter leave inlier_matches untouched, as the reference does (:1049-1051).
 template <class Keypoints, class Descriptors, class Geometry>
 void MatchGuidedSiftFeaturesGPU(const SiftMatchingOptions& match_options, const Keypoints* keypoints1,
                                 const Keypoints* keypoints2, const Descriptors* descriptors1,
                                 const Descriptors* descriptors2, SiftMatchGPU* sift_match_gpu,
                                 Geometry* two_view_geometry) {
-  auto stage = [&](int slot, const Keypoints* kp, const Descriptors* d) {
-    if (d == nullptr) return;
-    const size_t n = std::min<size_t>((size_t)d->rows(), (size_t)sift_match_gpu->GetMaxSift());
-    sift_match_gpu->guided_desc[slot].assign(d->data(), d->data() + n * 128);
-    sift_match_gpu->guided_xy[slot].resize(2 * n);
-    for (size_t i = 0; i < n; ++i) {
-      sift_match_gpu->guided_xy[slot][2 * i] = (*kp)[i].x;
-      sift_match_gpu->guided_xy[slot][2 * i + 1] = (*kp)[i].y;
-    }
+  using Keypoint = typename std::remove_reference<decltype((*keypoints1)[0])>::type;
+  static_assert(sizeof(Keypoint) % sizeof(float) == 0 && sizeof(Keypoint) >= 2 * sizeof(float), "keypoints are float records");
+  const int gap = (int)(sizeof(Keypoint) / sizeof(float)) - 2;  // kFeatureShapeNumElems = 4 for colmap's FeatureKeypoint
+  auto stage = [&](int index, const Keypoints* kp, const Descriptors* d) {
+    if (d == nullptr) return;  // NULL: same image as in the previous call (sift.cc:1009, :1022)
+    if (sift_match_gpu->GetMaxSift() < (int)d->rows())
+      std::printf("WARNING: Clamping features from %d to %d - consider increasing the maximum number of matches.\n",
+                  (int)d->rows(), sift_match_gpu->GetMaxSift());
+    sift_match_gpu->SetDescriptors(index, (int)d->rows(), d->data());
+    static const float kNoKeypoint[2] = {0, 0};
+    sift_match_gpu->SetFeautreLocation(index, kp->size() ? reinterpret_cast<const float*>(kp->data()) : kNoKeypoint, gap);
   };
   stage(0, keypoints1, descriptors1);
   stage(1, keypoints2, descriptors2);
+  float F[9], H[9];
+  float* F_ptr = nullptr;
+  float* H_ptr = nullptr;
   const int cfg = (int)two_view_geometry->config;
-  if (!(cfg == 2 || cfg == 3 || cfg == 4 || cfg == 5 || cfg == 6)) return;
-  b2_guided_geometry g;
-  g.config = cfg;
-  g.reserved = 0;
-  for (int r = 0; r < 3; ++r)
-    for (int c = 0; c < 3; ++c) {
-      g.F[3 * r + c] = two_view_geometry->F(r, c);
-      g.H[3 * r + c] = two_view_geometry->H(r, c);
-    }
-  static const unsigned char kEmptyDesc = 0;
-  static const float kEmptyXy = 0;
-  const unsigned char* dp[2];
-  const float* kp[2];
-  int32_t cnt[2];
-  for (int k = 0; k < 2; ++k) {
-    cnt[k] = (int32_t)(sift_match_gpu->guided_desc[k].size() / 128);
-    dp[k] = cnt[k] ? sift_match_gpu->guided_desc[k].data() : &kEmptyDesc;
-    kp[k] = cnt[k] ? sift_match_gpu->guided_xy[k].data() : &kEmptyXy;
+  if (cfg == 2 || cfg == 3) {  // CALIBRATED, UNCALIBRATED
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) F[3 * r + c] = (float)two_view_geometry->F(r, c);
+    F_ptr = F;
+  } else if (cfg == 4 || cfg == 5 || cfg == 6) {  // PLANAR, PANORAMIC, PLANAR_OR_PANORAMIC
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) H[3 * r + c] = (float)two_view_geometry->H(r, c);
+    H_ptr = H;
+  } else {
+    return;
   }
-  b2_match_options o;
-  o.max_ratio = (float)match_options.max_ratio;
-  o.max_distance = (float)match_options.max_distance;
-  o.cross_check = match_options.cross_check;
-  o.max_num_matches = match_options.max_num_matches;
-  const uint32_t pair[2] = {0, 1};
-  int64_t offsets[2] = {0, 0}, total = 0;
-  const int64_t cap = std::min(cnt[0], cnt[1]) > 0 ? (int64_t)cnt[0] : 0;
-  two_view_geometry->inlier_matches.resize((size_t)std::max<int64_t>(cap, 1));
-  b2_matcher* h = sift_match_gpu->handle();
-  const bool ok = h != nullptr && b2_match_set_images(h, 2, dp, cnt) == B2_OK &&
-                  b2_match_set_keypoints(h, 2, kp, cnt) == B2_OK &&
-                  b2_match_guided_pairs(h, 1, pair, &g, match_options.max_error, &o, offsets,
-                                        reinterpret_cast<uint32_t*>(two_view_geometry->inlier_matches.data()), cap,
-                                        &total) == B2_OK;
-  if (!ok) {
+  two_view_geometry->inlier_matches.resize(static_cast<size_t>(match_options.max_num_matches));
+  const int num_matches = sift_match_gpu->GetGuidedSiftMatch(
+      match_options.max_num_matches, reinterpret_cast<uint32_t(*)[2]>(two_view_geometry->inlier_matches.data()), H_ptr, F_ptr,
+      static_cast<float>(match_options.max_distance), static_cast<float>(match_options.max_ratio),
+      static_cast<float>(match_options.max_error * match_options.max_error),
+      static_cast<float>(match_options.max_error * match_options.max_error), match_options.cross_check);
+  if (num_matches < 0) {
     std::fprintf(stderr, "ERROR: Feature matching failed. This is probably caused by insufficient GPU memory. "
                          "Consider reducing the maximum number of features and/or matches.\n");
     two_view_geometry->inlier_matches.clear();
   } else {
-    two_view_geometry->inlier_matches.resize((size_t)total);
+    two_view_geometry->inlier_matches.resize(num_matches);
   }
 }
+
+// SiftGPU.h:369: the factory the reference loads (SIFTGPU_EXPORT_EXTERN).  The caller owns the object.
+inline SiftMatchGPU* CreateNewSiftMatchGPU(int max_sift = 4096) { return new SiftMatchGPU(max_sift); }
 
 }  // namespace dagsfm_b200

@@ -85,6 +85,36 @@ int main() {
   g.inlier_matches.assign(3, FeatureMatch());
   MatchGuidedSiftFeaturesGPU(opt, &k1, &k2, &d1, &d2, &gpu, &g);
   CHECK(g.inlier_matches.size() == 3);
+  // the SiftMatchGPU interface itself (SiftGPU.h:339-362), as a caller outside colmap's wrapper would drive it: the
+  // factory, SetDescriptors + SetFeautreLocation per image, GetGuidedSiftMatch with H or with F
+  SiftMatchGPU* raw = CreateNewSiftMatchGPU(64);
+  char arg0[] = "-cuda", arg1[] = "0";
+  char* argv[] = {arg0, arg1};
+  raw->SetDeviceParam(2, argv);
+  raw->SetLanguage(SiftMatchGPU::SIFTMATCH_CUDA);
+  CHECK(raw->CreateContextGL() != 0 && raw->Allocate(64, 1) && raw->GetMaxSift() == 64);
+  k1[0].x = 1; k1[1].x = 2;
+  uint32_t buf[8][2];
+  float Hf[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  raw->SetDescriptors(0, 2, d1.data());
+  raw->SetFeautreLocation(0, reinterpret_cast<const float*>(k1.data()), 4);
+  raw->SetDescriptors(1, 2, d2.data());
+  CHECK(raw->GetGuidedSiftMatch(8, buf, Hf, nullptr, 0.7f, 0.8f, 16.f, 16.f, 1) == -1);   // second image has no locations yet
+  raw->SetFeautreLocation(1, reinterpret_cast<const float*>(k2.data()), 4);
+  CHECK(raw->GetGuidedSiftMatch(8, buf, Hf, nullptr, 0.7f, 0.8f, 16.f, 16.f, 1) == 2);
+  CHECK(buf[0][0] == 0 && buf[0][1] == 1 && buf[1][0] == 1 && buf[1][1] == 0);
+  // F of a pure x-translation: x2' F x1 = y1 - y2 = 0 for these keypoints whatever their x
+  float Ff[9] = {0, 0, 0, 0, 0, -1, 0, 1, 0};
+  k1[0].x = 500;
+  raw->SetFeautreLocation(0, reinterpret_cast<const float*>(k1.data()), 4);
+  CHECK(raw->GetGuidedSiftMatch(8, buf, nullptr, Ff, 0.7f, 0.8f, 16.f, 16.f, 1) == 2);
+  CHECK(raw->GetGuidedSiftMatch(8, buf, Hf, nullptr, 0.7f, 0.8f, 16.f, 16.f, 1) == 1);     // H = I rejects the moved keypoint
+  CHECK(raw->GetGuidedSiftMatch(8, buf, Hf, Ff) == -1);                                   // both constraints: unsupported
+  SiftMatchGPU::SiftKeypoint sk[2] = {{1, 0, 1, 0}, {2, 0, 1, 0}};
+  raw->SetFeatureLocation(0, sk);
+  CHECK(raw->GetGuidedSiftMatch(8, buf, Hf, nullptr, 0.7f, 0.8f, 16.f, 16.f, 1) == 2);
+  CHECK(raw->GetGuidedSiftMatch(1, buf, Hf, nullptr, 0.7f, 0.8f, 16.f, 16.f, 1) == 1);     // max_match clamps
+  delete raw;
   std::printf("guided shim ok\n");
   return 0;
 }

@@ -173,3 +173,36 @@ def test_saturating_and_zero_descriptors(mm):
                 assert m[off[p]:off[p + 1]].tolist() == exp.tolist(), (p, i, j)
     finally:
         gpu.close()
+
+
+def test_guided_cpp_shim_on_the_emulated_library():
+    """include/dagsfm_b200/colmap_shim.hpp: the reference's TestMatchGuidedSiftFeaturesGPU replayed through
+    MatchGuidedSiftFeaturesGPU, and the SiftMatchGPU guided interface (factory, SetFeautreLocation, GetGuidedSiftMatch)
+    driven directly -- the C++ test program of tests/test_zz_guided_gpu.py linked against the emulated library."""
+    import subprocess
+    from pathlib import Path
+    from tests.cuda_emu.build_emu import HERE, build
+    root = Path(__file__).resolve().parent.parent
+    lib = build("match", ["common.cu", "match_post.cu", "match_guided.cu", "match_api.cu"], extra=[str(HERE / "match_tc_emu.cc")])
+    exe = HERE / "_build" / "guided_shim_test_emu"
+    r = subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-I", str(root / "include"), str(root / "tests/cpp/guided_shim_test.cc"),
+                        "-o", str(exe), str(lib), f"-Wl,-rpath,{lib.parent}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "guided shim ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_matcher_cpp_shim_on_the_emulated_library():
+    """The SiftMatchGPU / CreateSiftGPUMatcher / MatchSiftFeaturesGPU adaptors (tests/cpp/shim_test.cc, the reference's
+    sift_test.cc cases) linked against the emulated library."""
+    import subprocess
+    from pathlib import Path
+    from tests.cuda_emu.build_emu import HERE, build
+    root = Path(__file__).resolve().parent.parent
+    lib = build("match", ["common.cu", "match_post.cu", "match_guided.cu", "match_api.cu"], extra=[str(HERE / "match_tc_emu.cc")])
+    exe = HERE / "_build" / "shim_test_emu"
+    r = subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-I", str(root / "include"), str(root / "tests/cpp/shim_test.cc"),
+                        "-o", str(exe), str(lib), f"-Wl,-rpath,{lib.parent}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "shim ok" in r.stdout, r.stdout + r.stderr
