@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=48, help="pairs in the CPU baseline sample")
     ap.add_argument("--verify-pairs", type=int, default=20000, help="pairs in the verification leg (0 = skip)")
     ap.add_argument("--ba", default="500,100000,10", help="BA leg: images,points,track (empty = skip)")
+    ap.add_argument("--guided-pairs", type=int, default=0,
+                    help="opt-in leg: guided matching (b2_match_guided_pairs, MatchGuidedSiftFeaturesGPU) on this many synthetic pairs")
     ap.add_argument("--verify-pose", action="store_true",
                     help="verification leg: also time b2_verify_relative_pose (EstimateWithRelativePose) on the verified pairs")
     ap.add_argument("--ba-solver", default="auto", choices=["auto", "exact", "iterative"],
@@ -243,6 +245,48 @@ def bench_verify(a, local_rank, rank, world, cores, barrier):
                                "identical_to_gpu": f"{same}/{ns}"}
     v.close()
     return out
+
+
+def bench_guided(a, local_rank, rank, world, cores, barrier):
+    """Guided matching throughput (off by default in the reference): pairs of synthetic images with
+    matched keypoints, outliers and repeated-structure decoys; the guiding F / H come from the oracle's 8-point / DLT on
+    the true inliers; parity = index-exact with the oracle's MatchGuidedSiftFeaturesCPU on a sample of the pairs."""
+    from dagsfm_b200 import SiftMatchGPU, SiftMatchingOptions
+    from oracle import pyoracle as orc
+    from tests.test_host_guided import _inlier_pairs, _scene_with_descriptors
+    rng = np.random.default_rng(11 + rank)
+    n_scenes = min(a.guided_pairs, 16)                  # distinct image pairs; the pair list cycles over them
+    kps, descs, geos = [], [], []
+    for k in range(n_scenes):
+        planar = k % 2 == 1
+        k1, k2, d1, d2 = _scene_with_descriptors(rng, 1500, 548, planar)      # 2048 keypoints per image
+        x, y = _inlier_pairs(k1, k2, d1, d2)
+        geos.append((6, None, orc.h_dlt(x, y)) if planar else (3, orc.eight_point(x, y), None))
+        kps += [k1, k2]
+        descs += [d1, d2]
+    pairs = [(2 * (p % n_scenes), 2 * (p % n_scenes) + 1) for p in range(a.guided_pairs)]
+    geometries = [geos[p % n_scenes] for p in range(a.guided_pairs)]
+    opt = SiftMatchingOptions()
+    m = SiftMatchGPU(local_rank)
+    try:
+        m.set_images(descs)
+        m.set_keypoints(kps)
+        off, mt = m.match_guided_pairs(pairs, geometries, opt)            # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        off, mt = m.match_guided_pairs(pairs, geometries, opt)
+        barrier()
+        wall = time.perf_counter() - t0
+    finally:
+        m.close()
+    same = 0
+    for p in range(min(n_scenes, 4)):
+        cfg, F, H = geometries[p]
+        e = orc.match_guided(kps[2 * p], kps[2 * p + 1], descs[2 * p], descs[2 * p + 1], cfg, F=F, H=H)
+        same += int(mt[off[p]:off[p + 1]].tolist() == e.tolist())
+    return {"pairs": a.guided_pairs * world, "keypoints_per_image": 2048, "pairs_per_s_e2e": a.guided_pairs * world / wall,
+            "matches_per_pair": float(off[-1] / max(a.guided_pairs, 1)), "identical_to_oracle": f"{same}/{min(n_scenes, 4)}",
+            "api": "b2_match_guided_pairs (host buffers)"}
 
 
 def _mean_reproj(prob):
@@ -487,6 +531,12 @@ def main():
     verify = None
     if a.verify_pairs > 0:
         verify = bench_verify(a, local_rank, rank, world, cores, barrier)
+    guided = None
+    if getattr(a, "guided_pairs", 0) > 0:     # opt-in: the guided kernel has not been validated on a GPU yet
+        try:
+            guided = bench_guided(a, local_rank, rank, world, cores, barrier)
+        except Exception as e:
+            guided = {"error": repr(e)}
     # ------------------------------------------------------- bundle adjustment leg
     ba = None
     if a.ba:
@@ -539,7 +589,7 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "u8 x u8 -> s32 (exact)", "data": "synthetic",
         "config": cfg, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "roofline": roofline, "cpu_baseline": cpu,
-        "verify": verify, "ba": ba,
+        "verify": verify, "ba": ba, **({"guided": guided} if guided is not None else {}),
         "wall_ms_per_step": 1e3 * wall / a.steps, "matches_per_step": int(total),
         "fixup_candidates_last_chunk_sum": int(cands),
     }), flush=True)

@@ -15,6 +15,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-fil
 ncu --set full --clock-control none --import-source on -k regex:'image_pass_kernel|matvec_point_kernel' -s 40 -c 2 \
   -o gpurun_out/ba_iter_matvec python bench.py --pairs 2000 --verify-pairs 0 --no-cpu --no-e2e --steps 1 --warmup 1 \
   --ba 2000,400000,10 --ba-solver iterative > /dev/null 2>&1
+python bench.py --pairs 2000 --ba "" --verify-pairs 0 --no-cpu --no-e2e --steps 3 --warmup 3 --guided-pairs 4000 > gpurun_out/guided.json 2> gpurun_out/guided.err
 python bench.py --pairs 2000 --ba "" --no-cpu --no-e2e --steps 3 --warmup 3 --verify-pose > gpurun_out/verify_pose.json 2> gpurun_out/verify_pose.err
 for v in 0 1; do
   B2_VERIFY_VARIANT=$v B2_VERIFY_PROFILE=1 python bench.py --pairs 20000 --ba "" --no-cpu --no-e2e --steps 3 --warmup 3 \

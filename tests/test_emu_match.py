@@ -206,3 +206,22 @@ def test_matcher_cpp_shim_on_the_emulated_library():
     assert r.returncode == 0, r.stderr
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "shim ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_bench_guided_leg_runs_on_the_emulated_library(mm):
+    """bench.py's opt-in guided-matching leg end to end on the emulated library (index-exact with the oracle)."""
+    import sys
+    import types
+    argv, sys.argv = sys.argv, ["bench.py"]
+    try:
+        import bench
+    finally:
+        sys.argv = argv
+    import dagsfm_b200
+    saved = (dagsfm_b200.SiftMatchGPU, dagsfm_b200.SiftMatchingOptions)
+    dagsfm_b200.SiftMatchGPU, dagsfm_b200.SiftMatchingOptions = mm.SiftMatchGPU, mm.SiftMatchingOptions
+    try:
+        out = bench.bench_guided(types.SimpleNamespace(guided_pairs=3), 0, 0, 1, 1, lambda: None)
+    finally:
+        dagsfm_b200.SiftMatchGPU, dagsfm_b200.SiftMatchingOptions = saved
+    assert out["pairs"] == 3 and out["identical_to_oracle"] == "3/3" and out["matches_per_pair"] > 1000
