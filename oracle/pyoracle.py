@@ -526,6 +526,17 @@ def triangulate_point(R, t, p1, p2):
     return X
 
 
+def check_cheirality(R, t, p1, p2):
+    """CheckCheirality (base/pose.cc:225-248): the triangulated points in front of both cameras."""
+    R, t, p1, p2 = _p(R), _p(t), _p(p1), _p(p2)
+    X = np.zeros((max(len(p1), 1), 3))
+    f = _tv().orc_check_cheirality
+    f.restype = C.c_int
+    n = f(C.c_void_p(R.ctypes.data), C.c_void_p(t.ctypes.data), len(p1), C.c_void_p(p1.ctypes.data), C.c_void_p(p2.ctypes.data),
+          C.c_void_p(X.ctypes.data))
+    return X[:n]
+
+
 def triangulation_angles(R, t, points3D):
     R, t, X = _p(R), _p(t), _p(points3D)
     a = np.zeros(len(X))

@@ -1819,6 +1819,13 @@ void orc_triangulation_angles(const double* R, const double* t, int n, const dou
   const std::vector<double> a = tv::CalculateTriangulationAnglesWithPM(to_mat3(R), tt, pts);
   memcpy(angles, a.data(), 8 * (size_t)n);
 }
+int orc_check_cheirality(const double* R, const double* t, int n, const double* p1, const double* p2, double* points3D) {
+  tv::Vec3 tt; memcpy(tt.v, t, 24);
+  std::vector<tv::Vec3> pts;
+  tv::CheckCheirality(to_mat3(R), tt, to_vec(p1, n), to_vec(p2, n), &pts);
+  for (size_t i = 0; i < pts.size(); ++i) memcpy(points3D + 3 * i, pts[i].v, 24);
+  return (int)pts.size();
+}
 double orc_median(int n, const double* v) { return tv::Median(std::vector<double>(v, v + n)); }
 void orc_rotation_to_quaternion(const double* R, double* q) { tv::RotationMatrixToQuaternion(to_mat3(R), q); }
 // EstimateWithRelativePose's post-processing of an EstimateCalibrated result (config, E, H, inlier_matches)

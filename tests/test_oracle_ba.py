@@ -157,3 +157,30 @@ def test_general_camera_models_exact_and_iterative_reach_the_same_optimum():
         assert abs(reprojection_rms(a) - reprojection_rms(b)) < 1e-6
         assert s_it.final_cost == __import__("pytest").approx(s_ex.final_cost, rel=1e-8)
         assert (a["cam_params"][:, len(cam[1]):] == 0).all()
+
+
+def test_reprojection_error_reference_cases():
+    """base/projection_test.cc:95-124 (CalculateSquaredReprojectionError: 0 at the exact projection, 2 one pixel off in
+    x and y) and base/pose_test.cc:154-172 (QuaternionRotatePoint normalises its quaternion) through the B8 metric."""
+    rng = np.random.default_rng(0)
+    X = np.abs(rng.uniform(-1, 1, 3))
+    base = dict(qvec=np.array([[1.0, 0, 0, 0]]), tvec=np.zeros((1, 3)), img_cam=np.zeros(1, np.int32), pose_const=np.zeros(1, np.uint8),
+                tvec_const=np.zeros(1, np.uint8), cam_model=np.zeros(1, np.int32), cam_params=np.array([[1.0, 0, 0, 0]]),
+                cam_const=np.zeros(1, np.uint8), xyz=X[None].copy(), pt_const=np.zeros(1, np.uint8), obs_img=np.zeros(1, np.int32),
+                obs_pt=np.zeros(1, np.int32), obs_xy=(X[:2] / X[2])[None].copy())
+    mean, err = orc.ba_mean_reprojection_error(base)
+    assert mean == 0 and err[0] == 0
+    off = {k: v.copy() for k, v in base.items()}
+    off["obs_xy"] += 1
+    assert orc.ba_mean_reprojection_error(off)[0] ** 2 == __import__("pytest").approx(2, rel=1e-8)
+    scaled = {k: v.copy() for k, v in base.items()}
+    scaled["qvec"] *= 0.1                                  # Vector4d(0.1, 0, 0, 0) rotates like the identity
+    assert orc.ba_mean_reprojection_error(scaled)[0] == 0
+    behind = {k: v.copy() for k, v in off.items()}
+    behind["xyz"][0, 2] = -1.0                             # not in front of the camera: skipped, the track still counts
+    assert orc.ba_mean_reprojection_error(behind) [0] == 0
+    flip = {k: v.copy() for k, v in base.items()}          # rotation by pi about x maps (1, 1, z) to (1, -1, -z)
+    flip["qvec"][0] = [0, 1, 0, 0]
+    flip["xyz"][0] = [1, 1, -2]
+    flip["obs_xy"][0] = [0.5, -0.5]
+    assert orc.ba_mean_reprojection_error(flip)[0] < 1e-15

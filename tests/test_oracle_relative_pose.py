@@ -185,3 +185,11 @@ def test_relative_pose_degenerate_and_panoramic_cases():
     rp = orc.relative_pose(c, p, c, p2, 6, np.zeros((3, 3)), H, m)
     assert rp.config == 5 and rp.tri_angle == 0 and rp.n_points3D == 0 and list(rp.tvec) == [0, 0, 0]
     assert np.allclose(quat_to_R(np.array(rp.qvec)), Rr, atol=1e-9)
+
+
+def test_check_cheirality_reference_cases():      # base/pose_test.cc:384-411
+    R, t = np.eye(3), np.array([1.0, 0, 0])
+    assert len(orc.check_cheirality(R, t, [[0, 0]], [[0.1, 0]])) == 1
+    assert len(orc.check_cheirality(R, t, [[0, 0], [0, 0]], [[0.1, 0], [-0.1, 0]])) == 1
+    assert len(orc.check_cheirality(R, t, [[0, 0], [0, 0]], [[0.1, 0], [0.2, 0]])) == 2
+    assert len(orc.check_cheirality(R, t, [[0, 0], [0, 0]], [[-0.2, 0], [-0.2, 0]])) == 0
