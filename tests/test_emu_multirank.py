@@ -43,11 +43,11 @@ def _bind(lib_path):
     return ba, L
 
 
-def _solve(ba, L, prob, solver, hook=None):
+def _solve(ba, L, prob, solver, hook=None, iters=12):
     o = ba.BundleAdjustmentOptions()
     L.b2_ba_default_options(C.byref(o))
     o.linear_solver_type = solver
-    o.max_num_iterations, o.gradient_tolerance = 12, 1e-6
+    o.max_num_iterations, o.gradient_tolerance = iters, 1e-6
     adj = ba.BundleAdjuster(o)
     if hook:
         adj.set_allreduce(hook)
@@ -109,3 +109,40 @@ def test_two_ranks_reproduce_the_single_rank_solve(emu_lib, tmp_path, solver):
     xyz[r0["ids"]], xyz[r1["ids"]] = r0["xyz"], r1["xyz"]
     assert len(r0["ids"]) + len(r1["ids"]) == len(xyz) and np.abs(xyz - one["xyz"]).max() < 1e-5
     assert reprojection_rms(one) < reprojection_rms(start)
+
+
+def _worker_auto(rank, world, port, lib_path, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ba, L = _bind(lib_path)
+    sub, ids = shard_ba_problem(make_ba_problem(n_img=1001, n_pts=600, track_len=3, seed=23), rank, world)
+    s = _solve(ba, L, sub, 0, _gloo_hook, iters=2)          # linear_solver_type 0: the reference's rule picks the solver
+    np.savez(Path(out_dir) / f"auto{rank}.npz", ids=ids, qvec=sub["qvec"], xyz=sub["xyz"],
+             stats=np.array([s.linear_solver_type_used, s.num_successful_steps, s.num_linear_solver_iterations, s.final_cost]))
+    dist.destroy_process_group()
+
+
+def test_four_ranks_final_ba_shape_selects_the_iterative_solver(emu_lib, tmp_path):
+    """The C5 arrangement in miniature: more than 1000 images (so BundleAdjuster::Solve's rule selects ITERATIVE_SCHUR on
+    every rank), points sharded over four ranks, one all-reduce per inner iteration -- equal to the single-rank solve."""
+    port = 25000 + (os.getpid() % 2000)
+    mp.spawn(_worker_auto, args=(4, port, str(emu_lib), str(tmp_path)), nprocs=4, join=True)
+    r = [np.load(tmp_path / f"auto{k}.npz") for k in range(4)]
+    import dagsfm_b200.bundle_adjustment as ba_mod
+    saved = (ba_mod._L, ba_mod.check)
+    try:
+        ba, L = _bind(emu_lib)
+        one = make_ba_problem(n_img=1001, n_pts=600, track_len=3, seed=23)
+        s1 = _solve(ba, L, one, 0, iters=2)
+    finally:
+        ba_mod._L, ba_mod.check = saved
+    assert s1.linear_solver_type_used == 2
+    for k in range(4):
+        assert r[k]["stats"][0] == 2 and (r[k]["qvec"] == r[0]["qvec"]).all()
+        assert r[k]["stats"][1] == s1.num_successful_steps
+    assert r[0]["stats"][3] == pytest.approx(s1.final_cost, rel=1e-7)
+    xyz = np.zeros_like(one["xyz"])
+    for k in range(4):
+        xyz[r[k]["ids"]] = r[k]["xyz"]
+    assert np.abs(xyz - one["xyz"]).max() < 1e-5 and np.abs(r[0]["qvec"] - one["qvec"]).max() < 1e-7
