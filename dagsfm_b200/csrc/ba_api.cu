@@ -563,8 +563,10 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
       sum->num_unsuccessful_steps++;
       radius /= decrease_factor;
       decrease_factor *= 2.0;
-      if (radius < min_radius) {
-        sum->termination_type = 2;
+      // TrustRegionMinimizer::MinTrustRegionRadiusReached (Ceres 1.14): "Minimum trust region radius reached" is
+      // reported as CONVERGENCE, and is tested after the iteration limit
+      if (radius <= min_radius) {
+        sum->termination_type = (iter + 1 >= opt->max_num_iterations) ? 1 : 0;
         break;
       }
     }

@@ -923,7 +923,9 @@ static void Solve(Problem P, Options O, Summary* S) {
       S->num_unsuccessful_steps++;
       radius /= decrease_factor;
       decrease_factor *= 2.0;
-      if (radius < min_radius) { S->termination = 2; break; }
+      // TrustRegionMinimizer::MinTrustRegionRadiusReached: CONVERGENCE ("Minimum trust region radius reached"), checked
+      // after MaxSolverIterationsReached in FinalizeIterationAndCheckIfMinimizerCanContinue
+      if (radius <= min_radius) { S->termination = (iter + 1 >= O.max_num_iterations) ? 1 : 0; break; }
       continue;
     }
     // candidate x_plus_delta (undo the Jacobi scaling)
@@ -973,7 +975,9 @@ static void Solve(Problem P, Options O, Summary* S) {
       S->num_unsuccessful_steps++;
       radius /= decrease_factor;
       decrease_factor *= 2.0;
-      if (radius < min_radius) { S->termination = 2; break; }
+      // TrustRegionMinimizer::MinTrustRegionRadiusReached: CONVERGENCE ("Minimum trust region radius reached"), checked
+      // after MaxSolverIterationsReached in FinalizeIterationAndCheckIfMinimizerCanContinue
+      if (radius <= min_radius) { S->termination = (iter + 1 >= O.max_num_iterations) ? 1 : 0; break; }
     }
   }
   S->final_cost = cost;
