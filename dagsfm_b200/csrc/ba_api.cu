@@ -536,6 +536,12 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
       }
       const double new_cost = hs[5];
       const double cost_change = cost - new_cost;
+      // Ceres' TrustRegionMinimizer tests the function tolerance on every valid step before judging it; the candidate is
+      // then not applied (function_tolerance = 0, the reference's setting, fires on an exactly unchanged cost)
+      if (std::abs(cost_change) <= opt->function_tolerance * cost) {
+        sum->termination_type = 0;
+        break;
+      }
       const double rho = cost_change / model_cost_change;
       if (rho > min_rel_dec) {
         accepted = true;
@@ -548,15 +554,10 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
         radius = radius / std::max(1.0 / 3.0, 1.0 - t * t * t);
         radius = std::min(max_radius, radius);
         decrease_factor = 2.0;
-        const bool ftol = std::abs(cost_change) <= opt->function_tolerance * cost;
         cost = new_cost;
         B2_CUDA(cudaMemsetAsync(scal + 6, 0, 8, s));
         B2_CUDA(ba_launch_jacobian(P, P.qvec, P.tvec, P.cam_params, P.xyz, 0, scal + 6, s, loss_type, loss_scale));
         count_launches(1);
-        if (ftol) {
-          sum->termination_type = 0;
-          break;
-        }
       }
     }
     if (!accepted) {

@@ -955,6 +955,10 @@ static void Solve(Problem P, Options O, Summary* S) {
     if (std::sqrt(step_sq) <= O.parameter_tolerance * (std::sqrt(x_sq) + O.parameter_tolerance)) { S->termination = 0; break; }
     const double new_cost = sv.EvalCost(qn.data(), tn.data(), kn.data(), Xn.data());
     const double cost_change = cost - new_cost;
+    // TrustRegionMinimizer::Minimize (Ceres 1.12+): FunctionToleranceReached is tested on every valid step BEFORE the
+    // step is judged -- |cost_change| <= function_tolerance * cost ends the solve with CONVERGENCE and the candidate is
+    // not applied (with the reference's function_tolerance = 0 this fires on an exactly unchanged cost)
+    if (std::abs(cost_change) <= O.function_tolerance * cost) { S->termination = 0; break; }
     const double rho = cost_change / model_cost_change;
     if (rho > min_rel_dec) {  // successful step
       memcpy(P.qvec, qn.data(), qn.size() * 8);
@@ -966,11 +970,9 @@ static void Solve(Problem P, Options O, Summary* S) {
       radius = radius / std::max(1.0 / 3.0, 1.0 - t * t * t);
       radius = std::min(max_radius, radius);
       decrease_factor = 2.0;
-      const bool ftol = std::abs(cost_change) <= O.function_tolerance * cost;
       cost = new_cost;
       sv.EvalJacobian(true);
       need_grad_check = true;
-      if (ftol) { S->termination = 0; break; }
     } else {
       S->num_unsuccessful_steps++;
       radius /= decrease_factor;
