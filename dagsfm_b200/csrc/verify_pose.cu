@@ -273,7 +273,8 @@ __global__ void __launch_bounds__(128) relative_pose_kernel(PoseArgs a) {
     // comes from EstimateMultiple, which never computes poses.
     if (run) run = a.cams[i1].has_prior_focal_length && a.cams[i2].has_prior_focal_length;
     const int cfg = res.config;
-    if (cfg != 2 && cfg != 3 && cfg != 6 && cfg != 7) run = false;
+    // 4 / 5 (PLANAR / PANORAMIC) only occur when TwoViewGeometry::EstimateRelativePose (:169-230) is re-run on a stored geometry
+    if (cfg != 2 && cfg != 3 && cfg != 4 && cfg != 5 && cfg != 6 && cfg != 7) run = false;
     if (!run) {
       if (lane == 0) a.poses[p] = out;
       continue;

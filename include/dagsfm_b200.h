@@ -233,7 +233,8 @@ int b2_verify_pairs_device(b2_verifier* v, int64_t n_pairs, const uint32_t* pair
 /* TwoViewGeometry::EstimateWithRelativePose after EstimateCalibrated (two_view_geometry.cc:239-289): for every
  * pair whose two cameras have a prior focal length (the dispatch of TwoViewGeometry::Estimate, :113-126) and whose
  * config is CALIBRATED / UNCALIBRATED (pose from E, base/essential_matrix.cc:41-88) or PLANAR_OR_PANORAMIC / WATERMARK
- * (pose from H, base/homography_matrix.cc:65-197): the (R, t) candidate with the most inliers in front of both
+ * (pose from H, base/homography_matrix.cc:65-197; also PLANAR / PANORAMIC, which TwoViewGeometry::EstimateRelativePose,
+ * :169-230, accepts when it is re-run on a stored geometry): the (R, t) candidate with the most inliers in front of both
  * cameras (CheckCheirality, base/pose.cc:225-248; ties keep the later candidate), qvec = RotationMatrixToQuaternion(R),
  * tri_angle = median triangulation angle of those points (base/triangulation.cc:183-215), and PLANAR_OR_PANORAMIC
  * resolved to PANORAMIC (|t| == 0, tri_angle 0) or PLANAR.  Every other pair (a camera without prior focal length,

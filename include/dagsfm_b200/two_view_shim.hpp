@@ -197,6 +197,41 @@ struct TwoViewGeometryT {
     Run(camera1, points1, camera2, points2, matches, options, true, true, false, true);
   }
 
+  // two_view_geometry.cc:169-230: relative pose of an ALREADY estimated geometry (config, E / H, inlier_matches), as the
+  // incremental mapper calls it for its initial pair (sfm/incremental_mapper.cc:1161).  False when the configuration
+  // carries no epipolar geometry or homography to decompose.
+  template <class Camera, class Points>
+  bool EstimateRelativePose(const Camera& camera1, const Points& points1, const Camera& camera2, const Points& points2,
+                            int gpu_index = 0) {
+    if (config != CALIBRATED && config != UNCALIBRATED && config != PLANAR && config != PANORAMIC && config != PLANAR_OR_PANORAMIC)
+      return false;
+    b2_verifier* v = Verifier(gpu_index);
+    if (!v) return false;
+    const b2_camera cams[2] = {PackCamera(camera1, true), PackCamera(camera2, true)};
+    const std::vector<double> xy1 = PackPoints(points1), xy2 = PackPoints(points2);
+    static const double kNone[2] = {0, 0};
+    const double* xy[2] = {xy1.empty() ? kNone : xy1.data(), xy2.empty() ? kNone : xy2.data()};
+    const int32_t n_pts[2] = {(int32_t)points1.size(), (int32_t)points2.size()};
+    b2_two_view_result res = {};
+    res.config = config;
+    res.n_inliers = (int32_t)inlier_matches.size();
+    for (int i = 0; i < 9; ++i) { res.E[i] = E.m[i]; res.F[i] = F.m[i]; res.H[i] = H.m[i]; }
+    const uint32_t pair[2] = {0, 1};
+    const int64_t offsets[2] = {0, (int64_t)inlier_matches.size()};
+    static const uint32_t kNoMatch[2] = {0, 0};
+    const uint32_t* iptr = inlier_matches.empty() ? kNoMatch : reinterpret_cast<const uint32_t*>(inlier_matches.data());
+    b2_relative_pose rp;
+    if (b2_verify_set_images(v, 2, cams, xy, n_pts) != B2_OK || b2_verify_relative_pose(v, 1, pair, offsets, &res, iptr, &rp) != B2_OK) {
+      std::fprintf(stderr, "ERROR: relative pose failed: %s\n", b2_last_error());
+      return false;
+    }
+    config = rp.config;
+    for (int i = 0; i < 4; ++i) qvec(i) = rp.qvec[i];
+    for (int i = 0; i < 3; ++i) tvec(i) = rp.tvec[i];
+    tri_angle = rp.tri_angle;
+    return true;
+  }
+
   int config = UNDEFINED;
   Mat3 E, F, H;
   Vec4 qvec;

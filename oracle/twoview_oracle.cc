@@ -1538,7 +1538,9 @@ static RelPose RelativePose(const Camera& c1, const Vec2* pts1, const Camera& c2
                             const Mat3& H, const uint32_t* inlier_matches, size_t n_inl) {
   RelPose out;
   out.config = config;
-  if (config != CALIBRATED && config != UNCALIBRATED && config != PLANAR_OR_PANORAMIC && config != WATERMARK) return out;
+  if (config != CALIBRATED && config != UNCALIBRATED && config != PLANAR && config != PANORAMIC && config != PLANAR_OR_PANORAMIC &&
+      config != WATERMARK)
+    return out;
   std::vector<Vec2> n1(n_inl), n2(n_inl);
   for (size_t i = 0; i < n_inl; ++i) {
     n1[i] = ImageToWorld(c1, pts1[inlier_matches[2 * i]]);

@@ -141,6 +141,17 @@ static int test_estimate() {
   TwoViewGeometry gm;
   gm.EstimateMultiple(cam, p1, cam, p2, matches, opt);
   CHECK(gm.config == TwoViewGeometry::CALIBRATED && gm.inlier_matches.size() >= 0.95 * n_in && approx(gm.qvec.norm(), 1.0, 1e-9));
+  // EstimateRelativePose on a stored geometry (incremental_mapper.cc:1161): same pose as the one Estimate attached;
+  // configurations without E / H to decompose are refused
+  TwoViewGeometry gr = g;
+  gr.qvec = Vec4::Zero(); gr.tvec = Vec3::Zero(); gr.tri_angle = 0;
+  CHECK(gr.EstimateRelativePose(cam, p1, cam, p2));
+  CHECK(gr.qvec == g.qvec && gr.tvec == g.tvec && gr.tri_angle == g.tri_angle && gr.config == g.config);
+  TwoViewGeometry gw = g;
+  gw.config = TwoViewGeometry::WATERMARK;
+  CHECK(!gw.EstimateRelativePose(cam, p1, cam, p2));
+  gw.config = TwoViewGeometry::DEGENERATE;
+  CHECK(!gw.EstimateRelativePose(cam, p1, cam, p2));
   std::printf("two-view shim ok: %zu inliers, tri_angle %.4f\n", g.inlier_matches.size(), g.tri_angle);
   return 0;
 }
