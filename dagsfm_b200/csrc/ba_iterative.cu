@@ -218,7 +218,8 @@ __global__ void __launch_bounds__(128) precond_kernel(BaDev P, BaIter I) {
   const int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (o >= P.n_obs) return;
   const int i = P.obs_img[o], cm = P.img_cam[i], p = P.obs_pt[o], pc = P.pt_col[p];
-  const J& e = jac<J>(P)[o];
+  J e;
+  load_block(jac<J>(P) + o, &e);
   int col[NC];
 #pragma unroll
   for (int k = 0; k < 6; ++k) col[k] = P.pose_col[6 * i + k];
@@ -242,7 +243,8 @@ __global__ void __launch_bounds__(128) precond_kernel(BaDev P, BaIter I) {
       const int ib = P.obs_img[b];
       const bool same_img = ib == i, same_cam = same_img || P.img_cam[ib] == cm;
       if (!same_cam) continue;
-      const J& eb = jac<J>(P)[b];
+      J eb;
+      load_block(jac<J>(P) + b, &eb);
 #pragma unroll
       for (int k = 0; k < NC; ++k) {
         if (k < 6 && !same_img) continue;
