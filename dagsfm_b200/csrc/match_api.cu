@@ -53,6 +53,7 @@ cudaError_t launch_cross_write(const PairMeta* meta, int64_t n_pairs, const int*
                                int cross_check, const int64_t* offsets, uint32_t* out_matches,
                                int64_t capacity, cudaStream_t s);
 cudaError_t launch_guided_item_pairs(const PairMeta* meta, int64_t n_pairs, uint32_t* item_pair, cudaStream_t s);
+cudaError_t launch_geoms_from_results(int64_t n_pairs, const void* results, int min_num_inliers, GuidedGeom* geoms, cudaStream_t s);
 cudaError_t launch_guided_match(const uint8_t* pool, const float* kp_pool, const MatchItem* items,
                                 const uint32_t* item_pair, const uint32_t* n_items_ptr, const PairMeta* meta,
                                 const GuidedGeom* geoms, float max_residual, int thr_dist, const int* ratio_lim,
@@ -592,6 +593,23 @@ int b2_match_guided_pairs(b2_matcher* m, int64_t n_pairs, const uint32_t* pairs,
     B2_CUDA(cudaMemcpyAsync(out_matches, m->d_matches, total * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, m->stream));
   B2_CUDA(cudaStreamSynchronize(m->stream));
   return B2_OK;
+}
+
+int b2_match_guided_pairs_device(b2_matcher* m, int64_t n_pairs, const uint32_t* pairs_dev, const b2_two_view_result* results_dev,
+                                 int32_t min_num_inliers, double max_error, const b2_match_options* opt,
+                                 int64_t* out_offsets_dev, uint32_t* out_matches_dev, int64_t capacity, int64_t* n_total) {
+  if (!m || !out_offsets_dev || (n_pairs > 0 && (!pairs_dev || !results_dev)) || (capacity > 0 && !out_matches_dev))
+    return set_error(B2_ERR_INVALID, "NULL argument");
+  if (n_pairs < 0 || capacity < 0) return set_error(B2_ERR_INVALID, "negative size");
+  B2_CUDA(cudaSetDevice(m->device));
+  B2_TRY(grow((void**)&m->d_geoms, &m->d_geoms_cap, n_pairs, sizeof(GuidedGeom)));
+  B2_CUDA(launch_geoms_from_results(n_pairs, results_dev, min_num_inliers, m->d_geoms, m->stream));
+  count_launches(n_pairs > 0 ? 1 : 0);
+  int64_t total = 0;
+  const int rc = run_guided_device(m, m->store, n_pairs, pairs_dev, m->d_geoms, max_error, opt, out_offsets_dev, out_matches_dev,
+                                   capacity, &total);
+  if (n_total) *n_total = total;
+  return rc;
 }
 
 int b2_match_set_descriptors(b2_matcher* m, int slot, int32_t n, const uint8_t* desc) {

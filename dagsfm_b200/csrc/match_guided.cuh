@@ -31,7 +31,7 @@ struct GuidedGeom {  // per pair
 
 // TwoViewGeometry::ConfigurationType -> filter (sift.cc:838-866): CALIBRATED / UNCALIBRATED use F,
 // PLANAR / PANORAMIC / PLANAR_OR_PANORAMIC use H, anything else has no guided filter.
-inline GuidedGeom make_guided_geom(int config, const double* F_rowmajor, const double* H_rowmajor) {
+B2_HD GuidedGeom make_guided_geom(int config, const double* F_rowmajor, const double* H_rowmajor) {
   GuidedGeom g;
   g.kind = (config == 2 || config == 3) ? 1 : (config == 4 || config == 5 || config == 6) ? 2 : 0;
   const double* src = (g.kind == 1) ? F_rowmajor : H_rowmajor;

@@ -157,6 +157,19 @@ class SiftMatchGPU:
                                           capacity, C.byref(total)))
         return total.value
 
+    def match_guided_pairs_device(self, n_pairs: int, pairs_dev_ptr: int, results_dev_ptr: int, min_num_inliers: int,
+                                  options: SiftMatchingOptions, offsets_dev_ptr: int, matches_dev_ptr: int, capacity: int) -> int:
+        """The guided stage chained onto verify_pairs_device: geometries are read from the verifier's device results."""
+        opt = options.to_c()
+        total = C.c_int64(0)
+        L = lib()
+        L.b2_match_guided_pairs_device.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_double,
+                                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+        check(L.b2_match_guided_pairs_device(self._h, n_pairs, C.c_void_p(pairs_dev_ptr), C.c_void_p(results_dev_ptr),
+                                             int(min_num_inliers), float(options.max_error), C.byref(opt),
+                                             C.c_void_p(offsets_dev_ptr), C.c_void_p(matches_dev_ptr), capacity, C.byref(total)))
+        return total.value
+
     def last_timing(self) -> dict:
         tc, al = C.c_double(0), C.c_double(0)
         nl, nc = C.c_int64(0), C.c_int64(0)

@@ -145,6 +145,15 @@ int b2_match_guided_pairs(b2_matcher* m, int64_t n_pairs, const uint32_t* pairs,
                           const b2_guided_geometry* geoms, double max_error, const b2_match_options* opt,
                           int64_t* out_offsets, uint32_t* out_matches, int64_t capacity, int64_t* n_total);
 
+/* The guided stage chained onto the verifier on the device (GuidedSiftGPUFeatureMatcher::Run, matching.cc:493-530):
+ * the geometry of pair p is (config, F, H) of results_dev[p] as b2_verify_pairs_device wrote it; a pair with fewer than
+ * min_num_inliers inliers (:508-512) or a configuration without a guided filter gets an empty slice -- the reference
+ * passes such pairs through with the verifier's inlier list.  pairs / results / offsets / matches in DEVICE memory. */
+struct b2_two_view_result;
+int b2_match_guided_pairs_device(b2_matcher* m, int64_t n_pairs, const uint32_t* pairs_dev,
+                                 const struct b2_two_view_result* results_dev, int32_t min_num_inliers, double max_error,
+                                 const b2_match_options* opt, int64_t* out_offsets_dev, uint32_t* out_matches_dev,
+                                 int64_t capacity, int64_t* n_total);
 
 /* ================================================================= VERIFY ==
  * Replaces: TwoViewGeometry::Estimate (src/estimators/two_view_geometry.h:180-184,

@@ -225,3 +225,41 @@ def test_bench_guided_leg_runs_on_the_emulated_library(mm):
     finally:
         dagsfm_b200.SiftMatchGPU, dagsfm_b200.SiftMatchingOptions = saved
     assert out["pairs"] == 3 and out["identical_to_oracle"] == "3/3" and out["matches_per_pair"] > 1000
+
+
+def test_guided_stage_chained_on_device_results(mm):
+    """b2_match_guided_pairs_device: geometries come from b2_two_view_result records in device memory (host memory on the
+    emulator); equal to the host-buffer call with the same geometries; pairs below min_num_inliers and configurations
+    without a guided filter yield empty slices (GuidedSiftGPUFeatureMatcher::Run, matching.cc:508-512)."""
+    from dagsfm_b200.verification import RESULT_DTYPE
+    rng = np.random.default_rng(3)
+    kps, descs, geos = [], [], []
+    for k in range(4):
+        k1, k2, d1, d2 = _scene_with_descriptors(rng, 120 + 30 * k, 40, planar=(k % 2 == 1))
+        a, b = _inlier_pairs(k1, k2, d1, d2)
+        geos.append((6, None, orc.h_dlt(a, b)) if k % 2 else (2, orc.eight_point(a, b), None))
+        kps += [k1, k2]
+        descs += [d1, d2]
+    pairs = np.array([(0, 1), (2, 3), (4, 5), (6, 7), (0, 1), (2, 3)], np.uint32)
+    res = np.zeros(6, RESULT_DTYPE)
+    for p in range(6):
+        cfg, F, H = geos[p % 4]
+        res["config"][p], res["n_inliers"][p] = cfg, 50
+        res["F"][p] = np.zeros(9) if F is None else F.ravel()
+        res["H"][p] = np.zeros(9) if H is None else H.ravel()
+    res["n_inliers"][4] = 14            # below the gate
+    res["config"][5] = 7                # WATERMARK: no guided filter
+    o = mm.SiftMatchingOptions()
+    gpu = mm.SiftMatchGPU(0)
+    try:
+        gpu.set_images(descs)
+        gpu.set_keypoints(kps)
+        off_h, m_h = gpu.match_guided_pairs(pairs[:4], geos, o)
+        cap = int(sum(len(descs[a]) for a, _ in pairs))
+        off_d = np.zeros(7, np.int64)
+        m_d = np.zeros((cap, 2), np.uint32)
+        total = gpu.match_guided_pairs_device(6, pairs.ctypes.data, res.ctypes.data, 15, o, off_d.ctypes.data, m_d.ctypes.data, cap)
+    finally:
+        gpu.close()
+    assert off_d[:5].tolist() == off_h.tolist() and m_d[:off_h[-1]].tolist() == m_h.tolist()
+    assert off_d[5] == off_d[4] == off_d[6] == total and total > 300
