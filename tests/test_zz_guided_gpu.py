@@ -390,3 +390,46 @@ def test_mean_reprojection_error_matches_oracle_on_gpu():
             assert mean == pytest.approx(omean, rel=1e-12) and np.allclose(err, oerr, rtol=1e-11, atol=1e-13)
     finally:
         ba.close()
+
+
+@pytest.mark.gpu
+@FIRST_RUN
+def test_guided_stage_chained_on_device_results_on_gpu():
+    """match -> verify -> guided match with nothing but the final lists leaving the device: b2_match_guided_pairs_device
+    reads the verifier's results in device memory; equal to the host-buffer guided call with the same geometries."""
+    import torch
+    from dagsfm_b200 import Camera, SiftMatchGPU, SiftMatchingOptions, TwoViewGeometryVerifier, TwoViewOptions
+    from dagsfm_b200.verification import RESULT_DTYPE
+    rng = np.random.default_rng(8)
+    kps, descs, pairs = [], [], []
+    for k in range(4):
+        k1, k2, d1, d2 = _scene_with_descriptors(rng, 250 + 40 * k, 80, planar=(k % 2 == 1))
+        kps += [k1, k2]
+        descs += [d1, d2]
+        pairs.append((2 * k, 2 * k + 1))
+    pairs = np.array(pairs, np.uint32)
+    mo, vo = SiftMatchingOptions(), TwoViewOptions.default()
+    m, v = SiftMatchGPU(0), TwoViewGeometryVerifier(0)
+    try:
+        m.set_images(descs)
+        m.set_keypoints(kps)
+        v.set_images([Camera.make(prior_focal=False)] * len(kps), kps)
+        off, mt = m.match_pairs(pairs, mo)
+        seeds = np.arange(4, dtype=np.uint32) + 70
+        res, inl = v.verify_pairs(pairs, off, mt, vo, seeds)
+        geos = [(int(r["config"]), r["F"].reshape(3, 3), r["H"].reshape(3, 3)) for r in res]
+        off_h, m_h = m.match_guided_pairs(pairs, geos, mo)
+        dev = torch.device("cuda:0")
+        cap = int(sum(len(descs[a]) for a, _ in pairs))
+        pairs_d = torch.from_numpy(pairs.astype(np.int32).reshape(-1)).to(dev)
+        res_d = torch.from_numpy(res.view(np.uint8).reshape(-1).copy()).to(dev)
+        off_d = torch.zeros(5, dtype=torch.int64, device=dev)
+        m_d = torch.zeros(cap * 2, dtype=torch.int32, device=dev)
+        total = m.match_guided_pairs_device(4, pairs_d.data_ptr(), res_d.data_ptr(), vo.min_num_inliers, mo, off_d.data_ptr(),
+                                            m_d.data_ptr(), cap)
+        torch.cuda.synchronize()
+        assert off_d.cpu().numpy().tolist() == off_h.tolist() and total == off_h[-1] > 400
+        assert m_d.cpu().numpy().view(np.uint32).reshape(-1, 2)[:total].tolist() == m_h.tolist()
+    finally:
+        m.close()
+        v.close()
