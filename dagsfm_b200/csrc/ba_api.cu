@@ -338,7 +338,10 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
   memset(&I, 0, sizeof I);
   CgVectors V;
   memset(&V, 0, sizeof V);
-  if (iterative) {
+  // experimental (B2_BA_CAMTERMS=image): the exact path's camera terms summed per image before they touch S
+  bool camterms_image = false;
+  if (const char* e = getenv("B2_BA_CAMTERMS")) camterms_image = !iterative && strcmp(e, "image") == 0 && n_obs > 0 && n_obs < 0x7fffffffLL;
+  if (iterative || camterms_image) {
     // observations grouped by image (counting sort of the point-major order) for the image-major pass
     std::vector<int64_t> img_start(n_img + 1, 0);
     for (int64_t o = 0; o < n_obs; ++o) img_start[pr->obs_image[o] + 1]++;
@@ -364,6 +367,9 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
     B2_TRY(dev_upload(h, &d_blk_first, blk_first.data(), (size_t)D));
     B2_TRY(dev_upload(h, &d_blk_size, blk_size.data(), (size_t)D));
     I.img_start = d_img_start; I.img_obs = d_img_obs; I.blk_first = d_blk_first; I.blk_size = d_blk_size;
+    B2_CUDA(cudaStreamSynchronize(s));  // the host vectors above go out of scope
+  }
+  if (iterative) {
     B2_TRY(dev_alloc(h, &I.tp, (size_t)NP * 3));
     B2_TRY(dev_alloc(h, &I.zp, (size_t)NP * 3));
     B2_TRY(dev_alloc(h, &I.lm_c, (size_t)D));
@@ -376,7 +382,6 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
     B2_TRY(dev_alloc(h, &V.q, (size_t)D));
     B2_TRY(dev_alloc(h, &V.tmp, (size_t)D));
     B2_TRY(dev_alloc(h, &V.partial, (size_t)2 * kBaIterMaxPartials));
-    B2_CUDA(cudaStreamSynchronize(s));  // the host vectors above go out of scope
   }
   if (n_obs == 0 && !h->allreduce) return B2_OK;  // BundleAdjuster::Solve returns false: nothing to do
 
@@ -484,7 +489,8 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
       schur_launches += 2;
     } else {
     B2_CUDA(cudaEventRecord(h->ev[2], s));
-    if (!pair_major) B2_CUDA(ba_launch_camera_terms(P, s));  // folded into the (i, i) blocks in pair-major mode
+    if (!pair_major && camterms_image) B2_CUDA(bai_launch_camera_terms_image(P, I, s));
+    else if (!pair_major) B2_CUDA(ba_launch_camera_terms(P, s));  // folded into the (i, i) blocks in pair-major mode
     if (pair_major)
       B2_CUDA(ba_launch_schur_pm(P, radius, min_diag, max_diag, n_img, pm_start, pm_tuples, pm_W, pm_Y, h->n_sm, s));
     else

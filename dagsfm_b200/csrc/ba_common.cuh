@@ -101,6 +101,7 @@ struct BaIter {
 };
 cudaError_t bai_launch_point_prepare(const BaDev& P, const BaIter& I, double radius, double min_diag, double max_diag, cudaStream_t s);
 cudaError_t bai_launch_rhs(const BaDev& P, const BaIter& I, cudaStream_t s);
+cudaError_t bai_launch_camera_terms_image(const BaDev& P, const BaIter& I, cudaStream_t s);
 cudaError_t bai_launch_cam_diag(const BaDev& P, const BaIter& I, double radius, double min_diag, double max_diag, cudaStream_t s);
 cudaError_t bai_launch_precond(const BaDev& P, const BaIter& I, cudaStream_t s);
 cudaError_t bai_launch_precond_invert(const BaDev& P, const BaIter& I, cudaStream_t s);

@@ -325,6 +325,71 @@ __global__ void precond_invert_kernel(BaDev P, BaIter I) {
     for (int c = 0; c < n; ++c) I.M[KI * (f + r) + c] = Inv[r][c];
 }
 
+
+// ------------------------------------------------------------------ camera terms, image-major (experimental)
+// B2_BA_CAMTERMS=image on the exact path: what camera_terms_kernel adds with ~75 FP64 atomics per observation
+// (U = Jc'Jc into S, g_c, diag_c), summed per image first -- one block per image over the same image-major permutation
+// the iterative solver uses, each thread keeping the 55 unique entries of its 10 x 10 block plus g and the diagonal in
+// registers -- and written once per image: plain stores for the pose-pose entries (this block owns them), one atomic per
+// entry that involves the (possibly shared) intrinsics.  The production kernel stays the default until this is timed.
+template <class J>
+__global__ void __launch_bounds__(kImageThreads) camera_terms_image_kernel(BaDev P, BaIter I) {
+  constexpr int KI = J::kKI, NC = J::kNC, NU = NC * (NC + 1) / 2, NV = NU + 2 * NC;
+  __shared__ double sh[kImageThreads / 32][NV];
+  const int i = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cm = P.img_cam[i];
+  __shared__ int scol[NC];
+  if (tid < NC) scol[tid] = (tid < 6) ? P.pose_col[6 * i + tid] : P.intr_col[KI * cm + (tid - 6)];
+  __syncthreads();
+  double acc[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) acc[k] = 0.0;
+  const int64_t s0 = I.img_start[i], s1 = I.img_start[i + 1];
+  for (int64_t s = s0 + tid; s < s1; s += kImageThreads) {
+    J e;
+    load_block(jac<J>(P) + I.img_obs[s], &e);
+    int u = 0;
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      const double a0 = e.Jc[k], a1 = e.Jc[NC + k];
+#pragma unroll
+      for (int l = k; l < NC; ++l) acc[u++] += a0 * e.Jc[l] + a1 * e.Jc[NC + l];
+      acc[NU + k] += a0 * e.r[0] + a1 * e.r[1];
+      acc[NU + NC + k] += a0 * a0 + a1 * a1;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NV; ++k) acc[k] = warp_sum(acc[k]);
+  if (lane == 0)
+#pragma unroll
+    for (int k = 0; k < NV; ++k) sh[warp][k] = acc[k];
+  __syncthreads();
+  const int64_t D = P.D;
+  for (int v = tid; v < NV; v += kImageThreads) {
+    double t = 0;
+#pragma unroll
+    for (int w = 0; w < kImageThreads / 32; ++w) t += sh[w][v];
+    if (v < NU) {  // entry (k, l), k <= l, of the image's block: index v in row-major upper-triangular order
+      int k = 0, rem = v;
+      while (rem >= NC - k) { rem -= NC - k; ++k; }
+      const int l = k + rem;
+      const int ck = scol[k], cl = scol[l];
+      if (ck < 0 || cl < 0) continue;
+      const int r = min(ck, cl), c = max(ck, cl);
+      if (l < 6) P.S[r * D + c] += t;  // pose x pose: only this block touches the entry (the Schur kernel runs afterwards)
+      else atomicAdd(P.S + r * D + c, t);
+    } else {
+      const int k = (v - NU) % NC;
+      const int c = scol[k];
+      if (c < 0) continue;
+      double* dst = (v - NU < NC) ? P.g_c : P.diag_c;
+      if (k < 6) dst[c] += t;
+      else atomicAdd(dst + c, t);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ per CG iteration
 // x -> z_p = V^-1 sum_a Jp_a' (Jc_a x)   (eight lanes per point)
 template <class J>
@@ -449,6 +514,12 @@ cudaError_t bai_launch_rhs(const BaDev& P, const BaIter& I, cudaStream_t s) {
   if (P.n_img == 0 || P.n_obs == 0) return cudaSuccess;
   if (P.wide) bit::image_pass_kernel<1, ObsJacW><<<P.n_img, bit::kImageThreads, 0, s>>>(P, I, nullptr, I.tp, P.rhs, P.g_c, P.diag_c);
   else bit::image_pass_kernel<1, ObsJac><<<P.n_img, bit::kImageThreads, 0, s>>>(P, I, nullptr, I.tp, P.rhs, P.g_c, P.diag_c);
+  return cudaGetLastError();
+}
+cudaError_t bai_launch_camera_terms_image(const BaDev& P, const BaIter& I, cudaStream_t s) {
+  if (P.n_img == 0 || P.n_obs == 0) return cudaSuccess;
+  if (P.wide) bit::camera_terms_image_kernel<ObsJacW><<<P.n_img, bit::kImageThreads, 0, s>>>(P, I);
+  else bit::camera_terms_image_kernel<ObsJac><<<P.n_img, bit::kImageThreads, 0, s>>>(P, I);
   return cudaGetLastError();
 }
 cudaError_t bai_launch_cam_diag(const BaDev& P, const BaIter& I, double radius, double min_diag, double max_diag, cudaStream_t s) {

@@ -21,6 +21,8 @@ for v in 0 1; do
   B2_VERIFY_VARIANT=$v B2_VERIFY_PROFILE=1 python bench.py --pairs 20000 --ba "" --no-cpu --no-e2e --steps 3 --warmup 3 \
     > gpurun_out/ab_verify_$v.json 2> gpurun_out/ab_verify_$v.err
 done
+B2_BA_CAMTERMS=image python bench.py --pairs 20000 --verify-pairs 0 --no-cpu --no-e2e --steps 3 --warmup 3 \
+  > gpurun_out/ab_ba_camterms_image.json 2> gpurun_out/ab_ba_camterms_image.err
 for s in atomics blocks; do
   B2_BA_SCHUR=$s python bench.py --pairs 20000 --verify-pairs 0 --no-cpu --no-e2e --steps 3 --warmup 3 \
     > gpurun_out/ab_ba_$s.json 2> gpurun_out/ab_ba_$s.err

@@ -470,3 +470,26 @@ def test_mean_reprojection_error_metric(emu):
         assert adj.ComputeMeanReprojectionError(p)[0] == 0.0
     finally:
         adj.close()
+
+
+@pytest.mark.parametrize("kw", [
+    dict(n_img=6, n_pts=60, track_len=4, seed=5),
+    dict(n_img=8, n_pts=80, track_len=5, seed=3, shared_camera=True),      # intrinsics shared: atomics across image blocks
+    dict(n_img=150, n_pts=40, track_len=3, seed=8),                        # images without observations
+    dict(n_img=8, n_pts=90, track_len=4, seed=7, n_const_pts=20),
+    dict(n_img=8, n_pts=80, track_len=4, seed=3, camera=(4, [1180.0, 1210.0, 505.0, 495.0, -0.12, 0.03, 0.001, -0.0015]), noise_px=0.5),
+])
+def test_image_major_camera_terms_variant(emu, kw, monkeypatch):
+    """B2_BA_CAMTERMS=image (exact path): U = Jc'Jc, g_c and diag_c summed per image in registers and written once per
+    image instead of ~75 atomics per observation.  Same LM path as the production kernel and the oracle."""
+    p_v = make_ba_problem(**kw)
+    p_ref, p_cpu = copy_problem(p_v), copy_problem(p_v)
+    s_ref = emu_solve(emu, p_ref, linear_solver_type=1)
+    monkeypatch.setenv("B2_BA_CAMTERMS", "image")
+    s_v = emu_solve(emu, p_v, linear_solver_type=1)
+    monkeypatch.delenv("B2_BA_CAMTERMS")
+    s_cpu = orc.ba_solve(p_cpu)
+    for s in (s_ref, s_cpu):
+        assert (s_v.num_successful_steps, s_v.num_unsuccessful_steps) == (s.num_successful_steps, s.num_unsuccessful_steps)
+        assert s_v.final_cost == pytest.approx(s.final_cost, rel=1e-9)
+    assert np.abs(p_v["xyz"] - p_ref["xyz"]).max() < 1e-8 and np.abs(p_v["qvec"] - p_ref["qvec"]).max() < 1e-10
