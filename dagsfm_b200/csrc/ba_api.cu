@@ -634,11 +634,18 @@ int b2_ba_create(int device, b2_ba** out) {
   b2_ba* h = new b2_ba();
   h->device = device;
   h->n_sm = prop.multiProcessorCount;
-  B2_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-  if (cusolverDnCreate(&h->solver) != CUSOLVER_STATUS_SUCCESS) return set_error(B2_ERR_CUDA, "cusolverDnCreate failed");
-  cusolverDnSetStream(h->solver, h->stream);
-  if (cusolverDnCreateParams(&h->solver_params) != CUSOLVER_STATUS_SUCCESS) return set_error(B2_ERR_CUDA, "cusolverDnCreateParams failed");
-  for (auto& e : h->ev) B2_CUDA(cudaEventCreate(&e));
+  const int rc = [&]() -> int {
+    B2_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    if (cusolverDnCreate(&h->solver) != CUSOLVER_STATUS_SUCCESS) return set_error(B2_ERR_CUDA, "cusolverDnCreate failed");
+    cusolverDnSetStream(h->solver, h->stream);
+    if (cusolverDnCreateParams(&h->solver_params) != CUSOLVER_STATUS_SUCCESS) return set_error(B2_ERR_CUDA, "cusolverDnCreateParams failed");
+    for (auto& e : h->ev) B2_CUDA(cudaEventCreate(&e));
+    return B2_OK;
+  }();
+  if (rc != B2_OK) {  // a half-built handle is released here, never handed out
+    b2_ba_destroy(h);
+    return rc;
+  }
   *out = h;
   return B2_OK;
 }
@@ -646,12 +653,12 @@ int b2_ba_create(int device, b2_ba** out) {
 int b2_ba_destroy(b2_ba* h) {
   if (!h) return B2_OK;
   cudaSetDevice(h->device);
-  cudaStreamSynchronize(h->stream);
+  if (h->stream) cudaStreamSynchronize(h->stream);
   free_all(h);
   if (h->solver_params) cusolverDnDestroyParams(h->solver_params);
   if (h->solver) cusolverDnDestroy(h->solver);
   for (auto e : h->ev) if (e) cudaEventDestroy(e);
-  cudaStreamDestroy(h->stream);
+  if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return B2_OK;
 }

@@ -438,11 +438,18 @@ int b2_match_create(int device, b2_matcher** out) {
   b2_matcher* m = new b2_matcher();
   m->device = device;
   m->n_sm = prop.multiProcessorCount;
-  B2_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
-  B2_CUDA(cudaMalloc(&m->d_total_items, sizeof(uint32_t)));
-  B2_CUDA(cudaMalloc(&m->d_cand_count, sizeof(unsigned int)));
-  B2_CUDA(cudaMalloc(&m->d_carry, sizeof(int64_t)));
-  B2_CUDA(cudaMalloc(&m->d_err, sizeof(int)));
+  const int rc = [&]() -> int {
+    B2_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    B2_CUDA(cudaMalloc(&m->d_total_items, sizeof(uint32_t)));
+    B2_CUDA(cudaMalloc(&m->d_cand_count, sizeof(unsigned int)));
+    B2_CUDA(cudaMalloc(&m->d_carry, sizeof(int64_t)));
+    B2_CUDA(cudaMalloc(&m->d_err, sizeof(int)));
+    return B2_OK;
+  }();
+  if (rc != B2_OK) {  // a half-built handle is released here, never handed out
+    b2_match_destroy(m);
+    return rc;
+  }
   *out = m;
   return B2_OK;
 }
@@ -450,7 +457,7 @@ int b2_match_create(int device, b2_matcher** out) {
 int b2_match_destroy(b2_matcher* m) {
   if (!m) return B2_OK;
   cudaSetDevice(m->device);
-  cudaStreamSynchronize(m->stream);
+  if (m->stream) cudaStreamSynchronize(m->stream);
   m->store.release();
   m->slots.release();
   auto fr = [](void* p) { if (p) cudaFree(p); };
@@ -458,8 +465,8 @@ int b2_match_destroy(b2_matcher* m) {
   fr(m->d_nitems); fr(m->d_item_start); fr(m->d_total_items); fr(m->d_meta); fr(m->d_counts);
   fr(m->d_items); fr(m->d_midx); fr(m->d_cands); fr(m->d_cand_count); fr(m->d_carry); fr(m->d_err);
   fr(m->d_pairs); fr(m->d_offsets); fr(m->d_matches); fr(m->d_item_pair); fr(m->d_geoms);
-  for (auto e : m->ev) cudaEventDestroy(e);
-  cudaStreamDestroy(m->stream);
+  for (auto e : m->ev) if (e) cudaEventDestroy(e);
+  if (m->stream) cudaStreamDestroy(m->stream);
   delete m;
   return B2_OK;
 }

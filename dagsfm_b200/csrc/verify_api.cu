@@ -190,12 +190,19 @@ int b2_verify_create(int device, b2_verifier** out) {
   b2_verifier* v = new b2_verifier();
   v->device = device;
   v->n_sm = prop.multiProcessorCount;
-  B2_CUDA(cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking));
-  B2_CUDA(cudaMalloc(&v->d_counter, sizeof(unsigned long long)));
-  B2_CUDA(cudaMalloc(&v->d_err, sizeof(int)));
-  B2_CUDA(cudaMalloc(&v->d_maxm, sizeof(int)));
-  B2_CUDA(cudaEventCreate(&v->ev0));
-  B2_CUDA(cudaEventCreate(&v->ev1));
+  const int rc = [&]() -> int {
+    B2_CUDA(cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking));
+    B2_CUDA(cudaMalloc(&v->d_counter, sizeof(unsigned long long)));
+    B2_CUDA(cudaMalloc(&v->d_err, sizeof(int)));
+    B2_CUDA(cudaMalloc(&v->d_maxm, sizeof(int)));
+    B2_CUDA(cudaEventCreate(&v->ev0));
+    B2_CUDA(cudaEventCreate(&v->ev1));
+    return B2_OK;
+  }();
+  if (rc != B2_OK) {  // a half-built handle is released here, never handed out
+    b2_verify_destroy(v);
+    return rc;
+  }
   *out = v;
   return B2_OK;
 }
@@ -203,13 +210,13 @@ int b2_verify_create(int device, b2_verifier** out) {
 int b2_verify_destroy(b2_verifier* v) {
   if (!v) return B2_OK;
   cudaSetDevice(v->device);
-  cudaStreamSynchronize(v->stream);
+  if (v->stream) cudaStreamSynchronize(v->stream);
   auto fr = [](void* p) { if (p) cudaFree(p); };
   fr(v->d_cams); fr(v->d_img_off); fr(v->d_xy); fr(v->d_nxy); fr(v->d_scratch); fr(v->d_counter);
   fr(v->d_err); fr(v->d_maxm); fr(v->d_stage); fr(v->d_angles);
-  cudaEventDestroy(v->ev0);
-  cudaEventDestroy(v->ev1);
-  cudaStreamDestroy(v->stream);
+  if (v->ev0) cudaEventDestroy(v->ev0);
+  if (v->ev1) cudaEventDestroy(v->ev1);
+  if (v->stream) cudaStreamDestroy(v->stream);
   delete v;
   return B2_OK;
 }
@@ -226,11 +233,13 @@ int b2_verify_set_images(b2_verifier* v, int32_t n_images, const b2_camera* cams
   auto fr = [](void* p) { if (p) cudaFree(p); };
   fr(v->d_cams); fr(v->d_img_off); fr(v->d_xy); fr(v->d_nxy);
   v->d_cams = nullptr; v->d_img_off = nullptr; v->d_xy = nullptr; v->d_nxy = nullptr;
+  v->n_images = 0;  // the store stays empty (every pair is rejected) unless this call completes
+  v->n_pts_total = 0;
   std::vector<int64_t> off(n_images + 1, 0);
   for (int32_t i = 0; i < n_images; ++i) off[i + 1] = off[i] + n_pts[i];
-  v->n_images = n_images;
-  v->n_pts_total = off[n_images];
-  const size_t np = (size_t)std::max<int64_t>(v->n_pts_total, 1);
+  for (int32_t i = 0; i < n_images; ++i)
+    if (n_pts[i] > 0 && !xy[i]) return set_error(B2_ERR_INVALID, "NULL keypoint pointer");
+  const size_t np = (size_t)std::max<int64_t>(off[n_images], 1);
   B2_CUDA(cudaMalloc(&v->d_cams, std::max<size_t>(1, n_images) * sizeof(b2_camera)));
   B2_CUDA(cudaMalloc(&v->d_img_off, (n_images + 1) * sizeof(int64_t)));
   B2_CUDA(cudaMalloc(&v->d_xy, np * 16));
@@ -239,7 +248,11 @@ int b2_verify_set_images(b2_verifier* v, int32_t n_images, const b2_camera* cams
   // Keypoints are normalised with the camera's own model.  The array the verification kernels keep afterwards only
   // serves ImageToWorldThreshold / CalibrationMatrix, which depend on the parameter LAYOUT alone: every model with
   // two focal lengths (fx, fy, cx, cy first) is stored there as PINHOLE (id 1), so those kernels need one test.
-  b2_camera* d_true = nullptr;
+  struct Scratch {  // the true-model copy lives for this call only, whichever way it ends
+    b2_camera* p = nullptr;
+    ~Scratch() { if (p) cudaFree(p); }
+  } true_cams;
+  b2_camera*& d_true = true_cams.p;
   std::vector<b2_camera> view(cams, cams + n_images);
   bool any_general = false;
   for (auto& c : view)
@@ -258,16 +271,13 @@ int b2_verify_set_images(b2_verifier* v, int32_t n_images, const b2_camera* cams
   B2_CUDA(cudaMemcpyAsync(v->d_img_off, off.data(), (n_images + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
   for (int32_t i = 0; i < n_images; ++i) {
     if (n_pts[i] == 0) continue;
-    if (!xy[i]) {
-      if (d_true) cudaFree(d_true);
-      return set_error(B2_ERR_INVALID, "NULL keypoint pointer");
-    }
     B2_CUDA(cudaMemcpyAsync(v->d_xy + 2 * off[i], xy[i], (size_t)n_pts[i] * 16, cudaMemcpyHostToDevice, s));
   }
-  B2_CUDA(launch_normalize_points(d_true ? d_true : v->d_cams, v->d_img_off, n_images, v->d_xy, v->d_nxy, v->n_pts_total, s));
+  B2_CUDA(launch_normalize_points(d_true ? d_true : v->d_cams, v->d_img_off, n_images, v->d_xy, v->d_nxy, off[n_images], s));
   count_launches(1);
   B2_CUDA(cudaStreamSynchronize(s));
-  if (d_true) cudaFree(d_true);
+  v->n_images = n_images;
+  v->n_pts_total = off[n_images];
   return B2_OK;
 }
 
@@ -342,6 +352,8 @@ int pose_device(b2_verifier* v, int64_t n_pairs, int64_t total, const uint32_t* 
   int err = 0;
   B2_CUDA(cudaMemcpyAsync(&err, v->d_err, sizeof(int), cudaMemcpyDeviceToHost, s));
   B2_CUDA(cudaStreamSynchronize(s));
+  if (err == 2)
+    return set_error(B2_ERR_INVALID, "inlier list inconsistent with its pair (n_inliers > match count, or a keypoint index out of range)");
   if (err) return set_error(B2_ERR_INVALID, "pair references an image outside the store");
   return B2_OK;
 }

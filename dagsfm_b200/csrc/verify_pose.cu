@@ -283,6 +283,21 @@ __global__ void __launch_bounds__(128) relative_pose_kernel(PoseArgs a) {
     const uint32_t* inl = a.inliers + 2 * a.match_off[p];
     const double2* nx1 = a.nxy + a.img_off[i1];
     const double2* nx2 = a.nxy + a.img_off[i2];
+    {  // the inlier list must fit the pair's slot and name keypoints of the two images (device-chained callers
+       // cannot be checked on the host): an inconsistent pair gets the default pose and raises the error flag
+      bool bad = n < 0 || (int64_t)n > a.match_off[p + 1] - a.match_off[p];
+      if (!bad) {
+        const uint64_t np1 = (uint64_t)(a.img_off[i1 + 1] - a.img_off[i1]), np2 = (uint64_t)(a.img_off[i2 + 1] - a.img_off[i2]);
+        for (int i = lane; i < n; i += 32) bad |= inl[2 * i] >= np1 || inl[2 * i + 1] >= np2;
+      }
+      if (__any_sync(kFull, bad)) {
+        if (lane == 0) {
+          atomicExch(a.err, 2);
+          a.poses[p] = out;
+        }
+        continue;
+      }
+    }
     double Rc[36], tc[12];
     int nc;
     if (cfg == 2 || cfg == 3) {

@@ -215,6 +215,33 @@ def test_relative_pose_rejects_inconsistent_input(ver):
         ver.relative_pose([(0, 1)], [0, 10], res, np.zeros((10, 2), np.uint32))
 
 
+def test_relative_pose_device_flags_inconsistent_inlier_lists(ver):
+    """The device entry cannot be validated on the host: the kernel itself refuses an inlier list longer than the pair's
+    slot or naming a keypoint the image does not have (default pose for that pair, B2_ERR_INVALID for the call), and
+    still serves the consistent pairs of the same call."""
+    from dagsfm_b200.verification import POSE_DTYPE, RESULT_DTYPE, Camera
+    rng = np.random.default_rng(8)
+    p1, p2 = scene(rng, 40, 0, noise=0.0)
+    ver.set_images([Camera.make(prior_focal=True)] * 2, [p1, p2])
+    pairs = np.array([(0, 1), (0, 1), (0, 1)], np.uint32)
+    offs = np.array([0, 40, 80, 120], np.int64)
+    inl = np.tile(np.stack([np.arange(40)] * 2, 1), (3, 1)).astype(np.uint32)
+    res = np.zeros(3, RESULT_DTYPE)
+    res["config"] = 2
+    res["n_inliers"] = [40, 41, 40]                 # pair 1: one more inlier than its slot holds
+    res["E"][:] = np.array([0, 0, 0, 0, 0, -1, 0, 1, 0], float)
+    pose = np.zeros(3, POSE_DTYPE)
+    with pytest.raises(RuntimeError, match="inlier list inconsistent"):
+        ver.relative_pose_device(3, pairs.ctypes.data, offs.ctypes.data, res.ctypes.data, inl.ctypes.data, pose.ctypes.data)
+    res["n_inliers"] = 40
+    inl[85, 1] = len(p2)                             # pair 2: a keypoint index one past the image's last
+    with pytest.raises(RuntimeError, match="inlier list inconsistent"):
+        ver.relative_pose_device(3, pairs.ctypes.data, offs.ctypes.data, res.ctypes.data, inl.ctypes.data, pose.ctypes.data)
+    assert pose["n_points3D"][2] == 0 and (pose["qvec"][2] == 0).all()
+    inl[85, 1] = 5
+    ver.relative_pose_device(3, pairs.ctypes.data, offs.ctypes.data, res.ctypes.data, inl.ctypes.data, pose.ctypes.data)
+
+
 def test_relative_pose_random_geometries(ver):
     """Seeded differential fuzz of relative_pose_kernel against the oracle on hand-made verification results: exact and
     perturbed essential matrices, homographies of planes and of pure rotations, inlier counts around the warp size (the
