@@ -235,8 +235,21 @@ inline void run_block(BlockState& b, unsigned n_threads, const std::function<voi
 }
 
 // kernel launch: blocks sequentially, threads as fibers.  `smem_bytes` backs `extern __shared__`.
+// cudaGetLastError(): a launch whose configuration the driver would refuse (an empty grid or block, more than 1024
+// threads, grid.y / grid.z beyond 65535, more dynamic shared memory than an sm_100 block can opt into) does not run
+// and leaves cudaErrorInvalidConfiguration (9) behind, as on the device
+inline int& last_error() { static thread_local int e = 0; return e; }
+
 inline void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()>& body) {
   static thread_local BlockState state;
+  {
+    const unsigned long long threads = (unsigned long long)block.x * block.y * block.z;
+    if (grid.x == 0 || grid.y == 0 || grid.z == 0 || threads == 0 || threads > 1024 || block.z > 64 ||
+        grid.x > 2147483647u || grid.y > 65535u || grid.z > 65535u || smem_bytes > 232448) {
+      last_error() = 9;
+      return;
+    }
+  }
   std::vector<uint64_t> smem((smem_bytes + 7) / 8 + 1, 0);
   dyn_smem() = smem.data();
   idx().gridDim = grid;
@@ -344,9 +357,11 @@ constexpr unsigned cudaStreamNonBlocking = 1;
 constexpr int cudaFuncAttributeMaxDynamicSharedMemorySize = 8;
 struct cudaDeviceProp { int major = 10, minor = 0, multiProcessorCount = 2; char name[64] = "cuda_emu"; size_t totalGlobalMem = (size_t)64 << 30; };
 
-inline cudaError_t cudaGetLastError() { return cudaSuccess; }
-inline cudaError_t cudaPeekAtLastError() { return cudaSuccess; }
-inline const char* cudaGetErrorString(cudaError_t) { return "cuda_emu: no error"; }
+inline cudaError_t cudaGetLastError() { const int e = cuda_emu::last_error(); cuda_emu::last_error() = 0; return e; }
+inline cudaError_t cudaPeekAtLastError() { return cuda_emu::last_error(); }
+inline const char* cudaGetErrorString(cudaError_t e) {
+  return e == 9 ? "invalid configuration argument (cuda_emu)" : e == 2 ? "out of memory (cuda_emu)" : "cuda_emu: no error";
+}
 inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
 inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) { *p = cudaDeviceProp(); return cudaSuccess; }
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }

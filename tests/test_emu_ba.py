@@ -186,6 +186,18 @@ def test_edge_cases_nothing_to_optimise(emu):
     e["obs_xy"] = e["obs_xy"][:0].copy()
     s = emu_solve(emu, e)
     assert s.num_residuals_reduced == 0 and s.initial_cost == 0.0
+    # every camera-side block constant with the EXACT solver (reduced system of size 0: only the points move), then a
+    # single free intrinsics block and nothing else on the camera side (reduced system of size 2)
+    for free_cam in (False, True):
+        d0 = make_ba_problem(n_img=5, n_pts=40, track_len=3, seed=3, shared_camera=True)
+        d0["pose_const"][:] = 1
+        d0["cam_const"][:] = 0 if free_cam else 1
+        dc = copy_problem(d0)
+        s, sc = emu_solve(emu, d0, linear_solver_type=1), orc.ba_solve(dc, linear_solver=0)
+        assert s.num_effective_parameters_reduced == sc.num_effective_parameters == 3 * 40 + (2 if free_cam else 0)
+        assert (s.num_successful_steps, s.num_unsuccessful_steps) == (sc.num_successful_steps, sc.num_unsuccessful_steps)
+        assert s.final_cost == pytest.approx(sc.final_cost, rel=1e-9) and s.final_cost < s.initial_cost
+        assert np.abs(d0["xyz"] - dc["xyz"]).max() < 1e-7 and (d0["tvec"] == dc["tvec"]).all()
     bad = copy_problem(p)
     bad["obs_img"][0] = 99                                                        # observation of an unknown image
     with pytest.raises(RuntimeError):
