@@ -106,6 +106,8 @@ def build(name: str, sources: list[str], extra: list[str] | None = None) -> Path
     cxx = "/usr/bin/g++" if Path("/usr/bin/g++").exists() else "g++"
     import os
     san = ["-fsanitize=address", "-fno-omit-frame-pointer"] if os.environ.get("B2_EMU_ASAN") else []   # debugging aid
+    if os.environ.get("B2_EMU_UBSAN"):   # misaligned vector loads / stores (a device fault) trap instead of passing silently
+        san += ["-fsanitize=alignment", "-fsanitize-undefined-trap-on-error"]
     cmd = [cxx, "-std=c++17", "-O1", "-g", "-ffp-contract=off", "-U_FORTIFY_SOURCE", "-fno-gnu-unique", "-shared", "-fPIC", "-w"] + san + [
            "-I", str(HERE / "include"), "-I", str(CSRC), "-I", str(ROOT / "include"), "-o", str(lib)] + gen + (extra or [])
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -49,11 +49,13 @@ struct dim3 {
   dim3() {}
   dim3(unsigned X, unsigned Y = 1, unsigned Z = 1) : x(X), y(Y), z(Z) {}
 };
-struct double2 { double x, y; };
-struct float2 { float x, y; };
-struct uint4 { unsigned x, y, z, w; };
-struct int4 { int x, y, z, w; };
-struct int2 { int x, y; };
+// alignment as in vector_types.h: a misaligned vector access faults on the device; here B2_EMU_UBSAN=1 (build_emu.py)
+// turns it into a trap
+struct alignas(16) double2 { double x, y; };
+struct alignas(8) float2 { float x, y; };
+struct alignas(16) uint4 { unsigned x, y, z, w; };
+struct alignas(16) int4 { int x, y, z, w; };
+struct alignas(8) int2 { int x, y; };
 inline int2 make_int2(int x, int y) { return int2{x, y}; }
 inline double2 make_double2(double x, double y) { return double2{x, y}; }
 inline float2 make_float2(float x, float y) { return float2{x, y}; }
