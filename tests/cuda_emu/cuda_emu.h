@@ -110,7 +110,15 @@ struct Fiber {
   bool done = false;
   int wait_kind = 0;  // 0 runnable, 1 waiting at the block barrier, 2 waiting at its warp barrier
   unsigned tid = 0;
+  int site = 0;        // which warp-synchronous call of the source the fiber waits in (see Site)
+  const char* site_file = "";
+  int site_line = 0;
 };
+
+// The source location of a warp-synchronous intrinsic.  Lanes released together must wait in the SAME call: lanes
+// that pair a shuffle of one statement with a ballot (or a shuffle) of another exchange garbage on the device too, and
+// a host build would hide it.
+struct Site { const char* file; int line; int id; };
 
 struct BlockState {
   std::vector<Fiber> fibers;
@@ -154,9 +162,12 @@ inline int alive_in_block(BlockState* b) {
   return n;
 }
 // Blocks the calling fiber until every live fiber of its warp has arrived.
-inline void warp_barrier() {
+inline void warp_barrier(Site at = Site{"", 0, 0}, int phase = 0) {
   BlockState* b = cur();
   Fiber& f = b->fibers[b->current];
+  f.site = at.id * 2 + phase;
+  f.site_file = at.file;
+  f.site_line = at.line;
   f.wait_kind = 2;
   b->warp_arrived[f.tid / 32] += 1;
   yield_to_scheduler();
@@ -219,8 +230,19 @@ inline void run_block(BlockState& b, unsigned n_threads, const std::function<voi
       const int alive = alive_in_warp(&b, w);
       if (b.warp_arrived[w] > 0 && b.warp_arrived[w] >= alive) {
         b.warp_arrived[w] = 0;
+        const Fiber* first = nullptr;
         for (unsigned t = w * 32; t < std::min(n_threads, w * 32 + 32); ++t)
-          if (!b.fibers[t].done && b.fibers[t].wait_kind == 2) { b.fibers[t].wait_kind = 0; progressed = true; }
+          if (!b.fibers[t].done && b.fibers[t].wait_kind == 2) {
+            const Fiber& g = b.fibers[t];
+            if (!first) first = &g;
+            if (g.site != first->site) {
+              std::fprintf(stderr, "cuda_emu: lanes %u and %u of warp %u meet in different warp-synchronous calls (%s:%d and %s:%d)\n",
+                           first->tid % 32, g.tid % 32, w, first->site_file, first->site_line, g.site_file, g.site_line);
+              std::abort();
+            }
+            b.fibers[t].wait_kind = 0;
+            progressed = true;
+          }
       }
     }
     if (b.block_arrived > 0 && b.block_arrived >= alive_in_block(&b)) {
@@ -274,54 +296,65 @@ inline void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function
 
 // ------------------------------------------------------------------ synchronisation / warp intrinsics
 inline void __syncthreads() { cuda_emu::block_barrier(); }
-inline void __syncwarp(unsigned = 0xffffffffu) { cuda_emu::warp_barrier(); }
-
 namespace cuda_emu {
+struct SyncWarp {  // __syncwarp() and __syncwarp(mask): a functor, so the macro below needs no comma tricks
+  Site at;
+  void operator()(unsigned = 0xffffffffu) const { warp_barrier(at); }
+};
 template <class T>
-inline T warp_exchange(T v, int src_lane_of_me) {  // every live lane publishes v, then reads the lane it asks for
+inline T warp_exchange(Site at, T v, int src_lane_of_me) {  // every live lane publishes v, then reads the lane it asks for
   static_assert(sizeof(T) <= 8, "warp_exchange moves at most 64 bits");
   BlockState* b = cur();
   const unsigned tid = b->fibers[b->current].tid;
   uint64_t bits = 0;
   std::memcpy(&bits, &v, sizeof(T));
   b->slot[tid] = bits;
-  warp_barrier();
+  warp_barrier(at, 0);
   const unsigned base = tid / 32 * 32;
   unsigned src = base + (unsigned)(src_lane_of_me & 31);
   if (src >= b->n_threads) src = tid;
   const uint64_t got = b->slot[src];
-  warp_barrier();  // nobody overwrites its slot before everyone has read
+  warp_barrier(at, 1);  // nobody overwrites its slot before everyone has read
   T out;
   std::memcpy(&out, &got, sizeof(T));
   return out;
 }
-}  // namespace cuda_emu
-
-template <class T> inline T __shfl_sync(unsigned, T v, int src, int = 32) { return cuda_emu::warp_exchange(v, src); }
-template <class T> inline T __shfl_xor_sync(unsigned, T v, int mask, int = 32) {
-  return cuda_emu::warp_exchange(v, (int)(threadIdx.x & 31) ^ mask);
+template <class T> inline T shfl_at(Site at, unsigned, T v, int src, int = 32) { return warp_exchange(at, v, src); }
+template <class T> inline T shfl_xor_at(Site at, unsigned, T v, int mask, int = 32) {
+  return warp_exchange(at, v, (int)(threadIdx.x & 31) ^ mask);
 }
-template <class T> inline T __shfl_up_sync(unsigned, T v, unsigned d, int = 32) {
+template <class T> inline T shfl_up_at(Site at, unsigned, T v, unsigned d, int = 32) {
   const int lane = (int)(threadIdx.x & 31);
-  return cuda_emu::warp_exchange(v, lane >= (int)d ? lane - (int)d : lane);
+  return warp_exchange(at, v, lane >= (int)d ? lane - (int)d : lane);
 }
-template <class T> inline T __shfl_down_sync(unsigned, T v, unsigned d, int = 32) {
+template <class T> inline T shfl_down_at(Site at, unsigned, T v, unsigned d, int = 32) {
   const int lane = (int)(threadIdx.x & 31);
-  return cuda_emu::warp_exchange(v, lane + (int)d < 32 ? lane + (int)d : lane);
+  return warp_exchange(at, v, lane + (int)d < 32 ? lane + (int)d : lane);
 }
-inline unsigned __ballot_sync(unsigned, int pred) {
-  cuda_emu::BlockState* b = cuda_emu::cur();
+inline unsigned ballot_at(Site at, unsigned, int pred) {
+  BlockState* b = cur();
   const unsigned tid = b->fibers[b->current].tid;
   b->slot[tid] = pred ? 1u : 0u;
-  cuda_emu::warp_barrier();
+  warp_barrier(at, 0);
   unsigned m = 0;
   const unsigned base = tid / 32 * 32;
   for (unsigned l = 0; l < 32 && base + l < b->n_threads; ++l)
     if (!b->fibers[base + l].done && b->slot[base + l]) m |= 1u << l;
-  cuda_emu::warp_barrier();
+  warp_barrier(at, 1);
   return m;
 }
-inline int __any_sync(unsigned m, int p) { return __ballot_sync(m, p) != 0; }
+inline int any_at(Site at, unsigned m, int p) { return ballot_at(at, m, p) != 0; }
+}  // namespace cuda_emu
+
+// every textual call gets its own Site (__COUNTER__ is unique within a translation unit; 0 is "untagged")
+#define CUDA_EMU_SITE (cuda_emu::Site{__FILE__, __LINE__, __COUNTER__ + 1})
+#define __syncwarp(...) (cuda_emu::SyncWarp{CUDA_EMU_SITE})(__VA_ARGS__)
+#define __shfl_sync(...) cuda_emu::shfl_at(CUDA_EMU_SITE, __VA_ARGS__)
+#define __shfl_xor_sync(...) cuda_emu::shfl_xor_at(CUDA_EMU_SITE, __VA_ARGS__)
+#define __shfl_up_sync(...) cuda_emu::shfl_up_at(CUDA_EMU_SITE, __VA_ARGS__)
+#define __shfl_down_sync(...) cuda_emu::shfl_down_at(CUDA_EMU_SITE, __VA_ARGS__)
+#define __ballot_sync(...) cuda_emu::ballot_at(CUDA_EMU_SITE, __VA_ARGS__)
+#define __any_sync(...) cuda_emu::any_at(CUDA_EMU_SITE, __VA_ARGS__)
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __ffs(int v) { return __builtin_ffs(v); }
 inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
