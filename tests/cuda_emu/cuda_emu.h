@@ -212,9 +212,13 @@ inline void run_block(BlockState& b, unsigned n_threads, const std::function<voi
     for (int r = 0; r < 6; ++r) *--sp = nullptr;
     f.sp = sp;
   }
+  // B2_EMU_SCHED=reverse runs the threads of a block (and the blocks of a grid) last to first: results that depend on
+  // the order in which warps or blocks happen to run -- a missing barrier, a read of another block's output -- change
+  static const bool reverse = [] { const char* e = std::getenv("B2_EMU_SCHED"); return e && std::strcmp(e, "reverse") == 0; }();
   for (;;) {
     bool progressed = false, any_alive = false;
-    for (unsigned t = 0; t < n_threads; ++t) {
+    for (unsigned k = 0; k < n_threads; ++k) {
+      const unsigned t = reverse ? n_threads - 1 - k : k;
       Fiber& f = b.fibers[t];
       if (f.done) continue;
       any_alive = true;
@@ -278,9 +282,11 @@ inline void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function
   dyn_smem() = smem.data();
   idx().gridDim = grid;
   idx().blockDim = block;
-  for (unsigned bz = 0; bz < grid.z; ++bz)
-    for (unsigned by = 0; by < grid.y; ++by)
-      for (unsigned bx = 0; bx < grid.x; ++bx) {
+  static const bool reverse = [] { const char* e = std::getenv("B2_EMU_SCHED"); return e && std::strcmp(e, "reverse") == 0; }();
+  for (unsigned kz = 0; kz < grid.z; ++kz)
+    for (unsigned ky = 0; ky < grid.y; ++ky)
+      for (unsigned kx = 0; kx < grid.x; ++kx) {
+        const unsigned bx = reverse ? grid.x - 1 - kx : kx, by = reverse ? grid.y - 1 - ky : ky, bz = reverse ? grid.z - 1 - kz : kz;
         idx().blockIdx.x = bx; idx().blockIdx.y = by; idx().blockIdx.z = bz;
         run_block(state, block.x * block.y * block.z, body);
       }
