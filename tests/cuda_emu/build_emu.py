@@ -95,6 +95,9 @@ def build(name: str, sources: list[str], extra: list[str] | None = None) -> Path
     # every "device" allocation of the emulated libraries ends at an inaccessible page: an out-of-bounds access
     # fails at the access (with a native backtrace) instead of depending on the heap layout
     os.environ.setdefault("B2_EMU_GUARD", "1")
+    # ... and is inaccessible to host code outside kernels / cudaMemcpy / cuSOLVER calls: a host dereference of a device
+    # pointer (which the device would punish) faults here too
+    os.environ.setdefault("B2_EMU_DEVMEM", "1")
     OUT.mkdir(exist_ok=True)
     gen = []
     for s in sources:
@@ -102,6 +105,11 @@ def build(name: str, sources: list[str], extra: list[str] | None = None) -> Path
         g = OUT / (p.stem + "_emu.cc")
         g.write_text(f'#line 1 "{p}"\n' + rewrite(p.read_text()))
         gen.append(str(g))
+    # test hooks that stand in for device-side code (the gloo all-reduce of the multi-rank tests works on the emulated
+    # device buffer directly) open the same window a kernel gets when B2_EMU_DEVMEM=1 protects device memory from host code
+    exp = OUT / f"{name}_exports_emu.cc"
+    exp.write_text('#include <cuda_runtime.h>\nextern "C" void cuda_emu_device_window(int on) { cuda_emu::device_access(on != 0); }\n')
+    gen.append(str(exp))
     lib = OUT / f"libemu_{name}.so"
     cxx = "/usr/bin/g++" if Path("/usr/bin/g++").exists() else "g++"
     import os

@@ -263,6 +263,14 @@ inline void run_block(BlockState& b, unsigned n_threads, const std::function<voi
 }
 
 // kernel launch: blocks sequentially, threads as fibers.  `smem_bytes` backs `extern __shared__`.
+// B2_EMU_DEVMEM=1 (with guarded allocations): "device" memory is readable and writable only while a kernel, a cudaMemcpy /
+// cudaMemset or a cuSOLVER call runs; host code that dereferences a device pointer faults as it would on the device
+inline void device_access(bool on);
+struct DeviceWindow {
+  DeviceWindow() { device_access(true); }
+  ~DeviceWindow() { device_access(false); }
+};
+
 // cudaGetLastError(): a launch whose configuration the driver would refuse (an empty grid or block, more than 1024
 // threads, grid.y / grid.z beyond 65535, more dynamic shared memory than an sm_100 block can opt into) does not run
 // and leaves cudaErrorInvalidConfiguration (9) behind, as on the device
@@ -283,6 +291,7 @@ inline void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function
   idx().gridDim = grid;
   idx().blockDim = block;
   static const bool reverse = [] { const char* e = std::getenv("B2_EMU_SCHED"); return e && std::strcmp(e, "reverse") == 0; }();
+  DeviceWindow window;
   for (unsigned kz = 0; kz < grid.z; ++kz)
     for (unsigned ky = 0; ky < grid.y; ++ky)
       for (unsigned kx = 0; kx < grid.x; ++kx) {
@@ -435,6 +444,18 @@ inline std::unordered_map<void*, std::pair<void*, size_t>>& guard_registry() {
   static std::unordered_map<void*, std::pair<void*, size_t>> r;
   return r;
 }
+inline bool devmem_mode() {
+  static const bool on = std::getenv("B2_EMU_DEVMEM") != nullptr && std::getenv("B2_EMU_GUARD") != nullptr;
+  return on;
+}
+inline int& device_depth() { static int d = 0; return d; }
+inline void device_access(bool on) {
+  if (!devmem_mode()) return;
+  int& d = device_depth();
+  if (on ? d++ == 0 : --d == 0)
+    for (auto& kv : guard_registry())
+      mprotect(kv.second.first, kv.second.second - 4096, on ? PROT_READ | PROT_WRITE : PROT_NONE);
+}
 inline void* guarded_alloc(size_t n) {
   const size_t page = 4096, body = (n + 15) / 16 * 16, span = (body + page - 1) / page * page + page;
   char* base = (char*)mmap(nullptr, span, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
@@ -442,6 +463,7 @@ inline void* guarded_alloc(size_t n) {
   mprotect(base + span - page, page, PROT_NONE);
   void* p = base + span - page - body;   // the allocation ends where the inaccessible page begins
   guard_registry()[p] = {base, span};
+  if (devmem_mode() && device_depth() == 0) mprotect(base, span - page, PROT_NONE);
   return p;
 }
 inline void guarded_free(void* p) {
@@ -460,9 +482,17 @@ inline cudaError_t cudaFree(void* p) {
   if (cuda_emu::guard_mode()) cuda_emu::guarded_free(p); else std::free(p);
   return cudaSuccess;
 }
-inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { if (n) std::memmove(d, s, n); return cudaSuccess; }
+inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) {
+  cuda_emu::DeviceWindow window;
+  if (n) std::memmove(d, s, n);
+  return cudaSuccess;
+}
 inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind k, cudaStream_t = nullptr) { return cudaMemcpy(d, s, n, k); }
-inline cudaError_t cudaMemset(void* d, int v, size_t n) { if (n) std::memset(d, v, n); return cudaSuccess; }
+inline cudaError_t cudaMemset(void* d, int v, size_t n) {
+  cuda_emu::DeviceWindow window;
+  if (n) std::memset(d, v, n);
+  return cudaSuccess;
+}
 inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = nullptr) { return cudaMemset(d, v, n); }
 inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = nullptr; return cudaSuccess; }
 inline cudaError_t cudaStreamCreate(cudaStream_t* s) { *s = nullptr; return cudaSuccess; }
@@ -498,6 +528,7 @@ inline cusolverStatus_t cusolverDnXpotrf_bufferSize(cusolverDnHandle_t, cusolver
 // A = L L^T, lower triangle of a column-major n x n matrix, in place; info = 0 or the failing column (1-based).
 inline cusolverStatus_t cusolverDnXpotrf(cusolverDnHandle_t, cusolverDnParams_t, cublasFillMode_t uplo, int64_t n, cudaDataType,
                                          void* Av, int64_t lda, cudaDataType, void*, size_t, void*, size_t, int* info) {
+  cuda_emu::DeviceWindow window;
   double* A = (double*)Av;
   *info = 0;
   if (uplo != CUBLAS_FILL_MODE_LOWER) return 1;
@@ -517,6 +548,7 @@ inline cusolverStatus_t cusolverDnXpotrf(cusolverDnHandle_t, cusolverDnParams_t,
 }
 inline cusolverStatus_t cusolverDnXpotrs(cusolverDnHandle_t, cusolverDnParams_t, cublasFillMode_t, int64_t n, int64_t nrhs, cudaDataType,
                                          const void* Av, int64_t lda, cudaDataType, void* Bv, int64_t ldb, int* info) {
+  cuda_emu::DeviceWindow window;
   const double* A = (const double*)Av;
   double* B = (double*)Bv;
   *info = 0;

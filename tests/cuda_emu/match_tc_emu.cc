@@ -46,11 +46,13 @@ static cudaError_t tc_stage(const uint8_t* pool, const MatchItem* items, const u
 cudaError_t launch_match_top2(const CUtensorMap& tmap, const MatchItem* items, const uint32_t* n_items_ptr, int thr_dist,
                               const int* ratio_lim, int* midx, uint4* cands, unsigned int* cand_count,
                               unsigned int cand_capacity, int, cudaStream_t, unsigned long long*) {
+  cuda_emu::DeviceWindow window;  // stands in for a kernel: it may touch device memory
   return tc_stage((const uint8_t*)tmap.opaque[0], items, n_items_ptr, thr_dist, ratio_lim, midx, cands, cand_count, cand_capacity);
 }
 cudaError_t launch_match_top2_ts(const CUtensorMap&, const uint8_t* pool, const MatchItem* items, const uint32_t* n_items_ptr,
                                  int thr_dist, const int* ratio_lim, int* midx, uint4* cands, unsigned int* cand_count,
                                  unsigned int cand_capacity, int, cudaStream_t) {
+  cuda_emu::DeviceWindow window;
   return tc_stage(pool, items, n_items_ptr, thr_dist, ratio_lim, midx, cands, cand_count, cand_capacity);
 }
 

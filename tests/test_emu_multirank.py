@@ -40,6 +40,8 @@ def _bind(lib_path):
         if rc != 0:
             raise RuntimeError(f"emulated library error {rc}: {L.b2_last_error().decode()}")
     ba._L, ba.check = (lambda: L), check
+    global _LIB
+    _LIB = L
     return ba, L
 
 
@@ -57,10 +59,17 @@ def _solve(ba, L, prob, solver, hook=None, iters=12):
         adj.close()
 
 
+_LIB = None
+
+
 def _gloo_hook(ptr, n, op):
-    buf = np.ctypeslib.as_array((C.c_double * n).from_address(ptr))     # the emulated device buffer is host memory
-    t = torch.from_numpy(buf)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX if op == 1 else dist.ReduceOp.SUM)
+    _LIB.cuda_emu_device_window(1)                                      # stands in for NCCL working on device memory
+    try:
+        buf = np.ctypeslib.as_array((C.c_double * n).from_address(ptr))     # the emulated device buffer is host memory
+        t = torch.from_numpy(buf)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX if op == 1 else dist.ReduceOp.SUM)
+    finally:
+        _LIB.cuda_emu_device_window(0)
 
 
 def _worker(rank, world, port, lib_path, solver, out_dir):
