@@ -463,6 +463,16 @@ inline void* guarded_alloc(size_t n) {
   mprotect(base + span - page, page, PROT_NONE);
   void* p = base + span - page - body;   // the allocation ends where the inaccessible page begins
   guard_registry()[p] = {base, span};
+  // cudaMalloc does not clear: doubles start as NaN, indices as -1, not as zero (the tail of a very large allocation, to
+  // bound the cost of touching pages nobody may use: the allocation's last 32 MiB and its first 1 MiB)
+  {
+    const size_t len = span - page, cap = (size_t)32 << 20;
+    if (len <= cap + (1u << 20)) std::memset(base, 0xFF, len);
+    else {
+      std::memset(base, 0xFF, 1u << 20);
+      std::memset(base + len - cap, 0xFF, cap);
+    }
+  }
   if (devmem_mode() && device_depth() == 0) mprotect(base, span - page, PROT_NONE);
   return p;
 }
@@ -475,7 +485,8 @@ inline void guarded_free(void* p) {
 }  // namespace cuda_emu
 template <class T> inline cudaError_t cudaMalloc(T** p, size_t n) {
   n = std::max<size_t>(n, 1);
-  *p = (T*)(cuda_emu::guard_mode() ? cuda_emu::guarded_alloc(n) : std::calloc(n, 1));
+  *p = (T*)(cuda_emu::guard_mode() ? cuda_emu::guarded_alloc(n) : std::malloc(n));
+  if (*p && !cuda_emu::guard_mode()) std::memset(*p, 0xFF, n);
   return *p ? cudaSuccess : 2;
 }
 inline cudaError_t cudaFree(void* p) {
