@@ -286,7 +286,7 @@ inline void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function
       return;
     }
   }
-  std::vector<uint64_t> smem((smem_bytes + 7) / 8 + 1, 0);
+  std::vector<uint64_t> smem((smem_bytes + 7) / 8 + 1, ~0ull);  // shared memory is not cleared at launch either
   dyn_smem() = smem.data();
   idx().gridDim = grid;
   idx().blockDim = block;
