@@ -415,7 +415,18 @@ inline const char* cudaGetErrorString(cudaError_t e) {
 inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
 inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) { *p = cudaDeviceProp(); return cudaSuccess; }
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
-inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+// Asynchronous device-to-host copies are DELIVERED at the next synchronisation point (the data is taken at enqueue time,
+// in stream order): host code that reads the destination before it synchronised sees the old contents, as it may with
+// pinned memory on the device.
+namespace cuda_emu {
+struct PendingCopy { void* dst; std::vector<char> data; };
+inline std::vector<PendingCopy>& pending_copies() { static std::vector<PendingCopy> v; return v; }
+inline void deliver_pending_copies() {
+  for (auto& c : pending_copies()) std::memmove(c.dst, c.data.data(), c.data.size());
+  pending_copies().clear();
+}
+}  // namespace cuda_emu
+inline cudaError_t cudaDeviceSynchronize() { cuda_emu::deliver_pending_copies(); return cudaSuccess; }
 // B2_EMU_GUARD=1: every "device" allocation ends right before an inaccessible page, so an overrun of the kind
 // compute-sanitizer reports on the GPU faults at the offending access (debugging aid for the emulator).
 namespace cuda_emu {
@@ -495,10 +506,21 @@ inline cudaError_t cudaFree(void* p) {
 }
 inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) {
   cuda_emu::DeviceWindow window;
+  cuda_emu::deliver_pending_copies();
   if (n) std::memmove(d, s, n);
   return cudaSuccess;
 }
-inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind k, cudaStream_t = nullptr) { return cudaMemcpy(d, s, n, k); }
+inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind k, cudaStream_t = nullptr) {
+  if (k != cudaMemcpyDeviceToHost) {
+    cuda_emu::DeviceWindow window;
+    if (n) std::memmove(d, s, n);
+    return cudaSuccess;
+  }
+  cuda_emu::DeviceWindow window;
+  cuda_emu::PendingCopy c{d, std::vector<char>((const char*)s, (const char*)s + n)};
+  cuda_emu::pending_copies().push_back(std::move(c));
+  return cudaSuccess;
+}
 inline cudaError_t cudaMemset(void* d, int v, size_t n) {
   cuda_emu::DeviceWindow window;
   if (n) std::memset(d, v, n);
@@ -508,11 +530,11 @@ inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = null
 inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = nullptr; return cudaSuccess; }
 inline cudaError_t cudaStreamCreate(cudaStream_t* s) { *s = nullptr; return cudaSuccess; }
 inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
-inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) { cuda_emu::deliver_pending_copies(); return cudaSuccess; }
 inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new emu_event_(); return cudaSuccess; }
 inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
 inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr) { e->t = std::chrono::steady_clock::now(); return cudaSuccess; }
-inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+inline cudaError_t cudaEventSynchronize(cudaEvent_t) { cuda_emu::deliver_pending_copies(); return cudaSuccess; }
 inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) {
   *ms = std::max(1e-3f, std::chrono::duration<float, std::milli>(b->t - a->t).count());
   return cudaSuccess;
