@@ -4,6 +4,14 @@
 set -x
 cd ${GRAFT_REPO_ROOT:-.}
 python -m pytest tests/test_zz_guided_gpu.py tests/test_two_view_shim.py -m gpu -q -rxXs 2>&1 | tail -25 > gpurun_out/zz_first_run.log
+# what the CUDA emulator cannot see (tests/cuda_emu/README.md): races between warps, kernels reading host memory. One
+# pass of the never-run kernels under compute-sanitizer, small cases only (each tool slows the kernels 10-100x)
+for tool in memcheck racecheck synccheck; do
+  timeout 900 compute-sanitizer --tool $tool --error-exitcode 9 python -m pytest tests/test_zz_guided_gpu.py -m gpu -q -x \
+    -k "relative_pose or mean_reprojection or camera_model_is_normalised or iterative_schur_matches and kw1 or general_camera and camera2" \
+    > gpurun_out/sanitizer_$tool.log 2>&1
+  echo "compute-sanitizer $tool exit $?" >> gpurun_out/zz_first_run.log
+done
 # ITERATIVE_SCHUR (ba_iterative.cu) and relative pose (verify_pose.cu) were written after the round-1 GPU budget was spent:
 # time the inner solve at 2 000 and 10 000 images (C5 shape), and take the launch list + one full capture of the matvec pair
 python bench.py --pairs 2000 --verify-pairs 0 --no-cpu --no-e2e --steps 3 --warmup 3 --ba 2000,400000,10 --ba-solver iterative \
