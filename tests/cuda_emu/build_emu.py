@@ -14,7 +14,11 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 ROOT = HERE.parent.parent
 CSRC = ROOT / "dagsfm_b200" / "csrc"
-OUT = HERE / "_build"
+import os
+
+# B2_EMU_BUILD_DIR: a second build tree, so that a run in another mode (tests/test_emu_modes.py) does not replace the
+# libraries the parent process has loaded
+OUT = Path(os.environ["B2_EMU_BUILD_DIR"]) if os.environ.get("B2_EMU_BUILD_DIR") else HERE / "_build"
 
 
 # the translation units of each emulated library (the product's own sources)
