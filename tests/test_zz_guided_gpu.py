@@ -440,3 +440,55 @@ def test_guided_stage_chained_on_device_results_on_gpu():
     finally:
         m.close()
         v.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="first GPU execution of relative_pose_kernel through the device-pointer entry (written after the "
+                   "round's GPU budget was spent; verified on the CUDA emulator, tests/test_emu_verify.py)")
+def test_verify_then_pose_chained_on_device_on_gpu():
+    """b2_verify_pairs_device -> b2_verify_relative_pose_device on torch device buffers equals the host-buffer calls, and
+    the kernel's own consistency check (an inlier list longer than its slot) turns into B2_ERR_INVALID."""
+    import torch
+    from dagsfm_b200 import Camera, TwoViewGeometryVerifier, TwoViewOptions
+    from dagsfm_b200.verification import POSE_DTYPE, RESULT_DTYPE
+    from tests.tv_scene import scene
+    rng = np.random.default_rng(4)
+    kps, pairs, offs, matches = [], [], [0], []
+    for k in range(4):
+        p1, p2 = scene(rng, 60 + 15 * k, 12, planar=(k == 2), noise=0.4)
+        kps += [p1, p2]
+        pairs.append((2 * k, 2 * k + 1))
+        matches.append(np.stack([np.arange(len(p1))] * 2, 1))
+        offs.append(offs[-1] + len(p1))
+    pairs = np.array(pairs, np.uint32)
+    offs = np.array(offs, np.int64)
+    matches = np.concatenate(matches).astype(np.uint32)
+    seeds = np.arange(4, dtype=np.uint32) + 40
+    vo = TwoViewOptions.default()
+    dev = torch.device("cuda:0")
+
+    def to_dev(a):
+        return torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1).copy()).to(dev)
+    ver = TwoViewGeometryVerifier(0)
+    try:
+        ver.set_images([Camera.make(prior_focal=True)] * 8, kps)
+        res_h, inl_h = ver.verify_pairs(pairs, offs, matches, vo, seeds)
+        pose_h = ver.relative_pose(pairs, offs, res_h, inl_h)
+        pairs_d, offs_d, m_d, seeds_d = to_dev(pairs), to_dev(offs), to_dev(matches), to_dev(seeds)
+        res_d = torch.zeros(4 * RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+        inl_d = torch.zeros(matches.size * 4, dtype=torch.uint8, device=dev)
+        pose_d = torch.zeros(4 * POSE_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+        ver.verify_pairs_device(4, pairs_d.data_ptr(), offs_d.data_ptr(), m_d.data_ptr(), vo, seeds_d.data_ptr(),
+                                res_d.data_ptr(), inl_d.data_ptr())
+        ver.relative_pose_device(4, pairs_d.data_ptr(), offs_d.data_ptr(), res_d.data_ptr(), inl_d.data_ptr(), pose_d.data_ptr())
+        torch.cuda.synchronize()
+        assert res_d.cpu().numpy().tobytes() == res_h.tobytes()
+        got = pose_d.cpu().numpy().view(POSE_DTYPE)
+        assert (got["config"] == pose_h["config"]).all() and (got["n_points3D"] == pose_h["n_points3D"]).all()
+        assert got.tobytes() == pose_h.tobytes()
+        bad = res_h.copy()
+        bad["n_inliers"][1] = offs[2] - offs[1] + 1
+        with pytest.raises(RuntimeError, match="inlier list inconsistent"):
+            ver.relative_pose_device(4, pairs_d.data_ptr(), offs_d.data_ptr(), to_dev(bad).data_ptr(), inl_d.data_ptr(), pose_d.data_ptr())
+    finally:
+        ver.close()
