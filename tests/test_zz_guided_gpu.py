@@ -15,6 +15,8 @@ from tests.test_host_guided import _inlier_pairs, _scene_with_descriptors
 
 ROOT = Path(__file__).resolve().parent.parent
 EXE = ROOT / "tests" / "cpp" / "_guided_shim_test"
+# kernels on their first device run: bound each test, so that a hang ends the run with a report instead of the driver's limit
+pytestmark = pytest.mark.timeout(900)
 FIRST_RUN = pytest.mark.xfail(strict=False, reason="first GPU execution of the guided kernel (no GPU budget was left to run it)")
 
 
