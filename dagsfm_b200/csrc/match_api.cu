@@ -25,12 +25,7 @@
 
 namespace b2 {
 
-// kernels / launchers defined in match_tc.cu and match_post.cu
-cudaError_t launch_match_top2(const CUtensorMap& tmap, const MatchItem* items,
-                              const uint32_t* n_items_ptr, int thr_dist, const int* ratio_lim,
-                              int* midx, uint4* cands, unsigned int* cand_count,
-                              unsigned int cand_capacity, int grid, cudaStream_t stream,
-                              unsigned long long* prof = nullptr);
+// kernels / launchers defined in match_tc_ts.cu and match_post.cu
 cudaError_t launch_pair_items(const uint32_t* pairs, int64_t n_pairs, const int32_t* img_n,
                               int32_t n_images, uint32_t* n_items_of_pair, int* err, cudaStream_t s);
 cudaError_t launch_scan_u32(const uint32_t* in, int64_t n, uint32_t* out, uint32_t* total,
@@ -59,11 +54,10 @@ cudaError_t launch_guided_match(const uint8_t* pool, const float* kp_pool, const
                                 const GuidedGeom* geoms, float max_residual, int thr_dist, const int* ratio_lim,
                                 int* midx, int n_sm, cudaStream_t s);
 
-constexpr bool kDefaultTs = true;   // TS kernel (query operand in tensor memory) is the production kernel
 static inline uint32_t pad_up(uint32_t n, uint32_t m) { return (n + m - 1) / m * m; }
-// Rows reserved for an image of n descriptors: whole 256-row X supertiles, and enough zero
-// rows that Y blocks of 96 (TS kernel) or 128 (SS kernel) rows never reach the next image.
-static inline uint32_t image_rows(uint32_t n) { return pad_up(pad_up(n, 96), kSuperRows); }
+// Rows reserved for an image of n descriptors: whole 256-row X supertiles (the zero padding rows also keep every
+// 128-row Y block of the tensor-core kernel inside the image's own rows).
+static inline uint32_t image_rows(uint32_t n) { return pad_up(n, kSuperRows); }
 
 // ---------------------------------------------------------------- tensor map
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -107,8 +101,7 @@ struct ImageStore {
   std::vector<int32_t> h_img_n;
   std::vector<uint32_t> h_img_row;
   uint32_t max_n = 0;
-  CUtensorMap tmap;    // box 128 rows (SS kernel)
-  CUtensorMap tmap96;  // box  96 rows (TS kernel)
+  CUtensorMap tmap;    // box 128 rows x 128 B, SWIZZLE_128B
 
   void release() {
     if (pool) cudaFree(pool);
@@ -154,8 +147,27 @@ struct ImageStore {
       B2_CUDA(cudaMemcpyAsync(d_img_row, h_img_row.data(), n * sizeof(uint32_t),
                               cudaMemcpyHostToDevice, s));
     }
-    B2_TRY(make_pool_tmap(&tmap, pool, rows, kTileRows));
-    return make_pool_tmap(&tmap96, pool, rows, 96);
+    return make_pool_tmap(&tmap, pool, rows, kTileRows);
+  }
+  // SiftMatchCU::SetDescriptors clamps every upload to max_sift = max_num_matches (SiftMatchCU.cpp:108, sift.cc:200-209):
+  // features beyond the clamp take no part in any match.  Applied to the store in place on the first call whose options
+  // need it (rows beyond the clamp are zeroed: a zero row can never be a best or second-best match); a later call with a
+  // larger max_num_matches needs a new upload, as it does in the reference.
+  int clamp(int32_t max_n_per_image, cudaStream_t s) {
+    if ((int64_t)max_n <= (int64_t)max_n_per_image) return B2_OK;
+    uint32_t new_max = 0;
+    for (int32_t i = 0; i < n_images; ++i) {
+      if (h_img_n[i] > max_n_per_image) {
+        B2_CUDA(cudaMemsetAsync(pool + ((size_t)h_img_row[i] + (size_t)max_n_per_image) * kDescBytes, 0,
+                                (size_t)(h_img_n[i] - max_n_per_image) * kDescBytes, s));
+        h_img_n[i] = max_n_per_image;
+      }
+      new_max = std::max<uint32_t>(new_max, (uint32_t)h_img_n[i]);
+    }
+    max_n = new_max;
+    B2_CUDA(cudaMemcpyAsync(d_img_n, h_img_n.data(), (size_t)n_images * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    B2_CUDA(cudaStreamSynchronize(s));  // h_img_n may be re-laid-out by the caller right after
+    return B2_OK;
   }
 };
 
@@ -262,6 +274,7 @@ static int run_pairs_device(b2_matcher* m, ImageStore& st, int64_t n_pairs,
   B2_CUDA(cudaSetDevice(m->device));
   cudaStream_t s = m->stream;
   B2_TRY(m->tables.build(opt->max_ratio, opt->max_distance, s));
+  B2_TRY(st.clamp(opt->max_num_matches, s));
   B2_TRY(ensure_scratch(m, st.max_n));
   B2_CUDA(cudaMemsetAsync(m->d_carry, 0, sizeof(int64_t), s));
   B2_CUDA(cudaMemsetAsync(m->d_err, 0, sizeof(int), s));
@@ -276,15 +289,6 @@ static int run_pairs_device(b2_matcher* m, ImageStore& st, int64_t n_pairs,
   std::vector<unsigned int> h_cands(std::max<int64_t>(n_chunks, 1), 0);
   unsigned int* d_cand_hist = nullptr;
   B2_CUDA(cudaMalloc(&d_cand_hist, std::max<int64_t>(n_chunks, 1) * sizeof(unsigned int)));
-  // tensor-core kernel generation: "ts" = query operand in tensor memory, "ss" = both operands
-  // in shared memory (first generation, kept for A/B measurements)
-  const char* kenv = getenv("B2_MATCH_KERNEL");
-  const bool use_ts = kenv ? (strcmp(kenv, "ts") == 0) : kDefaultTs;
-  unsigned long long* d_prof = nullptr;
-  if (getenv("B2_MATCH_PROFILE")) {
-    B2_CUDA(cudaMalloc(&d_prof, 8 * sizeof(unsigned long long)));
-    B2_CUDA(cudaMemsetAsync(d_prof, 0, 8 * sizeof(unsigned long long), s));
-  }
   B2_CUDA(cudaEventRecord(m->ev[0], s));
   for (int64_t c = 0; c < n_chunks; ++c) {
     const int64_t p0 = c * m->cap_pairs, np = std::min(m->cap_pairs, n_pairs - p0);
@@ -295,14 +299,9 @@ static int run_pairs_device(b2_matcher* m, ImageStore& st, int64_t n_pairs,
                               (uint32_t)kTileRows, s));
     B2_CUDA(cudaMemsetAsync(m->d_cand_count, 0, sizeof(unsigned int), s));
     B2_CUDA(cudaEventRecord(m->ev[2 + 2 * c], s));
-    if (use_ts)
-      B2_CUDA(launch_match_top2_ts(st.tmap, st.pool, m->d_items, m->d_total_items, m->tables.thr_dist,
-                                   m->tables.d_ratio_lim, m->d_midx, m->d_cands, m->d_cand_count,
-                                   (unsigned int)std::min<uint64_t>(m->row_budget, 0xFFFFFFFFu), m->n_sm, s));
-    else
-      B2_CUDA(launch_match_top2(st.tmap, m->d_items, m->d_total_items, m->tables.thr_dist,
-                                m->tables.d_ratio_lim, m->d_midx, m->d_cands, m->d_cand_count,
-                                (unsigned int)std::min<uint64_t>(m->row_budget, 0xFFFFFFFFu), m->n_sm, s, d_prof));
+    B2_CUDA(launch_match_top2_ts(st.tmap, st.pool, m->d_items, m->d_total_items, m->tables.thr_dist,
+                                 m->tables.d_ratio_lim, m->d_midx, m->d_cands, m->d_cand_count,
+                                 (unsigned int)std::min<uint64_t>(m->row_budget, 0xFFFFFFFFu), m->n_sm, s));
     B2_CUDA(cudaEventRecord(m->ev[3 + 2 * c], s));
     B2_CUDA(launch_fixup(st.pool, m->d_items, m->d_cands, m->d_cand_count,
                          (unsigned int)std::min<uint64_t>(m->row_budget, 0xFFFFFFFFu),
@@ -324,13 +323,6 @@ static int run_pairs_device(b2_matcher* m, ImageStore& st, int64_t n_pairs,
                           cudaMemcpyDeviceToHost, s));
   B2_CUDA(cudaStreamSynchronize(s));
   cudaFree(d_cand_hist);
-  if (d_prof) {
-    unsigned long long hp[8];
-    cudaMemcpy(hp, d_prof, sizeof hp, cudaMemcpyDeviceToHost);
-    cudaFree(d_prof);
-    fprintf(stderr, "[b2 match profile] MMA thread cycles: wait_y %.3g wait_tmem_empty %.3g total %.3g | epilogue warp cycles (x8 warps): wait_full %.3g ldtm %.3g alu %.3g\n",
-            (double)hp[0], (double)hp[1], (double)hp[2], (double)hp[3], (double)hp[4], (double)hp[5]);
-  }
   float ms = 0;
   m->last_tc_s = 0;
   for (int64_t c = 0; c < n_chunks; ++c) {
@@ -344,7 +336,7 @@ static int run_pairs_device(b2_matcher* m, ImageStore& st, int64_t n_pairs,
   for (int64_t c = 0; c < n_chunks; ++c) m->last_cands += h_cands[c];
   if (n_total) *n_total = total;
   if (err == 1) return set_error(B2_ERR_INVALID, "pair references an image outside the store");
-  if (err != 0 && !getenv("B2_MATCH_EXP"))
+  if (err != 0)
     return set_error(B2_ERR_INTERNAL, "fix-up did not find the tensor-core maximum in its chunk");
   if (total > capacity) return set_error(B2_ERR_CAPACITY, "out_matches capacity too small");
   return B2_OK;
@@ -364,6 +356,7 @@ static int run_guided_device(b2_matcher* m, ImageStore& st, int64_t n_pairs, con
   B2_CUDA(cudaSetDevice(m->device));
   cudaStream_t s = m->stream;
   B2_TRY(m->tables.build(opt->max_ratio, opt->max_distance, s));
+  B2_TRY(st.clamp(opt->max_num_matches, s));
   B2_TRY(ensure_scratch(m, st.max_n));
   B2_CUDA(cudaMemsetAsync(m->d_carry, 0, sizeof(int64_t), s));
   B2_CUDA(cudaMemsetAsync(m->d_err, 0, sizeof(int), s));
@@ -665,22 +658,22 @@ int b2_match_run(b2_matcher* m, const b2_match_options* opt, uint32_t* out_match
   if (!m || !opt || !n_out) return set_error(B2_ERR_INVALID, "NULL argument");
   *n_out = 0;
   if (m->slots.n_images != 2) return set_error(B2_ERR_INVALID, "descriptors not set");
-  // SiftMatchCU clamps both sets to max_sift = max_num_matches at upload time
-  // (SiftMatchCU.cpp:108); the C++ shim does that clamp before b2_match_set_descriptors.
+  // SiftMatchCU clamps both sets to max_sift = max_num_matches at upload time (SiftMatchCU.cpp:108); run_pairs_device
+  // applies that clamp to the slots.  At most one match per row of image 0 comes back (without cross-check several rows
+  // may share a column, so the count can exceed n1); GetSiftMatch returns the first max_match of them (SiftMatchCU.cpp:
+  // 178-199 stops filling the caller's buffer at max_match).
   ImageStore& st = m->slots;
-  const std::vector<int32_t>& saved = st.h_img_n;
-  if (saved[0] > opt->max_num_matches || saved[1] > opt->max_num_matches)
-    return set_error(B2_ERR_INVALID, "descriptor count exceeds max_num_matches; clamp before upload");
   const uint32_t pair[2] = {0, 1};
   int64_t offsets[2] = {0, 0};
   int64_t total = 0;
-  const int64_t cap = std::min<int64_t>(opt->max_num_matches, std::min(saved[0], saved[1]));
+  const int64_t cap = std::min<int32_t>(st.h_img_n[0], opt->max_num_matches > 0 ? opt->max_num_matches : 0);
   std::vector<uint32_t> tmp(2 * std::max<int64_t>(cap, 1));
-  const int rc = run_pairs_host(m, st, 1, pair, opt, offsets, tmp.data(), cap, &total);
+  const int rc = run_pairs_host(m, st, 1, pair, opt, offsets, tmp.data(), std::max<int64_t>(cap, 1), &total);
   if (rc != B2_OK) return rc;
-  if (total > 0 && !out_matches) return set_error(B2_ERR_INVALID, "out_matches == NULL");
-  memcpy(out_matches, tmp.data(), (size_t)total * 2 * sizeof(uint32_t));
-  *n_out = (int32_t)total;
+  const int64_t n_ret = std::min<int64_t>(total, opt->max_num_matches);
+  if (n_ret > 0 && !out_matches) return set_error(B2_ERR_INVALID, "out_matches == NULL");
+  if (n_ret > 0) memcpy(out_matches, tmp.data(), (size_t)n_ret * 2 * sizeof(uint32_t));
+  *n_out = (int32_t)n_ret;
   return B2_OK;
 }
 

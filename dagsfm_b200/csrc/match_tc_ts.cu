@@ -1,9 +1,8 @@
-// Descriptor matching, stage 1, second-generation kernel: same algorithm as match_tc.cu
-// (dense u8 x u8 -> s32 contraction on tcgen05 + fused chunked top-2 epilogue) with the
-// stationary operand held in TENSOR MEMORY.
+// Descriptor matching, stage 1: dense u8 x u8 -> s32 contraction on tcgen05 + fused chunked top-2
+// epilogue, with the stationary operand held in TENSOR MEMORY.
 //
-// Why: cycle counters in match_tc.cu (B2_MATCH_PROFILE=1) show the MMA-issuing thread waits
-// on barriers only ~15 % of the time while the epilogue warps starve ~70 %: the SS-mode MMA
+// Why TS mode: cycle counters in the first-generation kernel (both operands in shared memory, round 1) showed the
+// MMA-issuing thread waiting on barriers only ~15 % of the time while the epilogue warps starved ~70 %: the SS-mode MMA
 // (both operands in shared memory) reads 8 KB of smem per 64-cycle M128 N128 K32 step, which
 // is exactly the 128 B/clk shared-memory port -- plus the TMA writes.  The query supertile X is
 // reused by every block of an item, so it is written once per item into TMEM (tcgen05.st by the
@@ -56,8 +55,8 @@ __device__ __forceinline__ int max32(const uint32_t* v) {
   return max(__vimax3_s32(a, b, c), d);
 }
 
-// EXP != 0 are timing experiments (results invalid): 1 = epilogue without LDTM and ALU,
-// 2 = LDTM without ALU.  B2_MATCH_EXP selects them; production is EXP == 0.
+// EXP != 0 are timing experiments (results invalid): 1 = epilogue without LDTM and ALU, 2 = LDTM without ALU.  They
+// exist only in builds with -DB2_MATCH_EXPERIMENTS (never in the shipped library); production is EXP == 0.
 template <int EXP>
 __global__ void __launch_bounds__(kThreads, 1)
 match_top2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restrict__ pool,
@@ -247,8 +246,10 @@ cudaError_t launch_match_top2_ts(const CUtensorMap& tmap, const uint8_t* pool, c
                                  uint4* cands, unsigned int* cand_count, unsigned int cand_capacity, int grid,
                                  cudaStream_t stream) {
   const size_t smem = ts::kSmemTotal + 1024;
+#ifdef B2_MATCH_EXPERIMENTS
   const char* ex = getenv("B2_MATCH_EXP");
   const int exp_mode = ex ? atoi(ex) : 0;
+#endif
   auto go = [&](auto kern) -> cudaError_t {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -256,8 +257,12 @@ cudaError_t launch_match_top2_ts(const CUtensorMap& tmap, const uint8_t* pool, c
                                                cand_count, cand_capacity);
     return cudaSuccess;
   };
+#ifdef B2_MATCH_EXPERIMENTS
   cudaError_t e = exp_mode == 1 ? go(ts::match_top2_ts_kernel<1>) : exp_mode == 2 ? go(ts::match_top2_ts_kernel<2>)
                                                                                     : go(ts::match_top2_ts_kernel<0>);
+#else
+  cudaError_t e = go(ts::match_top2_ts_kernel<0>);
+#endif
   if (e != cudaSuccess) return e;
   return cudaGetLastError();
 }

@@ -36,6 +36,10 @@ const char* b2_version(void);
 /* Number of CUDA kernels this library has launched since load (all threads);
  * bench.py reports the delta over the timed region as `gpu_launches`. */
 uint64_t b2_kernel_launch_count(void);
+/* Roofline denominators MEASURED_PEAKS.json does not hold, measured on this box: FMA
+ * throughput of the CUDA cores in FP64 / FP32, TFLOP/s (16 independent chains per thread, best of 4). */
+int b2_measure_fp64_peak(int device, double* tflops);
+int b2_measure_ffma_peak(int device, double* tflops);
 
 /* ================================================================== MATCH ==
  * Replaces: MatchSiftFeaturesGPU (src/feature/sift.h:235-239,
@@ -55,8 +59,9 @@ typedef struct b2_match_options {
   float max_ratio;        /* SiftMatchingOptions::max_ratio    (sift.h:131) default 0.8 */
   float max_distance;     /* SiftMatchingOptions::max_distance (sift.h:134) default 0.7 */
   int32_t cross_check;    /* SiftMatchingOptions::cross_check  (sift.h:137) default 1   */
-  int32_t max_num_matches;/* SiftMatchingOptions::max_num_matches (sift.h:140) 32768:
-                             features beyond it are clamped (SiftMatchCU.cpp:108) */
+  int32_t max_num_matches;/* SiftMatchingOptions::max_num_matches (sift.h:140) 32768: features of an image beyond it
+                             take no part in any match (the upload clamp of SiftMatchCU.cpp:108) -- applied IN PLACE
+                             to the image store / the two slots by the first call that needs it, on both seams */
 } b2_match_options;
 
 /* Fills the reference defaults (src/feature/sift.h:116-165). */
@@ -106,7 +111,8 @@ int b2_match_pairs_device(b2_matcher* m, int64_t n_pairs, const uint32_t* pairs_
 /* -- two-slot seam: SiftMatchGPU::SetDescriptors / GetSiftMatch ------------
  * (lib/SiftGPU/SiftGPU.h:312-326).  slot in {0,1}; `desc == NULL` keeps the
  * previous upload (sift.h:232-234).  b2_match_run returns the number of
- * matches in *n_out (<= max_num_matches) -- the reference returns -1 on a
+ * matches in *n_out: at most one per feature of slot 0 (without cross-check several of them may
+ * share a feature of slot 1), truncated to max_num_matches -- the reference returns -1 on a
  * device error (SiftMatchCU.cpp:193-196); here that is a non-zero status. */
 int b2_match_set_descriptors(b2_matcher* m, int slot, int32_t n, const uint8_t* desc);
 int b2_match_run(b2_matcher* m, const b2_match_options* opt,

@@ -78,6 +78,7 @@ class SiftMatchGPU {
     // (Eigen's data() of a 0-row matrix may be NULL) must still replace it
     static const unsigned char kEmpty = 0;
     const int n = std::max(0, std::min(num, max_sift_));
+    if (!descriptors && n > 0) return;  // nothing to copy from: keep the previous upload
     b2_match_set_descriptors(h_, index, n, descriptors ? descriptors : &kEmpty);
     if (descriptors || n == 0) {  // host copy for GetGuidedSiftMatch, whose filter needs both images in one call
       guided_desc[index].assign(descriptors ? descriptors : &kEmpty, (descriptors ? descriptors : &kEmpty) + (size_t)n * 128);
@@ -87,11 +88,19 @@ class SiftMatchGPU {
   // returns the number of matches, -1 on a device error (SiftMatchCU.cpp:193-196)
   int GetSiftMatch(int max_match, uint32_t match_buffer[][2], float distmax = 0.7f, float ratiomax = 0.8f,
                    int mutual_best_match = 1) {
-    if (!h_) return -1;
+    if (!h_ || max_match < 0) return -1;
+    // max_match is the size of the caller's buffer; the feature clamp is max_sift (SiftMatchCU.cpp:108), applied at upload
     b2_match_options o;
-    o.max_ratio = ratiomax; o.max_distance = distmax; o.cross_check = mutual_best_match; o.max_num_matches = max_match;
+    o.max_ratio = ratiomax; o.max_distance = distmax; o.cross_check = mutual_best_match; o.max_num_matches = std::max(max_sift_, 1);
     int32_t n = 0;
-    if (b2_match_run(h_, &o, &match_buffer[0][0], &n) != B2_OK) return -1;
+    if (max_match >= o.max_num_matches) {
+      if (b2_match_run(h_, &o, &match_buffer[0][0], &n) != B2_OK) return -1;
+      return n;
+    }
+    std::vector<uint32_t> tmp(2 * (size_t)o.max_num_matches);
+    if (b2_match_run(h_, &o, tmp.data(), &n) != B2_OK) return -1;
+    n = std::min(n, max_match);
+    for (int i = 0; i < n; ++i) { match_buffer[i][0] = tmp[2 * i]; match_buffer[i][1] = tmp[2 * i + 1]; }
     return n;
   }
 
@@ -144,8 +153,8 @@ class SiftMatchGPU {
       dp[k] = cnt[k] ? guided_desc[k].data() : &kEmptyDesc;
       kp[k] = cnt[k] ? guided_xy[k].data() : &kEmptyXy;
     }
-    b2_match_options o;
-    o.max_ratio = ratiomax; o.max_distance = distmax; o.cross_check = mutual_best_match; o.max_num_matches = max_match;
+    b2_match_options o;  // feature clamp = max_sift (already applied by SetDescriptors); max_match only bounds the output
+    o.max_ratio = ratiomax; o.max_distance = distmax; o.cross_check = mutual_best_match; o.max_num_matches = std::max(max_sift_, 1);
     const uint32_t pair[2] = {0, 1};
     int64_t offsets[2] = {0, 0}, total = 0;
     const double max_error = std::sqrt((double)(H ? hdistmax : fdistmax));

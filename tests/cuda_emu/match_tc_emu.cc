@@ -1,5 +1,5 @@
-// Host stand-in for the two tcgen05 kernels (match_tc.cu / match_tc_ts.cu), which have no CPU meaning: it
-// produces what those kernels are CONTRACTED to produce (match_common.cuh) -- per query
+// Host stand-in for the tcgen05 kernel (match_tc_ts.cu), which has no CPU meaning: it
+// produces what that kernel is CONTRACTED to produce (match_common.cuh) -- per query
 // row the exact best dot, the first 32-column chunk attaining it and the best maximum over all other
 // chunks; rows that can still pass the integer threshold tests go to the candidate list, midx = -1 --
 // so that the rest of the matcher (items, fix-up, cross-check, compaction, chunking in match_api.cu: all
@@ -43,12 +43,6 @@ static cudaError_t tc_stage(const uint8_t* pool, const MatchItem* items, const u
   return cudaSuccess;
 }
 
-cudaError_t launch_match_top2(const CUtensorMap& tmap, const MatchItem* items, const uint32_t* n_items_ptr, int thr_dist,
-                              const int* ratio_lim, int* midx, uint4* cands, unsigned int* cand_count,
-                              unsigned int cand_capacity, int, cudaStream_t, unsigned long long*) {
-  cuda_emu::DeviceWindow window;  // stands in for a kernel: it may touch device memory
-  return tc_stage((const uint8_t*)tmap.opaque[0], items, n_items_ptr, thr_dist, ratio_lim, midx, cands, cand_count, cand_capacity);
-}
 cudaError_t launch_match_top2_ts(const CUtensorMap&, const uint8_t* pool, const MatchItem* items, const uint32_t* n_items_ptr,
                                  int thr_dist, const int* ratio_lim, int* midx, uint4* cands, unsigned int* cand_count,
                                  unsigned int cand_capacity, int, cudaStream_t) {

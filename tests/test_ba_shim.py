@@ -38,8 +38,6 @@ def test_reference_structure_tests_through_the_adaptor_on_the_emulated_library()
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="first GPU execution (the last case uses an OPENCV camera, i.e. the wide Jacobian layout, "
-                   "which has not run on a GPU yet)")
 def test_reference_structure_tests_through_the_adaptor_on_gpu():
     r = subprocess.run([str(_product_exe())], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "ba shim ok" in r.stdout, r.stdout + r.stderr

@@ -64,6 +64,32 @@ def test_reference_cpu_vs_gpu_cases(mm):
         gpu.close()
 
 
+
+def test_no_cross_check_many_rows_few_columns_and_the_feature_clamp(mm):
+    """without cross-check several rows of image 1 may share a column, so the match count can exceed n2 (the
+    two-slot seam used to size its buffer by min(n1, n2) and fail); and the feature clamp of SiftMatchCU.cpp:108 --
+    features beyond max_num_matches take no part -- holds on the two-slot AND the batched seam."""
+    gpu = mm.SiftMatchGPU(0)
+    try:
+        d2 = orc.create_random_descriptors(40, seed=5)
+        d1 = np.concatenate([d2, d2, d2, d2[:30]])          # 150 rows, every one an exact copy of a column of d2
+        o = mm.SiftMatchingOptions(cross_check=False)
+        exp = orc.match_sift(d1, d2, cross_check=False)
+        assert len(exp) == 150 > len(d2)
+        assert mm.match_sift_features_gpu(o, d1, d2, gpu).tolist() == exp.tolist()
+        # clamp: only the first 100 / 25 features exist for the matcher
+        oc = mm.SiftMatchingOptions(cross_check=False, max_num_matches=100)
+        expc = orc.match_sift(d1[:100], d2, cross_check=False)
+        assert mm.match_sift_features_gpu(oc, d1, d2, gpu).tolist() == expc.tolist()
+        gpu.set_images([d1, d2])
+        oc = mm.SiftMatchingOptions(cross_check=True, max_num_matches=25)
+        off, m = gpu.match_pairs([(0, 1), (1, 0)], oc)
+        assert m[off[0]:off[1]].tolist() == orc.match_sift(d1[:25], d2[:25]).tolist()
+        assert m[off[1]:off[2]].tolist() == orc.match_sift(d2[:25], d1[:25]).tolist()
+    finally:
+        gpu.close()
+
+
 def test_batched_pairs_ragged_and_chunked(mm, monkeypatch):
     monkeypatch.setenv("B2_MATCH_ROW_BUDGET", "65536")        # forces several chunks of pairs per call
     rng = np.random.default_rng(3)

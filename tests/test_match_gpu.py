@@ -55,6 +55,24 @@ def test_reference_cpu_vs_gpu_cases(gpu):
     assert cpu_vs_gpu(gpu, opts(cross_check=True), d1, d2) == 98
 
 
+
+def test_no_cross_check_many_rows_few_columns_and_the_feature_clamp(gpu):
+    """Without cross-check the match count can exceed n2 (several rows share a column); the feature clamp of
+    SiftMatchCU.cpp:108 holds on both seams (same cases as tests/test_emu_match.py, on the device)."""
+    from dagsfm_b200 import match_sift_features_gpu
+    d2 = orc.create_random_descriptors(40, seed=5)
+    d1 = np.concatenate([d2, d2, d2, d2[:30]])
+    exp = orc.match_sift(d1, d2, cross_check=False)
+    assert len(exp) == 150
+    assert match_sift_features_gpu(opts(cross_check=False), d1, d2, gpu).tolist() == exp.tolist()
+    expc = orc.match_sift(d1[:100], d2, cross_check=False)
+    assert match_sift_features_gpu(opts(cross_check=False, max_num_matches=100), d1, d2, gpu).tolist() == expc.tolist()
+    gpu.set_images([d1, d2])
+    off, m = gpu.match_pairs([(0, 1), (1, 0)], opts(max_num_matches=25))
+    assert m[off[0]:off[1]].tolist() == orc.match_sift(d1[:25], d2[:25]).tolist()
+    assert m[off[1]:off[2]].tolist() == orc.match_sift(d2[:25], d1[:25]).tolist()
+
+
 def test_previous_upload_is_reused(gpu):
     # sift.h:232-234: a NULL descriptor pointer keeps the previous upload
     from dagsfm_b200 import match_sift_features_gpu

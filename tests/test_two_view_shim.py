@@ -42,7 +42,6 @@ def test_estimate_through_the_adaptor_on_the_emulated_library():
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="first GPU execution (depends on relative_pose_kernel, not yet run on a GPU)")
 def test_estimate_through_the_adaptor_on_gpu():
     r = subprocess.run([str(_product_exe()), "estimate"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr

@@ -2,8 +2,8 @@
 MatchGuidedSiftFeaturesCPU, plus the replay of the reference's own GPU test through the C++ shim.
 
 The kernel's row function and the threshold tables are verified on the CPU (tests/test_host_guided.py).
-This file ran for the first time after the round's GPU budget was spent, hence the non-strict xfail:
-a pass is reported as XPASS, a failure does not hide the rest of the suite."""
+All of these passed on the driver's B200 at the end of round 1 (GPUTEST_r01: 29 xpassed); the first-run
+xfail marks are gone, so a regression in any of them fails the suite."""
 import subprocess
 from pathlib import Path
 
@@ -17,7 +17,6 @@ ROOT = Path(__file__).resolve().parent.parent
 EXE = ROOT / "tests" / "cpp" / "_guided_shim_test"
 # kernels on their first device run: bound each test, so that a hang ends the run with a report instead of the driver's limit
 pytestmark = pytest.mark.timeout(900)
-FIRST_RUN = pytest.mark.xfail(strict=False, reason="first GPU execution of the guided kernel (no GPU budget was left to run it)")
 
 
 def build():
@@ -35,7 +34,6 @@ def test_guided_shim_compiles_and_links():
 
 
 @pytest.mark.gpu
-@FIRST_RUN
 def test_guided_pairs_equal_oracle_on_gpu():
     from dagsfm_b200 import SiftMatchGPU, SiftMatchingOptions
     rng = np.random.default_rng(11)
@@ -75,7 +73,6 @@ def test_guided_pairs_equal_oracle_on_gpu():
 
 
 @pytest.mark.gpu
-@FIRST_RUN
 def test_guided_shim_replays_reference_test_on_gpu():
     exe = EXE if EXE.exists() else build()
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
@@ -84,7 +81,6 @@ def test_guided_shim_replays_reference_test_on_gpu():
 
 
 @pytest.mark.gpu
-@FIRST_RUN
 def test_estimate_multiple_equals_oracle_on_gpu():
     """b2_verify_pairs_multiple = the round loop of verify_multiple.h (checked on the CPU with the oracle
     plugged in, tests/test_host_multiple.py) around the verified GPU Estimate."""
@@ -121,7 +117,6 @@ def test_estimate_multiple_equals_oracle_on_gpu():
 
 
 @pytest.mark.gpu
-@FIRST_RUN
 @pytest.mark.parametrize("loss_type,scale", [(1, 1.0), (2, 1.0), (1, 2.5)])
 def test_ba_robust_loss_matches_oracle_on_gpu(loss_type, scale):
     """SOFT_L1 / CAUCHY (BundleAdjustmentOptions::CreateLossFunction; the mapper's local BA): the Jacobian
@@ -151,7 +146,6 @@ def test_ba_robust_loss_matches_oracle_on_gpu(loss_type, scale):
 
 
 @pytest.mark.gpu
-@FIRST_RUN
 @pytest.mark.parametrize("case", ["two_view", "partial_tracks_forced_points", "variable_image"])
 def test_reference_ba_config_cases_on_gpu(case):
     """bundle_adjustment_test.cc cases packed by dagsfm_b200.ba_config (the mirror of BundleAdjuster::SetUp,
@@ -194,7 +188,6 @@ def test_reference_ba_config_cases_on_gpu(case):
 
 
 @pytest.mark.gpu
-@FIRST_RUN
 def test_verify_variant_is_bit_identical_on_gpu(monkeypatch):
     """B2_VERIFY_VARIANT=1 (groups of eight + division-free Sampson decision): same bytes as the production instance."""
     from dagsfm_b200 import Camera, TwoViewGeometryVerifier, TwoViewOptions
@@ -215,7 +208,6 @@ def test_verify_variant_is_bit_identical_on_gpu(monkeypatch):
 
 
 @pytest.mark.gpu
-@FIRST_RUN
 def test_pair_major_schur_matches_production_on_gpu(monkeypatch):
     """B2_BA_SCHUR=blocks: same LM path and optimum as the production Schur kernel and the oracle."""
     from dagsfm_b200 import BundleAdjuster, BundleAdjustmentOptions
@@ -242,12 +234,9 @@ def test_pair_major_schur_matches_production_on_gpu(monkeypatch):
         assert abs(reprojection_rms(p_pm) - reprojection_rms(p_cpu)) < 1e-6
 
 
-FIRST_RUN_ITER = pytest.mark.xfail(strict=False, reason="first GPU execution of the ITERATIVE_SCHUR kernels (written after the "
-                                   "round's GPU budget was spent; verified on the CUDA emulator, tests/test_emu_ba.py)")
 
 
 @pytest.mark.gpu
-@FIRST_RUN_ITER
 @pytest.mark.parametrize("kw", [
     dict(n_img=12, n_pts=300, track_len=5, seed=4),
     dict(n_img=8, n_pts=80, track_len=5, seed=3, shared_camera=True),
@@ -297,7 +286,6 @@ def test_iterative_schur_matches_oracle_on_gpu(kw):
 
 
 @pytest.mark.gpu
-@FIRST_RUN_ITER
 def test_iterative_schur_is_selected_above_1000_images_on_gpu():
     from dagsfm_b200 import BundleAdjuster, BundleAdjustmentOptions
     from tests.ba_scene import copy_problem, make_ba_problem, reprojection_rms
@@ -319,8 +307,6 @@ def test_iterative_schur_is_selected_above_1000_images_on_gpu():
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="first GPU execution of relative_pose_kernel (written after the round's GPU budget was spent; "
-                   "verified on the CUDA emulator, tests/test_emu_verify.py)")
 def test_relative_pose_matches_oracle_on_gpu():
     """b2_verify_relative_pose (EstimateWithRelativePose's pose / triangulation-angle step) against the
     oracle, same cases as the emulator run."""
@@ -334,8 +320,6 @@ def test_relative_pose_matches_oracle_on_gpu():
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="first GPU execution of the general camera-model table (written after the round's GPU budget "
-                   "was spent; verified on the CUDA emulator and compiled for the host, tests/test_camera_models.py)")
 def test_every_camera_model_is_normalised_like_the_oracle_on_gpu():
     """Camera::ImageToWorld (incl. IterativeUndistortion) of all eleven reference models, with the parameter sets of the
     reference's camera_models_test.cc, as the verifier computes it on the device."""
@@ -355,8 +339,6 @@ def test_every_camera_model_is_normalised_like_the_oracle_on_gpu():
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="first GPU execution of the wide Jacobian layout (general camera models in the bundle adjuster; "
-                   "written after the round's GPU budget was spent, verified on the CUDA emulator: tests/test_emu_ba.py)")
 @pytest.mark.parametrize("camera", [(3, [1200.0, 500, 500, 0.05, -0.01]),
                                     (4, [1180.0, 1210.0, 505.0, 495.0, -0.12, 0.03, 0.001, -0.0015]),
                                     (8, [1200.0, 500, 500, 0.04])])
@@ -386,7 +368,6 @@ def test_ba_general_camera_models_match_oracle_on_gpu(camera, solver):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="first GPU execution of reprojection_error_kernel (verified on the CUDA emulator)")
 def test_mean_reprojection_error_matches_oracle_on_gpu():
     from dagsfm_b200 import BundleAdjuster, BundleAdjustmentOptions
     from tests.ba_scene import make_ba_problem
@@ -402,7 +383,6 @@ def test_mean_reprojection_error_matches_oracle_on_gpu():
 
 
 @pytest.mark.gpu
-@FIRST_RUN
 def test_guided_stage_chained_on_device_results_on_gpu():
     """match -> verify -> guided match with nothing but the final lists leaving the device: b2_match_guided_pairs_device
     reads the verifier's results in device memory; equal to the host-buffer guided call with the same geometries."""
@@ -445,8 +425,6 @@ def test_guided_stage_chained_on_device_results_on_gpu():
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="first GPU execution of relative_pose_kernel through the device-pointer entry (written after the "
-                   "round's GPU budget was spent; verified on the CUDA emulator, tests/test_emu_verify.py)")
 def test_verify_then_pose_chained_on_device_on_gpu():
     """b2_verify_pairs_device -> b2_verify_relative_pose_device on torch device buffers equals the host-buffer calls, and
     the kernel's own consistency check (an inlier list longer than its slot) turns into B2_ERR_INVALID."""
