@@ -204,6 +204,10 @@ def _tv():
         L.orc_two_view.restype = None
         L.orc_two_view_pairs_mt.argtypes = [vp, vp, vp, C.c_long, vp, vp, C.POINTER(OrcTvOptions), vp, i32, vp]
         L.orc_two_view_pairs_mt.restype = d
+        L.orc_two_view_pairs_mt2.argtypes = [vp, vp, vp, C.c_long, vp, vp, C.POINTER(OrcTvOptions), vp, i32, vp, vp]
+        L.orc_two_view_pairs_mt2.restype = d
+        L.orc_set_solver_stack.argtypes = [i32]; L.orc_set_solver_stack.restype = None
+        L.orc_get_solver_stack.argtypes = []; L.orc_get_solver_stack.restype = i32
         _tv_ready = True
     return L
 
@@ -232,8 +236,11 @@ def eight_point(p1, p2, essential=False):
 def e5(p1, p2, with_system=False):
     p1, p2 = _p(p1), _p(p2)
     out = np.zeros((10, 3, 3)); A = np.zeros((10, 20)); c = np.zeros(11)
-    n = _tv().orc_e5(len(p1), p1.ctypes.data, p2.ctypes.data, out.ctypes.data, A.ctypes.data, c.ctypes.data)
-    return (out[:n], A, c) if with_system else out[:n]
+    if with_system:   # the 10 x 20 system / determinant coefficients exist in the oracle's own stack only
+        n = _tv().orc_e5(len(p1), p1.ctypes.data, p2.ctypes.data, out.ctypes.data, A.ctypes.data, c.ctypes.data)
+        return out[:n], A, c
+    n = _tv().orc_e5(len(p1), p1.ctypes.data, p2.ctypes.data, out.ctypes.data, None, None)
+    return out[:n]
 
 
 def h_dlt(p1, p2):
@@ -352,6 +359,31 @@ def ransac(est_type, X, Y, max_error, min_inlier_ratio=0.1, confidence=0.99, min
                           C.byref(ni), C.byref(rs), C.byref(nt), mask.ctypes.data)
     return {"success": bool(ok), "model": model, "num_inliers": ni.value, "residual_sum": rs.value,
             "num_trials": nt.value, "mask": mask[:n].astype(bool)}
+
+
+def set_solver_stack(stack: int) -> None:
+    """0 = the oracle's own floating-point solver stack (sequential sums; the default, pinned to the reference's
+    goldens); 1 = the same algorithms evaluated in the CUDA path's operation order (host build of
+    dagsfm_b200/csrc/verify_solvers.cuh + the warp-order QR / Jacobi restated in twoview_oracle.cc), against which the
+    GPU parity tests assert 100 % identity.  Process-wide."""
+    _tv().orc_set_solver_stack(int(stack))
+
+
+def get_solver_stack() -> int:
+    return int(_tv().orc_get_solver_stack())
+
+
+class solver_stack:
+    """with solver_stack(1): ... -- scoped selection, restores the previous stack."""
+    def __init__(self, stack):
+        self.stack = stack
+
+    def __enter__(self):
+        self.prev = get_solver_stack()
+        set_solver_stack(self.stack)
+
+    def __exit__(self, *a):
+        set_solver_stack(self.prev)
 
 
 def two_view(cam1, pts1, cam2, pts2, matches, opt=None, seed=0):

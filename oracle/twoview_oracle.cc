@@ -831,11 +831,257 @@ static void TranslationResiduals(const std::vector<Vec2>& p1, const std::vector<
   }
 }
 
+// ------------------------------------------------------------------ second solver stack ("device order")
+// The reference's linear algebra is Eigen, which is absent, so ANY restatement is one particular floating-point
+// implementation of the same solvers.  Stack 0 (default, everything above) is this oracle's own: sequential sums,
+// pinned to the reference's Matlab goldens.  Stack 1 evaluates the SAME algorithms in the operation order of the
+// CUDA path: the minimal solvers and the model finishers are the product's solver source compiled for the host
+// (dagsfm_b200/csrc/verify_solvers.cuh -- plain C++ once the CUDA qualifiers are defined away; the pins above are
+// replayed on it by tests/test_host_solvers.py and tests/test_oracle_twoview.py), and the over-determined local
+// estimators below restate verify_kernel.cu's warp-cooperative Householder QR / one-sided Jacobi / Hartley
+// statistics with their lane-strided partial sums and xor-butterfly reductions.  With one floating-point stack on
+// both sides a verification result is a deterministic function of (input, seed), and the GPU parity tests assert
+// 100 % identity against it instead of the agreement rate two independent stacks reach on ill-conditioned solves.
+}  // namespace tv
+#define __device__
+#define __constant__ static
+#define __forceinline__ inline
+#define __noinline__
+#include "../dagsfm_b200/csrc/verify_solvers.cuh"
+#undef __device__
+#undef __constant__
+#undef __forceinline__
+#undef __noinline__
+namespace tv {
+static int g_solver_stack = 0;
+
+namespace dev {
+namespace vf = ::b2::vf;
+// sum over the 32 lanes as `for (o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(full, v, o)` leaves it in every lane
+static double butterfly(double* part) {
+  for (int o = 16; o > 0; o >>= 1) {
+    double nw[32];
+    for (int l = 0; l < 32; ++l) nw[l] = part[l] + part[l ^ o];
+    for (int l = 0; l < 32; ++l) part[l] = nw[l];
+  }
+  return part[0];
+}
+// lane l accumulates term(i) for i = l, l + 32, ... < n in that order (terms with !pred(i) skipped), then the butterfly
+template <typename T, typename P>
+static double warp_sum(int n, T term, P pred) {
+  double part[32];
+  for (int l = 0; l < 32; ++l) {
+    double a = 0;
+    for (int i = l; i < n; i += 32)
+      if (pred(i)) a += term(i);
+    part[l] = a;
+  }
+  return butterfly(part);
+}
+template <typename T>
+static double warp_sum(int n, T term) { return warp_sum(n, term, [](int) { return true; }); }
+
+// verify_kernel.cu: warp_jacobi9.  G: rows x 9 column-major (G[c * ld + r]); V 9 x 9 row-major, sig[9].
+static void warp_jacobi9(double* G, int rows, int ld, double* V, double* sig) {
+  for (int i = 0; i < 81; ++i) V[i] = (i / 9 == i % 9) ? 1.0 : 0.0;
+  double frob2;
+  {
+    double part[32];
+    for (int l = 0; l < 32; ++l) {
+      double a = 0;
+      for (int c = 0; c < 9; ++c)
+        for (int i = l; i < rows; i += 32) a += G[(size_t)c * ld + i] * G[(size_t)c * ld + i];
+      part[l] = a;
+    }
+    frob2 = butterfly(part);
+  }
+  const double tiny = frob2 * 1e-40;
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    bool rotated = false;
+    for (int p = 0; p < 8; ++p) {
+      for (int q = p + 1; q < 9; ++q) {
+        double* gp = G + (size_t)p * ld;
+        double* gq = G + (size_t)q * ld;
+        const double alpha = warp_sum(rows, [&](int i) { return gp[i] * gp[i]; });
+        const double beta = warp_sum(rows, [&](int i) { return gq[i] * gq[i]; });
+        const double gamma = warp_sum(rows, [&](int i) { return gp[i] * gq[i]; });
+        if (gamma == 0.0 || (alpha <= tiny || beta <= tiny) || fabs(gamma) <= vf::kEps * sqrt(alpha * beta)) continue;
+        rotated = true;
+        const double zeta = (beta - alpha) / (2.0 * gamma);
+        const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        const double c = 1.0 / sqrt(1.0 + t * t);
+        const double s = c * t;
+        for (int i = 0; i < rows; ++i) {
+          const double a = gp[i], b = gq[i];
+          gp[i] = c * a - s * b;
+          gq[i] = s * a + c * b;
+        }
+        for (int l = 0; l < 9; ++l) {
+          const double a = V[l * 9 + p], b = V[l * 9 + q];
+          V[l * 9 + p] = c * a - s * b;
+          V[l * 9 + q] = s * a + c * b;
+        }
+      }
+    }
+    if (!rotated) break;
+  }
+  double nrm[9];
+  for (int j = 0; j < 9; ++j) {
+    const double* g = G + (size_t)j * ld;
+    nrm[j] = sqrt(warp_sum(rows, [&](int i) { return g[i] * g[i]; }));
+  }
+  int order[9];
+  for (int j = 0; j < 9; ++j) {
+    int rank = 0;
+    for (int i = 0; i < 9; ++i) rank += (nrm[i] > nrm[j] || (nrm[i] == nrm[j] && i < j)) ? 1 : 0;
+    order[rank] = j;
+  }
+  double W[81];
+  for (int l = 0; l < 9; ++l)
+    for (int j = 0; j < 9; ++j) W[l * 9 + j] = V[l * 9 + order[j]];
+  memcpy(V, W, sizeof W);
+  for (int l = 0; l < 9; ++l) sig[l] = nrm[order[l]];
+}
+// verify_kernel.cu: warp_qr9.  G destroyed; R 9 x 9 column-major.
+static void warp_qr9(double* G, int rows, int ld, double* R) {
+  for (int i = 0; i < 81; ++i) R[i] = 0.0;
+  for (int k = 0; k < 9; ++k) {
+    double* gk = G + (size_t)k * ld;
+    const int nj = 8 - k;
+    auto below = [&](int r) { return r > k; };
+    const double s = warp_sum(rows, [&](int r) { return gk[r] * gk[r]; }, below);
+    double w[8];
+    for (int jj = 0; jj < 8; ++jj)
+      w[jj] = jj < nj ? warp_sum(rows, [&](int r) { return gk[r] * gk[(size_t)(jj + 1) * ld + r]; }, below) : 0.0;
+    const double x0 = gk[k];
+    const double nrm = sqrt(x0 * x0 + s);
+    if (nrm == 0.0) {
+      for (int j = k + 1; j < 9; ++j) R[j * 9 + k] = G[(size_t)j * ld + k];
+      continue;
+    }
+    const double v0 = x0 + (x0 >= 0 ? nrm : -nrm);
+    const double beta = 2.0 / (v0 * v0 + s);
+    for (int jj = 0; jj < nj; ++jj) {
+      const double gkj = gk[(size_t)(jj + 1) * ld + k];
+      w[jj] = (w[jj] + v0 * gkj) * beta;
+      R[(k + 1 + jj) * 9 + k] = gkj - w[jj] * v0;
+    }
+    for (int r = k + 1; r < rows; ++r) {
+      const double a = gk[r];
+      for (int jj = 0; jj < nj; ++jj) gk[(size_t)(jj + 1) * ld + r] -= w[jj] * a;
+    }
+    R[k * 9 + k] = (x0 >= 0 ? -nrm : nrm);
+  }
+}
+static void warp_svd9(double* G, int rows, int ld, double* V, double* sig) {
+  if (rows > 9) {
+    double R[81];
+    warp_qr9(G, rows, ld, R);
+    warp_jacobi9(R, 9, 9, V, sig);
+  } else {
+    warp_jacobi9(G, rows, ld, V, sig);
+  }
+}
+// verify_kernel.cu: warp_hartley + apply_T
+static void warp_hartley(const std::vector<Vec2>& P, double* T) {
+  const int N = (int)P.size();
+  double cx = warp_sum(N, [&](int k) { return P[k].x; });
+  double cy = warp_sum(N, [&](int k) { return P[k].y; });
+  cx /= N;
+  cy /= N;
+  double rms = warp_sum(N, [&](int k) {
+    const double dx = P[k].x - cx, dy = P[k].y - cy;
+    return dx * dx + dy * dy;
+  });
+  rms = sqrt(rms / N);
+  const double nf = sqrt(2.0) / rms;
+  T[0] = nf; T[1] = 0; T[2] = -nf * cx; T[3] = 0; T[4] = nf; T[5] = -nf * cy; T[6] = 0; T[7] = 0; T[8] = 1;
+}
+static Vec2 apply_T(const double* T, Vec2 p) {
+  const double n0 = T[0] * p.x + T[1] * p.y + T[2];
+  const double n1 = T[3] * p.x + T[4] * p.y + T[5];
+  const double n2 = T[6] * p.x + T[7] * p.y + T[8];
+  const double inv = 1.0 / n2;
+  return Vec2{n0 * inv, n1 * inv};
+}
+static std::vector<Mat3> to_models(const double* m, int nm) {
+  std::vector<Mat3> out((size_t)nm);
+  for (int j = 0; j < nm; ++j) memcpy(out[j].m, m + 9 * j, 72);
+  return out;
+}
+static void interleave(const std::vector<Vec2>& a, double* out) {
+  for (size_t i = 0; i < a.size(); ++i) { out[2 * i] = a[i].x; out[2 * i + 1] = a[i].y; }
+}
+// minimal solvers: the product's own per-lane code (verify_solvers.cuh) on a private workspace
+static std::vector<Mat3> Estimate(int t, const std::vector<Vec2>& a, const std::vector<Vec2>& b) {
+  double ws[vf::kLaneWorkDoubles + 8], p1[16], p2[16], models[90];
+  interleave(a, p1);
+  interleave(b, p2);
+  int nm = 0;
+  if (t == 0) nm = vf::solve_e5(vf::View<1>{ws}, p1, p2, models);
+  else if (t == 1) nm = vf::solve_f7(vf::View<1>{ws}, p1, p2, models);
+  else nm = vf::solve_h4(vf::View<1>{ws}, p1, p2, models);
+  return to_models(models, nm);
+}
+// verify_kernel.cu: local_estimate (E 5-point on N points, F 8-point, H DLT)
+static std::vector<Mat3> LocalEstimate(int t, const std::vector<Vec2>& P1, const std::vector<Vec2>& P2) {
+  const int N = (int)P1.size();
+  const int ld = 2 * N;
+  std::vector<double> Gv((size_t)9 * ld, 0.0);
+  double* G = Gv.data();
+  double V[81], sig[9], models[90];
+  if (t == 0) {
+    for (int k = 0; k < N; ++k) {
+      const Vec2 a = P1[k], b = P2[k];
+      G[0 * (size_t)ld + k] = a.x * b.x; G[1 * (size_t)ld + k] = a.y * b.x; G[2 * (size_t)ld + k] = b.x;
+      G[3 * (size_t)ld + k] = a.x * b.y; G[4 * (size_t)ld + k] = a.y * b.y; G[5 * (size_t)ld + k] = b.y;
+      G[6 * (size_t)ld + k] = a.x; G[7 * (size_t)ld + k] = a.y; G[8 * (size_t)ld + k] = 1;
+    }
+    warp_svd9(G, N, ld, V, sig);
+    double Eb[36];
+    for (int k = 0; k < 4; ++k)
+      for (int i = 0; i < 9; ++i) Eb[9 * k + i] = V[i * 9 + 5 + k];
+    const int nm = vf::solve_e5_from_basis(Eb, models);
+    return to_models(models, nm);
+  }
+  double T1[9], T2[9];
+  warp_hartley(P1, T1);
+  warp_hartley(P2, T2);
+  int rows;
+  if (t == 1) {
+    rows = N;
+    for (int k = 0; k < N; ++k) {
+      const Vec2 a = apply_T(T1, P1[k]), b = apply_T(T2, P2[k]);
+      G[0 * (size_t)ld + k] = a.x * b.x; G[1 * (size_t)ld + k] = a.y * b.x; G[2 * (size_t)ld + k] = 1.0 * b.x;
+      G[3 * (size_t)ld + k] = a.x * b.y; G[4 * (size_t)ld + k] = a.y * b.y; G[5 * (size_t)ld + k] = 1.0 * b.y;
+      G[6 * (size_t)ld + k] = a.x; G[7 * (size_t)ld + k] = a.y; G[8 * (size_t)ld + k] = 1.0;
+    }
+  } else {
+    rows = 2 * N;
+    for (int k = 0; k < N; ++k) {
+      const Vec2 s = apply_T(T1, P1[k]), d = apply_T(T2, P2[k]);
+      const int j = N + k;
+      G[0 * (size_t)ld + k] = -s.x; G[1 * (size_t)ld + k] = -s.y; G[2 * (size_t)ld + k] = -1;
+      G[6 * (size_t)ld + k] = s.x * d.x; G[7 * (size_t)ld + k] = s.y * d.x; G[8 * (size_t)ld + k] = d.x;
+      G[3 * (size_t)ld + j] = -s.x; G[4 * (size_t)ld + j] = -s.y; G[5 * (size_t)ld + j] = -1;
+      G[6 * (size_t)ld + j] = s.x * d.y; G[7 * (size_t)ld + j] = s.y * d.y; G[8 * (size_t)ld + j] = d.y;
+    }
+  }
+  warp_svd9(G, rows, ld, V, sig);
+  double nv[9];
+  for (int k = 0; k < 9; ++k) nv[k] = V[k * 9 + 8];
+  if (t == 1) vf::finish_f8(nv, T1, T2, models);
+  else vf::finish_h(nv, T1, T2, models);
+  return to_models(models, 1);
+}
+}  // namespace dev
+
 // ------------------------------------------------------------------ RANSAC
 enum EstType { EST_E5 = 0, EST_F7 = 1, EST_H4 = 2, EST_T2 = 3 };
 static int MinSamples(int t) { return t == EST_E5 ? 5 : t == EST_F7 ? 7 : t == EST_H4 ? 4 : 1; }
 static int LocalMinSamples(int t) { return t == EST_E5 ? 5 : t == EST_F7 ? 8 : t == EST_H4 ? 4 : 1; }
 static std::vector<Mat3> Estimate(int t, const std::vector<Vec2>& a, const std::vector<Vec2>& b) {
+  if (g_solver_stack == 1 && t != EST_T2) return dev::Estimate(t, a, b);
   switch (t) {
     case EST_E5: return E5(a, b);
     case EST_F7: return F7(a, b);
@@ -844,6 +1090,7 @@ static std::vector<Mat3> Estimate(int t, const std::vector<Vec2>& a, const std::
   }
 }
 static std::vector<Mat3> LocalEstimate(int t, const std::vector<Vec2>& a, const std::vector<Vec2>& b) {
+  if (g_solver_stack == 1 && t != EST_T2) return dev::LocalEstimate(t, a, b);
   switch (t) {
     case EST_E5: return E5(a, b);
     case EST_F7: return EightPoint(a, b, false);
@@ -1595,14 +1842,35 @@ static int put_models(const std::vector<tv::Mat3>& ms, double* out, int cap) {
   return n;
 }
 
-int orc_f7(const double* p1, const double* p2, double* out) { return put_models(tv::F7(to_vec(p1, 7), to_vec(p2, 7)), out, 3); }
+// 0: the oracle's own solver stack (default); 1: the CUDA path's operation order (see "second solver stack" above).
+// Process-wide; set it before running, not concurrently with a run.
+void orc_set_solver_stack(int stack) { tv::g_solver_stack = stack == 1 ? 1 : 0; }
+int orc_get_solver_stack() { return tv::g_solver_stack; }
+// The solver entry points follow the selected stack, so that the reference's golden vectors are replayed on both
+// (the essential 8-point variant and the 5-point system dump exist in stack 0 only).
+int orc_f7(const double* p1, const double* p2, double* out) {
+  if (tv::g_solver_stack == 1) return put_models(tv::dev::Estimate(tv::EST_F7, to_vec(p1, 7), to_vec(p2, 7)), out, 3);
+  return put_models(tv::F7(to_vec(p1, 7), to_vec(p2, 7)), out, 3);
+}
 int orc_eight_point(int n, const double* p1, const double* p2, int essential, double* out) {
+  if (tv::g_solver_stack == 1 && !essential && n >= 8)
+    return put_models(tv::dev::LocalEstimate(tv::EST_F7, to_vec(p1, n), to_vec(p2, n)), out, 1);
   return put_models(tv::EightPoint(to_vec(p1, n), to_vec(p2, n), essential != 0), out, 1);
 }
 int orc_e5(int n, const double* p1, const double* p2, double* out, double* A_out, double* coeffs_out) {
+  if (tv::g_solver_stack == 1 && !A_out && !coeffs_out) {
+    if (n == 5) return put_models(tv::dev::Estimate(tv::EST_E5, to_vec(p1, n), to_vec(p2, n)), out, 10);
+    return put_models(tv::dev::LocalEstimate(tv::EST_E5, to_vec(p1, n), to_vec(p2, n)), out, 10);
+  }
   return put_models(tv::E5(to_vec(p1, n), to_vec(p2, n), A_out, coeffs_out), out, 10);
 }
-int orc_h_dlt(int n, const double* p1, const double* p2, double* out) { return put_models(tv::HomographyDLT(to_vec(p1, n), to_vec(p2, n)), out, 1); }
+int orc_h_dlt(int n, const double* p1, const double* p2, double* out) {
+  if (tv::g_solver_stack == 1) {
+    if (n == 4) return put_models(tv::dev::Estimate(tv::EST_H4, to_vec(p1, n), to_vec(p2, n)), out, 1);
+    return put_models(tv::dev::LocalEstimate(tv::EST_H4, to_vec(p1, n), to_vec(p2, n)), out, 1);
+  }
+  return put_models(tv::HomographyDLT(to_vec(p1, n), to_vec(p2, n)), out, 1);
+}
 void orc_e5_system(const double* basis /*4x9*/, double* A /*10x20*/) {
   double Eb[4][9];
   memcpy(Eb, basis, sizeof Eb);
@@ -1772,6 +2040,28 @@ double orc_two_view_pairs_mt(const orc_camera* cams, const double* const* pts, c
         const int m = (int)(match_off[p + 1] - match_off[p]);
         inl.resize(2 * (size_t)std::max(m, 1));
         orc_two_view(&cams[i1], pts[i1], &cams[i2], pts[i2], matches + 2 * match_off[p], m, opt, seeds[p], &results[p], inl.data());
+      }
+    });
+  }
+  for (auto& x : th) x.join();
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+// ... the same, keeping every pair's inlier matches (the parity tests compare the lists)
+double orc_two_view_pairs_mt2(const orc_camera* cams, const double* const* pts, const uint32_t* pairs, long n_pairs,
+                             const int64_t* match_off, const uint32_t* matches, const orc_tv_options* opt,
+                             const uint32_t* seeds, int n_threads, orc_tv_result* results,
+                              uint32_t* inliers /* [total matches][2]: pair p's inlier matches at match_off[p] */) {
+  std::atomic<long> next(0);
+  const auto t0 = std::chrono::steady_clock::now();
+  std::vector<std::thread> th;
+  for (int t = 0; t < n_threads; ++t) {
+    th.emplace_back([&]() {
+      for (;;) {
+        const long p = next.fetch_add(1);
+        if (p >= n_pairs) break;
+        const uint32_t i1 = pairs[2 * p], i2 = pairs[2 * p + 1];
+        const int m = (int)(match_off[p + 1] - match_off[p]);
+        orc_two_view(&cams[i1], pts[i1], &cams[i2], pts[i2], matches + 2 * match_off[p], m, opt, seeds[p], &results[p], inliers + 2 * match_off[p]);
       }
     });
   }

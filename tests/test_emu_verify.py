@@ -97,8 +97,18 @@ def test_two_view_decisions_equal_oracle(ver):
     cfgs = []
     for i in range(len(specs)):
         c = orc.make_camera(prior=priors[i])
-        r, oi = orc.two_view(c, kps[2 * i], c, kps[2 * i + 1], ms[i], oopt, seed=int(seeds[i]))
+        # the oracle evaluated in the kernel's own operation order (its "device-order" solver stack): one floating-point
+        # stack on both sides, so the model matrices must agree bit for bit, not only the decisions
+        with orc.solver_stack(1):
+            r1, oi1 = orc.two_view(c, kps[2 * i], c, kps[2 * i + 1], ms[i], oopt, seed=int(seeds[i]))
         g = res[i]
+        for m in ("E", "F", "H"):
+            assert np.array_equal(np.array(getattr(r1, m)[:]).view(np.uint64), g[m].view(np.uint64)), (i, m)
+        assert (g["config"], g["n_inliers"], g["E_num_trials"], g["F_num_trials"], g["H_num_trials"]) == \
+               (r1.config, r1.n_inliers, r1.E_trials, r1.F_trials, r1.H_trials)
+        assert inl[offs[i]:offs[i] + r1.n_inliers].tolist() == oi1.tolist()
+        # ... and in its independent stack (sequential sums): the same decisions
+        r, oi = orc.two_view(c, kps[2 * i], c, kps[2 * i + 1], ms[i], oopt, seed=int(seeds[i]))
         assert (g["config"], g["n_inliers"], g["E_num_inliers"], g["F_num_inliers"], g["H_num_inliers"]) == \
                (r.config, r.n_inliers, r.E_inl, r.F_inl, r.H_inl), i
         assert (g["E_num_trials"], g["F_num_trials"], g["H_num_trials"]) == (r.E_trials, r.F_trials, r.H_trials)

@@ -5,10 +5,20 @@ against values evaluated from the reference's generated headers (tests/golden)."
 from pathlib import Path
 
 import numpy as np
+import pytest
 
 from oracle import pyoracle as orc
 
 GOLD = Path(__file__).resolve().parent / "golden"
+
+
+@pytest.fixture(autouse=True, params=[0, 1], ids=["own_stack", "device_order_stack"])
+def solver_stack(request):
+    """Every pin below is replayed on both floating-point solver stacks of the oracle (oracle/twoview_oracle.cc,
+    "second solver stack"): 0 = its own sequential-sum restatement, 1 = the CUDA path's operation order (host build of
+    the product's solver source + the warp-order QR / Jacobi), the one the GPU parity tests assert 100 % identity with."""
+    with orc.solver_stack(request.param):
+        yield request.param
 
 P1_7 = np.array([0.4964, 1.0577, 0.3650, -0.0919, -0.5412, 0.0159, -0.5239, 0.9467, 0.3467, 0.5301,
                  0.2797, 0.0012, -0.1986, 0.0460]).reshape(7, 2)
