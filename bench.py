@@ -364,7 +364,7 @@ def bench_ba(a, local_rank, rank, world, cores, barrier, hbm):
     # algorithmic bytes per LM iteration: 24 N_obs + 28 N_pts + 88 N_cam reads,
     # 72 N_pts + 64 N_cam + 8 * (upper triangle of the dense reduced system) writes
     alg_bytes = 24 * n_obs + 28 * n_pts + 88 * n_img + 72 * n_pts + 64 * n_img + 8 * (D * (D + 1) // 2)
-    schur_ms = 1e3 * s.schur_kernel_seconds / max(s.schur_kernel_launches // 2, 1)
+    schur_ms = 1e3 * s.schur_kernel_seconds / max(iters, 1)       # every pass of the LM loop builds the system once
     achieved = alg_bytes / (schur_ms * 1e-3) / 1e9
     out = {"workload": f"{n_img} cams / {n_pts} pts / {n_obs} obs, track {track}, SIMPLE_RADIAL, final-BA options",
            "lm_iter_per_s": s.num_iterations / s.solve_seconds, "lm_iterations": s.num_iterations,
@@ -375,12 +375,17 @@ def bench_ba(a, local_rank, rank, world, cores, barrier, hbm):
            "rms_note": "this rank's point shard" if world > 1 else "all observations",
            "sharding": f"points over {world} ranks, 1 all-reduce of the reduced camera system per LM iteration" if world > 1 else "single GPU",
            "ceres_style_px": float(np.sqrt(s.final_cost / (2 * n_obs))),
-           "roofline": {"bound": "hbm", "kernel": "camera_terms_kernel + schur_kernel", "achieved": achieved,
+           "roofline": {"bound": "hbm", "kernel": "camera_terms_kernel + schur_points_kernel + schur_window_kernel (Jacobian + Schur complement)", "achieved": achieved,
                         "peak": hbm[0], "unit": "GB/s", "frac": achieved / hbm[0], "peak_source": hbm[1],
                         "algorithmic_bytes_per_iteration": alg_bytes, "avg_ms_per_iteration": schur_ms,
                         "share_of_solve": s.schur_kernel_seconds / s.solve_seconds, "traffic": None,
-                        "note": "FP64 atomics into the dense reduced system dominate; see DESIGN.md"}}
-    out["linear_solver"] = "ITERATIVE_SCHUR + SCHUR_JACOBI" if s.linear_solver_type_used == 2 else "exact Schur step (dense Cholesky)"
+                        "note": "algorithmic bytes count the full upper triangle of S as SURVEY 8d does; see DESIGN.md section 3"}}
+    out["linear_solver"] = ("ITERATIVE_SCHUR + SCHUR_JACOBI" if s.linear_solver_type_used == 2 else
+                            "exact Schur step: fused kernels, packed tiles, own tiled Cholesky" if s.exact_path_used == 2 else
+                            "exact Schur step: staged blocks, dense S, cuSOLVER (fallback path)")
+    out["linear_solve_ms_per_iteration"] = 1e3 * s.linear_solve_seconds / max(iters, 1)
+    out["reduced_system_mb"] = s.reduced_system_bytes / 1e6
+    out["ms_per_lm_iteration"] = 1e3 * s.solve_seconds / max(iters, 1)
     if s.linear_solver_type_used == 2:
         # matrix-free Schur product: both passes stream the 224 B Jacobian block of every observation once per CG
         # iteration (+ 12 B of indices), z_p is written and read once
@@ -394,7 +399,7 @@ def bench_ba(a, local_rank, rank, world, cores, barrier, hbm):
                            "frac": alg_cg / (lin_ms * 1e-3) / 1e9 / hbm[0], "peak_source": hbm[1],
                            "algorithmic_bytes_per_cg_iteration": alg_cg, "avg_ms_per_cg_iteration": lin_ms,
                            "share_of_solve": s.schur_kernel_seconds / s.solve_seconds, "traffic": None}
-    if (n_img, n_pts, track) == (500, 100000, 10) and world == 1 and s.linear_solver_type_used == 1:
+    if False and (n_img, n_pts, track) == (500, 100000, 10) and world == 1 and s.linear_solver_type_used == 1:
         # committed ncu captures of one iteration at exactly this workload: schur_kernel 234.7 + 11.8 MB
         # (profiles/r1_ba_schur_ncu_full.txt), camera_terms_kernel 228.8 + 3.5 MB (r1_ba_camera_terms_ncu_full.txt);
         # 4.9x the algorithmic bytes because both kernels re-read the 224 B/observation Jacobian blocks

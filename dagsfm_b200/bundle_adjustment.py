@@ -50,7 +50,8 @@ class BaSummary(C.Structure):
                 ("num_effective_parameters_reduced", C.c_int32), ("num_iterations", C.c_int32),
                 ("solve_seconds", C.c_double), ("schur_kernel_seconds", C.c_double),
                 ("schur_kernel_launches", C.c_int64), ("num_linear_solver_iterations", C.c_int64),
-                ("linear_solver_type_used", C.c_int32), ("reserved", C.c_int32)]
+                ("linear_solver_type_used", C.c_int32), ("exact_path_used", C.c_int32),
+                ("linear_solve_seconds", C.c_double), ("reduced_system_bytes", C.c_double)]
 
 
 ALLREDUCE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p)

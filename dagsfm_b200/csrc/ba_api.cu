@@ -16,6 +16,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -38,7 +40,7 @@ struct b2_ba {
   b2_allreduce_fn allreduce = nullptr;
   void* allreduce_user = nullptr;
   std::vector<void*> allocs;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 namespace {
@@ -89,6 +91,134 @@ int sum_partials(b2_ba* h, const double* d_partial, int n, double* out) {
   for (int k = 0; k < n; ++k) s += hp[k];
   *out = s;
   return B2_OK;
+}
+
+// ------------------------------------------------------------------ fused exact path: host-side plan (once per solve)
+// The structure of a bundle-adjustment problem does not change across LM iterations, so everything that depends on
+// it alone is laid out here: the processing order of the points, the windows (chunks of points whose images fit NLOC
+// slots) of schur_window_kernel, and the tile pattern of the packed reduced system incl. the fill of its Cholesky factor.
+struct FusedPlan {
+  int nloc = 12;
+  std::vector<int32_t> pt_order, chunk_pt0, chunk_img;
+  std::vector<uint8_t> obs_slot;
+  int nt = 0, n_tiles = 0;
+  std::vector<uint8_t> tmap;                       // nt x nt, upper: structural non-zero
+  std::vector<int32_t> tile_id, row_ptr, row_col;  // packed layout (after finish_tiles)
+};
+constexpr int kChunkMaxPoints = 192;
+
+// false: some variable point does not fit a window (track longer than kWinMaxLoc, or one image twice) -> staged path
+bool plan_windows(const b2_ba_problem* pr, const std::vector<int64_t>& pt_start, const std::vector<int32_t>& pt_col, FusedPlan* F) {
+  const int n_pts = pr->n_points;
+  int max_len = 0;
+  std::vector<int64_t> key;  // (lowest image, highest image, point) packed for the sort
+  key.reserve(n_pts);
+  int32_t tmp[kWinMaxLoc];
+  for (int p = 0; p < n_pts; ++p) {
+    if (pt_col[p] < 0) continue;
+    const int64_t o0 = pt_start[p];
+    const int L = (int)(pt_start[p + 1] - o0);
+    if (L > kWinMaxLoc) return false;
+    if (L == 0) continue;
+    for (int a = 0; a < L; ++a) tmp[a] = pr->obs_image[o0 + a];
+    std::sort(tmp, tmp + L);
+    for (int a = 1; a < L; ++a)
+      if (tmp[a] == tmp[a - 1]) return false;
+    max_len = std::max(max_len, L);
+    if (pr->n_images >= (1 << 21) || n_pts >= (1 << 21)) return false;  // key packing below
+    key.push_back(((int64_t)tmp[0] << 42) | ((int64_t)tmp[L - 1] << 21) | (int64_t)p);
+  }
+  std::sort(key.begin(), key.end());
+  F->nloc = max_len <= 12 ? 12 : 16;
+  const int nloc = F->nloc;
+  F->obs_slot.assign((size_t)pr->n_obs, 0);
+  F->pt_order.clear();
+  F->chunk_pt0.assign(1, 0);
+  F->chunk_img.clear();
+  std::vector<int32_t> cur;  // images of the open chunk
+  int cur_pts = 0;
+  auto close_chunk = [&]() {
+    if (cur_pts == 0) return;
+    for (int k = 0; k < nloc; ++k) F->chunk_img.push_back(k < (int)cur.size() ? cur[k] : -1);
+    F->chunk_pt0.push_back((int32_t)F->pt_order.size());
+    cur.clear();
+    cur_pts = 0;
+  };
+  for (int64_t kv : key) {
+    const int p = (int)(kv & ((1 << 21) - 1));
+    const int64_t o0 = pt_start[p];
+    const int L = (int)(pt_start[p + 1] - o0);
+    int fresh = 0;
+    for (int a = 0; a < L; ++a)
+      fresh += std::find(cur.begin(), cur.end(), pr->obs_image[o0 + a]) == cur.end() ? 1 : 0;
+    if ((int)cur.size() + fresh > nloc || cur_pts >= kChunkMaxPoints) {
+      close_chunk();
+    }
+    for (int a = 0; a < L; ++a) {
+      const int32_t img = pr->obs_image[o0 + a];
+      auto it = std::find(cur.begin(), cur.end(), img);
+      if (it == cur.end()) { cur.push_back(img); it = cur.end() - 1; }
+      F->obs_slot[(size_t)(o0 + a)] = (uint8_t)(it - cur.begin());
+    }
+    F->pt_order.push_back(p);
+    ++cur_pts;
+  }
+  close_chunk();
+  return true;
+}
+
+// tile pattern of S before fill: every pair of columns that some window or some image's own block can touch
+void plan_tile_map(const b2_ba_problem* pr, const std::vector<int32_t>& pose_col, const std::vector<int32_t>& intr_col, int64_t D,
+                   FusedPlan* F) {
+  const int nt = (int)((D + kST - 1) / kST);
+  F->nt = nt;
+  F->tmap.assign((size_t)nt * nt, 0);
+  for (int t = 0; t < nt; ++t) F->tmap[(size_t)t * nt + t] = 1;
+  std::vector<int> tl;
+  auto mark_images = [&](const int32_t* imgs, int n) {
+    tl.clear();
+    for (int k = 0; k < n; ++k) {
+      const int i = imgs[k];
+      if (i < 0) continue;
+      for (int c = 0; c < 6; ++c)
+        if (pose_col[6 * (size_t)i + c] >= 0) tl.push_back(pose_col[6 * (size_t)i + c] / kST);
+      const int cm = pr->image_camera[i];
+      for (int c = 0; c < 4; ++c)
+        if (intr_col[4 * (size_t)cm + c] >= 0) tl.push_back(intr_col[4 * (size_t)cm + c] / kST);
+    }
+    std::sort(tl.begin(), tl.end());
+    tl.erase(std::unique(tl.begin(), tl.end()), tl.end());
+    for (size_t a = 0; a < tl.size(); ++a)
+      for (size_t b = a; b < tl.size(); ++b) F->tmap[(size_t)tl[a] * nt + tl[b]] = 1;
+  };
+  const int n_chunks = (int)F->chunk_pt0.size() - 1;
+  for (int c = 0; c < n_chunks; ++c) mark_images(&F->chunk_img[(size_t)c * F->nloc], F->nloc);
+  for (int32_t i = 0; i < pr->n_images; ++i) mark_images(&i, 1);
+}
+
+// symbolic right-looking fill + packed layout (CSR by tile row, diagonal tile first)
+void finish_tiles(FusedPlan* F) {
+  const int nt = F->nt;
+  std::vector<int> cols;
+  for (int k = 0; k < nt; ++k) {
+    cols.clear();
+    for (int j = k + 1; j < nt; ++j)
+      if (F->tmap[(size_t)k * nt + j]) cols.push_back(j);
+    for (size_t a = 0; a < cols.size(); ++a)
+      for (size_t b = a; b < cols.size(); ++b) F->tmap[(size_t)cols[a] * nt + cols[b]] = 1;
+  }
+  F->tile_id.assign((size_t)nt * nt, -1);
+  F->row_ptr.assign(nt + 1, 0);
+  F->row_col.clear();
+  for (int k = 0; k < nt; ++k) {
+    for (int j = k; j < nt; ++j)
+      if (F->tmap[(size_t)k * nt + j]) {
+        F->tile_id[(size_t)k * nt + j] = (int32_t)F->row_col.size();
+        F->row_col.push_back(j);
+      }
+    F->row_ptr[k + 1] = (int32_t)F->row_col.size();
+  }
+  F->n_tiles = (int)F->row_col.size();
 }
 
 struct CgVectors { double *x, *r, *p, *q, *tmp, *partial; };
@@ -230,10 +360,48 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
   const bool iterative = opt->linear_solver_type == 2 || (opt->linear_solver_type == 0 && n_img > 1000);
   sum->linear_solver_type_used = iterative ? 2 : 1;
   sum->num_linear_solver_iterations = 0;
-  {  // exact path: the reduced camera system is dense, D x D doubles must fit in this GPU's memory
+  std::vector<int64_t> pt_start(n_pts + 1, 0);
+  for (int64_t o = 0; o < n_obs; ++o) pt_start[pr->obs_point[o] + 1]++;
+  for (int p = 0; p < n_pts; ++p) pt_start[p + 1] += pt_start[p];
+  // Exact step: the fused path (ba_fused.cu + ba_chol.cu: no staged Jacobian blocks, packed tiles, own Cholesky) whenever
+  // the problem qualifies -- 4-slot camera models, every variable track inside a window; B2_BA_EXACT=staged forces the
+  // first-generation path (staged ObsJac, dense S, cuSOLVER), which also serves everything that does not qualify.
+  FusedPlan plan;
+  bool fused = !iterative && !wide && n_obs > 0 && n_obs < 0x7fffffffLL && D > 0;
+  if (const char* e = getenv("B2_BA_EXACT")) fused = fused && strcmp(e, "staged") != 0;
+  if (fused) fused = plan_windows(pr, pt_start, pt_col, &plan);
+  if (h->allreduce) {  // every rank must take the same path: MIN over the ranks of the local decision
+    double* d_flag = nullptr;
+    B2_TRY(dev_alloc(h, &d_flag, 1));
+    const double mine = fused ? 0.0 : 1.0;
+    B2_CUDA(cudaMemcpyAsync(d_flag, &mine, 8, cudaMemcpyHostToDevice, s));
+    B2_TRY(sync_reduce(h, d_flag, 1, 1));
+    double any_staged = 0;
+    B2_CUDA(cudaMemcpyAsync(&any_staged, d_flag, 8, cudaMemcpyDeviceToHost, s));
+    B2_CUDA(cudaStreamSynchronize(s));
+    fused = fused && any_staged == 0.0;
+  }
+  if (fused) {
+    plan_tile_map(pr, pose_col, intr_col, D, &plan);
+    if (h->allreduce) {  // union of the ranks' tile patterns (each rank sees its own points only)
+      std::vector<double> m(plan.tmap.begin(), plan.tmap.end());
+      double* d_m = nullptr;
+      B2_TRY(dev_upload(h, &d_m, (const double*)m.data(), m.size()));
+      B2_TRY(sync_reduce(h, d_m, (int64_t)m.size(), 1));
+      B2_CUDA(cudaMemcpyAsync(m.data(), d_m, m.size() * 8, cudaMemcpyDeviceToHost, s));
+      B2_CUDA(cudaStreamSynchronize(s));
+      for (size_t k = 0; k < m.size(); ++k) plan.tmap[k] = m[k] != 0.0 ? 1 : 0;
+    }
+    finish_tiles(&plan);
+  }
+  sum->exact_path_used = iterative ? 0 : (fused ? 2 : 1);
+  sum->linear_solve_seconds = 0;
+  sum->reduced_system_bytes = 0;
+  {  // exact path: the reduced camera system must fit in this GPU's memory
     size_t free_b = 0, total_b = 0;
     B2_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    const double need = (iterative ? 24.0 * (double)D : (double)D * (double)D + 3.0 * (double)D) * 8.0 +
+    const double need = fused ? ((double)plan.n_tiles * kST * kST + (double)plan.nt * kST * kST + 8.0 * (double)D) * 8.0 + (double)n_obs * 260.0
+                              : (iterative ? 24.0 * (double)D : (double)D * (double)D + 3.0 * (double)D) * 8.0 +
                         (double)n_obs * ((wide ? sizeof(ObsJacW) : sizeof(ObsJac)) + (iterative ? 4.0 : 0.0));
     if (need > 0.9 * (double)free_b)
       return set_error(B2_ERR_INVALID, iterative ? "problem too large for this GPU's memory"
@@ -241,9 +409,6 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
                                                    "(linear_solver_type = 2 selects ITERATIVE_SCHUR)");
   }
   if (iterative && n_obs >= 0x7fffffffLL) return set_error(B2_ERR_INVALID, "too many observations for ITERATIVE_SCHUR");
-  std::vector<int64_t> pt_start(n_pts + 1, 0);
-  for (int64_t o = 0; o < n_obs; ++o) pt_start[pr->obs_point[o] + 1]++;
-  for (int p = 0; p < n_pts; ++p) pt_start[p + 1] += pt_start[p];
 
   // Ceres' reduced program drops residual blocks whose parameter blocks are all constant
   // (bundle_adjustment_test.cc:360-364 counts 402, not 404, for exactly that reason)
@@ -303,20 +468,46 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
   B2_TRY(dev_alloc(h, &P.cam_new, (size_t)n_cam * KI));
   B2_TRY(dev_alloc(h, &P.xyz_new, (size_t)n_pts * 3));
   if (wide) B2_TRY(dev_alloc(h, &P.JW, (size_t)n_obs));
-  else B2_TRY(dev_alloc(h, &P.J, (size_t)n_obs));
+  else if (!fused) B2_TRY(dev_alloc(h, &P.J, (size_t)n_obs));  // the fused path never stages Jacobian blocks
   B2_TRY(dev_alloc(h, &P.scale_c, (size_t)D));
   B2_TRY(dev_alloc(h, &P.scale_p, (size_t)NP * 3));
   B2_TRY(dev_alloc(h, &P.colnorm_c, (size_t)D));
   B2_TRY(dev_alloc(h, &P.colnorm_p, (size_t)NP * 3));
   double* reduced;  // S | rhs | g_c | diag_c : one buffer, one all-reduce
-  const size_t n_reduced = (iterative ? 0 : (size_t)D * D) + 3 * (size_t)D;  // S is never formed by ITERATIVE_SCHUR
+  // S is never formed by ITERATIVE_SCHUR; the fused path keeps it in packed tiles and pads the vectors to whole tiles
+  const size_t Dv = fused ? (size_t)plan.nt * kST : (size_t)D;
+  const size_t n_reduced = (iterative ? 0 : fused ? (size_t)plan.n_tiles * kST * kST : (size_t)D * D) + 3 * Dv;
   B2_TRY(dev_alloc(h, &reduced, n_reduced));
-  P.S = iterative ? nullptr : reduced; P.rhs = reduced + (n_reduced - 3 * (size_t)D); P.g_c = P.rhs + D; P.diag_c = P.g_c + D;
+  P.S = (iterative || fused) ? nullptr : reduced; P.rhs = reduced + (n_reduced - 3 * Dv); P.g_c = P.rhs + Dv; P.diag_c = P.g_c + Dv;
+  sum->reduced_system_bytes = (double)n_reduced * 8.0;
   B2_TRY(dev_alloc(h, &P.diag_p, (size_t)NP * 3));
   B2_TRY(dev_alloc(h, &P.g_p, (size_t)NP * 3));
   B2_TRY(dev_alloc(h, &P.Vinv, (size_t)NP * 9));
-  B2_TRY(dev_alloc(h, &P.dc, (size_t)D));
+  B2_TRY(dev_alloc(h, &P.dc, Dv));
   B2_TRY(dev_alloc(h, &P.dp, (size_t)NP * 3));
+  BaTiles Tl;
+  memset(&Tl, 0, sizeof Tl);
+  BaWin Wn;
+  memset(&Wn, 0, sizeof Wn);
+  if (fused) {
+    int32_t *d_tile_id, *d_row_ptr, *d_row_col, *d_order, *d_cpt0, *d_cimg;
+    uint8_t* d_slot;
+    B2_TRY(dev_upload(h, &d_tile_id, (const int32_t*)plan.tile_id.data(), plan.tile_id.size()));
+    B2_TRY(dev_upload(h, &d_row_ptr, (const int32_t*)plan.row_ptr.data(), plan.row_ptr.size()));
+    B2_TRY(dev_upload(h, &d_row_col, (const int32_t*)plan.row_col.data(), plan.row_col.size()));
+    B2_TRY(dev_upload(h, &d_order, (const int32_t*)plan.pt_order.data(), plan.pt_order.size()));
+    B2_TRY(dev_upload(h, &d_cpt0, (const int32_t*)plan.chunk_pt0.data(), plan.chunk_pt0.size()));
+    B2_TRY(dev_upload(h, &d_cimg, (const int32_t*)plan.chunk_img.data(), plan.chunk_img.size()));
+    B2_TRY(dev_upload(h, &d_slot, (const uint8_t*)plan.obs_slot.data(), plan.obs_slot.size()));
+    Tl.nt = plan.nt; Tl.n_tiles = plan.n_tiles; Tl.tile_id = d_tile_id; Tl.row_ptr = d_row_ptr; Tl.row_col = d_row_col;
+    Tl.tiles = reduced;
+    B2_TRY(dev_alloc(h, &Tl.rinv, (size_t)plan.nt * kST * kST));
+    B2_TRY(dev_alloc(h, &Tl.info, 1));
+    Wn.n_chunks = (int32_t)plan.chunk_pt0.size() - 1; Wn.nloc = plan.nloc; Wn.chunk_pt0 = d_cpt0; Wn.pt_order = d_order;
+    Wn.chunk_img = d_cimg; Wn.obs_slot = d_slot;
+    B2_TRY(dev_alloc(h, &Wn.Z, (size_t)n_obs * 30));
+    B2_TRY(dev_alloc(h, &Wn.U, (size_t)n_pts * 3));
+  }
   double* scal;  // [0] step^2 cams [1] x^2 cams [2] step^2 pts [3] x^2 pts [4] model change [5] new cost [6] cost [7] gmax
   B2_TRY(dev_alloc(h, &scal, 8));
   P.gmax = scal + 7;
@@ -326,7 +517,7 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
   uint8_t* work = nullptr;
   size_t work_dev = 0, work_host = 0;
   std::vector<uint8_t> work_h;
-  if (D > 0 && !iterative) {
+  if (D > 0 && !iterative && !fused) {
     if (cusolverDnXpotrf_bufferSize(h->solver, h->solver_params, CUBLAS_FILL_MODE_LOWER, D, CUDA_R_64F, P.S, D,
                                     CUDA_R_64F, &work_dev, &work_host) != CUSOLVER_STATUS_SUCCESS)
       return set_error(B2_ERR_CUDA, "cusolverDnXpotrf_bufferSize failed");
@@ -341,7 +532,7 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
   // experimental (B2_BA_CAMTERMS=image): the exact path's camera terms summed per image before they touch S
   bool camterms_image = false;
   if (const char* e = getenv("B2_BA_CAMTERMS")) camterms_image = !iterative && strcmp(e, "image") == 0 && n_obs > 0 && n_obs < 0x7fffffffLL;
-  if (iterative || camterms_image) {
+  if (iterative || camterms_image || fused) {
     // observations grouped by image (counting sort of the point-major order) for the image-major pass
     std::vector<int64_t> img_start(n_img + 1, 0);
     for (int64_t o = 0; o < n_obs; ++o) img_start[pr->obs_image[o] + 1]++;
@@ -401,9 +592,11 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
   sum->initial_cost = cost;
 
   B2_CUDA(cudaEventRecord(h->ev[0], s));
-  B2_CUDA(cudaMemsetAsync(scal + 6, 0, 8, s));
-  B2_CUDA(ba_launch_jacobian(P, P.qvec, P.tvec, P.cam_params, P.xyz, 0, scal + 6, s, loss_type, loss_scale));
-  count_launches(1);
+  if (!fused) {
+    B2_CUDA(cudaMemsetAsync(scal + 6, 0, 8, s));
+    B2_CUDA(ba_launch_jacobian(P, P.qvec, P.tvec, P.cam_params, P.xyz, 0, scal + 6, s, loss_type, loss_scale));
+    count_launches(1);
+  }
 
   // Experimental pair-major Schur accumulation (B2_BA_SCHUR=blocks): the (lo, hi) observation tuples of
   // every (image, image) block are gathered once -- the structure is fixed across LM iterations --
@@ -414,7 +607,7 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
   uint32_t *pm_count = nullptr, *pm_start = nullptr;
   uint64_t* pm_tuples = nullptr;
   double *pm_W = nullptr, *pm_Y = nullptr;
-  if (const char* e = getenv("B2_BA_SCHUR")) pair_major = !iterative && !wide && strcmp(e, "blocks") == 0 && n_img > 0 && n_img <= 4096 && n_obs > 0;
+  if (const char* e = getenv("B2_BA_SCHUR")) pair_major = !iterative && !fused && !wide && strcmp(e, "blocks") == 0 && n_img > 0 && n_img <= 4096 && n_obs > 0;
   if (pair_major) {
     uint64_t n_tuples = 0;
     for (int p = 0; p < n_pts; ++p) {
@@ -442,7 +635,9 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
 
   double radius = 1e4, decrease_factor = 2.0;
   const double min_radius = 1e-32, max_radius = 1e16, min_rel_dec = 1e-3, min_diag = 1e-6, max_diag = 1e32;
-  double schur_ms = 0;
+  const char* dump_path = getenv("B2_BA_DUMP");  // debugging aid: the reduced system of the first iteration, raw doubles
+  const bool trace = getenv("B2_BA_TRACE") != nullptr;  // per-iteration line on stderr (debugging aid)
+  double schur_ms = 0, solve_ms = 0;
   int64_t schur_launches = 0;
   for (int iter = 0; iter < opt->max_num_iterations; ++iter) {
     // ---- normal equations of the camera block + Schur complement
@@ -487,6 +682,40 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
       }
       B2_CUDA(cudaEventRecord(h->ev[3], s));
       schur_launches += 2;
+    } else if (fused) {
+      // ---- fused exact step: camera terms + per-point Z + window products -> packed tiles; own Cholesky
+      B2_CUDA(cudaEventRecord(h->ev[2], s));
+      B2_CUDA(baf_launch_camera_terms(P, I, Tl, loss_type, loss_scale, s));
+      B2_CUDA(baf_launch_schur_points(P, Wn, radius, min_diag, max_diag, loss_type, loss_scale, s));
+      B2_CUDA(baf_launch_schur_window(P, Wn, Tl, h->n_sm, s));
+      B2_CUDA(cudaEventRecord(h->ev[3], s));
+      schur_launches += 3;
+      count_launches(3);
+      B2_TRY(sync_reduce(h, reduced, (int64_t)n_reduced, 0));  // packed tiles + rhs + g_c + diag_c: one all-reduce
+      B2_CUDA(baf_launch_finish(P, Tl, radius, min_diag, max_diag, s));
+      B2_TRY(sync_reduce(h, P.gmax, 1, 1));
+      if (dump_path && iter == 0) {  // debugging aid: the assembled system as a dense upper triangle + rhs
+        std::vector<double> tiles((size_t)plan.n_tiles * kST * kST), dense((size_t)D * D, 0.0), rhs_h((size_t)D);
+        B2_CUDA(cudaMemcpyAsync(tiles.data(), Tl.tiles, tiles.size() * 8, cudaMemcpyDeviceToHost, s));
+        B2_CUDA(cudaMemcpyAsync(rhs_h.data(), P.rhs, (size_t)D * 8, cudaMemcpyDeviceToHost, s));
+        B2_CUDA(cudaStreamSynchronize(s));
+        for (int64_t r = 0; r < D; ++r)
+          for (int64_t c = r; c < D; ++c) {
+            const int id = plan.tile_id[(size_t)(r / kST) * plan.nt + (c / kST)];
+            if (id >= 0) dense[(size_t)r * D + c] = tiles[(size_t)id * kST * kST + (r % kST) * kST + (c % kST)];
+          }
+        if (FILE* f = fopen(dump_path, "wb")) { fwrite(dense.data(), 8, dense.size(), f); fwrite(rhs_h.data(), 8, rhs_h.size(), f); fclose(f); }
+      }
+      B2_CUDA(cudaEventRecord(h->ev[4], s));
+      B2_CUDA(cudaMemsetAsync(Tl.info, 0, sizeof(int), s));
+      B2_CUDA(cudaMemcpyAsync(P.dc, P.rhs, Dv * 8, cudaMemcpyDeviceToDevice, s));
+      int nl = 0;
+      B2_CUDA(bac_factor(Tl, plan.row_ptr.data(), plan.row_col.data(), plan.tile_id.data(), s, &nl));
+      B2_CUDA(bac_solve(Tl, P.dc, D, s));
+      B2_CUDA(ba_launch_negate(P.dc, D, s));
+      B2_CUDA(cudaEventRecord(h->ev[5], s));
+      B2_CUDA(cudaMemcpyAsync(&info, Tl.info, sizeof(int), cudaMemcpyDeviceToHost, s));
+      count_launches(nl + 3);
     } else {
     B2_CUDA(cudaEventRecord(h->ev[2], s));
     if (!pair_major && camterms_image) B2_CUDA(bai_launch_camera_terms_image(P, I, s));
@@ -500,6 +729,13 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
     B2_TRY(sync_reduce(h, reduced, (int64_t)n_reduced, 0));  // the one NVLink all-reduce of (S, rhs, g_c, diag)
     B2_CUDA(ba_launch_add_diag(P, radius, min_diag, max_diag, s));
     B2_TRY(sync_reduce(h, P.gmax, 1, 1));
+    if (dump_path && iter == 0) {
+      std::vector<double> dense((size_t)D * D), rhs_h((size_t)D);
+      B2_CUDA(cudaMemcpyAsync(dense.data(), P.S, dense.size() * 8, cudaMemcpyDeviceToHost, s));
+      B2_CUDA(cudaMemcpyAsync(rhs_h.data(), P.rhs, (size_t)D * 8, cudaMemcpyDeviceToHost, s));
+      B2_CUDA(cudaStreamSynchronize(s));
+      if (FILE* f = fopen(dump_path, "wb")) { fwrite(dense.data(), 8, dense.size(), f); fwrite(rhs_h.data(), 8, rhs_h.size(), f); fclose(f); }
+    }
     // ---- reduced solve: S y = rhs, dc = -y
     if (D > 0) {
       B2_CUDA(cudaMemcpyAsync(P.dc, P.rhs, D * 8, cudaMemcpyDeviceToDevice, s));
@@ -513,10 +749,14 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
       B2_CUDA(ba_launch_negate(P.dc, D, s));
     }
     }
-    B2_CUDA(ba_launch_backsub(P, s));
-    B2_CUDA(ba_launch_model_cost(P, scal + 4, s));
+    if (fused) {
+      B2_CUDA(baf_launch_backsub(P, scal, loss_type, loss_scale, s));  // dp, model cost change, candidate points
+    } else {
+      B2_CUDA(ba_launch_backsub(P, s));
+      B2_CUDA(ba_launch_model_cost(P, scal + 4, s));
+      B2_CUDA(ba_launch_candidate(P, scal, false, s));
+    }
     B2_CUDA(ba_launch_candidate(P, scal, true, s));
-    B2_CUDA(ba_launch_candidate(P, scal, false, s));
     B2_CUDA(ba_launch_jacobian(P, P.qvec_new, P.tvec_new, P.cam_new, P.xyz_new, 1, scal + 5, s, loss_type, loss_scale));
     count_launches(10);
     B2_TRY(sync_reduce(h, scal + 2, 4, 0));
@@ -526,12 +766,18 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
     float ms = 0;
     B2_CUDA(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]));
     schur_ms += ms;
+    if (fused) {
+      B2_CUDA(cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]));
+      solve_ms += ms;
+    }
     const double gmax = hs[7];
     if (gmax <= opt->gradient_tolerance) {  // gradient_max_norm <= gradient_tolerance at the current iterate
       sum->termination_type = 0;
       break;
     }
     const double model_cost_change = hs[4];
+    if (trace) fprintf(stderr, "[b2_ba] iter %d cost %.12e candidate %.12e model_change %.6e gmax %.3e radius %.3e info %d step^2 %.3e\n",
+                       iter, cost, hs[5], model_cost_change, gmax, radius, info, hs[0] + hs[2]);
     const bool ok = (info == 0) && (model_cost_change > 0) && std::isfinite(model_cost_change);
     bool accepted = false;
     if (ok) {
@@ -561,9 +807,11 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
         radius = std::min(max_radius, radius);
         decrease_factor = 2.0;
         cost = new_cost;
-        B2_CUDA(cudaMemsetAsync(scal + 6, 0, 8, s));
-        B2_CUDA(ba_launch_jacobian(P, P.qvec, P.tvec, P.cam_params, P.xyz, 0, scal + 6, s, loss_type, loss_scale));
-        count_launches(1);
+        if (!fused) {  // the fused path re-evaluates the blocks inside its kernels
+          B2_CUDA(cudaMemsetAsync(scal + 6, 0, 8, s));
+          B2_CUDA(ba_launch_jacobian(P, P.qvec, P.tvec, P.cam_params, P.xyz, 0, scal + 6, s, loss_type, loss_scale));
+          count_launches(1);
+        }
       }
     }
     if (!accepted) {
@@ -591,6 +839,7 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
   B2_CUDA(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
   sum->solve_seconds = ms * 1e-3;
   sum->schur_kernel_seconds = schur_ms * 1e-3;
+  sum->linear_solve_seconds = solve_ms * 1e-3;
   sum->schur_kernel_launches = schur_launches;
   sum->final_cost = cost;
   sum->num_iterations = sum->num_successful_steps + sum->num_unsuccessful_steps;
@@ -723,6 +972,61 @@ int b2_ba_reprojection_errors(b2_ba* h, const b2_ba_problem* pr, double* point_e
     return B2_OK;
   };
   const int rc = run();
+  cudaStreamSynchronize(s);
+  free_all(h);
+  return rc;
+}
+
+// Test seam of the tiled Cholesky (ba_chol.cu): solves A x = b for a dense symmetric positive definite A (row-major,
+// upper triangle read) through exactly the code path b2_ba_solve uses -- packed 64 x 64 tiles (here: every tile whose
+// block of A holds a non-zero, plus the symbolic fill), panel / update kernels, the two triangular solves.
+int b2_ba_debug_cholesky_solve(b2_ba* h, int64_t D, const double* A, const double* b, double* x, int32_t* info_out, int32_t* n_tiles_out) {
+  if (!h || !A || !b || !x || D <= 0) return set_error(B2_ERR_INVALID, "bad argument");
+  B2_CUDA(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  const int rc = [&]() -> int {
+    FusedPlan plan;
+    const int nt = (int)((D + kST - 1) / kST);
+    plan.nt = nt;
+    plan.tmap.assign((size_t)nt * nt, 0);
+    for (int64_t r = 0; r < D; ++r)
+      for (int64_t c = r; c < D; ++c)
+        if (A[r * D + c] != 0.0 || r == c) plan.tmap[(size_t)(r / kST) * nt + (c / kST)] = 1;
+    finish_tiles(&plan);
+    std::vector<double> tiles((size_t)plan.n_tiles * kST * kST, 0.0), rhs((size_t)nt * kST, 0.0);
+    for (int64_t r = 0; r < (int64_t)nt * kST; ++r)
+      for (int64_t c = r; c < (int64_t)nt * kST; ++c) {
+        const int id = plan.tile_id[(size_t)(r / kST) * nt + (c / kST)];
+        if (id < 0) continue;
+        const double v = (r < D && c < D) ? A[r * D + c] : (r == c ? 1.0 : 0.0);
+        tiles[(size_t)id * kST * kST + (r % kST) * kST + (c % kST)] = v;
+      }
+    for (int64_t r = 0; r < D; ++r) rhs[(size_t)r] = b[r];
+    BaTiles T;
+    memset(&T, 0, sizeof T);
+    int32_t *d_tile_id, *d_row_ptr, *d_row_col;
+    double* d_x;
+    B2_TRY(dev_upload(h, &d_tile_id, (const int32_t*)plan.tile_id.data(), plan.tile_id.size()));
+    B2_TRY(dev_upload(h, &d_row_ptr, (const int32_t*)plan.row_ptr.data(), plan.row_ptr.size()));
+    B2_TRY(dev_upload(h, &d_row_col, (const int32_t*)plan.row_col.data(), plan.row_col.size()));
+    B2_TRY(dev_upload(h, &T.tiles, (const double*)tiles.data(), tiles.size()));
+    B2_TRY(dev_upload(h, &d_x, (const double*)rhs.data(), rhs.size()));
+    B2_TRY(dev_alloc(h, &T.rinv, (size_t)nt * kST * kST));
+    B2_TRY(dev_alloc(h, &T.info, 1));
+    B2_CUDA(cudaMemsetAsync(T.info, 0, sizeof(int), s));
+    T.nt = nt; T.n_tiles = plan.n_tiles; T.tile_id = d_tile_id; T.row_ptr = d_row_ptr; T.row_col = d_row_col;
+    int nl = 0;
+    B2_CUDA(bac_factor(T, plan.row_ptr.data(), plan.row_col.data(), plan.tile_id.data(), s, &nl));
+    B2_CUDA(bac_solve(T, d_x, D, s));
+    count_launches(nl + 1);
+    int info = 0;
+    B2_CUDA(cudaMemcpyAsync(&info, T.info, sizeof(int), cudaMemcpyDeviceToHost, s));
+    B2_CUDA(cudaMemcpyAsync(x, d_x, (size_t)D * 8, cudaMemcpyDeviceToHost, s));
+    B2_CUDA(cudaStreamSynchronize(s));
+    if (info_out) *info_out = info;
+    if (n_tiles_out) *n_tiles_out = plan.n_tiles;
+    return B2_OK;
+  }();
   cudaStreamSynchronize(s);
   free_all(h);
   return rc;

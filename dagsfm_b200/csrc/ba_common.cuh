@@ -114,3 +114,53 @@ cudaError_t bai_launch_cg_update_xr(int64_t D, double* x, const double* p, doubl
                                     double alpha, int mode, double* partial, int* n_partial, cudaStream_t s);
 
 }  // namespace b2
+
+// =====================================================================================================================
+// Fused exact path (ba_fused.cu + ba_chol.cu): no staged Jacobian blocks, the reduced camera system S in packed 64 x 64
+// tiles (upper block triangle, only the tiles the camera graph + Cholesky fill make non-zero), a hand-written tiled
+// Cholesky.  Selected by b2_ba_solve for the 4-slot camera models when every variable point's track fits a window
+// (<= kWinMaxLoc images, no image twice); everything else keeps the staged path above.
+namespace b2 {
+
+constexpr int kST = 64;            // tile side of the packed reduced system
+constexpr int kWinMaxLoc = 16;     // images per accumulation window (schur_window_kernel<12> / <16>)
+constexpr int kWinBatch = 12;      // points per k-panel of the window product
+
+struct BaTiles {
+  int32_t nt;               // tiles per side = ceil(D / 64)
+  int32_t n_tiles;          // structurally non-zero upper tiles (after symbolic fill)
+  const int32_t* tile_id;   // [nt * nt] packed index of tile (ti, tj), ti <= tj, or -1
+  const int32_t* row_ptr;   // [nt + 1] CSR of the upper tiles by tile row, diagonal tile first
+  const int32_t* row_col;   // [n_tiles] tile column; a tile's packed index is its CSR position
+  double* tiles;            // [n_tiles][64 * 64] row-major
+  double* rinv;             // [nt][64 * 64] inverse of each factored diagonal tile (upper triangular)
+  int* info;                // != 0: a pivot was not positive
+};
+__host__ __device__ inline double* tile_entry(const BaTiles& T, int r, int c) {  // r <= c, the tile must exist
+  const int id = T.tile_id[(r >> 6) * T.nt + (c >> 6)];
+  return T.tiles + (size_t)id * (kST * kST) + (r & 63) * kST + (c & 63);
+}
+
+struct BaWin {
+  int32_t n_chunks;
+  int32_t nloc;               // 12 or 16
+  const int32_t* chunk_pt0;   // [n_chunks + 1] ranges of pt_order
+  const int32_t* pt_order;    // variable points in processing order (sorted by their lowest image)
+  const int32_t* chunk_img;   // [n_chunks * nloc] image of each window slot, -1 = unused
+  const uint8_t* obs_slot;    // [n_obs] window slot of the observation's image
+  double* Z;                  // [n_obs][30]  W_a M_p  (V_p^-1 = M_p M_p')
+  double* U;                  // [n_pts][3]   M_p' g_p
+};
+
+cudaError_t baf_launch_camera_terms(const BaDev& P, const BaIter& I, const BaTiles& T, int loss_type, double loss_scale, cudaStream_t s);
+cudaError_t baf_launch_schur_points(const BaDev& P, const BaWin& W, double radius, double min_diag, double max_diag,
+                                    int loss_type, double loss_scale, cudaStream_t s);
+cudaError_t baf_launch_schur_window(const BaDev& P, const BaWin& W, const BaTiles& T, int n_sm, cudaStream_t s);
+cudaError_t baf_launch_finish(const BaDev& P, const BaTiles& T, double radius, double min_diag, double max_diag, cudaStream_t s);
+cudaError_t baf_launch_backsub(const BaDev& P, double* scal, int loss_type, double loss_scale, cudaStream_t s);
+// tiled Cholesky of the packed system and the two triangular solves (x overwritten: in = rhs, out = solution)
+cudaError_t bac_factor(const BaTiles& T, const int32_t* h_row_ptr, const int32_t* h_row_col, const int32_t* h_tile_id,
+                       cudaStream_t s, int* n_launches);
+cudaError_t bac_solve(const BaTiles& T, double* x, int64_t D, cudaStream_t s);
+
+}  // namespace b2

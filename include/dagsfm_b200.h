@@ -360,7 +360,10 @@ typedef struct b2_ba_summary {   /* the fields of ceres::Solver::Summary the ref
   int64_t schur_kernel_launches;
   int64_t num_linear_solver_iterations; /* CG iterations over all LM steps (0 on the exact path) */
   int32_t linear_solver_type_used;      /* 1 exact, 2 ITERATIVE_SCHUR */
-  int32_t reserved;
+  int32_t exact_path_used;              /* 0 n/a (iterative), 1 staged blocks + dense S + library Cholesky (fallback),
+                                           2 fused kernels + packed tiles + the library's own tiled Cholesky */
+  double linear_solve_seconds;          /* device time of factorisation + triangular solves (fused exact path) */
+  double reduced_system_bytes;          /* size of the buffer (S | rhs | g_c | diag) that a multi-GPU run all-reduces */
 } b2_ba_summary;
 
 /* Collective hook for multi-GPU runs (points sharded across ranks, cameras replicated):
@@ -376,6 +379,11 @@ int b2_ba_set_allreduce(b2_ba* h, b2_allreduce_fn fn, void* user);
  * every rank passes ALL cameras/images and ITS shard of points + observations. */
 int b2_ba_solve(b2_ba* h, const b2_ba_problem* problem, const b2_ba_options* opt,
                 b2_ba_summary* summary);
+/* Test seam of the linear solver of the exact Schur step (the library's tiled Cholesky, dagsfm_b200/csrc/ba_chol.cu):
+ * solves A x = b for a dense symmetric positive definite A [D*D] (row-major, upper triangle read; zero 64 x 64 blocks
+ * are skipped as in the bundle adjuster) on the device.  info != 0: a pivot was not positive. */
+int b2_ba_debug_cholesky_solve(b2_ba* h, int64_t D, const double* A, const double* b, double* x, int32_t* info,
+                               int32_t* n_tiles);
 
 /* Result metrics the reference reports after a bundle adjustment:
  * Reconstruction::ComputeMeanReprojectionError (src/base/reconstruction.cc:814-858) with

@@ -42,6 +42,7 @@
 #define __constant__ static const
 #define __shared__ static
 #define __grid_constant__
+#define __align__(n) __attribute__((aligned(n)))
 
 struct uint3_emu { unsigned x = 0, y = 0, z = 0; };
 struct dim3 {

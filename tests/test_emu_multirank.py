@@ -49,7 +49,9 @@ def _solve(ba, L, prob, solver, hook=None, iters=12):
     o = ba.BundleAdjustmentOptions()
     L.b2_ba_default_options(C.byref(o))
     o.linear_solver_type = solver
-    o.max_num_iterations, o.gradient_tolerance = iters, 1e-6
+    # 1e-4: the last test before the cost changes reach the rounding floor (relative 1e-16), where the count of accepted
+    # steps depends on the summation order of the shards
+    o.max_num_iterations, o.gradient_tolerance = iters, 1e-4
     adj = ba.BundleAdjuster(o)
     if hook:
         adj.set_allreduce(hook)
