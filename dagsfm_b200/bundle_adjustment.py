@@ -70,6 +70,7 @@ def _L():
         L.b2_ba_set_allreduce.argtypes = [vp, ALLREDUCE_FN, vp]
         L.b2_ba_solve.argtypes = [vp, P(BaProblem), P(BundleAdjustmentOptions), P(BaSummary)]
         L.b2_ba_reprojection_errors.argtypes = [vp, P(BaProblem), vp, P(C.c_double)]
+        L.b2_ba_debug_cholesky_solve.argtypes = [vp, C.c_int64, vp, vp, vp, P(C.c_int32), P(C.c_int32)]
         _bound = True
     return L
 
@@ -115,6 +116,17 @@ class BundleAdjuster:
         mean = C.c_double(0)
         check(_L().b2_ba_reprojection_errors(self._h, C.byref(p), err.ctypes.data, C.byref(mean)))
         return mean.value, err[: p.n_points]
+
+    def debug_cholesky_solve(self, A: np.ndarray, b: np.ndarray):
+        """Test seam (b2_ba_debug_cholesky_solve): x with A x = b through the tiled Cholesky of the exact Schur step
+        -> (x, info, number of 64 x 64 tiles stored incl. fill)."""
+        A = np.ascontiguousarray(A, np.float64)
+        b = np.ascontiguousarray(b, np.float64)
+        x = np.zeros_like(b)
+        info, nt = C.c_int32(0), C.c_int32(0)
+        check(_L().b2_ba_debug_cholesky_solve(self._h, len(b), A.ctypes.data, b.ctypes.data, x.ctypes.data,
+                                             C.byref(info), C.byref(nt)))
+        return x, info.value, nt.value
 
     def Solve(self, prob: dict) -> BaSummary:
         """prob: dict with the arrays of tests/ba_scene.make_ba_problem (updated in place)."""

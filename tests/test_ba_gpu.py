@@ -87,3 +87,69 @@ def test_invalid_problem_is_rejected():
     prob["obs_pt"] = np.ascontiguousarray(prob["obs_pt"][::-1])
     with pytest.raises(B2Error):
         gpu_solve(prob)
+
+
+# ---------------------------------------------------------------- fused exact path (ba_fused.cu + ba_chol.cu)
+def test_tiled_cholesky_seam_on_device():
+    """The linear solver of the exact Schur step is the library's own tiled Cholesky (no cuSOLVER): dense and banded
+    SPD systems against LAPACK on the host, and a non-positive pivot is reported."""
+    from dagsfm_b200 import BundleAdjuster
+    from tests.test_emu_ba import spd_cases
+    adj = BundleAdjuster()
+    try:
+        rng = np.random.default_rng(9)
+        M = rng.normal(size=(2000, 2000))
+        big = (M @ M.T + 2000 * np.eye(2000), rng.normal(size=2000), None)
+        for A, b, band in spd_cases() + [big]:
+            x, info, n_tiles = adj.debug_cholesky_solve(A, b)
+            nt = (len(b) + 63) // 64
+            assert info == 0
+            assert n_tiles == nt * (nt + 1) // 2 if band is None else n_tiles < nt * (nt + 1) // 2
+            ref = np.linalg.solve(A, b)
+            assert np.abs(x - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max()) * np.linalg.cond(A)
+        A = np.eye(70)
+        A[3, 3] = -1.0
+        assert adj.debug_cholesky_solve(A, np.ones(70))[1] != 0
+    finally:
+        adj.close()
+
+
+@pytest.mark.parametrize("kw", [
+    dict(n_img=8, n_pts=150, track_len=4, seed=5),
+    dict(n_img=12, n_pts=300, track_len=5, seed=4, shared_camera=True),
+    dict(n_img=60, n_pts=3000, track_len=12, seed=8),
+    dict(n_img=60, n_pts=1500, track_len=16, seed=2),
+    dict(n_img=30, n_pts=500, track_len=7, seed=7, n_const_pts=60),
+])
+def test_fused_and_staged_exact_paths_agree_on_device(kw, monkeypatch):
+    p_f, p_s, p_cpu = make_ba_problem(**kw), make_ba_problem(**kw), make_ba_problem(**kw)
+    s_f = gpu_solve(p_f)
+    monkeypatch.setenv("B2_BA_EXACT", "staged")
+    s_s = gpu_solve(p_s)
+    monkeypatch.delenv("B2_BA_EXACT")
+    s_cpu = orc.ba_solve(p_cpu)
+    assert (s_f.exact_path_used, s_s.exact_path_used) == (2, 1)
+    for s in (s_f, s_s):
+        assert (s.num_successful_steps, s.num_unsuccessful_steps, s.termination_type) == \
+               (s_cpu.num_successful_steps, s_cpu.num_unsuccessful_steps, s_cpu.termination)
+        assert s.final_cost == pytest.approx(s_cpu.final_cost, rel=1e-9)
+    assert abs(reprojection_rms(p_f) - reprojection_rms(p_cpu)) < RMS_TOL
+    assert np.abs(p_f["xyz"] - p_s["xyz"]).max() < 1e-7
+
+
+@pytest.mark.timeout(900)
+def test_c4_shape_rms_within_tolerance_of_the_fp64_oracle():
+    """BASELINE configs[3] at full size (500 cams / 100k pts / 1M obs), reference final-BA options: the GPU solve and the
+    FP64 oracle (all host threads) stop at the same iterate, reprojection RMS within 1e-6 px (north_star)."""
+    kw = dict(n_img=500, n_pts=100000, track_len=10, seed=1)
+    p_gpu, p_cpu = make_ba_problem(**kw), make_ba_problem(**kw)
+    s_gpu = gpu_solve(p_gpu)
+    assert s_gpu.exact_path_used == 2
+    s_cpu = orc.ba_solve(p_cpu)
+    rms_gpu, rms_cpu = reprojection_rms(p_gpu), reprojection_rms(p_cpu)
+    print(f"\nC4: rms gpu {rms_gpu:.12f} cpu {rms_cpu:.12f} |d| {abs(rms_gpu - rms_cpu):.3e}; steps "
+          f"{s_gpu.num_successful_steps}+{s_gpu.num_unsuccessful_steps} / {s_cpu.num_successful_steps}+{s_cpu.num_unsuccessful_steps}")
+    assert abs(rms_gpu - rms_cpu) < RMS_TOL
+    assert (s_gpu.num_successful_steps, s_gpu.num_unsuccessful_steps, s_gpu.termination_type) == \
+           (s_cpu.num_successful_steps, s_cpu.num_unsuccessful_steps, s_cpu.termination)
+    assert s_gpu.final_cost == pytest.approx(s_cpu.final_cost, rel=1e-9)

@@ -25,6 +25,7 @@ def emu(request):
     L.b2_ba_destroy.argtypes = [vp]
     L.b2_ba_set_allreduce.argtypes = [vp, ba.ALLREDUCE_FN, vp]
     L.b2_ba_solve.argtypes = [vp, P(ba.BaProblem), P(ba.BundleAdjustmentOptions), P(ba.BaSummary)]
+    L.b2_ba_debug_cholesky_solve.argtypes = [vp, C.c_int64, vp, vp, vp, P(C.c_int32), P(C.c_int32)]
     L.b2_last_error.restype = C.c_char_p
     saved = (ba._L, ba.check)
 
@@ -505,3 +506,67 @@ def test_image_major_camera_terms_variant(emu, kw, monkeypatch):
         assert (s_v.num_successful_steps, s_v.num_unsuccessful_steps) == (s.num_successful_steps, s.num_unsuccessful_steps)
         assert s_v.final_cost == pytest.approx(s.final_cost, rel=1e-9)
     assert np.abs(p_v["xyz"] - p_ref["xyz"]).max() < 1e-8 and np.abs(p_v["qvec"] - p_ref["qvec"]).max() < 1e-10
+
+
+# ---------------------------------------------------------------- fused exact path (ba_fused.cu + ba_chol.cu)
+def spd_cases():
+    rng = np.random.default_rng(5)
+    out = []
+    for D, band in ((37, None), (150, None), (300, 70), (450, 64)):
+        M = rng.normal(size=(D, D))
+        A = M @ M.T + D * np.eye(D)
+        if band is not None:                         # banded camera graph: zero 64 x 64 tiles away from the diagonal
+            i, j = np.indices((D, D))
+            A[np.abs(i - j) > band] = 0.0
+            A += np.eye(D) * np.abs(A).sum(1).max()
+        out.append((A, rng.normal(size=D), band))
+    return out
+
+
+def test_tiled_cholesky_seam_solves_dense_and_banded_systems(emu):
+    adj = emu.BundleAdjuster(emu.BundleAdjustmentOptions())
+    try:
+        for A, b, band in spd_cases():
+            x, info, n_tiles = adj.debug_cholesky_solve(A, b)
+            nt = (len(b) + 63) // 64
+            assert info == 0
+            assert n_tiles == nt * (nt + 1) // 2 if band is None else n_tiles < nt * (nt + 1) // 2
+            ref = np.linalg.solve(A, b)
+            assert np.abs(x - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max()) * np.linalg.cond(A)
+        A = np.eye(70)
+        A[3, 3] = -1.0                               # not positive definite: reported, not hidden
+        assert adj.debug_cholesky_solve(A, np.ones(70))[1] != 0
+    finally:
+        adj.close()
+
+
+@pytest.mark.parametrize("kw", [
+    dict(n_img=6, n_pts=60, track_len=4, seed=5),
+    dict(n_img=8, n_pts=80, track_len=5, seed=3, shared_camera=True),
+    dict(n_img=30, n_pts=200, track_len=12, seed=8),                    # 12-slot windows, several tiles
+    dict(n_img=30, n_pts=120, track_len=16, seed=2),                    # 16-slot windows
+    dict(n_img=8, n_pts=90, track_len=4, seed=7, n_const_pts=20),
+])
+def test_fused_and_staged_exact_paths_agree(emu, kw, monkeypatch):
+    """The default exact step is the fused one (exact_path_used == 2); B2_BA_EXACT=staged selects the first-generation
+    kernels.  Same LM path (reference options) and the same optimum as the oracle on both."""
+    p_f, p_s, p_cpu = make_ba_problem(**kw), make_ba_problem(**kw), make_ba_problem(**kw)
+    s_f = emu_solve(emu, p_f)
+    monkeypatch.setenv("B2_BA_EXACT", "staged")
+    s_s = emu_solve(emu, p_s)
+    monkeypatch.delenv("B2_BA_EXACT")
+    s_cpu = orc.ba_solve(p_cpu)
+    assert (s_f.exact_path_used, s_s.exact_path_used) == (2, 1)
+    assert s_f.linear_solve_seconds >= 0 and s_f.reduced_system_bytes > 0
+    for s in (s_f, s_s):
+        assert (s.num_successful_steps, s.num_unsuccessful_steps, s.termination_type) == \
+               (s_cpu.num_successful_steps, s_cpu.num_unsuccessful_steps, s_cpu.termination)
+        assert s.final_cost == pytest.approx(s_cpu.final_cost, rel=1e-9)
+    assert abs(reprojection_rms(p_f) - reprojection_rms(p_cpu)) < 1e-6
+    assert np.abs(p_f["xyz"] - p_s["xyz"]).max() < 1e-7
+
+
+def test_tracks_that_do_not_fit_a_window_take_the_staged_path(emu):
+    p = make_ba_problem(n_img=40, n_pts=30, track_len=36, seed=6)
+    s = emu_solve(emu, p, **TIGHT)
+    assert s.exact_path_used == 1
