@@ -455,6 +455,18 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
   B2_TRY(dev_upload(h, &d_img_cam, pr->image_camera, (size_t)n_img));
   B2_TRY(dev_upload(h, &d_cam_model, pr->camera_model, (size_t)n_cam));
   B2_TRY(dev_upload(h, &d_pose_col, pose_col.data(), pose_col.size()));
+  {  // rotation blocks by column: their term of the gradient max norm goes through QuaternionParameterization::Plus
+    std::vector<int32_t> rot_img((size_t)std::max<int64_t>(D, 1), -1);
+    for (int i = 0; i < n_img; ++i) {
+      const int32_t c = pose_col[6 * (size_t)i];
+      if (c < 0) continue;
+      rot_img[c] = i;
+      rot_img[c + 1] = rot_img[c + 2] = -2;
+    }
+    int32_t* d_rot_img;
+    B2_TRY(dev_upload(h, &d_rot_img, rot_img.data(), rot_img.size()));
+    P.rot_img = d_rot_img;
+  }
   B2_TRY(dev_upload(h, &d_intr_col, intr_col.data(), intr_col.size()));
   B2_TRY(dev_upload(h, &d_pt_col, pt_col.data(), pt_col.size()));
   P.obs_img = d_obs_img; P.obs_pt = d_obs_pt; P.obs_xy = (const double2*)d_obs_xy; P.pt_start = d_pt_start;

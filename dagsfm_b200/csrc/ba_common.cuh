@@ -58,7 +58,29 @@ struct BaDev {
   ObsJacW* JW;                  // Jacobian blocks in the wide layout, when wide != 0 (then J == nullptr)
   int32_t wide;                 // 0: ObsJac, intrinsics stride 4; 1: ObsJacW, stride 12 (cam_params, cam_new, intr_col)
   int32_t reserved_;
+  const int32_t* rot_img;       // [D] image whose rotation block STARTS at this column, -2 for its 2nd / 3rd column, else -1
 };
+
+// Column j's term of Ceres' gradient_max_norm = |x - Plus(x, -g)|_inf (trust_region_minimizer.cc, Ceres 1.14, external;
+// g = the gradient in the tangent space of the UNSCALED problem).  Plain |g_j| for tvec / intrinsics columns (identity
+// or subset parameterisations); for a rotation block the quaternion moves by QuaternionParameterization::Plus, which is
+// not linear in g: the three columns are handled together by the block's first column.
+__device__ __forceinline__ double grad_norm_term(const BaDev& P, int64_t j) {
+  const int ri = P.rot_img[j];
+  if (ri == -1) return fabs(P.g_c[j] / P.scale_c[j]);
+  if (ri < 0) return 0.0;
+  const double d0 = -P.g_c[j] / P.scale_c[j], d1 = -P.g_c[j + 1] / P.scale_c[j + 1], d2 = -P.g_c[j + 2] / P.scale_c[j + 2];
+  const double nd = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+  if (!(nd > 0.0)) return 0.0;
+  const double* x = P.qvec + 4 * (int64_t)ri;
+  const double sn = sin(nd) / nd;
+  const double q0 = cos(nd), q1 = sn * d0, q2 = sn * d1, q3 = sn * d2;
+  const double y0 = q0 * x[0] - q1 * x[1] - q2 * x[2] - q3 * x[3];
+  const double y1 = q0 * x[1] + q1 * x[0] + q2 * x[3] - q3 * x[2];
+  const double y2 = q0 * x[2] - q1 * x[3] + q2 * x[0] + q3 * x[1];
+  const double y3 = q0 * x[3] + q1 * x[2] - q2 * x[1] + q3 * x[0];
+  return fmax(fmax(fabs(x[0] - y0), fabs(x[1] - y1)), fmax(fabs(x[2] - y2), fabs(x[3] - y3)));
+}
 template <class J> __host__ __device__ inline J* jac(const BaDev& P);
 template <> __host__ __device__ inline ObsJac* jac<ObsJac>(const BaDev& P) { return P.J; }
 template <> __host__ __device__ inline ObsJacW* jac<ObsJacW>(const BaDev& P) { return P.JW; }

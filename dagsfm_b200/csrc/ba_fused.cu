@@ -322,7 +322,7 @@ __global__ void finish_kernel(BaDev P, BaTiles T, double radius, double min_diag
   }
   *d += fmin(fmax(P.diag_c[j], min_diag), max_diag) / radius;
   P.rhs[j] += P.g_c[j];
-  atomic_max_nonneg(P.gmax, fabs(P.g_c[j] / P.scale_c[j]));
+  atomic_max_nonneg(P.gmax, grad_norm_term(P, j));
 }
 
 // ------------------------------------------------------------------ back-substitution + model cost + candidate points

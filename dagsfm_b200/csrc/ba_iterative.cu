@@ -204,7 +204,7 @@ __global__ void cam_diag_kernel(BaDev P, BaIter I, double radius, double min_dia
   const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (j >= P.D) return;
   I.lm_c[j] = fmin(fmax(P.diag_c[j], min_diag), max_diag) / radius;
-  atomic_max_nonneg(P.gmax, fabs(P.g_c[j] / P.scale_c[j]));
+  atomic_max_nonneg(P.gmax, grad_norm_term(P, j));
 }
 
 // Thread per observation a: the rows of the block diagonal of S that a touches,

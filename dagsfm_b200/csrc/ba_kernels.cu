@@ -429,7 +429,7 @@ __global__ void add_diag_kernel(BaDev P, double radius, double min_diag, double 
   if (j >= P.D) return;
   P.S[j * P.D + j] += fmin(fmax(P.diag_c[j], min_diag), max_diag) / radius;
   P.rhs[j] += P.g_c[j];  // rhs held only the Schur part -sum W V^-1 g_p so far
-  atomic_max_nonneg(P.gmax, fabs(P.g_c[j] / P.scale_c[j]));
+  atomic_max_nonneg(P.gmax, grad_norm_term(P, j));
 }
 
 // ----------------------------------------------------------- back-substitution

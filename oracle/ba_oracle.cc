@@ -631,7 +631,20 @@ static void Solve(Problem P, Options O, Summary* S) {
     }
     if (need_grad_check) {  // gradient_max_norm of the unscaled problem
       double gmax = 0;
-      for (int j = 0; j < D; ++j) gmax = std::max(gmax, std::abs(gc[j] / sv.scale_c[j]));
+      // |x - Plus(x, -g)|_inf (trust_region_minimizer.cc): plain |g_j| under identity / subset parameterisations, the
+      // displacement of the quaternion under QuaternionParameterization::Plus for a rotation block
+      std::vector<char> is_rot((size_t)std::max(D, 1), 0);
+      for (int i = 0; i < P.n_img; ++i) {
+        const int c = L.pose_col[6 * i];
+        if (c < 0) continue;
+        is_rot[c] = is_rot[c + 1] = is_rot[c + 2] = 1;
+        const double d[3] = {-gc[c] / sv.scale_c[c], -gc[c + 1] / sv.scale_c[c + 1], -gc[c + 2] / sv.scale_c[c + 2]};
+        double y[4];
+        QuatPlus(P.qvec + 4 * i, d, y);
+        for (int a = 0; a < 4; ++a) gmax = std::max(gmax, std::abs(P.qvec[4 * i + a] - y[a]));
+      }
+      for (int j = 0; j < D; ++j)
+        if (!is_rot[j]) gmax = std::max(gmax, std::abs(gc[j] / sv.scale_c[j]));
       for (int j = 0; j < 3 * NP; ++j) gmax = std::max(gmax, std::abs(gp[j] / sv.scale_p[j]));
       if (gmax <= O.gradient_tolerance) { S->termination = 0; break; }
       need_grad_check = false;

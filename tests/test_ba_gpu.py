@@ -153,3 +153,13 @@ def test_c4_shape_rms_within_tolerance_of_the_fp64_oracle():
     assert (s_gpu.num_successful_steps, s_gpu.num_unsuccessful_steps, s_gpu.termination_type) == \
            (s_cpu.num_successful_steps, s_cpu.num_unsuccessful_steps, s_cpu.termination)
     assert s_gpu.final_cost == pytest.approx(s_cpu.final_cost, rel=1e-9)
+
+
+def test_gradient_max_norm_goes_through_the_quaternion_plus_on_device():
+    from tests.test_emu_ba import rotation_only_problem
+    for solver in (1, 2):
+        s = gpu_solve(rotation_only_problem(), gradient_tolerance=2.0, linear_solver_type=solver)
+        assert (s.num_iterations, s.termination_type) == (0, 0)
+        p = rotation_only_problem()
+        p["tvec_const"][:] = 0
+        assert gpu_solve(p, gradient_tolerance=2.0, linear_solver_type=solver).num_iterations > 0

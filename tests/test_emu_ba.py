@@ -570,3 +570,32 @@ def test_tracks_that_do_not_fit_a_window_take_the_staged_path(emu):
     p = make_ba_problem(n_img=40, n_pts=30, track_len=36, seed=6)
     s = emu_solve(emu, p, **TIGHT)
     assert s.exact_path_used == 1
+
+
+def rotation_only_problem():
+    p = make_ba_problem(n_img=6, n_pts=80, track_len=4, seed=12, noise_px=3.0)
+    p["tvec_const"][:] = 7
+    p["cam_const"][:] = 1
+    p["pt_const"][:] = 1
+    p["pose_const"][:] = 0
+    return p
+
+
+def test_gradient_max_norm_goes_through_the_quaternion_plus(emu):
+    """Ceres' gradient_max_norm is |x - Plus(x, -g)|_inf (trust_region_minimizer.cc): for a rotation block the
+    quaternion's displacement under QuaternionParameterization::Plus, bounded by 2 whatever the gradient.  With only
+    rotations free and gradient_tolerance = 2 the solve therefore converges at iteration 0 although |g|_inf is in the
+    thousands; with the tvec free as well, the plain |g| of its columns keeps the solve going."""
+    for solver in (1, 2):
+        p, q = rotation_only_problem(), rotation_only_problem()
+        s = emu_solve(emu, p, gradient_tolerance=2.0, linear_solver_type=solver)
+        sc = orc.ba_solve(q, gradient_tolerance=2.0, linear_solver=0 if solver == 1 else 1)
+        assert (s.num_iterations, s.termination_type) == (0, 0)
+        assert (sc.num_successful_steps + sc.num_unsuccessful_steps, sc.termination) == (0, 0)
+        p, q = rotation_only_problem(), rotation_only_problem()
+        p["tvec_const"][:] = 0
+        q["tvec_const"][:] = 0
+        s = emu_solve(emu, p, gradient_tolerance=2.0, linear_solver_type=solver)
+        sc = orc.ba_solve(q, gradient_tolerance=2.0, linear_solver=0 if solver == 1 else 1)
+        assert s.num_iterations > 0 and sc.num_successful_steps > 0
+        assert (s.num_successful_steps, s.num_unsuccessful_steps) == (sc.num_successful_steps, sc.num_unsuccessful_steps)
