@@ -221,6 +221,21 @@ void finish_tiles(FusedPlan* F) {
   F->n_tiles = (int)F->row_col.size();
 }
 
+// task graph of the tiled Cholesky (ba_chol.cu) for the plan's tile pattern -> device
+int upload_chol_graph(b2_ba* h, const FusedPlan& plan, const BaTiles& T, BaCholDev* out) {
+  BaCholGraph G;
+  bac_build_graph(plan.nt, plan.tile_id.data(), plan.row_ptr.data(), plan.row_col.data(), &G);
+  int32_t *d_task, *d_ptr, *d_dep;
+  if (G.dep.empty()) G.dep.assign(2, 0);
+  B2_TRY(dev_upload(h, &d_task, (const int32_t*)G.task.data(), G.task.size()));
+  B2_TRY(dev_upload(h, &d_ptr, (const int32_t*)G.dep_ptr.data(), G.dep_ptr.size()));
+  B2_TRY(dev_upload(h, &d_dep, (const int32_t*)G.dep.data(), G.dep.size()));
+  out->task = d_task; out->dep_ptr = d_ptr; out->dep = d_dep; out->n_tasks = G.n_tasks;
+  B2_TRY(dev_alloc(h, &out->flags, bac_flag_count(T)));
+  B2_TRY(dev_alloc(h, &out->rdiag, (size_t)plan.nt * kST));
+  return B2_OK;
+}
+
 struct CgVectors { double *x, *r, *p, *q, *tmp, *partial; };
 
 // ceres::internal::ConjugateGradientsSolver::Solve (Ceres 1.14 conjugate_gradients_solver.cc, external)
@@ -499,6 +514,8 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
   B2_TRY(dev_alloc(h, &P.dp, (size_t)NP * 3));
   BaTiles Tl;
   memset(&Tl, 0, sizeof Tl);
+  BaCholDev Cg;
+  memset(&Cg, 0, sizeof Cg);
   BaWin Wn;
   memset(&Wn, 0, sizeof Wn);
   if (fused) {
@@ -515,6 +532,7 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
     Tl.tiles = reduced;
     B2_TRY(dev_alloc(h, &Tl.rinv, (size_t)plan.nt * kST * kST));
     B2_TRY(dev_alloc(h, &Tl.info, 1));
+    B2_TRY(upload_chol_graph(h, plan, Tl, &Cg));
     Wn.n_chunks = (int32_t)plan.chunk_pt0.size() - 1; Wn.nloc = plan.nloc; Wn.chunk_pt0 = d_cpt0; Wn.pt_order = d_order;
     Wn.chunk_img = d_cimg; Wn.obs_slot = d_slot;
     B2_TRY(dev_alloc(h, &Wn.Z, (size_t)n_obs * 30));
@@ -721,9 +739,8 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
       B2_CUDA(cudaEventRecord(h->ev[4], s));
       B2_CUDA(cudaMemsetAsync(Tl.info, 0, sizeof(int), s));
       B2_CUDA(cudaMemcpyAsync(P.dc, P.rhs, Dv * 8, cudaMemcpyDeviceToDevice, s));
-      int nl = 0;
-      B2_CUDA(bac_factor(Tl, plan.row_ptr.data(), plan.row_col.data(), plan.tile_id.data(), s, &nl));
-      B2_CUDA(bac_solve(Tl, P.dc, D, s));
+      B2_CUDA(bac_solve_system(Tl, Cg, P.dc, h->n_sm, s));  // one persistent task-graph kernel: factor + both solves
+      const int nl = 1;
       B2_CUDA(ba_launch_negate(P.dc, D, s));
       B2_CUDA(cudaEventRecord(h->ev[5], s));
       B2_CUDA(cudaMemcpyAsync(&info, Tl.info, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -1027,10 +1044,10 @@ int b2_ba_debug_cholesky_solve(b2_ba* h, int64_t D, const double* A, const doubl
     B2_TRY(dev_alloc(h, &T.info, 1));
     B2_CUDA(cudaMemsetAsync(T.info, 0, sizeof(int), s));
     T.nt = nt; T.n_tiles = plan.n_tiles; T.tile_id = d_tile_id; T.row_ptr = d_row_ptr; T.row_col = d_row_col;
-    int nl = 0;
-    B2_CUDA(bac_factor(T, plan.row_ptr.data(), plan.row_col.data(), plan.tile_id.data(), s, &nl));
-    B2_CUDA(bac_solve(T, d_x, D, s));
-    count_launches(nl + 1);
+    BaCholDev Cg;
+    B2_TRY(upload_chol_graph(h, plan, T, &Cg));
+    B2_CUDA(bac_solve_system(T, Cg, d_x, h->n_sm, s));
+    count_launches(1);
     int info = 0;
     B2_CUDA(cudaMemcpyAsync(&info, T.info, sizeof(int), cudaMemcpyDeviceToHost, s));
     B2_CUDA(cudaMemcpyAsync(x, d_x, (size_t)D * 8, cudaMemcpyDeviceToHost, s));

@@ -1,254 +1,394 @@
-// Tiled Cholesky of the reduced camera system in packed 64 x 64 tiles, and the two triangular solves -- the linear
-// solve of the exact Schur step (what Ceres' SPARSE_SCHUR / DENSE_SCHUR hand to CHOLMOD / LAPACK for the reference,
-// src/optim/bundle_adjustment.cc:274-284).  Hand-written; replaces the cuSOLVER potrf / potrs of the first build.
+// Tiled Cholesky of the reduced camera system in packed 64 x 64 tiles and the two triangular solves -- the linear solve
+// of the exact Schur step (what Ceres' SPARSE_SCHUR / DENSE_SCHUR hand to CHOLMOD / LAPACK for the reference,
+// src/optim/bundle_adjustment.cc:274-284).  Hand-written; no library on this path.
 //
 // Storage: upper block triangle, S = R'R, only the tiles that the camera graph and the symbolic fill (host, once per
 // solve) make non-zero: a banded / block-sparse camera graph costs O(D b^2), a complete graph is an ordinary dense
-// right-looking factorisation on all SMs.  Per tile row k:
-//   panel_kernel   one CTA per tile of row k.  Every CTA factors the (already updated) diagonal tile A_kk = R_kk'R_kk in
-//                  shared memory itself (64^3/3 flops, redundant but off the critical path of nobody); CTA 0 stores the
-//                  inverse of R_kk (all the solves need), CTA c > 0 turns its tile into R_kj = R_kk^-T A_kj.
-//   update_kernel  one CTA per pair (a <= b) of off-diagonal tiles of row k:  A_{ja, jb} -= R_{k, ja}' R_{k, jb}
-//                  (4 x 4 register tiles, explicit DFMA, operands staged through shared memory in two k-halves).
-// solve_kernel: one CTA walks the tile rows forward (R'y = b) and backward (R x = y); the diagonal solves are products
-// with the stored inverse tiles, so a step is two 64-long dot products deep instead of a 64-step substitution chain.
+// factorisation.
+//
+// ONE persistent kernel runs the whole solve as a task graph (left-looking, one task per tile, every tile written once):
+//   DIAG(i)    A_ii -= sum_k R_ki' R_ki over the tiles above it, factored in registers (A = U' D^-1 U elimination, one
+//              barrier per column, rows scaled at the end), R_ii and 1 / diag(R_ii) published; then, off the critical
+//              path, the inverse of R_ii (the two solves are products with it).
+//   OFF(i, j)  A_ij -= sum_k R_ki' R_kj, then R_ij = R_ii^-T A_ij by forward substitution, four threads per column.
+//   FWD(i)     y_i = R_ii^-T (b_i - sum_k R_ki' y_k)        (runs alongside the factorisation)
+//   BACK(i)    x_i = R_ii^-1 (y_i - sum_j R_ij x_j)         (last tile row first, after the factorisation)
+// Tasks are numbered so that every task depends on lower numbers only; CTAs draw task numbers from a global counter, so a
+// CTA that waits (acquire-spin on a per-task flag) always waits for a task that is running or done -- no deadlock
+// whatever the number of resident CTAs.  The dependency lists are laid out by the host once per solve: the structure of
+// a bundle-adjustment problem does not change across LM iterations.
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
 
 #include "ba_common.cuh"
 
 namespace b2 {
 namespace bac {
 
-constexpr int TS = kST;        // 64
-constexpr int LD = TS + 1;     // shared-memory row stride (bank-conflict padding)
+constexpr int TS = kST;  // 64
+constexpr int kThreads = 256;
+enum { TASK_DIAG = 0, TASK_OFF = 1, TASK_FWD = 2, TASK_BACK = 3 };
 
-// A (upper triangle valid) -> R in place: A = R'R.  All threads of the block take part (blockDim = 256, a 16 x 16 grid
-// over the trailing block).  Elimination runs on UNSCALED rows (A = L D L' form: one barrier per column, every thread
-// derives 1 / d_j itself), the rows are scaled by d_j^-1/2 at the end.
-__device__ void factor_tile(double (*A)[LD], int* bad) {
-  const int tid = threadIdx.x, tr = tid >> 4, tc = tid & 15;
-  for (int j = 0; j < TS - 1; ++j) {
-    __syncthreads();
-    const double d = A[j][j];
-    const double inv_d = 1.0 / d;
-    for (int r = j + 1 + tr; r < TS; r += 16) {
-      const double m = A[j][r] * inv_d;
-      for (int c = j + 1 + tc; c < TS; c += 16)
-        if (c >= r) A[r][c] = fma(-m, A[j][c], A[r][c]);
+// ---- memory-ordering helpers: data written by another CTA of this launch is read through L2 (never a stale L1 line)
+__device__ __forceinline__ double ld_l2(const double* p) {
+#ifdef __CUDA_ARCH__
+  return __ldcg(p);
+#else
+  return *p;
+#endif
+}
+__device__ __forceinline__ double2 ld_l2(const double2* p) {
+#ifdef __CUDA_ARCH__
+  return __ldcg(p);
+#else
+  return *p;
+#endif
+}
+__device__ __forceinline__ int ld_flag(const int* p) {
+#ifdef __CUDA_ARCH__
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+#else
+  return *(const volatile int*)p;
+#endif
+}
+// all threads of the CTA call; returns once *f != 0 and the producer's writes are visible to every thread
+__device__ __forceinline__ void wait_flag(const int* f) {
+  if (threadIdx.x == 0) {
+    while (ld_flag(f) == 0) {
+#ifdef __CUDA_ARCH__
+      __nanosleep(32);
+#else
+      // host build of the kernel (CPU test-suite): blocks run one after the other, so a flag that is not set here never
+      // will be -- a broken task order is reported instead of hanging
+      fprintf(stderr, "ba_chol: task waits for a flag that no earlier task set (task order broken)\n");
+      abort();
+#endif
     }
   }
   __syncthreads();
-  for (int e = tid; e < TS * TS; e += blockDim.x) {
-    const int r = e >> 6, c = e & 63;
-    if (c < r) continue;
-    const double d = A[r][r];
-    if (c == r) continue;
-    A[r][c] = A[r][c] / sqrt(d > 0.0 ? d : 1.0);
-  }
+}
+// all threads of the CTA call after their last write of the published data
+__device__ __forceinline__ void publish(int* f) {
   __syncthreads();
-  if (tid < TS) {
-    const double d = A[tid][tid];
-    if (!(d > 0.0)) *bad = 1;
-    A[tid][tid] = sqrt(d > 0.0 ? d : 1.0);
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicExch(f, 1);
   }
-  __syncthreads();
 }
 
-// X = R^-T B for the 64 columns of B (in place), R upper triangular in shared memory: forward substitution, one thread
-// per column with the column in registers; row l of R is a broadcast read.
-__device__ void trsm_tile(const double (*R)[LD], double (*B)[LD]) {
-  const int c = threadIdx.x;
-  if (c < TS) {
-    double a[TS];
+// ---- acc (4 x 4 per thread: rows 4 tr .., columns 4 tc ..) -= A' B for two 64 x 64 row-major tiles in shared memory
+__device__ __forceinline__ void tile_product(const double* __restrict__ sA, const double* __restrict__ sB, int r0, int c0,
+                                             double (&acc)[4][4]) {
+#pragma unroll 4
+  for (int l = 0; l < TS; ++l) {
+    const double2 a01 = *reinterpret_cast<const double2*>(sA + l * TS + r0);
+    const double2 a23 = *reinterpret_cast<const double2*>(sA + l * TS + r0 + 2);
+    const double2 b01 = *reinterpret_cast<const double2*>(sB + l * TS + c0);
+    const double2 b23 = *reinterpret_cast<const double2*>(sB + l * TS + c0 + 2);
+    const double av[4] = {a01.x, a01.y, a23.x, a23.y}, bv[4] = {b01.x, b01.y, b23.x, b23.y};
 #pragma unroll
-    for (int i = 0; i < TS; ++i) a[i] = B[i][c];
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int l = 0; l < TS; ++l) {
-      const double x = a[l] / R[l][l];
-      a[l] = x;
+      for (int j = 0; j < 4; ++j) acc[i][j] = fma(-av[i], bv[j], acc[i][j]);
+  }
+}
+__device__ __forceinline__ void load_tile(const double* __restrict__ g, double* __restrict__ s) {
+  const double2* g2 = reinterpret_cast<const double2*>(g);
+  double2* s2 = reinterpret_cast<double2*>(s);
+  double2 v[8];
 #pragma unroll
-      for (int i = l + 1; i < TS; ++i) a[i] = fma(-R[l][i], x, a[i]);
+  for (int m = 0; m < 8; ++m) v[m] = ld_l2(g2 + threadIdx.x + kThreads * m);
+#pragma unroll
+  for (int m = 0; m < 8; ++m) s2[threadIdx.x + kThreads * m] = v[m];
+}
+
+// X = R^-T B for the 64 columns of B: forward substitution, four threads per column (thread q of a column holds rows
+// q, q + 4, ...; the pivot entry travels by shuffle inside the quad).  sR: R (upper) row-major, sd: 1 / R_ll.
+__device__ __forceinline__ void quad_trsm(const double* __restrict__ sR, const double* __restrict__ sd, double (&a)[16], int q) {
+  const unsigned lane = threadIdx.x & 31u;
+#pragma unroll
+  for (int l = 0; l < TS; ++l) {
+    const double mine = a[l >> 2] * sd[l];
+    const double x = __shfl_sync(0xffffffffu, mine, (int)((lane & ~3u) | (unsigned)(l & 3)));
+    if (q == (l & 3)) a[l >> 2] = x;
+#pragma unroll
+    for (int m = l >> 2; m < 16; ++m) {
+      const int i = 4 * m + q;
+      if (i > l) a[m] = fma(-sR[l * TS + i], x, a[m]);
     }
-#pragma unroll
-    for (int i = 0; i < TS; ++i) B[i][c] = a[i];
   }
 }
 
-constexpr int kPanelSmem = 2 * TS * LD * (int)sizeof(double);  // 66 560 B: above the 48 KB static limit, opted in at launch
-__global__ void __launch_bounds__(256) panel_kernel(BaTiles T, int k) {
-  extern __shared__ double panel_smem[];
-  double (*sA)[LD] = reinterpret_cast<double (*)[LD]>(panel_smem);
-  double (*sB)[LD] = reinterpret_cast<double (*)[LD]>(panel_smem + TS * LD);
-  __shared__ int s_bad;
+struct Plan {
+  const int32_t* task;      // [n_tasks][4]: kind, i, j (OFF), target tile / -1
+  const int32_t* dep_ptr;   // [n_tasks + 1]
+  const int32_t* dep;       // [..][2]: DIAG/OFF (tile(k,i), tile(k,j)); FWD (tile(k,i), k); BACK (tile(i,j), j)
+  int32_t n_tasks;
+  int* flags;               // [n_tiles] tile | [nt] inverse | [nt] y | [nt] x | [1] task counter
+  double* rdiag;            // [nt][64] 1 / diag(R_ii)
+};
+
+__global__ void __launch_bounds__(kThreads, 2) solve_graph_kernel(BaTiles T, Plan Pn, double* __restrict__ x) {
+  extern __shared__ double chol_smem[];
+  double* sA = chol_smem;            // 64 x 64
+  double* sB = chol_smem + TS * TS;  // 64 x 64
+  __shared__ double urow[2][TS];
+  __shared__ double sd[TS], sv[TS], part[4][TS];
+  __shared__ int s_task;
   const int tid = threadIdx.x;
-  const int t0 = T.row_ptr[k];
-  double* Akk = T.tiles + (size_t)t0 * (TS * TS);
-  if (tid == 0) s_bad = 0;
-  for (int e = tid; e < TS * TS; e += blockDim.x) sA[e >> 6][e & 63] = Akk[e];
-  __syncthreads();
-  factor_tile(sA, &s_bad);
-  if (blockIdx.x == 0) {
-    if (tid == 0 && s_bad) *T.info = 1;
-    // A_kk itself stays untouched in global memory: the other CTAs of this launch are still reading it, and nothing
-    // after this launch needs R_kk (the solves work with its inverse)
-    // the inverse of R_kk: X = R^-T I = (R^-1)', stored transposed back as the upper triangular R^-1
-    for (int e = tid; e < TS * TS; e += blockDim.x) sB[e >> 6][e & 63] = ((e >> 6) == (e & 63)) ? 1.0 : 0.0;
+  const int tr = tid >> 4, tc = tid & 15, r0 = 4 * tr, c0 = 4 * tc;
+  int* f_tile = Pn.flags;
+  int* f_inv = Pn.flags + T.n_tiles;
+  int* f_y = f_inv + T.nt;
+  int* f_x = f_y + T.nt;
+  int* counter = f_x + T.nt;
+  for (;;) {
     __syncthreads();
-    trsm_tile(sA, sB);
+    if (tid == 0) s_task = atomicAdd(counter, 1);
     __syncthreads();
-    double* Ri = T.rinv + (size_t)k * (TS * TS);
-    for (int e = tid; e < TS * TS; e += blockDim.x) {
-      const int r = e >> 6, c = e & 63;
-      Ri[e] = (c >= r) ? sB[c][r] : 0.0;
-    }
-  } else {
-    double* Akj = T.tiles + (size_t)(t0 + blockIdx.x) * (TS * TS);
-    for (int e = tid; e < TS * TS; e += blockDim.x) sB[e >> 6][e & 63] = Akj[e];
-    __syncthreads();
-    trsm_tile(sA, sB);
-    __syncthreads();
-    for (int e = tid; e < TS * TS; e += blockDim.x) Akj[e] = sB[e >> 6][e & 63];
-  }
-}
-
-// A_{ja, jb} -= R_{k, ja}' R_{k, jb} for the pair (a <= b) = blockIdx.x of the off-diagonal tiles of row k.
-__global__ void __launch_bounds__(256) update_kernel(BaTiles T, int k) {
-  __shared__ __align__(16) double sA[32][TS];
-  __shared__ __align__(16) double sB[32][TS];
-  const int tid = threadIdx.x;
-  const int t0 = T.row_ptr[k], n = T.row_ptr[k + 1] - t0 - 1;
-  int a = 0, rem = blockIdx.x;
-  while (rem >= n - a) { rem -= n - a; ++a; }
-  const int b = a + rem;
-  const int ja = T.row_col[t0 + 1 + a], jb = T.row_col[t0 + 1 + b];
-  const double* Ra = T.tiles + (size_t)(t0 + 1 + a) * (TS * TS);
-  const double* Rb = T.tiles + (size_t)(t0 + 1 + b) * (TS * TS);
-  double* C = T.tiles + (size_t)T.tile_id[ja * T.nt + jb] * (TS * TS);
-  const int r0 = (tid >> 4) * 4, c0 = (tid & 15) * 4;
-  double acc[4][4];
+    const int t = s_task;
+    if (t >= Pn.n_tasks) break;
+    const int kind = Pn.task[4 * t], i = Pn.task[4 * t + 1], j = Pn.task[4 * t + 2], tile = Pn.task[4 * t + 3];
+    const int d0 = Pn.dep_ptr[t], d1 = Pn.dep_ptr[t + 1];
+    if (kind == TASK_DIAG || kind == TASK_OFF) {
+      double* Aij = T.tiles + (size_t)tile * (TS * TS);
+      double acc[4][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+      for (int a = 0; a < 4; ++a) {
+        const double2 v01 = ld_l2(reinterpret_cast<const double2*>(Aij + (r0 + a) * TS + c0));
+        const double2 v23 = ld_l2(reinterpret_cast<const double2*>(Aij + (r0 + a) * TS + c0 + 2));
+        acc[a][0] = v01.x; acc[a][1] = v01.y; acc[a][2] = v23.x; acc[a][3] = v23.y;
+      }
+      for (int d = d0; d < d1; ++d) {
+        const int ta = Pn.dep[2 * d], tb = Pn.dep[2 * d + 1];
+        wait_flag(f_tile + ta);
+        if (tb != ta) wait_flag(f_tile + tb);
+        load_tile(T.tiles + (size_t)ta * (TS * TS), sA);
+        if (tb != ta) load_tile(T.tiles + (size_t)tb * (TS * TS), sB);
+        __syncthreads();
+        tile_product(sA, tb != ta ? sB : sA, r0, c0, acc);
+        __syncthreads();
+      }
+      if (kind == TASK_DIAG) {
+        // ---- A = U' D^-1 U by elimination on the register blocks; the pivot row travels through shared memory
+        bool bad = false;
+        for (int c = 0; c < TS; ++c) {
+          double* u = urow[c & 1];
+          if (tr == (c >> 2)) {
+            const int a = c & 3;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-  for (int half = 0; half < 2; ++half) {
-    for (int e = tid; e < 32 * TS; e += blockDim.x) {
-      (&sA[0][0])[e] = Ra[half * 32 * TS + e];
-      (&sB[0][0])[e] = Rb[half * 32 * TS + e];
-    }
-    __syncthreads();
-#pragma unroll 8
-    for (int l = 0; l < 32; ++l) {
-      const double2 a01 = *reinterpret_cast<const double2*>(&sA[l][r0]);
-      const double2 a23 = *reinterpret_cast<const double2*>(&sA[l][r0 + 2]);
-      const double2 b01 = *reinterpret_cast<const double2*>(&sB[l][c0]);
-      const double2 b23 = *reinterpret_cast<const double2*>(&sB[l][c0 + 2]);
-      const double av[4] = {a01.x, a01.y, a23.x, a23.y}, bv[4] = {b01.x, b01.y, b23.x, b23.y};
+            for (int b = 0; b < 4; ++b) u[c0 + b] = (a == 0) ? acc[0][b] : (a == 1) ? acc[1][b] : (a == 2) ? acc[2][b] : acc[3][b];
+          }
+          __syncthreads();
+          double dpiv = u[c];
+          if (!(dpiv > 0.0)) { bad = true; dpiv = 1.0; }
+          if (tid == 0) sd[c] = dpiv;
+          if (r0 + 3 > c) {
+            const double inv = 1.0 / dpiv;
+            const double ub[4] = {u[c0], u[c0 + 1], u[c0 + 2], u[c0 + 3]};
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+            for (int a = 0; a < 4; ++a) {
+              if (r0 + a > c) {
+                const double m = u[r0 + a] * inv;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
-    }
-    __syncthreads();
-  }
-  const bool diag = (ja == jb);
+                for (int b = 0; b < 4; ++b) acc[a][b] = fma(-m, ub[b], acc[a][b]);
+              }
+            }
+          }
+        }
+        __syncthreads();
+        if (bad && tid == 0) *T.info = 1;
+        // R = D^-1/2 U; the tile in global memory and a copy in sA for the inverse
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+        for (int a = 0; a < 4; ++a) {
+          const int r = r0 + a;
+          const double sq = sqrt(sd[r]);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int r = r0 + i, c = c0 + j;
-      if (diag && c < r) continue;
-      C[r * TS + c] -= acc[i][j];
+          for (int b = 0; b < 4; ++b) {
+            const int c = c0 + b;
+            const double v = (c > r) ? acc[a][b] / sq : (c == r ? sq : 0.0);
+            sA[r * TS + c] = v;
+            Aij[r * TS + c] = v;
+          }
+        }
+        __syncthreads();
+        if (tid < TS) {
+          const double inv = 1.0 / sA[tid * TS + tid];
+          sv[tid] = inv;
+          Pn.rdiag[(size_t)i * TS + tid] = inv;
+        }
+        publish(f_tile + tile);  // (contains the barrier that orders sv)
+        // ---- off the critical path: Y = R^-T I, stored transposed = R^-1 (upper)
+        {
+          const int c = tid >> 2, q = tid & 3;
+          double a[16];
+#pragma unroll
+          for (int m = 0; m < 16; ++m) a[m] = (4 * m + q == c) ? 1.0 : 0.0;
+          quad_trsm(sA, sv, a, q);
+          double* Ri = T.rinv + (size_t)i * (TS * TS);
+#pragma unroll
+          for (int m = 0; m < 16; ++m) Ri[c * TS + 4 * m + q] = a[m];  // Rinv[c][r] = Y[r][c]; zero below the diagonal
+        }
+        publish(f_inv + i);
+      } else {
+        // ---- R_ij = R_ii^-T A_ij
+        const int tdiag = T.row_ptr[i];
+        wait_flag(f_tile + tdiag);
+        load_tile(T.tiles + (size_t)tdiag * (TS * TS), sA);
+        if (tid < TS) sv[tid] = ld_l2(Pn.rdiag + (size_t)i * TS + tid);
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) sB[(r0 + a) * TS + c0 + b] = acc[a][b];
+        __syncthreads();
+        const int c = tid >> 2, q = tid & 3;
+        double a[16];
+#pragma unroll
+        for (int m = 0; m < 16; ++m) a[m] = sB[(4 * m + q) * TS + c];
+        quad_trsm(sA, sv, a, q);
+        __syncthreads();
+#pragma unroll
+        for (int m = 0; m < 16; ++m) sB[(4 * m + q) * TS + c] = a[m];
+        __syncthreads();
+        {  // coalesced store of the finished tile
+          double2* g2 = reinterpret_cast<double2*>(Aij);
+          const double2* s2 = reinterpret_cast<const double2*>(sB);
+#pragma unroll
+          for (int m = 0; m < 8; ++m) g2[tid + kThreads * m] = s2[tid + kThreads * m];
+        }
+        publish(f_tile + tile);
+      }
+      (void)j;
+    } else if (kind == TASK_FWD) {
+      // ---- y_i = Rinv_i' (b_i - sum_k R_ki' y_k)
+      const int c = tid & 63, q = tid >> 6;
+      double t_own = 0.0;  // thread (q, c): partial of sum_k (R_ki' y_k)[c] over l = 16 q ..
+      for (int d = d0; d < d1; ++d) {
+        const int ta = Pn.dep[2 * d], k = Pn.dep[2 * d + 1];
+        wait_flag(f_tile + ta);
+        wait_flag(f_y + k);
+        if (tid < TS) sv[tid] = ld_l2(x + (size_t)k * TS + tid);
+        __syncthreads();
+        const double* R = T.tiles + (size_t)ta * (TS * TS);
+#pragma unroll 4
+        for (int l = 16 * q; l < 16 * q + 16; ++l) t_own = fma(ld_l2(R + l * TS + c), sv[l], t_own);
+        __syncthreads();
+      }
+      part[q][c] = t_own;
+      __syncthreads();
+      if (tid < TS) sv[tid] = ld_l2(x + (size_t)i * TS + tid) - (part[0][tid] + part[1][tid] + part[2][tid] + part[3][tid]);
+      wait_flag(f_inv + i);  // (barrier inside orders sv)
+      const double* Ri = T.rinv + (size_t)i * (TS * TS);
+      double s = 0.0;
+#pragma unroll 4
+      for (int l = 16 * q; l < 16 * q + 16; ++l)
+        if (l <= c) s = fma(ld_l2(Ri + l * TS + c), sv[l], s);
+      part[q][c] = s;
+      __syncthreads();
+      if (tid < TS) x[(size_t)i * TS + tid] = part[0][tid] + part[1][tid] + part[2][tid] + part[3][tid];
+      publish(f_y + i);
+    } else {
+      // ---- x_i = Rinv_i (y_i - sum_j R_ij x_j): a warp per eight rows, lanes across the columns
+      const int lane = tid & 31, w = tid >> 5;
+      double racc[8];
+#pragma unroll
+      for (int a = 0; a < 8; ++a) racc[a] = 0.0;
+      wait_flag(f_y + i);
+      for (int d = d0; d < d1; ++d) {
+        const int ta = Pn.dep[2 * d], jj = Pn.dep[2 * d + 1];
+        wait_flag(f_x + jj);
+        const double x0 = ld_l2(x + (size_t)jj * TS + lane), x1 = ld_l2(x + (size_t)jj * TS + lane + 32);
+        const double* R = T.tiles + (size_t)ta * (TS * TS);
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+          const int r = 8 * w + a;
+          racc[a] = fma(ld_l2(R + r * TS + lane), x0, fma(ld_l2(R + r * TS + lane + 32), x1, racc[a]));
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < 8; ++a) {
+        double v = racc[a];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) sv[8 * w + a] = v;
+      }
+      __syncthreads();
+      if (tid < TS) sd[tid] = ld_l2(x + (size_t)i * TS + tid) - sv[tid];
+      __syncthreads();
+      const double* Ri = T.rinv + (size_t)i * (TS * TS);
+      const double s0 = sd[lane], s1 = sd[lane + 32];
+#pragma unroll
+      for (int a = 0; a < 8; ++a) {
+        const int r = 8 * w + a;
+        double v = fma(ld_l2(Ri + r * TS + lane), s0, ld_l2(Ri + r * TS + lane + 32) * s1);  // zero below the diagonal
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) sv[r] = v;
+      }
+      __syncthreads();
+      if (tid < TS) x[(size_t)i * TS + tid] = sv[tid];
+      publish(f_x + i);
     }
-}
-
-// R'R x = b in place (x = b on entry).  One CTA of 512 threads = 8 groups of 64.
-__global__ void __launch_bounds__(512) solve_kernel(BaTiles T, double* __restrict__ x) {
-  __shared__ double sv[TS];
-  __shared__ double part[8][TS];
-  const int tid = threadIdx.x, g = tid >> 6, c = tid & 63;
-  // ---- forward: R' y = b
-  for (int k = 0; k < T.nt; ++k) {
-    const int t0 = T.row_ptr[k], n = T.row_ptr[k + 1] - t0 - 1;
-    double* xk = x + (size_t)k * TS;
-    if (tid < TS) sv[tid] = xk[tid];
-    __syncthreads();
-    if (tid < TS) {  // y_k = (R_kk^-1)' b_k
-      const double* Ri = T.rinv + (size_t)k * (TS * TS);
-      double s = 0;
-      for (int l = 0; l <= tid; ++l) s = fma(Ri[l * TS + tid], sv[l], s);
-      xk[tid] = s;
-    }
-    __syncthreads();
-    if (tid < TS) sv[tid] = xk[tid];
-    __syncthreads();
-    for (int t = g; t < n; t += 8) {  // b_j -= R_kj' y_k
-      const double* R = T.tiles + (size_t)(t0 + 1 + t) * (TS * TS);
-      double s = 0;
-      for (int l = 0; l < TS; ++l) s = fma(R[l * TS + c], sv[l], s);
-      x[(size_t)T.row_col[t0 + 1 + t] * TS + c] -= s;
-    }
-    __syncthreads();
-  }
-  // ---- backward: R x = y
-  for (int k = T.nt - 1; k >= 0; --k) {
-    const int t0 = T.row_ptr[k], n = T.row_ptr[k + 1] - t0 - 1;
-    double* xk = x + (size_t)k * TS;
-    double s = 0;
-    for (int t = g; t < n; t += 8) {  // sum_j R_kj x_j, row c of each tile
-      const double* R = T.tiles + (size_t)(t0 + 1 + t) * (TS * TS) + c * TS;
-      const double* xj = x + (size_t)T.row_col[t0 + 1 + t] * TS;
-      for (int l = 0; l < TS; ++l) s = fma(R[l], xj[l], s);
-    }
-    part[g][c] = s;
-    __syncthreads();
-    if (tid < TS) {
-      double t = xk[tid];
-      for (int q = 0; q < 8; ++q) t -= part[q][tid];
-      sv[tid] = t;
-    }
-    __syncthreads();
-    if (tid < TS) {  // x_k = R_kk^-1 s
-      const double* Ri = T.rinv + (size_t)k * (TS * TS) + tid * TS;
-      double t = 0;
-      for (int l = tid; l < TS; ++l) t = fma(Ri[l], sv[l], t);
-      xk[tid] = t;
-    }
-    __syncthreads();
   }
 }
 
 }  // namespace bac
 
-cudaError_t bac_factor(const BaTiles& T, const int32_t* h_row_ptr, const int32_t* h_row_col, const int32_t* h_tile_id,
-                       cudaStream_t s, int* n_launches) {
-  (void)h_row_col; (void)h_tile_id;
-  int launches = 0;
+// Task graph of the solve for a tile pattern (closed under the symbolic fill): host, once per b2_ba_solve.
+void bac_build_graph(int nt, const int32_t* tile_id, const int32_t* row_ptr, const int32_t* row_col, BaCholGraph* G) {
+  G->task.clear();
+  G->dep_ptr.assign(1, 0);
+  G->dep.clear();
+  auto tid_of = [&](int r, int c) { return tile_id[(size_t)r * nt + c]; };
+  for (int i = 0; i < nt; ++i) {
+    for (int e = row_ptr[i]; e < row_ptr[i + 1]; ++e) {
+      const int j = row_col[e];
+      G->task.insert(G->task.end(), {j == i ? bac::TASK_DIAG : bac::TASK_OFF, i, j, e});
+      for (int k = 0; k < i; ++k) {
+        const int ta = tid_of(k, i), tb = tid_of(k, j);
+        if (ta >= 0 && tb >= 0) G->dep.insert(G->dep.end(), {ta, tb});
+      }
+      G->dep_ptr.push_back((int32_t)(G->dep.size() / 2));
+      if (j == i) {  // the forward solve of row i right behind its diagonal tile
+        G->task.insert(G->task.end(), {bac::TASK_FWD, i, i, -1});
+        for (int k = 0; k < i; ++k)
+          if (tid_of(k, i) >= 0) G->dep.insert(G->dep.end(), {tid_of(k, i), k});
+        G->dep_ptr.push_back((int32_t)(G->dep.size() / 2));
+      }
+    }
+  }
+  for (int i = nt - 1; i >= 0; --i) {
+    G->task.insert(G->task.end(), {bac::TASK_BACK, i, i, -1});
+    for (int e = row_ptr[i + 1] - 1; e > row_ptr[i]; --e) G->dep.insert(G->dep.end(), {e, row_col[e]});  // farthest column first: x_{i+1}, the last one written, is waited for last
+    G->dep_ptr.push_back((int32_t)(G->dep.size() / 2));
+  }
+  G->n_tasks = (int32_t)(G->task.size() / 4);
+}
+
+size_t bac_flag_count(const BaTiles& T) { return (size_t)T.n_tiles + 3 * (size_t)T.nt + 1; }
+
+// S x = b in place (x = b on entry, padded to whole tiles); S is overwritten by its factor.
+cudaError_t bac_solve_system(const BaTiles& T, const BaCholDev& G, double* x, int n_sm, cudaStream_t s) {
+  if (T.nt == 0) return cudaSuccess;
+  constexpr int kSmem = 2 * bac::TS * bac::TS * (int)sizeof(double);  // 65 536 B: above the 48 KB static limit
   static bool attr_set = false;  // per process; the attribute is a property of the function, not of the handle
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(bac::panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bac::kPanelSmem);
+    cudaError_t e = cudaFuncSetAttribute(bac::solve_graph_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  for (int k = 0; k < T.nt; ++k) {
-    const int n = h_row_ptr[k + 1] - h_row_ptr[k];  // tiles in row k, the diagonal one included
-    bac::panel_kernel<<<n, 256, bac::kPanelSmem, s>>>(T, k);
-    ++launches;
-    if (n > 1) {
-      const int m = n - 1;
-      bac::update_kernel<<<m * (m + 1) / 2, 256, 0, s>>>(T, k);
-      ++launches;
-    }
-  }
-  if (n_launches) *n_launches = launches;
-  return cudaGetLastError();
-}
-
-cudaError_t bac_solve(const BaTiles& T, double* x, int64_t D, cudaStream_t s) {
-  (void)D;
-  if (T.nt == 0) return cudaSuccess;
-  bac::solve_kernel<<<1, 512, 0, s>>>(T, x);
+  cudaError_t e = cudaMemsetAsync(G.flags, 0, bac_flag_count(T) * sizeof(int), s);
+  if (e != cudaSuccess) return e;
+  bac::Plan Pn;
+  Pn.task = G.task; Pn.dep_ptr = G.dep_ptr; Pn.dep = G.dep; Pn.n_tasks = G.n_tasks; Pn.flags = G.flags; Pn.rdiag = G.rdiag;
+  const int grid = std::min(G.n_tasks, 2 * std::max(n_sm, 1));
+  bac::solve_graph_kernel<<<grid, bac::kThreads, kSmem, s>>>(T, Pn, x);
   return cudaGetLastError();
 }
 

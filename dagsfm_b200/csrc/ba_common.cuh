@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <vector>
 
 namespace b2 {
 
@@ -180,9 +181,21 @@ cudaError_t baf_launch_schur_points(const BaDev& P, const BaWin& W, double radiu
 cudaError_t baf_launch_schur_window(const BaDev& P, const BaWin& W, const BaTiles& T, int n_sm, cudaStream_t s);
 cudaError_t baf_launch_finish(const BaDev& P, const BaTiles& T, double radius, double min_diag, double max_diag, cudaStream_t s);
 cudaError_t baf_launch_backsub(const BaDev& P, double* scal, int loss_type, double loss_scale, cudaStream_t s);
-// tiled Cholesky of the packed system and the two triangular solves (x overwritten: in = rhs, out = solution)
-cudaError_t bac_factor(const BaTiles& T, const int32_t* h_row_ptr, const int32_t* h_row_col, const int32_t* h_tile_id,
-                       cudaStream_t s, int* n_launches);
-cudaError_t bac_solve(const BaTiles& T, double* x, int64_t D, cudaStream_t s);
+// tiled Cholesky of the packed system + the two triangular solves as ONE persistent task-graph kernel (ba_chol.cu)
+struct BaCholGraph {                 // host: built once per solve from the tile pattern
+  std::vector<int32_t> task;         // [n_tasks][4] kind, i, j, tile
+  std::vector<int32_t> dep_ptr, dep; // CSR of (tile, tile | vector block) pairs a task waits for and consumes
+  int32_t n_tasks = 0;
+};
+struct BaCholDev {                   // its device copy + the per-launch state
+  const int32_t *task, *dep_ptr, *dep;
+  int32_t n_tasks;
+  int* flags;                        // bac_flag_count(T) ints
+  double* rdiag;                     // [nt * 64]
+};
+void bac_build_graph(int nt, const int32_t* tile_id, const int32_t* row_ptr, const int32_t* row_col, BaCholGraph* G);
+size_t bac_flag_count(const BaTiles& T);
+// S x = b in place (x = b on entry, padded to whole tiles, out = solution); S is overwritten by its factor
+cudaError_t bac_solve_system(const BaTiles& T, const BaCholDev& G, double* x, int n_sm, cudaStream_t s);
 
 }  // namespace b2

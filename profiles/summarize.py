@@ -28,12 +28,22 @@ KEYS = [
     "sm__warps_active.avg.pct_of_peak_sustained_active",
     "smsp__issue_active.avg.pct_of_peak_sustained_active",
     "smsp__inst_executed.sum", "sm__inst_executed_pipe_tmem",
+    "smsp__average_warp_latency_issue_stalled_long_scoreboard", "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio", "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_membar_per_issue_active.ratio", "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio", "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
+    "sm__warps_active.avg.per_cycle_active", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+    "launch__shared_mem_per_block_static", "launch__waves_per_multiprocessor", "smsp__cycles_active.avg",
+    "derived__smsp__sass_thread_inst_executed_op_dfma_pred_on_x2", "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum",
 ]
 
 
 OURS = re.compile(r"b2::|match_top2|match_fixup|match_cross|verify_pairs|schur_kernel|camera_terms|jacobian_kernel|"
                   r"backsub_kernel|model_cost|candidate_|block_scan|pair_items|fill_items|normalize_points|"
-                  r"make_scale|negate_kernel|add_diag|score_models|debug_s|max_matches")
+                  r"make_scale|negate_kernel|add_diag|score_models|debug_s|max_matches|baf::|bac::|bak::|bit::|bai::|vp::|vf::|ts::|vt::")
 
 
 def is_ours(name):

@@ -376,6 +376,9 @@ inline int __ffs(int v) { return __builtin_ffs(v); }
 inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 inline long long clock64() { return 0; }
 template <class T> inline T __ldg(const T* p) { return *p; }
+template <class T> inline T __ldcg(const T* p) { return *p; }
+inline void __threadfence() {}   // one OS thread runs the whole grid: program order is memory order
+inline void __nanosleep(unsigned) {}
 inline long long __double_as_longlong(double d) { long long r; std::memcpy(&r, &d, 8); return r; }
 inline double __longlong_as_double(long long v) { double r; std::memcpy(&r, &v, 8); return r; }
 inline unsigned __dp4a(unsigned a, unsigned b, unsigned c) {
