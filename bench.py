@@ -1,19 +1,20 @@
 #!/usr/bin/env python
-"""bench.py -- headline benchmark of the hot path (BASELINE.json metric).
+"""bench.py -- headline benchmark of the hot path (BASELINE.json metric: image pairs VERIFIED per second + BA iter/s).
 
-Workload (configs[1] of BASELINE.json, SURVEY.md section 8d "C2"): 1000 synthetic
-images x 4096 SIFT descriptors (512 MiB, larger than L2), exhaustive matching of
-all 499 500 pairs with the reference defaults (max_ratio 0.8, max_distance 0.7,
-cross_check on).  One "step" = one pass over the whole pair list.
+Headline workload (BASELINE configs[2], SURVEY.md 8d "C3"): a synthetic sequence of 5000 images x 2048 SIFT keypoints
+(dagsfm_b200/synthetic.py: one long 3-D scene, neighbouring images overlap), the 50 candidate pairs per image a
+retrieval stage would hand over (248 725 pairs), every pair through descriptor matching (sift.cc:76-198) AND two-view
+geometric verification (two_view_geometry.cc:292-489) -- the reference's SiftFeatureMatcher pipeline
+(feature/matching.cc:610-839) -- with the match lists staying on the device.  One "step" = one pass over the whole
+candidate list.  `value` = candidate pairs verified per second with the images resident in HBM; `e2e` = the same pass
+with descriptors, keypoints and pairs coming from pinned host memory and results + match / inlier lists going back.
 
     python bench.py [--gpus N] [--steps K] [--warmup W]
-    python bench.py --impl reference ...     # reference CPU path (oracle port) on host cores
+    python bench.py --impl reference ...     # the reference's CPU path (oracle port) on the host cores
 
-Prints ONE JSON line (rank 0).  `value` = image pairs matched per second with the
-descriptors resident in HBM (device-event time); `e2e` = same metric through the
-host-buffer C ABI (b2_match_set_images + b2_match_pairs, H2D/D2H inside the timed
-region).  Multi-GPU: pairs are independent units -> every rank matches its own
-replica of the workload, no collective on the data path ("weak").
+Multi-GPU: ONE pair list, cut into contiguous (locality-ordered) ranges, one per rank; rank 0 gathers the results
+inside the timed region -> "strong" scaling.  Extra legs in the same JSON line: `match` (C2: 1000 x 4096 exhaustive
+matching, tcgen05 roofline), `ba` (C4: 500 cams / 100k pts / 1M obs), `ba_c5` with --ba-c5 (10k cams, ITERATIVE_SCHUR).
 """
 from __future__ import annotations
 
@@ -31,7 +32,7 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-METRIC = "image_pairs_matched_per_s"
+METRIC = "image_pairs_verified_per_s"
 UNIT = "pairs/s"
 
 
@@ -41,11 +42,14 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--images", type=int, default=1000)
-    ap.add_argument("--desc", type=int, default=4096)
-    ap.add_argument("--pairs", type=int, default=0, help="limit pairs per step (0 = exhaustive)")
-    ap.add_argument("--cpu-sample", type=int, default=48, help="pairs in the CPU baseline sample")
-    ap.add_argument("--verify-pairs", type=int, default=20000, help="pairs in the verification leg (0 = skip)")
+    ap.add_argument("--seq-images", type=int, default=5000, help="C3 pipeline: images in the sequence")
+    ap.add_argument("--seq-kp", type=int, default=2048, help="C3 pipeline: keypoints (= descriptors) per image")
+    ap.add_argument("--seq-cand", type=int, default=50, help="C3 pipeline: candidate pairs per image")
+    ap.add_argument("--images", type=int, default=1000, help="C2 match leg: images")
+    ap.add_argument("--desc", type=int, default=4096, help="C2 match leg: descriptors per image")
+    ap.add_argument("--pairs", type=int, default=131072, help="C2 match leg: pairs per step (0 = all 499 500; -1 = skip the leg)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="pairs in the CPU baseline sample (0 = 24 per core)")
+    ap.add_argument("--verify-pairs", type=int, default=0, help="opt-in leg: stand-alone verification of pre-matched pairs")
     ap.add_argument("--ba", default="500,100000,10", help="BA leg: images,points,track (empty = skip)")
     ap.add_argument("--guided-pairs", type=int, default=0,
                     help="opt-in leg: guided matching (b2_match_guided_pairs, MatchGuidedSiftFeaturesGPU) on this many synthetic pairs")
@@ -418,20 +422,232 @@ def bench_ba(a, local_rank, rank, world, cores, barrier, hbm):
     return out
 
 
+FP64_PEAK_FALLBACK = 36.6   # TFLOP/s, DFMA micro-benchmark on this pool's B200 (profiles/r2_fp64_peak.json)
+
+
+def peaks_fp64():
+    try:
+        d = json.loads((ROOT / "profiles" / "r2_fp64_peak.json").read_text())
+        return float(d["fp64_tflops"]), "profiles/r2_fp64_peak.json (b2_peak_fp64 DFMA micro-benchmark on a pool B200; MEASURED_PEAKS.json has no FP64 entry)"
+    except Exception:
+        return FP64_PEAK_FALLBACK, "fallback: 36.6 TFLOP/s measured on a pool B200 in round 2"
+
+
+def pipeline_cpu_reference(coll_desc_host, keypoints, cam_params, prior, pairs, seeds, n_sample, threads):
+    """The reference's CPU path for the pipeline on a uniform sample of the step's pairs: MatchSiftFeaturesCPU
+    (oracle port of sift.cc:76-198,810-822) then TwoViewGeometry::Estimate (oracle port of two_view_geometry.cc:292-489),
+    `threads` workers each on one pair at a time (matching.cc:640-660).  -> (pairs/s, seconds, sample indices,
+    oracle results, oracle match counts)."""
+    import ctypes as C
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import pyoracle as orc
+    rng = np.random.default_rng(0)
+    idx = np.sort(rng.choice(len(pairs), size=min(n_sample, len(pairs)), replace=False))
+    sample = np.ascontiguousarray(pairs[idx])
+    ns = len(sample)
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as ex:      # ctypes releases the GIL inside the oracle
+        mts = list(ex.map(lambda ab: orc.match_sift(coll_desc_host[ab[0]], coll_desc_host[ab[1]]), sample.tolist()))
+    t_match = time.perf_counter() - t0
+    off = np.concatenate([[0], np.cumsum([len(m) for m in mts])]).astype(np.int64)
+    mt = np.ascontiguousarray(np.concatenate(mts) if off[-1] else np.zeros((0, 2), np.uint32), dtype=np.uint32)
+    n_img = len(keypoints)
+    ocams = (orc.OrcCamera * n_img)(*[orc.make_camera(params=cam_params, prior=bool(p)) for p in prior])
+    kk = [np.ascontiguousarray(k, np.float64) for k in keypoints]
+    ptrs = (C.c_void_p * n_img)(*[k.ctypes.data for k in kk])
+    oo = orc.tv_default_options()
+    ores = (orc.OrcTvResult * ns)()
+    oinl = np.zeros((max(int(off[-1]), 1), 2), np.uint32)
+    sd = np.ascontiguousarray(seeds[idx], np.uint32)
+    with orc.solver_stack(1):   # the oracle in the kernel's operation order: identity with the GPU, not an agreement rate
+        t_verify = orc._tv().orc_two_view_pairs_mt2(C.cast(ocams, C.c_void_p), C.cast(ptrs, C.c_void_p), sample.ctypes.data, ns,
+                                                    off.ctypes.data, mt.ctypes.data, C.byref(oo), sd.ctypes.data, threads,
+                                                    C.cast(ores, C.c_void_p), oinl.ctypes.data)
+    secs = t_match + t_verify
+    return ns / secs, secs, idx, ores, np.diff(off), (t_match, t_verify)
+
+
+def bench_pipeline(a, dev, local_rank, rank, world, cores, barrier, dist):
+    """C3: match -> verify of one candidate list, sharded over the ranks; see the module docstring."""
+    import torch
+    from dagsfm_b200 import SiftMatchingOptions, TwoViewOptions, lib
+    from dagsfm_b200.pipeline import SiftFeatureMatcher, cameras_of
+    from dagsfm_b200.synthetic import candidate_pairs, make_image_collection
+    coll = make_image_collection(a.seq_images, a.seq_kp, seed=1234, device=dev, overlap_images=a.seq_cand)
+    pairs_all = candidate_pairs(a.seq_images, a.seq_cand)
+    n_all = len(pairs_all)
+    seeds_all = (np.arange(n_all, dtype=np.uint64) * 2654435761 % (2 ** 32)).astype(np.uint32)
+    lo, hi = (n_all * rank) // world, (n_all * (rank + 1)) // world       # contiguous, locality-ordered shard
+    pairs, seeds = pairs_all[lo:hi], seeds_all[lo:hi]
+    cams = cameras_of(coll)
+    fm = SiftFeatureMatcher(SiftMatchingOptions(), TwoViewOptions.default(), local_rank, chunk_pairs=16384)
+    fm.setup_device_descriptors(coll["desc"].data_ptr(), a.seq_images, a.seq_kp, coll["keypoints"], cams)
+    from dagsfm_b200.verification import RESULT_DTYPE
+    gathered = None
+
+    def gather(res):
+        """rank 0 receives every shard's results (the reference's single output queue / database writer)."""
+        nonlocal gathered
+        if world == 1:
+            gathered = res
+            return
+        t = torch.from_numpy(res.view(np.uint8).reshape(-1)).to(dev)
+        sizes = [((n_all * (r + 1)) // world - (n_all * r) // world) * RESULT_DTYPE.itemsize for r in range(world)]
+        pad = torch.zeros(max(sizes), dtype=torch.uint8, device=dev)
+        pad[:t.numel()] = t
+        out = [torch.empty(max(sizes), dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None
+        dist.gather(pad, out, dst=0)
+        if rank == 0:
+            gathered = np.concatenate([o[:sz].cpu().numpy() for o, sz in zip(out, sizes)]).view(RESULT_DTYPE)
+
+    def step():
+        res, _, _, _ = fm.run_device(pairs, seeds, keep_lists=False)
+        gather(res)
+        return res
+
+    for _ in range(a.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = lib().b2_kernel_launch_count()
+    t_match = t_verify = 0.0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    wall0 = time.perf_counter()
+    ev0.record()
+    for _ in range(a.steps):
+        res = step()
+        t_match += fm.match_seconds
+        t_verify += fm.verify_seconds
+    ev1.record()
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = lib().b2_kernel_launch_count() - launches0
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([wall, t_match, t_verify], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall, t_match, t_verify = t.tolist()
+    out = {"n_pairs": n_all, "wall_s": wall, "match_kernel_s": t_match, "verify_kernel_s": t_verify,
+           "launches": int(launches), "clocks": clocks, "value": n_all * a.steps / wall}
+    # ------------------------------------------------------------------ e2e: host buffers in, results + lists out
+    if not a.no_e2e:
+        host = torch.empty(coll["desc"].shape, dtype=torch.uint8, pin_memory=True)
+        host.copy_(coll["desc"])
+        hd = host.numpy()
+        hdescs = [hd[i] for i in range(a.seq_images)]
+        kps = list(coll["keypoints"])
+        e_steps = 1 if world == 1 else max(1, min(a.steps, 2))
+        barrier()
+        w0 = time.perf_counter()
+        d2h = 0
+        for _ in range(e_steps):
+            fm.Setup(hdescs, kps, cams)                                   # H2D: descriptors + keypoints + cameras
+            r2, off2, mt2, inl2 = fm.run_device(pairs, seeds, keep_lists=True)   # H2D pairs + seeds; D2H results + lists
+            gather(r2)
+            d2h = r2.nbytes + off2.nbytes + mt2.nbytes + inl2.nbytes
+        barrier()
+        w = time.perf_counter() - w0
+        if world > 1:
+            t = torch.tensor([w], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            w = t.item()
+        out["e2e"] = {"value": n_all * e_steps / w, "unit": UNIT,
+                      "h2d_bytes_per_step": int(hd.nbytes + coll["keypoints"].nbytes + pairs.nbytes + seeds.nbytes),
+                      "d2h_bytes_per_step": int(d2h), "steps": e_steps,
+                      "api": "SiftFeatureMatcher.Setup (b2_match_set_images + b2_verify_set_images, host buffers) + "
+                             "b2_match_pairs_device -> b2_verify_pairs_device per 16 384-pair chunk, results / match lists / inlier lists to the host",
+                      "bytes_note": "per rank" if world > 1 else "whole job"}
+        fm.setup_device_descriptors(coll["desc"].data_ptr(), a.seq_images, a.seq_kp, coll["keypoints"], cams)
+    if rank == 0:
+        g = gathered
+        m = np.maximum(g["E_num_trials"].astype(np.float64) + g["F_num_trials"], 0)
+        out["results"] = {"config_histogram": {int(k): int(c) for k, c in zip(*np.unique(g["config"], return_counts=True))},
+                          "mean_inliers_of_verified": float(g["n_inliers"][g["config"] > 1].mean()) if (g["config"] > 1).any() else 0.0,
+                          "trials_per_pair": {k: float(g[k + "_num_trials"].mean()) for k in ("E", "F", "H")}}
+        out["_gathered"] = g
+    out["_coll"], out["_pairs"], out["_seeds"], out["_fm"] = coll, pairs_all, seeds_all, fm
+    return out
+
+
+def bench_match(a, dev, local_rank, rank, world, barrier, dist):
+    """C2 leg (BASELINE configs[1]): exhaustive descriptor matching of 1000 x 4096 images, descriptors resident in HBM;
+    every rank matches its own replica of the pair list (extra leg, not the headline)."""
+    import torch
+    from dagsfm_b200 import SiftMatchGPU, SiftMatchingOptions
+    desc = make_descriptors_torch(a.images, a.desc, 1234 + rank, dev)
+    pairs = all_pairs(a.images, a.pairs)
+    n_pairs = len(pairs)
+    opt = SiftMatchingOptions()
+    m = SiftMatchGPU(local_rank)
+    torch.cuda.synchronize()
+    m.set_images_device(desc.data_ptr(), np.arange(a.images, dtype=np.int64) * a.desc, np.full(a.images, a.desc, dtype=np.int32))
+    pairs_dev = torch.from_numpy(pairs.astype(np.int32)).to(dev)
+    cap = max(64 << 20, int(n_pairs) * 64)
+    off_dev = torch.empty(n_pairs + 1, dtype=torch.int64, device=dev)
+    mat_dev = torch.empty((cap, 2), dtype=torch.int32, device=dev)
+    steps, warm = max(1, min(a.steps, 2)), max(1, min(a.warmup, 2))
+    for _ in range(warm):
+        m.match_pairs_device(n_pairs, pairs_dev.data_ptr(), opt, off_dev.data_ptr(), mat_dev.data_ptr(), cap)
+    barrier()
+    t_dev = t_tc = 0.0
+    n_tc = 0
+    for _ in range(steps):
+        total = m.match_pairs_device(n_pairs, pairs_dev.data_ptr(), opt, off_dev.data_ptr(), mat_dev.data_ptr(), cap)
+        tm = m.last_timing()
+        t_dev += tm["all_kernels_s"]
+        t_tc += tm["tc_kernel_s"]
+        n_tc += tm["tc_launches"]
+    barrier()
+    if world > 1:
+        t = torch.tensor([t_dev], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_dev = t.item()
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0
+    ops_per_pair = 2.0 * a.desc * a.desc * 128
+    achieved = ops_per_pair * n_pairs * steps / t_tc / 1e12
+    i8 = None
+    try:
+        i8 = json.loads((ROOT / "profiles" / "r2_fp64_peak.json").read_text()).get("i8_tops_library_gemm")
+    except Exception:
+        pass
+    out = {"workload": f"C2: {a.images} images x {a.desc} desc, {n_pairs} pairs per step ({'exhaustive' if n_pairs == a.images * (a.images - 1) // 2 else 'prefix of the exhaustive list'}), replicated per rank",
+           "pairs_per_s": world * n_pairs * steps / t_dev, "ms_per_step": 1e3 * t_dev / steps, "matches_per_step": int(total),
+           "roofline": {"bound": "tensor", "kernel": "match_top2_ts_kernel (tcgen05 kind::i8, query operand in TMEM)",
+                        "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                        "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s") +
+                                       "; the contraction is i8 (dense i8 peak nominally 2x bf16) and each pair is contracted twice, once per direction",
+                        "frac_of_i8_library_gemm": (2 * achieved / i8) if i8 else None,
+                        "i8_note": "executed i8 TOP/s (both directions) / cuBLASLt i8 GEMM TOP/s measured on a pool B200 (profiles/r2_fp64_peak.json)",
+                        "algorithmic_ops_per_pair": ops_per_pair, "avg_launch_ms": 1e3 * t_tc / max(n_tc, 1), "launches": n_tc,
+                        "share_of_step": t_tc / t_dev, "traffic": 4.534e9 if (a.desc == 4096 and n_tc and abs(n_pairs * steps / n_tc - 8192) < 64) else None}}
+    m.close()
+    return out
+
+
 def main():
     a = parse()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     cores = effective_cores()
-    a.cpu_sample = max(a.cpu_sample, 12 * cores)  # ~10 s of CPU work at one 4096x4096 pair per core-second
-    workload = f"C2: {a.images} images x {a.desc} desc, exhaustive match + ratio test"
-    cfg = {"workload": workload, "n_images": a.images, "desc_per_image": a.desc,
-           "options": "max_ratio 0.8, max_distance 0.7, cross_check 1",
+    if a.cpu_sample <= 0:
+        a.cpu_sample = 24 * cores      # ~10-20 s of host work at ~2 pairs per core-second
+    n_cand = a.seq_images * a.seq_cand - a.seq_cand * (a.seq_cand + 1) // 2
+    workload = (f"C3: {a.seq_images} images x {a.seq_kp} keypoints, {a.seq_cand} candidate pairs per image ({n_cand} pairs), "
+                f"descriptor match + ratio test + cross check -> E/F/H LO-RANSAC verification, chained on the device")
+    cfg = {"workload": workload, "n_images": a.seq_images, "keypoints_per_image": a.seq_kp, "candidates_per_image": a.seq_cand,
+           "options": "match: max_ratio 0.8, max_distance 0.7, cross_check 1; verify: reference defaults (max_error 4 px, confidence 0.999, "
+                      "max_num_trials 10000, min_inlier_ratio 0.25, min_num_inliers 15)",
            "l2": (lambda mib: f"descriptor pool {mib:.0f} MiB " + ("> 126 MB L2 (inputs larger than L2)" if mib > 126
                                                                      else "<= 126 MB L2 (NOT a valid timing configuration)"))(
-               a.images * a.desc * 128 / 2**20),
-           "sharding": "pairs replicated per rank, no collective"}
+               a.seq_images * a.seq_kp * 128 / 2**20),
+           "sharding": "one candidate list, contiguous ranges per rank, results gathered on rank 0 (no data-path collective)"}
 
     import torch
 
@@ -439,24 +655,27 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return
+        from dagsfm_b200.synthetic import candidate_pairs, make_image_collection
         dev = "cuda" if torch.cuda.is_available() else "cpu"
-        d = make_descriptors_torch(a.images, a.desc, 1234, dev).cpu().numpy()
-        descs = [d[i] for i in range(a.images)]
-        pairs = all_pairs(a.images, a.pairs)
+        coll = make_image_collection(a.seq_images, a.seq_kp, seed=1234, device=dev, overlap_images=a.seq_cand)
+        hd = coll["desc"].cpu().numpy()
+        pairs = candidate_pairs(a.seq_images, a.seq_cand)
+        seeds = (np.arange(len(pairs), dtype=np.uint64) * 2654435761 % (2 ** 32)).astype(np.uint32)
         from oracle import pyoracle as orc
         orc.lib()
         per = []
         for s in range(a.warmup + a.steps):
-            v, secs, ns, _, _ = cpu_reference(descs, pairs, a.cpu_sample, cores)
+            v, secs, *_ = pipeline_cpu_reference(hd, coll["keypoints"], coll["cam_params"], coll["prior"], pairs, seeds,
+                                                 a.cpu_sample, cores)
             if s >= a.warmup:
                 per.append((v, secs))
         v = float(np.mean([p[0] for p in per]))
         ms = float(np.mean([p[1] for p in per])) * 1e3
-        sample = f"{a.cpu_sample} uniformly sampled pairs of the step per timed step"
+        sample = f"{a.cpu_sample} uniformly sampled candidate pairs of the step per timed step, match + verify, {cores} threads"
         print(json.dumps({
             "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64 (verification) / u8 x u8 -> s32 (matching)", "data": "synthetic",
             "config": cfg,
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -467,6 +686,7 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    dist = None
     if world > 1:
         import torch.distributed as dist
         # NCCL prints its version banner on stdout at the first collective; keep stdout for the
@@ -483,156 +703,96 @@ def main():
             os.dup2(saved_fd, 1)
             os.close(saved_fd)
 
-    from dagsfm_b200 import SiftMatchGPU, SiftMatchingOptions, lib
-
-    desc = make_descriptors_torch(a.images, a.desc, 1234 + rank, dev)
-    pairs = all_pairs(a.images, a.pairs)
-    n_pairs = len(pairs)
-    opt = SiftMatchingOptions()
-    m = SiftMatchGPU(local_rank)
-    row_off = (np.arange(a.images, dtype=np.int64) * a.desc)
-    n_desc = np.full(a.images, a.desc, dtype=np.int32)
-    torch.cuda.synchronize()
-    m.set_images_device(desc.data_ptr(), row_off, n_desc)
-    pairs_dev = torch.from_numpy(pairs.astype(np.int32)).to(dev)
-    cap = max(64 << 20, int(n_pairs) * 64)
-    off_dev = torch.empty(n_pairs + 1, dtype=torch.int64, device=dev)
-    mat_dev = torch.empty((cap, 2), dtype=torch.int32, device=dev)
-
-    def step_device():
-        return m.match_pairs_device(n_pairs, pairs_dev.data_ptr(), opt, off_dev.data_ptr(),
-                                    mat_dev.data_ptr(), cap)
-
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(a.warmup):
-        total = step_device()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    launches0 = lib().b2_kernel_launch_count()
-    t_dev = t_tc = 0.0
-    n_tc = 0
-    wall0 = time.perf_counter()
-    for _ in range(a.steps):
-        total = step_device()
-        tm = m.last_timing()
-        t_dev += tm["all_kernels_s"]
-        t_tc += tm["tc_kernel_s"]
-        n_tc += tm["tc_launches"]
-        cands = tm["fixup_candidates"]
-    barrier()
-    wall = time.perf_counter() - wall0
-    launches = lib().b2_kernel_launch_count() - launches0
-    clocks = sampler.stop()
-    if world > 1:
-        t = torch.tensor([t_dev, wall], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_dev, wall = t.tolist()
-    value = world * n_pairs * a.steps / t_dev
+    pl = bench_pipeline(a, dev, local_rank, rank, world, cores, barrier, dist)
+    fm = pl.pop("_fm")
+    coll, pairs_all, seeds_all = pl.pop("_coll"), pl.pop("_pairs"), pl.pop("_seeds")
+    gathered = pl.pop("_gathered", None)
 
-    # ------------------------------------------------------------------ e2e leg
-    e2e = None
-    if not a.no_e2e:
-        host = torch.empty(desc.shape, dtype=torch.uint8, pin_memory=True)
-        host.copy_(desc)
-        hd = host.numpy()
-        hdescs = [hd[i] for i in range(a.images)]
-        e_steps = max(1, min(a.steps, 2))
-        for _ in range(1):
-            m.set_images(hdescs)
-            off, mm = m.match_pairs(pairs, opt, capacity=cap)
-        barrier()
-        w0 = time.perf_counter()
-        t_up = 0.0
-        for _ in range(e_steps):
-            u0 = time.perf_counter()
-            m.set_images(hdescs)                       # H2D of the step's descriptors
-            t_up += time.perf_counter() - u0
-            off, mm = m.match_pairs(pairs, opt, capacity=cap)  # H2D pairs, D2H offsets + matches
-        barrier()
-        w = time.perf_counter() - w0
-        if world > 1:
-            t = torch.tensor([w], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            w = t.item()
-        e2e = {"value": world * n_pairs * e_steps / w, "unit": UNIT,
-               "h2d_bytes_per_step": int(hd.nbytes + pairs.nbytes),
-               "d2h_bytes_per_step": int(off.nbytes + mm.nbytes), "steps": e_steps,
-               "upload_s_per_step": t_up / e_steps, "match_s_per_step": (w - t_up) / e_steps,
-               "api": "b2_match_set_images + b2_match_pairs (host buffers)"}
-        m.set_images_device(desc.data_ptr(), row_off, n_desc)
+    # ------------------------------------------------------------------ CPU baseline + parity spot check (rank 0)
+    cpu = None
+    if rank == 0 and not a.no_cpu:
+        hd = coll["desc"].cpu().numpy()
+        v, secs, idx, ores, ocounts, (tm, tv) = pipeline_cpu_reference(hd, coll["keypoints"], coll["cam_params"], coll["prior"],
+                                                                      pairs_all, seeds_all, a.cpu_sample, cores)
+        g = gathered[idx]
+        same = sum(int(ores[i].config == g["config"][i] and ores[i].n_inliers == g["n_inliers"][i] and
+                       ores[i].E_trials == g["E_num_trials"][i] and ores[i].F_trials == g["F_num_trials"][i] and
+                       ores[i].H_trials == g["H_num_trials"][i] and
+                       all(np.array_equal(np.array(getattr(ores[i], m)[:]).view(np.uint64), g[m][i].view(np.uint64)) for m in "EFH"))
+                   for i in range(len(idx)))
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{len(idx)} uniformly sampled candidate pairs of the step, {secs:.1f} s ({tm:.1f} s matching + {tv:.1f} s verification), "
+                         "oracle port of MatchSiftFeaturesCPU + TwoViewGeometry::Estimate",
+               "identical_to_gpu": f"{same}/{len(idx)}",
+               "identical_means": "configuration, inlier and trial counts, E / F / H bit for bit, on matches the oracle computed itself"}
+    fm.close()
+    del coll
+    torch.cuda.empty_cache()
 
-
-    # ------------------------------------------------------- verification leg (SURVEY C3 flavour)
-    verify = None
-    if a.verify_pairs > 0:
-        verify = bench_verify(a, local_rank, rank, world, cores, barrier)
+    # ------------------------------------------------------- extra legs
+    match = bench_match(a, dev, local_rank, rank, world, barrier, dist) if a.pairs >= 0 else None
+    verify = bench_verify(a, local_rank, rank, world, cores, barrier) if a.verify_pairs > 0 else None
     guided = None
-    if getattr(a, "guided_pairs", 0) > 0:     # opt-in: the guided kernel has not been validated on a GPU yet
+    if getattr(a, "guided_pairs", 0) > 0:
         try:
             guided = bench_guided(a, local_rank, rank, world, cores, barrier)
         except Exception as e:
             guided = {"error": repr(e)}
-    # ------------------------------------------------------- bundle adjustment leg
-    ba = None
-    if a.ba:
-        ba = bench_ba(a, local_rank, rank, world, cores, barrier, peaks_hbm())
+    ba = bench_ba(a, local_rank, rank, world, cores, barrier, peaks_hbm()) if a.ba else None
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # --------------------------------------------------------------- roofline
-    peaks = {}
+    # --------------------------------------------------------------- roofline of the dominant kernel of the step
+    # verify_pairs_kernel: SURVEY 8(d) unit = one hypothesis evaluated against one match (33 FP64 flop Sampson for E / F,
+    # 25 for H); lower bound from the trial counts the kernel reports (>= 1 hypothesis per trial, LO and tie passes not
+    # counted), divided by the kernel's device time (CUDA events on its stream) -- FP64 vector work, not HBM or tensor.
+    peak64, peak64_src = peaks_fp64()
+    g = gathered
+    mcount = None
+    roofline = {"bound": "fp64", "kernel": "verify_pairs_kernel (one warp per pair, 32 RANSAC trials per batch)", "unit": "TFLOP/s",
+                "peak": peak64, "peak_source": peak64_src, "traffic": None,
+                "share_of_step": pl["verify_kernel_s"] / max(pl["verify_kernel_s"] + pl["match_kernel_s"], 1e-12),
+                "avg_launch_ms": 1e3 * pl["verify_kernel_s"] / max(a.steps * ((pl["n_pairs"] // world + 16383) // 16384), 1)}
     try:
-        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
-    except Exception:
-        pass
-    peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0
-    peak_src = ("MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
-                if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)")
-    ops_per_pair = 2.0 * a.desc * a.desc * 128
-    achieved = ops_per_pair * n_pairs * a.steps / t_tc / 1e12
-    roofline = {"bound": "tensor", "kernel": "match_top2_ts_kernel (tcgen05 kind::i8, query operand in TMEM)",
-                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                "peak_source": peak_src + "; i8 dense peak is nominally 2x this",
-                "algorithmic_ops_per_pair": ops_per_pair,
-                "avg_launch_ms": 1e3 * t_tc / max(n_tc, 1), "launches": n_tc,
-                "share_of_step": t_tc / t_dev, "traffic": None}
-    # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the committed `ncu --set full` capture
-    # (profiles/r1_match_ts_ncu_full.txt: 4.257 GB + 0.277 GB for a full 8 192-pair launch of 4096 x 4096 images);
-    # only quoted when this run's launches have that shape.  Algorithmic bytes of such a launch: 8192 x 1.1 MB = 9.0 GB
-    # -- the images are shared by many pairs, so L2 serves more than half of them.
-    if a.desc == 4096 and n_tc > 0 and abs(n_pairs * a.steps / n_tc - 8192) < 64:
-        roofline["traffic"] = 4.534e9
-        roofline["traffic_source"] = "profiles/r1_match_ts_ncu_full.txt (bytes per 8192-pair launch)"
+        off = None
+        # matches per pair are not kept by the throughput run: expected count from the scene layout (shared points +
+        # distractors of the overlap), exact enough for a lower bound that is itself a lower bound
+        d = (pairs_all[:, 1].astype(np.int64) - pairs_all[:, 0].astype(np.int64))
+        shared, stride = a.seq_kp // 2, max((a.seq_kp // 2) // a.seq_cand, 1)
+        n_dis = int(a.seq_kp * 0.125)
+        dstride = max(n_dis // a.seq_cand, 1)
+        mexp = np.maximum(shared - d * stride, 0) + np.maximum(n_dis - d * dstride, 0)
+        ef = (g["E_num_trials"].astype(np.float64) + g["F_num_trials"]) * mexp
+        hh = g["H_num_trials"].astype(np.float64) * mexp
+        flops = a.steps * float(33.0 * ef.sum() + 25.0 * hh.sum())
+        roofline.update({"achieved": flops / pl["verify_kernel_s"] / 1e12, "frac": flops / pl["verify_kernel_s"] / 1e12 / peak64,
+                         "algorithmic_flop_per_unit": "33 (E, F Sampson) / 25 (H transfer) per hypothesis x match",
+                         "units_per_step_min": float(ef.sum() + hh.sum()), "mean_matches_per_pair_expected": float(mexp.mean())})
+    except Exception as e:
+        roofline["error"] = repr(e)
 
-    cpu = None
-    if not a.no_cpu:
-        hd = desc.cpu().numpy()
-        v, secs, ns, counts, idx = cpu_reference([hd[i] for i in range(a.images)], pairs, a.cpu_sample, cores)
-        # parity spot check on the sampled pairs: counts must agree with the device result
-        offs = off_dev.cpu().numpy()
-        got = (offs[1:] - offs[:-1])[idx]
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{ns} uniformly sampled pairs of the step, {secs:.1f} s, oracle port of MatchSiftFeaturesCPU",
-               "counts_equal_gpu": bool((got == counts).all())}
-
+    e2e = pl.pop("e2e", None)
     print(json.dumps({
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
-        "warmup": a.warmup, "ms_per_step": 1e3 * t_dev / a.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u8 x u8 -> s32 (exact)", "data": "synthetic",
-        "config": cfg, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "metric": METRIC, "value": pl["value"], "unit": UNIT, "n_gpus": world, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": 1e3 * pl["wall_s"] / a.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64 (verification) / u8 x u8 -> s32 exact (matching)", "data": "synthetic",
+        "config": cfg, "e2e": e2e, "gpu_launches": pl["launches"], "clocks": pl["clocks"],
         "roofline": roofline, "cpu_baseline": cpu,
-        "verify": verify, "ba": ba, **({"guided": guided} if guided is not None else {}),
-        "wall_ms_per_step": 1e3 * wall / a.steps, "matches_per_step": int(total),
-        "fixup_candidates_last_chunk_sum": int(cands),
+        "pipeline": {"pairs_per_step": pl["n_pairs"], "match_kernel_ms_per_step": 1e3 * pl["match_kernel_s"] / a.steps,
+                     "verify_kernel_ms_per_step": 1e3 * pl["verify_kernel_s"] / a.steps,
+                     "timing": "value = pairs / wall time of the K steps between device synchronisations (kernels, chunk "
+                               "hand-over, result gather); *_kernel_ms = CUDA-event time of the two stages on their streams, max over ranks",
+                     **pl.get("results", {})},
+        "match": match, "verify": verify, "ba": ba, **({"guided": guided} if guided is not None else {}),
     }), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -132,7 +132,17 @@ struct Plan {
   int32_t n_tasks;
   int* flags;               // [n_tiles] tile | [nt] inverse | [nt] y | [nt] x | [1] task counter
   double* rdiag;            // [nt][64] 1 / diag(R_ii)
+  unsigned long long* trace;  // optional [n_tasks][4] %globaltimer stamps: picked, dependencies consumed, published, done
 };
+__device__ __forceinline__ void stamp(const Plan& Pn, int t, int k) {
+#ifdef __CUDA_ARCH__
+  if (Pn.trace && threadIdx.x == 0) {
+    unsigned long long v;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(v));
+    Pn.trace[4 * (size_t)t + k] = v;
+  }
+#endif
+}
 
 __global__ void __launch_bounds__(kThreads, 2) solve_graph_kernel(BaTiles T, Plan Pn, double* __restrict__ x) {
   extern __shared__ double chol_smem[];
@@ -156,6 +166,7 @@ __global__ void __launch_bounds__(kThreads, 2) solve_graph_kernel(BaTiles T, Pla
     if (t >= Pn.n_tasks) break;
     const int kind = Pn.task[4 * t], i = Pn.task[4 * t + 1], j = Pn.task[4 * t + 2], tile = Pn.task[4 * t + 3];
     const int d0 = Pn.dep_ptr[t], d1 = Pn.dep_ptr[t + 1];
+    stamp(Pn, t, 0);
     if (kind == TASK_DIAG || kind == TASK_OFF) {
       double* Aij = T.tiles + (size_t)tile * (TS * TS);
       double acc[4][4];
@@ -175,6 +186,7 @@ __global__ void __launch_bounds__(kThreads, 2) solve_graph_kernel(BaTiles T, Pla
         tile_product(sA, tb != ta ? sB : sA, r0, c0, acc);
         __syncthreads();
       }
+      stamp(Pn, t, 1);
       if (kind == TASK_DIAG) {
         // ---- A = U' D^-1 U by elimination on the register blocks; the pivot row travels through shared memory
         bool bad = false;
@@ -224,6 +236,7 @@ __global__ void __launch_bounds__(kThreads, 2) solve_graph_kernel(BaTiles T, Pla
           Pn.rdiag[(size_t)i * TS + tid] = inv;
         }
         publish(f_tile + tile);  // (contains the barrier that orders sv)
+        stamp(Pn, t, 2);
         // ---- off the critical path: Y = R^-T I, stored transposed = R^-1 (upper)
         {
           const int c = tid >> 2, q = tid & 3;
@@ -236,10 +249,12 @@ __global__ void __launch_bounds__(kThreads, 2) solve_graph_kernel(BaTiles T, Pla
           for (int m = 0; m < 16; ++m) Ri[c * TS + 4 * m + q] = a[m];  // Rinv[c][r] = Y[r][c]; zero below the diagonal
         }
         publish(f_inv + i);
+        stamp(Pn, t, 3);
       } else {
         // ---- R_ij = R_ii^-T A_ij
         const int tdiag = T.row_ptr[i];
         wait_flag(f_tile + tdiag);
+        stamp(Pn, t, 2);  // (for an OFF task: the diagonal factor has arrived)
         load_tile(T.tiles + (size_t)tdiag * (TS * TS), sA);
         if (tid < TS) sv[tid] = ld_l2(Pn.rdiag + (size_t)i * TS + tid);
 #pragma unroll
@@ -263,6 +278,7 @@ __global__ void __launch_bounds__(kThreads, 2) solve_graph_kernel(BaTiles T, Pla
           for (int m = 0; m < 8; ++m) g2[tid + kThreads * m] = s2[tid + kThreads * m];
         }
         publish(f_tile + tile);
+        stamp(Pn, t, 3);
       }
       (void)j;
     } else if (kind == TASK_FWD) {
@@ -293,6 +309,7 @@ __global__ void __launch_bounds__(kThreads, 2) solve_graph_kernel(BaTiles T, Pla
       __syncthreads();
       if (tid < TS) x[(size_t)i * TS + tid] = part[0][tid] + part[1][tid] + part[2][tid] + part[3][tid];
       publish(f_y + i);
+      stamp(Pn, t, 3);
     } else {
       // ---- x_i = Rinv_i (y_i - sum_j R_ij x_j): a warp per eight rows, lanes across the columns
       const int lane = tid & 31, w = tid >> 5;
@@ -334,6 +351,7 @@ __global__ void __launch_bounds__(kThreads, 2) solve_graph_kernel(BaTiles T, Pla
       __syncthreads();
       if (tid < TS) x[(size_t)i * TS + tid] = sv[tid];
       publish(f_x + i);
+      stamp(Pn, t, 3);
     }
   }
 }
@@ -387,6 +405,7 @@ cudaError_t bac_solve_system(const BaTiles& T, const BaCholDev& G, double* x, in
   if (e != cudaSuccess) return e;
   bac::Plan Pn;
   Pn.task = G.task; Pn.dep_ptr = G.dep_ptr; Pn.dep = G.dep; Pn.n_tasks = G.n_tasks; Pn.flags = G.flags; Pn.rdiag = G.rdiag;
+  Pn.trace = G.trace;
   const int grid = std::min(G.n_tasks, 2 * std::max(n_sm, 1));
   bac::solve_graph_kernel<<<grid, bac::kThreads, kSmem, s>>>(T, Pn, x);
   return cudaGetLastError();

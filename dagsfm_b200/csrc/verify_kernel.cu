@@ -151,7 +151,7 @@ constexpr int kGroup = 4;
 
 // Inlier decision of one Sampson residual.  NODIV == false is the reference expression
 // `x2tEx1^2 / den <= max_res` (estimators/utils.cc:87-131 + support_measurement.cc:38-41).
-// NODIV == true (experimental, B2_VERIFY_VARIANT=1) decides the same thing without the FP64 divide on the
+// NODIV == true (production) decides the same thing without the FP64 divide on the
 // dependency chain: with q = num / den exact and r = fl(q) correctly rounded, r <= T holds for every
 // q <= T and fails for every q > T (1 + 2^-52); products carry a relative error of 2^-53, so
 // num < fl(T den) (1 - 2^-50) implies q < T and num > fl(T den) (1 + 2^-50) implies q > T (1 + 2^-52).
@@ -171,7 +171,45 @@ __device__ __forceinline__ bool sampson_inlier(const double* E, double2 p1, doub
   return ratio_at_most<NODIV>(num, den, max_res);
 }
 
-template <int TYPE, int G, bool NODIV>
+// Inlier decision of one homography transfer residual (homography_matrix.cc:94-131 + support_measurement.cc:38-41),
+// FAST == true: without the IEEE division on the dependency chain.  With y a reciprocal of pd_2 good to 2^-45 (single
+// precision seed + one Newton step) the residual r~ computed from it differs from the reference's floating-point value
+// r by at most `bound` (every intermediate of either evaluation carries a relative error <= 2^-45 on a magnitude
+// <= |d| + |pd / pd_2|; 2^-43 leaves a factor four), so r~ + bound <= T implies r <= T and r~ - bound > T implies
+// r > T.  Anything in between -- and every input outside the seed's range, NaN, infinity: all comparisons false --
+// is decided by the reference expression itself, so the decision is the reference's in every case.
+template <bool FAST>
+__device__ __forceinline__ bool transfer_inlier(const double* H, double2 s, double2 d, double T) {
+  if (FAST) {
+    const double pd_0 = H[0] * s.x + H[1] * s.y + H[2];
+    const double pd_1 = H[3] * s.x + H[4] * s.y + H[5];
+    const double pd_2 = H[6] * s.x + H[7] * s.y + H[8];
+    const double ap = fabs(pd_2);
+    if (ap > 0x1p-100 && ap < 0x1p100) {
+      const double y0 = (double)__frcp_rn((float)pd_2);
+      const double y = fma(y0, fma(-pd_2, y0, 1.0), y0);
+      const double q0 = pd_0 * y, q1 = pd_1 * y;
+      const double dd_0 = d.x - q0, dd_1 = d.y - q1;
+      const double r = dd_0 * dd_0 + dd_1 * dd_1;
+      const double e0 = (fabs(d.x) + fabs(q0)) * 0x1p-43, e1 = (fabs(d.y) + fabs(q1)) * 0x1p-43;
+      const double bound = 2.5 * (fabs(dd_0) * e0 + fabs(dd_1) * e1) + (e0 * e0 + e1 * e1) + r * 0x1p-48;
+      if (r + bound <= T) return true;
+      if (r - bound > T) return false;
+    }
+  }
+  return transfer(H, s.x, s.y, d.x, d.y) <= T;
+}
+template <int TYPE, bool FAST>
+__device__ __forceinline__ bool is_inlier(const double* M, double2 a, double2 b, double max_res) {
+  if (TYPE == EST_H4) return transfer_inlier<FAST>(M, a, b, max_res);
+  if (TYPE == EST_T2) return translation_res(M, a.x, a.y, b.x, b.y) <= max_res;
+  return sampson_inlier<FAST>(M, a, b, max_res);
+}
+
+// FAST: division-free decisions (identical results, see sampson_inlier / transfer_inlier); !FAST: the reference's
+// residual expressions as written (B2_VERIFY_VARIANT=1, kept for the A/B and as the executable statement of parity).
+// Counts are kept per lane and reduced once per group: no warp-wide exchange inside the loop over the matches.
+template <int TYPE, int G, bool FAST>
 __device__ __noinline__ void score_group(const double2* __restrict__ P1, const double2* __restrict__ P2, int M,
                                          const double* __restrict__ models, const uint16_t* ids, int n, double max_res,
                                          int lane, int* cnt_out) {
@@ -186,17 +224,16 @@ __device__ __noinline__ void score_group(const double2* __restrict__ P1, const d
   int c[G];
 #pragma unroll
   for (int u = 0; u < G; ++u) c[u] = 0;
-  for (int i0 = 0; i0 < M; i0 += 32) {
-    const int i = i0 + lane;
-    const bool ok = i < M;
-    const double2 a = P1[ok ? i : 0], b = P2[ok ? i : 0];
+#pragma unroll 2
+  for (int i = lane; i < M; i += 32) {
+    const double2 a = P1[i], b = P2[i];
 #pragma unroll
-    for (int u = 0; u < G; ++u) {
-      bool in;
-      if (NODIV) in = ok && sampson_inlier<true>(m[u], a, b, max_res);
-      else in = ok && residual_t<TYPE>(m[u], a, b) <= max_res;
-      c[u] += __popc(__ballot_sync(kFull, in));
-    }
+    for (int u = 0; u < G; ++u) c[u] += is_inlier<TYPE, FAST>(m[u], a, b, max_res) ? 1 : 0;
+  }
+#pragma unroll
+  for (int u = 0; u < G; ++u) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c[u] += __shfl_xor_sync(kFull, c[u], o);
   }
   if (lane == 0) {
 #pragma unroll
@@ -205,20 +242,20 @@ __device__ __noinline__ void score_group(const double2* __restrict__ P1, const d
   }
   __syncwarp();
 }
-// VAR == 0: production (groups of four, reference residual expression).  VAR == 1: groups of eight and the
-// division-free Sampson decision (H and the translation model keep their expressions).
+// VAR == 0: production (division-free decisions).  VAR == 1: the reference's residual expressions.
 template <int VAR>
 __device__ __forceinline__ void score_group_any(int type, const double2* P1, const double2* P2, int M,
                                                 const double* models, const uint16_t* ids, int n, double max_res,
                                                 int lane, int* cnt_out) {
-  constexpr int G = VAR ? 8 : kGroup;
-  if (type == EST_H4) score_group<EST_H4, G, false>(P1, P2, M, models, ids, n, max_res, lane, cnt_out);
+  constexpr int G = kGroup;
+  constexpr bool FAST = VAR == 0;
+  if (type == EST_H4) score_group<EST_H4, G, FAST>(P1, P2, M, models, ids, n, max_res, lane, cnt_out);
   else if (type == EST_T2) score_group<EST_T2, G, false>(P1, P2, M, models, ids, n, max_res, lane, cnt_out);
-  else score_group<EST_F7, G, VAR != 0>(P1, P2, M, models, ids, n, max_res, lane, cnt_out);
+  else score_group<EST_F7, G, FAST>(P1, P2, M, models, ids, n, max_res, lane, cnt_out);
 }
 
 // InlierSupportMeasurer::Evaluate, count only (all lanes return the same value).
-__device__ int score_count(int type, const double2* P1, const double2* P2, int M, const double* model, double max_res,
+__device__ __noinline__ int score_count(int type, const double2* P1, const double2* P2, int M, const double* model, double max_res,
                            int lane) {
   int cnt = 0;
   for (int i0 = 0; i0 < M; i0 += 32) {
@@ -231,7 +268,7 @@ __device__ int score_count(int type, const double2* P1, const double2* P2, int M
 }
 // ... and its residual_sum: a sequential FP64 sum in index order (support_measurement.cc:43-46);
 // optionally writes the inlier mask.  Needed only on ties and for a new best.
-__device__ double score_sum(int type, const double2* P1, const double2* P2, int M, const double* model, double max_res,
+__device__ __noinline__ double score_sum(int type, const double2* P1, const double2* P2, int M, const double* model, double max_res,
                             int lane, uint8_t* mask_out) {
   double sum = 0;
   for (int i0 = 0; i0 < M; i0 += 32) {
@@ -282,7 +319,7 @@ __device__ inline unsigned long long compute_num_trials(unsigned long long num_i
 // G: rows x 9, column-major (G[c * ld + r]) in global scratch; V (9x9 row-major) in shared.
 // One-sided Jacobi; lanes split the rows.  On return V's columns are sorted by descending
 // singular value (sig in shared too).
-__device__ void warp_jacobi9(double* G, int rows, int ld, double* V, double* sig, int lane) {
+__device__ __noinline__ void warp_jacobi9(double* G, int rows, int ld, double* V, double* sig, int lane) {
   for (int i = lane; i < 81; i += 32) V[i] = (i / 9 == i % 9) ? 1.0 : 0.0;
   __syncwarp();
   double frob2 = 0;
@@ -363,7 +400,7 @@ __device__ void warp_jacobi9(double* G, int rows, int ld, double* V, double* sig
 // singular vectors, so the Jacobi sweeps then run on 81 shared doubles instead of streaming the
 // rows x 9 matrix through L2 36 times per sweep (oracle: householder_r; Eigen::JacobiSVD
 // preconditions tall input with a QR too).  rows > 9.
-__device__ void warp_qr9(double* G, int rows, int ld, double* R, int lane) {
+__device__ __noinline__ void warp_qr9(double* G, int rows, int ld, double* R, int lane) {
   for (int i = lane; i < 81; i += 32) R[i] = 0.0;
   __syncwarp();
   for (int k = 0; k < 9; ++k) {
@@ -464,7 +501,7 @@ __device__ __forceinline__ double2 apply_T(const double* T, double2 p) {
 
 // Local estimator on the N inliers listed in inl[]; writes models (<= 10 x 9) to `models`
 // (global scratch, visible to all lanes) and returns the count (uniform).
-__device__ int local_estimate(int type, const double2* P1, const double2* P2, const uint32_t* inl, int N, double* G,
+__device__ __noinline__ int local_estimate(int type, const double2* P1, const double2* P2, const uint32_t* inl, int N, double* G,
                               int ld, WarpShared& sh, double* sig_sh, double* models, int lane) {
   if (type == EST_T2) {  // translation_transform.h:84-102: mean_dst - mean_src, sums in index order
     if (lane == 0) {
@@ -563,7 +600,7 @@ struct Scratch {
 
 // LORANSAC::Estimate for one estimator over the matched points (P1,P2)[0..M).
 template <int VAR>
-__device__ void ransac_warp(int type, const double2* P1, const double2* P2, int M, double max_error,
+__device__ __noinline__ void ransac_warp(int type, const double2* P1, const double2* P2, int M, double max_error,
                             double min_inlier_ratio, double confidence, long long min_num_trials,
                             long long max_num_trials_opt, WarpShared& sh, double* sig_sh, const Scratch& sc,
                             uint8_t* mask_out, RansacResult* out, int lane, LaneView ws) {
@@ -666,7 +703,7 @@ __device__ void ransac_warp(int type, const double2* P1, const double2* P2, int 
       }
       if ((j & 7) == 0) {  // support counts of the next eight trials' hypotheses
         const int g1 = sh.off[min(j + 8, 32)];
-        constexpr int GS = VAR ? 8 : kGroup;
+        constexpr int GS = kGroup;
         for (int g = sh.off[j]; g < g1; g += GS)
           score_group_any<VAR>(type, P1, P2, M, sc.models, sh.flat + g, min(GS, g1 - g), max_residual, lane, sh.cnt);
       }
@@ -701,7 +738,7 @@ __device__ void ransac_warp(int type, const double2* P1, const double2* P2, int 
             const long long cl0 = clock64();
             const int nlm = local_estimate(type, P1, P2, sc.inl, N, sc.G, sc.ld, sh, sig_sh, sc.lomodels, lane);
             lo_cycles += clock64() - cl0;
-            constexpr int GL = VAR ? 8 : kGroup;
+            constexpr int GL = kGroup;
             for (int g = 0; g < nlm; g += GL)
               score_group_any<VAR>(type, P1, P2, M, sc.lomodels, sh.lo_ids + g, min(GL, nlm - g), max_residual, lane,
                               sh.lo_cnt);
@@ -1024,6 +1061,22 @@ __global__ void score_models_kernel(int type, int n, const double2* P1, const do
   }
 }
 
+// Test seam of the division-free inlier decisions: both decisions of every point for one model.
+__global__ void debug_decisions_kernel(int type, int n, const double2* P1, const double2* P2, const double* model,
+                                       double max_res, uint8_t* fast, uint8_t* ref) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double m[9];
+  for (int k = 0; k < 9; ++k) m[k] = model[k];
+  if (type == EST_H4) {
+    fast[i] = is_inlier<EST_H4, true>(m, P1[i], P2[i], max_res);
+    ref[i] = residual_t<EST_H4>(m, P1[i], P2[i]) <= max_res;
+  } else {
+    fast[i] = is_inlier<EST_F7, true>(m, P1[i], P2[i], max_res);
+    ref[i] = residual_t<EST_F7>(m, P1[i], P2[i]) <= max_res;
+  }
+}
+
 __global__ void debug_sample_stream_kernel(uint32_t seed, int total, int k, int n_trials, uint32_t* idx, int* out) {
   __shared__ WarpShared sh;
   if (threadIdx.x == 0) {
@@ -1097,7 +1150,7 @@ cudaError_t launch_normalize_points(const b2_camera* cams, const int64_t* img_of
 }
 cudaError_t launch_verify_pairs(const VerifyArgs& a, int n_blocks, cudaStream_t s) {
   const size_t dyn = vf::kDynSmemBytes;
-  // B2_VERIFY_VARIANT=1 selects the experimental instance (groups of eight hypotheses, division-free
+  // B2_VERIFY_VARIANT=1 selects the instance that evaluates the reference's residual expressions as written (A/B of the division-free
   // Sampson decision); the default instance is the measured production kernel
   const char* venv = getenv("B2_VERIFY_VARIANT");
   const int variant = venv ? atoi(venv) : 0;
@@ -1117,6 +1170,12 @@ cudaError_t launch_score_models(int type, int n, const double* p1, const double*
   if (n_models == 0) return cudaSuccess;
   vf::score_models_kernel<<<(n_models + 3) / 4, 128, 0, s>>>(type, n, (const double2*)p1, (const double2*)p2, n_models,
                                                               models, max_res, counts, sums, masks);
+  return cudaGetLastError();
+}
+cudaError_t launch_debug_decisions(int type, int n, const double* p1, const double* p2, const double* model, double max_res,
+                                   uint8_t* fast, uint8_t* ref, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  vf::debug_decisions_kernel<<<(n + 127) / 128, 128, 0, s>>>(type, n, (const double2*)p1, (const double2*)p2, model, max_res, fast, ref);
   return cudaGetLastError();
 }
 cudaError_t launch_debug_sample_stream(uint32_t seed, int total, int k, int n_trials, uint32_t* idx, int* out,

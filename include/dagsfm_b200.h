@@ -276,6 +276,11 @@ int b2_verify_relative_pose_device(b2_verifier* v, int64_t n_pairs, const uint32
 int b2_score_models(b2_verifier* v, int32_t type, int32_t n, const double* xy1, const double* xy2,
                     int32_t n_models, const double* models, double max_residual,
                     int32_t* counts, double* sums, uint8_t* masks);
+/* Test hook: the two inlier decisions of every point for one model (type 0/1 Sampson, 2 homography transfer):
+ * fast[i] = the production kernel's division-free decision, ref[i] = `residual <= max_residual` with the reference's
+ * residual expression (src/estimators/utils.cc:87-131, homography_matrix.cc:94-131).  They must be equal for every input. */
+int b2_verify_debug_decisions(b2_verifier* v, int32_t type, int32_t n, const double* xy1, const double* xy2,
+                              const double* model, double max_residual, uint8_t* fast, uint8_t* ref);
 /* Test hook: the sampler's index stream (RandomSampler over std::mt19937(seed)), n_trials x k. */
 int b2_verify_debug_sample_stream(b2_verifier* v, uint32_t seed, int32_t total, int32_t k,
                                   int32_t n_trials, int32_t* out);

@@ -92,3 +92,43 @@ def test_device_resident_match_then_verify_equals_host_path_and_oracle():
         assert inl_h[off_h[k]:off_h[k] + r.n_inliers].tolist() == oi.tolist()
         cfgs.add(int(g["config"]))
     assert cfgs & {3, 4, 6}     # UNCALIBRATED and planar configurations both occur
+
+
+def test_sift_feature_matcher_match_equals_the_oracle_chain_and_keeps_the_reference_semantics():
+    """SiftFeatureMatcher.Match on a synthetic image sequence (dagsfm_b200.synthetic): every written pair equals the
+    oracle's MatchSiftFeaturesCPU -> TwoViewGeometry::Estimate on the same seeds; duplicates / self-pairs / existing
+    results are handled as matching.cc:763-808 does; short lists are written empty (:823-833)."""
+    from dagsfm_b200 import SiftMatchingOptions, TwoViewOptions
+    from dagsfm_b200.pipeline import MatchCache, SiftFeatureMatcher, cameras_of
+    from dagsfm_b200.synthetic import candidate_pairs, make_image_collection
+    w = make_image_collection(10, 768, seed=3, device="cuda", overlap_images=6)
+    d = w["desc"].cpu().numpy()
+    pairs = candidate_pairs(10, 7)
+    fm = SiftFeatureMatcher(SiftMatchingOptions(), TwoViewOptions.default(), 0, chunk_pairs=16)
+    try:
+        fm.Setup([d[i] for i in range(10)], list(w["keypoints"]), cameras_of(w))
+        cache = MatchCache()
+        noisy = [(int(a), int(b)) for a, b in pairs] + [(4, 4), (int(pairs[0][1]), int(pairs[0][0]))]
+        n_out = fm.Match(noisy, cache)
+        assert n_out == len(pairs) == len(cache.matches) == len(cache.two_view)
+        vo = TwoViewOptions.default()
+        for k, (a, b) in enumerate(pairs):
+            a, b = int(a), int(b)
+            em = orc.match_sift(d[a], d[b])
+            got = cache.GetMatches(a, b)
+            assert got.tolist() == (em.tolist() if len(em) >= vo.min_num_inliers else [])
+            ca, cb = (orc.make_camera(params=w["cam_params"], prior=bool(w["prior"][i])) for i in (a, b))
+            with orc.solver_stack(1):
+                r, oi = orc.two_view(ca, w["keypoints"][a], cb, w["keypoints"][b], em, seed=k)
+            g = cache.two_view[next(iter([p for p in cache.two_view if p == 2147483647 * a + b]))]
+            if r.n_inliers >= vo.min_num_inliers:
+                assert g.config == r.config and g.inlier_matches.tolist() == oi.tolist()
+            else:
+                assert g.config == 0 and len(g.inlier_matches) == 0
+        # a second call over the same list does nothing; with the geometry of one pair removed only that pair is redone
+        assert fm.Match(noisy, cache) == 0
+        a, b = int(pairs[1][0]), int(pairs[1][1])
+        cache.DeleteInlierMatches(a, b)
+        assert fm.Match(noisy, cache) == 1 and cache.ExistsInlierMatches(a, b)
+    finally:
+        fm.close()
