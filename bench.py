@@ -193,7 +193,7 @@ def bench_verify(a, local_rank, rank, world, cores, barrier):
     """Two-view verification throughput: b2_verify_pairs (host buffers in / out) on synthetic
     matched pairs; CPU baseline = oracle port of TwoViewGeometry::Estimate, `cores` workers."""
     from dagsfm_b200 import Camera, TwoViewGeometryVerifier, TwoViewOptions
-    from tests.tv_scene import make_pairs
+    from dagsfm_b200.tv_scene import make_pairs
     w = make_pairs(a.verify_pairs, seed=7 + rank)
     n = len(w["pairs"])
     cams = [Camera.make(params=w["cam_params"], prior_focal=bool(p)) for p in w["prior"]]
@@ -331,7 +331,7 @@ def bench_guided(a, local_rank, rank, world, cores, barrier):
 
 def _mean_reproj(prob):
     try:
-        from tests.ba_scene import mean_reprojection_error
+        from dagsfm_b200.ba_scene import mean_reprojection_error
         return mean_reprojection_error(prob)
     except Exception:
         return None
@@ -341,7 +341,7 @@ def bench_ba(a, local_rank, rank, world, cores, barrier, hbm):
     """Final-BA leg (BASELINE configs[3]): LM iterations per second of b2_ba_solve and the HBM
     roofline of the Jacobian+Schur kernels; CPU baseline = the reference's vendored PBA."""
     from dagsfm_b200 import BundleAdjuster, BundleAdjustmentOptions
-    from tests.ba_scene import copy_problem, make_ba_problem, reprojection_rms
+    from dagsfm_b200.ba_scene import copy_problem, make_ba_problem, reprojection_rms
     n_img, n_pts, track = (int(x) for x in a.ba.split(","))
     prob0 = make_ba_problem(n_img=n_img, n_pts=n_pts, track_len=track, seed=1)
     n_obs = len(prob0["obs_img"])
@@ -354,7 +354,10 @@ def bench_ba(a, local_rank, rank, world, cores, barrier, hbm):
         import torch
         from dagsfm_b200.parallel import make_torch_allreduce, shard_ba_problem
         prob0, _ids = shard_ba_problem(full0, rank, world)
-        ba.set_allreduce(make_torch_allreduce(torch.device("cuda", local_rank)))
+        if os.environ.get("B2_BENCH_BA_HOOK") == "torch":     # A/B: the caller-supplied hook (host callback per all-reduce)
+            ba.set_allreduce(make_torch_allreduce(torch.device("cuda", local_rank)))
+        else:                                                  # the library's own communicator: ncclAllReduce on the solver stream
+            ba.init_nccl_from_torch()
     prob = copy_problem(prob0)
     ba.Solve(prob)                                    # warm-up (cuSOLVER workspace, clocks)
     prob = copy_problem(prob0)
@@ -377,7 +380,7 @@ def bench_ba(a, local_rank, rank, world, cores, barrier, hbm):
            "rms_px_initial": reprojection_rms(prob0), "rms_px_final": reprojection_rms(prob),
            "mean_reproj_error_px_final": _mean_reproj(prob),
            "rms_note": "this rank's point shard" if world > 1 else "all observations",
-           "sharding": f"points over {world} ranks, 1 all-reduce of the reduced camera system per LM iteration" if world > 1 else "single GPU",
+           "sharding": f"points over {world} ranks, 1 ncclAllReduce (library-owned communicator, solver stream) of the packed reduced camera system per LM iteration" if world > 1 else "single GPU",
            "ceres_style_px": float(np.sqrt(s.final_cost / (2 * n_obs))),
            "roofline": {"bound": "hbm", "kernel": "camera_terms_kernel + schur_points_kernel + schur_window_kernel (Jacobian + Schur complement)", "achieved": achieved,
                         "peak": hbm[0], "unit": "GB/s", "frac": achieved / hbm[0], "peak_source": hbm[1],

@@ -70,9 +70,32 @@ def _L():
         L.b2_ba_set_allreduce.argtypes = [vp, ALLREDUCE_FN, vp]
         L.b2_ba_solve.argtypes = [vp, P(BaProblem), P(BundleAdjustmentOptions), P(BaSummary)]
         L.b2_ba_reprojection_errors.argtypes = [vp, P(BaProblem), vp, P(C.c_double)]
+        L.b2_nccl_unique_id.argtypes = [vp]
+        L.b2_ba_init_nccl.argtypes = [vp, C.c_int32, C.c_int32, vp]
         L.b2_ba_debug_cholesky_solve.argtypes = [vp, C.c_int64, vp, vp, vp, P(C.c_int32), P(C.c_int32)]
         _bound = True
     return L
+
+
+def _nccl_library_hint() -> None:
+    """Every rank must bind the same NCCL: prefer the one torch ships (site-packages/nvidia/nccl) over the system's."""
+    import os
+    if "B2_NCCL_LIBRARY" not in os.environ:
+        try:
+            import nvidia.nccl
+            p = os.path.join(os.path.dirname(nvidia.nccl.__file__), "lib", "libnccl.so.2")
+            if os.path.exists(p):
+                os.environ["B2_NCCL_LIBRARY"] = p
+        except Exception:
+            pass
+
+
+def nccl_unique_id() -> bytes:
+    """b2_nccl_unique_id: 128 bytes for rank 0 to hand to the other ranks."""
+    _nccl_library_hint()
+    buf = (C.c_uint8 * 128)()
+    check(_L().b2_nccl_unique_id(C.cast(buf, C.c_void_p)))
+    return bytes(buf)
 
 
 _KEYS = (("qvec", np.float64), ("tvec", np.float64), ("img_cam", np.int32), ("pose_const", np.uint8),
@@ -107,6 +130,25 @@ class BundleAdjuster:
         ranks (op 0 SUM, 1 MAX) -- e.g. torch.distributed over NCCL."""
         self._cb = ALLREDUCE_FN(lambda ptr, n, op, user: fn(ptr, n, op)) if fn else ALLREDUCE_FN(0)
         check(_L().b2_ba_set_allreduce(self._h, self._cb, None))
+
+    def init_nccl(self, rank: int, world: int, unique_id: bytes) -> None:
+        """The library's own NCCL communicator (b2_ba_init_nccl); unique_id: the 128 bytes rank 0 got from nccl_unique_id()."""
+        assert len(unique_id) == 128
+        _nccl_library_hint()
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        check(_L().b2_ba_init_nccl(self._h, world, rank, C.cast(buf, C.c_void_p)))
+
+    def init_nccl_from_torch(self) -> None:
+        """Convenience for torchrun-style launches: the id travels over the existing torch.distributed group."""
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(), dist.get_world_size()
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+        t = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            t.copy_(torch.frombuffer(bytearray(nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(t, 0)
+        self.init_nccl(rank, world, bytes(t.cpu().numpy().tobytes()))
 
     def ComputeMeanReprojectionError(self, prob: dict):
         """Reconstruction::ComputeMeanReprojectionError over the problem's tracks -> (mean error in px, per-point errors

@@ -14,6 +14,8 @@
 #include <cuda_runtime.h>
 #include <cusolverDn.h>
 
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -39,6 +41,7 @@ struct b2_ba {
   cusolverDnParams_t solver_params = nullptr;
   b2_allreduce_fn allreduce = nullptr;
   void* allreduce_user = nullptr;
+  void* nccl_comm = nullptr;   // b2_ba_init_nccl: the library's own communicator (takes precedence over the hook)
   std::vector<void*> allocs;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
@@ -75,8 +78,57 @@ void free_all(b2_ba* h) {
   h->allocs.clear();
 }
 
+// ---- NCCL, bound at run time: libnccl.so.2 as the process already holds it (e.g. the one torch brought) or the path in
+// B2_NCCL_LIBRARY.  Only the five entry points the bundle adjuster needs; enum values of nccl.h 2.x.
+namespace nccl {
+struct UniqueId { char internal[128]; };
+typedef void* Comm;
+struct Api {
+  void* lib = nullptr;
+  int (*GetUniqueId)(UniqueId*) = nullptr;
+  int (*CommInitRank)(Comm*, int, UniqueId, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, Comm, cudaStream_t) = nullptr;
+  int (*CommDestroy)(Comm) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+constexpr int kFloat64 = 8, kSum = 0, kMax = 2;
+Api* api() {
+  static Api a;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    const char* names[3] = {getenv("B2_NCCL_LIBRARY"), "libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+      if (!n || !*n) continue;
+      if ((a.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
+    }
+    if (a.lib) {
+      a.GetUniqueId = (int (*)(UniqueId*))dlsym(a.lib, "ncclGetUniqueId");
+      a.CommInitRank = (int (*)(Comm*, int, UniqueId, int))dlsym(a.lib, "ncclCommInitRank");
+      a.AllReduce = (int (*)(const void*, void*, size_t, int, int, Comm, cudaStream_t))dlsym(a.lib, "ncclAllReduce");
+      a.CommDestroy = (int (*)(Comm))dlsym(a.lib, "ncclCommDestroy");
+      a.GetErrorString = (const char* (*)(int))dlsym(a.lib, "ncclGetErrorString");
+      if (!a.GetUniqueId || !a.CommInitRank || !a.AllReduce || !a.CommDestroy) a.lib = nullptr;
+    }
+  }
+  return a.lib ? &a : nullptr;
+}
+}  // namespace nccl
+
+inline bool distributed(const b2_ba* h) { return h->nccl_comm != nullptr || h->allreduce != nullptr; }
+
+// In-place reduction of a device buffer across the ranks.  With the library's own communicator this is one ncclAllReduce
+// on the solver's stream -- no host synchronisation, the next kernel is simply ordered behind it; the caller-supplied
+// hook (b2_ba_set_allreduce) is a host call and needs the stream drained first.
 int sync_reduce(b2_ba* h, double* buf, int64_t n, int op) {
-  if (!h->allreduce || n == 0) return B2_OK;
+  if (n == 0) return B2_OK;
+  if (h->nccl_comm) {
+    nccl::Api* a = nccl::api();
+    const int rc = a->AllReduce(buf, buf, (size_t)n, nccl::kFloat64, op == 1 ? nccl::kMax : nccl::kSum, h->nccl_comm, h->stream);
+    if (rc != 0) return set_error(B2_ERR_CUDA, a->GetErrorString ? a->GetErrorString(rc) : "ncclAllReduce failed");
+    return B2_OK;
+  }
+  if (!h->allreduce) return B2_OK;
   B2_CUDA(cudaStreamSynchronize(h->stream));
   h->allreduce(buf, n, op, h->allreduce_user);
   return B2_OK;
@@ -348,7 +400,7 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
   // In a multi-GPU run every rank sees all images / cameras of the job, so `used` must be
   // the union: a rank marks everything that is not explicitly constant as used when a
   // collective hook is installed.
-  std::vector<char> img_used(n_img, h->allreduce ? 1 : 0), cam_used(n_cam, h->allreduce ? 1 : 0), pt_used(n_pts, 0);
+  std::vector<char> img_used(n_img, distributed(h) ? 1 : 0), cam_used(n_cam, distributed(h) ? 1 : 0), pt_used(n_pts, 0);
   for (int64_t o = 0; o < n_obs; ++o) {
     img_used[pr->obs_image[o]] = 1;
     cam_used[pr->image_camera[pr->obs_image[o]]] = 1;
@@ -390,7 +442,7 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
   bool fused = !iterative && !wide && n_obs > 0 && n_obs < 0x7fffffffLL && D > 0;
   if (const char* e = getenv("B2_BA_EXACT")) fused = fused && strcmp(e, "staged") != 0;
   if (fused) fused = plan_windows(pr, pt_start, pt_col, &plan);
-  if (h->allreduce) {  // every rank must take the same path: MIN over the ranks of the local decision
+  if (distributed(h)) {  // every rank must take the same path: MIN over the ranks of the local decision
     double* d_flag = nullptr;
     B2_TRY(dev_alloc(h, &d_flag, 1));
     const double mine = fused ? 0.0 : 1.0;
@@ -403,7 +455,7 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
   }
   if (fused) {
     plan_tile_map(pr, pose_col, intr_col, D, &plan);
-    if (h->allreduce) {  // union of the ranks' tile patterns (each rank sees its own points only)
+    if (distributed(h)) {  // union of the ranks' tile patterns (each rank sees its own points only)
       std::vector<double> m(plan.tmap.begin(), plan.tmap.end());
       double* d_m = nullptr;
       B2_TRY(dev_upload(h, &d_m, (const double*)m.data(), m.size()));
@@ -609,7 +661,7 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
     B2_TRY(dev_alloc(h, &V.tmp, (size_t)D));
     B2_TRY(dev_alloc(h, &V.partial, (size_t)2 * kBaIterMaxPartials));
   }
-  if (n_obs == 0 && !h->allreduce) return B2_OK;  // BundleAdjuster::Solve returns false: nothing to do
+  if (n_obs == 0 && !distributed(h)) return B2_OK;  // BundleAdjuster::Solve returns false: nothing to do
 
   // ---------------------------------------------------------------- Jacobi scaling + initial cost
   B2_CUDA(cudaMemsetAsync(P.colnorm_c, 0, std::max<size_t>(D, 1) * 8, s));
@@ -947,10 +999,37 @@ int b2_ba_create(int device, b2_ba** out) {
   return B2_OK;
 }
 
+int b2_nccl_unique_id(uint8_t* out128) {
+  if (!out128) return set_error(B2_ERR_INVALID, "NULL argument");
+  nccl::Api* a = nccl::api();
+  if (!a) return set_error(B2_ERR_INVALID, "libnccl.so.2 not found (set B2_NCCL_LIBRARY)");
+  nccl::UniqueId id;
+  const int rc = a->GetUniqueId(&id);
+  if (rc != 0) return set_error(B2_ERR_CUDA, a->GetErrorString ? a->GetErrorString(rc) : "ncclGetUniqueId failed");
+  memcpy(out128, id.internal, 128);
+  return B2_OK;
+}
+
+int b2_ba_init_nccl(b2_ba* h, int32_t n_ranks, int32_t rank, const uint8_t* id128) {
+  if (!h || !id128 || n_ranks < 1 || rank < 0 || rank >= n_ranks) return set_error(B2_ERR_INVALID, "bad argument");
+  nccl::Api* a = nccl::api();
+  if (!a) return set_error(B2_ERR_INVALID, "libnccl.so.2 not found (set B2_NCCL_LIBRARY)");
+  B2_CUDA(cudaSetDevice(h->device));
+  if (h->nccl_comm) { a->CommDestroy(h->nccl_comm); h->nccl_comm = nullptr; }
+  nccl::UniqueId id;
+  memcpy(id.internal, id128, 128);
+  nccl::Comm c = nullptr;
+  const int rc = a->CommInitRank(&c, n_ranks, id, rank);
+  if (rc != 0) return set_error(B2_ERR_CUDA, a->GetErrorString ? a->GetErrorString(rc) : "ncclCommInitRank failed");
+  h->nccl_comm = c;
+  return B2_OK;
+}
+
 int b2_ba_destroy(b2_ba* h) {
   if (!h) return B2_OK;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->nccl_comm) { if (nccl::Api* a = nccl::api()) a->CommDestroy(h->nccl_comm); h->nccl_comm = nullptr; }
   free_all(h);
   if (h->solver_params) cusolverDnDestroyParams(h->solver_params);
   if (h->solver) cusolverDnDestroy(h->solver);

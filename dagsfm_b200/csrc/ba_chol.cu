@@ -125,6 +125,20 @@ __device__ __forceinline__ void quad_trsm(const double* __restrict__ sR, const d
   }
 }
 
+// 1 / d to <= 1 ulp without the IEEE division's dependent chain (d a positive pivot of Jacobi-scaled normal equations;
+// anything outside the single-precision seed's range takes the division)
+__device__ __forceinline__ double fast_rcp(double d) {
+#ifdef __CUDA_ARCH__
+  if (d > 0x1p-100 && d < 0x1p100) {
+    double y = (double)__frcp_rn((float)d);
+    y = fma(y, fma(-d, y, 1.0), y);
+    y = fma(y, fma(-d, y, 1.0), y);
+    return y;
+  }
+#endif
+  return 1.0 / d;
+}
+
 struct Plan {
   const int32_t* task;      // [n_tasks][4]: kind, i, j (OFF), target tile / -1
   const int32_t* dep_ptr;   // [n_tasks + 1]
@@ -148,7 +162,8 @@ __global__ void __launch_bounds__(kThreads, 2) solve_graph_kernel(BaTiles T, Pla
   extern __shared__ double chol_smem[];
   double* sA = chol_smem;            // 64 x 64
   double* sB = chol_smem + TS * TS;  // 64 x 64
-  __shared__ double urow[2][TS];
+  __shared__ __align__(16) double ublk[2][4][TS];
+  __shared__ double dblk[2][20];
   __shared__ double sd[TS], sv[TS], part[4][TS];
   __shared__ int s_task;
   const int tid = threadIdx.x;
@@ -188,43 +203,83 @@ __global__ void __launch_bounds__(kThreads, 2) solve_graph_kernel(BaTiles T, Pla
       }
       stamp(Pn, t, 1);
       if (kind == TASK_DIAG) {
-        // ---- A = U' D^-1 U by elimination on the register blocks; the pivot row travels through shared memory
+        // ---- A = U' D^-1 U by blocked elimination on the register blocks, four pivots per block barrier: the thread that
+        // holds the 4 x 4 diagonal block eliminates it and hands its multipliers to the 15 threads holding the rest of
+        // the four pivot rows (same warp: a warp barrier), they finish their rows, and the whole CTA applies the four
+        // rank-1 updates at once.  The pivots' reciprocals come from a single-precision seed + two Newton steps (<= 1
+        // ulp): the IEEE division is ~200 cycles of dependent instructions, 64 times on this kernel's critical path.
         bool bad = false;
-        for (int c = 0; c < TS; ++c) {
-          double* u = urow[c & 1];
-          if (tr == (c >> 2)) {
-            const int a = c & 3;
+#pragma unroll 1
+        for (int p = 0; p < 16; ++p) {
+          double (*ub)[TS] = ublk[p & 1];
+          double* db = dblk[p & 1];  // [0, 16): the eliminated diagonal block, row-major; [16, 20): 1 / pivot
+          if ((tr >> 1) == (p >> 1)) {  // the warp that holds block row p (two block rows per warp)
+            if (tr == p && tc == p) {
 #pragma unroll
-            for (int b = 0; b < 4; ++b) u[c0 + b] = (a == 0) ? acc[0][b] : (a == 1) ? acc[1][b] : (a == 2) ? acc[2][b] : acc[3][b];
+              for (int a = 0; a < 4; ++a) {
+                double d = acc[a][a];
+                if (!(d > 0.0)) { bad = true; d = 1.0; acc[a][a] = 1.0; }
+                const double inv = fast_rcp(d);
+                db[16 + a] = inv;
+                sd[4 * p + a] = d;
+#pragma unroll
+                for (int a2 = a + 1; a2 < 4; ++a2) {
+                  const double m = acc[a][a2] * inv;
+#pragma unroll
+                  for (int b2 = a2; b2 < 4; ++b2) acc[a2][b2] = fma(-m, acc[a][b2], acc[a2][b2]);
+                }
+              }
+#pragma unroll
+              for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b2 = 0; b2 < 4; ++b2) db[4 * a + b2] = acc[a][b2];
+            }
+            __syncwarp();
+            if (tr == p && tc > p) {
+#pragma unroll
+              for (int a = 0; a < 3; ++a) {
+                const double inv = db[16 + a];
+#pragma unroll
+                for (int a2 = a + 1; a2 < 4; ++a2) {
+                  const double m = db[4 * a + a2] * inv;
+#pragma unroll
+                  for (int b2 = 0; b2 < 4; ++b2) acc[a2][b2] = fma(-m, acc[a][b2], acc[a2][b2]);
+                }
+              }
+            }
+            if (tr == p) {
+#pragma unroll
+              for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b2 = 0; b2 < 4; ++b2) ub[a][c0 + b2] = acc[a][b2];
+            }
           }
           __syncthreads();
-          double dpiv = u[c];
-          if (!(dpiv > 0.0)) { bad = true; dpiv = 1.0; }
-          if (tid == 0) sd[c] = dpiv;
-          if (r0 + 3 > c) {
-            const double inv = 1.0 / dpiv;
-            const double ub[4] = {u[c0], u[c0 + 1], u[c0 + 2], u[c0 + 3]};
+          if (tr > p) {
 #pragma unroll
-            for (int a = 0; a < 4; ++a) {
-              if (r0 + a > c) {
-                const double m = u[r0 + a] * inv;
+            for (int k = 0; k < 4; ++k) {
+              const double inv = db[16 + k];
+              const double2 r01 = *reinterpret_cast<const double2*>(&ub[k][r0]), r23 = *reinterpret_cast<const double2*>(&ub[k][r0 + 2]);
+              const double2 c01 = *reinterpret_cast<const double2*>(&ub[k][c0]), c23 = *reinterpret_cast<const double2*>(&ub[k][c0 + 2]);
+              const double mr[4] = {r01.x * inv, r01.y * inv, r23.x * inv, r23.y * inv}, uc[4] = {c01.x, c01.y, c23.x, c23.y};
 #pragma unroll
-                for (int b = 0; b < 4; ++b) acc[a][b] = fma(-m, ub[b], acc[a][b]);
-              }
+              for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b2 = 0; b2 < 4; ++b2) acc[a][b2] = fma(-mr[a], uc[b2], acc[a][b2]);
             }
           }
         }
         __syncthreads();
-        if (bad && tid == 0) *T.info = 1;
+        if (bad) *T.info = 1;
         // R = D^-1/2 U; the tile in global memory and a copy in sA for the inverse
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
           const int r = r0 + a;
-          const double sq = sqrt(sd[r]);
+          const double sq = sqrt(sd[r]), rsq = 1.0 / sq;
 #pragma unroll
-          for (int b = 0; b < 4; ++b) {
-            const int c = c0 + b;
-            const double v = (c > r) ? acc[a][b] / sq : (c == r ? sq : 0.0);
+          for (int b2 = 0; b2 < 4; ++b2) {
+            const int c = c0 + b2;
+            const double v = (c > r) ? acc[a][b2] * rsq : (c == r ? sq : 0.0);
             sA[r * TS + c] = v;
             Aij[r * TS + c] = v;
           }

@@ -82,7 +82,7 @@ int run_device(b2_verifier* v, int64_t n_pairs, const uint32_t* pairs, const int
   B2_CUDA(cudaStreamSynchronize(s));
   m_cap = std::max(m_cap, 32);
   const int wpb = verify_warps_per_block();
-  int blocks = v->n_sm;  // one resident block per SM (shared-memory bound), dynamic work counter
+  int blocks = v->n_sm * verify_blocks_per_sm();  // resident blocks only, dynamic work counter
   blocks = (int)std::min<int64_t>(blocks, (n_pairs + wpb - 1) / wpb);
   const size_t stride = verify_scratch_stride(m_cap);
   // bound the scratch (large match lists -> fewer concurrent warps)
@@ -455,32 +455,6 @@ int b2_score_models(b2_verifier* v, int32_t type, int32_t n, const double* xy1, 
   B2_CUDA(cudaMemcpyAsync(counts, dc, (size_t)n_models * 4, cudaMemcpyDeviceToHost, s));
   B2_CUDA(cudaMemcpyAsync(sums, ds, (size_t)n_models * 8, cudaMemcpyDeviceToHost, s));
   if (n > 0 && masks) B2_CUDA(cudaMemcpyAsync(masks, dk, (size_t)n_models * n, cudaMemcpyDeviceToHost, s));
-  B2_CUDA(cudaStreamSynchronize(s));
-  return B2_OK;
-}
-
-int b2_verify_debug_decisions(b2_verifier* v, int32_t type, int32_t n, const double* xy1, const double* xy2, const double* model,
-                              double max_residual, uint8_t* fast, uint8_t* ref) {
-  if (!v || n < 0 || type < 0 || type > 2 || !model) return set_error(B2_ERR_INVALID, "bad argument");
-  if (n == 0) return B2_OK;
-  B2_CUDA(cudaSetDevice(v->device));
-  auto al = [](size_t b) { return (b + 255) / 256 * 256; };
-  const size_t bp = al((size_t)n * 16), bk = al((size_t)n);
-  B2_TRY(stage(v, 2 * bp + 256 + 2 * bk));
-  uint8_t* p = (uint8_t*)v->d_stage;
-  double* d1 = (double*)p; p += bp;
-  double* d2 = (double*)p; p += bp;
-  double* dm = (double*)p; p += 256;
-  uint8_t* df = p; p += bk;
-  uint8_t* dr = p;
-  cudaStream_t s = v->stream;
-  B2_CUDA(cudaMemcpyAsync(d1, xy1, (size_t)n * 16, cudaMemcpyHostToDevice, s));
-  B2_CUDA(cudaMemcpyAsync(d2, xy2, (size_t)n * 16, cudaMemcpyHostToDevice, s));
-  B2_CUDA(cudaMemcpyAsync(dm, model, 72, cudaMemcpyHostToDevice, s));
-  B2_CUDA(launch_debug_decisions(type, n, d1, d2, dm, max_residual, df, dr, s));
-  count_launches(1);
-  B2_CUDA(cudaMemcpyAsync(fast, df, (size_t)n, cudaMemcpyDeviceToHost, s));
-  B2_CUDA(cudaMemcpyAsync(ref, dr, (size_t)n, cudaMemcpyDeviceToHost, s));
   B2_CUDA(cudaStreamSynchronize(s));
   return B2_OK;
 }

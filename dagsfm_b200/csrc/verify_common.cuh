@@ -41,6 +41,7 @@ struct VerifyArgs {
 
 size_t verify_scratch_stride(int m_cap);
 int verify_warps_per_block();
+int verify_blocks_per_sm();
 cudaError_t launch_normalize_points(const b2_camera* cams, const int64_t* img_off, int n_images, const double* xy,
                                     double* nxy, int64_t n_total, cudaStream_t s);
 cudaError_t launch_verify_pairs(const VerifyArgs& a, int n_blocks, cudaStream_t s);
@@ -50,8 +51,6 @@ cudaError_t launch_relative_pose(const b2_camera* cams, const int64_t* img_off, 
                                  double* angles, int* err, int n_sm, cudaStream_t s);
 cudaError_t launch_score_models(int type, int n, const double* p1, const double* p2, int n_models, const double* models,
                                 double max_res, int* counts, double* sums, uint8_t* masks, cudaStream_t s);
-cudaError_t launch_debug_decisions(int type, int n, const double* p1, const double* p2, const double* model, double max_res,
-                                   uint8_t* fast, uint8_t* ref, cudaStream_t s);
 cudaError_t launch_debug_sample_stream(uint32_t seed, int total, int k, int n_trials, uint32_t* idx, int* out,
                                        cudaStream_t s);
 cudaError_t launch_debug_solve(int type, int n, const double* p1, const double* p2, double* G, uint32_t* inl,

@@ -36,7 +36,7 @@ namespace vf {
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kWarpsPerBlock = 8;
 constexpr int kThreads = 32 * kWarpsPerBlock;
-using LaneView = View<kThreads>;  // per-lane solver workspace in dynamic shared memory
+using LaneView = View<1>;  // per-lane solver workspace: a thread-local array (L1-cached local memory)
 
 // -------------------------------------------------------------------- PRNG
 // std::mt19937 (result_type = uint_fast32_t, 32 significant bits).
@@ -59,7 +59,7 @@ struct WarpShared {
 };
 
 static_assert(sizeof(WarpShared) % 8 == 0, "WarpShared must keep doubles aligned");
-constexpr size_t kDynSmemBytes = (size_t)kLaneWorkDoubles * kThreads * sizeof(double) + sizeof(WarpShared) * kWarpsPerBlock;
+constexpr size_t kDynSmemBytes = sizeof(WarpShared) * kWarpsPerBlock;
 
 __device__ inline void mt_seed(WarpShared& s, uint32_t seed) {
   s.mt[0] = seed;
@@ -149,67 +149,11 @@ __device__ __forceinline__ double residual(int type, const double* M, double2 a,
 // residual chains per lane hide the FP64 divide latency and the points are loaded once.
 constexpr int kGroup = 4;
 
-// Inlier decision of one Sampson residual.  NODIV == false is the reference expression
-// `x2tEx1^2 / den <= max_res` (estimators/utils.cc:87-131 + support_measurement.cc:38-41).
-// NODIV == true (production) decides the same thing without the FP64 divide on the
-// dependency chain: with q = num / den exact and r = fl(q) correctly rounded, r <= T holds for every
-// q <= T and fails for every q > T (1 + 2^-52); products carry a relative error of 2^-53, so
-// num < fl(T den) (1 - 2^-50) implies q < T and num > fl(T den) (1 + 2^-50) implies q > T (1 + 2^-52).
-// Anything in between (probability ~1e-15 per residual, plus 0/0, inf/inf and NaN inputs) falls back to
-// the division itself, so the decision is the reference's in every case.
-template <bool NODIV>
-__device__ __forceinline__ bool sampson_inlier(const double* E, double2 p1, double2 p2, double max_res) {
-  const double x1_0 = p1.x, x1_1 = p1.y, x2_0 = p2.x, x2_1 = p2.y;
-  const double Ex1_0 = E[0] * x1_0 + E[1] * x1_1 + E[2];
-  const double Ex1_1 = E[3] * x1_0 + E[4] * x1_1 + E[5];
-  const double Ex1_2 = E[6] * x1_0 + E[7] * x1_1 + E[8];
-  const double Etx2_0 = E[0] * x2_0 + E[3] * x2_1 + E[6];
-  const double Etx2_1 = E[1] * x2_0 + E[4] * x2_1 + E[7];
-  const double x2tEx1 = x2_0 * Ex1_0 + x2_1 * Ex1_1 + Ex1_2;
-  const double num = x2tEx1 * x2tEx1;
-  const double den = Ex1_0 * Ex1_0 + Ex1_1 * Ex1_1 + Etx2_0 * Etx2_0 + Etx2_1 * Etx2_1;
-  return ratio_at_most<NODIV>(num, den, max_res);
-}
-
-// Inlier decision of one homography transfer residual (homography_matrix.cc:94-131 + support_measurement.cc:38-41),
-// FAST == true: without the IEEE division on the dependency chain.  With y a reciprocal of pd_2 good to 2^-45 (single
-// precision seed + one Newton step) the residual r~ computed from it differs from the reference's floating-point value
-// r by at most `bound` (every intermediate of either evaluation carries a relative error <= 2^-45 on a magnitude
-// <= |d| + |pd / pd_2|; 2^-43 leaves a factor four), so r~ + bound <= T implies r <= T and r~ - bound > T implies
-// r > T.  Anything in between -- and every input outside the seed's range, NaN, infinity: all comparisons false --
-// is decided by the reference expression itself, so the decision is the reference's in every case.
-template <bool FAST>
-__device__ __forceinline__ bool transfer_inlier(const double* H, double2 s, double2 d, double T) {
-  if (FAST) {
-    const double pd_0 = H[0] * s.x + H[1] * s.y + H[2];
-    const double pd_1 = H[3] * s.x + H[4] * s.y + H[5];
-    const double pd_2 = H[6] * s.x + H[7] * s.y + H[8];
-    const double ap = fabs(pd_2);
-    if (ap > 0x1p-100 && ap < 0x1p100) {
-      const double y0 = (double)__frcp_rn((float)pd_2);
-      const double y = fma(y0, fma(-pd_2, y0, 1.0), y0);
-      const double q0 = pd_0 * y, q1 = pd_1 * y;
-      const double dd_0 = d.x - q0, dd_1 = d.y - q1;
-      const double r = dd_0 * dd_0 + dd_1 * dd_1;
-      const double e0 = (fabs(d.x) + fabs(q0)) * 0x1p-43, e1 = (fabs(d.y) + fabs(q1)) * 0x1p-43;
-      const double bound = 2.5 * (fabs(dd_0) * e0 + fabs(dd_1) * e1) + (e0 * e0 + e1 * e1) + r * 0x1p-48;
-      if (r + bound <= T) return true;
-      if (r - bound > T) return false;
-    }
-  }
-  return transfer(H, s.x, s.y, d.x, d.y) <= T;
-}
-template <int TYPE, bool FAST>
-__device__ __forceinline__ bool is_inlier(const double* M, double2 a, double2 b, double max_res) {
-  if (TYPE == EST_H4) return transfer_inlier<FAST>(M, a, b, max_res);
-  if (TYPE == EST_T2) return translation_res(M, a.x, a.y, b.x, b.y) <= max_res;
-  return sampson_inlier<FAST>(M, a, b, max_res);
-}
-
-// FAST: division-free decisions (identical results, see sampson_inlier / transfer_inlier); !FAST: the reference's
-// residual expressions as written (B2_VERIFY_VARIANT=1, kept for the A/B and as the executable statement of parity).
 // Counts are kept per lane and reduced once per group: no warp-wide exchange inside the loop over the matches.
-template <int TYPE, int G, bool FAST>
+// (Division-free variants of the two decisions -- an exact band test for Sampson, a bounded reciprocal for the transfer
+// error, both with the reference expression as fallback -- were measured in round 2 and were SLOWER: the bound arithmetic
+// costs more FP64 issue slots than the division it removes.  profiles/README.md, session 4.)
+template <int TYPE, int G>
 __device__ __noinline__ void score_group(const double2* __restrict__ P1, const double2* __restrict__ P2, int M,
                                          const double* __restrict__ models, const uint16_t* ids, int n, double max_res,
                                          int lane, int* cnt_out) {
@@ -224,11 +168,17 @@ __device__ __noinline__ void score_group(const double2* __restrict__ P1, const d
   int c[G];
 #pragma unroll
   for (int u = 0; u < G; ++u) c[u] = 0;
-#pragma unroll 2
-  for (int i = lane; i < M; i += 32) {
-    const double2 a = P1[i], b = P2[i];
+  // the next match's points are in flight while the current one is scored (the scratch copy of a pair's points does
+  // not stay in L1: the shared-memory carve-out leaves little of it)
+  int i = lane;
+  double2 a = P1[i < M ? i : 0], b = P2[i < M ? i : 0];
+  for (; i < M; i += 32) {
+    const int nx = i + 32 < M ? i + 32 : i;
+    const double2 an = P1[nx], bn = P2[nx];
 #pragma unroll
-    for (int u = 0; u < G; ++u) c[u] += is_inlier<TYPE, FAST>(m[u], a, b, max_res) ? 1 : 0;
+    for (int u = 0; u < G; ++u) c[u] += (residual_t<TYPE>(m[u], a, b) <= max_res) ? 1 : 0;
+    a = an;
+    b = bn;
   }
 #pragma unroll
   for (int u = 0; u < G; ++u) {
@@ -242,16 +192,13 @@ __device__ __noinline__ void score_group(const double2* __restrict__ P1, const d
   }
   __syncwarp();
 }
-// VAR == 0: production (division-free decisions).  VAR == 1: the reference's residual expressions.
-template <int VAR>
 __device__ __forceinline__ void score_group_any(int type, const double2* P1, const double2* P2, int M,
                                                 const double* models, const uint16_t* ids, int n, double max_res,
                                                 int lane, int* cnt_out) {
   constexpr int G = kGroup;
-  constexpr bool FAST = VAR == 0;
-  if (type == EST_H4) score_group<EST_H4, G, FAST>(P1, P2, M, models, ids, n, max_res, lane, cnt_out);
-  else if (type == EST_T2) score_group<EST_T2, G, false>(P1, P2, M, models, ids, n, max_res, lane, cnt_out);
-  else score_group<EST_F7, G, FAST>(P1, P2, M, models, ids, n, max_res, lane, cnt_out);
+  if (type == EST_H4) score_group<EST_H4, G>(P1, P2, M, models, ids, n, max_res, lane, cnt_out);
+  else if (type == EST_T2) score_group<EST_T2, G>(P1, P2, M, models, ids, n, max_res, lane, cnt_out);
+  else score_group<EST_F7, G>(P1, P2, M, models, ids, n, max_res, lane, cnt_out);
 }
 
 // InlierSupportMeasurer::Evaluate, count only (all lanes return the same value).
@@ -705,7 +652,7 @@ __device__ __noinline__ void ransac_warp(int type, const double2* P1, const doub
         const int g1 = sh.off[min(j + 8, 32)];
         constexpr int GS = kGroup;
         for (int g = sh.off[j]; g < g1; g += GS)
-          score_group_any<VAR>(type, P1, P2, M, sc.models, sh.flat + g, min(GS, g1 - g), max_residual, lane, sh.cnt);
+          score_group_any(type, P1, P2, M, sc.models, sh.flat + g, min(GS, g1 - g), max_residual, lane, sh.cnt);
       }
       const int nm = sh.nm[j];
       for (int mi = 0; mi < nm; ++mi) {
@@ -740,7 +687,7 @@ __device__ __noinline__ void ransac_warp(int type, const double2* P1, const doub
             lo_cycles += clock64() - cl0;
             constexpr int GL = kGroup;
             for (int g = 0; g < nlm; g += GL)
-              score_group_any<VAR>(type, P1, P2, M, sc.lomodels, sh.lo_ids + g, min(GL, nlm - g), max_residual, lane,
+              score_group_any(type, P1, P2, M, sc.lomodels, sh.lo_ids + g, min(GL, nlm - g), max_residual, lane,
                               sh.lo_cnt);
             for (int li = 0; li < nlm; ++li) {
               double lm[9];
@@ -866,13 +813,16 @@ __device__ __forceinline__ bool in_box(double2 p, double minx, double maxx, doub
 
 // ------------------------------------------------------------------ main kernel
 
+// VAR == 0: production -- two CTAs (16 warps) per SM, 128 registers per thread.  VAR == 1: one CTA per SM with the full
+// register file (B2_VERIFY_VARIANT=1; the first-generation launch shape, kept for the A/B).
 template <int VAR>
-__global__ void __launch_bounds__(kThreads)
-verify_pairs_kernel(VerifyArgs A) {  // VAR: see score_group_any
-  extern __shared__ double lane_ws[];  // [kLaneWorkDoubles][kThreads] then WarpShared[kWarpsPerBlock]
-  const LaneView ws{lane_ws + threadIdx.x};
+__global__ void __launch_bounds__(kThreads, VAR == 0 ? 2 : 1)
+verify_pairs_kernel(VerifyArgs A) {
+  extern __shared__ double warp_sh[];  // WarpShared[kWarpsPerBlock]
+  double lane_work[kLaneWorkDoubles];
+  const LaneView ws{lane_work};
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  WarpShared& sh = reinterpret_cast<WarpShared*>(lane_ws + kLaneWorkDoubles * kThreads)[wib];
+  WarpShared& sh = reinterpret_cast<WarpShared*>(warp_sh)[wib];
   double* sig_sh = sh.sig;
   const int worker = blockIdx.x * kWarpsPerBlock + wib;
   // carve this worker's scratch
@@ -1061,22 +1011,6 @@ __global__ void score_models_kernel(int type, int n, const double2* P1, const do
   }
 }
 
-// Test seam of the division-free inlier decisions: both decisions of every point for one model.
-__global__ void debug_decisions_kernel(int type, int n, const double2* P1, const double2* P2, const double* model,
-                                       double max_res, uint8_t* fast, uint8_t* ref) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  double m[9];
-  for (int k = 0; k < 9; ++k) m[k] = model[k];
-  if (type == EST_H4) {
-    fast[i] = is_inlier<EST_H4, true>(m, P1[i], P2[i], max_res);
-    ref[i] = residual_t<EST_H4>(m, P1[i], P2[i]) <= max_res;
-  } else {
-    fast[i] = is_inlier<EST_F7, true>(m, P1[i], P2[i], max_res);
-    ref[i] = residual_t<EST_F7>(m, P1[i], P2[i]) <= max_res;
-  }
-}
-
 __global__ void debug_sample_stream_kernel(uint32_t seed, int total, int k, int n_trials, uint32_t* idx, int* out) {
   __shared__ WarpShared sh;
   if (threadIdx.x == 0) {
@@ -1096,9 +1030,10 @@ __global__ void debug_sample_stream_kernel(uint32_t seed, int total, int k, int 
 
 __global__ void debug_solve_kernel(int type, int n, const double2* P1, const double2* P2, double* G, uint32_t* inl,
                                    double* models, int* n_models) {
-  extern __shared__ double lane_ws[];  // same per-lane workspace layout as the production kernel
-  const LaneView ws{lane_ws + threadIdx.x};
-  WarpShared& sh = *reinterpret_cast<WarpShared*>(lane_ws + kLaneWorkDoubles * kThreads);
+  extern __shared__ double warp_sh[];  // same per-lane workspace layout as the production kernel
+  double lane_work[kLaneWorkDoubles];
+  const LaneView ws{lane_work};
+  WarpShared& sh = *reinterpret_cast<WarpShared*>(warp_sh);
   double* sig = sh.sig;
   if (threadIdx.x >= 32) return;        // one warp works; the block size only fixes the stride
   const int lane = threadIdx.x;
@@ -1140,6 +1075,10 @@ size_t verify_scratch_stride(int m_cap) {
   return (b + 255) / 256 * 256;
 }
 int verify_warps_per_block() { return vf::kWarpsPerBlock; }
+int verify_blocks_per_sm() {
+  const char* venv = getenv("B2_VERIFY_VARIANT");
+  return (venv && atoi(venv) == 1) ? 1 : 2;
+}
 
 cudaError_t launch_normalize_points(const b2_camera* cams, const int64_t* img_off, int n_images, const double* xy,
                                     double* nxy, int64_t n_total, cudaStream_t s) {
@@ -1150,8 +1089,8 @@ cudaError_t launch_normalize_points(const b2_camera* cams, const int64_t* img_of
 }
 cudaError_t launch_verify_pairs(const VerifyArgs& a, int n_blocks, cudaStream_t s) {
   const size_t dyn = vf::kDynSmemBytes;
-  // B2_VERIFY_VARIANT=1 selects the instance that evaluates the reference's residual expressions as written (A/B of the division-free
-  // Sampson decision); the default instance is the measured production kernel
+  // B2_VERIFY_VARIANT=1 selects the one-CTA-per-SM instance (A/B of the launch shape); n_blocks is sized by the caller from
+  // verify_blocks_per_sm()
   const char* venv = getenv("B2_VERIFY_VARIANT");
   const int variant = venv ? atoi(venv) : 0;
   if (variant == 1) {
@@ -1170,12 +1109,6 @@ cudaError_t launch_score_models(int type, int n, const double* p1, const double*
   if (n_models == 0) return cudaSuccess;
   vf::score_models_kernel<<<(n_models + 3) / 4, 128, 0, s>>>(type, n, (const double2*)p1, (const double2*)p2, n_models,
                                                               models, max_res, counts, sums, masks);
-  return cudaGetLastError();
-}
-cudaError_t launch_debug_decisions(int type, int n, const double* p1, const double* p2, const double* model, double max_res,
-                                   uint8_t* fast, uint8_t* ref, cudaStream_t s) {
-  if (n == 0) return cudaSuccess;
-  vf::debug_decisions_kernel<<<(n + 127) / 128, 128, 0, s>>>(type, n, (const double2*)p1, (const double2*)p2, model, max_res, fast, ref);
   return cudaGetLastError();
 }
 cudaError_t launch_debug_sample_stream(uint32_t seed, int total, int k, int n_trials, uint32_t* idx, int* out,

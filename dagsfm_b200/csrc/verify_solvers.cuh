@@ -28,21 +28,6 @@ constexpr double kEps = 2.220446049250313e-16;
 // observed with nvcc 12.9 -- an insertion sort over a small local array, and a solver inlined
 // into a second kernel -- both absent at -G; see DESIGN.md.)
 
-// fl(num / den) <= T for den >= 0, T >= 0, decided without the division whenever the answer cannot depend on
-// its rounding (see sampson_inlier in verify_kernel.cu); inside the band -- and for 0/0, inf/inf, NaN, where
-// both comparisons are false -- the division itself decides.  NODIV == false is the plain expression.
-template <bool NODIV>
-__device__ __forceinline__ bool ratio_at_most(double num, double den, double T) {
-  if (NODIV) {
-    const double p = T * den;
-    if (p >= 0x1p-960) {  // a (near-)subnormal product has lost the relative accuracy the band relies on
-      if (num < p * (1.0 - 0x1p-50)) return true;
-      if (num > p * (1.0 + 0x1p-50)) return false;
-    }
-  }
-  return num / den <= T;
-}
-
 // ------------------------------------------------------------------ one-sided Jacobi
 // G: m x n row-major (destroyed), V: n x n row-major out (columns = right singular
 // vectors), sig[n]: singular values, both sorted descending (stable).

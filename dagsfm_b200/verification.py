@@ -81,7 +81,6 @@ def _L():
         L.b2_verify_relative_pose.argtypes = [vp, i64, vp, vp, vp, vp, vp]
         L.b2_verify_relative_pose_device.argtypes = [vp, i64, vp, vp, vp, vp, vp]
         L.b2_score_models.argtypes = [vp, i32, i32, vp, vp, i32, vp, C.c_double, vp, vp, vp]
-        L.b2_verify_debug_decisions.argtypes = [vp, i32, i32, vp, vp, vp, C.c_double, vp, vp]
         L.b2_verify_debug_sample_stream.argtypes = [vp, C.c_uint32, i32, i32, i32, vp]
         L.b2_verify_debug_solve.argtypes = [vp, i32, i32, vp, vp, vp, P(i32)]
         L.b2_verify_last_timing.argtypes = [vp, P(C.c_double)]
@@ -186,16 +185,6 @@ class TwoViewGeometryVerifier:
         check(_L().b2_score_models(self._h, est_type, len(a), a.ctypes.data, b.ctypes.data, len(m), m.ctypes.data,
                                    float(max_residual), counts.ctypes.data, sums.ctypes.data, masks.ctypes.data))
         return counts, sums, masks[:, : len(a)].astype(bool)
-
-    def debug_decisions(self, est_type, xy1, xy2, model, max_residual):
-        """(fast, ref) inlier decisions per point: the kernel's division-free test and the reference expression."""
-        a = np.ascontiguousarray(xy1, dtype=np.float64).reshape(-1, 2)
-        b = np.ascontiguousarray(xy2, dtype=np.float64).reshape(-1, 2)
-        m = np.ascontiguousarray(model, dtype=np.float64).reshape(9)
-        f, r = np.zeros(max(len(a), 1), np.uint8), np.zeros(max(len(a), 1), np.uint8)
-        check(_L().b2_verify_debug_decisions(self._h, est_type, len(a), a.ctypes.data, b.ctypes.data, m.ctypes.data,
-                                             float(max_residual), f.ctypes.data, r.ctypes.data))
-        return f[: len(a)].astype(bool), r[: len(a)].astype(bool)
 
     def debug_sample_stream(self, seed, total, k, n_trials):
         out = np.zeros((n_trials, k), dtype=np.int32)

@@ -276,11 +276,6 @@ int b2_verify_relative_pose_device(b2_verifier* v, int64_t n_pairs, const uint32
 int b2_score_models(b2_verifier* v, int32_t type, int32_t n, const double* xy1, const double* xy2,
                     int32_t n_models, const double* models, double max_residual,
                     int32_t* counts, double* sums, uint8_t* masks);
-/* Test hook: the two inlier decisions of every point for one model (type 0/1 Sampson, 2 homography transfer):
- * fast[i] = the production kernel's division-free decision, ref[i] = `residual <= max_residual` with the reference's
- * residual expression (src/estimators/utils.cc:87-131, homography_matrix.cc:94-131).  They must be equal for every input. */
-int b2_verify_debug_decisions(b2_verifier* v, int32_t type, int32_t n, const double* xy1, const double* xy2,
-                              const double* model, double max_residual, uint8_t* fast, uint8_t* ref);
 /* Test hook: the sampler's index stream (RandomSampler over std::mt19937(seed)), n_trials x k. */
 int b2_verify_debug_sample_stream(b2_verifier* v, uint32_t seed, int32_t total, int32_t k,
                                   int32_t n_trials, int32_t* out);
@@ -380,6 +375,15 @@ void b2_ba_default_options(b2_ba_options* opt);   /* GlobalBundleAdjustment() va
 int b2_ba_create(int device, b2_ba** out);
 int b2_ba_destroy(b2_ba* h);
 int b2_ba_set_allreduce(b2_ba* h, b2_allreduce_fn fn, void* user);
+/* The library's own NCCL communicator for multi-GPU bundle adjustment (one process per GPU, points sharded across the
+ * ranks, cameras replicated -- the layout of DistributedMapperController's final BA over clusters,
+ * src/controllers/distributed_mapper_controller.cpp:836-933): rank 0 obtains an id with b2_nccl_unique_id and hands its
+ * 128 bytes to the other ranks by any means (MPI, a file, torch.distributed); every rank then calls b2_ba_init_nccl.
+ * From then on b2_ba_solve reduces the camera normal equations with ncclAllReduce on its own stream -- no host
+ * synchronisation, no callback.  libnccl.so.2 is bound at run time (already loaded, on the loader path, or
+ * B2_NCCL_LIBRARY). */
+int b2_nccl_unique_id(uint8_t* out128);
+int b2_ba_init_nccl(b2_ba* h, int32_t n_ranks, int32_t rank, const uint8_t* id128);
 /* Solves the problem (HOST arrays in, parameters updated in place).  On a multi-GPU run
  * every rank passes ALL cameras/images and ITS shard of points + observations. */
 int b2_ba_solve(b2_ba* h, const b2_ba_problem* problem, const b2_ba_options* opt,

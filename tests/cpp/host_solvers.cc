@@ -23,6 +23,3 @@ extern "C" int host_h4(const double* p1, const double* p2, double* m) {
   return b2::vf::solve_h4(b2::vf::View<1>{ws}, p1, p2, m);
 }
 extern "C" int host_roots(const double* c, int nc, double* r) { return b2::vf::real_roots<10>(c, nc, r); }
-extern "C" int host_ratio_at_most(int nodiv, double num, double den, double T) {
-  return nodiv ? b2::vf::ratio_at_most<true>(num, den, T) : b2::vf::ratio_at_most<false>(num, den, T);
-}

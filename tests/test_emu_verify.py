@@ -148,8 +148,8 @@ def test_estimate_multiple_through_the_c_abi(ver):
 
 
 def test_experimental_variant_keeps_every_decision(ver, monkeypatch):
-    """B2_VERIFY_VARIANT=1 (groups of eight hypotheses, division-free Sampson decision with an exact fallback in
-    the rounding band): decisions, inlier lists and trial counts must stay those of the oracle."""
+    """B2_VERIFY_VARIANT=1 (one CTA per SM with the full register file instead of two with 128 registers): decisions,
+    inlier lists and trial counts must stay those of the production instance and the oracle."""
     from dagsfm_b200 import Camera, TwoViewOptions
     rng = np.random.default_rng(19)
     specs = [(70, 15, False, True), (55, 12, True, False), (50, 25, False, False), (64, 0, False, True)]
@@ -376,48 +376,3 @@ def test_bench_verification_leg_runs_on_the_emulated_library(ver):
     assert "error" not in out["relative_pose"] and out["relative_pose"]["pairs_per_s_e2e"] > 0
     assert 0 <= out["relative_pose"]["pairs_with_pose"] <= 6
 
-
-def adversarial_decision_inputs(rng, kind, n=4000, T=16.0):
-    """Points whose residual under `model` sits within a few ulps of the threshold T, plus extreme magnitudes and
-    degenerate denominators: the inputs on which a division-free decision could disagree with the reference's."""
-    if kind == 2:      # homography: d = H s / (H s)_3 + offset of length sqrt(T) * (1 + k ulps)
-        H = np.array([[1.02, 0.03, 5.0], [-0.02, 0.97, -3.0], [1e-5, -2e-5, 1.0]]) * rng.choice([1.0, 1e-3, 1e3])
-        s = rng.uniform(0, 1000, (n, 2))
-        p = np.c_[s, np.ones(n)] @ H.T
-        th = rng.uniform(0, 2 * np.pi, n)
-        rad = np.sqrt(T) * (1 + rng.integers(-40, 41, n) * 2.0 ** -52 * rng.choice([1, 1, 1, 1e3, 1e6], n))
-        d = p[:, :2] / p[:, 2:3] + rad[:, None] * np.c_[np.cos(th), np.sin(th)]
-        # degenerate denominators and magnitudes
-        s[:8] = [[0, 0]] * 8
-        d[:8] = rng.uniform(-1e3, 1e3, (8, 2))
-        extra_s = np.array([[1e150, 1.0], [1e-150, 1e-150], [np.inf, 1.0], [np.nan, 2.0], [-1e5 / 1e-5, 0.0], [1.0, 5e4]])
-        extra_d = np.array([[1.0, 1.0], [5.0, -3.0], [1.0, 1.0], [0.0, 0.0], [1.0, 2.0], [3.0, 4.0]])
-        return np.r_[s, extra_s], np.r_[d, extra_d], H.reshape(-1), T
-    F = np.array([[1e-7, 3e-6, -2e-3], [-2e-6, 1e-7, 4e-3], [1e-3, -5e-3, 1.0]]) * rng.choice([1.0, 1e-4, 1e4])
-    x1 = rng.uniform(0, 1000, (n, 2))
-    x2 = rng.uniform(0, 1000, (n, 2))
-    # move x2 along the epipolar normal until the Sampson residual is T (first order), then nudge by ulps
-    for _ in range(6):
-        l = np.c_[x1, np.ones(n)] @ F.T
-        lt = np.c_[x2, np.ones(n)] @ F
-        num = (np.c_[x2, np.ones(n)] * l).sum(1)
-        den = l[:, 0] ** 2 + l[:, 1] ** 2 + lt[:, 0] ** 2 + lt[:, 1] ** 2
-        target = np.sqrt(T * den) * np.sign(num + 1e-300)
-        x2 += ((target - num) / (l[:, 0] ** 2 + l[:, 1] ** 2))[:, None] * l[:, :2]
-    x2 *= (1 + rng.integers(-8, 9, (n, 2)) * 2.0 ** -52)
-    extra1 = np.array([[0.0, 0.0], [1e160, 1e160], [1e-170, 1e-170], [np.nan, 1.0], [np.inf, 0.0]])
-    extra2 = np.array([[0.0, 0.0], [1e160, -1e160], [1e-170, 2e-170], [1.0, 1.0], [1.0, 1.0]])
-    return np.r_[x1, extra1], np.r_[x2, extra2], F.reshape(-1), T
-
-
-@pytest.mark.parametrize("kind", [1, 2])
-def test_division_free_decisions_equal_the_reference_expression_at_the_rounding_band(ver, kind):
-    rng = np.random.default_rng(77 + kind)
-    for _ in range(6):
-        a, b, model, T = adversarial_decision_inputs(rng, kind)
-        fast, ref = ver.debug_decisions(kind, a, b, model, T)
-        assert (fast == ref).all()
-        assert 0.2 < ref[:4000].mean() < 0.8          # the inputs really straddle the threshold
-    z = np.zeros(9)                                   # all-zero model: 0 / 0 and 1 / 0 everywhere
-    fast, ref = ver.debug_decisions(kind, a, b, z, T)
-    assert (fast == ref).all()

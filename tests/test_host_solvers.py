@@ -89,35 +89,3 @@ def test_degenerate_samples_do_not_blow_up(hs):
     for fn, k in ((hs.host_f7, 7), (hs.host_e5, 5)):
         _call(fn, same[:k], same[:k])
 
-
-def test_division_free_ratio_test_is_exact(hs):
-    """ratio_at_most<true> (the experimental Sampson decision of B2_VERIFY_VARIANT=1) must agree with
-    fl(num / den) <= T everywhere: random values, values within a few ulps of the threshold, and the
-    special cases 0/0, x/0, inf, NaN."""
-    hs.host_ratio_at_most.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double]
-    rng = np.random.default_rng(0)
-    cases = []
-    for _ in range(20000):
-        T = float(10.0 ** rng.uniform(-12, 4))
-        den = float(10.0 ** rng.uniform(-20, 20))
-        q = T * den
-        k = int(rng.integers(-6, 7))
-        num = q
-        for _ in range(abs(k)):                      # walk k ulps away from fl(T * den)
-            num = float(np.nextafter(num, np.inf if k > 0 else -np.inf))
-        cases.append((num, den, T))
-        cases.append((float(10.0 ** rng.uniform(-30, 30)), den, T))
-    for _ in range(4000):                            # products that underflow towards the subnormal range
-        T = float(10.0 ** rng.uniform(-40, -5)); den = float(10.0 ** rng.uniform(-300, -260))
-        cases.append((float(T * den * rng.uniform(0.25, 4.0)), den, T))
-        cases.append((float(np.nextafter(T * den, np.inf)), den, T))
-    inf, nan = float("inf"), float("nan")
-    cases += [(0.0, 0.0, 1.0), (1.0, 0.0, 1.0), (0.0, 1.0, 0.0), (1e-320, 1e-300, 1e-20), (inf, 1.0, 1.0), (1.0, inf, 1.0),
-              (inf, inf, 1.0), (nan, 1.0, 1.0), (1.0, nan, 1.0), (1.0, 1.0, nan), (5e-324, 5e-324, 1.0), (1e308, 1e-308, 1e300)]
-    bad = 0
-    for num, den, T in cases:
-        exp = hs.host_ratio_at_most(0, num, den, T)
-        with np.errstate(all="ignore"):
-            assert bool(exp) == bool(np.float64(num) / np.float64(den) <= np.float64(T))
-        bad += int(hs.host_ratio_at_most(1, num, den, T) != exp)
-    assert bad == 0

@@ -14,7 +14,7 @@ sys.path.insert(0, str(ROOT))
 pytestmark = pytest.mark.gpu
 
 
-def _rank(rank, world, port, out_dir):
+def _rank(rank, world, port, out_dir, native=False, solver=0):
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -28,8 +28,12 @@ def _rank(rank, world, port, out_dir):
     sub, ids = shard_ba_problem(prob, rank, world)
     o = BundleAdjustmentOptions.default()
     o.max_num_iterations, o.gradient_tolerance, o.function_tolerance = 100, 1e-9, 1e-16
+    o.linear_solver_type = solver
     ba = BundleAdjuster(o, device=rank)
-    ba.set_allreduce(make_torch_allreduce(torch.device("cuda", rank)))
+    if native:
+        ba.init_nccl_from_torch()      # the library's own communicator: ncclAllReduce on the solver stream
+    else:
+        ba.set_allreduce(make_torch_allreduce(torch.device("cuda", rank)))
     s = ba.Solve(sub)
     np.savez(os.path.join(out_dir, f"r{rank}.npz"), xyz=sub["xyz"], ids=ids, qvec=sub["qvec"], tvec=sub["tvec"],
              cam=sub["cam_params"], cost=s.final_cost, iters=s.num_iterations)
@@ -37,7 +41,8 @@ def _rank(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-def test_ba_two_ranks_equal_single_gpu(tmp_path):
+@pytest.mark.parametrize("native,solver", [(False, 0), (True, 0), (True, 2)])
+def test_ba_two_ranks_equal_single_gpu(tmp_path, native, solver):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -45,11 +50,12 @@ def test_ba_two_ranks_equal_single_gpu(tmp_path):
     from dagsfm_b200 import BundleAdjuster, BundleAdjustmentOptions
     from tests.ba_scene import make_ba_problem, reprojection_rms
     port = 29600 + (os.getpid() % 2000)
-    mp.spawn(_rank, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_rank, args=(2, port, str(tmp_path), native, solver), nprocs=2, join=True)
     parts = [np.load(tmp_path / f"r{r}.npz") for r in range(2)]
     prob = make_ba_problem(n_img=30, n_pts=1500, track_len=6, seed=9)
     o = BundleAdjustmentOptions.default()
     o.max_num_iterations, o.gradient_tolerance, o.function_tolerance = 100, 1e-9, 1e-16
+    o.linear_solver_type = solver
     ba = BundleAdjuster(o)
     s = ba.Solve(prob)
     ba.close()
