@@ -287,8 +287,8 @@ int upload_chol_graph(b2_ba* h, const FusedPlan& plan, const BaTiles& T, BaCholD
   B2_TRY(dev_alloc(h, &out->rdiag, (size_t)plan.nt * kST));
   out->trace = nullptr;
   if (getenv("B2_BA_CHOL_TRACE")) {  // profiling aid: per-task time stamps, dumped after the first factorisation
-    B2_TRY(dev_alloc(h, &out->trace, (size_t)G.n_tasks * 4));
-    B2_CUDA(cudaMemsetAsync(out->trace, 0, (size_t)G.n_tasks * 32, h->stream));
+    B2_TRY(dev_alloc(h, &out->trace, (size_t)G.n_tasks * 8));
+    B2_CUDA(cudaMemsetAsync(out->trace, 0, (size_t)G.n_tasks * 64, h->stream));
   }
   return B2_OK;
 }
@@ -799,14 +799,15 @@ int solve_impl(b2_ba* h, const b2_ba_problem* pr, const b2_ba_options* opt, b2_b
       B2_CUDA(bac_solve_system(Tl, Cg, P.dc, h->n_sm, s));  // one persistent task-graph kernel: factor + both solves
       if (Cg.trace && iter == 1) {
         if (const char* path = getenv("B2_BA_CHOL_TRACE")) {
-          std::vector<unsigned long long> tr((size_t)Cg.n_tasks * 4);
+          std::vector<unsigned long long> tr((size_t)Cg.n_tasks * 8);
           std::vector<int32_t> tk((size_t)Cg.n_tasks * 4);
           B2_CUDA(cudaMemcpyAsync(tr.data(), Cg.trace, tr.size() * 8, cudaMemcpyDeviceToHost, s));
           B2_CUDA(cudaMemcpyAsync(tk.data(), Cg.task, tk.size() * 4, cudaMemcpyDeviceToHost, s));
           B2_CUDA(cudaStreamSynchronize(s));
           if (FILE* f = fopen(path, "w")) {
             for (int t = 0; t < Cg.n_tasks; ++t)
-              fprintf(f, "%d %d %d %d %llu %llu %llu %llu\n", tk[4 * t], tk[4 * t + 1], tk[4 * t + 2], tk[4 * t + 3], tr[4 * t], tr[4 * t + 1], tr[4 * t + 2], tr[4 * t + 3]);
+              fprintf(f, "%d %d %d %d %llu %llu %llu %llu %llu %llu %llu %llu\n", tk[4 * t], tk[4 * t + 1], tk[4 * t + 2], tk[4 * t + 3], tr[8 * t],
+                      tr[8 * t + 1], tr[8 * t + 2], tr[8 * t + 3], tr[8 * t + 4], tr[8 * t + 5], tr[8 * t + 6], tr[8 * t + 7]);
             fclose(f);
           }
         }

@@ -146,14 +146,14 @@ struct Plan {
   int32_t n_tasks;
   int* flags;               // [n_tiles] tile | [nt] inverse | [nt] y | [nt] x | [1] task counter
   double* rdiag;            // [nt][64] 1 / diag(R_ii)
-  unsigned long long* trace;  // optional [n_tasks][4] %globaltimer stamps: picked, dependencies consumed, published, done
+  unsigned long long* trace;  // optional [n_tasks][8] %globaltimer stamps: picked, dependencies consumed, published, done, + 4 phase marks
 };
 __device__ __forceinline__ void stamp(const Plan& Pn, int t, int k) {
 #ifdef __CUDA_ARCH__
   if (Pn.trace && threadIdx.x == 0) {
     unsigned long long v;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(v));
-    Pn.trace[4 * (size_t)t + k] = v;
+    Pn.trace[8 * (size_t)t + k] = v;
   }
 #endif
 }
@@ -195,9 +195,11 @@ __global__ void __launch_bounds__(kThreads, 2) solve_graph_kernel(BaTiles T, Pla
         const int ta = Pn.dep[2 * d], tb = Pn.dep[2 * d + 1];
         wait_flag(f_tile + ta);
         if (tb != ta) wait_flag(f_tile + tb);
+        if (d == d1 - 1) stamp(Pn, t, 6);
         load_tile(T.tiles + (size_t)ta * (TS * TS), sA);
         if (tb != ta) load_tile(T.tiles + (size_t)tb * (TS * TS), sB);
         __syncthreads();
+        if (d == d1 - 1) stamp(Pn, t, 7);
         tile_product(sA, tb != ta ? sB : sA, r0, c0, acc);
         __syncthreads();
       }
@@ -270,6 +272,7 @@ __global__ void __launch_bounds__(kThreads, 2) solve_graph_kernel(BaTiles T, Pla
           }
         }
         __syncthreads();
+        stamp(Pn, t, 4);
         if (bad) *T.info = 1;
         // R = D^-1/2 U; the tile in global memory and a copy in sA for the inverse
 #pragma unroll
@@ -290,6 +293,7 @@ __global__ void __launch_bounds__(kThreads, 2) solve_graph_kernel(BaTiles T, Pla
           sv[tid] = inv;
           Pn.rdiag[(size_t)i * TS + tid] = inv;
         }
+        stamp(Pn, t, 5);
         publish(f_tile + tile);  // (contains the barrier that orders sv)
         stamp(Pn, t, 2);
         // ---- off the critical path: Y = R^-T I, stored transposed = R^-1 (upper)
@@ -321,8 +325,10 @@ __global__ void __launch_bounds__(kThreads, 2) solve_graph_kernel(BaTiles T, Pla
         double a[16];
 #pragma unroll
         for (int m = 0; m < 16; ++m) a[m] = sB[(4 * m + q) * TS + c];
+        stamp(Pn, t, 4);
         quad_trsm(sA, sv, a, q);
         __syncthreads();
+        stamp(Pn, t, 5);
 #pragma unroll
         for (int m = 0; m < 16; ++m) sB[(4 * m + q) * TS + c] = a[m];
         __syncthreads();

@@ -192,7 +192,7 @@ struct BaCholDev {                   // its device copy + the per-launch state
   int32_t n_tasks;
   int* flags;                        // bac_flag_count(T) ints
   double* rdiag;                     // [nt * 64]
-  unsigned long long* trace;         // nullptr, or [n_tasks * 4] time stamps (B2_BA_CHOL_TRACE, profiling aid)
+  unsigned long long* trace;         // nullptr, or [n_tasks * 8] time stamps (B2_BA_CHOL_TRACE, profiling aid)
 };
 void bac_build_graph(int nt, const int32_t* tile_id, const int32_t* row_ptr, const int32_t* row_col, BaCholGraph* G);
 size_t bac_flag_count(const BaTiles& T);

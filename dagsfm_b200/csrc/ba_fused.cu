@@ -222,13 +222,19 @@ struct WinCfg {
   static constexpr int NTILES = NT8 * (NT8 + 1) / 2;
   static constexpr int THREADS = (NTILES + 31) / 32 * 32;
   static constexpr int KB = 3 * kWinBatch;        // k-panel: 3 columns per point
+  // shared-memory row: every group of 8 columns (one register-tile side, 64 B) padded to 10 doubles, so that the 15 / 20
+  // groups a warp's tiles read in one LDS.128 spread over all banks (unpadded, groups 0, 2, 4, ... share four banks: the
+  // 57 M bank conflicts of the first capture, profiles/r2_ba_fused_ncu_full.txt)
+  static constexpr int NP = NT8 * 10;
+  __host__ __device__ static constexpr int pad(int e) { return (e >> 3) * 10 + (e & 7); }
 };
 
 template <int NLOC>
 __global__ void __launch_bounds__(WinCfg<NLOC>::THREADS) schur_window_kernel(BaDev P, BaWin W, BaTiles T) {
   using C = WinCfg<NLOC>;
   constexpr int N = C::N, KB = C::KB;
-  __shared__ __align__(16) double Zt[KB][N];  // Zt[3 pl + m][slot * 10 + k]
+  extern __shared__ double win_smem[];  // Zt[3 pl + m][pad(slot * 10 + k)] (above the 48 KB static limit for 16 slots)
+  double (*Zt)[C::NP] = reinterpret_cast<double (*)[C::NP]>(win_smem);
   __shared__ double sU[KB];
   __shared__ int sCol[N];
   const int tid = threadIdx.x;
@@ -255,7 +261,7 @@ __global__ void __launch_bounds__(WinCfg<NLOC>::THREADS) schur_window_kernel(BaD
     const int p_lo = W.chunk_pt0[chunk], p_hi = W.chunk_pt0[chunk + 1];
     for (int b0 = p_lo; b0 < p_hi; b0 += kWinBatch) {
       const int nb = min(kWinBatch, p_hi - b0);
-      for (int e = tid; e < 3 * nb * N; e += C::THREADS) (&Zt[0][0])[e] = 0.0;
+      for (int e = tid; e < 3 * nb * C::NP; e += C::THREADS) (&Zt[0][0])[e] = 0.0;
       __syncthreads();
       for (int pl = 0; pl < nb; ++pl) {
         const int p = W.pt_order[b0 + pl];
@@ -263,7 +269,7 @@ __global__ void __launch_bounds__(WinCfg<NLOC>::THREADS) schur_window_kernel(BaD
         const int L = (int)(P.pt_start[p + 1] - o0);
         for (int e = tid; e < L * 30; e += C::THREADS) {
           const int a = e / 30, q = e - 30 * a, k = q / 3, m = q - 3 * k;
-          Zt[3 * pl + m][W.obs_slot[o0 + a] * NC + k] = W.Z[(o0 + a) * 30 + q];
+          Zt[3 * pl + m][C::pad(W.obs_slot[o0 + a] * NC + k)] = W.Z[(o0 + a) * 30 + q];
         }
         if (tid < 3) sU[3 * pl + tid] = W.U[3 * (int64_t)p + tid];
       }
@@ -271,8 +277,8 @@ __global__ void __launch_bounds__(WinCfg<NLOC>::THREADS) schur_window_kernel(BaD
       if (owner) {
         for (int kk = 0; kk < 3 * nb; ++kk) {
           double av[8], bv[8];
-          const double2* pa = reinterpret_cast<const double2*>(&Zt[kk][ti * 8]);
-          const double2* pb = reinterpret_cast<const double2*>(&Zt[kk][tj * 8]);
+          const double2* pa = reinterpret_cast<const double2*>(&Zt[kk][ti * 10]);
+          const double2* pb = reinterpret_cast<const double2*>(&Zt[kk][tj * 10]);
 #pragma unroll
           for (int h = 0; h < 4; ++h) {
             const double2 x = pa[h], y = pb[h];
@@ -286,7 +292,7 @@ __global__ void __launch_bounds__(WinCfg<NLOC>::THREADS) schur_window_kernel(BaD
         }
       }
       if (tid < N)
-        for (int kk = 0; kk < 3 * nb; ++kk) racc = fma(Zt[kk][tid], sU[kk], racc);
+        for (int kk = 0; kk < 3 * nb; ++kk) racc = fma(Zt[kk][C::pad(tid)], sU[kk], racc);
       __syncthreads();
     }
     // ---- the window into the packed system: S -= Z Z' (upper entries), rhs -= Z u
@@ -420,8 +426,17 @@ cudaError_t baf_launch_schur_points(const BaDev& P, const BaWin& W, double radiu
 cudaError_t baf_launch_schur_window(const BaDev& P, const BaWin& W, const BaTiles& T, int n_sm, cudaStream_t s) {
   if (W.n_chunks == 0) return cudaSuccess;
   const int grid = std::min(W.n_chunks, n_sm * 4);
-  if (W.nloc == 12) baf::schur_window_kernel<12><<<grid, baf::WinCfg<12>::THREADS, 0, s>>>(P, W, T);
-  else baf::schur_window_kernel<16><<<grid, baf::WinCfg<16>::THREADS, 0, s>>>(P, W, T);
+  constexpr int smem12 = baf::WinCfg<12>::KB * baf::WinCfg<12>::NP * (int)sizeof(double);
+  constexpr int smem16 = baf::WinCfg<16>::KB * baf::WinCfg<16>::NP * (int)sizeof(double);
+  static bool attr_set = false;  // per process; the attribute is a property of the function
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(baf::schur_window_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem12);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(baf::schur_window_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem16);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  if (W.nloc == 12) baf::schur_window_kernel<12><<<grid, baf::WinCfg<12>::THREADS, smem12, s>>>(P, W, T);
+  else baf::schur_window_kernel<16><<<grid, baf::WinCfg<16>::THREADS, smem16, s>>>(P, W, T);
   return cudaGetLastError();
 }
 cudaError_t baf_launch_finish(const BaDev& P, const BaTiles& T, double radius, double min_diag, double max_diag,

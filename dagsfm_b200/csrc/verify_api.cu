@@ -141,6 +141,7 @@ int run_device(b2_verifier* v, int64_t n_pairs, const uint32_t* pairs, const int
     fprintf(stderr, "[b2 verify profile] warp-cycles: sample %.3g solve %.3g score %.3g lo %.3g | E %.3g F %.3g H %.3g T %.3g | kernel %.3f s\n",
             (double)hp[0], (double)hp[1], (double)hp[2], (double)hp[3], (double)hp[4], (double)hp[5], (double)hp[6], (double)hp[7], v->last_kernel_s);
   }
+  if (err == 2) return set_error(B2_ERR_CUDA, "sampler FIFO exhausted inside one batch of trials (more than 256 raw draws)");
   if (err) return set_error(B2_ERR_INVALID, "pair references an image outside the store");
   return B2_OK;
 }

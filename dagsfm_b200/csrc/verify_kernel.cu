@@ -40,12 +40,14 @@ using LaneView = View<1>;  // per-lane solver workspace: a thread-local array (L
 
 // -------------------------------------------------------------------- PRNG
 // std::mt19937 (result_type = uint_fast32_t, 32 significant bits).
+constexpr int kIdxSmem = 2048;
 struct WarpShared {
   double V[81];         // right singular vectors of the warp-level Jacobi SVD
   double R[81];         // triangular factor of the local estimator's constraint matrix
   double sig[9];
   uint32_t mt[624];
-  uint32_t ring[512];   // FIFO of raw mt outputs; rollback = moving r back
+  uint32_t ring[256];   // FIFO of raw mt outputs (a batch draws <= 32 x 7 + rejections); rollback = moving r back
+  uint16_t idx16[kIdxSmem];  // the sampler's persistent index vector, when the pair has at most kIdxSmem matches
   uint32_t samp[32][8]; // sample indices of the 32 trials of a batch
   uint32_t pos_after[32];
   int cnt[320];         // support count of hypothesis (trial j, model mi) at [10 j + mi]
@@ -56,6 +58,7 @@ struct WarpShared {
   int nm[32];
   int lo_nm;
   uint32_t mti, w, r;
+  uint32_t r0, overflow;  // FIFO position at the start of the batch; raised if a batch ever needs more than the ring holds
 };
 
 static_assert(sizeof(WarpShared) % 8 == 0, "WarpShared must keep doubles aligned");
@@ -67,6 +70,7 @@ __device__ inline void mt_seed(WarpShared& s, uint32_t seed) {
   s.mti = 624;
   s.w = 0;
   s.r = 0;
+  s.r0 = 0;
 }
 __device__ inline uint32_t mt_next(WarpShared& s) {
   if (s.mti >= 624) {
@@ -86,10 +90,11 @@ __device__ inline uint32_t mt_next(WarpShared& s) {
 // next raw output through the FIFO (lane 0 only)
 __device__ inline uint32_t raw_next(WarpShared& s) {
   if (s.r == s.w) {
-    s.ring[s.w & 511u] = mt_next(s);
+    if (s.w - s.r0 >= 256u) s.overflow = 1;  // a rollback could no longer reach the start of the batch
+    s.ring[s.w & 255u] = mt_next(s);
     ++s.w;
   }
-  return s.ring[(s.r++) & 511u];
+  return s.ring[(s.r++) & 255u];
 }
 // libstdc++ (GCC >= 11) std::uniform_int_distribution<uint32_t>(a, b) on a 32-bit URBG:
 // Lemire's nearly-divisionless method (bits/uniform_int_dist.h, _S_nd<uint64_t>).
@@ -571,7 +576,11 @@ __device__ __noinline__ void ransac_warp(int type, const double2* P1, const doub
   for (int k = 0; k < 9; ++k) best_model[k] = 0.0;
   bool abort = false;
   if (lane < 12) sh.lo_ids[lane] = (uint16_t)lane;
-  for (int i = lane; i < M; i += 32) sc.idx[i] = (uint32_t)i;  // sampler.Initialize
+  // sampler.Initialize.  The shuffle below is a chain of dependent swaps by one lane: in shared memory when the pair's
+  // matches fit (a swap through the global scratch costs two L2 round trips), in the scratch otherwise
+  const bool idx_sm = M <= kIdxSmem;
+  if (idx_sm) for (int i = lane; i < M; i += 32) sh.idx16[i] = (uint16_t)i;
+  else for (int i = lane; i < M; i += 32) sc.idx[i] = (uint32_t)i;
   __syncwarp();
   unsigned long long dyn_max = max_trials;
   unsigned long long t0 = 0;
@@ -588,14 +597,21 @@ __device__ __noinline__ void ransac_warp(int type, const double2* P1, const doub
     // --- lane 0: sample indices for trials t0 .. t0+nb-1 (Shuffle of the persistent vector)
     if (lane == 0) {
       const uint32_t last = (uint32_t)(M - 1);
+      sh.r0 = sh.r;
       for (int j = 0; j < nb; ++j) {
         for (uint32_t i = 0; i < (uint32_t)kmin; ++i) {
           const uint32_t jj = uniform_u32(sh, i, last);
-          const uint32_t a = sc.idx[i], b = sc.idx[jj];
-          sc.idx[i] = b;
-          sc.idx[jj] = a;
+          if (idx_sm) {
+            const uint16_t a = sh.idx16[i], b = sh.idx16[jj];
+            sh.idx16[i] = b;
+            sh.idx16[jj] = a;
+          } else {
+            const uint32_t a = sc.idx[i], b = sc.idx[jj];
+            sc.idx[i] = b;
+            sc.idx[jj] = a;
+          }
         }
-        for (int i = 0; i < kmin; ++i) sh.samp[j][i] = sc.idx[i];
+        for (int i = 0; i < kmin; ++i) sh.samp[j][i] = idx_sm ? (uint32_t)sh.idx16[i] : sc.idx[i];
         sh.pos_after[j] = sh.r;
       }
     }
@@ -656,12 +672,12 @@ __device__ __noinline__ void ransac_warp(int type, const double2* P1, const doub
       }
       const int nm = sh.nm[j];
       for (int mi = 0; mi < nm; ++mi) {
-        double model[9];
-        for (int k = 0; k < 9; ++k) model[k] = sc.models[(size_t)j * 90 + 9 * mi + k];
         const int cnt = sh.cnt[j * 10 + mi];
         bool better = cnt > best_count;
         double sum = 0;
-        if (cnt >= best_count) {
+        double model[9];
+        if (cnt >= best_count) {  // the hypothesis itself is only needed from here on (most trials stop at the count)
+          for (int k = 0; k < 9; ++k) model[k] = sc.models[(size_t)j * 90 + 9 * mi + k];
           sum = score_sum(type, P1, P2, M, model, max_residual, lane, sc.tmask);
           sum = __shfl_sync(kFull, sum, 0);
           if (cnt == best_count) better = sum < best_sum;
@@ -813,10 +829,17 @@ __device__ __forceinline__ bool in_box(double2 p, double minx, double maxx, doub
 
 // ------------------------------------------------------------------ main kernel
 
-// VAR == 0: production -- two CTAs (16 warps) per SM, 128 registers per thread.  VAR == 1: one CTA per SM with the full
-// register file (B2_VERIFY_VARIANT=1; the first-generation launch shape, kept for the A/B).
+// Launch shapes (threads per CTA, CTAs per SM -> registers per thread), B2_VERIFY_VARIANT selects one for the A/B:
+//   0  256 x 1   8 warps / SM, 255 registers   production (measured fastest, profiles/README.md session 5)
+//   1  256 x 2  16 warps / SM, 128 registers   twice the warps, but the solvers and the RANSAC driver spill
+//   2  128 x 3  12 warps / SM, 168 registers
+//   3  128 x 2   8 warps / SM, 255 registers   the production register budget in smaller CTAs
+struct Shape { int threads, blocks_per_sm; };
+__host__ __device__ constexpr Shape shape_of(int var) {
+  return var == 1 ? Shape{256, 2} : var == 2 ? Shape{128, 3} : var == 3 ? Shape{128, 2} : Shape{256, 1};
+}
 template <int VAR>
-__global__ void __launch_bounds__(kThreads, VAR == 0 ? 2 : 1)
+__global__ void __launch_bounds__(shape_of(VAR).threads, shape_of(VAR).blocks_per_sm)
 verify_pairs_kernel(VerifyArgs A) {
   extern __shared__ double warp_sh[];  // WarpShared[kWarpsPerBlock]
   double lane_work[kLaneWorkDoubles];
@@ -824,7 +847,7 @@ verify_pairs_kernel(VerifyArgs A) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   WarpShared& sh = reinterpret_cast<WarpShared*>(warp_sh)[wib];
   double* sig_sh = sh.sig;
-  const int worker = blockIdx.x * kWarpsPerBlock + wib;
+  const int worker = blockIdx.x * (int)(blockDim.x >> 5) + wib;
   // carve this worker's scratch
   Scratch sc;
   {
@@ -849,6 +872,8 @@ verify_pairs_kernel(VerifyArgs A) {
     sc.prof = A.prof;
   }
   const b2_two_view_options& o = A.opt;
+  if (lane == 0) sh.overflow = 0;
+  __syncwarp();
   for (;;) {
     long long p = 0;
     if (lane == 0) p = (long long)atomicAdd(A.work_counter, 1ull);
@@ -989,7 +1014,10 @@ verify_pairs_kernel(VerifyArgs A) {
         }
       }
     }
-    if (lane == 0) A.results[p] = res;
+    if (lane == 0) {
+      A.results[p] = res;
+      if (sh.overflow) atomicExch(A.err, 2);
+    }
     __syncwarp();
   }
 }
@@ -1074,11 +1102,13 @@ size_t verify_scratch_stride(int m_cap) {
   size_t b = mc * 16 * 6 + mc * 2 * 9 * 8 + 32 * 90 * 8 + 90 * 8 + mc * 4 * 2 + mc * 4;
   return (b + 255) / 256 * 256;
 }
-int verify_warps_per_block() { return vf::kWarpsPerBlock; }
-int verify_blocks_per_sm() {
+static int verify_variant() {
   const char* venv = getenv("B2_VERIFY_VARIANT");
-  return (venv && atoi(venv) == 1) ? 1 : 2;
+  const int v = venv ? atoi(venv) : 0;
+  return (v >= 0 && v <= 3) ? v : 0;
 }
+int verify_warps_per_block() { return vf::shape_of(verify_variant()).threads / 32; }
+int verify_blocks_per_sm() { return vf::shape_of(verify_variant()).blocks_per_sm; }
 
 cudaError_t launch_normalize_points(const b2_camera* cams, const int64_t* img_off, int n_images, const double* xy,
                                     double* nxy, int64_t n_total, cudaStream_t s) {
@@ -1087,22 +1117,23 @@ cudaError_t launch_normalize_points(const b2_camera* cams, const int64_t* img_of
       cams, img_off, n_images, (const double2*)xy, (double2*)nxy, n_total);
   return cudaGetLastError();
 }
-cudaError_t launch_verify_pairs(const VerifyArgs& a, int n_blocks, cudaStream_t s) {
-  const size_t dyn = vf::kDynSmemBytes;
-  // B2_VERIFY_VARIANT=1 selects the one-CTA-per-SM instance (A/B of the launch shape); n_blocks is sized by the caller from
-  // verify_blocks_per_sm()
-  const char* venv = getenv("B2_VERIFY_VARIANT");
-  const int variant = venv ? atoi(venv) : 0;
-  if (variant == 1) {
-    cudaError_t e = cudaFuncSetAttribute(vf::verify_pairs_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-    if (e != cudaSuccess) return e;
-    vf::verify_pairs_kernel<1><<<n_blocks, vf::kThreads, dyn, s>>>(a);
-    return cudaGetLastError();
-  }
-  cudaError_t e = cudaFuncSetAttribute(vf::verify_pairs_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+template <int VAR>
+static cudaError_t launch_verify_shape(const VerifyArgs& a, int n_blocks, cudaStream_t s) {
+  constexpr vf::Shape sh = vf::shape_of(VAR);
+  const size_t dyn = sizeof(vf::WarpShared) * (sh.threads / 32);
+  cudaError_t e = cudaFuncSetAttribute(vf::verify_pairs_kernel<VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
   if (e != cudaSuccess) return e;
-  vf::verify_pairs_kernel<0><<<n_blocks, vf::kThreads, dyn, s>>>(a);
+  vf::verify_pairs_kernel<VAR><<<n_blocks, sh.threads, dyn, s>>>(a);
   return cudaGetLastError();
+}
+// n_blocks is sized by the caller from verify_blocks_per_sm() / verify_warps_per_block()
+cudaError_t launch_verify_pairs(const VerifyArgs& a, int n_blocks, cudaStream_t s) {
+  switch (verify_variant()) {
+    case 1: return launch_verify_shape<1>(a, n_blocks, s);
+    case 2: return launch_verify_shape<2>(a, n_blocks, s);
+    case 3: return launch_verify_shape<3>(a, n_blocks, s);
+    default: return launch_verify_shape<0>(a, n_blocks, s);
+  }
 }
 cudaError_t launch_score_models(int type, int n, const double* p1, const double* p2, int n_models, const double* models,
                                 double max_res, int* counts, double* sums, uint8_t* masks, cudaStream_t s) {
