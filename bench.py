@@ -57,6 +57,8 @@ def parse():
                     help="verification leg: also time b2_verify_relative_pose (EstimateWithRelativePose) on the verified pairs")
     ap.add_argument("--ba-solver", default="auto", choices=["auto", "exact", "iterative"],
                     help="BA leg: linear solver (auto = the reference's rule: ITERATIVE_SCHUR above 1000 images)")
+    ap.add_argument("--retrieval-words", type=int, default=32768,
+                    help="retrieval leg (candidate pairs from a vocabulary tree over the C3 collection): visual words; 0 = skip")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -573,6 +575,63 @@ def bench_pipeline(a, dev, local_rank, rank, world, cores, barrier, dist):
     return out
 
 
+def bench_retrieval(a, coll, local_rank, cores, pairs_all):
+    """SURVEY 8f rank 3 / the input stage of C3: VocabSimilarityGraph::Run (similarity_graph.cpp:101-200) over the C3
+    collection resident in HBM -- exact nearest visual words of every descriptor, inverted index, query of every image,
+    top `seq_cand` images each.  One step = the whole stage (index + query).  Rank 0 only (the stage is not sharded)."""
+    import torch
+    from dagsfm_b200.retrieval import VisualIndex
+    from dagsfm_b200.synthetic import make_vocabulary_device
+    n_img, n_kp, K = a.seq_images, a.seq_kp, 5
+    vocab = make_vocabulary_device(coll["desc"], a.retrieval_words, n_train=min(1 << 20, n_img * n_kp), seed=7)
+    vi = VisualIndex(local_rank)
+    out = {"workload": f"{n_img} images x {n_kp} descriptors, {a.retrieval_words} visual words, num_neighbors {K}, "
+                       f"max_num_images {a.seq_cand} (VocabSimilarityGraph defaults: 50 / 5)"}
+    try:
+        vi.set_vocabulary(vocab)
+        steps = []
+        for s in range(1 + 2):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            vi.index_images_device(coll["desc"].data_ptr(), n_img, n_kp, K)
+            ids, sc, cnt = vi.query_all(a.seq_cand)
+            w = time.perf_counter() - t0
+            if s >= 1:
+                steps.append((w, vi.last_timing()))
+        w = float(np.mean([x[0] for x in steps]))
+        tm = {k: float(np.mean([x[1][k] for x in steps])) for k in steps[0][1]}
+        ops = 2.0 * 128 * n_img * n_kp * a.retrieval_words
+        q = np.repeat(np.arange(n_img), ids.shape[1]).reshape(ids.shape)
+        valid = (np.arange(ids.shape[1])[None, :] < cnt[:, None]) & (q < ids)
+        got = set(map(tuple, np.stack([q[valid], ids[valid]], 1).tolist()))
+        near = pairs_all[(pairs_all[:, 1].astype(np.int64) - pairs_all[:, 0]) <= max(a.seq_cand // 2, 1)]
+        out.update({"images_per_s": n_img / w, "wall_s_per_step": w, **{k: v for k, v in tm.items()},
+                    "candidate_pairs": int(valid.sum()),
+                    "recall_of_overlapping_pairs": float(np.mean([tuple(p) in got for p in near.tolist()])) if len(near) else None,
+                    "recall_note": f"share of the sequence's pairs up to {max(a.seq_cand // 2, 1)} images apart (>= half the scene points in common) found among the candidates",
+                    "roofline": {"bound": "int8 (dp4a / tensor)", "kernel": "word_knn_kernel<5> (exact nearest words)", "unit": "TOP/s",
+                                 "achieved": ops / tm["word_search_s"] / 1e12,
+                                 "algorithmic_ops": "2 x 128 per descriptor x word", "share_of_step": tm["word_search_s"] / w}})
+        # parity spot check + CPU baseline of the dominant part on a bounded sample (exact word search, OpenMP)
+        if not a.no_cpu:
+            from oracle import pyoracle as orc
+            o = orc.RetrievalOracle(vocab.words, vocab.proj, vocab.thresholds, vocab.has_embedding)
+            rng = np.random.default_rng(1)
+            n_s = min(64 * cores, n_img * n_kp)
+            pick = np.sort(rng.choice(n_img * n_kp, n_s, replace=False))
+            sample = coll["desc"].reshape(-1, 128)[torch.from_numpy(pick).to(coll["desc"].device)].cpu().numpy()
+            t0 = time.perf_counter()
+            exp = o.word_ids(sample, K)
+            t = time.perf_counter() - t0
+            gotw = vi.debug_word_ids()[pick]
+            out["cpu_baseline"] = {"value": n_s / t / n_kp, "unit": "images/s (word search only)", "cores": cores, "kind": "port",
+                                   "sample": f"exact 5 nearest words of {n_s} sampled descriptors, {t:.1f} s (the reference's FLANN search is approximate and cheaper)",
+                                   "identical_to_gpu": f"{int((gotw == exp).all(1).sum())}/{n_s}"}
+    finally:
+        vi.close()
+    return out
+
+
 def bench_match(a, dev, local_rank, rank, world, barrier, dist):
     """C2 leg (BASELINE configs[1]): exhaustive descriptor matching of 1000 x 4096 images, descriptors resident in HBM;
     every rank matches its own replica of the pair list (extra leg, not the headline)."""
@@ -735,6 +794,12 @@ def main():
                "identical_to_gpu": f"{same}/{len(idx)}",
                "identical_means": "configuration, inlier and trial counts, E / F / H bit for bit, on matches the oracle computed itself"}
     fm.close()
+    retrieval = None
+    if rank == 0 and a.retrieval_words > 0:
+        try:
+            retrieval = bench_retrieval(a, coll, local_rank, cores, pairs_all)
+        except Exception as e:   # an extra leg must not take the headline line down
+            retrieval = {"error": repr(e)}
     del coll
     torch.cuda.empty_cache()
 
@@ -795,7 +860,7 @@ def main():
                      "timing": "value = pairs / wall time of the K steps between device synchronisations (kernels, chunk "
                                "hand-over, result gather); *_kernel_ms = CUDA-event time of the two stages on their streams, max over ranks",
                      **pl.get("results", {})},
-        "match": match, "verify": verify, "ba": ba, **({"guided": guided} if guided is not None else {}),
+        "retrieval": retrieval, "match": match, "verify": verify, "ba": ba, **({"guided": guided} if guided is not None else {}),
     }), flush=True)
     if world > 1:
         dist.destroy_process_group()

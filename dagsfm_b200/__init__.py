@@ -14,3 +14,4 @@ from .bundle_adjustment import BundleAdjuster, BundleAdjustmentOptions  # noqa: 
 
 __version__ = "0.1"
 from .ba_config import BundleAdjustmentConfig, Reconstruction, pack_problem, unpack_problem  # noqa: F401,E402
+from .retrieval import QueryOptions, VisualIndex, VocabSimilarityGraph, Vocabulary, make_vocabulary  # noqa: F401,E402

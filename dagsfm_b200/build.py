@@ -23,7 +23,7 @@ LIB = PKG / "libdagsfm_b200.so"
 
 COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
           "-Xcompiler", "-fPIC"]
-NO_FMA_PREFIXES = ("verify_", "ba_", "match_guided")
+NO_FMA_PREFIXES = ("verify_", "ba_", "match_guided", "retrieval")
 
 
 def sources() -> list[Path]:

@@ -83,3 +83,42 @@ def candidate_pairs(n_img: int, per_image: int) -> np.ndarray:
     j = i + np.tile(np.arange(1, per_image + 1), n_img)
     ok = j < n_img
     return np.ascontiguousarray(np.stack([i[ok], j[ok]], 1).astype(np.uint32))
+
+
+def make_vocabulary_device(desc, n_words: int, n_train: int = 1 << 20, seed: int = 0):
+    """A synthetic vocabulary for a collection resident on the GPU (torch uint8 [..., 128]); same recipe as
+    retrieval.make_vocabulary (words = sampled descriptors, projection = 64 rows of a random orthogonal matrix,
+    thresholds = per-word medians of the projected training descriptors, embedding only for words with >= 5 of them;
+    inverted_index.h:173-227, inverted_file.h:286-303) with the training assignment done by torch on the device.
+    DATA GENERATOR for tests and benchmarks -- the reference loads pre-trained trees from disk."""
+    import torch
+    from .retrieval import Vocabulary
+    d = desc.reshape(-1, 128)
+    dev = d.device
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    words = d[torch.randperm(len(d), generator=g, device=dev)[:n_words]].contiguous()
+    if len(words) < n_words:
+        words = words[torch.randint(len(words), (n_words,), generator=g, device=dev)]
+    q, _ = torch.linalg.qr(torch.randn((128, 128), generator=g, device=dev, dtype=torch.float64))
+    proj = q.T[:64].to(torch.float32).contiguous()
+    train = d[torch.randperm(len(d), generator=g, device=dev)[:n_train]]
+    wf = words.to(torch.float32)
+    wsq = (wf * wf).sum(1)
+    assign = torch.empty(len(train), dtype=torch.int64, device=dev)
+    for a in range(0, len(train), 8192):                      # integer-valued fp32 products < 2^24: exact
+        x = train[a:a + 8192].to(torch.float32)
+        assign[a:a + 8192] = torch.argmin(wsq[None, :] - 2.0 * (x @ wf.T), dim=1)
+    pd = train.to(torch.float32) @ proj.T                     # [n_train, 64]
+    cnt = torch.bincount(assign, minlength=n_words)
+    start = torch.cumsum(cnt, 0) - cnt
+    thr = torch.zeros((n_words, 64), dtype=torch.float32, device=dev)
+    has = (cnt >= 5)
+    lo = (start + (cnt - 1).clamp_min(0) // 2).clamp_max(max(len(train) - 1, 0))
+    hi = (start + cnt // 2).clamp_max(max(len(train) - 1, 0))
+    for j in range(64):
+        o1 = torch.argsort(pd[:, j], stable=True)
+        o2 = torch.argsort(assign[o1], stable=True)           # grouped by word, ascending value inside a word
+        v = pd[o1[o2], j]
+        thr[:, j] = torch.where(has, 0.5 * (v[lo] + v[hi]), torch.zeros((), device=dev))
+    return Vocabulary(words.cpu().numpy(), proj.cpu().numpy(), thr.cpu().numpy(), has.to(torch.uint8).cpu().numpy())

@@ -403,6 +403,40 @@ int b2_ba_debug_cholesky_solve(b2_ba* h, int64_t D, const double* A, const doubl
 int b2_ba_reprojection_errors(b2_ba* h, const b2_ba_problem* problem, double* point_errors,
                               double* mean_reprojection_error);
 
+/* ======================================================================================================================
+ * Image retrieval: candidate pairs from a vocabulary tree.
+ * Replaces the retrieval loop of VocabSimilarityGraph::Run (src/graph/similarity_graph.cpp:101-200) over
+ * retrieval::VisualIndex<uint8_t, 128, 64> (src/retrieval/visual_index.h): Add for every image, Prepare, Query of every
+ * image with QueryOptions{max_num_images, num_neighbors}; spatial re-ranking (num_images_after_verification, off in
+ * the reference's defaults) is not part of this seam.  The visual words are searched EXACTLY (the reference uses FLANN's
+ * approximate index).  One handle per GPU. */
+typedef struct b2_retrieval b2_retrieval;
+int b2_retrieval_create(int device, b2_retrieval** out);
+int b2_retrieval_destroy(b2_retrieval* r);
+/* The vocabulary as VisualIndex::Read delivers it: words [n_words * 128] (uint8 centroids), the Hamming-embedding
+ * projection [64 * 128] (row-major float, InvertedIndex::proj_matrix_), per-word thresholds [n_words * 64]
+ * (InvertedFile::thresholds_) and has_embedding [n_words] (InvertedFile::status_ & HAS_EMBEDDING).  HOST buffers. */
+int b2_retrieval_set_vocabulary(b2_retrieval* r, int32_t n_words, const uint8_t* words, const float* proj,
+                                const float* thresholds, const uint8_t* has_embedding);
+/* VisualIndex::Add (IndexOptions::num_neighbors = 1) for images 0 .. n_images-1 + Prepare().  descriptors: all images
+ * concatenated [desc_offsets[n_images] * 128]; desc_offsets [n_images + 1] (HOST).  num_neighbors_query (1..8) nearest
+ * words are kept per descriptor for b2_retrieval_query_all (QueryOptions::num_neighbors, 5 in the reference).  The
+ * _device variant reads descriptors already resident in HBM (they must stay valid until the next index call). */
+int b2_retrieval_index_images(b2_retrieval* r, int32_t n_images, const uint8_t* descriptors, const int64_t* desc_offsets,
+                              int32_t num_neighbors_query);
+int b2_retrieval_index_images_device(b2_retrieval* r, int32_t n_images, const uint8_t* descriptors_dev,
+                                     const int64_t* desc_offsets_host, int32_t num_neighbors_query);
+/* VisualIndex::Query of every indexed image: for query image q, out_ids / out_scores [q * max_num_images + k], k <
+ * out_counts[q], sorted by descending score (equal scores: lower image id first); the image itself is among its results,
+ * as in the reference (the caller keeps pairs with image_id < other, similarity_graph.cpp:186-191).  HOST buffers. */
+int b2_retrieval_query_all(b2_retrieval* r, int32_t max_num_images, int32_t* out_ids, float* out_scores, int32_t* out_counts);
+/* Test hooks: nearest words of the indexed descriptors [n_desc * num_neighbors_query]; the inverted index (any pointer may
+ * be NULL): word_start [n_words + 1], per entry image / feature / 64-bit signature, idf [n_words], norm [n_images]. */
+int b2_retrieval_debug_word_ids(b2_retrieval* r, int32_t* out);
+int b2_retrieval_debug_index(b2_retrieval* r, uint32_t* word_start, int32_t* entry_image, int32_t* entry_feature,
+                             uint64_t* entry_bits, float* idf, float* norm);
+int b2_retrieval_last_timing(b2_retrieval* r, double* word_search_s, double* index_build_s, double* query_s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -646,3 +646,66 @@ def _pba_call(L, n, f, k, R, t, cc, prob, xy, n_threads, max_iter, of, ok, oR, o
                   prob["xyz"].ctypes.data, len(prob["obs_img"]), xy.ctypes.data, prob["obs_pt"].ctypes.data,
                   prob["obs_img"].ctypes.data, n_threads, max_iter, of.ctypes.data, ok.ctypes.data, oR.ctypes.data,
                   ot.ctypes.data, st.ctypes.data)
+
+
+# ======================================================================== retrieval (vocabulary tree)
+class RetrievalOracle:
+    """oracle/retrieval_oracle.cc: VisualIndex Add / Prepare / Query with exact word search."""
+
+    def __init__(self, words, proj, thresholds, has_embedding):
+        L = lib()
+        vp = C.c_void_p
+        L.orc_retrieval_create.restype = vp
+        L.orc_retrieval_create.argtypes = [C.c_int, vp, vp, vp, vp]
+        L.orc_retrieval_destroy.argtypes = [vp]
+        L.orc_retrieval_word_ids.argtypes = [vp, C.c_int, vp, C.c_int, vp]
+        L.orc_retrieval_signatures.argtypes = [vp, C.c_int, vp, vp, vp]
+        L.orc_retrieval_add.argtypes = [vp, C.c_int, C.c_int, vp]
+        L.orc_retrieval_prepare.argtypes = [vp]
+        L.orc_retrieval_query.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, vp, vp]
+        L.orc_retrieval_lut.argtypes = [vp, vp]
+        self._w = np.ascontiguousarray(words, np.uint8).reshape(-1, 128)
+        self._p = np.ascontiguousarray(proj, np.float32).reshape(64, 128)
+        self._t = np.ascontiguousarray(thresholds, np.float32).reshape(len(self._w), 64)
+        self._h = np.ascontiguousarray(has_embedding, np.uint8)
+        self._x = vp(L.orc_retrieval_create(len(self._w), self._w.ctypes.data, self._p.ctypes.data, self._t.ctypes.data, self._h.ctypes.data))
+        self._n_images = 0
+
+    def __del__(self):
+        try:
+            lib().orc_retrieval_destroy(self._x)
+        except Exception:
+            pass
+
+    def word_ids(self, desc, k):
+        d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 128)
+        out = np.zeros((len(d), k), np.int32)
+        lib().orc_retrieval_word_ids(self._x, len(d), d.ctypes.data, k, out.ctypes.data)
+        return out
+
+    def signatures(self, desc, word):
+        d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 128)
+        w = np.ascontiguousarray(word, np.int32)
+        out = np.zeros(len(d), np.uint64)
+        lib().orc_retrieval_signatures(self._x, len(d), d.ctypes.data, w.ctypes.data, out.ctypes.data)
+        return out
+
+    def lut(self):
+        out = np.zeros(65, np.float32)
+        lib().orc_retrieval_lut(self._x, out.ctypes.data)
+        return out
+
+    def Add(self, image_id, desc):
+        d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 128)
+        lib().orc_retrieval_add(self._x, int(image_id), len(d), d.ctypes.data)
+        self._n_images += 1
+
+    def Prepare(self):
+        lib().orc_retrieval_prepare(self._x)
+
+    def Query(self, desc, num_neighbors=5, max_num_images=-1):
+        d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 128)
+        ids = np.zeros(max(self._n_images, 1), np.int32)
+        sc = np.zeros(max(self._n_images, 1), np.float32)
+        m = lib().orc_retrieval_query(self._x, len(d), d.ctypes.data, num_neighbors, max_num_images, ids.ctypes.data, sc.ctypes.data)
+        return ids[:m].copy(), sc[:m].copy()

@@ -24,6 +24,7 @@ OUT = Path(os.environ["B2_EMU_BUILD_DIR"]) if os.environ.get("B2_EMU_BUILD_DIR")
 # the translation units of each emulated library (the product's own sources)
 BA_SOURCES = ["common.cu", "match_post.cu", "ba_kernels.cu", "ba_fused.cu", "ba_chol.cu", "ba_iterative.cu", "ba_metrics.cu", "ba_api.cu"]
 VERIFY_SOURCES = ["common.cu", "verify_kernel.cu", "verify_pose.cu", "verify_api.cu"]
+RETRIEVAL_SOURCES = ["common.cu", "match_post.cu", "retrieval.cu"]
 
 
 def _matching(s: str, i: int, open_c: str, close_c: str) -> int:

@@ -372,6 +372,7 @@ inline int any_at(Site at, unsigned m, int p) { return ballot_at(at, m, p) != 0;
 #define __ballot_sync(...) cuda_emu::ballot_at(CUDA_EMU_SITE, __VA_ARGS__)
 #define __any_sync(...) cuda_emu::any_at(CUDA_EMU_SITE, __VA_ARGS__)
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
 inline float __frcp_rn(float x) { return 1.0f / x; }   // correctly rounded on the device too
 inline int __ffs(int v) { return __builtin_ffs(v); }
 inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }

@@ -1,0 +1,80 @@
+"""The retrieval CUDA source (retrieval.cu) compiled for the HOST against tests/cuda_emu/cuda_emu.h and driven through
+the C ABI: nearest words, inverted files and signatures bit for bit against the oracle, idf / normalisation / scores to
+float-summation-order tolerance, the candidate pair list of VocabSimilarityGraph::Run.  TEST of the CUDA code -- the
+product library is not involved."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from tests.retrieval_cases import check_against_oracle, collection
+
+
+@pytest.fixture(scope="module")
+def rmod():
+    from tests.cuda_emu.build_emu import RETRIEVAL_SOURCES, build
+    import dagsfm_b200.retrieval as rm
+    L = C.CDLL(str(build("retrieval", RETRIEVAL_SOURCES)))
+    L.b2_last_error.restype = C.c_char_p
+    saved = (rm.lib, rm.check)
+    rm._bound = False
+
+    def check(rc):
+        if rc != 0:
+            raise RuntimeError(f"emulated library error {rc}: {L.b2_last_error().decode()}")
+    rm.lib = lambda: L
+    rm.check = check
+    yield rm
+    rm.lib, rm.check = saved
+    rm._bound = False
+
+
+@pytest.mark.parametrize("n_img,n_kp,n_words,k", [(10, 96, 40, 5), (6, 64, 200, 3), (5, 40, 7, 1)])
+def test_index_and_query_equal_oracle(rmod, n_img, n_kp, n_words, k):
+    descs, vocab = collection(n_img, n_kp, n_words, seed=3 + n_img, overlap=4)
+    vi = rmod.VisualIndex(0)
+    try:
+        vi.set_vocabulary(vocab)
+        vi.index_images(descs, k)
+        check_against_oracle(vi, descs, vocab, k=k, max_images=4)
+    finally:
+        vi.close()
+
+
+def test_ragged_and_empty_images(rmod):
+    descs, vocab = collection(8, 80, 32, seed=11, overlap=3)
+    descs[2] = descs[2][:0]                   # an image without features: no entries, never retrieved
+    descs[5] = descs[5][:17]
+    vi = rmod.VisualIndex(0)
+    try:
+        vi.set_vocabulary(vocab)
+        vi.index_images(descs, 5)
+        check_against_oracle(vi, descs, vocab, k=5, max_images=8)
+        ids, sc, cnt = vi.query_all(8)
+        assert cnt[2] == 0 and not (ids[:, :][ids >= 0] == 2).any()
+    finally:
+        vi.close()
+
+
+def test_similarity_graph_pairs(rmod):
+    descs, vocab = collection(12, 96, 48, seed=4, overlap=4)
+    g = rmod.VocabSimilarityGraph(vocab, num_images=4, num_nearest_neighbors=5)
+    pairs, scores = g.Run(descs)
+    assert len(pairs) and (pairs[:, 0] < pairs[:, 1]).all() and (scores > 0).all()
+    # neighbouring images (which share scene points) dominate the candidate list
+    assert (np.abs(pairs[:, 0].astype(int) - pairs[:, 1].astype(int)) <= 4).mean() > 0.7
+
+
+def test_argument_errors(rmod):
+    vi = rmod.VisualIndex(0)
+    try:
+        with pytest.raises(RuntimeError):
+            vi.index_images([np.zeros((4, 128), np.uint8)], 5)       # no vocabulary
+        descs, vocab = collection(4, 32, 8, seed=1, overlap=2)
+        vi.set_vocabulary(vocab)
+        with pytest.raises(RuntimeError):
+            vi.index_images(descs, 9)                                 # num_neighbors > 8
+        with pytest.raises(RuntimeError):
+            vi.query_all(3)                                           # nothing indexed
+    finally:
+        vi.close()
