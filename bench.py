@@ -59,6 +59,9 @@ def parse():
                     help="BA leg: linear solver (auto = the reference's rule: ITERATIVE_SCHUR above 1000 images)")
     ap.add_argument("--retrieval-words", type=int, default=32768,
                     help="retrieval leg (candidate pairs from a vocabulary tree over the C3 collection): visual words; 0 = skip")
+    ap.add_argument("--c1", action="store_true",
+                    help="BASELINE configs[0] (the reference's CPU-runnable plumbing case): 100 images x 2048 descriptors, EXHAUSTIVE "
+                         "pairs (4950), match + verify; the CPU leg runs the oracle port on ALL pairs and every result is compared")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -617,7 +620,7 @@ def bench_retrieval(a, coll, local_rank, cores, pairs_all):
             from oracle import pyoracle as orc
             o = orc.RetrievalOracle(vocab.words, vocab.proj, vocab.thresholds, vocab.has_embedding)
             rng = np.random.default_rng(1)
-            n_s = min(64 * cores, n_img * n_kp)
+            n_s = min(12288 * cores, n_img * n_kp)   # ~10 s of exact search on the host cores
             pick = np.sort(rng.choice(n_img * n_kp, n_s, replace=False))
             sample = coll["desc"].reshape(-1, 128)[torch.from_numpy(pick).to(coll["desc"].device)].cpu().numpy()
             t0 = time.perf_counter()
@@ -698,10 +701,14 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     cores = effective_cores()
+    if a.c1:
+        a.seq_images, a.seq_kp, a.seq_cand = 100, 2048, 99      # every successor = the exhaustive pair list
+        a.cpu_sample, a.pairs, a.ba = 4950, -1, ""
+        a.retrieval_words = min(a.retrieval_words, 4096)
     if a.cpu_sample <= 0:
         a.cpu_sample = 24 * cores      # ~10-20 s of host work at ~2 pairs per core-second
     n_cand = a.seq_images * a.seq_cand - a.seq_cand * (a.seq_cand + 1) // 2
-    workload = (f"C3: {a.seq_images} images x {a.seq_kp} keypoints, {a.seq_cand} candidate pairs per image ({n_cand} pairs), "
+    workload = (f"{'C1 (exhaustive pairs)' if a.c1 else 'C3'}: {a.seq_images} images x {a.seq_kp} keypoints, {a.seq_cand} candidate pairs per image ({n_cand} pairs), "
                 f"descriptor match + ratio test + cross check -> E/F/H LO-RANSAC verification, chained on the device")
     cfg = {"workload": workload, "n_images": a.seq_images, "keypoints_per_image": a.seq_kp, "candidates_per_image": a.seq_cand,
            "options": "match: max_ratio 0.8, max_distance 0.7, cross_check 1; verify: reference defaults (max_error 4 px, confidence 0.999, "

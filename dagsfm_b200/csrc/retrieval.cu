@@ -8,10 +8,12 @@
 //   HammingDistWeightFunctor<64, 16>                            src/retrieval/utils.h:52-82
 // The reference runs FLANN's approximate kd-forest per descriptor on the CPU and scores one query image per thread.
 // Here:
-//   word_knn_kernel     EXACT k nearest visual words of every descriptor (integer squared L2 via dp4a; a thread owns a
-//                       descriptor in registers, the word tile is broadcast from shared memory); ties -> lower word id.
-//   index_sig_kernel    Hamming-embedding signature of every indexed descriptor for its nearest word (one warp per
-//                       descriptor, projection matrix transposed in shared memory, bits assembled with two ballots).
+//   word_knn_tc_kernel  (retrieval_tc.cu) EXACT k nearest visual words of every descriptor: descriptor x word contraction on
+//                       tcgen05 (u8 x u8 -> s32, descriptors in TMEM, words streamed by TMA) with a register top-k epilogue on
+//                       2 d.w - |w|^2; ties -> lower word id.  word_knn_kernel (dp4a, below) is the independent SIMT
+//                       statement of the same result, kept as the test seam b2_retrieval_debug_word_ids_simt.
+//   project_kernel      the 64 Hamming-embedding projections of every descriptor (once per descriptor, shared by its words)
+//   index_sig_kernel    signature of every indexed descriptor for its nearest word (thresholds, bits assembled with two ballots).
 //   word histogram -> scan -> scatter -> per-word rank sort by (image, feature): the inverted files as one CSR array,
 //                       deterministic whatever the atomics' order; idf weights, per-image normalisation constants.
 //   query_kernel        one CTA per query image: every (feature, neighbouring word) walks that word's inverted file,
@@ -20,6 +22,7 @@
 // Differences from the reference (both stated in oracle/retrieval_oracle.cc as well): the word search is exact where
 // FLANN is approximate; the projection is summed left to right in float where Eigen picks its own order.  Scores are
 // float sums whose order differs from the reference's (atomics): parity is to 1e-5 relative, not bitwise.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -33,13 +36,15 @@
 
 namespace b2 {
 cudaError_t launch_scan_u32(const uint32_t* in, int64_t n, uint32_t* out, uint32_t* total, cudaStream_t s);
+cudaError_t launch_word_knn_tc(const CUtensorMap& tmap_words, const uint8_t* desc, long long n_desc, const int* word_sq,
+                               uint32_t n_blk, int k, int32_t* out, int n_sm, cudaStream_t stream);   // retrieval_tc.cu
 
 namespace rt {
 
 constexpr int kDim = 128, kEmb = 64, kMaxHamming = 24, kMaxK = 8;
 constexpr int kInvalidWord = 0x7fffffff;
 
-struct Entry { int32_t image, feature; unsigned long long bits; };
+struct __align__(16) Entry { int32_t image, feature; unsigned long long bits; };
 
 // ------------------------------------------------------------------ exact k nearest words
 constexpr int kKnnThreads = 128, kWordTile = 64;
@@ -86,12 +91,14 @@ __global__ void __launch_bounds__(kKnnThreads) word_knn_kernel(const uint8_t* __
       const int dist = dsq + tile_sq[w] - 2 * (int)dot;  // exact: every term < 2^24
       if (dist < bd[K - 1]) {  // strict: an equal distance keeps the earlier (lower) word id
         int cd = dist, cw = w0 + w;
+        bool placed = false;  // once the new word has its slot, everything behind it moves down one (equal distances keep their order)
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-          if (cd < bd[k]) {
+          if (placed || cd < bd[k]) {
             const int td = bd[k], tw = bw[k];
             bd[k] = cd; bw[k] = cw;
             cd = td; cw = tw;
+            placed = true;
           }
         }
       }
@@ -103,26 +110,43 @@ __global__ void __launch_bounds__(kKnnThreads) word_knn_kernel(const uint8_t* __
   }
 }
 
-__global__ void word_norms_kernel(const uint8_t* __restrict__ words, int n_words, int32_t* __restrict__ sq) {
+__global__ void word_norms_kernel(const uint8_t* __restrict__ words, int n_words, int n_pad, int32_t* __restrict__ sq) {
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= n_words) return;
+  if (w >= n_pad) return;
+  if (w >= n_words) { sq[w] = 0x7fffffff; return; }  // padding rows of the tensor-core blocks: never a nearest word
   int s = 0;
   for (int j = 0; j < kDim; ++j) { const int v = words[(size_t)w * kDim + j]; s += v * v; }
   sq[w] = s;
 }
 
 // ------------------------------------------------------------------ Hamming embedding
-// projT: [128][64] (transposed projection) in shared memory.  Lane l computes projections l and l + 32 of one descriptor,
-// summing left to right in float (mul, then add: this file is compiled with --fmad=false).
-__device__ __forceinline__ void project(const float* __restrict__ projT, const uint8_t* __restrict__ d, int lane, float* lo, float* hi) {
-  float s0 = 0.0f, s1 = 0.0f;
-  for (int j = 0; j < kDim; ++j) {
-    const float x = (float)d[j];
-    s0 += projT[j * kEmb + lane] * x;
-    s1 += projT[j * kEmb + lane + 32] * x;
+// project_kernel: P[f][i] = sum_j proj[i][j] * d_f[j] for the descriptors of a batch of images, one warp per descriptor,
+// lane l computes rows l and l + 32, summing left to right in float (mul, then add: this file is compiled with
+// --fmad=false) -- the projection of a descriptor does not depend on the visual word, only the thresholds do, so it is
+// computed once per descriptor and shared by its num_neighbors signatures.  projT: [128][64] (transposed) in shared memory.
+constexpr int kProjWarps = 8;
+__global__ void __launch_bounds__(32 * kProjWarps) project_kernel(const uint8_t* __restrict__ desc, int64_t f0, int64_t f1, const float* __restrict__ proj,
+                                                                  float* __restrict__ out) {
+  __shared__ float projT[kDim * kEmb];
+  for (int e = threadIdx.x; e < kDim * kEmb; e += blockDim.x) projT[(e % kDim) * kEmb + e / kDim] = proj[e];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  for (int64_t f = f0 + blockIdx.x * (int64_t)kProjWarps + (threadIdx.x >> 5); f < f1; f += (int64_t)gridDim.x * kProjWarps) {
+    const uint32_t* d4 = reinterpret_cast<const uint32_t*>(desc + f * kDim);
+    float s0 = 0.0f, s1 = 0.0f;
+    for (int j4 = 0; j4 < kDim / 4; ++j4) {
+      const uint32_t v = d4[j4];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const float x = (float)((v >> (8 * b)) & 0xffu);
+        const int j = 4 * j4 + b;
+        s0 += projT[j * kEmb + lane] * x;
+        s1 += projT[j * kEmb + lane + 32] * x;
+      }
+    }
+    out[(f - f0) * kEmb + lane] = s0;
+    out[(f - f0) * kEmb + lane + 32] = s1;
   }
-  *lo = s0;
-  *hi = s1;
 }
 __device__ __forceinline__ unsigned long long signature_bits(float lo, float hi, const float* __restrict__ thr, int lane) {
   const unsigned b0 = __ballot_sync(0xffffffffu, lo > thr[lane]);
@@ -130,19 +154,16 @@ __device__ __forceinline__ unsigned long long signature_bits(float lo, float hi,
   return (unsigned long long)b0 | ((unsigned long long)b1 << 32);
 }
 
+// Signature of every indexed descriptor of the batch for its nearest word + the per-word entry counts (one warp per descriptor).
 constexpr int kSigWarps = 8;
-__global__ void __launch_bounds__(32 * kSigWarps) index_sig_kernel(const uint8_t* __restrict__ desc, int64_t n, const int32_t* __restrict__ nn, int nn_stride,
-                                                                   const float* __restrict__ proj, const float* __restrict__ thr,
-                                                                   const int32_t* __restrict__ feat_image, const int32_t* __restrict__ feat_index,
-                                                                   uint32_t* __restrict__ word_count, Entry* __restrict__ staged) {
-  __shared__ float projT[kDim * kEmb];
-  for (int e = threadIdx.x; e < kDim * kEmb; e += blockDim.x) projT[(e % kDim) * kEmb + e / kDim] = proj[e];
-  __syncthreads();
+__global__ void __launch_bounds__(32 * kSigWarps) index_sig_kernel(const float* __restrict__ P, int64_t f0, int64_t f1, const int32_t* __restrict__ nn, int nn_stride,
+                                                                   const float* __restrict__ thr, const int32_t* __restrict__ feat_image,
+                                                                   const int32_t* __restrict__ feat_index, uint32_t* __restrict__ word_count,
+                                                                   Entry* __restrict__ staged) {
   const int lane = threadIdx.x & 31;
-  for (int64_t f = blockIdx.x * (int64_t)kSigWarps + (threadIdx.x >> 5); f < n; f += (int64_t)gridDim.x * kSigWarps) {
+  for (int64_t f = f0 + blockIdx.x * (int64_t)kSigWarps + (threadIdx.x >> 5); f < f1; f += (int64_t)gridDim.x * kSigWarps) {
     const int w = nn[f * nn_stride];
-    float lo, hi;
-    project(projT, desc + f * kDim, lane, &lo, &hi);
+    const float lo = P[(f - f0) * kEmb + lane], hi = P[(f - f0) * kEmb + lane + 32];
     const unsigned long long bits = (w == kInvalidWord) ? 0ull : signature_bits(lo, hi, thr + (size_t)w * kEmb, lane);
     if (lane == 0) {
       Entry e;
@@ -211,11 +232,12 @@ __global__ void __launch_bounds__(256) image_norm_kernel(const int32_t* __restri
 
 // ------------------------------------------------------------------ query
 struct QueryArgs {
-  const uint8_t* desc;        // query descriptors (all query images, concatenated)
-  const int64_t* q_off;       // [n_query + 1]
+  const float* P;             // projections of the batch's descriptors [(f - f_base) * 64]
+  int64_t f_base;
+  const int64_t* q_off;       // [n_images + 1] descriptor offsets of all images
+  int q0, q1;                 // query images of this launch
   const int32_t* nn;          // [n_desc * K] nearest words of the query descriptors
   int K;
-  const float* proj;
   const float* thr;
   const uint8_t* has_emb;
   const float* idf;
@@ -231,27 +253,31 @@ struct QueryArgs {
   float* score_scratch;       // [gridDim.x * n_index_images] when the score array does not fit shared memory, else null
 };
 
+// One CTA per query image.  A warp takes a feature and, for each of its K words, streams the word's inverted file 32
+// entries at a time (one coalesced 512-byte load); lane l weighs entry l.  Entries are sorted by image, so the entries of
+// one image form a run: the lane at the head of a run sums it IN ENTRY ORDER (shuffles inside the chunk, plain loads if it
+// runs past the chunk's end -- the lanes of the next chunk that continue it are skipped), applies the burstiness
+// normalisation and adds the vote to the image's score in shared memory.
 constexpr int kQueryThreads = 256;
-__global__ void __launch_bounds__(kQueryThreads) query_kernel(QueryArgs A, int n_query, int scores_in_smem) {
-  extern __shared__ float q_smem[];  // projT [128 * 64] | scores [n_index_images] (when they fit) | hit flags
-  float* projT = q_smem;
+__global__ void __launch_bounds__(kQueryThreads) query_kernel(QueryArgs A, int scores_in_smem) {
+  extern __shared__ float q_smem[];  // scores [n_index_images] (when they fit) | hit flags
   __shared__ double s_self[kQueryThreads / 32];
   __shared__ float s_best[kQueryThreads];
   __shared__ int s_besti[kQueryThreads];
+  __shared__ float s_lut[kEmb + 1];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = A.n_index_images;
-  float* scores = scores_in_smem ? q_smem + kDim * kEmb : A.score_scratch + (size_t)blockIdx.x * N;
-  uint8_t* hit = reinterpret_cast<uint8_t*>(q_smem + kDim * kEmb + (scores_in_smem ? N : 0));
-  for (int e = tid; e < kDim * kEmb; e += kQueryThreads) projT[(e % kDim) * kEmb + e / kDim] = A.proj[e];
-  for (int q = blockIdx.x; q < n_query; q += gridDim.x) {
+  float* scores = scores_in_smem ? q_smem : A.score_scratch + (size_t)blockIdx.x * N;
+  uint8_t* hit = reinterpret_cast<uint8_t*>(q_smem + (scores_in_smem ? N : 0));
+  if (tid <= kEmb) s_lut[tid] = A.lut[tid];
+  for (int q = A.q0 + blockIdx.x; q < A.q1; q += gridDim.x) {
     __syncthreads();
     for (int e = tid; e < N; e += kQueryThreads) { scores[e] = 0.0f; hit[e] = 0; }
     __syncthreads();
     const int64_t f0 = A.q_off[q], f1 = A.q_off[q + 1];
     double self = 0.0;
     for (int64_t f = f0 + warp; f < f1; f += kQueryThreads / 32) {
-      float lo, hi;
-      project(projT, A.desc + f * kDim, lane, &lo, &hi);
+      const float lo = A.P[(f - A.f_base) * kEmb + lane], hi = A.P[(f - A.f_base) * kEmb + lane + 32];
       for (int k = 0; k < A.K; ++k) {
         const int w = A.nn[f * A.K + k];
         if (w == kInvalidWord) continue;
@@ -260,29 +286,49 @@ __global__ void __launch_bounds__(kQueryThreads) query_kernel(QueryArgs A, int n
         const uint32_t s = A.word_start[w], e = A.word_start[w + 1];
         if (!A.has_emb[w] || e == s) continue;  // InvertedFile::IsUsable
         const unsigned long long bits = signature_bits(lo, hi, A.thr + (size_t)w * kEmb, lane);
-        // lanes take contiguous chunks of the file; a run of one image belongs to the lane in whose chunk it STARTS
-        const uint32_t len = e - s, chunk = (len + 31) / 32;
-        uint32_t a = s + lane * chunk;
-        const uint32_t a_end = min(e, a + chunk);
-        if (a < a_end && a > s) {  // skip the tail of a run that began in the previous chunk
-          const int prev = A.entries[a - 1].image;
-          while (a < e && A.entries[a].image == prev) ++a;
-        }
-        while (a < a_end) {
-          const int img = A.entries[a].image;
-          float sc = 0.0f;
-          int votes = 0;
-          while (a < e && A.entries[a].image == img) {  // may run past a_end: the run is this lane's
-            const int hd = __popcll(bits ^ A.entries[a].bits);
-            if (hd <= kMaxHamming) { sc += A.lut[hd]; votes += 1; }
-            ++a;
+        int carry_img = -1;  // image of the previous chunk's last entry
+        for (uint32_t base = s; base < e; base += 32) {
+          const uint32_t a = base + lane;
+          const bool valid = a < e;
+          int img = -2 - lane;  // padding lanes: distinct, equal to no image
+          float wgt = 0.0f;
+          int vote = 0;
+          if (valid) {
+            const uint4 raw = *reinterpret_cast<const uint4*>(A.entries + a);
+            img = (int)raw.x;
+            const unsigned long long eb = (unsigned long long)raw.z | ((unsigned long long)raw.w << 32);
+            const int hd = __popcll(bits ^ eb);
+            if (hd <= kMaxHamming) { wgt = s_lut[hd]; vote = 1; }
           }
-          if (votes > 0) {
+          int prev = __shfl_up_sync(0xffffffffu, img, 1);
+          if (lane == 0) prev = carry_img;
+          const bool head = valid && img != prev;
+          float sc = wgt;
+          int votes = vote;
+          for (int step = 1; step < 32; ++step) {
+            const int oi = __shfl_down_sync(0xffffffffu, img, step);
+            const float ow = __shfl_down_sync(0xffffffffu, wgt, step);
+            const int ov = __shfl_down_sync(0xffffffffu, vote, step);
+            const bool ext = head && lane + step < 32 && oi == img;
+            if (ext) { sc += ow; votes += ov; }
+            if (!__any_sync(0xffffffffu, ext)) break;
+          }
+          const int last_img = __shfl_sync(0xffffffffu, img, 31);
+          if (head && img == last_img) {  // the run may continue behind the chunk: it stays this lane's
+            for (uint32_t b = base + 32; b < e; ++b) {
+              const uint4 raw = *reinterpret_cast<const uint4*>(A.entries + b);
+              if ((int)raw.x != img) break;
+              const int hd = __popcll(bits ^ ((unsigned long long)raw.z | ((unsigned long long)raw.w << 32)));
+              if (hd <= kMaxHamming) { sc += s_lut[hd]; votes += 1; }
+            }
+          }
+          if (head && votes > 0) {
             float v = sc / sqrtf((float)votes);
             v *= sq;
             atomicAdd(scores + img, v);
             hit[img] = 1;
           }
+          carry_img = last_img;
         }
       }
     }
@@ -339,8 +385,10 @@ struct b2_retrieval {
   int device = 0, n_sm = 148;
   cudaStream_t stream = nullptr;
   int n_words = 0;
-  uint8_t* d_words = nullptr;
-  int32_t* d_word_sq = nullptr;
+  uint8_t* d_words = nullptr;   // [n_blk * 128][128], rows >= n_words zero
+  int32_t* d_word_sq = nullptr; // [n_blk * 128], INT_MAX at the padding rows
+  uint32_t n_blk = 0;
+  CUtensorMap tmap_words;
   float *d_proj = nullptr, *d_thr = nullptr, *d_idf = nullptr, *d_norm = nullptr, *d_lut = nullptr;
   uint8_t* d_has = nullptr;
   uint32_t* d_word_start = nullptr;  // [n_words + 1]
@@ -354,6 +402,9 @@ struct b2_retrieval {
   int64_t n_desc = 0;
   int32_t* d_nn = nullptr;  // [n_desc * nn_k]
   int nn_k = 0;
+  float* d_P = nullptr;        // projections of one batch of images' descriptors [batch_desc * 64]
+  size_t p_floats = 0;
+  std::vector<int64_t> h_img_off;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   double last_seconds[3] = {0, 0, 0};  // word search, index build, query
 };
@@ -361,7 +412,8 @@ struct b2_retrieval {
 namespace {
 template <class T> void fr(T*& p) { if (p) cudaFree(p); p = nullptr; }
 
-int knn(b2_retrieval* r, const uint8_t* d_desc, int64_t n, int k, int32_t* d_out) {
+// SIMT statement of the word search (test seam)
+int knn_simt(b2_retrieval* r, const uint8_t* d_desc, int64_t n, int k, int32_t* d_out) {
   if (n == 0) return B2_OK;
   const unsigned g = (unsigned)((n + rt::kKnnThreads - 1) / rt::kKnnThreads);
   cudaStream_t s = r->stream;
@@ -377,6 +429,69 @@ int knn(b2_retrieval* r, const uint8_t* d_desc, int64_t n, int k, int32_t* d_out
   }
   B2_CUDA(cudaGetLastError());
   count_launches(1);
+  return B2_OK;
+}
+int knn(b2_retrieval* r, const uint8_t* d_desc, int64_t n, int k, int32_t* d_out) {
+  if (n == 0) return B2_OK;
+  B2_CUDA(launch_word_knn_tc(r->tmap_words, d_desc, (long long)n, r->d_word_sq, r->n_blk, k, d_out, r->n_sm, r->stream));
+  count_launches(1);
+  return B2_OK;
+}
+
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// [rows][128] uint8, box 128 rows x 128 bytes, SWIZZLE_128B (one K-major operand block of the contraction)
+int make_words_tmap(CUtensorMap* tm, void* base, uint64_t rows) {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || !p) return set_error(B2_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+    fn = reinterpret_cast<PFN_tmapEncodeTiled>(p);
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)rt::kDim, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)rt::kDim};
+  const cuuint32_t box[2] = {(cuuint32_t)rt::kDim, 128u};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult res = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (res != CUDA_SUCCESS) return set_error(B2_ERR_CUDA, "cuTensorMapEncodeTiled failed for the word pool");
+  return B2_OK;
+}
+
+// Image batches whose descriptors' projections fit the projection buffer (<= kProjBudget bytes); a batch holds at least
+// one image.  Returns the image boundaries.
+constexpr size_t kProjBudget = (size_t)2 << 30;
+std::vector<int> image_batches(const std::vector<int64_t>& off) {
+  std::vector<int> b{0};
+  const int64_t cap = (int64_t)(kProjBudget / (rt::kEmb * 4));
+  const int n = (int)off.size() - 1;
+  int i = 0;
+  while (i < n) {
+    int j = i + 1;
+    while (j < n && off[j + 1] - off[i] <= cap) ++j;
+    b.push_back(j);
+    i = j;
+  }
+  return b;
+}
+int project_batch(b2_retrieval* r, int64_t f0, int64_t f1) {
+  const size_t need = (size_t)std::max<int64_t>(f1 - f0, 1) * rt::kEmb;
+  if (need > r->p_floats) {
+    fr(r->d_P);
+    r->p_floats = 0;
+    B2_CUDA(cudaMalloc(&r->d_P, need * 4));
+    r->p_floats = need;
+  }
+  if (f1 > f0) {
+    const int64_t warps = f1 - f0;
+    const int grid = (int)std::min<int64_t>((warps + rt::kProjWarps - 1) / rt::kProjWarps, (int64_t)r->n_sm * 8);
+    rt::project_kernel<<<grid, 32 * rt::kProjWarps, 0, r->stream>>>(r->d_desc, f0, f1, r->d_proj, r->d_P);
+    B2_CUDA(cudaGetLastError());
+    count_launches(1);
+  }
   return B2_OK;
 }
 }  // namespace
@@ -404,7 +519,7 @@ int b2_retrieval_destroy(b2_retrieval* r) {
   cudaSetDevice(r->device);
   if (r->stream) cudaStreamSynchronize(r->stream);
   fr(r->d_words); fr(r->d_word_sq); fr(r->d_proj); fr(r->d_thr); fr(r->d_idf); fr(r->d_norm); fr(r->d_lut); fr(r->d_has);
-  fr(r->d_word_start); fr(r->d_entries); fr(r->d_img_off); fr(r->d_nn);
+  fr(r->d_word_start); fr(r->d_entries); fr(r->d_img_off); fr(r->d_nn); fr(r->d_P);
   if (r->own_desc) fr(r->d_desc);
   if (r->ev0) cudaEventDestroy(r->ev0);
   if (r->ev1) cudaEventDestroy(r->ev1);
@@ -420,8 +535,12 @@ int b2_retrieval_set_vocabulary(b2_retrieval* r, int32_t n_words, const uint8_t*
   cudaStream_t s = r->stream;
   fr(r->d_words); fr(r->d_word_sq); fr(r->d_proj); fr(r->d_thr); fr(r->d_idf); fr(r->d_lut); fr(r->d_has); fr(r->d_word_start);
   r->n_words = n_words;
-  B2_CUDA(cudaMalloc(&r->d_words, (size_t)n_words * rt::kDim));
-  B2_CUDA(cudaMalloc(&r->d_word_sq, (size_t)n_words * 4));
+  r->n_blk = (uint32_t)((n_words + 127) / 128);
+  const size_t pad_rows = (size_t)r->n_blk * 128;
+  B2_CUDA(cudaMalloc(&r->d_words, pad_rows * rt::kDim));
+  B2_CUDA(cudaMalloc(&r->d_word_sq, pad_rows * 4));
+  B2_CUDA(cudaMemsetAsync(r->d_words, 0, pad_rows * rt::kDim, s));
+  B2_TRY(make_words_tmap(&r->tmap_words, r->d_words, pad_rows));
   B2_CUDA(cudaMalloc(&r->d_proj, rt::kEmb * rt::kDim * 4));
   B2_CUDA(cudaMalloc(&r->d_thr, (size_t)n_words * rt::kEmb * 4));
   B2_CUDA(cudaMalloc(&r->d_idf, (size_t)n_words * 4));
@@ -438,7 +557,7 @@ int b2_retrieval_set_vocabulary(b2_retrieval* r, int32_t n_words, const uint8_t*
     lut[n] = h <= (float)rt::kMaxHamming ? std::exp(-h * h / 256.0f) : 0.0f;
   }
   B2_CUDA(cudaMemcpyAsync(r->d_lut, lut, sizeof lut, cudaMemcpyHostToDevice, s));
-  rt::word_norms_kernel<<<(n_words + 255) / 256, 256, 0, s>>>(r->d_words, n_words, r->d_word_sq);
+  rt::word_norms_kernel<<<(unsigned)((pad_rows + 255) / 256), 256, 0, s>>>(r->d_words, n_words, (int)pad_rows, r->d_word_sq);
   B2_CUDA(cudaGetLastError());
   count_launches(1);
   B2_CUDA(cudaStreamSynchronize(s));
@@ -490,9 +609,18 @@ static int index_impl(b2_retrieval* r, int32_t n_images, const uint8_t* d_desc, 
   B2_CUDA(cudaEventCreate(&e2));
   B2_CUDA(cudaEventCreate(&e3));
   B2_CUDA(cudaEventRecord(e2, s));
+  r->h_img_off.assign(desc_off_host, desc_off_host + n_images + 1);
   if (n > 0) {
-    rt::index_sig_kernel<<<r->n_sm * 4, 32 * rt::kSigWarps, 0, s>>>(r->d_desc, n, r->d_nn, k_query, r->d_proj, r->d_thr, d_fimg, d_fidx, d_count, d_staged);
-    B2_CUDA(cudaGetLastError());
+    const std::vector<int> bat = image_batches(r->h_img_off);
+    for (size_t b = 0; b + 1 < bat.size(); ++b) {
+      const int64_t f0 = r->h_img_off[bat[b]], f1 = r->h_img_off[bat[b + 1]];
+      if (f1 == f0) continue;
+      B2_TRY(project_batch(r, f0, f1));
+      const int grid = (int)std::min<int64_t>((f1 - f0 + rt::kSigWarps - 1) / rt::kSigWarps, (int64_t)r->n_sm * 8);
+      rt::index_sig_kernel<<<grid, 32 * rt::kSigWarps, 0, s>>>(r->d_P, f0, f1, r->d_nn, k_query, r->d_thr, d_fimg, d_fidx, d_count, d_staged);
+      B2_CUDA(cudaGetLastError());
+      count_launches(1);
+    }
   }
   uint32_t* d_total = d_count + r->n_words;  // the scan writes the grand total behind the last count's slot
   B2_CUDA(launch_scan_u32(d_count, r->n_words, r->d_word_start, d_total, s));
@@ -509,7 +637,7 @@ static int index_impl(b2_retrieval* r, int32_t n_images, const uint8_t* d_desc, 
   } else {
     B2_CUDA(cudaMemsetAsync(r->d_idf, 0, (size_t)r->n_words * 4, s));
   }
-  count_launches(5);
+  count_launches(4);
   B2_CUDA(cudaEventRecord(e3, s));
   B2_CUDA(cudaStreamSynchronize(s));
   float ms = 0;
@@ -555,22 +683,30 @@ int b2_retrieval_query_all(b2_retrieval* r, int32_t max_num_images, int32_t* out
   B2_CUDA(cudaMalloc(&d_cnt, (size_t)Q * 4));
   B2_CUDA(cudaMemsetAsync(d_ids, 0xff, (size_t)Q * max_num_images * 4, s));
   B2_CUDA(cudaMemsetAsync(d_sc, 0, (size_t)Q * max_num_images * 4, s));
-  const size_t base = (size_t)rt::kDim * rt::kEmb * 4;
-  const size_t with_scores = base + (size_t)N * 4 + (size_t)N + 16;
+  const size_t with_scores = (size_t)N * 4 + (size_t)N + 16;
   const bool in_smem = with_scores <= 200 * 1024;
-  const size_t smem = in_smem ? with_scores : base + (size_t)N + 16;
-  const int grid = std::min(Q, r->n_sm * (in_smem && with_scores > 100 * 1024 ? 1 : 2));
+  const size_t smem = in_smem ? with_scores : (size_t)N + 16;
+  int ctas_per_sm = (int)std::min<size_t>(6, (220 * 1024) / (smem + 4 * 1024));
+  if (ctas_per_sm < 1) ctas_per_sm = 1;
+  const int max_grid = r->n_sm * ctas_per_sm;
   float* d_scratch = nullptr;
-  if (!in_smem) B2_CUDA(cudaMalloc(&d_scratch, (size_t)grid * N * 4));
+  if (!in_smem) B2_CUDA(cudaMalloc(&d_scratch, (size_t)max_grid * N * 4));
   B2_CUDA(cudaFuncSetAttribute(rt::query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   rt::QueryArgs A;
-  A.desc = r->d_desc; A.q_off = r->d_img_off; A.nn = r->d_nn; A.K = r->nn_k; A.proj = r->d_proj; A.thr = r->d_thr; A.has_emb = r->d_has;
+  A.q_off = r->d_img_off; A.nn = r->d_nn; A.K = r->nn_k; A.thr = r->d_thr; A.has_emb = r->d_has;
   A.idf = r->d_idf; A.word_start = r->d_word_start; A.entries = r->d_entries; A.norm = r->d_norm; A.lut = r->d_lut; A.n_index_images = N;
   A.max_num_images = max_num_images; A.out_ids = d_ids; A.out_scores = d_sc; A.out_count = d_cnt; A.score_scratch = d_scratch;
   B2_CUDA(cudaEventRecord(r->ev0, s));
-  rt::query_kernel<<<grid, rt::kQueryThreads, smem, s>>>(A, Q, in_smem ? 1 : 0);
-  B2_CUDA(cudaGetLastError());
-  count_launches(1);
+  const std::vector<int> bat = image_batches(r->h_img_off);
+  for (size_t b = 0; b + 1 < bat.size(); ++b) {
+    const int64_t f0 = r->h_img_off[bat[b]], f1 = r->h_img_off[bat[b + 1]];
+    B2_TRY(project_batch(r, f0, f1));
+    A.P = r->d_P; A.f_base = f0; A.q0 = bat[b]; A.q1 = bat[b + 1];
+    const int grid = std::min(bat[b + 1] - bat[b], max_grid);
+    rt::query_kernel<<<grid, rt::kQueryThreads, smem, s>>>(A, in_smem ? 1 : 0);
+    B2_CUDA(cudaGetLastError());
+    count_launches(1);
+  }
   B2_CUDA(cudaEventRecord(r->ev1, s));
   B2_CUDA(cudaMemcpyAsync(out_ids, d_ids, (size_t)Q * max_num_images * 4, cudaMemcpyDeviceToHost, s));
   B2_CUDA(cudaMemcpyAsync(out_scores, d_sc, (size_t)Q * max_num_images * 4, cudaMemcpyDeviceToHost, s));
@@ -589,6 +725,18 @@ int b2_retrieval_debug_word_ids(b2_retrieval* r, int32_t* out) {
   B2_CUDA(cudaSetDevice(r->device));
   B2_CUDA(cudaMemcpy(out, r->d_nn, (size_t)r->n_desc * r->nn_k * 4, cudaMemcpyDeviceToHost));
   return B2_OK;
+}
+int b2_retrieval_debug_word_ids_simt(b2_retrieval* r, int32_t* out) {
+  if (!r || !out || !r->d_nn) return set_error(B2_ERR_INVALID, "bad argument");
+  B2_CUDA(cudaSetDevice(r->device));
+  int32_t* tmp = nullptr;
+  B2_CUDA(cudaMalloc(&tmp, std::max<size_t>((size_t)r->n_desc * r->nn_k, 1) * 4));
+  int rc = knn_simt(r, r->d_desc, r->n_desc, r->nn_k, tmp);
+  if (rc == B2_OK && cudaStreamSynchronize(r->stream) != cudaSuccess) rc = set_error(B2_ERR_CUDA, "word search (SIMT seam) failed");
+  if (rc == B2_OK && cudaMemcpy(out, tmp, (size_t)r->n_desc * r->nn_k * 4, cudaMemcpyDeviceToHost) != cudaSuccess)
+    rc = set_error(B2_ERR_CUDA, "copy failed");
+  cudaFree(tmp);
+  return rc;
 }
 int b2_retrieval_debug_index(b2_retrieval* r, uint32_t* word_start, int32_t* entry_image, int32_t* entry_feature, uint64_t* entry_bits, float* idf,
                              float* norm) {

@@ -31,6 +31,8 @@ struct b2_verifier {
   // per-call
   uint8_t* d_scratch = nullptr;
   size_t scratch_bytes = 0;
+  uint8_t *d_state = nullptr, *d_masks = nullptr;   // inter-stage pair state and inlier masks (verify_kernel.cu)
+  size_t state_bytes = 0, mask_bytes = 0;
   unsigned long long* d_counter = nullptr;
   int* d_err = nullptr;
   int* d_maxm = nullptr;
@@ -66,6 +68,9 @@ int check_options(const b2_two_view_options* o) {
   return B2_OK;
 }
 
+// Pairs per launch group: bounds the inter-stage state (3.8 KB per pair) whatever the size of the call.
+constexpr int64_t kStageBatch = 65536;
+
 int run_device(b2_verifier* v, int64_t n_pairs, const uint32_t* pairs, const int64_t* off, const uint32_t* matches,
                const b2_two_view_options* opt, const uint32_t* seeds, b2_two_view_result* results, uint32_t* inl) {
   B2_TRY(check_options(opt));
@@ -73,17 +78,26 @@ int run_device(b2_verifier* v, int64_t n_pairs, const uint32_t* pairs, const int
   if (n_pairs == 0) return B2_OK;
   B2_CUDA(cudaSetDevice(v->device));
   cudaStream_t s = v->stream;
-  // largest match list of the call sizes the per-warp scratch
+  // largest match list of the call sizes the per-warp scratch; the match offsets at the batch boundaries size the masks
   B2_CUDA(cudaMemsetAsync(v->d_maxm, 0, sizeof(int), s));
   max_matches_kernel<<<64, 256, 0, s>>>(off, n_pairs, v->d_maxm);
   B2_CUDA(cudaGetLastError());
   int m_cap = 0;
   B2_CUDA(cudaMemcpyAsync(&m_cap, v->d_maxm, sizeof(int), cudaMemcpyDeviceToHost, s));
+  const int64_t n_batches = (n_pairs + kStageBatch - 1) / kStageBatch;
+  std::vector<int64_t> bound((size_t)n_batches + 1);
+  for (int64_t b = 0; b <= n_batches; ++b)
+    B2_CUDA(cudaMemcpyAsync(&bound[(size_t)b], off + std::min(b * kStageBatch, n_pairs), sizeof(int64_t), cudaMemcpyDeviceToHost, s));
   B2_CUDA(cudaStreamSynchronize(s));
   m_cap = std::max(m_cap, 32);
+  int64_t max_span = 0;
+  for (int64_t b = 0; b < n_batches; ++b) {
+    if (bound[(size_t)b + 1] < bound[(size_t)b]) return set_error(B2_ERR_INVALID, "match offsets are not ascending");
+    max_span = std::max(max_span, bound[(size_t)b + 1] - bound[(size_t)b]);
+  }
   const int wpb = verify_warps_per_block();
   int blocks = v->n_sm * verify_blocks_per_sm();  // resident blocks only, dynamic work counter
-  blocks = (int)std::min<int64_t>(blocks, (n_pairs + wpb - 1) / wpb);
+  blocks = (int)std::min<int64_t>(blocks, (std::min(n_pairs, kStageBatch) + wpb - 1) / wpb);
   const size_t stride = verify_scratch_stride(m_cap);
   // bound the scratch (large match lists -> fewer concurrent warps)
   const size_t budget = (size_t)8 << 30;
@@ -96,7 +110,22 @@ int run_device(b2_verifier* v, int64_t n_pairs, const uint32_t* pairs, const int
     B2_CUDA(cudaMalloc(&v->d_scratch, need));
     v->scratch_bytes = need;
   }
-  B2_CUDA(cudaMemsetAsync(v->d_counter, 0, sizeof(unsigned long long), s));
+  const size_t state_need = (size_t)std::min(n_pairs, kStageBatch) * sizeof(VerifyPairState);
+  if (state_need > v->state_bytes) {
+    if (v->d_state) cudaFree(v->d_state);
+    v->d_state = nullptr;
+    v->state_bytes = 0;
+    B2_CUDA(cudaMalloc(&v->d_state, state_need));
+    v->state_bytes = state_need;
+  }
+  const size_t mask_need = 3 * (size_t)std::max<int64_t>(max_span, 1);
+  if (mask_need > v->mask_bytes) {
+    if (v->d_masks) cudaFree(v->d_masks);
+    v->d_masks = nullptr;
+    v->mask_bytes = 0;
+    B2_CUDA(cudaMalloc(&v->d_masks, mask_need));
+    v->mask_bytes = mask_need;
+  }
   B2_CUDA(cudaMemsetAsync(v->d_err, 0, sizeof(int), s));
   VerifyArgs a;
   a.cams = v->d_cams;
@@ -104,18 +133,17 @@ int run_device(b2_verifier* v, int64_t n_pairs, const uint32_t* pairs, const int
   a.n_images = v->n_images;
   a.xy = (const double2*)v->d_xy;
   a.nxy = (const double2*)v->d_nxy;
-  a.n_pairs = n_pairs;
-  a.pairs = pairs;
-  a.match_off = off;
   a.matches = matches;
-  a.seeds = seeds;
   a.opt = *opt;
-  a.results = results;
   a.inlier_out = inl;
   a.scratch = v->d_scratch;
   a.scratch_stride = stride;
   a.m_cap = m_cap;
+  a.max_workers = blocks * wpb;
   a.work_counter = v->d_counter;
+  a.state = (VerifyPairState*)v->d_state;
+  a.masks = v->d_masks;
+  a.mask_stride = std::max<int64_t>(max_span, 1);
   a.err = v->d_err;
   a.prof = nullptr;
   unsigned long long* d_prof = nullptr;
@@ -125,9 +153,20 @@ int run_device(b2_verifier* v, int64_t n_pairs, const uint32_t* pairs, const int
     a.prof = d_prof;
   }
   B2_CUDA(cudaEventRecord(v->ev0, s));
-  B2_CUDA(launch_verify_pairs(a, blocks, s));
+  for (int64_t b = 0; b < n_batches; ++b) {
+    const int64_t p0 = b * kStageBatch, p1 = std::min(n_pairs, p0 + kStageBatch);
+    a.n_pairs = p1 - p0;
+    a.pairs = pairs + 2 * p0;
+    a.match_off = off + p0;
+    a.seeds = seeds + p0;
+    a.results = results + p0;
+    a.mask_base = bound[(size_t)b];
+    B2_CUDA(cudaMemsetAsync(v->d_counter, 0, 4 * sizeof(unsigned long long), s));
+    B2_CUDA(launch_verify_pairs(a, v->n_sm, s));
+    count_launches(4);
+  }
   B2_CUDA(cudaEventRecord(v->ev1, s));
-  count_launches(2);
+  count_launches(1);
   int err = 0;
   B2_CUDA(cudaMemcpyAsync(&err, v->d_err, sizeof(int), cudaMemcpyDeviceToHost, s));
   B2_CUDA(cudaStreamSynchronize(s));
@@ -193,7 +232,7 @@ int b2_verify_create(int device, b2_verifier** out) {
   v->n_sm = prop.multiProcessorCount;
   const int rc = [&]() -> int {
     B2_CUDA(cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking));
-    B2_CUDA(cudaMalloc(&v->d_counter, sizeof(unsigned long long)));
+    B2_CUDA(cudaMalloc(&v->d_counter, 4 * sizeof(unsigned long long)));
     B2_CUDA(cudaMalloc(&v->d_err, sizeof(int)));
     B2_CUDA(cudaMalloc(&v->d_maxm, sizeof(int)));
     B2_CUDA(cudaEventCreate(&v->ev0));
@@ -213,7 +252,7 @@ int b2_verify_destroy(b2_verifier* v) {
   cudaSetDevice(v->device);
   if (v->stream) cudaStreamSynchronize(v->stream);
   auto fr = [](void* p) { if (p) cudaFree(p); };
-  fr(v->d_cams); fr(v->d_img_off); fr(v->d_xy); fr(v->d_nxy); fr(v->d_scratch); fr(v->d_counter);
+  fr(v->d_cams); fr(v->d_img_off); fr(v->d_xy); fr(v->d_nxy); fr(v->d_scratch); fr(v->d_state); fr(v->d_masks); fr(v->d_counter);
   fr(v->d_err); fr(v->d_maxm); fr(v->d_stage); fr(v->d_angles);
   if (v->ev0) cudaEventDestroy(v->ev0);
   if (v->ev1) cudaEventDestroy(v->ev1);

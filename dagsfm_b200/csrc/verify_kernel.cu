@@ -23,7 +23,9 @@
 
 #include <cfloat>
 #include <cstdint>
+#include <algorithm>
 #include <cstdlib>
+#include <cstring>
 
 #include "../../include/dagsfm_b200.h"
 #include "verify_common.cuh"
@@ -143,11 +145,6 @@ __device__ __forceinline__ double residual_t(const double* M, double2 a, double2
   if (TYPE == EST_T2) return translation_res(M, a.x, a.y, b.x, b.y);
   return sampson(M, a.x, a.y, b.x, b.y);
 }
-__device__ __forceinline__ double residual(int type, const double* M, double2 a, double2 b) {
-  if (type == EST_H4) return residual_t<EST_H4>(M, a, b);
-  if (type == EST_T2) return residual_t<EST_T2>(M, a, b);
-  return residual_t<EST_F7>(M, a, b);
-}
 
 // Support counts of up to four hypotheses in one pass over the matches: the counts are pure
 // functions of (model, points), so they can be taken ahead of the ordered replay; four independent
@@ -197,30 +194,26 @@ __device__ __noinline__ void score_group(const double2* __restrict__ P1, const d
   }
   __syncwarp();
 }
-__device__ __forceinline__ void score_group_any(int type, const double2* P1, const double2* P2, int M,
-                                                const double* models, const uint16_t* ids, int n, double max_res,
-                                                int lane, int* cnt_out) {
-  constexpr int G = kGroup;
-  if (type == EST_H4) score_group<EST_H4, G>(P1, P2, M, models, ids, n, max_res, lane, cnt_out);
-  else if (type == EST_T2) score_group<EST_T2, G>(P1, P2, M, models, ids, n, max_res, lane, cnt_out);
-  else score_group<EST_F7, G>(P1, P2, M, models, ids, n, max_res, lane, cnt_out);
-}
+// E and F share the Sampson residual: one instantiation serves both
+template <int TYPE> struct ResidualOf { static constexpr int value = (TYPE == EST_H4 || TYPE == EST_T2) ? TYPE : EST_F7; };
 
 // InlierSupportMeasurer::Evaluate, count only (all lanes return the same value).
-__device__ __noinline__ int score_count(int type, const double2* P1, const double2* P2, int M, const double* model, double max_res,
+template <int TYPE>
+__device__ __noinline__ int score_count(const double2* P1, const double2* P2, int M, const double* model, double max_res,
                            int lane) {
   int cnt = 0;
   for (int i0 = 0; i0 < M; i0 += 32) {
     const int i = i0 + lane;
     bool in = false;
-    if (i < M) in = residual(type, model, P1[i], P2[i]) <= max_res;
+    if (i < M) in = residual_t<TYPE>(model, P1[i], P2[i]) <= max_res;
     cnt += __popc(__ballot_sync(kFull, in));
   }
   return cnt;
 }
 // ... and its residual_sum: a sequential FP64 sum in index order (support_measurement.cc:43-46);
 // optionally writes the inlier mask.  Needed only on ties and for a new best.
-__device__ __noinline__ double score_sum(int type, const double2* P1, const double2* P2, int M, const double* model, double max_res,
+template <int TYPE>
+__device__ __noinline__ double score_sum(const double2* P1, const double2* P2, int M, const double* model, double max_res,
                             int lane, uint8_t* mask_out) {
   double sum = 0;
   for (int i0 = 0; i0 < M; i0 += 32) {
@@ -228,7 +221,7 @@ __device__ __noinline__ double score_sum(int type, const double2* P1, const doub
     bool in = false;
     double r = 0;
     if (i < M) {
-      r = residual(type, model, P1[i], P2[i]);
+      r = residual_t<TYPE>(model, P1[i], P2[i]);
       in = r <= max_res;
       if (mask_out) mask_out[i] = in ? 1 : 0;
     }
@@ -453,7 +446,8 @@ __device__ __forceinline__ double2 apply_T(const double* T, double2 p) {
 
 // Local estimator on the N inliers listed in inl[]; writes models (<= 10 x 9) to `models`
 // (global scratch, visible to all lanes) and returns the count (uniform).
-__device__ __noinline__ int local_estimate(int type, const double2* P1, const double2* P2, const uint32_t* inl, int N, double* G,
+template <int type>
+__device__ __noinline__ int local_estimate(const double2* P1, const double2* P2, const uint32_t* inl, int N, double* G,
                               int ld, WarpShared& sh, double* sig_sh, double* models, int lane) {
   if (type == EST_T2) {  // translation_transform.h:84-102: mean_dst - mean_src, sums in index order
     if (lane == 0) {
@@ -537,7 +531,7 @@ struct RansacResult {
 };
 
 struct Scratch {
-  double2 *px1, *px2, *nx1, *nx2;  // matched points, pixel / normalised   [Mcap]
+  double2 *px1, *px2;              // matched points of the stage (normalised for E, pixel for F / H)   [Mcap]
   double2 *ip1, *ip2;              // inlier pixel points (watermark)       [Mcap]
   uint32_t* idx;                   // sampler's persistent index vector     [Mcap]
   uint32_t* inl;                   // inlier index list                     [Mcap]
@@ -545,14 +539,13 @@ struct Scratch {
   int ld;
   double* models;                  // [32][10][9] per-lane sample models
   double* lomodels;                // [10][9] local models
-  uint8_t* mask[3];                // E, F, H inlier masks                  [Mcap]
   uint8_t* tmask;                  // scratch mask
   unsigned long long* prof;        // optional cycle counters
 };
 
 // LORANSAC::Estimate for one estimator over the matched points (P1,P2)[0..M).
-template <int VAR>
-__device__ __noinline__ void ransac_warp(int type, const double2* P1, const double2* P2, int M, double max_error,
+template <int type, int GS>
+__device__ __noinline__ void ransac_warp(const double2* P1, const double2* P2, int M, double max_error,
                             double min_inlier_ratio, double confidence, long long min_num_trials,
                             long long max_num_trials_opt, WarpShared& sh, double* sig_sh, const Scratch& sc,
                             uint8_t* mask_out, RansacResult* out, int lane, LaneView ws) {
@@ -666,9 +659,8 @@ __device__ __noinline__ void ransac_warp(int type, const double2* P1, const doub
       }
       if ((j & 7) == 0) {  // support counts of the next eight trials' hypotheses
         const int g1 = sh.off[min(j + 8, 32)];
-        constexpr int GS = kGroup;
         for (int g = sh.off[j]; g < g1; g += GS)
-          score_group_any(type, P1, P2, M, sc.models, sh.flat + g, min(GS, g1 - g), max_residual, lane, sh.cnt);
+          score_group<ResidualOf<type>::value, GS>(P1, P2, M, sc.models, sh.flat + g, min(GS, g1 - g), max_residual, lane, sh.cnt);
       }
       const int nm = sh.nm[j];
       for (int mi = 0; mi < nm; ++mi) {
@@ -678,7 +670,7 @@ __device__ __noinline__ void ransac_warp(int type, const double2* P1, const doub
         double model[9];
         if (cnt >= best_count) {  // the hypothesis itself is only needed from here on (most trials stop at the count)
           for (int k = 0; k < 9; ++k) model[k] = sc.models[(size_t)j * 90 + 9 * mi + k];
-          sum = score_sum(type, P1, P2, M, model, max_residual, lane, sc.tmask);
+          sum = score_sum<ResidualOf<type>::value>(P1, P2, M, model, max_residual, lane, sc.tmask);
           sum = __shfl_sync(kFull, sum, 0);
           if (cnt == best_count) better = sum < best_sum;
         }
@@ -699,12 +691,11 @@ __device__ __noinline__ void ransac_warp(int type, const double2* P1, const doub
             }
             __syncwarp();
             const long long cl0 = clock64();
-            const int nlm = local_estimate(type, P1, P2, sc.inl, N, sc.G, sc.ld, sh, sig_sh, sc.lomodels, lane);
+            const int nlm = local_estimate<type>(P1, P2, sc.inl, N, sc.G, sc.ld, sh, sig_sh, sc.lomodels, lane);
             lo_cycles += clock64() - cl0;
-            constexpr int GL = kGroup;
-            for (int g = 0; g < nlm; g += GL)
-              score_group_any(type, P1, P2, M, sc.lomodels, sh.lo_ids + g, min(GL, nlm - g), max_residual, lane,
-                              sh.lo_cnt);
+            for (int g = 0; g < nlm; g += GS)
+              score_group<ResidualOf<type>::value, GS>(P1, P2, M, sc.lomodels, sh.lo_ids + g, min(GS, nlm - g), max_residual, lane,
+                                                       sh.lo_cnt);
             for (int li = 0; li < nlm; ++li) {
               double lm[9];
               for (int k = 0; k < 9; ++k) lm[k] = sc.lomodels[9 * li + k];
@@ -712,7 +703,7 @@ __device__ __noinline__ void ransac_warp(int type, const double2* P1, const doub
               bool lbetter = lc > best_count;
               double lsum = 0;
               if (lc >= best_count) {
-                lsum = score_sum(type, P1, P2, M, lm, max_residual, lane, nullptr);
+                lsum = score_sum<ResidualOf<type>::value>(P1, P2, M, lm, max_residual, lane, nullptr);
                 lsum = __shfl_sync(kFull, lsum, 0);
                 if (lc == best_count) lbetter = lsum < best_sum;
               }
@@ -750,7 +741,7 @@ __device__ __noinline__ void ransac_warp(int type, const double2* P1, const doub
   for (int k = 0; k < 9; ++k) out->model[k] = best_model[k];
   if (best_count < kmin) return;
   out->success = true;
-  score_sum(type, P1, P2, M, best_model, max_residual, lane, mask_out);
+  score_sum<ResidualOf<type>::value>(P1, P2, M, best_model, max_residual, lane, mask_out);
   __syncwarp();
 }
 
@@ -827,20 +818,39 @@ __device__ __forceinline__ bool in_box(double2 p, double minx, double maxx, doub
   return p.x >= minx && p.x <= maxx && p.y >= miny && p.y <= maxy;
 }
 
-// ------------------------------------------------------------------ main kernel
-
-// Launch shapes (threads per CTA, CTAs per SM -> registers per thread), B2_VERIFY_VARIANT selects one for the A/B:
-//   0  256 x 1   8 warps / SM, 255 registers   production (measured fastest, profiles/README.md session 5)
-//   1  256 x 2  16 warps / SM, 128 registers   twice the warps, but the solvers and the RANSAC driver spill
-//   2  128 x 3  12 warps / SM, 168 registers
-//   3  128 x 2   8 warps / SM, 255 registers   the production register budget in smaller CTAs
-struct Shape { int threads, blocks_per_sm; };
-__host__ __device__ constexpr Shape shape_of(int var) {
-  return var == 1 ? Shape{256, 2} : var == 2 ? Shape{128, 3} : var == 3 ? Shape{128, 2} : Shape{256, 1};
+// ------------------------------------------------------------------ staged kernels
+// TwoViewGeometry::Estimate of a pair is four sequential steps on one PRNG stream -- the E, F and H LORANSACs, then the
+// decision with the inlier extraction and the watermark test -- and each step is its own kernel over all pairs of the
+// call: STAGE 0 seeds the pair's mt19937 and runs the E estimator (calibrated pairs), 1 = F, 2 = H, 3 = decision.  The
+// pair's PRNG state (mt vector, FIFO of drawn-but-returned outputs), the three RANSAC reports and the three inlier masks
+// travel between the kernels through HBM (VerifyPairState, ~3.8 KB per pair).  Per pair the operations and their order
+// are those of the single-kernel formulation (round 1), so the results are bit-identical; what changes is that every
+// warp on the chip runs the SAME estimator at any time: the instruction footprint of a launch is one solver + one
+// residual instead of all of them (the single kernel spent more issue slots waiting for instructions than for data,
+// profiles/r2_verify_*), and each stage gets its own register budget / CTAs per SM (BPS) and hypotheses per scoring pass.
+__device__ __forceinline__ void prng_save(const WarpShared& sh, VerifyPairState& st, int lane) {
+  for (int i = lane; i < 624; i += 32) st.mt[i] = sh.mt[i];
+  for (int i = lane; i < 256; i += 32) st.ring[i] = sh.ring[i];
+  if (lane == 0) { st.mti = sh.mti; st.w = sh.w; st.r = sh.r; }
 }
-template <int VAR>
-__global__ void __launch_bounds__(shape_of(VAR).threads, shape_of(VAR).blocks_per_sm)
-verify_pairs_kernel(VerifyArgs A) {
+__device__ __forceinline__ void prng_load(WarpShared& sh, const VerifyPairState& st, int lane) {
+  for (int i = lane; i < 624; i += 32) sh.mt[i] = st.mt[i];
+  for (int i = lane; i < 256; i += 32) sh.ring[i] = st.ring[i];
+  if (lane == 0) { sh.mti = st.mti; sh.w = st.w; sh.r = st.r; sh.r0 = st.r; }
+}
+__device__ __forceinline__ void report_store(VerifyRansacReport& d, const RansacResult& r, int lane) {
+  if (lane == 0) {
+    d.success = r.success ? 1 : 0;
+    d.num_inliers = r.num_inliers;
+    d.num_trials = r.num_trials;
+    for (int k = 0; k < 9; ++k) d.model[k] = r.model[k];
+  }
+}
+
+__host__ __device__ constexpr int stage_group(int bps) { return bps >= 2 ? 2 : kGroup; }
+
+template <int STAGE, int BPS>
+__global__ void __launch_bounds__(kThreads, BPS) verify_stage_kernel(VerifyArgs A) {
   extern __shared__ double warp_sh[];  // WarpShared[kWarpsPerBlock]
   double lane_work[kLaneWorkDoubles];
   const LaneView ws{lane_work};
@@ -848,15 +858,12 @@ verify_pairs_kernel(VerifyArgs A) {
   WarpShared& sh = reinterpret_cast<WarpShared*>(warp_sh)[wib];
   double* sig_sh = sh.sig;
   const int worker = blockIdx.x * (int)(blockDim.x >> 5) + wib;
-  // carve this worker's scratch
   Scratch sc;
   {
     uint8_t* base = A.scratch + (size_t)worker * A.scratch_stride;
     const size_t mc = (size_t)A.m_cap;
     sc.px1 = (double2*)base; base += mc * 16;
     sc.px2 = (double2*)base; base += mc * 16;
-    sc.nx1 = (double2*)base; base += mc * 16;
-    sc.nx2 = (double2*)base; base += mc * 16;
     sc.ip1 = (double2*)base; base += mc * 16;
     sc.ip2 = (double2*)base; base += mc * 16;
     sc.G = (double*)base; base += mc * 2 * 9 * 8;
@@ -865,65 +872,78 @@ verify_pairs_kernel(VerifyArgs A) {
     sc.lomodels = (double*)base; base += 90 * 8;
     sc.idx = (uint32_t*)base; base += mc * 4;
     sc.inl = (uint32_t*)base; base += mc * 4;
-    sc.mask[0] = base; base += mc;
-    sc.mask[1] = base; base += mc;
-    sc.mask[2] = base; base += mc;
     sc.tmask = base;
     sc.prof = A.prof;
   }
   const b2_two_view_options& o = A.opt;
+  constexpr int GS = stage_group(BPS);
   if (lane == 0) sh.overflow = 0;
   __syncwarp();
   for (;;) {
     long long p = 0;
-    if (lane == 0) p = (long long)atomicAdd(A.work_counter, 1ull);
+    if (lane == 0) p = (long long)atomicAdd(A.work_counter + STAGE, 1ull);
     p = __shfl_sync(kFull, p, 0);
     if (p >= A.n_pairs) break;
     const uint32_t i1 = A.pairs[2 * p], i2 = A.pairs[2 * p + 1];
     const int64_t moff = A.match_off[p];
     const int M = (int)(A.match_off[p + 1] - moff);
+    const bool invalid = i1 >= (uint32_t)A.n_images || i2 >= (uint32_t)A.n_images || M > A.m_cap;
+    // DEGENERATE before any estimator runs (two_view_geometry.cc:298-301)
+    const bool skip = invalid || (unsigned long long)M < (unsigned long long)o.min_num_inliers;
+    VerifyPairState& st = A.state[p];
+    uint8_t* const masks = A.masks + (moff - A.mask_base);   // [3][mask_stride], this pair's slice at +moff
+    if (STAGE < 3) {
+      if (skip) continue;
+      const b2_camera c1 = A.cams[i1], c2 = A.cams[i2];
+      const bool calibrated = c1.has_prior_focal_length && c2.has_prior_focal_length;
+      const uint32_t* mt = A.matches + 2 * moff;
+      const int64_t o1 = A.img_off[i1], o2 = A.img_off[i2];
+      const double2* src = (STAGE == 0) ? A.nxy : A.xy;   // E works on normalised points, F and H on pixels
+      if (STAGE == 0) {
+        if (lane == 0) mt_seed(sh, A.seeds[p]);
+      } else {
+        prng_load(sh, st, lane);
+      }
+      const bool run = STAGE != 0 || calibrated;
+      if (run)
+        for (int i = lane; i < M; i += 32) {
+          sc.px1[i] = src[o1 + mt[2 * i]];
+          sc.px2[i] = src[o2 + mt[2 * i + 1]];
+        }
+      __syncwarp();
+      RansacResult R;
+      R.success = false; R.num_inliers = 0; R.num_trials = 0; R.residual_sum = 0;
+      for (int k = 0; k < 9; ++k) R.model[k] = 0.0;
+      if (run) {
+        double err = o.max_error;
+        if (STAGE == 0) err = (image_to_world_threshold(c1, o.max_error) + image_to_world_threshold(c2, o.max_error)) / 2;
+        constexpr int TYPE = STAGE == 0 ? EST_E5 : STAGE == 1 ? EST_F7 : EST_H4;
+        ransac_warp<TYPE, GS>(sc.px1, sc.px2, M, err, o.min_inlier_ratio, o.confidence, o.min_num_trials, o.max_num_trials,
+                              sh, sig_sh, sc, masks + (size_t)STAGE * A.mask_stride, &R, lane, ws);
+      }
+      report_store(st.report[STAGE], R, lane);
+      __syncwarp();
+      prng_save(sh, st, lane);
+      if (lane == 0 && sh.overflow) atomicExch(A.err, 2);
+      __syncwarp();
+      continue;
+    }
+    // ------------------------------------------------------------- STAGE 3: the decision
     b2_two_view_result res;
     res.config = 0;
     res.n_inliers = 0;
     res.E_num_inliers = res.F_num_inliers = res.H_num_inliers = 0;
     res.E_num_trials = res.F_num_trials = res.H_num_trials = 0;
     for (int k = 0; k < 9; ++k) res.E[k] = res.F[k] = res.H[k] = 0.0;
-    bool done = false;
-    if (i1 >= (uint32_t)A.n_images || i2 >= (uint32_t)A.n_images || M > A.m_cap) {
-      if (lane == 0) atomicExch(A.err, 1);
+    if (invalid && lane == 0) atomicExch(A.err, 1);
+    if (skip) {
       res.config = 1;
-      done = true;
-    }
-    if (!done && (unsigned long long)M < (unsigned long long)o.min_num_inliers) {
-      res.config = 1;  // DEGENERATE (two_view_geometry.cc:298-301)
-      done = true;
-    }
-    if (!done) {
+    } else {
       const b2_camera c1 = A.cams[i1], c2 = A.cams[i2];
       const bool calibrated = c1.has_prior_focal_length && c2.has_prior_focal_length;
       const uint32_t* mt = A.matches + 2 * moff;
       const int64_t o1 = A.img_off[i1], o2 = A.img_off[i2];
-      for (int i = lane; i < M; i += 32) {
-        const uint32_t a = mt[2 * i], b = mt[2 * i + 1];
-        sc.px1[i] = A.xy[o1 + a];
-        sc.px2[i] = A.xy[o2 + b];
-        sc.nx1[i] = A.nxy[o1 + a];
-        sc.nx2[i] = A.nxy[o2 + b];
-      }
-      if (lane == 0) mt_seed(sh, A.seeds[p]);
-      __syncwarp();
-      RansacResult E, F, H;
-      E.success = false; E.num_inliers = 0; E.num_trials = 0;
-      for (int k = 0; k < 9; ++k) E.model[k] = 0.0;
-      if (calibrated) {
-        const double e_err = (image_to_world_threshold(c1, o.max_error) + image_to_world_threshold(c2, o.max_error)) / 2;
-        ransac_warp<VAR>(EST_E5, sc.nx1, sc.nx2, M, e_err, o.min_inlier_ratio, o.confidence, o.min_num_trials,
-                    o.max_num_trials, sh, sig_sh, sc, sc.mask[0], &E, lane, ws);
-      }
-      ransac_warp<VAR>(EST_F7, sc.px1, sc.px2, M, o.max_error, o.min_inlier_ratio, o.confidence, o.min_num_trials,
-                  o.max_num_trials, sh, sig_sh, sc, sc.mask[1], &F, lane, ws);
-      ransac_warp<VAR>(EST_H4, sc.px1, sc.px2, M, o.max_error, o.min_inlier_ratio, o.confidence, o.min_num_trials,
-                  o.max_num_trials, sh, sig_sh, sc, sc.mask[2], &H, lane, ws);
+      const VerifyRansacReport E = st.report[0], F = st.report[1], H = st.report[2];
       for (int k = 0; k < 9; ++k) { res.E[k] = E.model[k]; res.F[k] = F.model[k]; res.H[k] = H.model[k]; }
       res.E_num_inliers = E.num_inliers; res.F_num_inliers = F.num_inliers; res.H_num_inliers = H.num_inliers;
       res.E_num_trials = (int)E.num_trials; res.F_num_trials = (int)F.num_trials; res.H_num_trials = (int)H.num_trials;
@@ -976,7 +996,7 @@ verify_pairs_kernel(VerifyArgs A) {
       }
       if (best >= 0 && res.config != 1) {
         // ExtractInlierMatches (two_view_geometry.cc:54-66) in match order
-        const uint8_t* mk = sc.mask[best];
+        const uint8_t* mk = masks + (size_t)best * A.mask_stride;
         uint32_t* outm = A.inlier_out + 2 * moff;
         int N = 0, nb_border = 0;
         const double d1 = sqrt((double)(c1.width * c1.width + c1.height * c1.height));
@@ -990,11 +1010,13 @@ verify_pairs_kernel(VerifyArgs A) {
           bool border = false;
           if (in) {
             const int pos = N + __popc(bm & ((1u << lane) - 1));
-            outm[2 * pos] = mt[2 * i];
-            outm[2 * pos + 1] = mt[2 * i + 1];
-            sc.ip1[pos] = sc.px1[i];
-            sc.ip2[pos] = sc.px2[i];
-            border = !in_box(sc.px1[i], minx1, maxx1, minx1, maxy1) && !in_box(sc.px2[i], minx2, maxx2, minx2, maxy2);
+            const uint32_t a = mt[2 * i], b = mt[2 * i + 1];
+            const double2 q1 = A.xy[o1 + a], q2 = A.xy[o2 + b];
+            outm[2 * pos] = a;
+            outm[2 * pos + 1] = b;
+            sc.ip1[pos] = q1;
+            sc.ip2[pos] = q2;
+            border = !in_box(q1, minx1, maxx1, minx1, maxy1) && !in_box(q2, minx2, maxx2, minx2, maxy2);
           }
           nb_border += __popc(__ballot_sync(kFull, border));
           N += __popc(bm);
@@ -1005,9 +1027,11 @@ verify_pairs_kernel(VerifyArgs A) {
           // DetectWatermark (:491-555); num_inliers is the report's count (== N when the mask is valid)
           const double ratio = (double)nb_border / (double)num_inliers;
           if (!(ratio < o.watermark_min_inlier_ratio)) {
+            prng_load(sh, st, lane);
+            __syncwarp();
             RansacResult T;
-            ransac_warp<VAR>(EST_T2, sc.ip1, sc.ip2, (int)num_inliers, o.max_error, o.watermark_min_inlier_ratio,
-                        o.confidence, o.min_num_trials, o.max_num_trials, sh, sig_sh, sc, sc.tmask, &T, lane, ws);
+            ransac_warp<EST_T2, kGroup>(sc.ip1, sc.ip2, (int)num_inliers, o.max_error, o.watermark_min_inlier_ratio,
+                                        o.confidence, o.min_num_trials, o.max_num_trials, sh, sig_sh, sc, sc.tmask, &T, lane, ws);
             const double inlier_ratio = (double)T.num_inliers / (double)num_inliers;
             if (inlier_ratio >= o.watermark_min_inlier_ratio) res.config = 7;
           }
@@ -1022,6 +1046,7 @@ verify_pairs_kernel(VerifyArgs A) {
   }
 }
 
+
 // ----------------------------------------------------------------- test seams
 __global__ void score_models_kernel(int type, int n, const double2* P1, const double2* P2, int n_models,
                                     const double* models, double max_res, int* counts, double* sums, uint8_t* masks) {
@@ -1030,8 +1055,12 @@ __global__ void score_models_kernel(int type, int n, const double2* P1, const do
   if (w >= n_models) return;
   double model[9];
   for (int k = 0; k < 9; ++k) model[k] = models[9 * w + k];
-  const int c = score_count(type, P1, P2, n, model, max_res, lane);
-  double s = score_sum(type, P1, P2, n, model, max_res, lane, masks + (size_t)w * n);
+  int c;
+  double s;
+  uint8_t* mk = masks + (size_t)w * n;
+  if (type == EST_H4) { c = score_count<EST_H4>(P1, P2, n, model, max_res, lane); s = score_sum<EST_H4>(P1, P2, n, model, max_res, lane, mk); }
+  else if (type == EST_T2) { c = score_count<EST_T2>(P1, P2, n, model, max_res, lane); s = score_sum<EST_T2>(P1, P2, n, model, max_res, lane, mk); }
+  else { c = score_count<EST_F7>(P1, P2, n, model, max_res, lane); s = score_sum<EST_F7>(P1, P2, n, model, max_res, lane, mk); }
   s = __shfl_sync(kFull, s, 0);
   if (lane == 0) {
     counts[w] = c;
@@ -1068,14 +1097,16 @@ __global__ void debug_solve_kernel(int type, int n, const double2* P1, const dou
   if (type == 3) {  // F 8-point local estimator on all n points
     for (int i = lane; i < n; i += 32) inl[i] = i;
     __syncwarp();
-    const int nm = local_estimate(EST_F7, P1, P2, inl, n, G, 2 * n, sh, sig, models, lane);
+    const int nm = local_estimate<EST_F7>(P1, P2, inl, n, G, 2 * n, sh, sig, models, lane);
     if (lane == 0) *n_models = nm;
     return;
   }
   if (type <= 2 && n > min_samples(type)) {  // local estimators E5 / H on n points
     for (int i = lane; i < n; i += 32) inl[i] = i;
     __syncwarp();
-    const int nm = local_estimate(type, P1, P2, inl, n, G, 2 * n, sh, sig, models, lane);
+    const int nm = type == EST_E5 ? local_estimate<EST_E5>(P1, P2, inl, n, G, 2 * n, sh, sig, models, lane)
+                 : type == EST_F7 ? local_estimate<EST_F7>(P1, P2, inl, n, G, 2 * n, sh, sig, models, lane)
+                                  : local_estimate<EST_H4>(P1, P2, inl, n, G, 2 * n, sh, sig, models, lane);
     if (lane == 0) *n_models = nm;
     return;
   }
@@ -1099,16 +1130,23 @@ __global__ void debug_solve_kernel(int type, int n, const double2* P1, const dou
 // ---------------------------------------------------------------- launchers
 size_t verify_scratch_stride(int m_cap) {
   const size_t mc = (size_t)m_cap;
-  size_t b = mc * 16 * 6 + mc * 2 * 9 * 8 + 32 * 90 * 8 + 90 * 8 + mc * 4 * 2 + mc * 4;
+  size_t b = mc * 16 * 4 + mc * 2 * 9 * 8 + 32 * 90 * 8 + 90 * 8 + mc * 4 * 2 + mc;
   return (b + 255) / 256 * 256;
 }
-static int verify_variant() {
-  const char* venv = getenv("B2_VERIFY_VARIANT");
-  const int v = venv ? atoi(venv) : 0;
-  return (v >= 0 && v <= 3) ? v : 0;
+// CTAs per SM of the E, F and H stages (1 -> 255 registers, 4 hypotheses per scoring pass; 2 -> 128 registers, 2 per pass).
+// B2_VERIFY_BPS = three digits selects them for an A/B; the default is the measured-fastest setting.
+void verify_stage_shapes(int bps[3]) {
+  bps[0] = 1; bps[1] = 1; bps[2] = 1;
+  const char* e = getenv("B2_VERIFY_BPS");
+  if (e && strlen(e) == 3)
+    for (int k = 0; k < 3; ++k) bps[k] = e[k] == '2' ? 2 : 1;
 }
-int verify_warps_per_block() { return vf::shape_of(verify_variant()).threads / 32; }
-int verify_blocks_per_sm() { return vf::shape_of(verify_variant()).blocks_per_sm; }
+int verify_warps_per_block() { return vf::kWarpsPerBlock; }
+int verify_blocks_per_sm() {   // the largest stage sizes the per-warp scratch
+  int b[3];
+  verify_stage_shapes(b);
+  return std::max(b[0], std::max(b[1], b[2]));
+}
 
 cudaError_t launch_normalize_points(const b2_camera* cams, const int64_t* img_off, int n_images, const double* xy,
                                     double* nxy, int64_t n_total, cudaStream_t s) {
@@ -1117,23 +1155,30 @@ cudaError_t launch_normalize_points(const b2_camera* cams, const int64_t* img_of
       cams, img_off, n_images, (const double2*)xy, (double2*)nxy, n_total);
   return cudaGetLastError();
 }
-template <int VAR>
-static cudaError_t launch_verify_shape(const VerifyArgs& a, int n_blocks, cudaStream_t s) {
-  constexpr vf::Shape sh = vf::shape_of(VAR);
-  const size_t dyn = sizeof(vf::WarpShared) * (sh.threads / 32);
-  cudaError_t e = cudaFuncSetAttribute(vf::verify_pairs_kernel<VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+template <int STAGE, int BPS>
+static cudaError_t launch_stage(const VerifyArgs& a, int n_sm, cudaStream_t s) {
+  const size_t dyn = vf::kDynSmemBytes;
+  cudaError_t e = cudaFuncSetAttribute(vf::verify_stage_kernel<STAGE, BPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
   if (e != cudaSuccess) return e;
-  vf::verify_pairs_kernel<VAR><<<n_blocks, sh.threads, dyn, s>>>(a);
+  int blocks = n_sm * BPS;   // resident CTAs only: the pairs are handed out by the stage's work counter
+  blocks = (int)std::min<int64_t>(blocks, (a.n_pairs + vf::kWarpsPerBlock - 1) / vf::kWarpsPerBlock);
+  blocks = std::min(blocks, a.max_workers / vf::kWarpsPerBlock);
+  if (blocks < 1) blocks = 1;
+  vf::verify_stage_kernel<STAGE, BPS><<<blocks, vf::kThreads, dyn, s>>>(a);
   return cudaGetLastError();
 }
-// n_blocks is sized by the caller from verify_blocks_per_sm() / verify_warps_per_block()
-cudaError_t launch_verify_pairs(const VerifyArgs& a, int n_blocks, cudaStream_t s) {
-  switch (verify_variant()) {
-    case 1: return launch_verify_shape<1>(a, n_blocks, s);
-    case 2: return launch_verify_shape<2>(a, n_blocks, s);
-    case 3: return launch_verify_shape<3>(a, n_blocks, s);
-    default: return launch_verify_shape<0>(a, n_blocks, s);
-  }
+// The four stages of one call, in stream order (work_counter[0..3] and err cleared by the caller).
+cudaError_t launch_verify_pairs(const VerifyArgs& a, int n_sm, cudaStream_t s) {
+  int bps[3];
+  verify_stage_shapes(bps);
+  cudaError_t e;
+  e = bps[0] == 2 ? launch_stage<0, 2>(a, n_sm, s) : launch_stage<0, 1>(a, n_sm, s);
+  if (e != cudaSuccess) return e;
+  e = bps[1] == 2 ? launch_stage<1, 2>(a, n_sm, s) : launch_stage<1, 1>(a, n_sm, s);
+  if (e != cudaSuccess) return e;
+  e = bps[2] == 2 ? launch_stage<2, 2>(a, n_sm, s) : launch_stage<2, 1>(a, n_sm, s);
+  if (e != cudaSuccess) return e;
+  return launch_stage<3, 1>(a, n_sm, s);
 }
 cudaError_t launch_score_models(int type, int n, const double* p1, const double* p2, int n_models, const double* models,
                                 double max_res, int* counts, double* sums, uint8_t* masks, cudaStream_t s) {

@@ -28,6 +28,7 @@ def _L():
         L.b2_retrieval_index_images_device.argtypes = [vp, i32, vp, vp, i32]
         L.b2_retrieval_query_all.argtypes = [vp, i32, vp, vp, vp]
         L.b2_retrieval_debug_word_ids.argtypes = [vp, vp]
+        L.b2_retrieval_debug_word_ids_simt.argtypes = [vp, vp]
         L.b2_retrieval_debug_index.argtypes = [vp, vp, vp, vp, vp, vp, vp]
         L.b2_retrieval_last_timing.argtypes = [vp, P(C.c_double), P(C.c_double), P(C.c_double)]
         _bound = True
@@ -133,6 +134,11 @@ class VisualIndex:
     def debug_word_ids(self) -> np.ndarray:
         out = np.zeros((self._n_desc, self._k), np.int32)
         check(_L().b2_retrieval_debug_word_ids(self._h, out.ctypes.data))
+        return out
+
+    def debug_word_ids_simt(self) -> np.ndarray:
+        out = np.zeros((self._n_desc, self._k), np.int32)
+        check(_L().b2_retrieval_debug_word_ids_simt(self._h, out.ctypes.data))
         return out
 
     def debug_index(self):

@@ -433,6 +433,8 @@ int b2_retrieval_query_all(b2_retrieval* r, int32_t max_num_images, int32_t* out
 /* Test hooks: nearest words of the indexed descriptors [n_desc * num_neighbors_query]; the inverted index (any pointer may
  * be NULL): word_start [n_words + 1], per entry image / feature / 64-bit signature, idf [n_words], norm [n_images]. */
 int b2_retrieval_debug_word_ids(b2_retrieval* r, int32_t* out);
+/* the same list recomputed by the independent SIMT (dp4a) statement of the word search */
+int b2_retrieval_debug_word_ids_simt(b2_retrieval* r, int32_t* out);
 int b2_retrieval_debug_index(b2_retrieval* r, uint32_t* word_start, int32_t* entry_image, int32_t* entry_feature,
                              uint64_t* entry_bits, float* idf, float* norm);
 int b2_retrieval_last_timing(b2_retrieval* r, double* word_search_s, double* index_build_s, double* query_s);

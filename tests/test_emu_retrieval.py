@@ -14,7 +14,8 @@ from tests.retrieval_cases import check_against_oracle, collection
 def rmod():
     from tests.cuda_emu.build_emu import RETRIEVAL_SOURCES, build
     import dagsfm_b200.retrieval as rm
-    L = C.CDLL(str(build("retrieval", RETRIEVAL_SOURCES)))
+    from pathlib import Path
+    L = C.CDLL(str(build("retrieval", RETRIEVAL_SOURCES, extra=[str(Path(__file__).parent / "cuda_emu" / "retrieval_tc_emu.cc")])))
     L.b2_last_error.restype = C.c_char_p
     saved = (rm.lib, rm.check)
     rm._bound = False
@@ -29,7 +30,7 @@ def rmod():
     rm._bound = False
 
 
-@pytest.mark.parametrize("n_img,n_kp,n_words,k", [(10, 96, 40, 5), (6, 64, 200, 3), (5, 40, 7, 1)])
+@pytest.mark.parametrize("n_img,n_kp,n_words,k", [(10, 96, 40, 5), (6, 64, 200, 3), (5, 40, 7, 1), (12, 128, 6, 3)])
 def test_index_and_query_equal_oracle(rmod, n_img, n_kp, n_words, k):
     descs, vocab = collection(n_img, n_kp, n_words, seed=3 + n_img, overlap=4)
     vi = rmod.VisualIndex(0)
@@ -37,6 +38,34 @@ def test_index_and_query_equal_oracle(rmod, n_img, n_kp, n_words, k):
         vi.set_vocabulary(vocab)
         vi.index_images(descs, k)
         check_against_oracle(vi, descs, vocab, k=k, max_images=4)
+    finally:
+        vi.close()
+
+
+def test_duplicate_words_keep_the_lower_id_first(rmod):
+    """Identical centroids (sampled vocabularies contain them): every distance to the copies ties, the lower word id ranks
+    first and a later insertion must not reorder the ties already in the list."""
+    descs, vocab = collection(6, 64, 24, seed=9, overlap=3)
+    vocab.words[5] = vocab.words[2]
+    vocab.words[17] = vocab.words[2]
+    vocab.words[11] = vocab.words[20]
+    vocab.words[3] = vocab.words[20]
+    vi = rmod.VisualIndex(0)
+    try:
+        vi.set_vocabulary(vocab)
+        vi.index_images(descs, 5)
+        check_against_oracle(vi, descs, vocab, k=5, max_images=4)
+    finally:
+        vi.close()
+
+
+def test_simt_word_search_seam_equals_the_production_list(rmod):
+    descs, vocab = collection(7, 90, 150, seed=21, overlap=3)
+    vi = rmod.VisualIndex(0)
+    try:
+        vi.set_vocabulary(vocab)
+        vi.index_images(descs, 5)
+        assert (vi.debug_word_ids() == vi.debug_word_ids_simt()).all()
     finally:
         vi.close()
 

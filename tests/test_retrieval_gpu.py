@@ -10,7 +10,7 @@ from tests.retrieval_cases import check_against_oracle, collection
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("n_img,n_kp,n_words,k", [(14, 256, 96, 5), (40, 300, 1000, 5), (9, 77, 33, 2), (6, 64, 5, 1)])
+@pytest.mark.parametrize("n_img,n_kp,n_words,k", [(14, 256, 96, 5), (40, 300, 1000, 5), (9, 77, 33, 2), (6, 64, 5, 1), (12, 400, 6, 3)])
 def test_index_and_query_equal_oracle(n_img, n_kp, n_words, k):
     from dagsfm_b200 import VisualIndex
     descs, vocab = collection(n_img, n_kp, n_words, seed=n_img, overlap=5)
