@@ -62,6 +62,8 @@ def parse():
     ap.add_argument("--c1", action="store_true",
                     help="BASELINE configs[0] (the reference's CPU-runnable plumbing case): 100 images x 2048 descriptors, EXHAUSTIVE "
                          "pairs (4950), match + verify; the CPU leg runs the oracle port on ALL pairs and every result is compared")
+    ap.add_argument("--chunk-pairs", type=int, default=65536,
+                    help="pairs per b2_match_pairs_device -> b2_verify_pairs_device call (one launch group of the stage kernels)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -488,7 +490,7 @@ def bench_pipeline(a, dev, local_rank, rank, world, cores, barrier, dist):
     lo, hi = (n_all * rank) // world, (n_all * (rank + 1)) // world       # contiguous, locality-ordered shard
     pairs, seeds = pairs_all[lo:hi], seeds_all[lo:hi]
     cams = cameras_of(coll)
-    fm = SiftFeatureMatcher(SiftMatchingOptions(), TwoViewOptions.default(), local_rank, chunk_pairs=16384)
+    fm = SiftFeatureMatcher(SiftMatchingOptions(), TwoViewOptions.default(), local_rank, chunk_pairs=a.chunk_pairs)
     fm.setup_device_descriptors(coll["desc"].data_ptr(), a.seq_images, a.seq_kp, coll["keypoints"], cams)
     from dagsfm_b200.verification import RESULT_DTYPE
     gathered = None
@@ -497,7 +499,7 @@ def bench_pipeline(a, dev, local_rank, rank, world, cores, barrier, dist):
         """rank 0 receives every shard's results (the reference's single output queue / database writer)."""
         nonlocal gathered
         if world == 1:
-            gathered = res
+            gathered = res.copy()        # the matcher's result array is a view of its pinned buffer, rewritten by the next call
             return
         t = torch.from_numpy(res.view(np.uint8).reshape(-1)).to(dev)
         sizes = [((n_all * (r + 1)) // world - (n_all * r) // world) * RESULT_DTYPE.itemsize for r in range(world)]
@@ -564,7 +566,7 @@ def bench_pipeline(a, dev, local_rank, rank, world, cores, barrier, dist):
                       "h2d_bytes_per_step": int(hd.nbytes + coll["keypoints"].nbytes + pairs.nbytes + seeds.nbytes),
                       "d2h_bytes_per_step": int(d2h), "steps": e_steps,
                       "api": "SiftFeatureMatcher.Setup (b2_match_set_images + b2_verify_set_images, host buffers) + "
-                             "b2_match_pairs_device -> b2_verify_pairs_device per 16 384-pair chunk, results / match lists / inlier lists to the host",
+                             "b2_match_pairs_device -> b2_verify_pairs_device per chunk of pairs (--chunk-pairs), results / match lists / inlier lists to the host",
                       "bytes_note": "per rank" if world > 1 else "whole job"}
         fm.setup_device_descriptors(coll["desc"].data_ptr(), a.seq_images, a.seq_kp, coll["keypoints"], cams)
     if rank == 0:
@@ -833,10 +835,11 @@ def main():
     peak64, peak64_src = peaks_fp64()
     g = gathered
     mcount = None
-    roofline = {"bound": "fp64", "kernel": "verify_pairs_kernel (one warp per pair, 32 RANSAC trials per batch)", "unit": "TFLOP/s",
+    roofline = {"bound": "fp64", "kernel": "verify_stage_kernel<E|F|H|decision> (one warp per pair, 32 RANSAC trials per batch; the H stage is ~65 % of it)", "unit": "TFLOP/s",
                 "peak": peak64, "peak_source": peak64_src, "traffic": None,
                 "share_of_step": pl["verify_kernel_s"] / max(pl["verify_kernel_s"] + pl["match_kernel_s"], 1e-12),
-                "avg_launch_ms": 1e3 * pl["verify_kernel_s"] / max(a.steps * ((pl["n_pairs"] // world + 16383) // 16384), 1)}
+                "avg_launch_ms": 1e3 * pl["verify_kernel_s"] / max(a.steps * ((pl["n_pairs"] // world + a.chunk_pairs - 1) // a.chunk_pairs), 1),
+                "launch_note": "one launch = the four stage kernels (E, F, H, decision) of one chunk of pairs"}
     try:
         off = None
         # matches per pair are not kept by the throughput run: expected count from the scene layout (shared points +

@@ -10,9 +10,10 @@
 // stream through an 8-stage TMA ring as 128-row K-major SWIZZLE_128B blocks (the whole vocabulary -- 4 MB at 32 k words --
 // is L2 resident and is read by every CTA); four K = 32-byte tcgen05.mma.kind::i8 per (tile, block) accumulate 128 x 128
 // s32 in TMEM; eight epilogue warps (one TMEM lane = one descriptor per thread) pull a block's 128 dot products with one
-// LDTM.x128, hand the accumulator back, and fold the block into the thread's running top-k IN REGISTERS: per four
-// columns three integer adds/max decide warp-uniformly whether anything can enter a list (about one group in six), and
-// only then the insertion code runs.  Words are visited in ascending id and an insertion needs a strictly larger
+// LDTM.x128, hand the accumulator back, and fold the block into the thread's running top-k: per four columns a few
+// integer instructions (scores, their maximum, one vote against a register copy of the list's tail) decide warp-uniformly
+// whether anything can enter a list (about one group in six), and only then the out-of-line insertion code runs; the
+// block's |w|^2 reach the lanes as shared-memory broadcasts (staged per warp from one coalesced load).  Words are visited in ascending id and an insertion needs a strictly larger
 // score, so equal scores keep the lower id first -- the oracle's order.
 //
 // TMEM (512 columns): accumulators 2 tiles x 128 columns (ping-pong between the tiles), A operand 2 buffers x 2 tiles x 32.
@@ -40,24 +41,38 @@ constexpr uint32_t kACol = 256;
 constexpr uint32_t kSmemY = 0;
 constexpr uint32_t kSmemBar = kStagesY * kYBytes;
 constexpr uint32_t kNumBars = 2 * kStagesY + 8;
-constexpr uint32_t kSmemTotal = kSmemBar + kNumBars * 8 + 16;
+constexpr uint32_t kSmemWsq = kSmemBar + kNumBars * 8 + 16;   // per epilogue warp: the |w|^2 of the current block (128 ints)
+constexpr uint32_t kSmemTotal = kSmemWsq + kNumEpiWarps * kN * 4;
 constexpr int kInvalidWord = 0x7fffffff;
 constexpr int kNever = -0x7fffffff;         // score of a padding word (|w|^2 = INT_MAX, d.w = 0): never strictly above the initial lists
 
-// the running k best (score descending; bw = word ids)
+// The running k best of a descriptor (score descending; bw = word ids) live in LOCAL memory: only the rare insertion path
+// touches them, the per-column path compares against a register copy of the list's tail.  One out-of-line copy of the
+// insertion code serves all 32 column groups of a block (inlined per group it was 50-80 KB of SASS and the epilogue waited
+// for instructions).  Scores are offered in ascending column order and must be strictly larger to enter, so equal scores
+// keep the lower word id first.  Returns the new tail.
 template <int K>
-__device__ __forceinline__ void insert(int (&bd)[K], int (&bw)[K], int s, int w) {
-  int cd = s, cw = w;
-  bool placed = false;
+__device__ __noinline__ int offer4(int* bd, int* bw, int s0, int s1, int s2, int s3, int w) {
+  int tail = bd[K - 1];
 #pragma unroll
-  for (int k = 0; k < K; ++k) {
-    if (placed || cd > bd[k]) {
-      const int td = bd[k], tw = bw[k];
-      bd[k] = cd; bw[k] = cw;
-      cd = td; cw = tw;
-      placed = true;
+  for (int e = 0; e < 4; ++e) {
+    const int sc = e == 0 ? s0 : e == 1 ? s1 : e == 2 ? s2 : s3;
+    if (sc > tail) {
+      int cd = sc, cw = w + e;
+      bool placed = false;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const int td = bd[k], tw = bw[k];
+        if (placed || cd > td) {
+          bd[k] = cd; bw[k] = cw;
+          cd = td; cw = tw;
+          placed = true;
+        }
+      }
+      tail = bd[K - 1];
     }
   }
+  return tail;
 }
 
 template <int K>
@@ -160,6 +175,7 @@ word_knn_tc_kernel(const __grid_constant__ CUtensorMap tmap_words, const uint8_t
     const uint32_t tile = ew >> 2;
     const uint32_t lane_addr = (quad * 32u) << 16;
     const uint32_t row_in_item = tile * 128 + quad * 32 + lane;
+    int4* const wsq_sm = reinterpret_cast<int4*>(smem_raw + (smem_base - smem_u32(smem_raw)) + kSmemWsq) + ew * (kN / 4);
     auto load_a = [&](uint32_t item, uint32_t xi) {
       const uint32_t ab = xi & 1;
       mbar_wait(a_empty(ab), ((xi >> 1) & 1) ^ 1);
@@ -189,7 +205,10 @@ word_knn_tc_kernel(const __grid_constant__ CUtensorMap tmap_words, const uint8_t
       int bd[K], bw[K];
 #pragma unroll
       for (int k = 0; k < K; ++k) { bd[k] = kNever; bw[k] = kInvalidWord; }
+      int tail = kNever;
       for (uint32_t b = 0; b < n_blk; ++b) {
+        // this block's |w|^2: one coalesced load per warp, issued before the wait so that its latency hides behind the MMAs
+        const int4 wq_mine = __ldg(reinterpret_cast<const int4*>(word_sq + (size_t)b * kN) + lane);
         mbar_wait(t_full(tile), tb & 1);
         tc_fence_after();
         uint32_t v[128];
@@ -197,22 +216,20 @@ word_knn_tc_kernel(const __grid_constant__ CUtensorMap tmap_words, const uint8_t
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(t_empty(tile));
-        const int4* wq = reinterpret_cast<const int4*>(word_sq + (size_t)b * kN);
+        wsq_sm[lane] = wq_mine;   // the previous block's reads of this buffer are complete (same warp, program order)
+        __syncwarp();
         const int w0 = (int)(b * kN);
 #pragma unroll
         for (int g = 0; g < 32; ++g) {
-          const int4 q = __ldg(wq + g);   // the same address in every lane: one broadcast transaction
-          int s0 = 2 * (int)v[4 * g] - q.x, s1 = 2 * (int)v[4 * g + 1] - q.y;
-          int s2 = 2 * (int)v[4 * g + 2] - q.z, s3 = 2 * (int)v[4 * g + 3] - q.w;
+          const int4 q = wsq_sm[g];   // the same address in every lane: a shared-memory broadcast
+          const int s0 = 2 * (int)v[4 * g] - q.x, s1 = 2 * (int)v[4 * g + 1] - q.y;
+          const int s2 = 2 * (int)v[4 * g + 2] - q.z, s3 = 2 * (int)v[4 * g + 3] - q.w;
           const int m = max(__vimax3_s32(s0, s1, s2), s3);
-          if (__any_sync(0xffffffffu, m > bd[K - 1])) {
-            // ascending column order; a lane whose four scores all stay below its list's tail skips every insertion
-            if (s0 > bd[K - 1]) insert<K>(bd, bw, s0, w0 + 4 * g);
-            if (s1 > bd[K - 1]) insert<K>(bd, bw, s1, w0 + 4 * g + 1);
-            if (s2 > bd[K - 1]) insert<K>(bd, bw, s2, w0 + 4 * g + 2);
-            if (s3 > bd[K - 1]) insert<K>(bd, bw, s3, w0 + 4 * g + 3);
+          if (__builtin_expect(__any_sync(0xffffffffu, m > tail), 0)) {
+            if (m > tail) tail = offer4<K>(bd, bw, s0, s1, s2, s3, w0 + 4 * g);
           }
         }
+        __syncwarp();
         ++tb;
       }
       const long long row = (long long)item * kSuperRows + row_in_item;

@@ -128,55 +128,115 @@ class SiftFeatureMatcher:
     def run_device(self, pairs: np.ndarray, seeds: np.ndarray | None = None, keep_lists: bool = True):
         """match -> verify for `pairs` [n, 2], chunk by chunk, match lists staying on the device.
         -> (results RESULT_DTYPE [n], offsets int64 [n + 1], matches uint32 [total, 2], inliers uint32 [total, 2]);
-        the two lists are None with keep_lists = False (throughput runs: only the results come back)."""
+        the two lists are None with keep_lists = False (throughput runs: only the results come back).
+        The chunks alternate between two sets of device buffers; a chunk's outputs go to pinned host memory on a copy stream
+        while the next chunk is matched and verified, so the PCIe traffic hides behind the kernels.  The returned arrays are
+        views of pinned buffers owned by this object: valid until the next call."""
         import torch
         dev = torch.device("cuda", self.device)
         pr = np.ascontiguousarray(pairs, dtype=np.uint32).reshape(-1, 2)
         n = len(pr)
         sd = np.ascontiguousarray(seeds if seeds is not None else np.arange(n), dtype=np.uint32)
-        res = np.zeros(n, RESULT_DTYPE)
-        offs, mts, inls = [np.zeros(1, np.int64)], [], []
+        isz = RESULT_DTYPE.itemsize
         self.match_seconds = self.verify_seconds = 0.0
-        base = 0
-        for c0 in range(0, n, self.chunk_pairs):
+        if n == 0:
+            z = np.zeros((0, 2), np.uint32)
+            return np.zeros(0, RESULT_DTYPE), (np.zeros(1, np.int64) if keep_lists else None), (z if keep_lists else None), (z if keep_lists else None)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(dev)
+        cs = self._copy_stream
+        n_chunks = (n + self.chunk_pairs - 1) // self.chunk_pairs
+        caps = [int(np.minimum(self._n_kp[pr[c0:c0 + self.chunk_pairs, 0]], self._n_kp[pr[c0:c0 + self.chunk_pairs, 1]]).sum()) + 1
+                for c0 in range(0, n, self.chunk_pairs)]
+        sets = [self._buffers(dev, min(self.chunk_pairs, n), max(caps), which) for which in range(2 if n_chunks > 1 else 1)]
+        pin = self._pinned(n, n_chunks, isz)
+        done = [None, None]                      # copy-complete event of the chunk that last used a buffer set
+        chunk_tot, base = [], 0
+        for ci, c0 in enumerate(range(0, n, self.chunk_pairs)):
             c1 = min(n, c0 + self.chunk_pairs)
             k = c1 - c0
-            cap = int(np.minimum(self._n_kp[pr[c0:c1, 0]], self._n_kp[pr[c0:c1, 1]]).sum()) + 1
-            bufs = self._buffers(dev, k, cap)
+            w = ci % len(sets)
+            bufs = sets[w]
+            if done[w] is not None:
+                done[w].synchronize()            # the set's previous outputs have left the device
             bufs["pairs"][:2 * k].copy_(torch.from_numpy(pr[c0:c1].astype(np.int32).reshape(-1)), non_blocking=True)
             bufs["seeds"][:k].copy_(torch.from_numpy(sd[c0:c1].astype(np.int32)), non_blocking=True)
             torch.cuda.current_stream(dev).synchronize()
             total = self._m.match_pairs_device(k, bufs["pairs"].data_ptr(), self.match_options, bufs["off"].data_ptr(),
-                                               bufs["mt"].data_ptr(), cap)
+                                               bufs["mt"].data_ptr(), caps[ci])
             self.match_seconds += self._m.last_timing()["all_kernels_s"]
             self._v.verify_pairs_device(k, bufs["pairs"].data_ptr(), bufs["off"].data_ptr(), bufs["mt"].data_ptr(),
                                         self.two_view_options, bufs["seeds"].data_ptr(), bufs["res"].data_ptr(),
                                         bufs["inl"].data_ptr())
             self.verify_seconds += self._v.last_kernel_seconds()
-            res[c0:c1] = bufs["res"][:k * RESULT_DTYPE.itemsize].cpu().numpy().view(RESULT_DTYPE)
-            if keep_lists:
-                o = bufs["off"][:k + 1].cpu().numpy()
-                offs.append(o[1:] + base)
-                base += int(o[-1])
-                mts.append(bufs["mt"][:2 * total].cpu().numpy().view(np.uint32).reshape(-1, 2))
-                inls.append(bufs["inl"][:2 * total].cpu().numpy().view(np.uint32).reshape(-1, 2))
+            # both calls return after their kernels: the chunk's outputs are final, the copy stream may read them now
+            if keep_lists and 2 * (base + total) > pin["mt"].numel():
+                cs.synchronize()
+                self._grow_lists(pin, int(2 * (base + total) * max(1.0, 1.15 * n / c1)), 2 * base)
+            with torch.cuda.stream(cs):
+                pin["res"][c0 * isz:c1 * isz].copy_(bufs["res"][:k * isz], non_blocking=True)
+                if keep_lists:
+                    pin["off"][c0 + ci:c1 + ci + 1].copy_(bufs["off"][:k + 1], non_blocking=True)
+                    pin["mt"][2 * base:2 * (base + total)].copy_(bufs["mt"][:2 * total], non_blocking=True)
+                    pin["inl"][2 * base:2 * (base + total)].copy_(bufs["inl"][:2 * total], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(cs)
+            done[w] = ev
+            chunk_tot.append(total)
+            base += total
+        cs.synchronize()
+        res = pin["res"][:n * isz].numpy().view(RESULT_DTYPE)
         if not keep_lists:
             return res, None, None, None
-        cat = lambda xs: np.concatenate(xs) if xs else np.zeros((0, 2), np.uint32)  # noqa: E731
-        return res, np.concatenate(offs), cat(mts), cat(inls)
+        raw = pin["off"].numpy()                  # per chunk k + 1 chunk-relative offsets
+        off = np.empty(n + 1, np.int64)
+        off[0] = 0
+        b = 0
+        for ci, c0 in enumerate(range(0, n, self.chunk_pairs)):
+            c1 = min(n, c0 + self.chunk_pairs)
+            off[c0 + 1:c1 + 1] = raw[c0 + ci + 1:c1 + ci + 1] + b
+            b += chunk_tot[ci]
+        mt = pin["mt"][:2 * base].numpy().view(np.uint32).reshape(-1, 2)
+        inl = pin["inl"][:2 * base].numpy().view(np.uint32).reshape(-1, 2)
+        return res, off, mt, inl
 
-    def _buffers(self, dev, k, cap):
+    def _buffers(self, dev, k, cap, which=0):
         import torch
-        b = getattr(self, "_bufs", None)
+        sets = getattr(self, "_bufs", None)
+        if sets is None:
+            sets = self._bufs = {}
+        b = sets.get(which)
         if b is None or b["k"] < k or b["cap"] < cap:
-            kk, cc = max(k, self.chunk_pairs), int(cap * 1.25)
+            kk, cc = max(k, 1), int(cap * 1.05) + 16
             b = {"k": kk, "cap": cc,
                  "pairs": torch.empty(2 * kk, dtype=torch.int32, device=dev), "seeds": torch.empty(kk, dtype=torch.int32, device=dev),
                  "off": torch.zeros(kk + 1, dtype=torch.int64, device=dev), "mt": torch.empty(2 * cc, dtype=torch.int32, device=dev),
                  "inl": torch.empty(2 * cc, dtype=torch.int32, device=dev),
                  "res": torch.empty(kk * RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)}
-            self._bufs = b
+            sets[which] = b
         return b
+
+    def _pinned(self, n, n_chunks, isz):
+        """Pinned host buffers of the outputs, kept across calls (pinning gigabytes costs more than a step)."""
+        import torch
+        p = getattr(self, "_pin", None)
+        if p is None:
+            p = self._pin = {"res": torch.empty(0, dtype=torch.uint8), "off": torch.empty(0, dtype=torch.int64),
+                             "mt": torch.empty(0, dtype=torch.int32), "inl": torch.empty(0, dtype=torch.int32)}
+        if p["res"].numel() < n * isz:
+            p["res"] = torch.empty(n * isz, dtype=torch.uint8, pin_memory=True)
+        if p["off"].numel() < n + n_chunks + 1:
+            p["off"] = torch.empty(n + n_chunks + 1, dtype=torch.int64, pin_memory=True)
+        return p
+
+    @staticmethod
+    def _grow_lists(pin, numel, keep):
+        import torch
+        for key in ("mt", "inl"):
+            t = torch.empty(numel, dtype=torch.int32, pin_memory=True)
+            if keep:
+                t[:keep].copy_(pin[key][:keep])
+            pin[key] = t
 
     # ---- the reference's entry point
     def Match(self, image_pairs, cache: MatchCache, seeds=None) -> int:
