@@ -116,6 +116,53 @@ __device__ inline uint32_t uniform_u32(WarpShared& s, uint32_t a, uint32_t b) {
   return (uint32_t)(product >> 32) + a;
 }
 
+// ---- the same generator, advanced by the whole warp ------------------------------------------------------------------
+// std::mt19937's regeneration: new[k] = mt[(k + 397) % 624] ^ twist(mt[k], mt[(k + 1) % 624]) for k = 0 .. 623 IN ORDER.  For
+// k < 227 every operand is an old word; from k = 227 on the first operand is the already regenerated word k - 227, which a
+// 32-wide step never shares with its own range; the second operand k + 1 is regenerated only by a later step (or by a
+// higher lane of this one, hence read-then-barrier-then-write).  k = 623 needs the regenerated words 0 and 396.
+__device__ __forceinline__ uint32_t mt_twist_word(uint32_t a, uint32_t b, uint32_t m) {
+  const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+  return m ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+}
+__device__ inline void mt_twist_warp(WarpShared& s, int lane) {
+  for (int k0 = 0; k0 < 623; k0 += 32) {
+    const int k = k0 + lane;
+    uint32_t v = 0;
+    if (k < 623) v = mt_twist_word(s.mt[k], s.mt[k + 1], s.mt[k < 227 ? k + 397 : k - 227]);
+    __syncwarp();
+    if (k < 623) s.mt[k] = v;
+    __syncwarp();
+  }
+  if (lane == 0) {
+    s.mt[623] = mt_twist_word(s.mt[623], s.mt[0], s.mt[396]);
+    s.mti = 0;
+  }
+  __syncwarp();
+}
+// Appends raw outputs to the FIFO until it holds `need` unread ones (need <= 224: a batch of 32 trials of <= 7 draws), 32 per
+// step: lane l tempers state word mti + l.  The FIFO never holds more than need + 31 <= 255 words behind r0 = r.
+__device__ inline void ring_fill_warp(WarpShared& s, uint32_t need, int lane) {
+  for (;;) {
+    const uint32_t have = s.w - s.r;   // uniform: read by all lanes after a barrier
+    if (have >= need) break;
+    if (s.mti >= 624) mt_twist_warp(s, lane);
+    const uint32_t mti = s.mti, w = s.w;
+    const uint32_t c = min(32u, 624u - mti);
+    if ((uint32_t)lane < c) {
+      uint32_t y = s.mt[mti + lane];
+      y ^= (y >> 11);
+      y ^= (y << 7) & 0x9d2c5680u;
+      y ^= (y << 15) & 0xefc60000u;
+      y ^= (y >> 18);
+      s.ring[(w + lane) & 255u] = y;
+    }
+    __syncwarp();
+    if (lane == 0) { s.mti = mti + c; s.w = w + c; }
+    __syncwarp();
+  }
+}
+
 // ----------------------------------------------------------------- residuals
 __device__ __forceinline__ double sampson(const double* E, double x1_0, double x1_1, double x2_0, double x2_1) {
   const double Ex1_0 = E[0] * x1_0 + E[1] * x1_1 + E[2];
@@ -587,25 +634,45 @@ __device__ __noinline__ void ransac_warp(const double2* P1, const double2* P2, i
     }
     const int nb = (int)((max_trials - t0) < 32ull ? (max_trials - t0) : 32ull);
     const long long c0 = clock64();
-    // --- lane 0: sample indices for trials t0 .. t0+nb-1 (Shuffle of the persistent vector)
-    if (lane == 0) {
-      const uint32_t last = (uint32_t)(M - 1);
-      sh.r0 = sh.r;
-      for (int j = 0; j < nb; ++j) {
-        for (uint32_t i = 0; i < (uint32_t)kmin; ++i) {
-          const uint32_t jj = uniform_u32(sh, i, last);
-          if (idx_sm) {
-            const uint16_t a = sh.idx16[i], b = sh.idx16[jj];
-            sh.idx16[i] = b;
-            sh.idx16[jj] = a;
-          } else {
-            const uint32_t a = sc.idx[i], b = sc.idx[jj];
-            sc.idx[i] = b;
-            sc.idx[jj] = a;
+    // --- sample indices for trials t0 .. t0+nb-1 (Shuffle of the persistent vector).  The generator runs ahead by the whole
+    // warp (regeneration and tempering 32 words at a time), every lane turns raw outputs into swap targets with Lemire's
+    // multiply -- draw d of the batch reads output r + d, which holds as long as no draw is rejected (probability
+    // range / 2^32 per draw) -- and lane 0 is left with the chain of swaps.  A batch with a possible rejection (low < range
+    // for any draw) is sampled by the sequential code instead; both consume the stream exactly as the reference does.
+    {
+      const uint32_t need = (uint32_t)(nb * kmin);
+      ring_fill_warp(sh, need, lane);
+      const uint32_t r = sh.r;
+      bool suspect = false;
+      for (uint32_t d = lane; d < need; d += 32) {
+        const uint32_t i = d % (uint32_t)kmin, j = d / (uint32_t)kmin;
+        const uint32_t range = (uint32_t)M - i;   // uniform_int_distribution(i, M - 1)
+        const uint64_t product = (uint64_t)sh.ring[(r + d) & 255u] * (uint64_t)range;
+        suspect |= (uint32_t)product < range;
+        sh.samp[j][i] = (uint32_t)(product >> 32) + i;
+      }
+      const bool fast = !__any_sync(kFull, suspect);
+      __syncwarp();
+      if (lane == 0) {
+        const uint32_t last = (uint32_t)(M - 1);
+        sh.r0 = sh.r;
+        for (int j = 0; j < nb; ++j) {
+          for (uint32_t i = 0; i < (uint32_t)kmin; ++i) {
+            const uint32_t jj = fast ? sh.samp[j][i] : uniform_u32(sh, i, last);
+            if (idx_sm) {
+              const uint16_t a = sh.idx16[i], b = sh.idx16[jj];
+              sh.idx16[i] = b;
+              sh.idx16[jj] = a;
+            } else {
+              const uint32_t a = sc.idx[i], b = sc.idx[jj];
+              sc.idx[i] = b;
+              sc.idx[jj] = a;
+            }
           }
+          for (int i = 0; i < kmin; ++i) sh.samp[j][i] = idx_sm ? (uint32_t)sh.idx16[i] : sc.idx[i];
+          if (fast) sh.r = r + (uint32_t)((j + 1) * kmin);
+          sh.pos_after[j] = sh.r;
         }
-        for (int i = 0; i < kmin; ++i) sh.samp[j][i] = idx_sm ? (uint32_t)sh.idx16[i] : sc.idx[i];
-        sh.pos_after[j] = sh.r;
       }
     }
     __syncwarp();

@@ -233,6 +233,12 @@ class ParallelBA {
   const int *pidx_ = nullptr, *cidx_ = nullptr;
 };
 
+// lib/PBA/pba.h:146-152: the factory a caller that loads PBA dynamically resolves, and the version probe (pba.cpp:128-132
+// returns 105).  Here they are ordinary inline functions of the adaptor: nothing in the reference's src/ uses the dlopen route.
+inline ParallelBA* NewParallelBA(ParallelBA::DeviceT device = ParallelBA::PBA_CUDA_DEVICE_DEFAULT) { return new ParallelBA(device); }
+typedef ParallelBA* (*NEWPARALLELBAPROC)(ParallelBA::DeviceT);
+inline int ParallelBA_GetVersion() { return 105; }
+
 }  // namespace pba
 }  // namespace dagsfm_b200
 #endif  // DAGSFM_B200_PBA_SHIM_HPP_
