@@ -51,6 +51,9 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="pairs in the CPU baseline sample (0 = 24 per core)")
     ap.add_argument("--verify-pairs", type=int, default=0, help="opt-in leg: stand-alone verification of pre-matched pairs")
     ap.add_argument("--ba", default="500,100000,10", help="BA leg: images,points,track (empty = skip)")
+    ap.add_argument("--ba-c5", default="10000,2000000,10",
+                    help="second BA leg, the C5 shape (BASELINE configs[4]: 10 k images / 2 M points / 20 M observations; the "
+                         "reference's rule selects ITERATIVE_SCHUR above 1000 images); images,points,track (empty = skip)")
     ap.add_argument("--guided-pairs", type=int, default=0,
                     help="opt-in leg: guided matching (b2_match_guided_pairs, MatchGuidedSiftFeaturesGPU) on this many synthetic pairs")
     ap.add_argument("--verify-pose", action="store_true",
@@ -413,19 +416,20 @@ def bench_ba(a, local_rank, rank, world, cores, barrier, hbm):
                            "frac": alg_cg / (lin_ms * 1e-3) / 1e9 / hbm[0], "peak_source": hbm[1],
                            "algorithmic_bytes_per_cg_iteration": alg_cg, "avg_ms_per_cg_iteration": lin_ms,
                            "share_of_solve": s.schur_kernel_seconds / s.solve_seconds, "traffic": None}
-    if False and (n_img, n_pts, track) == (500, 100000, 10) and world == 1 and s.linear_solver_type_used == 1:
-        # committed ncu captures of one iteration at exactly this workload: schur_kernel 234.7 + 11.8 MB
-        # (profiles/r1_ba_schur_ncu_full.txt), camera_terms_kernel 228.8 + 3.5 MB (r1_ba_camera_terms_ncu_full.txt);
-        # 4.9x the algorithmic bytes because both kernels re-read the 224 B/observation Jacobian blocks
-        out["roofline"]["traffic"] = 478.8e6
-        out["roofline"]["traffic_source"] = "profiles/r1_ba_schur_ncu_full.txt + r1_ba_camera_terms_ncu_full.txt (bytes per LM iteration)"
+    if (n_img, n_pts, track) == (500, 100000, 10) and world == 1 and s.linear_solver_type_used != 2 and s.exact_path_used == 2:
+        # committed ncu capture of one iteration at exactly this workload (profiles/r2_ba_fused_ncu_full.txt): camera_terms 31.5 MB,
+        # schur_points 49.8 + 217.5 MB (it writes the 240 B / observation Z that schur_window reads back), schur_window 254.8 + 3.6 MB
+        out["roofline"]["traffic"] = 557.2e6
+        out["roofline"]["traffic_source"] = "profiles/r2_ba_fused_ncu_full.txt (dram bytes read + written per LM iteration, three kernels)"
     if rank == 0 and not a.no_cpu:
         from oracle import pyoracle as orc
         if orc.pba_ref_available():
             pc = copy_problem(full0)
-            r = orc.pba_ref_solve(pc, n_threads=cores, max_iter=50)
+            big = n_obs_total > 4_000_000          # bounded sample: a C5-size problem gets two LM iterations of the CPU reference
+            r = orc.pba_ref_solve(pc, n_threads=cores, max_iter=2 if big else 50)
             out["cpu_baseline"] = {"value": r["lm_iterations"] / r["seconds"], "unit": "LM iter/s", "cores": cores,
-                                   "kind": "reference", "sample": f"vendored PBA CPU double, {r['lm_iterations']} LM iterations, {r['seconds']:.1f} s",
+                                   "kind": "reference", "sample": f"vendored PBA CPU double, {r['lm_iterations']} LM iterations, {r['seconds']:.1f} s"
+                                                                   + (" (bounded: 2 iterations)" if big else ""),
                                    "final_mse_px2": float(r["final_mse"]),
                                    "gpu_final_mse_px2": float(2 * s.final_cost / n_obs)}
     ba.close()
@@ -645,6 +649,11 @@ def bench_retrieval(a, coll, local_rank, cores, pairs_all):
             n_s = min(12288 * cores, n_img * n_kp)   # ~10 s of exact search on the host cores
             pick = np.sort(rng.choice(n_img * n_kp, n_s, replace=False))
             sample = coll["desc"].reshape(-1, 128)[torch.from_numpy(pick).to(coll["desc"].device)].cpu().numpy()
+            try:      # torchrun exports OMP_NUM_THREADS=1; the oracle's word search is an OpenMP loop and gets all host cores here
+                import ctypes
+                ctypes.CDLL("libgomp.so.1").omp_set_num_threads(int(cores))
+            except OSError:
+                pass
             t0 = time.perf_counter()
             exp = o.word_ids(sample, K)
             t = time.perf_counter() - t0
@@ -725,7 +734,7 @@ def main():
     cores = effective_cores()
     if a.c1:
         a.seq_images, a.seq_kp, a.seq_cand = 100, 2048, 99      # every successor = the exhaustive pair list
-        a.cpu_sample, a.pairs, a.ba = 4950, -1, ""
+        a.cpu_sample, a.pairs, a.ba, a.ba_c5 = 4950, -1, "", ""
         a.retrieval_words = min(a.retrieval_words, 4096)
     if a.cpu_sample <= 0:
         a.cpu_sample = 24 * cores      # ~10-20 s of host work at ~2 pairs per core-second
@@ -842,6 +851,15 @@ def main():
         except Exception as e:
             guided = {"error": repr(e)}
     ba = bench_ba(a, local_rank, rank, world, cores, barrier, peaks_hbm()) if a.ba else None
+    ba_c5 = None
+    if a.ba_c5:
+        import copy
+        a5 = copy.copy(a)
+        a5.ba, a5.ba_solver = a.ba_c5, "auto"
+        try:
+            ba_c5 = bench_ba(a5, local_rank, rank, world, cores, barrier, peaks_hbm())
+        except Exception as e:   # an extra leg must not take the headline line down
+            ba_c5 = {"error": repr(e)}
 
     if rank != 0:
         if world > 1:
@@ -890,7 +908,7 @@ def main():
                      "timing": "value = pairs / wall time of the K steps between device synchronisations (kernels, chunk "
                                "hand-over, result gather); *_kernel_ms = CUDA-event time of the two stages on their streams, max over ranks",
                      **pl.get("results", {})},
-        "retrieval": retrieval, "match": match, "verify": verify, "ba": ba, **({"guided": guided} if guided is not None else {}),
+        "retrieval": retrieval, "match": match, "verify": verify, "ba": ba, "ba_c5": ba_c5, **({"guided": guided} if guided is not None else {}),
     }), flush=True)
     if world > 1:
         dist.destroy_process_group()

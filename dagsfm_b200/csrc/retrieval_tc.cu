@@ -219,9 +219,11 @@ word_knn_tc_kernel(const __grid_constant__ CUtensorMap tmap_words, const uint8_t
         wsq_sm[lane] = wq_mine;   // the previous block's reads of this buffer are complete (same warp, program order)
         __syncwarp();
         const int w0 = (int)(b * kN);
+        int4 qn = wsq_sm[0];          // the same address in every lane: a shared-memory broadcast, fetched one group ahead
 #pragma unroll
         for (int g = 0; g < 32; ++g) {
-          const int4 q = wsq_sm[g];   // the same address in every lane: a shared-memory broadcast
+          const int4 q = qn;
+          qn = wsq_sm[(g + 1) & 31];
           const int s0 = 2 * (int)v[4 * g] - q.x, s1 = 2 * (int)v[4 * g + 1] - q.y;
           const int s2 = 2 * (int)v[4 * g + 2] - q.z, s3 = 2 * (int)v[4 * g + 3] - q.w;
           const int m = max(__vimax3_s32(s0, s1, s2), s3);

@@ -309,9 +309,22 @@ int b2_verify_set_images(b2_verifier* v, int32_t n_images, const b2_camera* cams
     }
   }
   B2_CUDA(cudaMemcpyAsync(v->d_img_off, off.data(), (n_images + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
-  for (int32_t i = 0; i < n_images; ++i) {
-    if (n_pts[i] == 0) continue;
-    B2_CUDA(cudaMemcpyAsync(v->d_xy + 2 * off[i], xy[i], (size_t)n_pts[i] * 16, cudaMemcpyHostToDevice, s));
+  {  // keypoint arrays that are adjacent in the caller's memory travel as one copy (the device array is contiguous anyway)
+    const double* run_src = nullptr;
+    int64_t run_first = 0, run_pts = 0;
+    for (int32_t i = 0; i <= n_images; ++i) {
+      const bool last = i == n_images;
+      if (!last && n_pts[i] == 0) continue;
+      if (!last && run_pts && xy[i] == run_src + 2 * run_pts) {
+        run_pts += n_pts[i];
+        continue;
+      }
+      if (run_pts) B2_CUDA(cudaMemcpyAsync(v->d_xy + 2 * run_first, run_src, (size_t)run_pts * 16, cudaMemcpyHostToDevice, s));
+      if (last) break;
+      run_src = xy[i];
+      run_first = off[i];
+      run_pts = n_pts[i];
+    }
   }
   B2_CUDA(launch_normalize_points(d_true ? d_true : v->d_cams, v->d_img_off, n_images, v->d_xy, v->d_nxy, off[n_images], s));
   count_launches(1);

@@ -311,6 +311,11 @@ __device__ inline unsigned long long compute_num_trials(unsigned long long num_i
 // G: rows x 9, column-major (G[c * ld + r]) in global scratch; V (9x9 row-major) in shared.
 // One-sided Jacobi; lanes split the rows.  On return V's columns are sorted by descending
 // singular value (sig in shared too).
+// Sum of nine terms held one per lane on lanes 0..8 (zeros elsewhere) as the 32-lane xor butterfly (offsets 16, 8, 4, 2, 1)
+// associates it: (((x0 + x8) + x4) + (x2 + x6)) + ((x1 + x5) + (x3 + x7)); the additions of +0.0 it also performs are exact.
+__device__ __forceinline__ double butterfly9(const double* x) {
+  return (((x[0] + x[8]) + x[4]) + (x[2] + x[6])) + ((x[1] + x[5]) + (x[3] + x[7]));
+}
 __device__ __noinline__ void warp_jacobi9(double* G, int rows, int ld, double* V, double* sig, int lane) {
   for (int i = lane; i < 81; i += 32) V[i] = (i / 9 == i % 9) ? 1.0 : 0.0;
   __syncwarp();
@@ -327,17 +332,33 @@ __device__ __noinline__ void warp_jacobi9(double* G, int rows, int ld, double* V
         double alpha = 0, beta = 0, gamma = 0;
         double* gp = G + (size_t)p * ld;
         double* gq = G + (size_t)q * ld;
-        for (int i = lane; i < rows; i += 32) {
-          const double a = gp[i], b = gq[i];
-          alpha += a * a;
-          beta += b * b;
-          gamma += a * b;
-        }
+        if (rows <= 9) {
+          // The 9 x 9 triangular factor (or a minimal problem): every lane forms the three sums itself from broadcast loads,
+          // in the association the xor butterfly below gives nine terms on lanes 0..8 -- bit-identical, without 15 shuffles.
+          double xa[9], xb[9], xg[9];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          alpha += __shfl_xor_sync(kFull, alpha, o);
-          beta += __shfl_xor_sync(kFull, beta, o);
-          gamma += __shfl_xor_sync(kFull, gamma, o);
+          for (int i = 0; i < 9; ++i) {
+            double a = 0.0, b = 0.0;
+            if (i < rows) { a = gp[i]; b = gq[i]; }
+            xa[i] = a * a; xb[i] = b * b; xg[i] = a * b;
+          }
+          alpha = butterfly9(xa);
+          beta = butterfly9(xb);
+          gamma = butterfly9(xg);
+          __syncwarp();  // every lane has read both columns before the lanes that own rows rotate them
+        } else {
+          for (int i = lane; i < rows; i += 32) {
+            const double a = gp[i], b = gq[i];
+            alpha += a * a;
+            beta += b * b;
+            gamma += a * b;
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            alpha += __shfl_xor_sync(kFull, alpha, o);
+            beta += __shfl_xor_sync(kFull, beta, o);
+            gamma += __shfl_xor_sync(kFull, gamma, o);
+          }
         }
         if (gamma == 0.0 || (alpha <= tiny || beta <= tiny) || fabs(gamma) <= kEps * sqrt(alpha * beta)) continue;
         rotated = true;
@@ -365,9 +386,19 @@ __device__ __noinline__ void warp_jacobi9(double* G, int rows, int ld, double* V
   for (int j = 0; j < 9; ++j) {
     double s = 0;
     const double* g = G + (size_t)j * ld;
-    for (int i = lane; i < rows; i += 32) s += g[i] * g[i];
+    if (rows <= 9) {
+      double x[9];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
+      for (int i = 0; i < 9; ++i) {
+        const double a = i < rows ? g[i] : 0.0;
+        x[i] = a * a;
+      }
+      s = butterfly9(x);
+    } else {
+      for (int i = lane; i < rows; i += 32) s += g[i] * g[i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
+    }
     nrm[j] = sqrt(s);
   }
   int order[9];
