@@ -9,15 +9,18 @@
 // once into TENSOR MEMORY as the A operand (TS mode: the stationary operand stays off the shared-memory port); the words
 // stream through an 8-stage TMA ring as 128-row K-major SWIZZLE_128B blocks (the whole vocabulary -- 4 MB at 32 k words --
 // is L2 resident and is read by every CTA); four K = 32-byte tcgen05.mma.kind::i8 per (tile, block) accumulate 128 x 128
-// s32 in TMEM; sixteen epilogue warps (a thread = one descriptor's row of one 64-column half of every block) pull their 64
-// dot products with one LDTM.x64, hand the accumulator back, and fold them into the thread's running top-k (the two halves
-// of a row are merged once per item): per four columns a few
+// s32 in TMEM; eight epilogue warps (one TMEM lane = one descriptor per thread) pull a block's 128 dot products with one
+// LDTM.x128, hand the accumulator back, and fold the block into the thread's running top-k: per four columns a few
 // integer instructions (scores, their maximum, one vote against a register copy of the list's tail) decide warp-uniformly
 // whether anything can enter a list (about one group in six), and only then the out-of-line insertion code runs; the
 // block's |w|^2 reach the lanes as shared-memory broadcasts (staged per warp from one coalesced load).  Words are visited in ascending id and an insertion needs a strictly larger
 // score, so equal scores keep the lower id first -- the oracle's order.
 //
 // TMEM (512 columns): accumulators 2 tiles x 128 columns (ping-pong between the tiles), A operand 2 buffers x 2 tiles x 32.
+//
+// Measured alternative (round 2, session 14): 16 epilogue warps, each thread folding one 64-column half of every block and
+// the halves merged per item, were SLOWER (89 vs 52 ms per 2 M descriptors x 32 k words): two half-streams warm up two
+// lists, so the insertion events -- the expensive part -- nearly double (14.5 G vs 10.9 G instructions).
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -33,10 +36,8 @@ constexpr int kSuperRows = 256;
 constexpr int kTileRows = 128;
 constexpr int kN = 128;                     // UMMA N = words per block
 constexpr int kStagesY = 8;
-constexpr int kNumEpiWarps = 16;                     // 2 tiles x 2 column halves x 4 TMEM lane quadrants
-constexpr int kNumLoadWarps = 8;                     // the half-0 warps also write the descriptors (A operand) into TMEM
-constexpr int kThreads = 64 + 32 * kNumEpiWarps;     // 576
-constexpr int kHalf = 64;                            // columns of a block per epilogue thread
+constexpr int kNumEpiWarps = 8;
+constexpr int kThreads = 64 + 32 * kNumEpiWarps;     // 320
 constexpr uint32_t kYBytes = kN * kDescBytes;        // 16 KiB per stage
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kAccCol = 0;
@@ -44,9 +45,8 @@ constexpr uint32_t kACol = 256;
 constexpr uint32_t kSmemY = 0;
 constexpr uint32_t kSmemBar = kStagesY * kYBytes;
 constexpr uint32_t kNumBars = 2 * kStagesY + 8;
-constexpr uint32_t kSmemWsq = kSmemBar + kNumBars * 8 + 16;   // per epilogue warp: the |w|^2 of its 64 columns of the current block
-constexpr uint32_t kSmemMerge = kSmemWsq + kNumEpiWarps * kHalf * 4;   // half-1 lists of an item: [2 parities][256 rows][8][2] ints
-constexpr uint32_t kSmemTotal = kSmemMerge + 2 * kSuperRows * 8 * 2 * 4;
+constexpr uint32_t kSmemWsq = kSmemBar + kNumBars * 8 + 16;   // per epilogue warp: the |w|^2 of the current block (128 ints)
+constexpr uint32_t kSmemTotal = kSmemWsq + kNumEpiWarps * kN * 4;
 constexpr int kInvalidWord = 0x7fffffff;
 constexpr int kNever = -0x7fffffff;         // score of a padding word (|w|^2 = INT_MAX, d.w = 0): never strictly above the initial lists
 
@@ -79,23 +79,6 @@ __device__ __noinline__ int offer4(int* bd, int* bw, int s0, int s1, int s2, int
   return tail;
 }
 
-// Offers one (score, word) of the other column half's list: ahead of the first entry with a smaller score, or the same score
-// and a larger word id (the lists are ordered by score descending, word ascending; the two halves interleave in word id).
-template <int K>
-__device__ __forceinline__ void offer_ordered(int* bd, int* bw, int sc, int w) {
-  int cd = sc, cw = w;
-  bool placed = false;
-#pragma unroll
-  for (int k = 0; k < K; ++k) {
-    const int td = bd[k], tw = bw[k];
-    if (placed || cd > td || (cd == td && cw < tw)) {
-      bd[k] = cd; bw[k] = cw;
-      cd = td; cw = tw;
-      placed = true;
-    }
-  }
-}
-
 template <int K>
 __global__ void __launch_bounds__(kThreads, 1)
 word_knn_tc_kernel(const __grid_constant__ CUtensorMap tmap_words, const uint8_t* __restrict__ desc, long long n_desc,
@@ -122,10 +105,10 @@ word_knn_tc_kernel(const __grid_constant__ CUtensorMap tmap_words, const uint8_t
       mbar_init(y_empty(s), 1);
     }
     for (uint32_t s = 0; s < 2; ++s) {
-      mbar_init(a_full(s), kNumLoadWarps);
+      mbar_init(a_full(s), kNumEpiWarps);
       mbar_init(a_empty(s), 1);
       mbar_init(t_full(s), 1);
-      mbar_init(t_empty(s), kNumEpiWarps / 2);   // both column halves of a tile have read it
+      mbar_init(t_empty(s), kNumEpiWarps / 2);
     }
     mbar_fence_init();
   }
@@ -191,18 +174,12 @@ word_knn_tc_kernel(const __grid_constant__ CUtensorMap tmap_words, const uint8_t
     }
   } else {
     // ================================================= epilogue (+ A-operand loader)
-    // 16 warps: warp (tile, half, quadrant) owns TMEM lanes [32 q, 32 q + 32) of accumulator `tile` and the columns
-    // [64 half, 64 half + 64) of every block; four warps per scheduler hide the epilogue's dependent chains.  The two halves
-    // of a descriptor's row keep separate top-k lists and are merged once per item through shared memory.
     const int ew = warp - 2;
-    const uint32_t quad = warp & 3;              // tcgen05.ld: a warp reaches the lanes of its own quadrant (warp id mod 4)
-    const uint32_t tile = (ew >> 2) & 1;
-    const uint32_t half = ew >> 3;
+    const uint32_t quad = warp & 3;
+    const uint32_t tile = ew >> 2;
     const uint32_t lane_addr = (quad * 32u) << 16;
     const uint32_t row_in_item = tile * 128 + quad * 32 + lane;
-    uint8_t* const smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
-    int4* const wsq_sm = reinterpret_cast<int4*>(smem_al + kSmemWsq) + ew * (kHalf / 4);
-    int* const merge_sm = reinterpret_cast<int*>(smem_al + kSmemMerge);
+    int4* const wsq_sm = reinterpret_cast<int4*>(smem_raw + (smem_base - smem_u32(smem_raw)) + kSmemWsq) + ew * (kN / 4);
     auto load_a = [&](uint32_t item, uint32_t xi) {
       const uint32_t ab = xi & 1;
       mbar_wait(a_empty(ab), ((xi >> 1) & 1) ^ 1);
@@ -226,31 +203,31 @@ word_knn_tc_kernel(const __grid_constant__ CUtensorMap tmap_words, const uint8_t
       if (lane == 0) mbar_arrive(a_full(ab));
     };
     uint32_t tb = 0, xi = 0;
-    if (half == 0 && blockIdx.x < n_items) load_a(blockIdx.x, 0);
+    if (blockIdx.x < n_items) load_a(blockIdx.x, 0);
     for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-      if (half == 0 && item + gridDim.x < n_items) load_a(item + gridDim.x, xi + 1);
+      if (item + gridDim.x < n_items) load_a(item + gridDim.x, xi + 1);
       int bd[K], bw[K];
 #pragma unroll
       for (int k = 0; k < K; ++k) { bd[k] = kNever; bw[k] = kInvalidWord; }
       int tail = kNever;
       for (uint32_t b = 0; b < n_blk; ++b) {
-        // this half block's |w|^2: one coalesced load per warp, issued before the wait so that its latency hides behind the MMAs
-        const int2 wq_mine = __ldg(reinterpret_cast<const int2*>(word_sq + (size_t)b * kN + half * kHalf) + lane);
+        // this block's |w|^2: one coalesced load per warp, issued before the wait so that its latency hides behind the MMAs
+        const int4 wq_mine = __ldg(reinterpret_cast<const int4*>(word_sq + (size_t)b * kN) + lane);
         mbar_wait(t_full(tile), tb & 1);
         tc_fence_after();
-        uint32_t v[kHalf];
-        tmem_ld_32x32b_x64_wait(tmem_base + lane_addr + kAccCol + tile * kN + half * kHalf, v);
+        uint32_t v[128];
+        tmem_ld_32x32b_x128_wait(tmem_base + lane_addr + kAccCol + tile * kN, v);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(t_empty(tile));
-        reinterpret_cast<int2*>(wsq_sm)[lane] = wq_mine;   // the previous block's reads are complete (same warp, program order)
+        wsq_sm[lane] = wq_mine;   // the previous block's reads of this buffer are complete (same warp, program order)
         __syncwarp();
-        const int w0 = (int)(b * kN + half * kHalf);
+        const int w0 = (int)(b * kN);
         int4 qn = wsq_sm[0];          // the same address in every lane: a shared-memory broadcast, fetched one group ahead
 #pragma unroll
-        for (int g = 0; g < kHalf / 4; ++g) {
+        for (int g = 0; g < 32; ++g) {
           const int4 q = qn;
-          qn = wsq_sm[(g + 1) & (kHalf / 4 - 1)];
+          qn = wsq_sm[(g + 1) & 31];
           const int s0 = 2 * (int)v[4 * g] - q.x, s1 = 2 * (int)v[4 * g + 1] - q.y;
           const int s2 = 2 * (int)v[4 * g + 2] - q.z, s3 = 2 * (int)v[4 * g + 3] - q.w;
           const int m = max(__vimax3_s32(s0, s1, s2), s3);
@@ -261,26 +238,10 @@ word_knn_tc_kernel(const __grid_constant__ CUtensorMap tmap_words, const uint8_t
         __syncwarp();
         ++tb;
       }
-      // merge the two column halves of every row: half 1 publishes its list, half 0 folds it in and writes the result.  The
-      // buffer alternates with the item's parity, so one barrier per item is enough (a buffer is rewritten two items later,
-      // after the barrier of the item in between, which its readers have passed).
-      int* slot = merge_sm + ((size_t)(xi & 1) * kSuperRows + row_in_item) * 16;
-      if (half == 1) {
+      const long long row = (long long)item * kSuperRows + row_in_item;
+      if (row < n_desc) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) { slot[2 * k] = bd[k]; slot[2 * k + 1] = bw[k]; }
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * kNumEpiWarps) : "memory");
-      if (half == 0) {
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-          const int sd = slot[2 * k], sw = slot[2 * k + 1];
-          if (sw != kInvalidWord) offer_ordered<K>(bd, bw, sd, sw);
-        }
-        const long long row = (long long)item * kSuperRows + row_in_item;
-        if (row < n_desc) {
-#pragma unroll
-          for (int k = 0; k < K; ++k) out[row * K + k] = bw[k];
-        }
+        for (int k = 0; k < K; ++k) out[row * K + k] = bw[k];
       }
       ++xi;
     }
