@@ -390,10 +390,14 @@ def bench_ba(a, local_rank, rank, world, cores, barrier, hbm):
            "rms_px_initial": reprojection_rms(prob0), "rms_px_final": reprojection_rms(prob),
            "mean_reproj_error_px_final": _mean_reproj(prob),
            "rms_note": "this rank's point shard" if world > 1 else "all observations",
-           "sharding": f"points over {world} ranks, 1 ncclAllReduce (library-owned communicator, solver stream) of the packed reduced camera system per LM iteration" if world > 1 else "single GPU",
+           "sharding": "single GPU" if world == 1 else
+                       (f"points over {world} ranks, 1 ncclAllReduce (library-owned communicator, solver stream) of D doubles per inner CG iteration "
+                        "(+ rhs / preconditioner blocks once per LM iteration)" if s.linear_solver_type_used == 2 else
+                        f"points over {world} ranks, 1 ncclAllReduce (library-owned communicator, solver stream) of the packed reduced camera system per LM iteration"),
            "ceres_style_px": float(np.sqrt(s.final_cost / (2 * n_obs))),
            "roofline": {"bound": "hbm", "kernel": "camera_terms_kernel + schur_points_kernel + schur_window_kernel (Jacobian + Schur complement)", "achieved": achieved,
-                        "peak": hbm[0], "unit": "GB/s", "frac": achieved / hbm[0], "peak_source": hbm[1],
+                        "peak": hbm[0] * world, "unit": "GB/s", "frac": achieved / (hbm[0] * world),
+                        "peak_source": hbm[1] + (f" x {world} GPUs (whole-job bytes against the aggregate)" if world > 1 else ""),
                         "algorithmic_bytes_per_iteration": alg_bytes, "avg_ms_per_iteration": schur_ms,
                         "share_of_solve": s.schur_kernel_seconds / s.solve_seconds, "traffic": None,
                         "note": "algorithmic bytes count the full upper triangle of S as SURVEY 8d does; see DESIGN.md section 3"}}
@@ -412,8 +416,9 @@ def bench_ba(a, local_rank, rank, world, cores, barrier, hbm):
         out["cg_iterations"] = int(s.num_linear_solver_iterations)
         out["roofline"] = {"bound": "hbm", "kernel": "matvec_point_kernel + image_pass_kernel<0> (per CG iteration; includes the "
                            "preconditioner set-up and the host-side reductions of the inner solve)",
-                           "achieved": alg_cg / (lin_ms * 1e-3) / 1e9, "peak": hbm[0], "unit": "GB/s",
-                           "frac": alg_cg / (lin_ms * 1e-3) / 1e9 / hbm[0], "peak_source": hbm[1],
+                           "achieved": alg_cg / (lin_ms * 1e-3) / 1e9, "peak": hbm[0] * world, "unit": "GB/s",
+                           "frac": alg_cg / (lin_ms * 1e-3) / 1e9 / (hbm[0] * world),
+                           "peak_source": hbm[1] + (f" x {world} GPUs (whole-job bytes against the aggregate)" if world > 1 else ""),
                            "algorithmic_bytes_per_cg_iteration": alg_cg, "avg_ms_per_cg_iteration": lin_ms,
                            "share_of_solve": s.schur_kernel_seconds / s.solve_seconds, "traffic": None}
     if (n_img, n_pts, track) == (500, 100000, 10) and world == 1 and s.linear_solver_type_used != 2 and s.exact_path_used == 2:
@@ -890,7 +895,10 @@ def main():
         ef = (g["E_num_trials"].astype(np.float64) + g["F_num_trials"]) * mexp
         hh = g["H_num_trials"].astype(np.float64) * mexp
         flops = a.steps * float(33.0 * ef.sum() + 25.0 * hh.sum())
-        roofline.update({"achieved": flops / pl["verify_kernel_s"] / 1e12, "frac": flops / pl["verify_kernel_s"] / 1e12 / peak64,
+        roofline["peak"] = peak64 * world
+        if world > 1:
+            roofline["peak_source"] = peak64_src + f" x {world} GPUs (whole-job flops against the aggregate)"
+        roofline.update({"achieved": flops / pl["verify_kernel_s"] / 1e12, "frac": flops / pl["verify_kernel_s"] / 1e12 / (peak64 * world),
                          "algorithmic_flop_per_unit": "33 (E, F Sampson) / 25 (H transfer) per hypothesis x match",
                          "units_per_step_min": float(ef.sum() + hh.sum()), "mean_matches_per_pair_expected": float(mexp.mean())})
     except Exception as e:
