@@ -609,6 +609,41 @@ def bench_pipeline(a, dev, local_rank, rank, world, cores, barrier, dist):
     return out
 
 
+def bench_retrieval_sharded(a, coll, local_rank, rank, world, barrier, dist, pairs_all):
+    """The retrieval stage on N GPUs: every rank searches the visual words of its images, ONE all-gather of the word ids
+    (NCCL), every rank builds the same inverted index and queries its own images, rank 0 gathers the candidate pairs."""
+    import torch
+    from dagsfm_b200.retrieval import VocabSimilarityGraph
+    from dagsfm_b200.synthetic import make_vocabulary_device
+    n_img, n_kp = a.seq_images, a.seq_kp
+    box = [make_vocabulary_device(coll["desc"], a.retrieval_words, n_train=min(1 << 20, n_img * n_kp), seed=7) if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    g = VocabSimilarityGraph(box[0], num_images=a.seq_cand, num_nearest_neighbors=5, device=local_rank)
+    walls = []
+    pairs = None
+    for s in range(1 + 2):
+        barrier()
+        t0 = time.perf_counter()
+        pairs, _sc = g.RunSharded(coll["desc"], rank, world, dist)
+        barrier()
+        walls.append(time.perf_counter() - t0)
+    w = float(np.mean(walls[1:]))
+    t = torch.tensor([g.timing.get("word_search_s", 0.0), g.timing.get("index_build_s", 0.0), g.timing.get("query_s", 0.0)],
+                     dtype=torch.float64, device=coll["desc"].device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        return None
+    got = set(map(tuple, pairs.tolist()))
+    near = pairs_all[(pairs_all[:, 1].astype(np.int64) - pairs_all[:, 0]) <= max(a.seq_cand // 2, 1)]
+    return {"workload": f"{n_img} images x {n_kp} descriptors, {a.retrieval_words} visual words, num_neighbors 5, max_num_images {a.seq_cand}",
+            "images_per_s": n_img / w, "wall_s_per_step": w, "word_search_s": t[0].item(), "index_build_s": t[1].item(), "query_s": t[2].item(),
+            "timing_note": "kernel times = max over ranks of the last step; wall = the whole stage incl. the all-gather and the gather of the pairs",
+            "candidate_pairs": len(pairs),
+            "recall_of_overlapping_pairs": float(np.mean([tuple(p) in got for p in near.tolist()])) if len(near) else None,
+            "sharding": f"word search and queries of {n_img} images over {world} ranks (contiguous image ranges), 1 all-gather of the word ids "
+                        f"({n_img * n_kp * 5 * 4 / 1e6:.0f} MB) per step, inverted index replicated, candidate pairs gathered on rank 0"}
+
+
 def bench_retrieval(a, coll, local_rank, cores, pairs_all):
     """SURVEY 8f rank 3 / the input stage of C3: VocabSimilarityGraph::Run (similarity_graph.cpp:101-200) over the C3
     collection resident in HBM -- exact nearest visual words of every descriptor, inverted index, query of every image,
@@ -838,7 +873,9 @@ def main():
                "identical_means": "configuration, inlier and trial counts, E / F / H bit for bit, on matches the oracle computed itself"}
     fm.close()
     retrieval = None
-    if rank == 0 and a.retrieval_words > 0:
+    if a.retrieval_words > 0 and world > 1:
+        retrieval = bench_retrieval_sharded(a, coll, local_rank, rank, world, barrier, dist, pairs_all)   # collective: every rank
+    elif rank == 0 and a.retrieval_words > 0:
         try:
             retrieval = bench_retrieval(a, coll, local_rank, cores, pairs_all)
         except Exception as e:   # an extra leg must not take the headline line down

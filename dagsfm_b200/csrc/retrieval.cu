@@ -411,6 +411,27 @@ struct b2_retrieval {
 
 namespace {
 template <class T> void fr(T*& p) { if (p) cudaFree(p); p = nullptr; }
+// Call-scoped device buffers: freed on every way out of the function (the pointer VARIABLES are tracked, so a buffer that
+// was swapped with a handle-owned one is the one released).
+struct ScopedDev {
+  std::vector<void**> vars;
+  std::vector<cudaEvent_t> events;
+  template <class T> cudaError_t alloc(T** var, size_t bytes) {
+    *var = nullptr;
+    const cudaError_t e = cudaMalloc(reinterpret_cast<void**>(var), bytes);
+    if (e == cudaSuccess) vars.push_back(reinterpret_cast<void**>(var));
+    return e;
+  }
+  cudaError_t event(cudaEvent_t* ev) {
+    const cudaError_t e = cudaEventCreate(ev);
+    if (e == cudaSuccess) events.push_back(*ev);
+    return e;
+  }
+  ~ScopedDev() {
+    for (void** v : vars) if (*v) cudaFree(*v);
+    for (cudaEvent_t ev : events) cudaEventDestroy(ev);
+  }
+};
 
 // SIMT statement of the word search (test seam)
 int knn_simt(b2_retrieval* r, const uint8_t* d_desc, int64_t n, int k, int32_t* d_out) {
@@ -566,7 +587,8 @@ int b2_retrieval_set_vocabulary(b2_retrieval* r, int32_t n_words, const uint8_t*
 
 // VisualIndex::Add for every image (IndexOptions::num_neighbors = 1) + Prepare().  k_query = the number of nearest
 // words kept per descriptor for b2_retrieval_query_all (QueryOptions::num_neighbors; the first of them is the indexing word).
-static int index_impl(b2_retrieval* r, int32_t n_images, const uint8_t* d_desc, bool own, const int64_t* desc_off_host, int32_t k_query) {
+static int index_impl(b2_retrieval* r, int32_t n_images, const uint8_t* d_desc, bool own, const int64_t* desc_off_host, int32_t k_query,
+                      const int32_t* d_word_ids = nullptr) {
   if (r->n_words == 0) return set_error(B2_ERR_INVALID, "no vocabulary set");
   if (k_query < 1 || k_query > rt::kMaxK) return set_error(B2_ERR_INVALID, "num_neighbors must be in [1, 8]");
   cudaStream_t s = r->stream;
@@ -583,7 +605,11 @@ static int index_impl(b2_retrieval* r, int32_t n_images, const uint8_t* d_desc, 
   B2_CUDA(cudaMalloc(&r->d_nn, std::max<size_t>((size_t)n * k_query, 1) * 4));
   B2_CUDA(cudaMalloc(&r->d_norm, std::max<size_t>(n_images, 1) * 4));
   B2_CUDA(cudaEventRecord(r->ev0, s));
-  B2_TRY(knn(r, r->d_desc, n, k_query, r->d_nn));
+  if (d_word_ids) {  // the word search ran elsewhere (sharded over the ranks of a multi-GPU job, all-gathered by the caller)
+    if (n > 0) B2_CUDA(cudaMemcpyAsync(r->d_nn, d_word_ids, (size_t)n * k_query * 4, cudaMemcpyDeviceToDevice, s));
+  } else {
+    B2_TRY(knn(r, r->d_desc, n, k_query, r->d_nn));
+  }
   B2_CUDA(cudaEventRecord(r->ev1, s));
   // per-feature image / index-in-image (host: cheap, once)
   std::vector<int32_t> fimg((size_t)std::max<int64_t>(n, 1)), fidx((size_t)std::max<int64_t>(n, 1));
@@ -595,19 +621,20 @@ static int index_impl(b2_retrieval* r, int32_t n_images, const uint8_t* d_desc, 
   int32_t *d_fimg = nullptr, *d_fidx = nullptr;
   uint32_t *d_count = nullptr, *d_cursor = nullptr;
   rt::Entry* d_staged = nullptr;
-  B2_CUDA(cudaMalloc(&d_fimg, fimg.size() * 4));
-  B2_CUDA(cudaMalloc(&d_fidx, fidx.size() * 4));
-  B2_CUDA(cudaMalloc(&d_count, ((size_t)r->n_words + 1) * 4));
-  B2_CUDA(cudaMalloc(&d_cursor, (size_t)r->n_words * 4));
-  B2_CUDA(cudaMalloc(&d_staged, std::max<size_t>(n, 1) * sizeof(rt::Entry)));
+  ScopedDev tmp;
+  B2_CUDA(tmp.alloc(&d_fimg, fimg.size() * 4));
+  B2_CUDA(tmp.alloc(&d_fidx, fidx.size() * 4));
+  B2_CUDA(tmp.alloc(&d_count, ((size_t)r->n_words + 1) * 4));
+  B2_CUDA(tmp.alloc(&d_cursor, (size_t)r->n_words * 4));
+  B2_CUDA(tmp.alloc(&d_staged, std::max<size_t>(n, 1) * sizeof(rt::Entry)));
   B2_CUDA(cudaMalloc(&r->d_entries, std::max<size_t>(n, 1) * sizeof(rt::Entry)));
   B2_CUDA(cudaMemcpyAsync(d_fimg, fimg.data(), fimg.size() * 4, cudaMemcpyHostToDevice, s));
   B2_CUDA(cudaMemcpyAsync(d_fidx, fidx.data(), fidx.size() * 4, cudaMemcpyHostToDevice, s));
   B2_CUDA(cudaMemsetAsync(d_count, 0, ((size_t)r->n_words + 1) * 4, s));
   B2_CUDA(cudaMemsetAsync(d_cursor, 0, (size_t)r->n_words * 4, s));
   cudaEvent_t e2, e3;
-  B2_CUDA(cudaEventCreate(&e2));
-  B2_CUDA(cudaEventCreate(&e3));
+  B2_CUDA(tmp.event(&e2));
+  B2_CUDA(tmp.event(&e3));
   B2_CUDA(cudaEventRecord(e2, s));
   r->h_img_off.assign(desc_off_host, desc_off_host + n_images + 1);
   if (n > 0) {
@@ -645,21 +672,23 @@ static int index_impl(b2_retrieval* r, int32_t n_images, const uint8_t* d_desc, 
   r->last_seconds[0] = ms * 1e-3;
   B2_CUDA(cudaEventElapsedTime(&ms, e2, e3));
   r->last_seconds[1] = ms * 1e-3;
-  cudaEventDestroy(e2);
-  cudaEventDestroy(e3);
   r->n_entries = n;
-  fr(d_fimg); fr(d_fidx); fr(d_count); fr(d_cursor); fr(d_staged);
   return B2_OK;
 }
 
 int b2_retrieval_index_images(b2_retrieval* r, int32_t n_images, const uint8_t* descriptors, const int64_t* desc_offsets, int32_t num_neighbors_query) {
   if (!r || n_images < 0 || !desc_offsets || (desc_offsets[n_images] > 0 && !descriptors)) return set_error(B2_ERR_INVALID, "bad argument");
+  if (r->n_words == 0) return set_error(B2_ERR_INVALID, "no vocabulary set");
+  if (num_neighbors_query < 1 || num_neighbors_query > rt::kMaxK) return set_error(B2_ERR_INVALID, "num_neighbors must be in [1, 8]");
   B2_CUDA(cudaSetDevice(r->device));
   const int64_t n = desc_offsets[n_images];
   uint8_t* d = nullptr;
   B2_CUDA(cudaMalloc(&d, std::max<size_t>((size_t)n * rt::kDim, 16)));
-  if (n) B2_CUDA(cudaMemcpyAsync(d, descriptors, (size_t)n * rt::kDim, cudaMemcpyHostToDevice, r->stream));
-  return index_impl(r, n_images, d, true, desc_offsets, num_neighbors_query);
+  if (n && cudaMemcpyAsync(d, descriptors, (size_t)n * rt::kDim, cudaMemcpyHostToDevice, r->stream) != cudaSuccess) {
+    cudaFree(d);
+    return set_error(B2_ERR_CUDA, "descriptor upload failed");
+  }
+  return index_impl(r, n_images, d, true, desc_offsets, num_neighbors_query);   // the handle owns d from here on
 }
 
 int b2_retrieval_index_images_device(b2_retrieval* r, int32_t n_images, const uint8_t* descriptors_dev, const int64_t* desc_offsets_host,
@@ -669,18 +698,55 @@ int b2_retrieval_index_images_device(b2_retrieval* r, int32_t n_images, const ui
   return index_impl(r, n_images, descriptors_dev, false, desc_offsets_host, num_neighbors_query);
 }
 
+// Multi-GPU: the word search of a rank's share of the descriptors (n_desc rows at descriptors_dev) into the caller's device
+// buffer, and the index built from word ids that the ranks exchanged (all-gather; the one collective of the stage).
+int b2_retrieval_word_search_device(b2_retrieval* r, const uint8_t* descriptors_dev, int64_t n_desc, int32_t num_neighbors,
+                                    int32_t* out_word_ids_dev) {
+  if (!r || n_desc < 0 || (n_desc > 0 && (!descriptors_dev || !out_word_ids_dev))) return set_error(B2_ERR_INVALID, "bad argument");
+  if (r->n_words == 0) return set_error(B2_ERR_INVALID, "no vocabulary set");
+  if (num_neighbors < 1 || num_neighbors > rt::kMaxK) return set_error(B2_ERR_INVALID, "num_neighbors must be in [1, 8]");
+  B2_CUDA(cudaSetDevice(r->device));
+  B2_CUDA(cudaEventRecord(r->ev0, r->stream));
+  B2_TRY(knn(r, descriptors_dev, n_desc, num_neighbors, out_word_ids_dev));
+  B2_CUDA(cudaEventRecord(r->ev1, r->stream));
+  B2_CUDA(cudaStreamSynchronize(r->stream));
+  float ms = 0;
+  B2_CUDA(cudaEventElapsedTime(&ms, r->ev0, r->ev1));
+  r->last_seconds[0] = ms * 1e-3;
+  return B2_OK;
+}
+int b2_retrieval_index_images_words_device(b2_retrieval* r, int32_t n_images, const uint8_t* descriptors_dev, const int64_t* desc_offsets_host,
+                                           int32_t num_neighbors_query, const int32_t* word_ids_dev) {
+  if (!r || n_images < 0 || !desc_offsets_host || !descriptors_dev || !word_ids_dev) return set_error(B2_ERR_INVALID, "bad argument");
+  B2_CUDA(cudaSetDevice(r->device));
+  const double searched = r->last_seconds[0];
+  const int rc = index_impl(r, n_images, descriptors_dev, false, desc_offsets_host, num_neighbors_query, word_ids_dev);
+  r->last_seconds[0] = searched;   // the word search was this rank's b2_retrieval_word_search_device call
+  return rc;
+}
+
 // VisualIndex::Query of every indexed image against the index (VocabSimilarityGraph::Run's retrieval loop).
 int b2_retrieval_query_all(b2_retrieval* r, int32_t max_num_images, int32_t* out_ids, float* out_scores, int32_t* out_counts) {
+  if (!r) return set_error(B2_ERR_INVALID, "bad argument");
+  return b2_retrieval_query_range(r, 0, r->n_images, max_num_images, out_ids, out_scores, out_counts);
+}
+
+// The same for the query images [q0, q1) only (a rank's share of a multi-GPU job); outputs are indexed from q0.
+int b2_retrieval_query_range(b2_retrieval* r, int32_t q0, int32_t q1, int32_t max_num_images, int32_t* out_ids, float* out_scores,
+                             int32_t* out_counts) {
   if (!r || max_num_images <= 0 || !out_ids || !out_scores || !out_counts) return set_error(B2_ERR_INVALID, "bad argument");
   if (!r->d_entries || r->n_images == 0) return set_error(B2_ERR_INVALID, "no images indexed");
+  if (q0 < 0 || q1 < q0 || q1 > r->n_images) return set_error(B2_ERR_INVALID, "query range outside the indexed images");
+  if (q1 == q0) return B2_OK;
   B2_CUDA(cudaSetDevice(r->device));
   cudaStream_t s = r->stream;
-  const int N = r->n_images, Q = r->n_images;
+  const int N = r->n_images, Q = q1 - q0;
   int32_t *d_ids = nullptr, *d_cnt = nullptr;
   float* d_sc = nullptr;
-  B2_CUDA(cudaMalloc(&d_ids, (size_t)Q * max_num_images * 4));
-  B2_CUDA(cudaMalloc(&d_sc, (size_t)Q * max_num_images * 4));
-  B2_CUDA(cudaMalloc(&d_cnt, (size_t)Q * 4));
+  ScopedDev tmp;
+  B2_CUDA(tmp.alloc(&d_ids, (size_t)Q * max_num_images * 4));
+  B2_CUDA(tmp.alloc(&d_sc, (size_t)Q * max_num_images * 4));
+  B2_CUDA(tmp.alloc(&d_cnt, (size_t)Q * 4));
   B2_CUDA(cudaMemsetAsync(d_ids, 0xff, (size_t)Q * max_num_images * 4, s));
   B2_CUDA(cudaMemsetAsync(d_sc, 0, (size_t)Q * max_num_images * 4, s));
   const size_t with_scores = (size_t)N * 4 + (size_t)N + 16;
@@ -690,19 +756,23 @@ int b2_retrieval_query_all(b2_retrieval* r, int32_t max_num_images, int32_t* out
   if (ctas_per_sm < 1) ctas_per_sm = 1;
   const int max_grid = r->n_sm * ctas_per_sm;
   float* d_scratch = nullptr;
-  if (!in_smem) B2_CUDA(cudaMalloc(&d_scratch, (size_t)max_grid * N * 4));
+  if (!in_smem) B2_CUDA(tmp.alloc(&d_scratch, (size_t)max_grid * N * 4));
   B2_CUDA(cudaFuncSetAttribute(rt::query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   rt::QueryArgs A;
   A.q_off = r->d_img_off; A.nn = r->d_nn; A.K = r->nn_k; A.thr = r->d_thr; A.has_emb = r->d_has;
   A.idf = r->d_idf; A.word_start = r->d_word_start; A.entries = r->d_entries; A.norm = r->d_norm; A.lut = r->d_lut; A.n_index_images = N;
-  A.max_num_images = max_num_images; A.out_ids = d_ids; A.out_scores = d_sc; A.out_count = d_cnt; A.score_scratch = d_scratch;
+  // the kernel indexes its outputs by the absolute query image: bias the pointers so that image q0 lands at slot 0
+  A.max_num_images = max_num_images; A.out_ids = d_ids - (size_t)q0 * max_num_images; A.out_scores = d_sc - (size_t)q0 * max_num_images;
+  A.out_count = d_cnt - q0; A.score_scratch = d_scratch;
   B2_CUDA(cudaEventRecord(r->ev0, s));
-  const std::vector<int> bat = image_batches(r->h_img_off);
+  const std::vector<int64_t> sub(r->h_img_off.begin() + q0, r->h_img_off.begin() + q1 + 1);
+  const std::vector<int> bat = image_batches(sub);
   for (size_t b = 0; b + 1 < bat.size(); ++b) {
-    const int64_t f0 = r->h_img_off[bat[b]], f1 = r->h_img_off[bat[b + 1]];
+    const int i0 = q0 + bat[b], i1 = q0 + bat[b + 1];
+    const int64_t f0 = r->h_img_off[i0], f1 = r->h_img_off[i1];
     B2_TRY(project_batch(r, f0, f1));
-    A.P = r->d_P; A.f_base = f0; A.q0 = bat[b]; A.q1 = bat[b + 1];
-    const int grid = std::min(bat[b + 1] - bat[b], max_grid);
+    A.P = r->d_P; A.f_base = f0; A.q0 = i0; A.q1 = i1;
+    const int grid = std::min(i1 - i0, max_grid);
     rt::query_kernel<<<grid, rt::kQueryThreads, smem, s>>>(A, in_smem ? 1 : 0);
     B2_CUDA(cudaGetLastError());
     count_launches(1);
@@ -715,7 +785,6 @@ int b2_retrieval_query_all(b2_retrieval* r, int32_t max_num_images, int32_t* out
   float ms = 0;
   B2_CUDA(cudaEventElapsedTime(&ms, r->ev0, r->ev1));
   r->last_seconds[2] = ms * 1e-3;
-  fr(d_ids); fr(d_sc); fr(d_cnt); fr(d_scratch);
   return B2_OK;
 }
 

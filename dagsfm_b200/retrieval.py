@@ -27,6 +27,9 @@ def _L():
         L.b2_retrieval_index_images.argtypes = [vp, i32, vp, vp, i32]
         L.b2_retrieval_index_images_device.argtypes = [vp, i32, vp, vp, i32]
         L.b2_retrieval_query_all.argtypes = [vp, i32, vp, vp, vp]
+        L.b2_retrieval_query_range.argtypes = [vp, i32, i32, i32, vp, vp, vp]
+        L.b2_retrieval_word_search_device.argtypes = [vp, vp, C.c_int64, i32, vp]
+        L.b2_retrieval_index_images_words_device.argtypes = [vp, i32, vp, vp, i32, vp]
         L.b2_retrieval_debug_word_ids.argtypes = [vp, vp]
         L.b2_retrieval_debug_word_ids_simt.argtypes = [vp, vp]
         L.b2_retrieval_debug_index.argtypes = [vp, vp, vp, vp, vp, vp, vp]
@@ -122,6 +125,27 @@ class VisualIndex:
         check(_L().b2_retrieval_index_images_device(self._h, n_images, C.c_void_p(desc_dev_ptr), off.ctypes.data, num_neighbors_query))
         self._n_desc, self._k, self._n_images = int(off[-1]), num_neighbors_query, n_images
 
+    # ---- multi-GPU: word search of a share of the descriptors, index from exchanged word ids, query of a range of images
+    def word_search_device(self, desc_dev_ptr: int, n_desc: int, num_neighbors: int, out_dev_ptr: int) -> None:
+        check(_L().b2_retrieval_word_search_device(self._h, C.c_void_p(desc_dev_ptr), n_desc, num_neighbors, C.c_void_p(out_dev_ptr)))
+
+    def index_images_words_device(self, desc_dev_ptr: int, n_images: int, n_per_image: int, num_neighbors_query: int,
+                                  word_ids_dev_ptr: int) -> None:
+        off = (np.arange(n_images + 1, dtype=np.int64) * n_per_image)
+        check(_L().b2_retrieval_index_images_words_device(self._h, n_images, C.c_void_p(desc_dev_ptr), off.ctypes.data,
+                                                          num_neighbors_query, C.c_void_p(word_ids_dev_ptr)))
+        self._n_desc, self._k, self._n_images = int(off[-1]), num_neighbors_query, n_images
+
+    def query_range(self, q0: int, q1: int, max_num_images: int):
+        """-> (ids [q1 - q0, max_num_images], scores, counts [q1 - q0]) of the query images q0 .. q1 - 1."""
+        n = max(q1 - q0, 0)
+        ids = np.full((n, max_num_images), -1, np.int32)
+        sc = np.zeros((n, max_num_images), np.float32)
+        cnt = np.zeros(n, np.int32)
+        if n:
+            check(_L().b2_retrieval_query_range(self._h, q0, q1, max_num_images, ids.ctypes.data, sc.ctypes.data, cnt.ctypes.data))
+        return ids, sc, cnt
+
     def query_all(self, max_num_images: int):
         """-> (ids int32 [n_images, max_num_images] (-1 = none), scores float32, counts int32 [n_images])."""
         n = self._n_images
@@ -180,8 +204,52 @@ class VocabSimilarityGraph:
             self.timing = vi.last_timing()
         finally:
             vi.close()
-        q = np.repeat(np.arange(len(ids), dtype=np.int64), ids.shape[1]).reshape(ids.shape)
+        self.image_pairs, self.scores = self._pairs_of(ids, sc, cnt, 0)
+        return self.image_pairs, self.scores
+
+    @staticmethod
+    def _pairs_of(ids, sc, cnt, q0):
+        """(image, other, score * 1e3) for image < other (similarity_graph.cpp:186-191); the rows are queries q0, q0 + 1, ..."""
+        q = q0 + np.repeat(np.arange(len(ids), dtype=np.int64), ids.shape[1]).reshape(ids.shape)
         valid = (np.arange(ids.shape[1])[None, :] < cnt[:, None]) & (q < ids)
-        self.image_pairs = np.ascontiguousarray(np.stack([q[valid], ids[valid]], 1).astype(np.uint32))
-        self.scores = np.ascontiguousarray(sc[valid] * np.float32(1e3))
+        return (np.ascontiguousarray(np.stack([q[valid], ids[valid]], 1).astype(np.uint32)),
+                np.ascontiguousarray(sc[valid] * np.float32(1e3)))
+
+    def RunSharded(self, desc, rank: int, world: int, dist):
+        """The same stage on `world` GPUs (one process each, `dist` = an initialised torch.distributed): rank r searches the
+        words of ITS images, the ranks all-gather the word ids (the stage's one collective), every rank builds the same
+        inverted index and queries its own images; rank 0 receives all candidate pairs in query order (others return empty
+        lists).  desc: torch uint8 [n_images, n_per_image, 128] resident on this rank's device (the collection is replicated,
+        as the matcher needs it)."""
+        import torch
+        n_img, n_kp = int(desc.shape[0]), int(desc.shape[1])
+        k = self.num_nearest_neighbors
+        bounds = [(n_img * r) // world for r in range(world + 1)]
+        lo, hi = bounds[rank], bounds[rank + 1]
+        per = max(bounds[r + 1] - bounds[r] for r in range(world)) * n_kp * k
+        vi = VisualIndex(self.device)
+        try:
+            vi.set_vocabulary(self.vocabulary)
+            mine = torch.full((max(per, 1),), 0x7fffffff, dtype=torch.int32, device=desc.device)
+            if desc.is_cuda:
+                torch.cuda.current_stream(desc.device).synchronize()
+            vi.word_search_device(desc[lo:hi].data_ptr() if hi > lo else desc.data_ptr(), (hi - lo) * n_kp, k, mine.data_ptr())
+            parts = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(parts, mine)
+            words = torch.cat([parts[r][:(bounds[r + 1] - bounds[r]) * n_kp * k] for r in range(world)]).contiguous()
+            if desc.is_cuda:
+                torch.cuda.current_stream(desc.device).synchronize()
+            vi.index_images_words_device(desc.data_ptr(), n_img, n_kp, k, words.data_ptr())
+            ids, sc, cnt = vi.query_range(lo, hi, self.num_images)
+            self.timing = vi.last_timing()
+        finally:
+            vi.close()
+        pairs, scores = self._pairs_of(ids, sc, cnt, lo)
+        gathered = [None] * world if rank == 0 else None
+        dist.gather_object((pairs, scores), gathered, dst=0)
+        if rank == 0:
+            self.image_pairs = np.concatenate([g[0] for g in gathered]) if gathered else pairs
+            self.scores = np.concatenate([g[1] for g in gathered]) if gathered else scores
+        else:
+            self.image_pairs, self.scores = np.zeros((0, 2), np.uint32), np.zeros(0, np.float32)
         return self.image_pairs, self.scores

@@ -430,6 +430,18 @@ int b2_retrieval_index_images_device(b2_retrieval* r, int32_t n_images, const ui
  * out_counts[q], sorted by descending score (equal scores: lower image id first); the image itself is among its results,
  * as in the reference (the caller keeps pairs with image_id < other, similarity_graph.cpp:186-191).  HOST buffers. */
 int b2_retrieval_query_all(b2_retrieval* r, int32_t max_num_images, int32_t* out_ids, float* out_scores, int32_t* out_counts);
+/* The same for the query images [q0, q1) only; outputs are indexed from q0 (out_ids [(q - q0) * max_num_images + k]). */
+int b2_retrieval_query_range(b2_retrieval* r, int32_t q0, int32_t q1, int32_t max_num_images, int32_t* out_ids, float* out_scores,
+                             int32_t* out_counts);
+/* Multi-GPU (one handle per GPU, vocabulary set on each): a rank searches the words of ITS share of the descriptors
+ * (b2_retrieval_word_search_device: n_desc rows at descriptors_dev -> out_word_ids_dev [n_desc * num_neighbors], device
+ * buffers), the ranks all-gather the word ids (the stage's one collective; NCCL, by the caller), every rank builds the
+ * same index from them (b2_retrieval_index_images_words_device: all descriptors resident, word_ids_dev [n_total *
+ * num_neighbors_query]) and queries its own range of images (b2_retrieval_query_range). */
+int b2_retrieval_word_search_device(b2_retrieval* r, const uint8_t* descriptors_dev, int64_t n_desc, int32_t num_neighbors,
+                                    int32_t* out_word_ids_dev);
+int b2_retrieval_index_images_words_device(b2_retrieval* r, int32_t n_images, const uint8_t* descriptors_dev,
+                                           const int64_t* desc_offsets_host, int32_t num_neighbors_query, const int32_t* word_ids_dev);
 /* Test hooks: nearest words of the indexed descriptors [n_desc * num_neighbors_query]; the inverted index (any pointer may
  * be NULL): word_start [n_words + 1], per entry image / feature / 64-bit signature, idf [n_words], norm [n_images]. */
 int b2_retrieval_debug_word_ids(b2_retrieval* r, int32_t* out);

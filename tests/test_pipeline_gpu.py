@@ -132,3 +132,39 @@ def test_sift_feature_matcher_match_equals_the_oracle_chain_and_keeps_the_refere
         assert fm.Match(noisy, cache) == 1 and cache.ExistsInlierMatches(a, b)
     finally:
         fm.close()
+
+
+def test_c3_chain_retrieval_to_match_to_verify_on_one_descriptor_pool():
+    """BASELINE configs[2] at reduced size, end to end on the device: candidate pairs from the vocabulary tree
+    (VocabSimilarityGraph::Run, similarity_graph.cpp:101-200) over the SAME descriptor tensor the matcher reads, then
+    SiftFeatureMatcher's match -> verify chain on exactly those pairs; a sample of the results is replayed on the oracle
+    (MatchSiftFeaturesCPU -> TwoViewGeometry::Estimate), and the retrieved list contains the truly overlapping pairs."""
+    from dagsfm_b200 import SiftMatchingOptions, TwoViewOptions, VocabSimilarityGraph
+    from dagsfm_b200.pipeline import SiftFeatureMatcher, cameras_of
+    from dagsfm_b200.synthetic import make_image_collection, make_vocabulary_device
+    n_img, n_kp = 48, 768
+    w = make_image_collection(n_img, n_kp, seed=8, device="cuda", overlap_images=6)
+    vocab = make_vocabulary_device(w["desc"], 2048, n_train=n_img * n_kp, seed=4)
+    graph = VocabSimilarityGraph(vocab, num_images=8, num_nearest_neighbors=5)
+    pairs, scores = graph.Run(device_descriptors=(w["desc"].data_ptr(), n_img, n_kp))
+    got = {(int(a), int(b)) for a, b in pairs}
+    near = {(i, j) for i in range(n_img) for j in range(i + 1, min(i + 4, n_img))}
+    assert len(near & got) >= 0.95 * len(near)
+    seeds = (np.arange(len(pairs), dtype=np.uint32) * 2654435761 % (2 ** 32)).astype(np.uint32)
+    fm = SiftFeatureMatcher(SiftMatchingOptions(), TwoViewOptions.default(), 0, chunk_pairs=64)
+    try:
+        fm.setup_device_descriptors(w["desc"].data_ptr(), n_img, n_kp, w["keypoints"], cameras_of(w))
+        res, off, mt, inl = fm.run_device(pairs, seeds, keep_lists=True)
+        d = w["desc"].cpu().numpy()
+        assert (res["config"] > 1).sum() >= len(near) * 0.9          # the overlapping pairs verify
+        for k in range(0, len(pairs), max(len(pairs) // 12, 1)):
+            a, b = int(pairs[k][0]), int(pairs[k][1])
+            em = orc.match_sift(d[a], d[b])
+            assert mt[off[k]:off[k + 1]].tolist() == em.tolist()
+            ca, cb = (orc.make_camera(params=w["cam_params"], prior=bool(w["prior"][i])) for i in (a, b))
+            with orc.solver_stack(1):
+                r, oi = orc.two_view(ca, w["keypoints"][a], cb, w["keypoints"][b], em, seed=int(seeds[k]))
+            assert res["config"][k] == r.config and res["n_inliers"][k] == r.n_inliers
+            assert inl[off[k]:off[k] + max(r.n_inliers, 0)].tolist() == oi.tolist()
+    finally:
+        fm.close()
