@@ -131,18 +131,27 @@ match_fixup_kernel(const uint8_t* __restrict__ pool, const MatchItem* __restrict
     const uint32_t out = cd.x, chunk = cd.y;
     const int best = (int)cd.z, s_outer = (int)cd.w;
     const MatchItem w = items[out / kSuperRows];
-    const uint4* xr = reinterpret_cast<const uint4*>(pool + (size_t)(w.x_row + out % kSuperRows) * kDescBytes);
-    const uint4* yr = reinterpret_cast<const uint4*>(pool + (size_t)(w.y_row + chunk * kChunk + lane) * kDescBytes);
-    unsigned acc = 0;
+    // The chunk's 32 rows are read COALESCED: in step t the warp loads rows 4t .. 4t+3 as one 512-byte span (lane l: row
+    // 4t + l/8, 16-byte piece l%8), each lane multiplies its piece with the matching piece of the query row, and three
+    // butterfly steps add the eight pieces of a row.  (One row per lane, 8 loads of 16 bytes at a 128-byte stride, touched
+    // 32 cache lines per load instruction and fetched every 32-byte sector twice.)  Integer sums: the order does not matter.
+    const int piece = lane & 7;
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(pool + (size_t)(w.x_row + out % kSuperRows) * kDescBytes) + piece);
+    const uint4* yc = reinterpret_cast<const uint4*>(pool + (size_t)(w.y_row + chunk * kChunk) * kDescBytes) + lane;
+    int v = 0;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const uint4 a = __ldg(xr + q), b = __ldg(yr + q);
-      acc = __dp4a(a.x, b.x, acc);
+    for (int t = 0; t < 8; ++t) {
+      const uint4 b = __ldg(yc + t * 32);   // rows 4t .. 4t+3: 32 lanes x 16 bytes, contiguous
+      unsigned acc = __dp4a(a.x, b.x, 0u);
       acc = __dp4a(a.y, b.y, acc);
       acc = __dp4a(a.z, b.z, acc);
       acc = __dp4a(a.w, b.w, acc);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);          // the eight lanes of group g = lane / 8 hold the dot of row 4t + g
+      const unsigned mine = __shfl_sync(0xffffffffu, acc, 8 * (lane & 3));   // lane l wants row l = 4 (l/4) + l%4
+      if ((lane >> 2) == t) v = (int)mine;
     }
-    const int v = (int)acc;
     const unsigned hit = __ballot_sync(0xffffffffu, v == best);
     if (hit == 0) {  // cannot happen: the tensor-core pass found `best` in this chunk
       if (lane == 0) atomicExch(err, 2);

@@ -26,7 +26,7 @@ def _same(x, y):
     if not (np.array_equal(oa, ob) and np.array_equal(ma, mb)):
         return False
     for f in ra.dtype.names:
-        if not np.array_equal(ra[f].view(np.uint8), rb[f].view(np.uint8)):
+        if not np.array_equal(np.ascontiguousarray(ra[f]).view(np.uint8), np.ascontiguousarray(rb[f]).view(np.uint8)):
             return False
     for k in range(len(ra)):
         n = max(int(ra["n_inliers"][k]), 0)

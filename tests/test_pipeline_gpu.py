@@ -150,7 +150,7 @@ def test_c3_chain_retrieval_to_match_to_verify_on_one_descriptor_pool():
     got = {(int(a), int(b)) for a, b in pairs}
     near = {(i, j) for i in range(n_img) for j in range(i + 1, min(i + 4, n_img))}
     assert len(near & got) >= 0.95 * len(near)
-    seeds = (np.arange(len(pairs), dtype=np.uint32) * 2654435761 % (2 ** 32)).astype(np.uint32)
+    seeds = (np.arange(len(pairs), dtype=np.uint64) * 2654435761 % (2 ** 32)).astype(np.uint32)
     fm = SiftFeatureMatcher(SiftMatchingOptions(), TwoViewOptions.default(), 0, chunk_pairs=64)
     try:
         fm.setup_device_descriptors(w["desc"].data_ptr(), n_img, n_kp, w["keypoints"], cameras_of(w))
