@@ -8,6 +8,13 @@
  *
  * There is NO CPU fallback behind these calls: if no CUDA device / sm_100a
  * kernel image is available they return B2_ERR_CUDA / B2_ERR_NO_DEVICE.
+ *
+ * Ownership and threading.  A handle (b2_matcher, b2_verifier, b2_ba, b2_retrieval) belongs to one GPU and owns its
+ * device buffers and its CUDA stream; calls on one handle must not overlap in time, calls on DIFFERENT handles may come
+ * from different host threads at the same time (handles share nothing but the device; the last-error text is per thread,
+ * the launch counter atomic; tests/test_concurrency_gpu.py).  Every call returns after its device work has completed: a
+ * host buffer or a caller-owned device buffer passed in may be reused as soon as the call returns, and device outputs are
+ * ready for any stream.  Multi-GPU jobs use one process (or thread) and one set of handles per GPU.
  */
 #ifndef DAGSFM_B200_H_
 #define DAGSFM_B200_H_
