@@ -415,8 +415,8 @@ int b2_ba_reprojection_errors(b2_ba* h, const b2_ba_problem* problem, double* po
  * Replaces the retrieval loop of VocabSimilarityGraph::Run (src/graph/similarity_graph.cpp:101-200) over
  * retrieval::VisualIndex<uint8_t, 128, 64> (src/retrieval/visual_index.h): Add for every image, Prepare, Query of every
  * image with QueryOptions{max_num_images, num_neighbors}; spatial re-ranking (num_images_after_verification, off in
- * the reference's defaults) is not part of this seam.  The visual words are searched EXACTLY (the reference uses FLANN's
- * approximate index).  One handle per GPU. */
+ * the reference's defaults) is not part of this seam.  The visual words are searched EXACTLY: the answer of the reference's
+ * vendored FLANN in exact mode (flann::LinearIndex), which its autotuned approximate index approximates.  One handle per GPU. */
 typedef struct b2_retrieval b2_retrieval;
 int b2_retrieval_create(int device, b2_retrieval** out);
 int b2_retrieval_destroy(b2_retrieval* r);

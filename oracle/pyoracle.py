@@ -709,3 +709,39 @@ class RetrievalOracle:
         sc = np.zeros(max(self._n_images, 1), np.float32)
         m = lib().orc_retrieval_query(self._x, len(d), d.ctypes.data, num_neighbors, max_num_images, ids.ctypes.data, sc.ctypes.data)
         return ids[:m].copy(), sc[:m].copy()
+
+
+# ------------------------------------------------------------------------ the reference's vendored FLANN (oracle/_ref)
+FLANN_REF_PATH = Path(__file__).resolve().parent / "_ref" / "libflann_ref.so"
+
+
+def flann_ref_available() -> bool:
+    return FLANN_REF_PATH.exists()
+
+
+def _flann():
+    L = C.CDLL(str(FLANN_REF_PATH))
+    L.flann_ref_knn_linear.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.flann_ref_knn_autotuned.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p]
+    return L
+
+
+def flann_ref_knn_linear(words, desc, k):
+    """The k nearest words by the reference's own FLANN in EXACT mode (flann::LinearIndex over flann::L2<uint8>).
+    -> (ids int32 [n, k], squared distances float32 [n, k])"""
+    w = np.ascontiguousarray(words, np.uint8).reshape(-1, 128)
+    d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 128)
+    ids = np.zeros((len(d), k), np.int32)
+    dist = np.zeros((len(d), k), np.float32)
+    _flann().flann_ref_knn_linear(w.ctypes.data, len(w), d.ctypes.data, len(d), k, ids.ctypes.data, dist.ctypes.data)
+    return ids, dist
+
+
+def flann_ref_knn_autotuned(words, desc, k, num_checks=256, target_precision=0.95, cores=1):
+    """What VisualIndex::Build + FindWordIds do (visual_index.h:517-521, 701-744; BuildOptions::target_precision 0.95,
+    num_checks 256): approximate, tuned by timing experiments on this host, randomised trees.  -> ids int32 [n, k]"""
+    w = np.ascontiguousarray(words, np.uint8).reshape(-1, 128)
+    d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 128)
+    ids = np.zeros((len(d), k), np.int32)
+    _flann().flann_ref_knn_autotuned(w.ctypes.data, len(w), d.ctypes.data, len(d), k, num_checks, C.c_float(target_precision), cores, ids.ctypes.data)
+    return ids

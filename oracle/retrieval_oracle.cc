@@ -10,16 +10,21 @@
 //   HammingDistWeightFunctor<64, 16>                        src/retrieval/utils.h:52-82
 //   VocabSimilarityGraph::Run (pairs image_id < other)       src/graph/similarity_graph.cpp:101-200
 //
-// Two stated differences from the reference, both outside the reference's own sources:
-//   * FindWordIds uses FLANN's autotuned approximate index (external, not in /root/reference); here the nearest words
-//     are EXACT (squared L2 over the uint8 descriptors, ties -> lower word id).  Where FLANN's search is exact the two
-//     agree; otherwise this is the answer FLANN approximates.
-//   * the Hamming projection proj * descriptor is an Eigen float product whose summation order is Eigen's; here it is
-//     the plain left-to-right float sum (both the GPU path and this oracle), which can flip a signature bit only when a
-//     projected value equals its threshold to the last ulp.
-// Parity status: the reference's tests (visual_index_test.cc) pin structure only -- ranking of an image against itself,
-// result sizes under max_num_images -- and those are replayed in tests/test_oracle_retrieval.py; there are no numeric
-// golden vectors for scores: "parity unpinned" for the score values.
+// Two stated differences from the reference:
+//   * FindWordIds asks a flann::AutotunedIndex (the reference vendors FLANN under lib/FLANN): its algorithm and parameters
+//     come from TIMING experiments on the host (target_precision 0.95), its trees are randomised and the search stops after
+//     num_checks = 256 leaves -- approximate and not reproducible.  Here the nearest words are EXACT (squared L2 over the
+//     uint8 descriptors, ties -> lower word id).  PINNED: this function returns the same ids in the same order, ties
+//     included, as the reference's own FLANN in exact mode (flann::LinearIndex over flann::L2<uint8>, built from lib/FLANN
+//     into oracle/_ref/libflann_ref.so; golden vectors tests/golden/retrieval_flann_linear.npz), and on the synthetic
+//     collection of the tests the reference's autotuned index returns exactly these words too (2 000 / 2 000 queries,
+//     k = 5); on uniform random descriptors it finds 39 % of the nearest words.
+//   * the Hamming projection proj * descriptor is an Eigen float product whose summation order is Eigen's (Eigen is not
+//     vendored and not installed); here it is the plain left-to-right float sum (both the GPU path and this oracle), which
+//     can flip a signature bit only when a projected value equals its threshold to the last ulp.
+// Parity status: word search pinned as above.  For the voting stage the reference's tests (visual_index_test.cc) pin
+// structure only -- ranking of an image against itself, result sizes under max_num_images -- and those are replayed in
+// tests/test_oracle_retrieval.py; there are no numeric golden vectors for scores: "parity unpinned" for the score values.
 #include <algorithm>
 #include <cmath>
 #include <cstdint>

@@ -107,3 +107,22 @@ def test_argument_errors(rmod):
             vi.query_all(3)                                           # nothing indexed
     finally:
         vi.close()
+
+
+def test_word_search_equals_the_references_flann_golden_vectors(rmod):
+    """The library's word search (SIMT seam = the real dp4a kernel on the emulator; the production list comes from the
+    stand-in of the tcgen05 kernel) against tests/golden/retrieval_flann_linear.npz -- the reference's vendored FLANN in
+    exact mode, duplicate words included."""
+    from pathlib import Path
+    g = np.load(Path(__file__).parent / "golden" / "retrieval_flann_linear.npz")
+    words, desc = g["words"], g["desc"]
+    vocab = rmod.Vocabulary(words, np.zeros((64, 128), np.float32), np.zeros((len(words), 64), np.float32), np.ones(len(words), np.uint8))
+    for k in (1, 5, 8):
+        vi = rmod.VisualIndex(0)
+        try:
+            vi.set_vocabulary(vocab)
+            vi.index_images([desc[:140], desc[140:]], k)
+            assert (vi.debug_word_ids_simt() == g[f"ids_k{k}"]).all()
+            assert (vi.debug_word_ids() == g[f"ids_k{k}"]).all()
+        finally:
+            vi.close()

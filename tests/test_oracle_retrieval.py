@@ -77,3 +77,42 @@ def test_neighbouring_images_outrank_distant_ones():
     o = oracle_index(descs, vocab)
     ids, sc = o.Query(descs[6], 5, 5)
     assert ids[0] == 6 and set(ids[1:3].tolist()) <= {4, 5, 7, 8}
+
+
+# ---------------------------------------------------------------- pins against the reference's own (vendored) FLANN
+def _golden():
+    from pathlib import Path
+    return np.load(Path(__file__).parent / "golden" / "retrieval_flann_linear.npz")
+
+
+def test_exact_word_search_equals_the_references_flann_golden_vectors():
+    """tests/golden/retrieval_flann_linear.npz: the reference's vendored FLANN (lib/FLANN) in exact mode -- flann::LinearIndex,
+    flann::L2<uint8>, KNNResultSet -- on a vocabulary with duplicate words; generator tests/golden/make_retrieval_flann_golden.py.
+    The oracle's nearest words (and through them the kernels') must be the same ids in the same order, ties included, and the
+    squared distances FLANN reports must be the integers the oracle's definition gives."""
+    g = _golden()
+    words, desc = g["words"], g["desc"]
+    o = orc.RetrievalOracle(words, np.zeros((64, 128), np.float32), np.zeros((len(words), 64), np.float32), np.ones(len(words), np.uint8))
+    for k in (1, 2, 5, 8):
+        ids = o.word_ids(desc, k)
+        assert (ids == g[f"ids_k{k}"]).all()
+        d2 = ((desc[:, None, :].astype(np.int64) - words[ids].astype(np.int64)) ** 2).sum(2)
+        assert (d2 == g[f"dist_k{k}"].astype(np.int64)).all()
+
+
+def test_exact_word_search_equals_the_vendored_flann_live_where_it_is_built():
+    """The same comparison against oracle/_ref/libflann_ref.so itself (present wherever `make -C oracle ref` ran with the
+    reference tree, and on the GPU box, where the prebuilt file travels) on fresh random cases."""
+    import pytest
+    if not orc.flann_ref_available():
+        pytest.skip("oracle/_ref/libflann_ref.so not built")
+    rng = np.random.default_rng(7)
+    for n_words, n, k in ((33, 100, 5), (700, 400, 5), (1, 10, 1), (129, 64, 8)):
+        words = rng.integers(0, 256, (n_words, 128)).astype(np.uint8)
+        if n_words > 20:
+            words[n_words // 2] = words[3]
+        desc = rng.integers(0, 256, (n, 128)).astype(np.uint8)
+        o = orc.RetrievalOracle(words, np.zeros((64, 128), np.float32), np.zeros((n_words, 64), np.float32), np.ones(n_words, np.uint8))
+        kk = min(k, n_words)
+        ids, _ = orc.flann_ref_knn_linear(words, desc, kk)
+        assert (o.word_ids(desc, kk) == ids).all()

@@ -107,3 +107,23 @@ def test_similarity_graph_feeds_the_matcher():
     got = {(int(a), int(b)) for a, b in pairs}
     assert len(true_pairs & got) >= 0.95 * len(true_pairs)
     assert (gap <= 6).mean() > 0.6
+
+
+def test_word_search_equals_the_references_flann_golden_vectors():
+    """tcgen05 word search and its SIMT seam against tests/golden/retrieval_flann_linear.npz: the reference's own vendored FLANN
+    (lib/FLANN, flann::LinearIndex over flann::L2<uint8>) on a vocabulary with duplicate words -- same ids, same order."""
+    from pathlib import Path
+    from dagsfm_b200 import VisualIndex
+    from dagsfm_b200.retrieval import Vocabulary
+    g = np.load(Path(__file__).parent / "golden" / "retrieval_flann_linear.npz")
+    words, desc = g["words"], g["desc"]
+    vocab = Vocabulary(words, np.zeros((64, 128), np.float32), np.zeros((len(words), 64), np.float32), np.ones(len(words), np.uint8))
+    for k in (1, 2, 5, 8):
+        vi = VisualIndex(0)
+        try:
+            vi.set_vocabulary(vocab)
+            vi.index_images([desc[:140], desc[140:]], k)
+            assert (vi.debug_word_ids() == g[f"ids_k{k}"]).all()
+            assert (vi.debug_word_ids_simt() == g[f"ids_k{k}"]).all()
+        finally:
+            vi.close()
