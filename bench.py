@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the hot path (BASELINE.json metric: image pairs VERIFIED per second + BA iter/s).
 
-Headline workload (BASELINE configs[2], SURVEY.md 8d "C3"): a synthetic sequence of 5000 images x 2048 SIFT keypoints
+Headline workload (BASELINE configs[2], SURVEY.md 8d "C3"): a synthetic sequence of 5000 images x 4096 SIFT keypoints
 (dagsfm_b200/synthetic.py: one long 3-D scene, neighbouring images overlap), the 50 candidate pairs per image a
 retrieval stage would hand over (248 725 pairs), every pair through descriptor matching (sift.cc:76-198) AND two-view
 geometric verification (two_view_geometry.cc:292-489) -- the reference's SiftFeatureMatcher pipeline
@@ -43,7 +43,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--seq-images", type=int, default=5000, help="C3 pipeline: images in the sequence")
-    ap.add_argument("--seq-kp", type=int, default=2048, help="C3 pipeline: keypoints (= descriptors) per image")
+    ap.add_argument("--seq-kp", type=int, default=4096,
+                    help="C3 pipeline: keypoints (= descriptors) per image (SURVEY 8d C3: 5000 images x 4096 descriptors; the measurements of rounds 2's sessions 7-21 used 2048)")
     ap.add_argument("--seq-cand", type=int, default=50, help="C3 pipeline: candidate pairs per image")
     ap.add_argument("--images", type=int, default=1000, help="C2 match leg: images")
     ap.add_argument("--desc", type=int, default=4096, help="C2 match leg: descriptors per image")
