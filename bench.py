@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--seq-images", type=int, default=5000, help="C3 pipeline: images in the sequence")
     ap.add_argument("--seq-kp", type=int, default=4096,
-                    help="C3 pipeline: keypoints (= descriptors) per image (SURVEY 8d C3: 5000 images x 4096 descriptors; the measurements of rounds 2's sessions 7-21 used 2048)")
+                    help="C3 pipeline: keypoints (= descriptors) per image (SURVEY 8d C3: 5000 images x 4096 descriptors; round 2's GPU sessions 7-21 measured with 2048)")
     ap.add_argument("--seq-cand", type=int, default=50, help="C3 pipeline: candidate pairs per image")
     ap.add_argument("--images", type=int, default=1000, help="C2 match leg: images")
     ap.add_argument("--desc", type=int, default=4096, help="C2 match leg: descriptors per image")
