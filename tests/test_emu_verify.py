@@ -147,9 +147,9 @@ def test_estimate_multiple_through_the_c_abi(ver):
     assert cfgs[0] == 8 and cfgs[2] == 1
 
 
-def test_experimental_variant_keeps_every_decision(ver, monkeypatch):
-    """B2_VERIFY_VARIANT=1 (one CTA per SM with the full register file instead of two with 128 registers): decisions,
-    inlier lists and trial counts must stay those of the production instance and the oracle."""
+def test_stage_launch_shapes_keep_every_decision(ver, monkeypatch):
+    """B2_VERIFY_BPS=222 (two CTAs per SM for the E, F and H stage kernels: the instances that score two hypotheses per pass
+    instead of four): decisions, inlier lists and trial counts must stay those of the production shapes and the oracle."""
     from dagsfm_b200 import Camera, TwoViewOptions
     rng = np.random.default_rng(19)
     specs = [(70, 15, False, True), (55, 12, True, False), (50, 25, False, False), (64, 0, False, True)]
@@ -166,9 +166,9 @@ def test_experimental_variant_keeps_every_decision(ver, monkeypatch):
     opt = TwoViewOptions.default(); opt.max_num_trials = 300
     oopt = orc.tv_default_options(); oopt.max_num_trials = 300
     base, inl0 = ver.verify_pairs(pairs, offs, np.concatenate(ms), opt, seeds)
-    monkeypatch.setenv("B2_VERIFY_VARIANT", "1")
+    monkeypatch.setenv("B2_VERIFY_BPS", "222")
     res, inl = ver.verify_pairs(pairs, offs, np.concatenate(ms), opt, seeds)
-    monkeypatch.delenv("B2_VERIFY_VARIANT")
+    monkeypatch.delenv("B2_VERIFY_BPS")
     assert res.tobytes() == base.tobytes() and (inl == inl0).all()        # bit-identical to the production instance
     for i in range(len(specs)):
         c = orc.make_camera(prior=priors[i])
@@ -176,6 +176,38 @@ def test_experimental_variant_keeps_every_decision(ver, monkeypatch):
         assert (res["config"][i], res["n_inliers"][i], res["E_num_trials"][i], res["F_num_trials"][i], res["H_num_trials"][i]) == \
                (r.config, r.n_inliers, r.E_trials, r.F_trials, r.H_trials)
         assert inl[offs[i]:offs[i] + r.n_inliers].tolist() == oi.tolist()
+
+
+def test_pair_with_more_matches_than_the_shared_memory_sampler_holds(ver):
+    """A pair with more than 2 048 matches (kIdxSmem): the sampler's persistent index vector lives in the global scratch
+    instead of shared memory -- the warp-parallel generator, the swaps and every decision must still equal the oracle's, bit
+    for bit (images of 4 096 keypoints produce such pairs in the C3 workload)."""
+    from dagsfm_b200 import Camera, TwoViewOptions
+    rng = np.random.default_rng(77)
+    kps, pairs, offs, ms, priors = [], [], [0], [], []
+    for i, (n_in, n_out, planar, prior) in enumerate([(1900, 300, False, True), (1500, 700, True, False)]):
+        p1, p2 = scene(rng, n_in, n_out, planar=planar, noise=0.4)
+        kps += [p1, p2]
+        ms.append(np.stack([np.arange(len(p1))] * 2, 1).astype(np.uint32))
+        priors.append(prior); pairs.append((2 * i, 2 * i + 1)); offs.append(offs[-1] + len(p1))
+    assert all(len(m) > 2048 for m in ms)
+    cams = [Camera.make(prior_focal=p) for p in priors for _ in range(2)]
+    ver.set_images(cams, kps)
+    seeds = np.array([123, 456], np.uint32)
+    opt = TwoViewOptions.default(); opt.max_num_trials = 200
+    oopt = orc.tv_default_options(); oopt.max_num_trials = 200
+    res, inl = ver.verify_pairs(pairs, offs, np.concatenate(ms), opt, seeds)
+    for i in range(2):
+        c = orc.make_camera(prior=priors[i])
+        with orc.solver_stack(1):
+            r, oi = orc.two_view(c, kps[2 * i], c, kps[2 * i + 1], ms[i], oopt, seed=int(seeds[i]))
+        g = res[i]
+        for m in ("E", "F", "H"):
+            assert np.array_equal(np.array(getattr(r, m)[:]).view(np.uint64), g[m].view(np.uint64)), (i, m)
+        assert (g["config"], g["n_inliers"], g["E_num_trials"], g["F_num_trials"], g["H_num_trials"]) == \
+               (r.config, r.n_inliers, r.E_trials, r.F_trials, r.H_trials)
+        assert inl[offs[i]:offs[i] + r.n_inliers].tolist() == oi.tolist()
+        assert g["n_inliers"] > 1000
 
 
 def test_edge_cases_empty_tiny_and_invalid_pairs(ver):
