@@ -923,10 +923,16 @@ def main():
     g = gathered
     mcount = None
     roofline = {"bound": "fp64", "kernel": "verify_stage_kernel<E|F|H|decision> (one warp per pair, 32 RANSAC trials per batch; the H stage is ~65 % of it)", "unit": "TFLOP/s",
-                "peak": peak64, "peak_source": peak64_src, "traffic": None,
+                "peak": peak64, "peak_source": peak64_src,
                 "share_of_step": pl["verify_kernel_s"] / max(pl["verify_kernel_s"] + pl["match_kernel_s"], 1e-12),
                 "avg_launch_ms": 1e3 * pl["verify_kernel_s"] / max(a.steps * ((pl["n_pairs"] // world + a.chunk_pairs - 1) // a.chunk_pairs), 1),
                 "launch_note": "one launch = the four stage kernels (E, F, H, decision) of one chunk of pairs"}
+    # dram__bytes_read + write of the three RANSAC stage kernels in the committed capture (profiles/r2_verify_final_ncu_full.txt:
+    # 3.96 + 2.94 + 4.49 GB for a 13 725-pair launch group at 2 048 keypoints per image = 0.83 MB per pair, mostly the per-warp
+    # scratch -- hypotheses, local-optimisation matrices -- spilling past L2), scaled to this run's pairs per launch
+    pairs_per_launch = min(a.chunk_pairs, max(pl["n_pairs"] // world, 1))
+    roofline["traffic"] = 11.39e9 / 13725 * pairs_per_launch
+    roofline["traffic_source"] = "profiles/r2_verify_final_ncu_full.txt (bytes per pair of the 2 048-keypoint capture x pairs per launch)"
     try:
         off = None
         # matches per pair are not kept by the throughput run: expected count from the scene layout (shared points +
