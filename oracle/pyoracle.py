@@ -745,3 +745,14 @@ def flann_ref_knn_autotuned(words, desc, k, num_checks=256, target_precision=0.9
     ids = np.zeros((len(d), k), np.int32)
     _flann().flann_ref_knn_autotuned(w.ctypes.data, len(w), d.ctypes.data, len(d), k, num_checks, C.c_float(target_precision), cores, ids.ctypes.data)
     return ids
+
+
+def reference_similarity_ransac_test(use_lo: bool):
+    """ransac_test.cc:89-133 / loransac_test.cc:57-107 replayed literally on the oracle's RANSAC loop (same data recipe and PRNG
+    stream: std::mt19937(0), RandomReal outliers, then the sampler), with the reference's 3-D similarity estimator restated.
+    -> dict(success, num_trials, num_inliers, mask bool [1000], matrix_diff)"""
+    L = _tv()
+    nt, ni, md = C.c_int64(0), C.c_int32(0), C.c_double(0)
+    mask = np.zeros(1000, np.uint8)
+    ok = L.orc_reference_similarity_ransac_test(int(use_lo), C.byref(nt), C.byref(ni), mask.ctypes.data_as(C.c_void_p), C.byref(md))
+    return {"success": bool(ok), "num_trials": nt.value, "num_inliers": ni.value, "mask": mask.astype(bool), "matrix_diff": md.value}

@@ -1109,14 +1109,16 @@ struct RansacOptions {
   size_t min_num_trials = 0, max_num_trials = std::numeric_limits<size_t>::max();
 };
 struct Support { size_t num_inliers = 0; double residual_sum = std::numeric_limits<double>::max(); };
-struct Report {
+template <class M>
+struct ReportT {
   bool success = false;
   size_t num_trials = 0;
   Support support;
   std::vector<char> inlier_mask;
-  Mat3 model;
-  Report() { memset(model.m, 0, sizeof model.m); }
+  M model;
+  ReportT() { memset(&model, 0, sizeof model); }
 };
+using Report = ReportT<Mat3>;
 
 static size_t ComputeNumTrials(size_t num_inliers, size_t num_samples, double confidence, int kmin) {
   const double inlier_ratio = num_inliers / static_cast<double>(num_samples);
@@ -1156,24 +1158,31 @@ struct Sampler {
   }
 };
 
-// loransac.h:92-233 (use_lo == true) and ransac.h:169-268 (use_lo == false).
-static Report RunRansac(int type, bool use_lo, RansacOptions opt, const std::vector<Vec2>& X, const std::vector<Vec2>& Y, std::mt19937& prng) {
-  const int kmin = MinSamples(type);
+// loransac.h:92-233 (use_lo == true) and ransac.h:169-268 (use_lo == false), ONE loop for every estimator: Pol supplies
+// the point and model types, kMinNumSamples of the estimator and of the local estimator, Estimate / LocalEstimate /
+// Residuals.  The two-view estimators (E5, F7 / F8, H4, T2) run through it as TypePolicy; the reference's own RANSAC and
+// LO-RANSAC tests run through the same loop with the 3-D similarity estimator they use (SimilarityPolicy, below).
+template <class Pol>
+static ReportT<typename Pol::Model> RunRansacT(const Pol& pol, bool use_lo, RansacOptions opt, const std::vector<typename Pol::X>& X,
+                                               const std::vector<typename Pol::Y>& Y, std::mt19937& prng) {
+  using Model = typename Pol::Model;
+  const int kmin = pol.MinSamples();
   {  // RANSAC ctor, ransac.h:135-147
     const size_t kNumSamples = 100000;
     const size_t dyn = ComputeNumTrials(static_cast<size_t>(opt.min_inlier_ratio * kNumSamples), kNumSamples, opt.confidence, kmin);
     opt.max_num_trials = std::min<size_t>(opt.max_num_trials, dyn);
   }
   const size_t num_samples = X.size();
-  Report report;
+  ReportT<Model> report;
   if (num_samples < (size_t)kmin) return report;
   Support best_support;
-  Mat3 best_model;
-  memset(best_model.m, 0, sizeof best_model.m);
+  Model best_model;
+  memset(&best_model, 0, sizeof best_model);
   bool abort = false;
   const double max_residual = opt.max_error * opt.max_error;
   std::vector<double> residuals(num_samples);
-  std::vector<Vec2> X_inlier, Y_inlier, X_rand(kmin), Y_rand(kmin);
+  std::vector<typename Pol::X> X_inlier, X_rand(kmin);
+  std::vector<typename Pol::Y> Y_inlier, Y_rand(kmin);
   Sampler sampler(kmin);
   sampler.Initialize(num_samples);
   std::vector<size_t> sidx;
@@ -1183,21 +1192,21 @@ static Report RunRansac(int type, bool use_lo, RansacOptions opt, const std::vec
     if (abort) { report.num_trials += 1; break; }
     sampler.Sample(prng, &sidx);
     for (int i = 0; i < kmin; ++i) { X_rand[i] = X[sidx[i]]; Y_rand[i] = Y[sidx[i]]; }
-    const std::vector<Mat3> sample_models = Estimate(type, X_rand, Y_rand);
+    const std::vector<Model> sample_models = pol.Estimate(X_rand, Y_rand);
     for (const auto& sample_model : sample_models) {
-      Residuals(type, X, Y, sample_model, &residuals);
+      pol.Residuals(X, Y, sample_model, &residuals);
       const Support support = Evaluate(residuals, max_residual);
       if (Compare(support, best_support)) {
         best_support = support;
         best_model = sample_model;
-        if (use_lo && support.num_inliers > (size_t)kmin && support.num_inliers >= (size_t)LocalMinSamples(type)) {
+        if (use_lo && support.num_inliers > (size_t)kmin && support.num_inliers >= (size_t)pol.LocalMinSamples()) {
           X_inlier.clear();
           Y_inlier.clear();
           for (size_t i = 0; i < residuals.size(); ++i)
             if (residuals[i] <= max_residual) { X_inlier.push_back(X[i]); Y_inlier.push_back(Y[i]); }
-          const std::vector<Mat3> local_models = LocalEstimate(type, X_inlier, Y_inlier);
+          const std::vector<Model> local_models = pol.LocalEstimate(X_inlier, Y_inlier);
           for (const auto& local_model : local_models) {
-            Residuals(type, X, Y, local_model, &residuals);
+            pol.Residuals(X, Y, local_model, &residuals);
             const Support local_support = Evaluate(residuals, max_residual);
             if (Compare(local_support, best_support)) {
               best_support = local_support;
@@ -1217,11 +1226,95 @@ static Report RunRansac(int type, bool use_lo, RansacOptions opt, const std::vec
   report.model = best_model;
   if (report.support.num_inliers < (size_t)kmin) return report;
   report.success = true;
-  Residuals(type, X, Y, report.model, &residuals);
+  pol.Residuals(X, Y, report.model, &residuals);
   report.inlier_mask.resize(num_samples);
   for (size_t i = 0; i < residuals.size(); ++i) report.inlier_mask[i] = residuals[i] <= max_residual;
   return report;
 }
+
+struct TypePolicy {   // the four LORANSAC instantiations of two_view_geometry.cc:325-341, 539-541
+  using X = Vec2; using Y = Vec2; using Model = Mat3;
+  int type;
+  int MinSamples() const { return tv::MinSamples(type); }
+  int LocalMinSamples() const { return tv::LocalMinSamples(type); }
+  std::vector<Mat3> Estimate(const std::vector<Vec2>& a, const std::vector<Vec2>& b) const { return tv::Estimate(type, a, b); }
+  std::vector<Mat3> LocalEstimate(const std::vector<Vec2>& a, const std::vector<Vec2>& b) const { return tv::LocalEstimate(type, a, b); }
+  void Residuals(const std::vector<Vec2>& a, const std::vector<Vec2>& b, const Mat3& M, std::vector<double>* r) const { tv::Residuals(type, a, b, M, r); }
+};
+static Report RunRansac(int type, bool use_lo, RansacOptions opt, const std::vector<Vec2>& X, const std::vector<Vec2>& Y, std::mt19937& prng) {
+  return RunRansacT(TypePolicy{type}, use_lo, opt, X, Y, prng);
+}
+
+// ---- SimilarityTransformEstimator<3> (estimators/similarity_transform.h:58-130), the estimator of the reference's own
+// ransac_test.cc / loransac_test.cc: Eigen::umeyama restated (means, covariance dst src^T / n, 3 x 3 SVD, reflection fix
+// S = diag(1, 1, det(U) det(V)), scale = sum(sigma_i S_i) / var(src)).  With three samples the covariance has rank 2: the third
+// left singular vector is completed as u1 x u2 -- its sign is Eigen's choice and cancels in U S V^T.
+struct P3 { double v[3]; };
+struct Mat34 { double m[12]; };
+struct SimilarityPolicy {
+  using X = P3; using Y = P3; using Model = Mat34;
+  int MinSamples() const { return 3; }
+  int LocalMinSamples() const { return 3; }
+  std::vector<Mat34> Estimate(const std::vector<P3>& src, const std::vector<P3>& dst) const {
+    const size_t n = src.size();
+    double ms[3] = {0, 0, 0}, md[3] = {0, 0, 0};
+    for (size_t i = 0; i < n; ++i)
+      for (int k = 0; k < 3; ++k) { ms[k] += src[i].v[k]; md[k] += dst[i].v[k]; }
+    for (int k = 0; k < 3; ++k) { ms[k] /= (double)n; md[k] /= (double)n; }
+    double var = 0, sig[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (size_t i = 0; i < n; ++i) {
+      double a[3], b[3];
+      for (int k = 0; k < 3; ++k) { a[k] = src[i].v[k] - ms[k]; b[k] = dst[i].v[k] - md[k]; var += a[k] * a[k]; }
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) sig[3 * r + c] += b[r] * a[c];
+    }
+    var /= (double)n;
+    for (double& x : sig) x /= (double)n;
+    double sv[3], V[9], AV[9];
+    jacobi_svd(sig, 3, 3, sv, V, AV);   // sig V = U diag(sv), singular values descending
+    double U[9];
+    for (int c = 0; c < 2; ++c) {
+      double nrm = 0;
+      for (int r = 0; r < 3; ++r) nrm += AV[3 * r + c] * AV[3 * r + c];
+      nrm = std::sqrt(nrm);
+      for (int r = 0; r < 3; ++r) U[3 * r + c] = nrm > 0 ? AV[3 * r + c] / nrm : 0.0;
+    }
+    if (sv[2] > 1e-12 * sv[0]) {          // full rank: the third left singular vector is determined
+      for (int r = 0; r < 3; ++r) U[3 * r + 2] = AV[3 * r + 2] / sv[2];
+    } else {                              // rank 2 (three samples): completed as u1 x u2
+      U[2] = U[3] * U[7] - U[6] * U[4];
+      U[5] = U[6] * U[1] - U[0] * U[7];
+      U[8] = U[0] * U[4] - U[3] * U[1];
+    }
+    auto det = [](const double* a) {
+      return a[0] * (a[4] * a[8] - a[5] * a[7]) - a[1] * (a[3] * a[8] - a[5] * a[6]) + a[2] * (a[3] * a[7] - a[4] * a[6]);
+    };
+    const double s3 = det(U) * det(V) < 0 ? -1.0 : 1.0;   // umeyama: S(m - 1) = -1 when det(U) det(V) < 0
+    double R[9];
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) R[3 * r + c] = U[3 * r] * V[3 * c] + U[3 * r + 1] * V[3 * c + 1] + s3 * U[3 * r + 2] * V[3 * c + 2];
+    const double scale = (sv[0] + sv[1] + s3 * sv[2]) / var;
+    Mat34 M;
+    for (int r = 0; r < 3; ++r) {
+      double t = md[r];
+      for (int c = 0; c < 3; ++c) { M.m[4 * r + c] = scale * R[3 * r + c]; t -= scale * R[3 * r + c] * ms[c]; }
+      M.m[4 * r + 3] = t;
+    }
+    return {M};
+  }
+  std::vector<Mat34> LocalEstimate(const std::vector<P3>& a, const std::vector<P3>& b) const { return Estimate(a, b); }
+  void Residuals(const std::vector<P3>& src, const std::vector<P3>& dst, const Mat34& M, std::vector<double>* res) const {
+    res->resize(src.size());
+    for (size_t i = 0; i < src.size(); ++i) {
+      double e = 0;
+      for (int r = 0; r < 3; ++r) {
+        const double t = M.m[4 * r] * src[i].v[0] + M.m[4 * r + 1] * src[i].v[1] + M.m[4 * r + 2] * src[i].v[2] + M.m[4 * r + 3];
+        e += (dst[i].v[r] - t) * (dst[i].v[r] - t);
+      }
+      (*res)[i] = e;
+    }
+  }
+};
 
 // ------------------------------------------------------------------ camera
 // All eleven models of src/base/camera_models.h (ids :117-129): parameter layouts, Distortion functions,
@@ -1982,6 +2075,37 @@ int orc_ransac(int type, int use_lo, int n, const double* X, const double* Y, do
   *num_trials = (int64_t)r.num_trials;
   memset(mask, 0, n);
   for (size_t i = 0; i < r.inlier_mask.size(); ++i) mask[i] = r.inlier_mask[i];
+  return r.success ? 1 : 0;
+}
+
+// ransac_test.cc:89-133 (use_lo = 0) and loransac_test.cc:57-107 (use_lo = 1), literally: SetPRNGSeed(0), 1000 samples of which
+// the first 400 get outlier destinations drawn with RandomReal (std::uniform_real_distribution<double> on the SAME
+// std::mt19937 the sampler then continues with, util/random.h:100-119), RANSACOptions{max_error = 10}, the 3-D similarity
+// estimator.  Outputs: success, num_trials, num_inliers, the mask [1000] and |orig_tform(3 x 4) - model|_F.
+int orc_reference_similarity_ransac_test(int use_lo, int64_t* num_trials, int32_t* num_inliers, uint8_t* mask, double* matrix_diff) {
+  std::mt19937 prng(0);
+  const size_t num_samples = 1000, num_outliers = 400;
+  std::vector<tv::P3> src(num_samples), dst(num_samples);
+  for (size_t i = 0; i < num_samples; ++i) {
+    src[i] = {{(double)i, std::sqrt((double)i) + 2, std::sqrt((double)(2 * i + 2))}};
+    dst[i] = {{2 * src[i].v[0] + 100, 2 * src[i].v[1] + 10, 2 * src[i].v[2] + 10}};   // SimilarityTransform3(2, identity, (100, 10, 10))
+  }
+  auto RandomReal = [&](double lo, double hi) { return std::uniform_real_distribution<double>(lo, hi)(prng); };
+  for (size_t i = 0; i < num_outliers; ++i) {
+    const double x = RandomReal(-3000.0, -2000.0), y = RandomReal(-4000.0, -3000.0), z = RandomReal(-5000.0, -4000.0);
+    dst[i] = {{x, y, z}};
+  }
+  tv::RansacOptions o;   // RANSACOptions defaults (ransac.h:45-75): min_inlier_ratio 0.1, confidence 0.99, no trial bounds
+  o.max_error = 10;
+  const auto r = tv::RunRansacT(tv::SimilarityPolicy{}, use_lo != 0, o, src, dst, prng);
+  *num_trials = (int64_t)r.num_trials;
+  *num_inliers = (int32_t)r.support.num_inliers;
+  memset(mask, 0, num_samples);
+  for (size_t i = 0; i < r.inlier_mask.size(); ++i) mask[i] = r.inlier_mask[i];
+  const double orig[12] = {2, 0, 0, 100, 0, 2, 0, 10, 0, 0, 2, 10};
+  double d2 = 0;
+  for (int k = 0; k < 12; ++k) d2 += (orig[k] - r.model.m[k]) * (orig[k] - r.model.m[k]);
+  *matrix_diff = std::sqrt(d2);
   return r.success ? 1 : 0;
 }
 

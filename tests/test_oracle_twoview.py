@@ -191,6 +191,20 @@ def test_two_view_calibrated_and_uncalibrated():
     assert res.config == 1 and res.n_inliers == 0
 
 
+@pytest.mark.parametrize("use_lo", [False, True])
+def test_reference_ransac_and_loransac_tests_replayed_literally(use_lo):
+    """optim/ransac_test.cc:89-133 (RANSAC) and optim/loransac_test.cc:57-107 (LORANSAC), TestSimilarityTransform: SetPRNGSeed(0),
+    1000 exact correspondences under SimilarityTransform3(2, identity, (100, 10, 10)), the first 400 destinations replaced by
+    RandomReal outliers drawn from the same PRNG, RANSACOptions{max_error = 10}, SimilarityTransformEstimator<3>.  The oracle runs
+    them through the SAME loop its two-view estimators use (RunRansacT in twoview_oracle.cc); the assertions are the tests' own."""
+    r = orc.reference_similarity_ransac_test(use_lo)
+    assert r["success"] is True                                  # BOOST_CHECK_EQUAL(report.success, true)
+    assert r["num_trials"] > 0                                   # BOOST_CHECK_GT(report.num_trials, 0)
+    assert r["num_inliers"] == 1000 - 400                        # BOOST_CHECK_EQUAL(num_inliers, num_samples - num_outliers)
+    assert not r["mask"][:400].any() and r["mask"][400:].all()   # every outlier rejected, every inlier kept
+    assert abs(r["matrix_diff"]) < 1e-6                          # |orig_tform.Matrix().topLeftCorner<3,4>() - model| < 1e-6
+
+
 def test_loransac_exact_mask_with_gross_outliers():
     # as loransac_test.cc:57-107 in spirit: exact inlier mask under a fixed seed
     rng = np.random.default_rng(4)
