@@ -99,3 +99,23 @@ def test_matches_vs_numpy_bruteforce():
     exp = [[i, m12[i]] for i in range(len(m12)) if m12[i] >= 0 and m21[m12[i]] == i]
     assert m.tolist() == exp
     assert len(exp) > 50
+
+
+def test_feature_utils_tests_replayed_on_the_descriptor_conversion():
+    """feature/utils_test.cc:49-86 (TestL2NormalizeFeatureDescriptors, TestFeatureDescriptorsToUnsignedByte) on the oracle's
+    restatement of feature/utils.cc:47-76 -- the conversion that defines layout T1 (uint8 = min(255, round(512 * d / |d|))):
+    100 rows of Random(100, 128) + 1, every normalised row has unit norm to 1e-6 and every byte equals the test's formula."""
+    rng = np.random.default_rng(0)
+    d = (rng.uniform(-1.0, 1.0, (100, 128)) + 1.0).astype(np.float32)
+    for r in range(100):
+        row = d[r]
+        n = row / np.sqrt((row * row).sum(dtype=np.float32), dtype=np.float32)
+        assert abs(float(np.linalg.norm(n)) - 1.0) < 1e-6
+        expected = np.minimum(255.0, np.floor(512.0 * n.astype(np.float64) + 0.5)).astype(np.uint8)   # std::round on positive values
+        got = orc.l2_normalize_to_u8(row)
+        # the float32 division / product may differ from the float64 recomputation only when 512 * n sits within float
+        # rounding of a half-integer; everywhere else the bytes are the test's formula exactly
+        diff = np.nonzero(got != expected)[0]
+        for j in diff:
+            assert abs(512.0 * float(n[j]) - np.floor(512.0 * float(n[j])) - 0.5) < 1e-4
+        assert len(diff) <= 1
