@@ -619,7 +619,7 @@ def bench_retrieval_sharded(a, coll, local_rank, rank, world, barrier, dist, pai
     n_img, n_kp = a.seq_images, a.seq_kp
     box = [make_vocabulary_device(coll["desc"], a.retrieval_words, n_train=min(1 << 20, n_img * n_kp), seed=7) if rank == 0 else None]
     dist.broadcast_object_list(box, src=0)
-    g = VocabSimilarityGraph(box[0], num_images=a.seq_cand, num_nearest_neighbors=5, device=local_rank)
+    g = VocabSimilarityGraph(box[0], num_images=2 * a.seq_cand, num_nearest_neighbors=5, device=local_rank)
     walls = []
     pairs = None
     for s in range(1 + 2):
@@ -636,7 +636,7 @@ def bench_retrieval_sharded(a, coll, local_rank, rank, world, barrier, dist, pai
         return None
     got = set(map(tuple, pairs.tolist()))
     near = pairs_all[(pairs_all[:, 1].astype(np.int64) - pairs_all[:, 0]) <= max(a.seq_cand // 2, 1)]
-    return {"workload": f"{n_img} images x {n_kp} descriptors, {a.retrieval_words} visual words, num_neighbors 5, max_num_images {a.seq_cand}",
+    return {"workload": f"{n_img} images x {n_kp} descriptors, {a.retrieval_words} visual words, num_neighbors 5, max_num_images {2 * a.seq_cand}",
             "images_per_s": n_img / w, "wall_s_per_step": w, "word_search_s": t[0].item(), "index_build_s": t[1].item(), "query_s": t[2].item(),
             "timing_note": "kernel times = max over ranks of the last step; wall = the whole stage incl. the all-gather and the gather of the pairs",
             "candidate_pairs": len(pairs),
@@ -655,8 +655,9 @@ def bench_retrieval(a, coll, local_rank, cores, pairs_all):
     n_img, n_kp, K = a.seq_images, a.seq_kp, 5
     vocab = make_vocabulary_device(coll["desc"], a.retrieval_words, n_train=min(1 << 20, n_img * n_kp), seed=7)
     vi = VisualIndex(local_rank)
+    n_ret = 2 * a.seq_cand      # VocabSimilaritySearchOptions::num_images = 100 (similarity_graph.h:44): the seq_cand successors + predecessors
     out = {"workload": f"{n_img} images x {n_kp} descriptors, {a.retrieval_words} visual words, num_neighbors {K}, "
-                       f"max_num_images {a.seq_cand} (VocabSimilarityGraph defaults: 50 / 5)"}
+                       f"max_num_images {n_ret} (VocabSimilaritySearchOptions defaults: 100 / 5)"}
     try:
         vi.set_vocabulary(vocab)
         steps = []
@@ -664,7 +665,7 @@ def bench_retrieval(a, coll, local_rank, cores, pairs_all):
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             vi.index_images_device(coll["desc"].data_ptr(), n_img, n_kp, K)
-            ids, sc, cnt = vi.query_all(a.seq_cand)
+            ids, sc, cnt = vi.query_all(n_ret)
             w = time.perf_counter() - t0
             if s >= 1:
                 steps.append((w, vi.last_timing()))
@@ -679,6 +680,7 @@ def bench_retrieval(a, coll, local_rank, cores, pairs_all):
                     "candidate_pairs": int(valid.sum()),
                     "recall_of_overlapping_pairs": float(np.mean([tuple(p) in got for p in near.tolist()])) if len(near) else None,
                     "recall_note": f"share of the sequence's pairs up to {max(a.seq_cand // 2, 1)} images apart (>= half the scene points in common) found among the candidates",
+                    "recall_of_the_pipeline_list": float(np.mean([tuple(p) in got for p in pairs_all[::max(len(pairs_all) // 20000, 1)].tolist()])),
                     "roofline": {"bound": "int8 (dp4a / tensor)", "kernel": "word_knn_kernel<5> (exact nearest words)", "unit": "TOP/s",
                                  "achieved": ops / tm["word_search_s"] / 1e12,
                                  "algorithmic_ops": "2 x 128 per descriptor x word", "share_of_step": tm["word_search_s"] / w}})

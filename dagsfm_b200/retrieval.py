@@ -185,7 +185,8 @@ class VocabSimilarityGraph:
     """VocabSimilarityGraph (similarity_graph.cpp:97-200): index all images, query each, keep (image, other, score * 1e3)
     for image < other -- the candidate pairs and their weights."""
 
-    def __init__(self, vocabulary: Vocabulary, num_images: int = 50, num_nearest_neighbors: int = 5, device: int = 0):
+    def __init__(self, vocabulary: Vocabulary, num_images: int = 100, num_nearest_neighbors: int = 5, device: int = 0):
+        # defaults of VocabSimilaritySearchOptions (similarity_graph.h:42-48): num_images 100, num_nearest_neighbors 5
         self.vocabulary, self.num_images, self.num_nearest_neighbors, self.device = vocabulary, num_images, num_nearest_neighbors, device
         self.image_pairs = np.zeros((0, 2), np.uint32)
         self.scores = np.zeros(0, np.float32)
